@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""bench.py -- DISORT spectral-points/sec on B200 (BASELINE.json metric).
+
+Workload (config C2): shortwave 0.25-4.0 um at 0.005 um, NSTR=16,
+33 layers; the bin set (one bin per wavelength x k-term) is replicated R times
+so that one step is one batched launch over R complete spectra.  Inputs are
+synthetic optical properties of that shape (sbdart_b200/workloads.py).
+
+A step = one pass of the hot path (one batched DISORT solve of every bin).
+  value : bins/s with inputs resident in HBM (device pointers, CUDA events
+          on the solver's stream), max over ranks.
+  e2e   : the same through the host-buffer C-ABI call sbd_disort_batch
+          (pinned host inputs -> H2D -> kernel -> D2H of all fluxes).
+  --impl reference : the CPU restatement (oracle/) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "DISORT spectral-points/sec (NSTR=16, 33-layer MLS)"
+UNIT = "spectral-points/s"
+
+
+def algorithmic_flops(nstr, nlyr, ncut, plank, beam, nt):
+    """SURVEY 8(d) agreed FLOP count per bin (flux path, M=1)."""
+    N, n = nstr, nstr // 2
+    b = 3 * n - 1
+    per_layer = 3 * n * N * N + 29 * n ** 3
+    per_layer = per_layer + beam * (2.0 / 3.0 * N ** 3 + 10 * N * N)
+    per_layer = per_layer + plank * (2.0 / 3.0 * N ** 3 + 9 * N * N)
+    return ncut * (per_layer + 4 * b * b * N + 26 * b * N) + 5 * N * N * nt
+
+
+def workload_ncut(w):
+    """NCUT per bin (disort.f:2557-2605): first layer where the cumulative
+    absorption depth reaches 10, applied only without a thermal source."""
+    ss = np.where(w["ssalb"] == 1.0, 1.0 - 100 * 2.0 ** -52, w["ssalb"])
+    ab = np.cumsum((1.0 - ss) * np.maximum(w["dtauc"], 0.0), axis=1)
+    L = ab.shape[1]
+    before = np.concatenate([np.zeros((ab.shape[0], 1)), ab[:, :-1]], axis=1)
+    ncut = (before < 10.0).sum(axis=1)
+    cut = (ab[:, -1] >= 10.0) & (w["bins"]["plank"] == 0) & (L > 1)
+    return np.where(cut, ncut, L)
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons during the timed region (NVML)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop_evt = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+def build_workload(replicate):
+    from sbdart_b200 import workloads
+    w = workloads.mls_shortwave(nstr=16, nlyr=33, wlinf=0.25, wlsup=4.0, wlinc=0.005)
+    base = w["dtauc"].shape[0]
+    if replicate > 1:
+        for k in ("dtauc", "ssalb", "pmom"):
+            w[k] = np.tile(w[k], (replicate,) + (1,) * (w[k].ndim - 1))
+        w["bins"] = np.tile(w["bins"], replicate)
+    w["base_bins"] = base
+    return w
+
+
+def run_reference(args, rank, world):
+    """CPU arm: the oracle port on the host cores (rank 0 only)."""
+    if rank != 0:
+        return
+    from oracle import oracle
+    w = build_workload(1)
+    cores = os.cpu_count() or 1
+    sample = min(args.ref_bins, w["dtauc"].shape[0] * 8)
+    rep = -(-sample // w["dtauc"].shape[0])
+    idx = np.arange(sample) % w["dtauc"].shape[0]
+    b = w["bins"][idx]
+    kw = dict(nstr=16, fbeam=b["fbeam"], umu0=b["umu0"], albedo=b["albedo"], plank=b["plank"],
+              wvnmlo=b["wvnmlo"], wvnmhi=b["wvnmhi"], btemp=b["btemp"], ttemp=b["ttemp"],
+              temis=b["temis"], fisot=b["fisot"], temper=w["temper"], col=b["col"], nthreads=cores)
+    dt, ss, pm = w["dtauc"][idx], w["ssalb"][idx], w["pmom"][idx]
+    for _ in range(args.warmup):
+        oracle.disort_flux_batch(dt, ss, pm, **kw)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r = oracle.disort_flux_batch(dt, ss, pm, **kw)
+    dtm = (time.perf_counter() - t0) / args.steps
+    val = sample / dtm
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dtm * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": w["name"], "bins_per_step": int(sample),
+                   "note": "CPU restatement of disort.f (oracle/, OpenMP over bins); "
+                           "no Fortran compiler in the image so the reference itself cannot be built"},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{sample} bins of the C2 set per step ({rep} spectra)"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "bad_bins": int((r["status"] != 0).sum()),
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--replicate", type=int, default=64, help="spectra per step per GPU")
+    ap.add_argument("--ref-bins", type=int, default=8192, help="bins per CPU reference step")
+    ap.add_argument("--cpu-sample", type=int, default=16384, help="bins for cpu_baseline")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import sbdart_b200 as sb
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback for the product arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    w = build_workload(args.replicate)
+    B, L = w["dtauc"].shape
+    NT = L + 1
+    nmom = w["pmom"].shape[2] - 1
+    solver = sb.Solver(local_rank)
+    ext = torch.cuda.ExternalStream(solver.stream, device=dev)
+
+    # ---- pinned host copies (e2e arm) and device-resident copies (value arm) ----
+    def pinned(a):
+        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        return t
+
+    h_dt, h_ss, h_pm = pinned(w["dtauc"]), pinned(w["ssalb"]), pinned(w["pmom"])
+    h_bins = torch.from_numpy(w["bins"].view(np.uint8).reshape(B, -1).copy()).pin_memory()
+    h_tp = pinned(w["temper"])
+    h_out = {k: torch.empty((B, NT), dtype=torch.float64).pin_memory()
+             for k in ("rfldir", "rfldn", "flup", "dfdt", "uavg")}
+    h_status = torch.empty(B, dtype=torch.int32).pin_memory()
+
+    d_dt, d_ss, d_pm = h_dt.to(dev), h_ss.to(dev), h_pm.to(dev)
+    d_bins, d_tp = h_bins.to(dev), h_tp.to(dev)
+    d_out = {k: torch.empty((B, NT), dtype=torch.float64, device=dev) for k in h_out}
+    d_status = torch.empty(B, dtype=torch.int32, device=dev)
+    # compact top/bottom spectrum gathered at the end of a step
+    d_spec = torch.empty((B, 6), dtype=torch.float64, device=dev)
+    g_spec = torch.empty((world * B, 6), dtype=torch.float64, device=dev) if world > 1 else None
+    torch.cuda.synchronize()
+
+    dims = sb.SbdDims()
+    dims.nbins, dims.nlyr, dims.nstr, dims.nmom, dims.ncol = B, L, 16, nmom, 1
+    ptrs = dict(dtauc=d_dt.data_ptr(), ssalb=d_ss.data_ptr(), pmom=d_pm.data_ptr(),
+                bins=d_bins.data_ptr(), temper=d_tp.data_ptr(), status=d_status.data_ptr(),
+                **{k: v.data_ptr() for k, v in d_out.items()})
+
+    def step_device():
+        solver.disort_batch_device(dims, ptrs)
+        if world > 1:
+            with torch.cuda.stream(ext):
+                torch.stack([d_out["rfldn"][:, 0], d_out["flup"][:, 0], d_out["rfldir"][:, 0],
+                             d_out["rfldn"][:, -1], d_out["flup"][:, -1], d_out["rfldir"][:, -1]],
+                            dim=1, out=d_spec)
+                dist.all_gather_into_tensor(g_spec, d_spec)
+
+    hp = lambda t: t.data_ptr()  # noqa: E731
+
+    def step_host():
+        rc = sb.lib().sbd_disort_batch(
+            solver._h, dims, hp(h_dt), hp(h_ss), hp(h_pm), hp(h_bins), hp(h_tp), None, None,
+            None, hp(h_out["rfldir"]), hp(h_out["rfldn"]), hp(h_out["flup"]), hp(h_out["dfdt"]),
+            hp(h_out["uavg"]), None, hp(h_status))
+        if rc:
+            raise sb.SbdError(rc, "sbd_disort_batch")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: device-resident inputs, CUDA events on the solver stream ----
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = solver.kernel_launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(ext):
+        e0.record(ext)
+    for _ in range(args.steps):
+        step_device()
+    with torch.cuda.stream(ext):
+        e1.record(ext)
+    barrier()
+    clocks = sampler.stop()
+    launches = solver.kernel_launches - l0
+    ms_dev = e0.elapsed_time(e1) / args.steps
+    bad = int((d_status != 0).sum().item())
+
+    # ---- e2e: host buffers through the C ABI (H2D + kernel + D2H inside) ----
+    for _ in range(2):
+        step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_host()
+    barrier()
+    ms_e2e = (time.perf_counter() - t0) * 1e3 / args.steps
+
+    t_dev = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
+    ms_dev, ms_e2e = float(t_dev[0]), float(t_dev[1])
+
+    if rank == 0:
+        h2d = (w["dtauc"].nbytes + w["ssalb"].nbytes + w["pmom"].nbytes + w["bins"].nbytes +
+               w["temper"].nbytes)
+        d2h = 5 * B * NT * 8 + 4 * B
+        ncut = workload_ncut(w)
+        beam = (w["bins"]["fbeam"] > 0).astype(float)
+        fl = algorithmic_flops(16, L, ncut, w["bins"]["plank"].astype(float), beam, NT).sum()
+        fp64_peak = solver.measure_fp64_peak(5)
+        achieved = fl / (ms_dev * 1e-3) / 1e12
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        alg_bytes = B * (8 * (2 * L + (nmom + 1) * L) + w["bins"].dtype.itemsize + 8 * 5 * NT + 4)
+        traffic = None
+        try:
+            prof = json.load(open(os.path.join(ROOT, "profiles", "ncu_summary.json")))
+            if prof.get("bins_per_launch"):
+                traffic = prof["dram_bytes_per_launch"] * (B / prof["bins_per_launch"])
+        except Exception:
+            pass
+        line = {
+            "metric": METRIC, "value": world * B / (ms_dev * 1e-3), "unit": UNIT,
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": w["name"], "bins_per_gpu_per_step": int(B),
+                       "spectra_per_step": args.replicate, "bins_per_spectrum": int(w["base_bins"]),
+                       "levels_out": NT,
+                       "l2": f"inputs larger than L2: {h2d / 2**20:.0f} MiB read per step",
+                       "parallelism": f"bins sharded over {world} GPU(s), one all-gather of the "
+                                      "top/bottom spectrum per step" if world > 1 else "1 GPU"},
+            "clocks": clocks,
+            "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": UNIT,
+                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": ms_e2e},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak,
+                         "unit": "TFLOP/s", "frac": achieved / fp64_peak if fp64_peak else None,
+                         "traffic": traffic,
+                         "peak_source": "sbd_measure_fp64_peak (live DFMA microbenchmark; "
+                                        "MEASURED_PEAKS.json has no FP64 entry)",
+                         "flops_per_launch": float(fl),
+                         "hbm": {"achieved": alg_bytes / (ms_dev * 1e-3) / 1e9, "peak": hbm_peak,
+                                 "unit": "GB/s",
+                                 "frac": alg_bytes / (ms_dev * 1e-3) / 1e9 / hbm_peak,
+                                 "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}},
+            "bad_bins": bad,
+        }
+        if not args.no_cpu_baseline and world >= 1:
+            from oracle import oracle
+            cores = os.cpu_count() or 1
+            ns = min(args.cpu_sample, B)
+            idx = np.arange(ns)
+            b = w["bins"][idx]
+            t0 = time.perf_counter()
+            oracle.disort_flux_batch(
+                w["dtauc"][idx], w["ssalb"][idx], w["pmom"][idx], nstr=16, fbeam=b["fbeam"],
+                umu0=b["umu0"], albedo=b["albedo"], plank=b["plank"], wvnmlo=b["wvnmlo"],
+                wvnmhi=b["wvnmhi"], btemp=b["btemp"], ttemp=b["ttemp"], temis=b["temis"],
+                fisot=b["fisot"], temper=w["temper"], col=b["col"], nthreads=cores)
+            dtc = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": ns / dtc, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"first {ns} bins of the same step, one pass"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,176 @@
+/*
+ * sbdart_b200.h -- C ABI of the B200 batched discrete-ordinate solver.
+ *
+ * Drop-in boundary for SBDART's hot path: the body of the wavelength loop
+ * (reference drt.f:425-561) calls SUBROUTINE DISORT once per
+ * (wavelength, k-distribution term) "bin" (drt.f:541-546, disort.f:1-6).
+ * This library replaces that call with
+ *   - disort_()            : the gfortran-mangled single-call entry with the
+ *                            reference's own 46-argument list, and
+ *   - sbd_disort_batch*()  : all bins of a run flattened into one launch.
+ * No torch / C++ types cross this boundary: plain pointers and sizes only.
+ * The library has no CPU fallback: every entry fails with SBD_ERR_CUDA when
+ * no CUDA device is usable.
+ */
+#ifndef SBDART_B200_H
+#define SBDART_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SBD_ABI_VERSION 1
+
+/* hard limits mirrored from the reference (params.f:8-15) */
+#define SBD_MAX_NSTR 40
+#define SBD_MAX_NLYR 128
+
+/* return codes of the API calls */
+enum {
+    SBD_SUCCESS = 0,
+    SBD_ERR_CUDA = -100,      /* no device / CUDA runtime failure            */
+    SBD_ERR_ARG = -101,       /* bad dims or NULL pointer                    */
+    SBD_ERR_UNSUPPORTED = -102 /* IBCND=1, BRDF surface, USRTAU w/ radiances  */
+};
+
+/* per-bin status written to status[B]; numbering follows the reference's
+ * errmsg numbers where one exists (disutil.f:278-325)     */
+enum {
+    SBD_BIN_OK = 0,
+    SBD_BIN_ANGLE_CLASH = 1,  /* disort.f:2645-2650 -> NSTR returned negative;
+                                 the host retries with NSTR-2 / NSTR+2 as
+                                 drt.f:536-554 does                           */
+    SBD_BIN_BAD_INPUT = -1,   /* CHEKIN fatal (disort.f:5155)                 */
+    SBD_BIN_EIG_FAIL = -2,    /* eigen-solve failed (disort.f:3254-3261)      */
+    SBD_BIN_SINGULAR = -3     /* zero pivot in the boundary system            */
+};
+
+/* Shapes of one batched call.  All bins of a call share these. */
+typedef struct sbd_dims {
+    int32_t nbins;  /* B : number of (wavelength, k-term[, column]) bins     */
+    int32_t nlyr;   /* L : NLYR  (SBDART passes nz)     */
+    int32_t nstr;   /* N : NSTR, even, 4..SBD_MAX_NSTR                        */
+    int32_t nmom;   /* pmom holds moments 0..nmom per layer, nmom >= nstr
+                       (SBDART passes nstr+2, drt.f:493)                      */
+    int32_t ntau;   /* 0 => USRTAU=.FALSE.: the L+1 layer boundaries
+                       (the only mode SBDART uses, drt.f:175-178);
+                       >0 => USRTAU=.TRUE. with utau[B][ntau] (flux only)     */
+    int32_t numu;   /* 0 => ONLYFL=.TRUE. (fluxes only); >0 => USRANG user
+                       polar angles umu[numu] shared by all bins              */
+    int32_t nphi;   /* number of azimuths phi[nphi] (numu>0 only)             */
+    int32_t ncol;   /* number of temperature profiles temper[ncol][L+1]       */
+} sbd_dims;
+
+/* Per-bin scalar arguments of DISORT (disort.f:1-6). */
+typedef struct sbd_bin {
+    double fbeam;   /* FBEAM  */
+    double umu0;    /* UMU0   */
+    double phi0;    /* PHI0   (degrees)                                       */
+    double fisot;   /* FISOT  */
+    double albedo;  /* ALBEDO (Lambertian)                                    */
+    double btemp;   /* BTEMP  */
+    double ttemp;   /* TTEMP  */
+    double temis;   /* TEMIS  */
+    double wvnmlo;  /* WVNMLO */
+    double wvnmhi;  /* WVNMHI */
+    int32_t plank;  /* PLANK  */
+    int32_t col;    /* row of temper[][] used by this bin                     */
+} sbd_bin;
+
+typedef struct sbd_handle sbd_handle; /* owns a CUDA stream + device scratch */
+
+/* Create / destroy a solver bound to CUDA device `device`. */
+int sbd_create(sbd_handle **out, int device);
+void sbd_destroy(sbd_handle *h);
+
+/*
+ * Batched solve, HOST buffers (the reference-facing call: copies inputs to
+ * the device, launches, copies results back; synchronous on return).
+ *
+ *  dtauc [B][L], ssalb [B][L]     DTAUC, SSALB       (top layer first)
+ *  pmom  [B][L][nmom+1]           PMOM(0:nmom, lc)   (moment index fastest)
+ *  bins  [B]                      scalars
+ *  temper[ncol][L+1]              TEMPER(0:NLYR); may be NULL if no bin has
+ *                                 plank set
+ *  utau  [B][ntau]                only when dims.ntau > 0, else NULL
+ *  umu   [numu], phi [nphi]       only when dims.numu > 0, else NULL
+ * Outputs, NT = ntau ? ntau : L+1; any flux pointer may be NULL:
+ *  rfldir, rfldn, flup, dfdt, uavg : [B][NT]
+ *  uu   [B][nphi][NT][numu]       (numu>0), Fortran UU(iu,lu,j) transposed
+ *  status [B]
+ * The inputs are const: the in-place edits DISORT makes (SSALB=1 -> 1-DITHER
+ * disort.f:486, DTAUC<0 -> 0 disort.f:4944) are applied on the device copy.
+ */
+int sbd_disort_batch(sbd_handle *h, const sbd_dims *dims, const double *dtauc,
+                     const double *ssalb, const double *pmom,
+                     const sbd_bin *bins, const double *temper,
+                     const double *utau, const double *umu, const double *phi,
+                     double *rfldir, double *rfldn, double *flup, double *dfdt,
+                     double *uavg, double *uu, int32_t *status);
+
+/* Same, all pointers are DEVICE pointers; enqueued on the handle's stream
+ * (or on `stream` if non-NULL, a cudaStream_t passed as void*), returns
+ * without synchronising. */
+int sbd_disort_batch_device(sbd_handle *h, const sbd_dims *dims,
+                            const double *dtauc, const double *ssalb,
+                            const double *pmom, const sbd_bin *bins,
+                            const double *temper, const double *utau,
+                            const double *umu, const double *phi,
+                            double *rfldir, double *rfldn, double *flup,
+                            double *dfdt, double *uavg, double *uu,
+                            int32_t *status, void *stream);
+
+/* Block until everything enqueued on the handle's stream has finished. */
+int sbd_synchronize(sbd_handle *h);
+
+/* cudaStream_t of the handle (as void*), for event timing by the caller. */
+void *sbd_stream(sbd_handle *h);
+
+/* Number of kernels of this library launched through `h` so far. */
+int64_t sbd_kernel_launches(const sbd_handle *h);
+
+/* Gauss-Legendre nodes/weights on (0,1) used for NSTR = 2*m streams
+ * (same rule as QGAUSN, disort.f:5984). Host-only helper. */
+int sbd_quadrature(int m, double *mu, double *wt);
+
+/* Diagnostic: sustained FP64 FMA throughput of the device in TFLOP/s (FMA = 2
+ * flops), best of `reps` launches of a register-resident DFMA loop.  Used as
+ * the roofline denominator of the solver kernel in bench.py. */
+int sbd_measure_fp64_peak(sbd_handle *h, int reps, double *tflops);
+
+const char *sbd_status_string(int code);
+int sbd_abi_version(void);
+
+/*
+ * gfortran-compatible replacement for SUBROUTINE DISORT (disort.f:1-6), call
+ * site drt.f:541-546.  Everything by reference, LOGICAL = 4-byte int,
+ * arrays column-major with the leading dimensions the caller passes
+ * (PMOM(0:MAXMOM,MAXCLY), UU(MAXUMU,MAXULV,MAXPHI)), hidden length of
+ * HEADER*127 appended by value.  Reproduces the reference's visible argument
+ * mutations: NSTR -> -NSTR on beam/quadrature angle clash, NTAU/UTAU set to
+ * the layer boundaries, NUMU/UMU set to the quadrature angles for flux runs,
+ * SSALB=1 -> 1-DITHER, DTAUC<0 -> 0, PMOM(0,:) = 1.
+ * Uses a process-wide handle on device 0 created on first use.
+ */
+void disort_(int *nlyr, double *dtauc, double *ssalb, int *corint, int *nmom,
+             double *pmom, double *temper, double *wvnmlo, double *wvnmhi,
+             int *usrtau, int *ntau, double *utau, int *nstr, int *usrang,
+             int *numu, double *umu, int *nphi, double *phi, int *ibcnd,
+             double *fbeam, double *umu0, double *phi0, double *fisot,
+             int *lamber, double *albedo, double *btemp, double *ttemp,
+             double *temis, int *plank, int *onlyfl, double *accur, int *prnt,
+             char *header, int *maxcly, int *maxulv, int *maxumu, int *maxphi,
+             int *maxmom, double *rfldir, double *rfldn, double *flup,
+             double *dfdt, double *uavg, double *uu, double *albmed,
+             double *trnmed, size_t header_len);
+
+/* status of the last disort_() call on this thread (SBD_BIN_* or SBD_ERR_*) */
+int sbd_disort_last_status(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SBDART_B200_H */

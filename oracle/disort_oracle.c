@@ -676,7 +676,23 @@ typedef struct {
 #define AMB(iq, jq) w->amb[(iq) + (size_t)(jq) * n]
 #define APB(iq, jq) w->apb[(iq) + (size_t)(jq) * n]
 
-static double *dalloc(size_t k) { return (double *)calloc(k ? k : 1, sizeof(double)); }
+/* Per-thread bump arena: one (re)allocation per thread instead of ~50
+ * calloc/free pairs per call (those serialise OpenMP threads in mmap). */
+static __thread char *tl_base = NULL;
+static __thread size_t tl_cap = 0, tl_off = 0;
+static __thread int tl_measure = 0;
+
+static void *arena_take(size_t bytes)
+{
+    bytes = (bytes + 63) & ~(size_t)63;
+    if (bytes == 0) bytes = 64;
+    size_t at = tl_off;
+    tl_off += bytes;
+    if (tl_measure) return NULL;
+    return tl_base + at;
+}
+static double *dalloc(size_t k) { return (double *)arena_take(k * sizeof(double)); }
+static int *ialloc(size_t k) { return (int *)arena_take(k * sizeof(int)); }
 
 /* ------------------------------------------------------------------ */
 /* SOLEIG (disort.f:3099-3320); lc is 0-based layer index              */
@@ -1337,7 +1353,9 @@ static void intcor(work_t *w, double dither, double fbeam, int ldp, int nmom,
 {
     const int N = w->N, NT = w->NT, NU = w->NU, ncut = w->ncut,
               lyrcut = w->lyrcut;
-    double *phasa = dalloc(ncut), *phast = dalloc(ncut), *phasm = dalloc(ncut);
+    double *phasa = (double *)calloc(ncut, sizeof(double)),
+           *phast = (double *)calloc(ncut, sizeof(double)),
+           *phasm = (double *)calloc(ncut, sizeof(double));
     const double dtheta = 10.;
     double theta0 = 0.0, thetap = 0.0;
 #define PMOM(k, lc) pmom[(size_t)(lc) * ldp + (k)]
@@ -1408,19 +1426,6 @@ static double ratio(double a, double b)
     return r;
 }
 
-static void free_work(work_t *w)
-{
-    double **p[] = { &w->cmu, &w->cwt, &w->gl, &w->dtaucp, &w->oprim, &w->flyr,
-        &w->taucpr, &w->expbea, &w->tauc, &w->pkag, &w->utau, &w->utaupr,
-        &w->ylm0, &w->ylmc, &w->ylmu, &w->cc, &w->evecc, &w->array, &w->amb,
-        &w->apb, &w->eval, &w->gc, &w->gu, &w->kk, &w->ll, &w->zz, &w->zplk0,
-        &w->zplk1, &w->xr0, &w->xr1, &w->zbeam, &w->z0u, &w->z1u, &w->bdr,
-        &w->bem, &w->rmu, &w->emu, &w->wk, &w->z0, &w->z1, &w->zj, &w->psi0,
-        &w->psi1, &w->cband, &w->b, &w->uum, &w->u0c, &w->phirad };
-    for (size_t i = 0; i < sizeof(p) / sizeof(p[0]); i++) { free(*p[i]); *p[i] = NULL; }
-    free(w->layru); free(w->ipvt);
-}
-
 /* ------------------------------------------------------------------ */
 /* DISORT main (disort.f:472-871)                                      */
 /* ------------------------------------------------------------------ */
@@ -1458,40 +1463,57 @@ int sbdo_disort(const sbdo_input *in, const double *dtauc_in,
 
     work_t W; memset(&W, 0, sizeof W);
     work_t *w = &W;
-    w->N = N; w->n = n; w->L = L; w->NT = NT; w->NU = NU;
-    w->cmu = dalloc(N); w->cwt = dalloc(N);
-    w->gl = dalloc((size_t)L * (N + 1));
-    w->dtaucp = dalloc(L); w->oprim = dalloc(L); w->flyr = dalloc(L);
-    w->taucpr = dalloc(L + 1); w->expbea = dalloc(L + 1); w->tauc = dalloc(L + 1);
-    w->pkag = dalloc(L + 1);
-    w->utau = dalloc(NT); w->utaupr = dalloc(NT);
-    w->layru = (int *)calloc(NT, sizeof(int));
-    w->ylm0 = dalloc(N + 1); w->ylmc = dalloc((size_t)N * (N + 1));
-    w->ylmu = dalloc((size_t)NU * (N + 1));
-    w->cc = dalloc((size_t)N * N); w->evecc = dalloc((size_t)N * N);
-    w->array = dalloc((size_t)N * N);
-    w->amb = dalloc((size_t)n * n); w->apb = dalloc((size_t)n * n); w->eval = dalloc(n);
-    w->gc = dalloc((size_t)L * N * N);
-    w->gu = dalloc((size_t)L * N * NU);
-    w->kk = dalloc((size_t)L * N); w->ll = dalloc((size_t)L * N);
-    w->zz = dalloc((size_t)L * N); w->zplk0 = dalloc((size_t)L * N);
-    w->zplk1 = dalloc((size_t)L * N);
-    w->xr0 = dalloc(L); w->xr1 = dalloc(L);
-    w->zbeam = dalloc((size_t)L * NU); w->z0u = dalloc((size_t)L * NU);
-    w->z1u = dalloc((size_t)L * NU);
-    w->bdr = dalloc((size_t)n * (n + 1)); w->bem = dalloc(n);
-    w->rmu = dalloc((size_t)NU * (n + 1)); w->emu = dalloc(NU);
-    w->wk = dalloc(2 * N + 2); w->z0 = dalloc(N); w->z1 = dalloc(N);
-    w->zj = dalloc(N); w->psi0 = dalloc(N + 1); w->psi1 = dalloc(N + 1);
-    {
-        int ncd = 3 * n - 1, lda = 3 * ncd + 1;
-        w->cband = dalloc((size_t)lda * N * L);
-        w->b = dalloc((size_t)N * L);
-        w->ipvt = (int *)calloc((size_t)N * L + N, sizeof(int));
+    double *dtauc = NULL, *ssalb = NULL, *umu = NULL;
+    /* pass 0 measures the arena, pass 1 hands out zeroed memory */
+    for (int pass = 0; pass < 2; pass++) {
+        tl_measure = (pass == 0);
+        tl_off = 0;
+        w->N = N; w->n = n; w->L = L; w->NT = NT; w->NU = NU;
+        w->cmu = dalloc(N); w->cwt = dalloc(N);
+        w->gl = dalloc((size_t)L * (N + 1));
+        w->dtaucp = dalloc(L); w->oprim = dalloc(L); w->flyr = dalloc(L);
+        w->taucpr = dalloc(L + 1); w->expbea = dalloc(L + 1); w->tauc = dalloc(L + 1);
+        w->pkag = dalloc(L + 1);
+        w->utau = dalloc(NT); w->utaupr = dalloc(NT);
+        w->layru = ialloc(NT);
+        w->ylm0 = dalloc(N + 1); w->ylmc = dalloc((size_t)N * (N + 1));
+        w->ylmu = dalloc((size_t)NU * (N + 1));
+        w->cc = dalloc((size_t)N * N); w->evecc = dalloc((size_t)N * N);
+        w->array = dalloc((size_t)N * N);
+        w->amb = dalloc((size_t)n * n); w->apb = dalloc((size_t)n * n); w->eval = dalloc(n);
+        w->gc = dalloc((size_t)L * N * N);
+        w->gu = dalloc((size_t)L * N * NU);
+        w->kk = dalloc((size_t)L * N); w->ll = dalloc((size_t)L * N);
+        w->zz = dalloc((size_t)L * N); w->zplk0 = dalloc((size_t)L * N);
+        w->zplk1 = dalloc((size_t)L * N);
+        w->xr0 = dalloc(L); w->xr1 = dalloc(L);
+        w->zbeam = dalloc((size_t)L * NU); w->z0u = dalloc((size_t)L * NU);
+        w->z1u = dalloc((size_t)L * NU);
+        w->bdr = dalloc((size_t)n * (n + 1)); w->bem = dalloc(n);
+        w->rmu = dalloc((size_t)NU * (n + 1)); w->emu = dalloc(NU);
+        w->wk = dalloc(2 * N + 2); w->z0 = dalloc(N); w->z1 = dalloc(N);
+        w->zj = dalloc(N); w->psi0 = dalloc(N + 1); w->psi1 = dalloc(N + 1);
+        {
+            int ncd = 3 * n - 1, lda = 3 * ncd + 1;
+            w->cband = dalloc((size_t)lda * N * L);
+            w->b = dalloc((size_t)N * L);
+            w->ipvt = ialloc((size_t)N * L + N);
+        }
+        w->uum = dalloc((size_t)NT * NU); w->u0c = dalloc((size_t)NT * N);
+        w->phirad = dalloc(in->nphi > 0 ? in->nphi : 1);
+        dtauc = dalloc(L); ssalb = dalloc(L); umu = dalloc(NU);
+        if (pass == 0) {
+            if (tl_off > tl_cap) {
+                free(tl_base);
+                tl_cap = tl_off + tl_off / 4;
+                tl_base = (char *)malloc(tl_cap);
+                if (!tl_base) { tl_cap = 0; return SBDO_BAD_INPUT; }
+            }
+        }
     }
-    w->uum = dalloc((size_t)NT * NU); w->u0c = dalloc((size_t)NT * N);
-    w->phirad = dalloc(in->nphi > 0 ? in->nphi : 1);
-    double *dtauc = dalloc(L), *ssalb = dalloc(L), *umu = dalloc(NU);
+    /* the cband region is zeroed by setmtx_solve0 itself; zero the rest */
+    memset(tl_base, 0, (size_t)((char *)w->cband - tl_base));
+    memset(w->b, 0, tl_off - (size_t)((char *)w->b - tl_base));
 
     /* cumulative optical depth, SSALB dither (disort.f:482-489) */
     for (int lc = 0; lc < L; lc++) {
@@ -1692,8 +1714,6 @@ int sbdo_disort(const sbdo_input *in, const double *dtauc_in,
                umu, umu0, pi, rpd, uu);
 done:
     if (warn_out) *warn_out = warn;
-    free(dtauc); free(ssalb); free(umu);
-    free_work(w);
     return status;
 }
 
@@ -1702,6 +1722,9 @@ done:
 /* ------------------------------------------------------------------ */
 #ifdef _OPENMP
 #include <omp.h>
+#endif
+#ifdef __GLIBC__
+#include <malloc.h>
 #endif
 int sbdo_disort_flux_batch(int nbins, int nlyr, int nstr, int nmom,
                            const double *dtauc, const double *ssalb,
@@ -1718,6 +1741,12 @@ int sbdo_disort_flux_batch(int nbins, int nlyr, int nstr, int nmom,
     int nbad = 0;
     const int NT = nlyr + 1;
     (void)nthreads;
+#ifdef __GLIBC__
+    /* keep the per-call work arrays on the heap: mmap/munmap of the band
+       matrix on every call serialises the threads in the kernel */
+    mallopt(M_MMAP_THRESHOLD, 256 << 20);
+    mallopt(M_TRIM_THRESHOLD, 512 << 20);
+#endif
 #ifdef _OPENMP
 #pragma omp parallel for schedule(dynamic, 4) num_threads(nthreads > 0 ? nthreads : 1) reduction(+ : nbad)
 #endif

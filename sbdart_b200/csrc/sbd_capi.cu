@@ -1,0 +1,412 @@
+// C ABI of the B200 batched discrete-ordinate solver (include/sbdart_b200.h).
+// Host side only: argument checks, quadrature / Legendre tables, device
+// buffers, launches.  There is deliberately no CPU compute path here: if no
+// CUDA device is usable every entry returns SBD_ERR_CUDA.
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <map>
+#include <mutex>
+#include <vector>
+
+#include "sbd_internal.h"
+
+using namespace sbd;
+
+namespace {
+
+// Gauss-Legendre rule on (0,1) with m points, nodes ascending (the rule
+// QGAUSN produces, disort.f:5984-6157).  Newton on P_m with the standard
+// cosine first guess; nodes come in +- pairs on (-1,1).
+void gauss01(int m, double *mu, double *wt)
+{
+    const double pi = 3.14159265358979323846;
+    for (int k = 0; k < (m + 1) / 2; k++) {
+        double x = cos(pi * (k + 0.75) / (m + 0.5));   // descending from +1
+        double pp = 1.0;
+        for (int it = 0; it < 100; it++) {
+            double p0 = 1.0, p1 = x;
+            for (int l = 2; l <= m; l++) {
+                double p2 = ((2 * l - 1) * x * p1 - (l - 1) * p0) / l;
+                p0 = p1; p1 = p2;
+            }
+            if (m == 1) { p1 = x; p0 = 1.0; }
+            pp = m * (x * p1 - p0) / (x * x - 1.0);
+            double dx = p1 / pp;
+            x -= dx;
+            if (fabs(dx) < 1e-16) break;
+        }
+        {   // derivative at the converged node
+            double p0 = 1.0, p1 = x;
+            for (int l = 2; l <= m; l++) {
+                double p2 = ((2 * l - 1) * x * p1 - (l - 1) * p0) / l;
+                p0 = p1; p1 = p2;
+            }
+            pp = m * (x * p1 - p0) / (x * x - 1.0);
+        }
+        double w = 2.0 / ((1.0 - x * x) * pp * pp);
+        // x is the k-th largest node on (-1,1); map to (0,1)
+        mu[m - 1 - k] = 0.5 * x + 0.5;
+        wt[m - 1 - k] = 0.5 * w;
+        mu[k] = 0.5 * (-x) + 0.5;
+        wt[k] = 0.5 * w;
+    }
+}
+
+// normalised associated Legendre functions Y_l^m(x), l = 0..lmax, for
+// m = 0..M-1 (the functions LEPOLY builds mode by mode, disort.f:5286-5408):
+//   Y_l^m = sqrt((l-m)!/(l+m)!) P_l^m, Y_m^m = -sqrt((2m-1)/(2m)) sqrt(1-x^2) Y_{m-1}^{m-1}
+// out[(m*(lmax+1) + l)*nx + i]
+void legendre_table(int M, int lmax, int nx, const double *x, double *out)
+{
+    std::vector<double> diag(nx, 1.0);
+    for (int m = 0; m < M; m++) {
+        for (int i = 0; i < nx; i++) {
+            if (m > 0)
+                diag[i] = -sqrt((double)(2 * m - 1)) / sqrt((double)(2 * m)) *
+                          sqrt(1.0 - x[i] * x[i]) * diag[i];
+            double *o = out + (size_t)m * (lmax + 1) * nx;
+            for (int l = 0; l < m && l <= lmax; l++) o[(size_t)l * nx + i] = 0.0;
+            if (m <= lmax) o[(size_t)m * nx + i] = diag[i];
+            if (m + 1 <= lmax)
+                o[(size_t)(m + 1) * nx + i] = sqrt((double)(2 * m + 1)) * x[i] * diag[i];
+            for (int l = m + 2; l <= lmax; l++) {
+                double t1 = sqrt((double)(l - m)) * sqrt((double)(l + m));
+                double t2 = sqrt((double)(l - m - 1)) * sqrt((double)(l + m - 1));
+                o[(size_t)l * nx + i] = ((2 * l - 1) * x[i] * o[(size_t)(l - 1) * nx + i] -
+                                         t2 * o[(size_t)(l - 2) * nx + i]) / t1;
+            }
+        }
+    }
+}
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct Tables {
+    double *quad = nullptr;   // [2n]
+    double *ylmc = nullptr;   // [N][N][n]
+};
+
+}  // namespace
+
+struct sbd_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int sm_count = 0;
+    size_t smem_optin = 0;
+    int64_t launches = 0;
+    std::map<int, Tables> tables;          // per NSTR
+    DevBuf scratch, counter, ylmu, angles;
+    // staging for the host-pointer API
+    DevBuf d_dtauc, d_ssalb, d_pmom, d_bins, d_temper, d_utau, d_out, d_uu, d_status;
+    std::vector<double> h_umu_key;
+};
+
+static int check_dims(const sbd_dims *d)
+{
+    if (!d) return SBD_ERR_ARG;
+    if (d->nbins < 0 || d->nlyr < 1 || d->nlyr > SBD_MAX_NLYR) return SBD_ERR_ARG;
+    if (d->nstr < 4 || d->nstr > SBD_MAX_NSTR || (d->nstr & 1)) return SBD_ERR_ARG;
+    if (d->nmom < d->nstr) return SBD_ERR_ARG;
+    if (d->ntau < 0 || d->numu < 0 || d->nphi < 0 || d->ncol < 0) return SBD_ERR_ARG;
+    if (d->numu > 0 && d->nphi < 1) return SBD_ERR_ARG;
+    return SBD_SUCCESS;
+}
+
+extern "C" int sbd_abi_version(void) { return SBD_ABI_VERSION; }
+
+extern "C" const char *sbd_status_string(int code)
+{
+    switch (code) {
+    case SBD_SUCCESS: return "ok";
+    case SBD_BIN_ANGLE_CLASH: return "beam angle equals a quadrature angle; change NSTR (disort.f:2645)";
+    case SBD_BIN_BAD_INPUT: return "input out of range (CHEKIN, disort.f:4864)";
+    case SBD_BIN_EIG_FAIL: return "eigen-solve failed (ASYMTX, disort.f:3254)";
+    case SBD_BIN_SINGULAR: return "boundary system singular (SOLVE0, disort.f:3609)";
+    case SBD_ERR_CUDA: return "CUDA device unavailable or runtime error";
+    case SBD_ERR_ARG: return "bad argument";
+    case SBD_ERR_UNSUPPORTED: return "option outside the supported hot path";
+    default: return "unknown";
+    }
+}
+
+extern "C" int sbd_quadrature(int m, double *mu, double *wt)
+{
+    if (m < 1 || !mu || !wt) return SBD_ERR_ARG;
+    gauss01(m, mu, wt);
+    return SBD_SUCCESS;
+}
+
+extern "C" int sbd_create(sbd_handle **out, int device)
+{
+    if (!out) return SBD_ERR_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return SBD_ERR_CUDA;
+    if (cudaSetDevice(device) != cudaSuccess) return SBD_ERR_CUDA;
+    sbd_handle *h = new sbd_handle();
+    h->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete h; return SBD_ERR_CUDA; }
+    h->sm_count = prop.multiProcessorCount;
+    h->smem_optin = prop.sharedMemPerBlockOptin;
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return SBD_ERR_CUDA; }
+    if (h->counter.reserve(256) != cudaSuccess) { delete h; return SBD_ERR_CUDA; }
+    *out = h;
+    return SBD_SUCCESS;
+}
+
+extern "C" void sbd_destroy(sbd_handle *h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    for (auto &kv : h->tables) { cudaFree(kv.second.quad); cudaFree(kv.second.ylmc); }
+    DevBuf *bufs[] = { &h->scratch, &h->counter, &h->ylmu, &h->angles, &h->d_dtauc, &h->d_ssalb,
+                       &h->d_pmom, &h->d_bins, &h->d_temper, &h->d_utau, &h->d_out, &h->d_uu,
+                       &h->d_status };
+    for (DevBuf *b : bufs) b->release();
+    cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+extern "C" int sbd_synchronize(sbd_handle *h)
+{
+    if (!h) return SBD_ERR_ARG;
+    return cudaStreamSynchronize(h->stream) == cudaSuccess ? SBD_SUCCESS : SBD_ERR_CUDA;
+}
+
+extern "C" void *sbd_stream(sbd_handle *h) { return h ? (void *)h->stream : nullptr; }
+
+extern "C" int64_t sbd_kernel_launches(const sbd_handle *h) { return h ? h->launches : 0; }
+
+static int get_tables(sbd_handle *h, int N, Tables &t, cudaStream_t st)
+{
+    auto it = h->tables.find(N);
+    if (it != h->tables.end()) { t = it->second; return SBD_SUCCESS; }
+    const int n = N / 2;
+    std::vector<double> quad(2 * n), ylm((size_t)N * N * n);
+    gauss01(n, quad.data(), quad.data() + n);
+    legendre_table(N, N - 1, n, quad.data(), ylm.data());
+    Tables nt;
+    if (cudaMalloc(&nt.quad, quad.size() * 8) != cudaSuccess) return SBD_ERR_CUDA;
+    if (cudaMalloc(&nt.ylmc, ylm.size() * 8) != cudaSuccess) return SBD_ERR_CUDA;
+    cudaMemcpyAsync(nt.quad, quad.data(), quad.size() * 8, cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(nt.ylmc, ylm.data(), ylm.size() * 8, cudaMemcpyHostToDevice, st);
+    if (cudaStreamSynchronize(st) != cudaSuccess) return SBD_ERR_CUDA;
+    h->tables[N] = nt;
+    t = nt;
+    return SBD_SUCCESS;
+}
+
+extern "C" int sbd_disort_batch_device(sbd_handle *h, const sbd_dims *dims, const double *dtauc,
+                                       const double *ssalb, const double *pmom,
+                                       const sbd_bin *bins, const double *temper,
+                                       const double *utau, const double *umu, const double *phi,
+                                       double *rfldir, double *rfldn, double *flup, double *dfdt,
+                                       double *uavg, double *uu, int32_t *status, void *stream)
+{
+    if (!h) return SBD_ERR_ARG;
+    int rc = check_dims(dims);
+    if (rc) return rc;
+    if (!dtauc || !ssalb || !pmom || !bins || !status) return SBD_ERR_ARG;
+    if (dims->ntau > 0 && !utau) return SBD_ERR_ARG;
+    if (dims->numu > 0) return SBD_ERR_UNSUPPORTED;   // radiance path: see sbd_radiance (next)
+    if (dims->nbins == 0) return SBD_SUCCESS;
+    if (cudaSetDevice(h->device) != cudaSuccess) return SBD_ERR_CUDA;
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+
+    const int N = dims->nstr, L = dims->nlyr;
+    const int NT = dims->ntau > 0 ? dims->ntau : L + 1;
+    Tables tb;
+    rc = get_tables(h, N, tb, st);
+    if (rc) return rc;
+
+    size_t smem_limit = h->smem_optin ? h->smem_optin : 48 * 1024;
+    int warps = generic_pick_warps(N, L, NT, smem_limit);
+    if (warps == 0) return SBD_ERR_UNSUPPORTED;
+    if (warps > 4) warps = 4;
+    size_t smem = generic_smem_bytes(N, L, NT, warps);
+    int cta_per_sm = (int)((smem_limit + 1024) / (smem + 1024));
+    if (cta_per_sm < 1) cta_per_sm = 1;
+    if (cta_per_sm * warps > 16) cta_per_sm = 16 / warps > 0 ? 16 / warps : 1;
+    int grid = h->sm_count * cta_per_sm;
+    int need = (dims->nbins + warps - 1) / warps;
+    if (grid > need) grid = need;
+
+    LaunchArgs a;
+    memset(&a, 0, sizeof a);
+    a.d = *dims;
+    a.dtauc = dtauc; a.ssalb = ssalb; a.pmom = pmom; a.bins = bins; a.temper = temper;
+    a.utau = utau; a.umu = umu; a.phi = phi;
+    a.rfldir = rfldir; a.rfldn = rfldn; a.flup = flup; a.dfdt = dfdt; a.uavg = uavg; a.uu = uu;
+    a.status = status;
+    a.quad = tb.quad; a.ylmc = tb.ylmc; a.ylmu = nullptr;
+    a.nslots = grid * warps;
+    a.slot_stride = generic_slot_doubles(N, L, 0);
+    a.nmodes = 1;
+    if (h->scratch.reserve(a.slot_stride * (size_t)a.nslots * 8) != cudaSuccess) return SBD_ERR_CUDA;
+    a.scratch = (double *)h->scratch.p;
+    a.work_counter = (int *)h->counter.p;
+    if (cudaMemsetAsync(a.work_counter, 0, sizeof(int), st) != cudaSuccess) return SBD_ERR_CUDA;
+    if (launch_generic(a, warps, grid, st) != cudaSuccess) return SBD_ERR_CUDA;
+    h->launches += 1;
+    return SBD_SUCCESS;
+}
+
+extern "C" int sbd_disort_batch(sbd_handle *h, const sbd_dims *dims, const double *dtauc,
+                                const double *ssalb, const double *pmom, const sbd_bin *bins,
+                                const double *temper, const double *utau, const double *umu,
+                                const double *phi, double *rfldir, double *rfldn, double *flup,
+                                double *dfdt, double *uavg, double *uu, int32_t *status)
+{
+    if (!h) return SBD_ERR_ARG;
+    int rc = check_dims(dims);
+    if (rc) return rc;
+    if (!dtauc || !ssalb || !pmom || !bins || !status) return SBD_ERR_ARG;
+    if (dims->numu > 0) return SBD_ERR_UNSUPPORTED;
+    if (dims->nbins == 0) return SBD_SUCCESS;
+    if (cudaSetDevice(h->device) != cudaSuccess) return SBD_ERR_CUDA;
+    cudaStream_t st = h->stream;
+    const size_t B = dims->nbins, L = dims->nlyr, ldp = dims->nmom + 1;
+    const size_t NT = dims->ntau > 0 ? dims->ntau : L + 1;
+    bool any_plank = false;
+    for (size_t b = 0; b < B; b++) {
+        if (bins[b].plank) {
+            any_plank = true;
+            if (bins[b].col < 0 || bins[b].col >= dims->ncol) return SBD_ERR_ARG;
+        }
+    }
+    if (any_plank && !temper) return SBD_ERR_ARG;
+
+#define CK(x) do { if ((x) != cudaSuccess) return SBD_ERR_CUDA; } while (0)
+    CK(h->d_dtauc.reserve(B * L * 8));
+    CK(h->d_ssalb.reserve(B * L * 8));
+    CK(h->d_pmom.reserve(B * L * ldp * 8));
+    CK(h->d_bins.reserve(B * sizeof(sbd_bin)));
+    CK(h->d_out.reserve(5 * B * NT * 8));
+    CK(h->d_status.reserve(B * 4));
+    CK(cudaMemcpyAsync(h->d_dtauc.p, dtauc, B * L * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->d_ssalb.p, ssalb, B * L * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->d_pmom.p, pmom, B * L * ldp * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(h->d_bins.p, bins, B * sizeof(sbd_bin), cudaMemcpyHostToDevice, st));
+    const double *d_temper = nullptr, *d_utau = nullptr;
+    if (temper && dims->ncol > 0) {
+        CK(h->d_temper.reserve((size_t)dims->ncol * (L + 1) * 8));
+        CK(cudaMemcpyAsync(h->d_temper.p, temper, (size_t)dims->ncol * (L + 1) * 8,
+                           cudaMemcpyHostToDevice, st));
+        d_temper = (const double *)h->d_temper.p;
+    }
+    if (dims->ntau > 0) {
+        if (!utau) return SBD_ERR_ARG;
+        CK(h->d_utau.reserve(B * NT * 8));
+        CK(cudaMemcpyAsync(h->d_utau.p, utau, B * NT * 8, cudaMemcpyHostToDevice, st));
+        d_utau = (const double *)h->d_utau.p;
+    }
+    double *o = (double *)h->d_out.p;
+    const size_t per = B * NT;
+    rc = sbd_disort_batch_device(h, dims, (const double *)h->d_dtauc.p, (const double *)h->d_ssalb.p,
+                                 (const double *)h->d_pmom.p, (const sbd_bin *)h->d_bins.p, d_temper,
+                                 d_utau, nullptr, nullptr, o, o + per, o + 2 * per, o + 3 * per,
+                                 o + 4 * per, nullptr, (int32_t *)h->d_status.p, st);
+    if (rc) return rc;
+    double *dst[5] = { rfldir, rfldn, flup, dfdt, uavg };
+    for (int k = 0; k < 5; k++)
+        if (dst[k]) CK(cudaMemcpyAsync(dst[k], o + k * per, per * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(status, h->d_status.p, B * 4, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+#undef CK
+    (void)uu; (void)umu; (void)phi;
+    return SBD_SUCCESS;
+}
+
+// ---------------------------------------------------------------------------
+// gfortran-compatible single-call entry (reference call site drt.f:541-546)
+// ---------------------------------------------------------------------------
+static thread_local int g_last_status = 0;
+static sbd_handle *g_handle = nullptr;
+static std::mutex g_mutex;
+
+extern "C" int sbd_disort_last_status(void) { return g_last_status; }
+
+extern "C" void disort_(int *nlyr, double *dtauc, double *ssalb, int *corint, int *nmom,
+                        double *pmom, double *temper, double *wvnmlo, double *wvnmhi, int *usrtau,
+                        int *ntau, double *utau, int *nstr, int *usrang, int *numu, double *umu,
+                        int *nphi, double *phi, int *ibcnd, double *fbeam, double *umu0,
+                        double *phi0, double *fisot, int *lamber, double *albedo, double *btemp,
+                        double *ttemp, double *temis, int *plank, int *onlyfl, double *accur,
+                        int *prnt, char *header, int *maxcly, int *maxulv, int *maxumu,
+                        int *maxphi, int *maxmom, double *rfldir, double *rfldn, double *flup,
+                        double *dfdt, double *uavg, double *uu, double *albmed, double *trnmed,
+                        size_t header_len)
+{
+    (void)corint; (void)accur; (void)prnt; (void)header; (void)header_len; (void)maxphi;
+    (void)albmed; (void)trnmed; (void)uu; (void)nphi; (void)phi; (void)maxcly;
+    std::lock_guard<std::mutex> lock(g_mutex);
+    if (!g_handle && sbd_create(&g_handle, 0) != SBD_SUCCESS) {
+        fprintf(stderr, "sbdart_b200: disort_: no usable CUDA device\n");
+        g_last_status = SBD_ERR_CUDA;
+        return;
+    }
+    const int L = *nlyr, N = *nstr;
+    if (*ibcnd != 0 || !*lamber || !*onlyfl) {   // radiances arrive with the radiance kernel
+        g_last_status = SBD_ERR_UNSUPPORTED;
+        return;
+    }
+    sbd_dims d;
+    memset(&d, 0, sizeof d);
+    d.nbins = 1; d.nlyr = L; d.nstr = N; d.nmom = *nmom; d.ncol = 1;
+    d.ntau = *usrtau ? *ntau : 0;
+    const int ldp = *maxmom + 1;
+    std::vector<double> pm((size_t)L * (*nmom + 1));
+    for (int lc = 0; lc < L; lc++) {
+        pmom[(size_t)lc * ldp] = 1.0;                         // disort.f:2555
+        for (int k = 0; k <= *nmom; k++) pm[(size_t)lc * (*nmom + 1) + k] = pmom[(size_t)lc * ldp + k];
+    }
+    sbd_bin b;
+    memset(&b, 0, sizeof b);
+    b.fbeam = *fbeam; b.umu0 = *umu0; b.phi0 = *phi0; b.fisot = *fisot; b.albedo = *albedo;
+    b.btemp = *btemp; b.ttemp = *ttemp; b.temis = *temis; b.wvnmlo = *wvnmlo; b.wvnmhi = *wvnmhi;
+    b.plank = *plank ? 1 : 0; b.col = 0;
+    const int NT = *usrtau ? *ntau : L + 1;
+    if (NT > *maxulv) { g_last_status = SBD_ERR_ARG; return; }
+    int32_t st = 0;
+    int rc = sbd_disort_batch(g_handle, &d, dtauc, ssalb, pm.data(), &b, temper,
+                              *usrtau ? utau : nullptr, nullptr, nullptr, rfldir, rfldn, flup,
+                              dfdt, uavg, nullptr, &st);
+    g_last_status = rc ? rc : st;
+    if (rc) return;
+    // visible argument mutations of the reference
+    double tc = 0.0;
+    if (!*usrtau) { *ntau = L + 1; utau[0] = 0.0; }
+    for (int lc = 0; lc < L; lc++) {
+        if (ssalb[lc] == 1.0) ssalb[lc] = 1.0 - kDither;       // disort.f:486
+        tc += dtauc[lc];
+        if (!*usrtau) utau[lc + 1] = tc;                       // disort.f:2534-2543
+        if (dtauc[lc] < 0.0) dtauc[lc] = 0.0;                  // disort.f:4944
+    }
+    if (st == SBD_BIN_ANGLE_CLASH) { *nstr = -abs(N); return; } // disort.f:2648
+    if (!*usrang || (*onlyfl && *maxumu >= N)) {               // disort.f:2655-2669
+        std::vector<double> mu(N / 2), wt(N / 2);
+        gauss01(N / 2, mu.data(), wt.data());
+        *numu = N;
+        for (int iu = 0; iu < N / 2; iu++) umu[iu] = -mu[N / 2 - 1 - iu];
+        for (int iu = N / 2; iu < N; iu++) umu[iu] = mu[iu - N / 2];
+    }
+}

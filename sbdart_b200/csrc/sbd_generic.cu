@@ -1,0 +1,906 @@
+// Generic warp-per-bin discrete-ordinate kernel (any even NSTR <= 40).
+//
+// One warp owns one spectral bin and runs the whole solve with its working
+// set in shared memory; the per-layer factors needed by the upward sweep are
+// spilled to an L2-resident scratch slot owned by the warp.
+//
+// The mathematics is the DISORT v2 solution (reference disort.f:472-871;
+// SURVEY appendix C) but none of the reference's algorithms are kept where a
+// GPU-friendlier one gives the same numbers:
+//   * SOLEIG/ASYMTX (disort.f:3099, :873): the reduced n x n eigenproblem
+//     (alpha+beta)(alpha-beta) e = k^2 e is symmetrised with
+//     D = diag(sqrt(w_i mu_i)); a Cholesky factor of the odd-parity operator
+//     turns it into a symmetric positive semidefinite problem solved by
+//     parallel-order cyclic Jacobi (Stamnes, Tsay, Nakajima 1988).
+//   * UPBEAM (disort.f:4130): the N x N LU is replaced by the spectral
+//     solution of the same linear system in the eigenbasis already computed.
+//   * UPISOT (disort.f:4247): (I-C) 1 = (1-w') 1 holds exactly for the
+//     quadrature, so Z1 = XR1 and Z0 needs two triangular solves with the
+//     Cholesky factor.
+//   * SETMTX/SOLVE0 + SGBCO/SGBSL (disort.f:2702, :3322): the block
+//     bidiagonal boundary system is eliminated layer by layer with partial
+//     pivoting inside a (n+N) x (2N+1) window; only N pivot rows per layer
+//     are kept for the back substitution.
+//   * FLUXES (disort.f:1780): evaluated layer by layer during the back
+//     substitution, exponentials hoisted out of the double sum.
+#include <math.h>
+#include <stdio.h>
+
+#include "sbd_internal.h"
+
+namespace sbd {
+
+#define FULLMASK 0xffffffffu
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULLMASK, v, o);
+    return v;
+}
+
+// ---- PLKAVG (disort.f:5410-5671), same three regimes --------------------
+__device__ double plkf(double x) { return x * x * x / (exp(x) - 1.0); }
+
+__device__ double plkavg_dev(double wnumlo, double wnumhi, double t)
+{
+    const double a1 = 1. / 3., a2 = -1. / 8., a3 = 1. / 60., a4 = -1. / 5040.,
+                 a5 = 1. / 272160., a6 = -1. / 13305600.;
+    const double c2 = (double)1.438786f, sigma = (double)5.67032E-8f;
+    const double vcp[7] = { 10.25, (double)5.7f, (double)3.9f, (double)2.9f,
+                            (double)2.3f, (double)1.9f, 0.0 };
+    const double pi = kPiRef;
+    const double vmax = 709.782712893384;   // log(DBL_MAX)
+    const double epsil = 2.220446049250313e-16;
+    const double sigdpi = sigma / pi;
+    const double conc = 15. / (pi * pi * pi * pi);
+    if (t < 1.e-4) return 0.0;
+    double v[2] = { c2 * wnumlo / t, c2 * wnumhi / t };
+    if (v[0] > epsil && v[1] < vmax && (wnumhi - wnumlo) / wnumhi < 1.e-2) {
+        double hh = v[1] - v[0], oldval = 0.0, val = 0.0;
+        double val0 = plkf(v[0]) + plkf(v[1]);
+        for (int n = 1; n <= 10; n++) {
+            double del = hh / (2 * n);
+            val = val0;
+            for (int k = 1; k <= 2 * n - 1; k++)
+                val += 2 * (1 + (k & 1)) * plkf(v[0] + k * del);
+            val = del / 3. * val;
+            if (fabs((val - oldval) / val) <= 1.e-6) break;
+            oldval = val;
+        }
+        return sigdpi * t * t * t * t * conc * val;
+    }
+    double d[2] = { 0, 0 }, p[2] = { 0, 0 };
+    int smallv = 0;
+    for (int i = 0; i < 2; i++) {
+        if (v[i] < 1.5) {
+            smallv++;
+            double vsq = v[i] * v[i];
+            p[i] = conc * vsq * v[i] *
+                   (a1 + v[i] * (a2 + v[i] * (a3 + vsq * (a4 + vsq * (a5 + vsq * a6)))));
+        } else {
+            int mmax = 0;
+            do { mmax++; } while (v[i] < vcp[mmax - 1]);
+            double ex = exp(-v[i]), exm = 1.0, s = 0.0;
+            for (int m = 1; m <= mmax; m++) {
+                double mv = m * v[i];
+                exm = ex * exm;
+                s += exm * (6. + mv * (6. + mv * (3. + mv))) / ((double)m * m * m * m);
+            }
+            d[i] = conc * s;
+        }
+    }
+    double r;
+    if (smallv == 2) r = p[1] - p[0];
+    else if (smallv == 1) r = 1. - p[0] - d[1];
+    else r = d[0] - d[1];
+    return sigdpi * t * t * t * t * r;
+}
+
+// ---- shared-memory carve-up ----------------------------------------------
+struct CtaShared {          // same for every warp of the CTA
+    double *mu, *wt, *sq, *dinv, *ylm;   // [n] x4, [N*n]
+};
+
+struct WarpShared {
+    double *gl, *y0;                 // [N]
+    double *Pe, *Lo, *T, *V, *X, *P; // [n*n] each
+    double *kk[2], *ek[2], *Gp[2], *Gm[2], *zz[2], *zp0[2];
+    double *W;                       // [(n+N)*(2N+1)]
+    double *xn, *xc;                 // [N]
+    double *v1, *v2, *v3, *v4;       // [N] scratch vectors
+    double *taucpr, *tauc, *pk;      // [L+1]
+    int *layru;                      // [NT]
+    double *cs;                      // Jacobi rotations [n+2]
+    int *pq;                         // [n+2]
+};
+
+__host__ __device__ inline size_t cta_shared_doubles(int N)
+{
+    int n = N / 2;
+    return 4 * n + (size_t)N * n;
+}
+
+__host__ __device__ inline size_t warp_shared_doubles(int N, int L, int NT)
+{
+    int n = N / 2;
+    size_t o = 2 * N + 6 * (size_t)n * n + 2 * (2 * n + 2 * (size_t)n * n + 2 * N) +
+               (size_t)(n + N) * (2 * N + 1) + 2 * N + 4 * N + 3 * (size_t)(L + 1) +
+               (n + 2);
+    size_t ints = (size_t)NT + (n + 2);
+    return o + (ints + 1) / 2 + 2;
+}
+
+size_t generic_smem_bytes(int N, int L, int NT, int warps)
+{
+    return 8 * (cta_shared_doubles(N) + warps * warp_shared_doubles(N, L, NT > 8 ? NT : 8));
+}
+
+size_t generic_slot_doubles(int N, int L, int NU)
+{
+    LayerLayout ll(N, NU);
+    return (size_t)ll.stride * L + (size_t)N * L;
+}
+
+int generic_pick_warps(int N, int L, int NT, size_t smem_limit)
+{
+    int w = 8;
+    while (w > 1 && generic_smem_bytes(N, L, NT, w) > smem_limit) w--;
+    if (generic_smem_bytes(N, L, NT, w) > smem_limit) return 0;
+    return w;
+}
+
+__device__ void carve(double *base, int N, int L, int NT, WarpShared &w)
+{
+    int n = N / 2;
+    double *p = base;
+    w.gl = p; p += N;
+    w.y0 = p; p += N;
+    w.Pe = p; p += n * n;
+    w.Lo = p; p += n * n;
+    w.T = p; p += n * n;
+    w.V = p; p += n * n;
+    w.X = p; p += n * n;
+    w.P = p; p += n * n;
+    for (int s = 0; s < 2; s++) {
+        w.kk[s] = p; p += n;
+        w.ek[s] = p; p += n;
+        w.Gp[s] = p; p += n * n;
+        w.Gm[s] = p; p += n * n;
+        w.zz[s] = p; p += N;
+        w.zp0[s] = p; p += N;
+    }
+    w.W = p; p += (n + N) * (2 * N + 1);
+    w.xn = p; p += N;
+    w.xc = p; p += N;
+    w.v1 = p; p += N;
+    w.v2 = p; p += N;
+    w.v3 = p; p += N;
+    w.v4 = p; p += N;
+    w.taucpr = p; p += L + 1;
+    w.tauc = p; p += L + 1;
+    w.pk = p; p += L + 1;
+    w.cs = p; p += n + 2;
+    w.layru = (int *)p;
+    w.pq = w.layru + NT;
+}
+
+// per-bin scalars held in registers by every lane
+struct BinCtx {
+    int N, n, L, NT, ncut, lyrcut, plank, mazim;
+    double fbeam, umu0, albedo, fisot, tplank, bplank, delm0;
+    const double *dtauc, *ssalb, *pmom;
+    int ldp;
+};
+
+// ---------------------------------------------------------------------------
+// Per-layer solution for azimuth mode m: eigenvalues k_j, eigenvector blocks
+// G+ / G-, beam and thermal particular solutions (reference SOLEIG, UPBEAM,
+// UPISOT).  Results go to buffer set `s` in shared memory.
+// returns 0 or SBD_BIN_EIG_FAIL (uniform across the warp)
+// ---------------------------------------------------------------------------
+__device__ int solve_layer(const BinCtx &c, const CtaShared &cs, WarpShared &w,
+                           int lc, int s, double &xr0, double &xr1, int lane)
+{
+    const int N = c.N, n = c.n, m = c.mazim;
+    double ss = c.ssalb[lc];
+    if (ss == 1.0) ss = 1.0 - kDither;                 // disort.f:486
+    double dt = c.dtauc[lc];
+    if (dt < 0.0) dt = 0.0;                            // disort.f:4944
+    const double f = c.pmom[(size_t)lc * c.ldp + N];   // delta-M, disort.f:2577
+    const double oprim = ss * (1. - f) / (1. - f * ss);
+    const double dtaucp = (1. - f * ss) * dt;
+
+    for (int l = lane; l < N; l += 32) {
+        double pm = (l == 0) ? 1.0 : c.pmom[(size_t)lc * c.ldp + l];
+        w.gl[l] = (2 * l + 1) * oprim * (pm - f) / (1. - f);   // disort.f:2583
+    }
+    __syncwarp();
+
+    // symmetrised even / odd parity operators
+    //   Pe~ = M^-1/2 (I - 2 W^1/2 Se W^1/2) M^-1/2 , Po~ likewise with So
+    for (int e = lane; e < n * n; e += 32) {
+        int i = e / n, j = e - i * n;
+        double se = 0.0, so = 0.0;
+        for (int l = m; l < N; l++) {
+            double t = w.gl[l] * cs.ylm[l * n + i] * cs.ylm[l * n + j];
+            if ((l - m) & 1) so += t; else se += t;
+        }
+        double dg = (i == j) ? 1.0 / cs.mu[i] : 0.0;
+        double sc = cs.sq[i] * cs.sq[j];
+        w.Pe[e] = dg - sc * se;
+        w.Lo[e] = dg - sc * so;
+    }
+    __syncwarp();
+
+    // Cholesky Po~ = L L^T (lower triangle of Lo, in place)
+    int bad = 0;
+    for (int j = 0; j < n; j++) {
+        double d = w.Lo[j * n + j];
+        if (!(d > 0.0)) { bad = 1; break; }
+        d = sqrt(d);
+        __syncwarp();
+        for (int i = j + lane; i < n; i += 32) w.Lo[i * n + j] = (i == j) ? d : w.Lo[i * n + j] / d;
+        __syncwarp();
+        int rem = n - j - 1;
+        for (int e = lane; e < rem * rem; e += 32) {
+            int a = e / rem, b = e - a * rem;
+            if (b <= a) {
+                int i = j + 1 + a, k = j + 1 + b;
+                w.Lo[i * n + k] -= w.Lo[i * n + j] * w.Lo[k * n + j];
+            }
+        }
+        __syncwarp();
+    }
+    if (bad) return SBD_BIN_EIG_FAIL;
+
+    // X = Pe~ L ;  T = L^T X  (symmetric positive semidefinite, eigenvalues k^2)
+    for (int e = lane; e < n * n; e += 32) {
+        int i = e / n, j = e - i * n;
+        double a = 0.0;
+        for (int k = j; k < n; k++) a += w.Pe[i * n + k] * w.Lo[k * n + j];
+        w.X[e] = a;
+    }
+    __syncwarp();
+    for (int e = lane; e < n * n; e += 32) {
+        int i = e / n, j = e - i * n;
+        double a = 0.0;
+        for (int k = i; k < n; k++) a += w.Lo[k * n + i] * w.X[k * n + j];
+        w.P[e] = a;
+    }
+    __syncwarp();
+    for (int e = lane; e < n * n; e += 32) {
+        int i = e / n, j = e - i * n;
+        w.T[e] = 0.5 * (w.P[i * n + j] + w.P[j * n + i]);
+        w.V[e] = (i == j) ? 1.0 : 0.0;
+    }
+    __syncwarp();
+
+    // parallel-order cyclic Jacobi on T, eigenvectors accumulated in V
+    {
+        const int mm = (n & 1) ? n + 1 : n;    // players in the tournament
+        const int np = mm / 2;
+        double tr = 0.0;
+        for (int i = lane; i < n; i += 32) tr += fabs(w.T[i * n + i]);
+        const double floor_abs = 1.0e-19 * warp_sum(tr);
+        int sweep = 0;
+        for (; sweep < 60; sweep++) {
+            int nrot = 0;
+            for (int r = 0; r < mm - 1; r++) {
+                int did = 0;
+                if (lane < np) {
+                    int p, q;
+                    if (lane == 0) { p = r; q = mm - 1; }
+                    else { p = (r + lane) % (mm - 1); q = (r - lane + (mm - 1)) % (mm - 1); }
+                    if (p > q) { int t = p; p = q; q = t; }
+                    double cc = 1.0, sn = 0.0;
+                    if (q < n) {
+                        double apq = w.T[p * n + q], app = w.T[p * n + p], aqq = w.T[q * n + q];
+                        if (fabs(apq) > floor_abs &&
+                            fabs(apq) > 1.1e-16 * sqrt(fabs(app) * fabs(aqq))) {
+                            double th = (aqq - app) / (2.0 * apq);
+                            double t = 1.0 / (fabs(th) + sqrt(th * th + 1.0));
+                            if (th < 0.0) t = -t;
+                            cc = 1.0 / sqrt(t * t + 1.0);
+                            sn = t * cc;
+                            did = 1;
+                        }
+                    } else { q = p; }
+                    w.cs[2 * lane] = cc; w.cs[2 * lane + 1] = sn;
+                    w.pq[2 * lane] = p; w.pq[2 * lane + 1] = q;
+                }
+                nrot += __popc(__ballot_sync(FULLMASK, did));
+                __syncwarp();
+                // column rotations of T and V
+                for (int e = lane; e < np * n; e += 32) {
+                    int k = e / n, i = e - k * n;
+                    int p = w.pq[2 * k], q = w.pq[2 * k + 1];
+                    if (p != q) {
+                        double cc = w.cs[2 * k], sn = w.cs[2 * k + 1];
+                        double a = w.T[i * n + p], b = w.T[i * n + q];
+                        w.T[i * n + p] = cc * a - sn * b;
+                        w.T[i * n + q] = sn * a + cc * b;
+                        a = w.V[i * n + p]; b = w.V[i * n + q];
+                        w.V[i * n + p] = cc * a - sn * b;
+                        w.V[i * n + q] = sn * a + cc * b;
+                    }
+                }
+                __syncwarp();
+                // row rotations of T
+                for (int e = lane; e < np * n; e += 32) {
+                    int k = e / n, j = e - k * n;
+                    int p = w.pq[2 * k], q = w.pq[2 * k + 1];
+                    if (p != q) {
+                        double cc = w.cs[2 * k], sn = w.cs[2 * k + 1];
+                        double a = w.T[p * n + j], b = w.T[q * n + j];
+                        w.T[p * n + j] = cc * a - sn * b;
+                        w.T[q * n + j] = sn * a + cc * b;
+                    }
+                }
+                __syncwarp();
+            }
+            if (nrot == 0) break;
+        }
+        if (sweep >= 60) return SBD_BIN_EIG_FAIL;
+    }
+
+    // k_j = sqrt(|lambda_j|)  (disort.f:3264-3269)
+    for (int j = lane; j < n; j += 32) {
+        double k = sqrt(fabs(w.T[j * n + j]));
+        w.kk[s][j] = k;
+        w.ek[s][j] = exp(-k * dtaucp);
+    }
+    // Q = L^-T V (into X), P = L V
+    for (int j = lane; j < n; j += 32) {
+        for (int i = n - 1; i >= 0; i--) {
+            double a = w.V[i * n + j];
+            for (int k = i + 1; k < n; k++) a -= w.Lo[k * n + i] * w.X[k * n + j];
+            w.X[i * n + j] = a / w.Lo[i * n + i];
+        }
+    }
+    for (int e = lane; e < n * n; e += 32) {
+        int i = e / n, j = e - i * n;
+        double a = 0.0;
+        for (int k = 0; k <= i; k++) a += w.Lo[i * n + k] * w.V[k * n + j];
+        w.P[e] = a;
+    }
+    __syncwarp();
+    // G+ - G- = e = D^-1 Q ; G+ + G- = (alpha-beta) e / k = -D^-1 P / k
+    for (int e = lane; e < n * n; e += 32) {
+        int i = e / n, j = e - i * n;
+        double gd = cs.dinv[i] * w.X[e];
+        double gs = -cs.dinv[i] * w.P[e] / w.kk[s][j];
+        w.Gp[s][e] = 0.5 * (gs + gd);
+        w.Gm[s][e] = 0.5 * (gs - gd);
+    }
+
+    // ---- beam particular solution (reference UPBEAM) ----------------------
+    if (c.fbeam > 0.0) {
+        const double fac = (2. - c.delm0) * c.fbeam / (4. * kPiRef);
+        const double rmu0 = 1.0 / c.umu0;
+        // b^_s, b^_d: even / odd parity parts of the source, scaled by sq
+        for (int i = lane; i < n; i += 32) {
+            double be = 0.0, bo = 0.0;
+            for (int l = m; l < N; l++) {
+                double t = w.gl[l] * cs.ylm[l * n + i] * w.y0[l];
+                if ((l - m) & 1) bo += t; else be += t;
+            }
+            w.v1[i] = 2.0 * fac * cs.sq[i] * be;   // b^_s
+            w.v2[i] = 2.0 * fac * cs.sq[i] * bo;   // b^_d
+        }
+        __syncwarp();
+        // r = b^_s / mu0 - Pe~ b^_d
+        for (int i = lane; i < n; i += 32) {
+            double a = w.v1[i] * rmu0;
+            for (int k = 0; k < n; k++) a -= w.Pe[i * n + k] * w.v2[k];
+            w.v3[i] = a;
+        }
+        __syncwarp();
+        // c = V^T L^T r, scaled by 1/(1/mu0^2 - lambda)
+        for (int i = lane; i < n; i += 32) {
+            double a = 0.0;
+            for (int k = i; k < n; k++) a += w.Lo[k * n + i] * w.v3[k];
+            w.v4[i] = a;
+        }
+        __syncwarp();
+        for (int j = lane; j < n; j += 32) {
+            double a = 0.0;
+            for (int k = 0; k < n; k++) a += w.V[k * n + j] * w.v4[k];
+            double den = rmu0 * rmu0 - w.T[j * n + j];
+            w.v3[j] = a / den;
+        }
+        __syncwarp();
+        // y = V c
+        for (int i = lane; i < n; i += 32) {
+            double a = 0.0;
+            for (int k = 0; k < n; k++) a += w.V[i * n + k] * w.v3[k];
+            w.v4[i] = a;
+        }
+        __syncwarp();
+        // d^ = L^-T y (one lane, n is small), s^ = mu0 (b^_d - L y)
+        if (lane == 0) {
+            for (int i = n - 1; i >= 0; i--) {
+                double a = w.v4[i];
+                for (int k = i + 1; k < n; k++) a -= w.Lo[k * n + i] * w.v3[k];
+                w.v3[i] = a / w.Lo[i * n + i];
+            }
+        }
+        __syncwarp();
+        for (int i = lane; i < n; i += 32) {
+            double a = 0.0;
+            for (int k = 0; k <= i; k++) a += w.Lo[i * n + k] * w.v4[k];
+            double sh = c.umu0 * (w.v2[i] - a);
+            double dh = w.v3[i];
+            double sv = cs.dinv[i] * sh, dv = cs.dinv[i] * dh;
+            w.zz[s][n + i] = 0.5 * (sv + dv);       // +mu_i
+            w.zz[s][n - 1 - i] = 0.5 * (sv - dv);   // -mu_i
+        }
+    } else {
+        for (int i = lane; i < N; i += 32) w.zz[s][i] = 0.0;
+    }
+
+    // ---- thermal particular solution (reference UPISOT) -------------------
+    xr0 = 0.0; xr1 = 0.0;
+    if (c.plank && m == 0) {
+        if (dtaucp > 0.0) xr1 = (w.pk[lc + 1] - w.pk[lc]) / dtaucp;   // disort.f:661-666
+        xr0 = w.pk[lc] - xr1 * w.taucpr[lc];
+        // q = D^-1 L^-T L^-1 D 1 ;  Z0(+-mu_i) = xr0 +- xr1 q_i ; Z1 = xr1
+        __syncwarp();
+        if (lane == 0) {
+            for (int i = 0; i < n; i++) {
+                double a = 1.0 / cs.dinv[i];
+                for (int k = 0; k < i; k++) a -= w.Lo[i * n + k] * w.v1[k];
+                w.v1[i] = a / w.Lo[i * n + i];
+            }
+            for (int i = n - 1; i >= 0; i--) {
+                double a = w.v1[i];
+                for (int k = i + 1; k < n; k++) a -= w.Lo[k * n + i] * w.v2[k];
+                w.v2[i] = a / w.Lo[i * n + i];
+            }
+        }
+        __syncwarp();
+        for (int i = lane; i < n; i += 32) {
+            double q = cs.dinv[i] * w.v2[i];
+            w.zp0[s][n + i] = xr0 + xr1 * q;
+            w.zp0[s][n - 1 - i] = xr0 - xr1 * q;
+        }
+    } else {
+        for (int i = lane; i < N; i += 32) w.zp0[s][i] = 0.0;
+    }
+    __syncwarp();
+    return 0;
+}
+
+// GC(r, j) of the reference (disort.f:3309-3312) from the compact blocks
+__device__ __forceinline__ double gc_elem(const double *Gp, const double *Gm,
+                                          int n, int r, int j)
+{
+    if (r >= n) {
+        int i = r - n;
+        return (j >= n) ? Gp[i * n + (j - n)] : -Gm[i * n + (n - 1 - j)];
+    } else {
+        int i = n - 1 - r;
+        return (j >= n) ? Gm[i * n + (j - n)] : -Gp[i * n + (n - 1 - j)];
+    }
+}
+
+// copy a layer record shared -> scratch
+__device__ void store_layer(const LayerLayout &ll, double *rec, const WarpShared &w,
+                            int s, double xr0, double xr1, int lane)
+{
+    const int n = ll.n, N = ll.N;
+    for (int e = lane; e < n; e += 32) { rec[ll.off_kk + e] = w.kk[s][e]; rec[ll.off_ek + e] = w.ek[s][e]; }
+    for (int e = lane; e < n * n; e += 32) { rec[ll.off_gp + e] = w.Gp[s][e]; rec[ll.off_gm + e] = w.Gm[s][e]; }
+    for (int e = lane; e < N; e += 32) { rec[ll.off_zz + e] = w.zz[s][e]; rec[ll.off_zp0 + e] = w.zp0[s][e]; }
+    if (lane == 0) { rec[ll.off_xr] = xr0; rec[ll.off_xr + 1] = xr1; }
+}
+
+__device__ void load_layer(const LayerLayout &ll, const double *rec, WarpShared &w,
+                           int s, double &xr0, double &xr1, int lane)
+{
+    const int n = ll.n, N = ll.N;
+    for (int e = lane; e < n; e += 32) { w.kk[s][e] = rec[ll.off_kk + e]; w.ek[s][e] = rec[ll.off_ek + e]; }
+    for (int e = lane; e < n * n; e += 32) { w.Gp[s][e] = rec[ll.off_gp + e]; w.Gm[s][e] = rec[ll.off_gm + e]; }
+    for (int e = lane; e < N; e += 32) { w.zz[s][e] = rec[ll.off_zz + e]; w.zp0[s][e] = rec[ll.off_zp0 + e]; }
+    xr0 = rec[ll.off_xr]; xr1 = rec[ll.off_xr + 1];
+}
+
+// Gaussian elimination with partial pivoting of the first `ncols` columns of
+// the row-major window W[rows][C]; pivot rows end up in rows 0..ncols-1.
+// returns 0 or SBD_BIN_SINGULAR
+__device__ int eliminate(double *W, int rows, int C, int ncols, int lane)
+{
+    for (int j = 0; j < ncols; j++) {
+        // pivot search in column j among rows j..rows-1
+        double best = -1.0; int bi = j;
+        for (int r = j + lane; r < rows; r += 32) {
+            double v = fabs(W[r * C + j]);
+            if (v > best) { best = v; bi = r; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            double ob = __shfl_xor_sync(FULLMASK, best, o);
+            int oi = __shfl_xor_sync(FULLMASK, bi, o);
+            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        }
+        if (!(best > 0.0)) return SBD_BIN_SINGULAR;
+        if (bi != j) {
+            for (int cidx = j + lane; cidx < C; cidx += 32) {
+                double t = W[j * C + cidx];
+                W[j * C + cidx] = W[bi * C + cidx];
+                W[bi * C + cidx] = t;
+            }
+        }
+        __syncwarp();
+        const double rp = 1.0 / W[j * C + j];
+        // lanes over columns, loop over rows
+        for (int cidx = j + 1 + lane; cidx < C; cidx += 32) {
+            const double pv = W[j * C + cidx];
+            for (int r = j + 1; r < rows; r++) {
+                double mlt = W[r * C + j] * rp;
+                W[r * C + cidx] -= mlt * pv;
+            }
+        }
+        __syncwarp();
+    }
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------
+extern __shared__ double smem_dyn[];
+
+__global__ void __launch_bounds__(256)
+disort_generic_kernel(const LaunchArgs a)
+{
+    const int N = a.d.nstr, n = N / 2, L = a.d.nlyr;
+    const int NT = a.d.ntau > 0 ? a.d.ntau : L + 1;
+    const int NU = a.d.numu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int warps = blockDim.x >> 5;
+    const int ldp = a.d.nmom + 1;
+    const LayerLayout ll(N, NU);
+
+    CtaShared cs;
+    cs.mu = smem_dyn; cs.wt = cs.mu + n; cs.sq = cs.wt + n; cs.dinv = cs.sq + n;
+    cs.ylm = cs.dinv + n;
+    WarpShared w;
+    const int NTs = NT > 8 ? NT : 8;
+    carve(smem_dyn + cta_shared_doubles(N) + (size_t)warp * warp_shared_doubles(N, L, NTs),
+          N, L, NTs, w);
+
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        double mu = a.quad[i], wt = a.quad[n + i];
+        cs.mu[i] = mu; cs.wt[i] = wt;
+        cs.sq[i] = sqrt(wt / mu);
+        cs.dinv[i] = 1.0 / sqrt(wt * mu);
+    }
+    // flux path: azimuth mode 0 only
+    for (int e = threadIdx.x; e < N * n; e += blockDim.x) cs.ylm[e] = a.ylmc[e];
+    __syncthreads();
+
+    const int slot = blockIdx.x * warps + warp;
+    double *scr = a.scratch + (size_t)slot * a.slot_stride;
+    double *LLs = scr + (size_t)ll.stride * L;   // [L][N] solution coefficients
+
+    for (;;) {
+        int bin = 0;
+        if (lane == 0) bin = atomicAdd(a.work_counter, 1);
+        bin = __shfl_sync(FULLMASK, bin, 0);
+        if (bin >= a.d.nbins) break;
+
+        const sbd_bin bp = a.bins[bin];
+        BinCtx c;
+        c.N = N; c.n = n; c.L = L; c.NT = NT; c.mazim = 0; c.delm0 = 1.0;
+        c.fbeam = bp.fbeam; c.umu0 = bp.umu0; c.albedo = bp.albedo; c.fisot = bp.fisot;
+        c.plank = bp.plank;
+        c.dtauc = a.dtauc + (size_t)bin * L;
+        c.ssalb = a.ssalb + (size_t)bin * L;
+        c.pmom = a.pmom + (size_t)bin * L * ldp;
+        c.ldp = ldp;
+        double *o_rfldir = a.rfldir ? a.rfldir + (size_t)bin * NT : nullptr;
+        double *o_rfldn = a.rfldn ? a.rfldn + (size_t)bin * NT : nullptr;
+        double *o_flup = a.flup ? a.flup + (size_t)bin * NT : nullptr;
+        double *o_dfdt = a.dfdt ? a.dfdt + (size_t)bin * NT : nullptr;
+        double *o_uavg = a.uavg ? a.uavg + (size_t)bin * NT : nullptr;
+
+        int status = 0;
+        // ---- input checks (subset of CHEKIN, disort.f:4920-5155) ----------
+        {
+            int badl = 0;
+            for (int lc = lane; lc < L; lc += 32) {
+                double s = c.ssalb[lc];
+                if (!(s >= 0.0 && s <= 1.0)) badl = 1;
+                for (int k = 1; k <= a.d.nmom; k++) {
+                    double pm = c.pmom[(size_t)lc * ldp + k];
+                    if (!(pm >= -1.0 && pm <= 1.0)) badl = 1;
+                }
+            }
+            if (c.fbeam < 0.0 || (c.fbeam > 0.0 && !(c.umu0 > 0.0 && c.umu0 <= 1.0))) badl = 1;
+            if (!(c.albedo >= 0.0 && c.albedo <= 1.0) || c.fisot < 0.0) badl = 1;
+            if (c.plank && (bp.wvnmlo < 0.0 || bp.wvnmhi <= bp.wvnmlo || bp.temis < 0.0 ||
+                            bp.temis > 1.0 || bp.btemp < 0.0 || bp.ttemp < 0.0)) badl = 1;
+            if (__any_sync(FULLMASK, badl)) status = SBD_BIN_BAD_INPUT;
+            // beam angle = quadrature angle (disort.f:2641-2650)
+            int clash = 0;
+            if (c.fbeam > 0.0)
+                for (int i = lane; i < n; i += 32)
+                    if (fabs(c.umu0 - cs.mu[i]) / c.umu0 < 1.e-4) clash = 1;
+            if (!status && __any_sync(FULLMASK, clash)) status = SBD_BIN_ANGLE_CLASH;
+        }
+
+        // ---- SETDIS prologue: cumulative depths, truncation (:2546-2605) --
+        if (lane == 0) {
+            double tc = 0.0, tp = 0.0, abstau = 0.0;
+            int ncut = L;
+            w.tauc[0] = 0.0; w.taucpr[0] = 0.0;
+            for (int lc = 0; lc < L; lc++) {
+                double s = c.ssalb[lc];
+                if (s == 1.0) s = 1.0 - kDither;
+                double dt = c.dtauc[lc];
+                tc += dt;                               // TAUC uses unclipped DTAUC
+                if (dt < 0.0) dt = 0.0;
+                if (abstau < 10.0) ncut = lc + 1;
+                abstau += (1. - s) * dt;
+                double f = c.pmom[(size_t)lc * ldp + N];
+                tp += (1. - f * s) * dt;
+                w.tauc[lc + 1] = tc; w.taucpr[lc + 1] = tp;
+            }
+            int lyrcut = (abstau >= 10.0 && !c.plank && L > 1);
+            if (!lyrcut) ncut = L;
+            w.pq[0] = ncut; w.pq[1] = lyrcut;
+        }
+        __syncwarp();
+        c.ncut = w.pq[0]; c.lyrcut = w.pq[1];
+        __syncwarp();
+        const int ncut = c.ncut;
+
+        // level -> layer map and scaled level depths (disort.f:2610-2625)
+        int badtau = 0;
+        for (int lu = lane; lu < NT; lu += 32) {
+            double ut = a.d.ntau > 0 ? a.utau[(size_t)bin * NT + lu] : w.tauc[lu];
+            if (a.d.ntau > 0 && fabs(ut - w.tauc[L]) <= 1.e-4) ut = w.tauc[L];
+            if (a.d.ntau > 0 && !(ut >= 0.0 && ut <= w.tauc[L])) badtau = 1;
+            int lc;
+            for (lc = 1; lc <= L; lc++)
+                if (ut >= w.tauc[lc - 1] && ut <= w.tauc[lc]) break;
+            if (lc > L) lc = L;
+            w.layru[lu] = lc;
+        }
+        if (__any_sync(FULLMASK, badtau)) status = SBD_BIN_BAD_INPUT;
+
+        // Planck function at the levels (disort.f:556-571)
+        c.tplank = 0.0; c.bplank = 0.0;
+        if (c.plank && !status) {
+            const double *tp = a.temper + (size_t)bp.col * (L + 1);
+            for (int lev = lane; lev <= L; lev += 32)
+                w.pk[lev] = plkavg_dev(bp.wvnmlo, bp.wvnmhi, tp[lev]);
+            c.tplank = bp.temis * plkavg_dev(bp.wvnmlo, bp.wvnmhi, bp.ttemp);
+            c.bplank = plkavg_dev(bp.wvnmlo, bp.wvnmhi, bp.btemp);
+        }
+        // Y_l^0(-mu0) by the Legendre recurrence (LEPOLY, disort.f:5354-5370)
+        if (lane == 0 && c.fbeam > 0.0) {
+            double x = -c.umu0;
+            w.y0[0] = 1.0; w.y0[1] = x;
+            for (int l = 2; l < N; l++)
+                w.y0[l] = ((2 * l - 1) * x * w.y0[l - 1] - (l - 1) * w.y0[l - 2]) / l;
+        }
+        __syncwarp();
+
+        // zero the outputs (ZEROAL, disort.f:518); levels below NCUT stay 0
+        for (int lu = lane; lu < NT; lu += 32) {
+            if (o_rfldir) o_rfldir[lu] = 0.0;
+            if (o_rfldn) o_rfldn[lu] = 0.0;
+            if (o_flup) o_flup[lu] = 0.0;
+            if (o_dfdt) o_dfdt[lu] = 0.0;
+            if (o_uavg) o_uavg[lu] = 0.0;
+        }
+
+        const int R = n + N, C = 2 * N + 1;
+        double xr0c = 0, xr1c = 0, xr0n = 0, xr1n = 0;
+        int cur = 0;
+
+        // ================= downward sweep ================================
+        if (!status) status = solve_layer(c, cs, w, 0, cur, xr0c, xr1c, lane);
+        if (!status) {
+            store_layer(ll, scr, w, cur, xr0c, xr1c, lane);
+            // top boundary rows (disort.f:2887-2915, :3547-3550)
+            for (int e = lane; e < n * C; e += 32) {
+                int r = e / C, j = e - r * C;
+                double v;
+                if (j < N) {
+                    double g = gc_elem(w.Gp[cur], w.Gm[cur], n, r, j);
+                    v = (j < n) ? g * w.ek[cur][n - 1 - j] : g;
+                } else if (j < 2 * N) {
+                    v = 0.0;
+                } else {
+                    v = c.fisot + c.tplank - w.zz[cur][r] - w.zp0[cur][r];
+                }
+                w.W[r * C + j] = v;
+            }
+        }
+        for (int lc = 0; lc < ncut - 1 && !status; lc++) {
+            const int nxt = cur ^ 1;
+            status = solve_layer(c, cs, w, lc + 1, nxt, xr0n, xr1n, lane);
+            if (status) break;
+            store_layer(ll, scr + (size_t)(lc + 1) * ll.stride, w, nxt, xr0n, xr1n, lane);
+            // interface rows between layer lc and lc+1 (disort.f:2846-2882, :3585-3593)
+            const double tb = w.taucpr[lc + 1];
+            const double eb = (c.fbeam > 0.0) ? exp(-tb / c.umu0) : 0.0;
+            for (int e = lane; e < N * C; e += 32) {
+                int r = e / C, j = e - r * C;
+                double v;
+                if (j < N) {
+                    double g = gc_elem(w.Gp[cur], w.Gm[cur], n, r, j);
+                    v = (j < n) ? g : g * w.ek[cur][j - n];
+                } else if (j < 2 * N) {
+                    int jj = j - N;
+                    double g = gc_elem(w.Gp[nxt], w.Gm[nxt], n, r, jj);
+                    v = (jj < n) ? -g * w.ek[nxt][n - 1 - jj] : -g;
+                } else {
+                    v = (w.zz[nxt][r] - w.zz[cur][r]) * eb + w.zp0[nxt][r] - w.zp0[cur][r] +
+                        (xr1n - xr1c) * tb;
+                }
+                w.W[(n + r) * C + j] = v;
+            }
+            __syncwarp();
+            status = eliminate(w.W, R, C, N, lane);
+            if (status) break;
+            // keep the N pivot rows, carry the n remaining rows
+            double *U = scr + (size_t)lc * ll.stride + ll.off_u;
+            for (int e = lane; e < N * C; e += 32) U[e] = w.W[e];
+            __syncwarp();
+            for (int e = lane; e < n * C; e += 32) {
+                int r = e / C, j = e - r * C;
+                double v;
+                if (j < N) v = w.W[(N + r) * C + N + j];
+                else if (j < 2 * N) v = 0.0;
+                else v = w.W[(N + r) * C + 2 * N];
+                // source rows N..R-1 never overlap destination rows 0..n-1
+                w.W[r * C + j] = v;
+            }
+            __syncwarp();
+            cur = nxt; xr0c = xr0n; xr1c = xr1n;
+        }
+
+        // ================= bottom boundary + last layer ====================
+        if (!status) {
+            const int lc = ncut - 1;
+            const double tb = w.taucpr[ncut];
+            const double eb = (c.fbeam > 0.0) ? exp(-tb / c.umu0) : 0.0;
+            const int refl = !c.lyrcut;     // Lambertian, m = 0 (disort.f:2929-2947)
+            // sum_k w_k mu_k GC(-mu_k, j): one value per column, and for the rhs
+            for (int j = lane; j <= N; j += 32) {
+                double sacc = 0.0;
+                if (refl) {
+                    for (int k = 0; k < n; k++) {
+                        double g = (j < N) ? gc_elem(w.Gp[cur], w.Gm[cur], n, n - 1 - k, j)
+                                           : (w.zz[cur][n - 1 - k] * eb + w.zp0[cur][n - 1 - k] + xr1c * tb);
+                        sacc += cs.wt[k] * cs.mu[k] * g;
+                    }
+                }
+                if (j < N) w.v1[j] = sacc; else w.v2[0] = sacc;   // v2[0]: rhs part
+            }
+            __syncwarp();
+            for (int e = lane; e < n * C; e += 32) {
+                int i = e / C, j = e - i * C;
+                int r = n + i;
+                double v;
+                if (j < N) {
+                    double g = gc_elem(w.Gp[cur], w.Gm[cur], n, r, j);
+                    if (refl) g -= 2.0 * c.albedo * w.v1[j];
+                    v = (j < n) ? g : g * w.ek[cur][j - n];
+                } else if (j < 2 * N) {
+                    v = 0.0;
+                } else {
+                    v = -w.zz[cur][r] * eb - w.zp0[cur][r] - xr1c * tb;
+                    if (refl)
+                        v += 2.0 * c.albedo * w.v2[0] + c.albedo * c.umu0 * c.fbeam / kPiRef * eb +
+                             (1.0 - c.albedo) * c.bplank;
+                }
+                w.W[(n + i) * C + j] = v;
+            }
+            __syncwarp();
+            status = eliminate(w.W, N, C, N, lane);
+            (void)lc;
+        }
+
+        // ================= upward sweep: back substitution + fluxes ========
+        if (!status) {
+            for (int lc = ncut - 1; lc >= 0; lc--) {
+                if (lc < ncut - 1) {
+                    const double *U = scr + (size_t)lc * ll.stride + ll.off_u;
+                    for (int e = lane; e < N * C; e += 32) w.W[e] = U[e];
+                    load_layer(ll, scr + (size_t)lc * ll.stride, w, cur, xr0c, xr1c, lane);
+                    __syncwarp();
+                    // rhs -= U[:, N:2N] x_{lc+1}
+                    for (int r = lane; r < N; r += 32) {
+                        double acc = w.W[r * C + 2 * N];
+                        for (int j = 0; j < N; j++) acc -= w.W[r * C + N + j] * w.xn[j];
+                        w.W[r * C + 2 * N] = acc;
+                    }
+                    __syncwarp();
+                }
+                // upper-triangular solve
+                for (int j = N - 1; j >= 0; j--) {
+                    double xj = w.W[j * C + 2 * N] / w.W[j * C + j];
+                    __syncwarp();
+                    if (lane == 0) w.xc[j] = xj;
+                    for (int r = lane; r < j; r += 32) w.W[r * C + 2 * N] -= w.W[r * C + j] * xj;
+                    __syncwarp();
+                }
+                for (int j = lane; j < N; j += 32) { LLs[(size_t)lc * N + j] = w.xc[j]; }
+                __syncwarp();
+
+                // fluxes at the levels that live in this layer (FLUXES)
+                for (int lu = 0; lu < NT; lu++) {
+                    if (w.layru[lu] != lc + 1) continue;
+                    double ut = a.d.ntau > 0 ? a.utau[(size_t)bin * NT + lu] : w.tauc[lu];
+                    if (a.d.ntau > 0 && fabs(ut - w.tauc[L]) <= 1.e-4) ut = w.tauc[L];
+                    double ss = c.ssalb[lc]; if (ss == 1.0) ss = 1.0 - kDither;
+                    const double f = c.pmom[(size_t)lc * ldp + N];
+                    const double utp = w.taucpr[lc] + (1. - ss * f) * (ut - w.tauc[lc]);
+                    // a_j = x+_j exp(-k (t - t_top)), b_j = x-_j exp(-k (t_bot - t))
+                    for (int j = lane; j < n; j += 32) {
+                        double k = w.kk[cur][j];
+                        w.v1[j] = w.xc[n + j] * exp(-k * (utp - w.taucpr[lc]));
+                        w.v2[j] = w.xc[n - 1 - j] * exp(-k * (w.taucpr[lc + 1] - utp));
+                    }
+                    __syncwarp();
+                    double fact = 0.0, dirint = 0.0, fldir = 0.0, rfldir = 0.0;
+                    if (c.fbeam > 0.0) {
+                        fact = exp(-utp / c.umu0);
+                        dirint = c.fbeam * fact;
+                        fldir = c.umu0 * (c.fbeam * fact);
+                        rfldir = c.umu0 * c.fbeam * exp(-ut / c.umu0);
+                    }
+                    double up = 0.0, dn = 0.0, av = 0.0;
+                    for (int i = lane; i < n; i += 32) {
+                        double uu = 0.0, ud = 0.0;
+                        for (int j = 0; j < n; j++) {
+                            double gp = w.Gp[cur][i * n + j], gm = w.Gm[cur][i * n + j];
+                            uu += gp * w.v1[j] - gm * w.v2[j];
+                            ud += gm * w.v1[j] - gp * w.v2[j];
+                        }
+                        uu += w.zz[cur][n + i] * fact + w.zp0[cur][n + i] + xr1c * utp;
+                        ud += w.zz[cur][n - 1 - i] * fact + w.zp0[cur][n - 1 - i] + xr1c * utp;
+                        double wm = cs.wt[i] * cs.mu[i];
+                        up += wm * uu; dn += wm * ud; av += cs.wt[i] * (uu + ud);
+                    }
+                    up = warp_sum(up); dn = warp_sum(dn); av = warp_sum(av);
+                    if (lane == 0) {
+                        const double pi = kPiRef;
+                        double flup = 2. * pi * up, fldn = 2. * pi * dn;
+                        double fdntot = fldn + fldir;
+                        double uavg = (2. * pi * av + dirint) / (4. * pi);
+                        double plsorc = xr0c + xr1c * utp;
+                        if (o_rfldir) o_rfldir[lu] = rfldir;
+                        if (o_rfldn) o_rfldn[lu] = fdntot - rfldir;
+                        if (o_flup) o_flup[lu] = flup;
+                        if (o_uavg) o_uavg[lu] = uavg;
+                        if (o_dfdt) o_dfdt[lu] = (1. - ss) * 4. * pi * (uavg - plsorc);
+                    }
+                    __syncwarp();
+                }
+                for (int j = lane; j < N; j += 32) w.xn[j] = w.xc[j];
+                __syncwarp();
+            }
+        }
+        if (lane == 0) a.status[bin] = status;
+        __syncwarp();
+    }
+}
+
+cudaError_t launch_generic(const LaunchArgs &a, int warps, int grid, cudaStream_t st)
+{
+    size_t smem = generic_smem_bytes(a.d.nstr, a.d.nlyr,
+                                     a.d.ntau > 0 ? a.d.ntau : a.d.nlyr + 1, warps);
+    cudaError_t e = cudaFuncSetAttribute(disort_generic_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    disort_generic_kernel<<<grid, warps * 32, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace sbd

@@ -1,0 +1,65 @@
+// Internal declarations shared by the C-ABI host code and the CUDA kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/sbdart_b200.h"
+
+namespace sbd {
+
+// DITHER of the reference: 10*R1MACH(4), times 10 again because it is
+// below 1e-10 (disort.f:442-448) => 100 * 2^-52.
+constexpr double kDither = 100.0 * 2.220446049250313e-16;
+// PI = 2.*ASIN(1.0) evaluated in default REAL and widened (disort.f:441).
+constexpr double kPiRef = 3.1415927410125732;
+
+// Everything a kernel launch needs (device pointers).
+struct LaunchArgs {
+    sbd_dims d;
+    const double *dtauc, *ssalb, *pmom;
+    const sbd_bin *bins;
+    const double *temper, *utau, *umu, *phi;
+    double *rfldir, *rfldn, *flup, *dfdt, *uavg, *uu;
+    int32_t *status;
+    const double *quad;   // [2n]: mu[0..n), wt[0..n)
+    const double *ylmc;   // [M][N][n]   Y_l^m(mu_i)
+    const double *ylmu;   // [M][N][numu] Y_l^m(umu_iu)  (radiance runs)
+    double *scratch;      // nslots * slot_stride doubles
+    size_t slot_stride;
+    int nslots;           // number of concurrently resident warps
+    int nmodes;           // azimuth modes to run (1 for flux-only)
+    int *work_counter;    // dynamic bin scheduler
+};
+
+// Per-layer record kept in scratch between the downward elimination sweep
+// and the upward back-substitution sweep.
+struct LayerLayout {
+    int n, N, NU;
+    int off_kk, off_ek, off_gp, off_gm, off_zz, off_zp0, off_xr, off_u,
+        off_gu, off_zb, off_z0u, off_z1u, stride;
+    __host__ __device__ LayerLayout(int N_, int NU_) {
+        N = N_; n = N_ / 2; NU = NU_;
+        int o = 0;
+        off_kk = o; o += n;
+        off_ek = o; o += n;
+        off_gp = o; o += n * n;
+        off_gm = o; o += n * n;
+        off_zz = o; o += N;
+        off_zp0 = o; o += N;
+        off_xr = o; o += 2;
+        off_u = o; o += N * (2 * N + 1);
+        off_gu = o; o += NU * N;
+        off_zb = o; o += NU;
+        off_z0u = o; o += NU;
+        off_z1u = o; o += NU;
+        stride = (o + 1) & ~1;
+    }
+};
+
+size_t generic_smem_bytes(int N, int L, int NT, int warps);
+size_t generic_slot_doubles(int N, int L, int NU);
+int generic_pick_warps(int N, int L, int NT, size_t smem_limit);
+cudaError_t launch_generic(const LaunchArgs &a, int warps, int grid,
+                           cudaStream_t st);
+
+}  // namespace sbd
