@@ -239,14 +239,29 @@ extern "C" int sbd_disort_batch_device(sbd_handle *h, const sbd_dims *dims, cons
     if (rc) return rc;
 
     size_t smem_limit = h->smem_optin ? h->smem_optin : 48 * 1024;
-    int warps = generic_pick_warps(N, L, NT, smem_limit);
-    if (warps == 0) return SBD_ERR_UNSUPPORTED;
-    if (warps > 4) warps = 4;
-    size_t smem = generic_smem_bytes(N, L, NT, warps);
-    int cta_per_sm = (int)((smem_limit + 1024) / (smem + 1024));
-    if (cta_per_sm < 1) cta_per_sm = 1;
-    if (cta_per_sm * warps > 16) cta_per_sm = 16 / warps > 0 ? 16 / warps : 1;
-    int grid = h->sm_count * cta_per_sm;
+    const bool fast = fast_supported(N) && !getenv("SBD_FORCE_GENERIC");
+    int warps, grid;
+    size_t slot;
+    if (fast) {
+        warps = 4;
+        size_t smem = fast_smem_bytes(N, L, NT, warps);
+        if (smem > smem_limit) return SBD_ERR_UNSUPPORTED;
+        int cta_per_sm = (int)((smem_limit + 1024) / (smem + 1024));
+        if (cta_per_sm > 4) cta_per_sm = 4;
+        if (cta_per_sm < 1) cta_per_sm = 1;
+        grid = h->sm_count * cta_per_sm;
+        slot = fast_slot_doubles(N, L);
+    } else {
+        warps = generic_pick_warps(N, L, NT, smem_limit);
+        if (warps == 0) return SBD_ERR_UNSUPPORTED;
+        if (warps > 4) warps = 4;
+        size_t smem = generic_smem_bytes(N, L, NT, warps);
+        int cta_per_sm = (int)((smem_limit + 1024) / (smem + 1024));
+        if (cta_per_sm < 1) cta_per_sm = 1;
+        if (cta_per_sm * warps > 16) cta_per_sm = 16 / warps > 0 ? 16 / warps : 1;
+        grid = h->sm_count * cta_per_sm;
+        slot = generic_slot_doubles(N, L, 0);
+    }
     int need = (dims->nbins + warps - 1) / warps;
     if (grid > need) grid = need;
 
@@ -259,13 +274,14 @@ extern "C" int sbd_disort_batch_device(sbd_handle *h, const sbd_dims *dims, cons
     a.status = status;
     a.quad = tb.quad; a.ylmc = tb.ylmc; a.ylmu = nullptr;
     a.nslots = grid * warps;
-    a.slot_stride = generic_slot_doubles(N, L, 0);
+    a.slot_stride = slot;
     a.nmodes = 1;
     if (h->scratch.reserve(a.slot_stride * (size_t)a.nslots * 8) != cudaSuccess) return SBD_ERR_CUDA;
     a.scratch = (double *)h->scratch.p;
     a.work_counter = (int *)h->counter.p;
     if (cudaMemsetAsync(a.work_counter, 0, sizeof(int), st) != cudaSuccess) return SBD_ERR_CUDA;
-    if (launch_generic(a, warps, grid, st) != cudaSuccess) return SBD_ERR_CUDA;
+    cudaError_t le = fast ? launch_fast(a, warps, grid, st) : launch_generic(a, warps, grid, st);
+    if (le != cudaSuccess) return SBD_ERR_CUDA;
     h->launches += 1;
     return SBD_SUCCESS;
 }

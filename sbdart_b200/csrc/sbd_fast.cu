@@ -1,0 +1,728 @@
+// Register-resident warp-per-bin discrete-ordinate kernel for NSTR = 4, 8, 16.
+//
+// Same mathematics as sbd_generic.cu (see the header comment there) but laid
+// out for the hardware:
+//   phase 1  per-layer eigen / particular solutions.  A warp works on 32/n
+//            layers of its bin at once; each layer is owned by a group of n
+//            lanes, lane j holding ROW j (Cholesky factors) or COLUMN j
+//            (one-sided Jacobi) of the n x n matrices in registers, exchanged
+//            with width-n shuffles.  The symmetric eigenproblem
+//            T = L^T Pe~ L is solved as the SVD of A = K^T L (Pe~ = K K^T)
+//            by one-sided (Hestenes) Jacobi with round-robin pairing: the
+//            singular values are the DISORT eigenvalues k_j themselves.
+//   phase 2  downward elimination of the block-bidiagonal boundary system,
+//            one matrix row per lane ((n+N) x (2N+1) window in registers),
+//            pivot row broadcast by shuffles, pivot choice by REDUX on the
+//            high word of |a|.
+//   phase 3  upward back-substitution (row per lane) fused with the flux
+//            evaluation at the layer boundaries.
+// Per-layer records and pivot rows travel between the phases through a
+// per-warp scratch slot in global memory.
+#include <math.h>
+
+#include "sbd_internal.h"
+#include "sbd_planck.cuh"
+
+namespace sbd {
+
+#define FULLMASK 0xffffffffu
+
+
+template <int n>
+struct FastLayout {
+    static constexpr int N = 2 * n;
+    static constexpr int C = 2 * N + 1;
+    // per-layer record (doubles)
+    static constexpr int off_kk = 0;
+    static constexpr int off_ek = n;
+    static constexpr int off_gp = 2 * n;
+    static constexpr int off_gm = 2 * n + n * n;
+    static constexpr int off_zz = 2 * n + 2 * n * n;
+    static constexpr int off_zp0 = off_zz + N;
+    static constexpr int off_xr = off_zp0 + N;
+    static constexpr int rec = ((off_xr + 2 + 1) / 2) * 2;
+    static constexpr int urow = ((C + 1) / 2) * 2;        // padded pivot-row length
+    static constexpr int ublk = N * urow;
+    __host__ __device__ static size_t slot_doubles(int L) { return (size_t)L * (rec + ublk); }
+    // shared memory (doubles)
+    static constexpr int cta = 4 * n + N * n;
+    static constexpr int tasks = 32 / n;
+    static constexpr int task = N + 4 * n * n + 4 * n;     // gl, K, L, G1, G2, vectors
+    __host__ __device__ static size_t warp_doubles(int L, int NT)
+    {
+        return (size_t)N + 3 * (L + 1) + (NT + 1) / 2 + (size_t)tasks * task + 2;
+    }
+};
+
+__device__ __forceinline__ double shfl_d(double v, int src, int width)
+{
+    return __shfl_sync(FULLMASK, v, src, width);
+}
+
+// ---------------------------------------------------------------------------
+// phase 1: one layer per group of n lanes
+// ---------------------------------------------------------------------------
+template <int n>
+__device__ __forceinline__ int phase1_layers(
+    const double *__restrict__ dtauc, const double *__restrict__ ssalb,
+    const double *__restrict__ pmom, int ldp, int lc, bool active, int mazim,
+    double fbeam, double umu0, bool plank, double delm0,
+    const double *cmu, const double *csq, const double *cdinv, const double *cylm,
+    const double *y0, const double *taucpr, const double *pk,
+    double *tsm /* per-task shared */, double *rec /* scratch record of this layer */,
+    int g /* lane in group */)
+{
+    constexpr int N = 2 * n;
+    double *sgl = tsm, *sK = sgl + N, *sL = sK + n * n, *sG1 = sL + n * n, *sG2 = sG1 + n * n,
+           *sv = sG2 + n * n;   // sv: 4 vectors of n
+
+    double ss = ssalb[lc];
+    if (ss == 1.0) ss = 1.0 - kDither;
+    double dt = dtauc[lc];
+    if (dt < 0.0) dt = 0.0;
+    const double f = pmom[(size_t)lc * ldp + N];
+    const double oprim = ss * (1. - f) / (1. - f * ss);
+    const double dtaucp = (1. - f * ss) * dt;
+    const double rf = 1.0 / (1. - f);
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        int l = g + h * n;
+        double pm = (l == 0) ? 1.0 : pmom[(size_t)lc * ldp + l];
+        sgl[l] = (2 * l + 1) * oprim * (pm - f) * rf;
+    }
+    __syncwarp();
+
+    // rows g of Pe~ and Po~
+    double pe[n], po[n];
+#pragma unroll
+    for (int j = 0; j < n; j++) { pe[j] = 0.0; po[j] = 0.0; }
+#pragma unroll
+    for (int l = 0; l < N; l++) {
+        if (l >= mazim) {
+            const double t = sgl[l] * cylm[l * n + g];
+            if ((l - mazim) & 1) {
+#pragma unroll
+                for (int j = 0; j < n; j++) po[j] = fma(t, cylm[l * n + j], po[j]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < n; j++) pe[j] = fma(t, cylm[l * n + j], pe[j]);
+            }
+        }
+    }
+    const double sqg = csq[g], rmu = 1.0 / cmu[g];
+#pragma unroll
+    for (int j = 0; j < n; j++) {
+        const double sc = sqg * csq[j];
+        const double dg = (j == g) ? rmu : 0.0;
+        pe[j] = dg - sc * pe[j];
+        po[j] = dg - sc * po[j];
+    }
+
+    // row Cholesky of both operators: Po~ = L L^T, Pe~ = K K^T (lane g = row g)
+    int bad = 0;
+#pragma unroll
+    for (int j = 0; j < n; j++) {
+        double nume = pe[j], numo = po[j];
+#pragma unroll
+        for (int k = 0; k < j; k++) {
+            nume = fma(-pe[k], shfl_d(pe[k], j, n), nume);
+            numo = fma(-po[k], shfl_d(po[k], j, n), numo);
+        }
+        double pive = shfl_d(nume, j, n), pivo = shfl_d(numo, j, n);
+        if (!(pivo > 0.0)) { bad = 1; pivo = 1.0; }
+        // Pe~ is only semidefinite when w' -> 1: keep the factor real
+        const double floor_e = 1.0e-30;
+        if (!(pive > floor_e)) pive = floor_e;
+        const double rie = rsqrt(pive), rio = rsqrt(pivo);
+        pe[j] = (g == j) ? pive * rie : ((g > j) ? nume * rie : 0.0);
+        po[j] = (g == j) ? pivo * rio : ((g > j) ? numo * rio : 0.0);
+    }
+#pragma unroll
+    for (int j = 0; j < n; j++) { sK[g * n + j] = pe[j]; sL[g * n + j] = po[j]; }
+    __syncwarp();
+
+    // column g of A = K^T L, V = I
+    double a[n], v[n];
+    {
+        double lcol[n];
+#pragma unroll
+        for (int k = 0; k < n; k++) lcol[k] = sL[k * n + g];
+#pragma unroll
+        for (int i = 0; i < n; i++) {
+            double acc = 0.0;
+#pragma unroll
+            for (int k = i; k < n; k++) acc = fma(sK[k * n + i], lcol[k], acc);
+            a[i] = acc;
+            v[i] = (i == g) ? 1.0 : 0.0;
+        }
+    }
+
+    // one-sided Jacobi, round-robin pairing; columns exchanged by shuffles
+    if (n > 1) {
+        for (int sweep = 0; sweep < 40; sweep++) {
+            int did = 0;
+#pragma unroll
+            for (int r = 0; r < n - 1; r++) {
+                int partner;
+                if (g == n - 1) partner = r;
+                else if (g == r) partner = n - 1;
+                else {
+                    partner = 2 * r - g + (n - 1);
+                    if (partner >= n - 1) partner -= n - 1;
+                    if (partner >= n - 1) partner -= n - 1;
+                }
+                double pa[n], pv[n];
+                double own2 = 0.0, oth2 = 0.0, gam = 0.0;
+#pragma unroll
+                for (int i = 0; i < n; i++) {
+                    pa[i] = shfl_d(a[i], partner, n);
+                    pv[i] = shfl_d(v[i], partner, n);
+                    own2 = fma(a[i], a[i], own2);
+                    oth2 = fma(pa[i], pa[i], oth2);
+                    gam = fma(a[i], pa[i], gam);
+                }
+                const bool lo = g < partner;
+                const double alpha = lo ? own2 : oth2, beta = lo ? oth2 : own2;
+                if (fabs(gam) > 1.0e-14 * sqrt(alpha * beta) && fabs(gam) > 1.0e-300) {
+                    did = 1;
+                    const double dl = 0.5 * (beta - alpha);
+                    const double hy = sqrt(fma(dl, dl, gam * gam));
+                    const double t = gam / (dl + (dl >= 0.0 ? hy : -hy));
+                    const double cc = rsqrt(fma(t, t, 1.0));
+                    const double sn = lo ? -t * cc : t * cc;
+#pragma unroll
+                    for (int i = 0; i < n; i++) {
+                        a[i] = fma(sn, pa[i], cc * a[i]);
+                        v[i] = fma(sn, pv[i], cc * v[i]);
+                    }
+                }
+            }
+            if (!__any_sync(FULLMASK, did)) break;
+        }
+    }
+
+    // singular value = DISORT eigenvalue k (disort.f:3264-3269)
+    double s2 = 0.0;
+#pragma unroll
+    for (int i = 0; i < n; i++) s2 = fma(a[i], a[i], s2);
+    const double kk = sqrt(s2);
+    const double ek = exp(-kk * dtaucp);
+    // column g of P = L V and of Q = L^-T V
+    double P[n], Q[n];
+#pragma unroll
+    for (int i = 0; i < n; i++) {
+        double acc = 0.0;
+#pragma unroll
+        for (int k = 0; k <= i; k++) acc = fma(sL[i * n + k], v[k], acc);
+        P[i] = acc;
+    }
+#pragma unroll
+    for (int i = n - 1; i >= 0; i--) {
+        double acc = v[i];
+#pragma unroll
+        for (int k = i + 1; k < n; k++) acc = fma(-sL[k * n + i], Q[k], acc);
+        Q[i] = acc / sL[i * n + i];
+    }
+    // G+ - G- = D^-1 Q ; G+ + G- = -D^-1 P / k   (disort.f:3273-3301)
+    const double rk = 1.0 / kk;
+    double gs[n], gd[n];
+#pragma unroll
+    for (int i = 0; i < n; i++) {
+        gd[i] = cdinv[i] * Q[i];
+        gs[i] = -cdinv[i] * P[i] * rk;
+        sG1[g * n + i] = gs[i];      // [mode j][direction i]
+        sG2[g * n + i] = gd[i];
+    }
+    if (active) {
+        rec[FastLayout<n>::off_kk + g] = kk;
+        rec[FastLayout<n>::off_ek + g] = ek;
+#pragma unroll
+        for (int i = 0; i < n; i++) {
+            rec[FastLayout<n>::off_gp + i * n + g] = 0.5 * (gs[i] + gd[i]);
+            rec[FastLayout<n>::off_gm + i * n + g] = 0.5 * (gs[i] - gd[i]);
+        }
+    }
+
+    // ---- beam particular solution: spectral form of UPBEAM (disort.f:4130) ----
+    double zup = 0.0, zdn = 0.0;
+    if (fbeam > 0.0) {
+        const double fac = (2. - delm0) * fbeam / (4. * kPiRef);
+        const double rmu0 = 1.0 / umu0;
+        double be = 0.0, bo = 0.0;
+#pragma unroll
+        for (int l = 0; l < N; l++) {
+            if (l >= mazim) {
+                const double t = sgl[l] * cylm[l * n + g] * y0[l];
+                if ((l - mazim) & 1) bo += t; else be += t;
+            }
+        }
+        const double bs = 2.0 * fac * sqg * be, bd = 2.0 * fac * sqg * bo;
+        sv[g] = bd;
+        __syncwarp();
+        double t1 = 0.0;                                    // (K^T b^_d)_g
+#pragma unroll
+        for (int k = 0; k < n; k++) t1 = fma(sK[k * n + g], sv[k], t1);
+        sv[n + g] = t1;
+        __syncwarp();
+        double t2 = 0.0;                                    // (K K^T b^_d)_g
+#pragma unroll
+        for (int k = 0; k < n; k++) t2 = fma(sK[g * n + k], sv[n + k], t2);
+        sv[2 * n + g] = bs * rmu0 - t2;                     // r_g
+        __syncwarp();
+        double cj = 0.0;                                    // (P^T r)_g / (1/mu0^2 - k^2)
+#pragma unroll
+        for (int i = 0; i < n; i++) cj = fma(P[i], sv[2 * n + i], cj);
+        cj = cj / (rmu0 * rmu0 - s2);
+        sv[3 * n + g] = cj;
+        sv[g] = cj * kk;
+        __syncwarp();
+        // d = sum_j Gd(:,j) c_j ; s = mu0 (D^-1 b^_d + sum_j Gs(:,j) k_j c_j), direction i = g
+        double dv = 0.0, sv2 = 0.0;
+#pragma unroll
+        for (int j = 0; j < n; j++) {
+            dv = fma(sG2[j * n + g], sv[3 * n + j], dv);
+            sv2 = fma(sG1[j * n + g], sv[j], sv2);
+        }
+        sv2 = umu0 * (cdinv[g] * bd + sv2);
+        zup = 0.5 * (sv2 + dv);
+        zdn = 0.5 * (sv2 - dv);
+        __syncwarp();
+    }
+    // ---- thermal particular solution (UPISOT, disort.f:4247) -----------------
+    double xr0 = 0.0, xr1 = 0.0, q = 0.0;
+    if (plank && mazim == 0) {
+        if (dtaucp > 0.0) xr1 = (pk[lc + 1] - pk[lc]) / dtaucp;
+        xr0 = pk[lc] - xr1 * taucpr[lc];
+        double y[n], z[n];
+#pragma unroll
+        for (int i = 0; i < n; i++) {
+            double acc = 1.0 / cdinv[i];
+#pragma unroll
+            for (int k = 0; k < i; k++) acc = fma(-sL[i * n + k], y[k], acc);
+            y[i] = acc / sL[i * n + i];
+        }
+#pragma unroll
+        for (int i = n - 1; i >= 0; i--) {
+            double acc = y[i];
+#pragma unroll
+            for (int k = i + 1; k < n; k++) acc = fma(-sL[k * n + i], z[k], acc);
+            z[i] = acc / sL[i * n + i];
+            if (i == g) q = cdinv[i] * z[i];
+        }
+    }
+    if (active) {
+        rec[FastLayout<n>::off_zz + n + g] = zup;
+        rec[FastLayout<n>::off_zz + n - 1 - g] = zdn;
+        rec[FastLayout<n>::off_zp0 + n + g] = xr0 + xr1 * q;
+        rec[FastLayout<n>::off_zp0 + n - 1 - g] = xr0 - xr1 * q;
+        if (g == 0) { rec[FastLayout<n>::off_xr] = xr0; rec[FastLayout<n>::off_xr + 1] = xr1; }
+    }
+    __syncwarp();
+    return (bad && active) ? SBD_BIN_EIG_FAIL : 0;
+}
+
+// row r of GC times the layer-bottom (bottom=true) or layer-top exponential
+// factors, from a layer record (disort.f:2846-2882)
+template <int n>
+__device__ __forceinline__ void gc_row_scaled(const double *rec, int r, bool bottom, double *out)
+{
+    const bool up = r >= n;
+    const int i = up ? r - n : n - 1 - r;
+    const double *gp = rec + FastLayout<n>::off_gp + i * n;
+    const double *gm = rec + FastLayout<n>::off_gm + i * n;
+    const double *ek = rec + FastLayout<n>::off_ek;
+#pragma unroll
+    for (int j = 0; j < n; j++) {
+        const double p = gp[j], m = gm[j], e = ek[j];
+        const double plus = up ? p : m;      // column n+j  (+k_j)
+        const double minus = up ? -m : -p;   // column n-1-j (-k_j)
+        out[n + j] = bottom ? plus * e : plus;
+        out[n - 1 - j] = bottom ? minus : minus * e;
+    }
+}
+
+template <int n>
+__global__ void __launch_bounds__(128)
+disort_fast_kernel(const LaunchArgs a)
+{
+    using FL = FastLayout<n>;
+    constexpr int N = 2 * n, C = 2 * N + 1, R = n + N, TASKS = 32 / n;
+    const int L = a.d.nlyr;
+    const int NT = a.d.ntau > 0 ? a.d.ntau : L + 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+    const int ldp = a.d.nmom + 1;
+    extern __shared__ double smem_fast[];
+    double *cmu = smem_fast, *cwt = cmu + n, *csq = cwt + n, *cdinv = csq + n, *cylm = cdinv + n;
+    double *wsm = smem_fast + FL::cta + (size_t)warp * FL::warp_doubles(L, NT);
+    double *y0 = wsm, *taucpr = y0 + N, *tauc = taucpr + (L + 1), *pk = tauc + (L + 1);
+    int *layru = (int *)(pk + (L + 1));
+    double *tsm_base = pk + (L + 1) + (NT + 1) / 2;
+
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        double mu = a.quad[i], wt = a.quad[n + i];
+        cmu[i] = mu; cwt[i] = wt; csq[i] = sqrt(wt / mu); cdinv[i] = 1.0 / sqrt(wt * mu);
+    }
+    for (int e = threadIdx.x; e < N * n; e += blockDim.x) cylm[e] = a.ylmc[e];
+    __syncthreads();
+
+    const int slot = blockIdx.x * warps + warp;
+    double *scr = a.scratch + (size_t)slot * a.slot_stride;
+    double *recs = scr;                        // [L][rec]
+    double *ublk = scr + (size_t)L * FL::rec;  // [L][N][urow]
+    const int g = lane % n, task = lane / n;
+    double *tsm = tsm_base + (size_t)task * FL::task;
+
+    for (;;) {
+        int bin = 0;
+        if (lane == 0) bin = atomicAdd(a.work_counter, 1);
+        bin = __shfl_sync(FULLMASK, bin, 0);
+        if (bin >= a.d.nbins) break;
+        const sbd_bin bp = a.bins[bin];
+        const double *dtauc = a.dtauc + (size_t)bin * L;
+        const double *ssalb = a.ssalb + (size_t)bin * L;
+        const double *pmom = a.pmom + (size_t)bin * L * ldp;
+        const double fbeam = bp.fbeam, umu0 = bp.umu0, albedo = bp.albedo;
+        const bool plank = bp.plank != 0;
+        double *o_rfldir = a.rfldir ? a.rfldir + (size_t)bin * NT : nullptr;
+        double *o_rfldn = a.rfldn ? a.rfldn + (size_t)bin * NT : nullptr;
+        double *o_flup = a.flup ? a.flup + (size_t)bin * NT : nullptr;
+        double *o_dfdt = a.dfdt ? a.dfdt + (size_t)bin * NT : nullptr;
+        double *o_uavg = a.uavg ? a.uavg + (size_t)bin * NT : nullptr;
+
+        int status = 0;
+        {   // CHEKIN subset (disort.f:4920-5155)
+            int badl = 0;
+            for (int lc = lane; lc < L; lc += 32) {
+                double s = ssalb[lc];
+                if (!(s >= 0.0 && s <= 1.0)) badl = 1;
+                for (int k = 1; k <= a.d.nmom; k++) {
+                    double pm = pmom[(size_t)lc * ldp + k];
+                    if (!(pm >= -1.0 && pm <= 1.0)) badl = 1;
+                }
+            }
+            if (fbeam < 0.0 || (fbeam > 0.0 && !(umu0 > 0.0 && umu0 <= 1.0))) badl = 1;
+            if (!(albedo >= 0.0 && albedo <= 1.0) || bp.fisot < 0.0) badl = 1;
+            if (plank && (bp.wvnmlo < 0.0 || bp.wvnmhi <= bp.wvnmlo || bp.temis < 0.0 ||
+                          bp.temis > 1.0 || bp.btemp < 0.0 || bp.ttemp < 0.0)) badl = 1;
+            if (__any_sync(FULLMASK, badl)) status = SBD_BIN_BAD_INPUT;
+            int clash = 0;
+            if (fbeam > 0.0 && lane < n && fabs(umu0 - cmu[lane]) / umu0 < 1.e-4) clash = 1;
+            if (!status && __any_sync(FULLMASK, clash)) status = SBD_BIN_ANGLE_CLASH;
+        }
+        int ncut = L, lyrcut = 0;
+        if (lane == 0) {   // SETDIS prologue (disort.f:2546-2605)
+            double tc = 0.0, tp = 0.0, abstau = 0.0;
+            tauc[0] = 0.0; taucpr[0] = 0.0;
+            for (int lc = 0; lc < L; lc++) {
+                double s = ssalb[lc];
+                if (s == 1.0) s = 1.0 - kDither;
+                double dt = dtauc[lc];
+                tc += dt;
+                if (dt < 0.0) dt = 0.0;
+                if (abstau < 10.0) ncut = lc + 1;
+                abstau += (1. - s) * dt;
+                double f = pmom[(size_t)lc * ldp + N];
+                tp += (1. - f * s) * dt;
+                tauc[lc + 1] = tc; taucpr[lc + 1] = tp;
+            }
+            lyrcut = (abstau >= 10.0 && !plank && L > 1);
+            if (!lyrcut) ncut = L;
+        }
+        ncut = __shfl_sync(FULLMASK, ncut, 0);
+        lyrcut = __shfl_sync(FULLMASK, lyrcut, 0);
+        __syncwarp();
+        int badtau = 0;
+        for (int lu = lane; lu < NT; lu += 32) {
+            double ut = a.d.ntau > 0 ? a.utau[(size_t)bin * NT + lu] : tauc[lu];
+            if (a.d.ntau > 0 && fabs(ut - tauc[L]) <= 1.e-4) ut = tauc[L];
+            if (a.d.ntau > 0 && !(ut >= 0.0 && ut <= tauc[L])) badtau = 1;
+            int lc;
+            for (lc = 1; lc <= L; lc++)
+                if (ut >= tauc[lc - 1] && ut <= tauc[lc]) break;
+            if (lc > L) lc = L;
+            layru[lu] = lc;
+        }
+        if (__any_sync(FULLMASK, badtau)) status = SBD_BIN_BAD_INPUT;
+        double tplank = 0.0, bplank = 0.0;
+        if (plank && !status) {
+            const double *tp = a.temper + (size_t)bp.col * (L + 1);
+            for (int lev = lane; lev <= L; lev += 32) pk[lev] = plkavg_dev(bp.wvnmlo, bp.wvnmhi, tp[lev]);
+            tplank = bp.temis * plkavg_dev(bp.wvnmlo, bp.wvnmhi, bp.ttemp);
+            bplank = plkavg_dev(bp.wvnmlo, bp.wvnmhi, bp.btemp);
+        }
+        if (lane == 0 && fbeam > 0.0) {   // Y_l^0(-mu0), LEPOLY m = 0
+            double x = -umu0;
+            y0[0] = 1.0; y0[1] = x;
+            for (int l = 2; l < N; l++) y0[l] = ((2 * l - 1) * x * y0[l - 1] - (l - 1) * y0[l - 2]) / l;
+        }
+        for (int lu = lane; lu < NT; lu += 32) {
+            if (o_rfldir) o_rfldir[lu] = 0.0;
+            if (o_rfldn) o_rfldn[lu] = 0.0;
+            if (o_flup) o_flup[lu] = 0.0;
+            if (o_dfdt) o_dfdt[lu] = 0.0;
+            if (o_uavg) o_uavg[lu] = 0.0;
+        }
+        __syncwarp();
+
+        // ===================== phase 1 =====================================
+        if (!status) {
+            for (int lc0 = 0; lc0 < ncut; lc0 += TASKS) {
+                int lc = lc0 + task;
+                const bool active = lc < ncut;
+                if (!active) lc = ncut - 1;
+                int st = phase1_layers<n>(dtauc, ssalb, pmom, ldp, lc, active, 0, fbeam, umu0, plank,
+                                          1.0, cmu, csq, cdinv, cylm, y0, taucpr, pk, tsm,
+                                          recs + (size_t)lc * FL::rec, g);
+                if (__any_sync(FULLMASK, st != 0)) { status = SBD_BIN_EIG_FAIL; break; }
+            }
+        }
+        __syncwarp();
+        __threadfence_block();
+
+        // ===================== phase 2: downward elimination ================
+        // lane = matrix row.  Rows not yet used as pivots are "live".
+        double w[C];
+        unsigned live = 0;          // rows currently holding an equation
+        if (!status) {
+            // top boundary rows on lanes 0..n-1 (disort.f:2887-2915, :3547-3550)
+#pragma unroll
+            for (int c = 0; c < C; c++) w[c] = 0.0;
+            if (lane < n) {
+                gc_row_scaled<n>(recs, lane, false, w);
+                w[2 * N] = bp.fisot + tplank - recs[FL::off_zz + lane] - recs[FL::off_zp0 + lane];
+            }
+            live = (1u << n) - 1u;
+            for (int lc = 0; lc < ncut; lc++) {
+                const bool last = (lc == ncut - 1);
+                const double *rc = recs + (size_t)lc * FL::rec;
+                const double tb = taucpr[lc + 1];
+                const double eb = (fbeam > 0.0) ? exp(-tb / umu0) : 0.0;
+                // free lanes take the new equations: N interface rows, or n bottom rows
+                const unsigned freem = ~live & ((R >= 32) ? 0xffffffffu : ((1u << R) - 1u));
+                const int rank = __popc(freem & ((1u << lane) - 1u));
+                const int nnew = last ? n : N;
+                const bool isnew = ((freem >> lane) & 1u) && rank < nnew;
+                if (isnew) {
+                    if (!last) {
+                        const double *rn = rc + FL::rec;
+                        const int r = rank;
+                        gc_row_scaled<n>(rc, r, true, w);
+                        double tmp[N];
+                        gc_row_scaled<n>(rn, r, false, tmp);
+#pragma unroll
+                        for (int j = 0; j < N; j++) w[N + j] = -tmp[j];
+                        w[2 * N] = (rn[FL::off_zz + r] - rc[FL::off_zz + r]) * eb +
+                                   rn[FL::off_zp0 + r] - rc[FL::off_zp0 + r] +
+                                   (rn[FL::off_xr + 1] - rc[FL::off_xr + 1]) * tb;
+                    } else {
+                        // bottom boundary, Lambertian m = 0 (disort.f:2919-2990, :3552-3578)
+                        const int r = n + rank;
+                        const double xr1 = rc[FL::off_xr + 1];
+                        gc_row_scaled<n>(rc, r, true, w);
+                        double rhs = -rc[FL::off_zz + r] * eb - rc[FL::off_zp0 + r] - xr1 * tb;
+                        if (!lyrcut) {
+                            double refl[N];
+#pragma unroll
+                            for (int j = 0; j < N; j++) refl[j] = 0.0;
+                            double rsum = 0.0;
+                            for (int k = 0; k < n; k++) {
+                                double tmp[N];
+                                gc_row_scaled<n>(rc, n - 1 - k, true, tmp);
+                                const double wm = cwt[k] * cmu[k];
+#pragma unroll
+                                for (int j = 0; j < N; j++) refl[j] = fma(wm, tmp[j], refl[j]);
+                                rsum = fma(wm, rc[FL::off_zz + n - 1 - k] * eb + rc[FL::off_zp0 + n - 1 - k] + xr1 * tb, rsum);
+                            }
+#pragma unroll
+                            for (int j = 0; j < N; j++) w[j] = fma(-2.0 * albedo, refl[j], w[j]);
+                            rhs += 2.0 * albedo * rsum + albedo * umu0 * fbeam / kPiRef * eb +
+                                   (1.0 - albedo) * bplank;
+                        }
+#pragma unroll
+                        for (int j = 0; j < N; j++) w[N + j] = 0.0;
+                        w[2 * N] = rhs;
+                    }
+                }
+                unsigned act = live | __ballot_sync(FULLMASK, isnew);
+                // eliminate the N columns of layer lc
+                int mycol = -1;     // which pivot column this lane's row became
+#pragma unroll
+                for (int j = 0; j < N; j++) {
+                    const bool cand = (act >> lane) & 1u;
+                    const double av = cand ? fabs(w[j]) : -1.0;
+                    // pivot: largest |a| by high word (any near-maximal pivot is as stable)
+                    int hi = cand ? __double2hiint(av) : -1;
+                    int mx = __reduce_max_sync(FULLMASK, hi);
+                    unsigned who = __ballot_sync(FULLMASK, hi == mx && cand);
+                    if (mx <= 0 || who == 0) { status = SBD_BIN_SINGULAR; }
+                    const int pl = __ffs(who) - 1;
+                    const double pj = __shfl_sync(FULLMASK, w[j], pl >= 0 ? pl : 0);
+                    const double rp = 1.0 / pj;
+                    const bool ispiv = (lane == pl);
+                    const double mlt = (cand && !ispiv) ? w[j] * rp : 0.0;
+#pragma unroll
+                    for (int c = j + 1; c < C; c++) {
+                        const double pc = __shfl_sync(FULLMASK, w[c], pl >= 0 ? pl : 0);
+                        w[c] = fma(-mlt, pc, w[c]);
+                    }
+                    if (ispiv) mycol = j;
+                    act &= ~(1u << (pl >= 0 ? pl : 0));
+                }
+                if (status) break;
+                // pivot rows -> scratch (row j = pivot column j)
+                if (mycol >= 0) {
+                    double *u = ublk + ((size_t)lc * N + mycol) * FL::urow;
+#pragma unroll
+                    for (int c = 0; c < C; c++) u[c] = w[c];
+                }
+                live = act;      // the n rows that were never pivots carry over
+                if (!last && ((live >> lane) & 1u)) {
+#pragma unroll
+                    for (int j = 0; j < N; j++) { w[j] = w[N + j]; w[N + j] = 0.0; }
+                }
+            }
+        }
+        __syncwarp();
+        __threadfence_block();
+
+        // ===================== phase 3: back substitution + fluxes ===========
+        if (!status) {
+            double xs[N];          // solution of the layer below (uniform)
+#pragma unroll
+            for (int j = 0; j < N; j++) xs[j] = 0.0;
+            for (int lc = ncut - 1; lc >= 0; lc--) {
+                const double *rc = recs + (size_t)lc * FL::rec;
+                double acc = 0.0, dinv = 1.0;
+                double ur[N];      // row `lane` of the upper triangle
+#pragma unroll
+                for (int j = 0; j < N; j++) ur[j] = 0.0;
+                if (lane < N) {
+                    const double *u = ublk + ((size_t)lc * N + lane) * FL::urow;
+                    acc = u[2 * N];
+#pragma unroll
+                    for (int j = 0; j < N; j++) acc = fma(-u[N + j], xs[j], acc);
+#pragma unroll
+                    for (int j = 0; j < N; j++) ur[j] = u[j];
+                }
+#pragma unroll
+                for (int j = 0; j < N; j++) if (j == lane) dinv = 1.0 / ur[j];
+#pragma unroll
+                for (int c = N - 1; c >= 0; c--) {
+                    const double xc = __shfl_sync(FULLMASK, acc * dinv, c);
+                    xs[c] = xc;
+                    if (lane < c) acc = fma(-ur[c], xc, acc);
+                }
+                // ---- fluxes at the levels living in this layer (FLUXES, disort.f:1780) ----
+                for (int lu = 0; lu < NT; lu++) {
+                    if (layru[lu] != lc + 1) continue;
+                    double ut = a.d.ntau > 0 ? a.utau[(size_t)bin * NT + lu] : tauc[lu];
+                    if (a.d.ntau > 0 && fabs(ut - tauc[L]) <= 1.e-4) ut = tauc[L];
+                    double ss = ssalb[lc]; if (ss == 1.0) ss = 1.0 - kDither;
+                    const double f = pmom[(size_t)lc * ldp + N];
+                    const double utp = taucpr[lc] + (1. - ss * f) * (ut - tauc[lc]);
+                    const double xr0 = rc[FL::off_xr], xr1 = rc[FL::off_xr + 1];
+                    double fact = 0.0, dirint = 0.0, fldir = 0.0, rfldir = 0.0;
+                    if (fbeam > 0.0) {
+                        fact = exp(-utp / umu0);
+                        dirint = fbeam * fact;
+                        fldir = umu0 * (fbeam * fact);
+                        rfldir = umu0 * fbeam * exp(-ut / umu0);
+                    }
+                    // lanes 0..n-1: upward direction i, lanes n..N-1: downward direction i
+                    double uval = 0.0, wgt = 0.0, wm = 0.0;
+                    if (lane < N) {
+                        const bool up = lane < n;
+                        const int i = up ? lane : lane - n;
+                        const double *gp = rc + FL::off_gp + i * n, *gm = rc + FL::off_gm + i * n;
+                        const bool atbot = (a.d.ntau == 0 && lu == lc + 1);
+                        const bool attop = (a.d.ntau == 0 && lu == lc);
+                        double s = 0.0;
+#pragma unroll
+                        for (int j = 0; j < n; j++) {
+                            const double k = rc[FL::off_kk + j], e = rc[FL::off_ek + j];
+                            double ep, em;     // exp(-k(t - t_top)), exp(-k(t_bot - t))
+                            if (atbot) { ep = e; em = 1.0; }
+                            else if (attop) { ep = 1.0; em = e; }
+                            else { ep = exp(-k * (utp - taucpr[lc])); em = exp(-k * (taucpr[lc + 1] - utp)); }
+                            const double aj = xs[n + j] * ep, bj = xs[n - 1 - j] * em;
+                            s += up ? (gp[j] * aj - gm[j] * bj) : (gm[j] * aj - gp[j] * bj);
+                        }
+                        const int r = up ? n + i : n - 1 - i;
+                        uval = s + rc[FL::off_zz + r] * fact + rc[FL::off_zp0 + r] + xr1 * utp;
+                        wgt = cwt[i]; wm = cwt[i] * cmu[i];
+                    }
+                    double fu = (lane < n) ? wm * uval : 0.0;
+                    double fd = (lane >= n && lane < N) ? wm * uval : 0.0;
+                    double av = wgt * uval;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        fu += __shfl_xor_sync(FULLMASK, fu, o);
+                        fd += __shfl_xor_sync(FULLMASK, fd, o);
+                        av += __shfl_xor_sync(FULLMASK, av, o);
+                    }
+                    if (lane == 0) {
+                        const double pi = kPiRef;
+                        const double flup = 2. * pi * fu, fldn = 2. * pi * fd;
+                        const double fdntot = fldn + fldir;
+                        const double uavg = (2. * pi * av + dirint) / (4. * pi);
+                        const double plsorc = xr0 + xr1 * utp;
+                        if (o_rfldir) o_rfldir[lu] = rfldir;
+                        if (o_rfldn) o_rfldn[lu] = fdntot - rfldir;
+                        if (o_flup) o_flup[lu] = flup;
+                        if (o_uavg) o_uavg[lu] = uavg;
+                        if (o_dfdt) o_dfdt[lu] = (1. - ss) * 4. * pi * (uavg - plsorc);
+                    }
+                }
+            }
+        }
+        if (lane == 0) a.status[bin] = status;
+        __syncwarp();
+    }
+}
+
+// ---- host-side launch helpers ---------------------------------------------
+template <int n>
+static cudaError_t launch_fast_t(const LaunchArgs &a, int warps, int grid, cudaStream_t st)
+{
+    const int L = a.d.nlyr, NT = a.d.ntau > 0 ? a.d.ntau : L + 1;
+    size_t smem = 8 * (FastLayout<n>::cta + (size_t)warps * FastLayout<n>::warp_doubles(L, NT));
+    cudaError_t e = cudaFuncSetAttribute(disort_fast_kernel<n>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    disort_fast_kernel<n><<<grid, warps * 32, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+bool fast_supported(int N) { return N == 4 || N == 8 || N == 16; }
+
+size_t fast_slot_doubles(int N, int L)
+{
+    switch (N) {
+    case 4: return FastLayout<2>::slot_doubles(L);
+    case 8: return FastLayout<4>::slot_doubles(L);
+    case 16: return FastLayout<8>::slot_doubles(L);
+    }
+    return 0;
+}
+
+size_t fast_smem_bytes(int N, int L, int NT, int warps)
+{
+    switch (N) {
+    case 4: return 8 * (FastLayout<2>::cta + (size_t)warps * FastLayout<2>::warp_doubles(L, NT));
+    case 8: return 8 * (FastLayout<4>::cta + (size_t)warps * FastLayout<4>::warp_doubles(L, NT));
+    case 16: return 8 * (FastLayout<8>::cta + (size_t)warps * FastLayout<8>::warp_doubles(L, NT));
+    }
+    return 0;
+}
+
+cudaError_t launch_fast(const LaunchArgs &a, int warps, int grid, cudaStream_t st)
+{
+    switch (a.d.nstr) {
+    case 4: return launch_fast_t<2>(a, warps, grid, st);
+    case 8: return launch_fast_t<4>(a, warps, grid, st);
+    case 16: return launch_fast_t<8>(a, warps, grid, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace sbd

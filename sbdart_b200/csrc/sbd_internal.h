@@ -62,4 +62,10 @@ int generic_pick_warps(int N, int L, int NT, size_t smem_limit);
 cudaError_t launch_generic(const LaunchArgs &a, int warps, int grid,
                            cudaStream_t st);
 
+// register-resident kernel for NSTR in {4, 8, 16} (sbd_fast.cu)
+bool fast_supported(int N);
+size_t fast_slot_doubles(int N, int L);
+size_t fast_smem_bytes(int N, int L, int NT, int warps);
+cudaError_t launch_fast(const LaunchArgs &a, int warps, int grid, cudaStream_t st);
+
 }  // namespace sbd
