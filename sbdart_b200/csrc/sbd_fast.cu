@@ -50,13 +50,28 @@ struct FastLayout {
     static constexpr int task = N + 4 * n * n + 4 * n;     // gl, K, L, G1, G2, vectors
     __host__ __device__ static size_t warp_doubles(int L, int NT)
     {
-        return (size_t)N + 3 * (L + 1) + (NT + 1) / 2 + (size_t)tasks * task + 2;
+        // pivot-row double buffer, y0, taucpr/tauc/pk(+2 boundary temps), prologue
+        // work, level map, per-task areas; kept even for 16-byte alignment
+        size_t d = (size_t)4 * (N + 1) + N + 3 * (L + 1) + 2 + 3 * L + (NT + 1) / 2 +
+                   (size_t)tasks * task;
+        return (d + 1) & ~(size_t)1;
     }
 };
 
 __device__ __forceinline__ double shfl_d(double v, int src, int width)
 {
     return __shfl_sync(FULLMASK, v, src, width);
+}
+
+// 1/x to ~1 ulp without the IEEE slow paths of the division operator:
+// MUFU.RCP64H seed + two Newton steps (x must be normal and non-zero).
+__device__ __forceinline__ double fast_rcp(double x)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    y = fma(y, fma(-x, y, 1.0), y);
+    y = fma(y, fma(-x, y, 1.0), y);
+    return y;
 }
 
 // ---------------------------------------------------------------------------
@@ -120,6 +135,7 @@ __device__ __forceinline__ int phase1_layers(
 
     // row Cholesky of both operators: Po~ = L L^T, Pe~ = K K^T (lane g = row g)
     int bad = 0;
+    double rK[n], rL[n];     // reciprocal diagonals of K and L (uniform in the group)
 #pragma unroll
     for (int j = 0; j < n; j++) {
         double nume = pe[j], numo = po[j];
@@ -134,6 +150,7 @@ __device__ __forceinline__ int phase1_layers(
         const double floor_e = 1.0e-30;
         if (!(pive > floor_e)) pive = floor_e;
         const double rie = rsqrt(pive), rio = rsqrt(pivo);
+        rK[j] = rie; rL[j] = rio;
         pe[j] = (g == j) ? pive * rie : ((g > j) ? nume * rie : 0.0);
         po[j] = (g == j) ? pivo * rio : ((g > j) ? numo * rio : 0.0);
     }
@@ -141,8 +158,8 @@ __device__ __forceinline__ int phase1_layers(
     for (int j = 0; j < n; j++) { sK[g * n + j] = pe[j]; sL[g * n + j] = po[j]; }
     __syncwarp();
 
-    // column g of A = K^T L, V = I
-    double a[n], v[n];
+    // column g of A = K^T L
+    double a[n];
     {
         double lcol[n];
 #pragma unroll
@@ -153,11 +170,12 @@ __device__ __forceinline__ int phase1_layers(
 #pragma unroll
             for (int k = i; k < n; k++) acc = fma(sK[k * n + i], lcol[k], acc);
             a[i] = acc;
-            v[i] = (i == g) ? 1.0 : 0.0;
         }
     }
 
-    // one-sided Jacobi, round-robin pairing; columns exchanged by shuffles
+    // One-sided Jacobi, round-robin pairing; partner columns come by shuffle.
+    // Only A is rotated: with A V = U S, the vectors needed downstream are
+    // P = L V = K^-T (A V) and Q = L^-T V = (L L^T)^-1 P, so V is never formed.
     if (n > 1) {
         for (int sweep = 0; sweep < 40; sweep++) {
             int did = 0;
@@ -171,30 +189,27 @@ __device__ __forceinline__ int phase1_layers(
                     if (partner >= n - 1) partner -= n - 1;
                     if (partner >= n - 1) partner -= n - 1;
                 }
-                double pa[n], pv[n];
+                double pa[n];
                 double own2 = 0.0, oth2 = 0.0, gam = 0.0;
 #pragma unroll
                 for (int i = 0; i < n; i++) {
                     pa[i] = shfl_d(a[i], partner, n);
-                    pv[i] = shfl_d(v[i], partner, n);
                     own2 = fma(a[i], a[i], own2);
                     oth2 = fma(pa[i], pa[i], oth2);
                     gam = fma(a[i], pa[i], gam);
                 }
                 const bool lo = g < partner;
                 const double alpha = lo ? own2 : oth2, beta = lo ? oth2 : own2;
-                if (fabs(gam) > 1.0e-14 * sqrt(alpha * beta) && fabs(gam) > 1.0e-300) {
+                if (gam * gam > 1.0e-28 * (alpha * beta) && fabs(gam) > 1.0e-300) {
                     did = 1;
                     const double dl = 0.5 * (beta - alpha);
-                    const double hy = sqrt(fma(dl, dl, gam * gam));
-                    const double t = gam / (dl + (dl >= 0.0 ? hy : -hy));
+                    const double h2 = fma(dl, dl, gam * gam);
+                    const double hy = h2 * rsqrt(h2);
+                    const double t = gam * fast_rcp(dl + (dl >= 0.0 ? hy : -hy));
                     const double cc = rsqrt(fma(t, t, 1.0));
                     const double sn = lo ? -t * cc : t * cc;
 #pragma unroll
-                    for (int i = 0; i < n; i++) {
-                        a[i] = fma(sn, pa[i], cc * a[i]);
-                        v[i] = fma(sn, pv[i], cc * v[i]);
-                    }
+                    for (int i = 0; i < n; i++) a[i] = fma(sn, pa[i], cc * a[i]);
                 }
             }
             if (!__any_sync(FULLMASK, did)) break;
@@ -207,21 +222,31 @@ __device__ __forceinline__ int phase1_layers(
     for (int i = 0; i < n; i++) s2 = fma(a[i], a[i], s2);
     const double kk = sqrt(s2);
     const double ek = exp(-kk * dtaucp);
-    // column g of P = L V and of Q = L^-T V
+    // column g of P = K^-T a, then Q = L^-T (L^-1 P)
     double P[n], Q[n];
 #pragma unroll
-    for (int i = 0; i < n; i++) {
-        double acc = 0.0;
-#pragma unroll
-        for (int k = 0; k <= i; k++) acc = fma(sL[i * n + k], v[k], acc);
-        P[i] = acc;
-    }
-#pragma unroll
     for (int i = n - 1; i >= 0; i--) {
-        double acc = v[i];
+        double acc = a[i];
 #pragma unroll
-        for (int k = i + 1; k < n; k++) acc = fma(-sL[k * n + i], Q[k], acc);
-        Q[i] = acc / sL[i * n + i];
+        for (int k = i + 1; k < n; k++) acc = fma(-sK[k * n + i], P[k], acc);
+        P[i] = acc * rK[i];
+    }
+    {
+        double y[n];
+#pragma unroll
+        for (int i = 0; i < n; i++) {
+            double acc = P[i];
+#pragma unroll
+            for (int k = 0; k < i; k++) acc = fma(-sL[i * n + k], y[k], acc);
+            y[i] = acc * rL[i];
+        }
+#pragma unroll
+        for (int i = n - 1; i >= 0; i--) {
+            double acc = y[i];
+#pragma unroll
+            for (int k = i + 1; k < n; k++) acc = fma(-sL[k * n + i], Q[k], acc);
+            Q[i] = acc * rL[i];
+        }
     }
     // G+ - G- = D^-1 Q ; G+ + G- = -D^-1 P / k   (disort.f:3273-3301)
     const double rk = 1.0 / kk;
@@ -272,7 +297,7 @@ __device__ __forceinline__ int phase1_layers(
         double cj = 0.0;                                    // (P^T r)_g / (1/mu0^2 - k^2)
 #pragma unroll
         for (int i = 0; i < n; i++) cj = fma(P[i], sv[2 * n + i], cj);
-        cj = cj / (rmu0 * rmu0 - s2);
+        cj = cj * fast_rcp(rmu0 * rmu0 - s2);
         sv[3 * n + g] = cj;
         sv[g] = cj * kk;
         __syncwarp();
@@ -296,17 +321,17 @@ __device__ __forceinline__ int phase1_layers(
         double y[n], z[n];
 #pragma unroll
         for (int i = 0; i < n; i++) {
-            double acc = 1.0 / cdinv[i];
+            double acc = cmu[i] * csq[i];      // D_i = sqrt(w mu) = mu sqrt(w/mu)
 #pragma unroll
             for (int k = 0; k < i; k++) acc = fma(-sL[i * n + k], y[k], acc);
-            y[i] = acc / sL[i * n + i];
+            y[i] = acc * rL[i];
         }
 #pragma unroll
         for (int i = n - 1; i >= 0; i--) {
             double acc = y[i];
 #pragma unroll
             for (int k = i + 1; k < n; k++) acc = fma(-sL[k * n + i], z[k], acc);
-            z[i] = acc / sL[i * n + i];
+            z[i] = acc * rL[i];
             if (i == g) q = cdinv[i] * z[i];
         }
     }
@@ -342,7 +367,7 @@ __device__ __forceinline__ void gc_row_scaled(const double *rec, int r, bool bot
 }
 
 template <int n>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
 disort_fast_kernel(const LaunchArgs a)
 {
     using FL = FastLayout<n>;
@@ -354,9 +379,11 @@ disort_fast_kernel(const LaunchArgs a)
     extern __shared__ double smem_fast[];
     double *cmu = smem_fast, *cwt = cmu + n, *csq = cwt + n, *cdinv = csq + n, *cylm = cdinv + n;
     double *wsm = smem_fast + FL::cta + (size_t)warp * FL::warp_doubles(L, NT);
-    double *y0 = wsm, *taucpr = y0 + N, *tauc = taucpr + (L + 1), *pk = tauc + (L + 1);
-    int *layru = (int *)(pk + (L + 1));
-    double *tsm_base = pk + (L + 1) + (NT + 1) / 2;
+    double2 *prow2 = reinterpret_cast<double2 *>(wsm);          // 2 x (N+1) pairs, 16-byte aligned
+    double *y0 = wsm + 4 * (N + 1), *taucpr = y0 + N, *tauc = taucpr + (L + 1), *pk = tauc + (L + 1);
+    double *lw = pk + (L + 3);                                   // 3 x L prologue work values
+    int *layru = (int *)(lw + 3 * L);
+    double *tsm_base = lw + 3 * L + (NT + 1) / 2;
 
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         double mu = a.quad[i], wt = a.quad[n + i];
@@ -409,20 +436,27 @@ disort_fast_kernel(const LaunchArgs a)
             if (fbeam > 0.0 && lane < n && fabs(umu0 - cmu[lane]) / umu0 < 1.e-4) clash = 1;
             if (!status && __any_sync(FULLMASK, clash)) status = SBD_BIN_ANGLE_CLASH;
         }
-        int ncut = L, lyrcut = 0;
-        if (lane == 0) {   // SETDIS prologue (disort.f:2546-2605)
+        int ncut = L, lyrcut = 0, monotone = 1;
+        // SETDIS prologue (disort.f:2546-2605): lanes fetch the per-layer terms,
+        // lane 0 accumulates them in the reference's order
+        for (int lc = lane; lc < L; lc += 32) {
+            double s = ssalb[lc];
+            if (s == 1.0) s = 1.0 - kDither;
+            const double dtr = dtauc[lc];
+            const double dt = dtr < 0.0 ? 0.0 : dtr;
+            const double f = pmom[(size_t)lc * ldp + N];
+            lw[lc] = dtr; lw[L + lc] = (1. - s) * dt; lw[2 * L + lc] = (1. - f * s) * dt;
+        }
+        __syncwarp();
+        if (lane == 0) {
             double tc = 0.0, tp = 0.0, abstau = 0.0;
             tauc[0] = 0.0; taucpr[0] = 0.0;
             for (int lc = 0; lc < L; lc++) {
-                double s = ssalb[lc];
-                if (s == 1.0) s = 1.0 - kDither;
-                double dt = dtauc[lc];
-                tc += dt;
-                if (dt < 0.0) dt = 0.0;
+                if (lw[lc] < 0.0) monotone = 0;
+                tc += lw[lc];
                 if (abstau < 10.0) ncut = lc + 1;
-                abstau += (1. - s) * dt;
-                double f = pmom[(size_t)lc * ldp + N];
-                tp += (1. - f * s) * dt;
+                abstau += lw[L + lc];
+                tp += lw[2 * L + lc];
                 tauc[lc + 1] = tc; taucpr[lc + 1] = tp;
             }
             lyrcut = (abstau >= 10.0 && !plank && L > 1);
@@ -430,6 +464,8 @@ disort_fast_kernel(const LaunchArgs a)
         }
         ncut = __shfl_sync(FULLMASK, ncut, 0);
         lyrcut = __shfl_sync(FULLMASK, lyrcut, 0);
+        monotone = __shfl_sync(FULLMASK, monotone, 0);
+        const bool fastmap = (a.d.ntau == 0) && monotone;
         __syncwarp();
         int badtau = 0;
         for (int lu = lane; lu < NT; lu += 32) {
@@ -437,18 +473,27 @@ disort_fast_kernel(const LaunchArgs a)
             if (a.d.ntau > 0 && fabs(ut - tauc[L]) <= 1.e-4) ut = tauc[L];
             if (a.d.ntau > 0 && !(ut >= 0.0 && ut <= tauc[L])) badtau = 1;
             int lc;
-            for (lc = 1; lc <= L; lc++)
-                if (ut >= tauc[lc - 1] && ut <= tauc[lc]) break;
-            if (lc > L) lc = L;
+            if (fastmap && lu >= 1 && tauc[lu - 1] < ut) {
+                lc = lu;          // no earlier layer can contain this boundary
+            } else {
+                for (lc = 1; lc <= L; lc++)
+                    if (ut >= tauc[lc - 1] && ut <= tauc[lc]) break;
+                if (lc > L) lc = L;
+            }
             layru[lu] = lc;
         }
         if (__any_sync(FULLMASK, badtau)) status = SBD_BIN_BAD_INPUT;
         double tplank = 0.0, bplank = 0.0;
         if (plank && !status) {
+            // one list: L+1 level temperatures, then TTEMP, BTEMP (disort.f:556-571)
             const double *tp = a.temper + (size_t)bp.col * (L + 1);
-            for (int lev = lane; lev <= L; lev += 32) pk[lev] = plkavg_dev(bp.wvnmlo, bp.wvnmhi, tp[lev]);
-            tplank = bp.temis * plkavg_dev(bp.wvnmlo, bp.wvnmhi, bp.ttemp);
-            bplank = plkavg_dev(bp.wvnmlo, bp.wvnmhi, bp.btemp);
+            for (int lev = lane; lev <= L + 2; lev += 32) {
+                const double t = lev <= L ? tp[lev] : (lev == L + 1 ? bp.ttemp : bp.btemp);
+                pk[lev] = plkavg_dev(bp.wvnmlo, bp.wvnmhi, t);
+            }
+            __syncwarp();
+            tplank = bp.temis * pk[L + 1];
+            bplank = pk[L + 2];
         }
         if (lane == 0 && fbeam > 0.0) {   // Y_l^0(-mu0), LEPOLY m = 0
             double x = -umu0;
@@ -481,12 +526,12 @@ disort_fast_kernel(const LaunchArgs a)
 
         // ===================== phase 2: downward elimination ================
         // lane = matrix row.  Rows not yet used as pivots are "live".
-        double w[C];
+        double w[C + 1];            // +1: pad so that columns pair up for 16-byte moves
         unsigned live = 0;          // rows currently holding an equation
         if (!status) {
             // top boundary rows on lanes 0..n-1 (disort.f:2887-2915, :3547-3550)
 #pragma unroll
-            for (int c = 0; c < C; c++) w[c] = 0.0;
+            for (int c = 0; c < C + 1; c++) w[c] = 0.0;
             if (lane < n) {
                 gc_row_scaled<n>(recs, lane, false, w);
                 w[2 * N] = bp.fisot + tplank - recs[FL::off_zz + lane] - recs[FL::off_zp0 + lane];
@@ -556,24 +601,33 @@ disort_fast_kernel(const LaunchArgs a)
                     unsigned who = __ballot_sync(FULLMASK, hi == mx && cand);
                     if (mx <= 0 || who == 0) { status = SBD_BIN_SINGULAR; }
                     const int pl = __ffs(who) - 1;
-                    const double pj = __shfl_sync(FULLMASK, w[j], pl >= 0 ? pl : 0);
-                    const double rp = 1.0 / pj;
                     const bool ispiv = (lane == pl);
+                    // the pivot row travels through shared memory (double-buffered by
+                    // column parity): 16-byte stores by one lane, broadcast 16-byte loads
+                    double2 *pb = prow2 + (j & 1) * (N + 1);
+                    if (ispiv) {
+#pragma unroll
+                        for (int c2 = j / 2; c2 <= N; c2++) pb[c2] = make_double2(w[2 * c2], w[2 * c2 + 1]);
+                        mycol = j;
+                    }
+                    __syncwarp();
+                    const double2 pjp = pb[j / 2];
+                    const double rp = fast_rcp((j & 1) ? pjp.y : pjp.x);
                     const double mlt = (cand && !ispiv) ? w[j] * rp : 0.0;
 #pragma unroll
-                    for (int c = j + 1; c < C; c++) {
-                        const double pc = __shfl_sync(FULLMASK, w[c], pl >= 0 ? pl : 0);
-                        w[c] = fma(-mlt, pc, w[c]);
+                    for (int c2 = (j + 1) / 2; c2 <= N; c2++) {
+                        const double2 p = pb[c2];
+                        if (2 * c2 > j) w[2 * c2] = fma(-mlt, p.x, w[2 * c2]);
+                        if (2 * c2 + 1 < C) w[2 * c2 + 1] = fma(-mlt, p.y, w[2 * c2 + 1]);
                     }
-                    if (ispiv) mycol = j;
                     act &= ~(1u << (pl >= 0 ? pl : 0));
                 }
                 if (status) break;
                 // pivot rows -> scratch (row j = pivot column j)
                 if (mycol >= 0) {
-                    double *u = ublk + ((size_t)lc * N + mycol) * FL::urow;
+                    double2 *u2 = reinterpret_cast<double2 *>(ublk + ((size_t)lc * N + mycol) * FL::urow);
 #pragma unroll
-                    for (int c = 0; c < C; c++) u[c] = w[c];
+                    for (int c2 = 0; c2 <= N; c2++) u2[c2] = make_double2(w[2 * c2], w[2 * c2 + 1]);
                 }
                 live = act;      // the n rows that were never pivots carry over
                 if (!last && ((live >> lane) & 1u)) {
@@ -590,22 +644,32 @@ disort_fast_kernel(const LaunchArgs a)
             double xs[N];          // solution of the layer below (uniform)
 #pragma unroll
             for (int j = 0; j < N; j++) xs[j] = 0.0;
+            int lu_next = NT - 1;  // levels are visited bottom-up when the map is monotone
             for (int lc = ncut - 1; lc >= 0; lc--) {
                 const double *rc = recs + (size_t)lc * FL::rec;
-                double acc = 0.0, dinv = 1.0;
+                double acc = 0.0, diag = 1.0;
                 double ur[N];      // row `lane` of the upper triangle
 #pragma unroll
                 for (int j = 0; j < N; j++) ur[j] = 0.0;
                 if (lane < N) {
-                    const double *u = ublk + ((size_t)lc * N + lane) * FL::urow;
-                    acc = u[2 * N];
+                    const double2 *u2 = reinterpret_cast<const double2 *>(
+                        ublk + ((size_t)lc * N + lane) * FL::urow);
+                    acc = u2[N].x;
 #pragma unroll
-                    for (int j = 0; j < N; j++) acc = fma(-u[N + j], xs[j], acc);
+                    for (int j2 = 0; j2 < n; j2++) {
+                        const double2 t = u2[n + j2];
+                        acc = fma(-t.x, xs[2 * j2], acc);
+                        acc = fma(-t.y, xs[2 * j2 + 1], acc);
+                    }
 #pragma unroll
-                    for (int j = 0; j < N; j++) ur[j] = u[j];
+                    for (int j2 = 0; j2 < n; j2++) {
+                        const double2 t = u2[j2];
+                        ur[2 * j2] = t.x; ur[2 * j2 + 1] = t.y;
+                    }
                 }
 #pragma unroll
-                for (int j = 0; j < N; j++) if (j == lane) dinv = 1.0 / ur[j];
+                for (int j = 0; j < N; j++) if (j == lane) diag = ur[j];
+                const double dinv = fast_rcp(diag);
 #pragma unroll
                 for (int c = N - 1; c >= 0; c--) {
                     const double xc = __shfl_sync(FULLMASK, acc * dinv, c);
@@ -613,8 +677,11 @@ disort_fast_kernel(const LaunchArgs a)
                     if (lane < c) acc = fma(-ur[c], xc, acc);
                 }
                 // ---- fluxes at the levels living in this layer (FLUXES, disort.f:1780) ----
-                for (int lu = 0; lu < NT; lu++) {
-                    if (layru[lu] != lc + 1) continue;
+                if (fastmap)
+                    while (lu_next >= 0 && layru[lu_next] > lc + 1) lu_next--;
+                for (int lu = fastmap ? lu_next : NT - 1; lu >= 0; lu--) {
+                    if (layru[lu] != lc + 1) { if (fastmap) break; else continue; }
+                    if (fastmap) lu_next = lu - 1;
                     double ut = a.d.ntau > 0 ? a.utau[(size_t)bin * NT + lu] : tauc[lu];
                     if (a.d.ntau > 0 && fabs(ut - tauc[L]) <= 1.e-4) ut = tauc[L];
                     double ss = ssalb[lc]; if (ss == 1.0) ss = 1.0 - kDither;

@@ -74,3 +74,27 @@ def test_self_test_fluxes_through_c_abi(solver):
     assert abs(got["rfldir"][0, 0] / 1.527286 - 1) < 1e-7
     assert abs(got["rfldn"][0, 0] / 28.372225 - 1) < 1e-7
     assert abs(got["flup"][0, 0] / 152.585284 - 1) < 1e-7
+
+
+@pytest.mark.parametrize("nstr", [4, 16])
+def test_conservative_scattering_layers(solver, nstr):
+    """SSALB == 1 exactly (dithered to 1-DITHER, disort.f:486) in Rayleigh and
+    cloud layers: the near-null eigenvalue k -> 0 is the hardest case for
+    every eigen-solver; fluxes must still agree."""
+    rng = np.random.default_rng(5)
+    B, L, nmom = 48, 33, nstr + 2
+    dtauc = 10.0 ** rng.uniform(-3, 0.3, size=(B, L))
+    ssalb = np.ones((B, L))
+    ssalb[:, ::5] = 1.0 - 10.0 ** rng.uniform(-9, -2, size=(B, len(range(0, L, 5))))
+    pmom = np.zeros((B, L, nmom + 1))
+    pmom[:, :, 0] = 1.0
+    pmom[:, :, 2] = 0.1                                    # Rayleigh
+    cloud = workloads.hg_moments(np.full((B,), 0.85), nmom)
+    pmom[:, 20, :] = cloud
+    dtauc[:, 20] = rng.uniform(1, 30, size=B)
+    bins = sb.make_bins(B, fbeam=1.0, umu0=rng.uniform(0.2, 0.95, B), albedo=rng.uniform(0, 1, B))
+    w = dict(dtauc=dtauc, ssalb=ssalb, pmom=pmom, bins=bins, nstr=nstr, temper=None)
+    got = solver.disort_batch(dtauc, ssalb, pmom, bins, nstr=nstr)
+    ref = oracle_flux(w)
+    assert (ref["status"] == 0).all()
+    assert_close(got, ref, rtol=1e-6, atol_scale=1e-9)
