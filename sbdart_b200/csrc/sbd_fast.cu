@@ -179,8 +179,8 @@ __device__ __forceinline__ int phase1_layers(
     if (n > 1) {
         for (int sweep = 0; sweep < 40; sweep++) {
             int did = 0;
-#pragma unroll
-            for (int r = 0; r < n - 1; r++) {
+#pragma unroll 1
+            for (int r = 0; r < n - 1; r++) {     // not unrolled: keeps the code in the I-cache
                 int partner;
                 if (g == n - 1) partner = r;
                 else if (g == r) partner = n - 1;
@@ -498,7 +498,12 @@ disort_fast_kernel(const LaunchArgs a)
         if (lane == 0 && fbeam > 0.0) {   // Y_l^0(-mu0), LEPOLY m = 0
             double x = -umu0;
             y0[0] = 1.0; y0[1] = x;
-            for (int l = 2; l < N; l++) y0[l] = ((2 * l - 1) * x * y0[l - 1] - (l - 1) * y0[l - 2]) / l;
+            double pm2 = 1.0, pm1 = x;
+#pragma unroll
+            for (int l = 2; l < N; l++) {
+                const double p = ((2 * l - 1) * x * pm1 - (l - 1) * pm2) * (1.0 / l);
+                y0[l] = p; pm2 = pm1; pm1 = p;
+            }
         }
         for (int lu = lane; lu < NT; lu += 32) {
             if (o_rfldir) o_rfldir[lu] = 0.0;
@@ -570,6 +575,7 @@ disort_fast_kernel(const LaunchArgs a)
 #pragma unroll
                             for (int j = 0; j < N; j++) refl[j] = 0.0;
                             double rsum = 0.0;
+#pragma unroll 1
                             for (int k = 0; k < n; k++) {
                                 double tmp[N];
                                 gc_row_scaled<n>(rc, n - 1 - k, true, tmp);
@@ -590,16 +596,19 @@ disort_fast_kernel(const LaunchArgs a)
                 }
                 unsigned act = live | __ballot_sync(FULLMASK, isnew);
                 // eliminate the N columns of layer lc
+                // The window slides: after each column every live row drops its
+                // leading entry, so the current column is always w[0] and ONE copy
+                // of the loop body serves all N columns (I-cache friendly).
                 int mycol = -1;     // which pivot column this lane's row became
-#pragma unroll
+#pragma unroll 1
                 for (int j = 0; j < N; j++) {
                     const bool cand = (act >> lane) & 1u;
-                    const double av = cand ? fabs(w[j]) : -1.0;
+                    const double av = cand ? fabs(w[0]) : -1.0;
                     // pivot: largest |a| by high word (any near-maximal pivot is as stable)
                     int hi = cand ? __double2hiint(av) : -1;
                     int mx = __reduce_max_sync(FULLMASK, hi);
                     unsigned who = __ballot_sync(FULLMASK, hi == mx && cand);
-                    if (mx <= 0 || who == 0) { status = SBD_BIN_SINGULAR; }
+                    if (mx <= 0 || who == 0) { status = SBD_BIN_SINGULAR; break; }
                     const int pl = __ffs(who) - 1;
                     const bool ispiv = (lane == pl);
                     // the pivot row travels through shared memory (double-buffered by
@@ -607,32 +616,36 @@ disort_fast_kernel(const LaunchArgs a)
                     double2 *pb = prow2 + (j & 1) * (N + 1);
                     if (ispiv) {
 #pragma unroll
-                        for (int c2 = j / 2; c2 <= N; c2++) pb[c2] = make_double2(w[2 * c2], w[2 * c2 + 1]);
-                        mycol = j;
+                        for (int c2 = 0; c2 <= N; c2++) pb[c2] = make_double2(w[2 * c2], w[2 * c2 + 1]);
+                        mycol = j;      // this row now rests (entry i = column j+i)
                     }
                     __syncwarp();
-                    const double2 pjp = pb[j / 2];
-                    const double rp = fast_rcp((j & 1) ? pjp.y : pjp.x);
-                    const double mlt = (cand && !ispiv) ? w[j] * rp : 0.0;
+                    if (cand && !ispiv) {
+                        const double2 p0 = pb[0];
+                        const double mlt = w[0] * fast_rcp(p0.x);
+                        w[0] = fma(-mlt, p0.y, w[1]);
 #pragma unroll
-                    for (int c2 = (j + 1) / 2; c2 <= N; c2++) {
-                        const double2 p = pb[c2];
-                        if (2 * c2 > j) w[2 * c2] = fma(-mlt, p.x, w[2 * c2]);
-                        if (2 * c2 + 1 < C) w[2 * c2 + 1] = fma(-mlt, p.y, w[2 * c2 + 1]);
+                        for (int c2 = 1; c2 <= N; c2++) {
+                            const double2 p = pb[c2];
+                            w[2 * c2 - 1] = fma(-mlt, p.x, w[2 * c2]);
+                            w[2 * c2] = fma(-mlt, p.y, w[2 * c2 + 1]);
+                        }
                     }
-                    act &= ~(1u << (pl >= 0 ? pl : 0));
+                    act &= ~(1u << pl);
                 }
                 if (status) break;
-                // pivot rows -> scratch (row j = pivot column j)
+                // pivot rows -> scratch: row j holds columns j..2N at entries 0..2N-j
                 if (mycol >= 0) {
                     double2 *u2 = reinterpret_cast<double2 *>(ublk + ((size_t)lc * N + mycol) * FL::urow);
 #pragma unroll
                     for (int c2 = 0; c2 <= N; c2++) u2[c2] = make_double2(w[2 * c2], w[2 * c2 + 1]);
                 }
-                live = act;      // the n rows that were never pivots carry over
+                live = act;      // the n rows that were never pivots carry over:
+                                 // their next-layer coefficients already sit in w[0..N-1]
                 if (!last && ((live >> lane) & 1u)) {
+                    w[2 * N] = w[N];
 #pragma unroll
-                    for (int j = 0; j < N; j++) { w[j] = w[N + j]; w[N + j] = 0.0; }
+                    for (int j = N; j < 2 * N; j++) w[j] = 0.0;
                 }
             }
         }
@@ -652,20 +665,13 @@ disort_fast_kernel(const LaunchArgs a)
 #pragma unroll
                 for (int j = 0; j < N; j++) ur[j] = 0.0;
                 if (lane < N) {
-                    const double2 *u2 = reinterpret_cast<const double2 *>(
-                        ublk + ((size_t)lc * N + lane) * FL::urow);
-                    acc = u2[N].x;
+                    // stored row `lane`: entry i is column lane+i (see phase 2)
+                    const double *u = ublk + ((size_t)lc * N + lane) * FL::urow - lane;
+                    acc = u[2 * N];
 #pragma unroll
-                    for (int j2 = 0; j2 < n; j2++) {
-                        const double2 t = u2[n + j2];
-                        acc = fma(-t.x, xs[2 * j2], acc);
-                        acc = fma(-t.y, xs[2 * j2 + 1], acc);
-                    }
+                    for (int j = 0; j < N; j++) acc = fma(-u[N + j], xs[j], acc);
 #pragma unroll
-                    for (int j2 = 0; j2 < n; j2++) {
-                        const double2 t = u2[j2];
-                        ur[2 * j2] = t.x; ur[2 * j2 + 1] = t.y;
-                    }
+                    for (int c = 0; c < N; c++) if (c >= lane) ur[c] = u[c];
                 }
 #pragma unroll
                 for (int j = 0; j < N; j++) if (j == lane) diag = ur[j];

@@ -6,6 +6,10 @@
 
 namespace sbd {
 
+// 1/m^4 for the exponential series of PLKAVG (disort.f:5628-5633), m = 1..7
+static __constant__ double kRm4[8] = { 0.0, 1.0, 1.0 / 16.0, 1.0 / 81.0, 1.0 / 256.0,
+                                       1.0 / 625.0, 1.0 / 1296.0, 1.0 / 2401.0 };
+
 // ---- PLKAVG (disort.f:5410-5671), same three regimes --------------------
 static __device__ __forceinline__ double plkf(double x) { return x * x * x / (exp(x) - 1.0); }
 
@@ -52,7 +56,7 @@ static __device__ __noinline__ double plkavg_dev(double wnumlo, double wnumhi, d
             for (int m = 1; m <= mmax; m++) {
                 double mv = m * v[i];
                 exm = ex * exm;
-                s += exm * (6. + mv * (6. + mv * (3. + mv))) / ((double)m * m * m * m);
+                s += exm * (6. + mv * (6. + mv * (3. + mv))) * kRm4[m];   // m <= 7
             }
             d[i] = conc * s;
         }
