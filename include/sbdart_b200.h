@@ -76,6 +76,7 @@ typedef struct sbd_bin {
     double temis;   /* TEMIS  */
     double wvnmlo;  /* WVNMLO */
     double wvnmhi;  /* WVNMHI */
+    double accur;   /* ACCUR  azimuth-series convergence (SBDART passes 0, drt.f:142) */
     int32_t plank;  /* PLANK  */
     int32_t col;    /* row of temper[][] used by this bin                     */
 } sbd_bin;

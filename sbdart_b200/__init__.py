@@ -46,12 +46,12 @@ class SbdBin(C.Structure):
 
     _fields_ = [(k, C.c_double) for k in (
         "fbeam", "umu0", "phi0", "fisot", "albedo", "btemp", "ttemp", "temis",
-        "wvnmlo", "wvnmhi")] + [("plank", C.c_int32), ("col", C.c_int32)]
+        "wvnmlo", "wvnmhi", "accur")] + [("plank", C.c_int32), ("col", C.c_int32)]
 
 
 BIN_DTYPE = np.dtype([(k, "<f8") for k in (
     "fbeam", "umu0", "phi0", "fisot", "albedo", "btemp", "ttemp", "temis",
-    "wvnmlo", "wvnmhi")] + [("plank", "<i4"), ("col", "<i4")])
+    "wvnmlo", "wvnmhi", "accur")] + [("plank", "<i4"), ("col", "<i4")])
 assert BIN_DTYPE.itemsize == C.sizeof(SbdBin)
 
 
@@ -119,11 +119,11 @@ def _f64(a):
 
 
 def make_bins(nbins, *, fbeam=0.0, umu0=1.0, phi0=0.0, fisot=0.0, albedo=0.0, btemp=0.0,
-              ttemp=0.0, temis=0.0, wvnmlo=0.0, wvnmhi=0.0, plank=0, col=0):
+              ttemp=0.0, temis=0.0, wvnmlo=0.0, wvnmhi=0.0, accur=0.0, plank=0, col=0):
     """Array of struct sbd_bin; every argument is a scalar or a length-B array."""
     b = np.zeros(nbins, dtype=BIN_DTYPE)
     for k, v in dict(fbeam=fbeam, umu0=umu0, phi0=phi0, fisot=fisot, albedo=albedo, btemp=btemp,
-                     ttemp=ttemp, temis=temis, wvnmlo=wvnmlo, wvnmhi=wvnmhi, plank=plank,
+                     ttemp=ttemp, temis=temis, wvnmlo=wvnmlo, wvnmhi=wvnmhi, accur=accur, plank=plank,
                      col=col).items():
         b[k] = v
     return b

@@ -227,7 +227,17 @@ extern "C" int sbd_disort_batch_device(sbd_handle *h, const sbd_dims *dims, cons
     if (rc) return rc;
     if (!dtauc || !ssalb || !pmom || !bins || !status) return SBD_ERR_ARG;
     if (dims->ntau > 0 && !utau) return SBD_ERR_ARG;
-    if (dims->numu > 0) return SBD_ERR_UNSUPPORTED;   // radiance path: see sbd_radiance (next)
+    const int NU = dims->numu;
+    if (NU > 0) {
+        // user angles are call-level parameters: HOST arrays even in the device variant
+        if (!umu || !phi || !uu) return SBD_ERR_ARG;
+        for (int iu = 0; iu < NU; iu++) {      // CHEKIN, disort.f:5022-5036
+            if (!(umu[iu] >= -1.0 && umu[iu] <= 1.0) || umu[iu] == 0.0) return SBD_ERR_ARG;
+            if (iu > 0 && umu[iu] < umu[iu - 1]) return SBD_ERR_ARG;
+        }
+        for (int j = 0; j < dims->nphi; j++)
+            if (!(phi[j] >= 0.0 && phi[j] <= 360.0)) return SBD_ERR_ARG;
+    }
     if (dims->nbins == 0) return SBD_SUCCESS;
     if (cudaSetDevice(h->device) != cudaSuccess) return SBD_ERR_CUDA;
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
@@ -239,7 +249,7 @@ extern "C" int sbd_disort_batch_device(sbd_handle *h, const sbd_dims *dims, cons
     if (rc) return rc;
 
     size_t smem_limit = h->smem_optin ? h->smem_optin : 48 * 1024;
-    const bool fast = fast_supported(N) && !getenv("SBD_FORCE_GENERIC");
+    const bool fast = fast_supported(N) && NU == 0 && !getenv("SBD_FORCE_GENERIC");
     int warps, grid;
     size_t slot;
     if (fast) {
@@ -260,7 +270,7 @@ extern "C" int sbd_disort_batch_device(sbd_handle *h, const sbd_dims *dims, cons
         if (cta_per_sm < 1) cta_per_sm = 1;
         if (cta_per_sm * warps > 16) cta_per_sm = 16 / warps > 0 ? 16 / warps : 1;
         grid = h->sm_count * cta_per_sm;
-        slot = generic_slot_doubles(N, L, 0);
+        slot = generic_slot_doubles(N, L, NU);
     }
     int need = (dims->nbins + warps - 1) / warps;
     if (grid > need) grid = need;
@@ -269,10 +279,24 @@ extern "C" int sbd_disort_batch_device(sbd_handle *h, const sbd_dims *dims, cons
     memset(&a, 0, sizeof a);
     a.d = *dims;
     a.dtauc = dtauc; a.ssalb = ssalb; a.pmom = pmom; a.bins = bins; a.temper = temper;
-    a.utau = utau; a.umu = umu; a.phi = phi;
+    a.utau = utau;
+    if (NU > 0) {
+        // Y_l^m at the user cosines for every azimuth mode (LEPOLY, disort.f:608-609)
+        std::vector<double> tab((size_t)N * N * NU + NU + dims->nphi);
+        legendre_table(N, N - 1, NU, umu, tab.data());
+        double *ang = tab.data() + (size_t)N * N * NU;
+        for (int iu = 0; iu < NU; iu++) ang[iu] = umu[iu];
+        for (int j = 0; j < dims->nphi; j++) ang[NU + j] = phi[j];
+        if (h->ylmu.reserve(tab.size() * 8) != cudaSuccess) return SBD_ERR_CUDA;
+        if (cudaMemcpyAsync(h->ylmu.p, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice, st) != cudaSuccess)
+            return SBD_ERR_CUDA;
+        a.ylmu = (const double *)h->ylmu.p;
+        a.umu = a.ylmu + (size_t)N * N * NU;
+        a.phi = a.umu + NU;
+    }
     a.rfldir = rfldir; a.rfldn = rfldn; a.flup = flup; a.dfdt = dfdt; a.uavg = uavg; a.uu = uu;
     a.status = status;
-    a.quad = tb.quad; a.ylmc = tb.ylmc; a.ylmu = nullptr;
+    a.quad = tb.quad; a.ylmc = tb.ylmc;
     a.nslots = grid * warps;
     a.slot_stride = slot;
     a.nmodes = 1;
@@ -296,7 +320,7 @@ extern "C" int sbd_disort_batch(sbd_handle *h, const sbd_dims *dims, const doubl
     int rc = check_dims(dims);
     if (rc) return rc;
     if (!dtauc || !ssalb || !pmom || !bins || !status) return SBD_ERR_ARG;
-    if (dims->numu > 0) return SBD_ERR_UNSUPPORTED;
+    if (dims->numu > 0 && (!umu || !phi || !uu)) return SBD_ERR_ARG;
     if (dims->nbins == 0) return SBD_SUCCESS;
     if (cudaSetDevice(h->device) != cudaSuccess) return SBD_ERR_CUDA;
     cudaStream_t st = h->stream;
@@ -337,18 +361,21 @@ extern "C" int sbd_disort_batch(sbd_handle *h, const sbd_dims *dims, const doubl
     }
     double *o = (double *)h->d_out.p;
     const size_t per = B * NT;
+    const size_t nuu = (size_t)dims->numu * dims->nphi * B * NT;
+    if (nuu) CK(h->d_uu.reserve(nuu * 8));
     rc = sbd_disort_batch_device(h, dims, (const double *)h->d_dtauc.p, (const double *)h->d_ssalb.p,
                                  (const double *)h->d_pmom.p, (const sbd_bin *)h->d_bins.p, d_temper,
-                                 d_utau, nullptr, nullptr, o, o + per, o + 2 * per, o + 3 * per,
-                                 o + 4 * per, nullptr, (int32_t *)h->d_status.p, st);
+                                 d_utau, umu, phi, o, o + per, o + 2 * per, o + 3 * per,
+                                 o + 4 * per, nuu ? (double *)h->d_uu.p : nullptr,
+                                 (int32_t *)h->d_status.p, st);
     if (rc) return rc;
+    if (nuu) CK(cudaMemcpyAsync(uu, h->d_uu.p, nuu * 8, cudaMemcpyDeviceToHost, st));
     double *dst[5] = { rfldir, rfldn, flup, dfdt, uavg };
     for (int k = 0; k < 5; k++)
         if (dst[k]) CK(cudaMemcpyAsync(dst[k], o + k * per, per * 8, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(status, h->d_status.p, B * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
 #undef CK
-    (void)uu; (void)umu; (void)phi;
     return SBD_SUCCESS;
 }
 
@@ -372,8 +399,7 @@ extern "C" void disort_(int *nlyr, double *dtauc, double *ssalb, int *corint, in
                         double *dfdt, double *uavg, double *uu, double *albmed, double *trnmed,
                         size_t header_len)
 {
-    (void)corint; (void)accur; (void)prnt; (void)header; (void)header_len; (void)maxphi;
-    (void)albmed; (void)trnmed; (void)uu; (void)nphi; (void)phi; (void)maxcly;
+    (void)prnt; (void)header; (void)header_len; (void)albmed; (void)trnmed; (void)maxcly;
     std::lock_guard<std::mutex> lock(g_mutex);
     if (!g_handle && sbd_create(&g_handle, 0) != SBD_SUCCESS) {
         fprintf(stderr, "sbdart_b200: disort_: no usable CUDA device\n");
@@ -381,14 +407,23 @@ extern "C" void disort_(int *nlyr, double *dtauc, double *ssalb, int *corint, in
         return;
     }
     const int L = *nlyr, N = *nstr;
-    if (*ibcnd != 0 || !*lamber || !*onlyfl) {   // radiances arrive with the radiance kernel
+    const bool rad = !*onlyfl;
+    // outside the hot path: IBCND=1, BRDF surfaces, intensities at the quadrature
+    // angles (USRANG=F, never used by SBDART) and the CORINT correction when it
+    // would be active (disort.f:2695-2696)
+    if (*ibcnd != 0 || !*lamber || (rad && !*usrang) || (rad && *corint && *fbeam > 0.0)) {
         g_last_status = SBD_ERR_UNSUPPORTED;
+        return;
+    }
+    if (rad && (*numu < 1 || *nphi < 1 || *numu > *maxumu || *nphi > *maxphi)) {
+        g_last_status = SBD_ERR_ARG;
         return;
     }
     sbd_dims d;
     memset(&d, 0, sizeof d);
     d.nbins = 1; d.nlyr = L; d.nstr = N; d.nmom = *nmom; d.ncol = 1;
     d.ntau = *usrtau ? *ntau : 0;
+    if (rad) { d.numu = *numu; d.nphi = *nphi; }
     const int ldp = *maxmom + 1;
     std::vector<double> pm((size_t)L * (*nmom + 1));
     for (int lc = 0; lc < L; lc++) {
@@ -399,15 +434,22 @@ extern "C" void disort_(int *nlyr, double *dtauc, double *ssalb, int *corint, in
     memset(&b, 0, sizeof b);
     b.fbeam = *fbeam; b.umu0 = *umu0; b.phi0 = *phi0; b.fisot = *fisot; b.albedo = *albedo;
     b.btemp = *btemp; b.ttemp = *ttemp; b.temis = *temis; b.wvnmlo = *wvnmlo; b.wvnmhi = *wvnmhi;
-    b.plank = *plank ? 1 : 0; b.col = 0;
+    b.plank = *plank ? 1 : 0; b.col = 0; b.accur = *accur;
     const int NT = *usrtau ? *ntau : L + 1;
     if (NT > *maxulv) { g_last_status = SBD_ERR_ARG; return; }
     int32_t st = 0;
+    std::vector<double> uuc(rad ? (size_t)d.nphi * NT * d.numu : 0);
     int rc = sbd_disort_batch(g_handle, &d, dtauc, ssalb, pm.data(), &b, temper,
-                              *usrtau ? utau : nullptr, nullptr, nullptr, rfldir, rfldn, flup,
-                              dfdt, uavg, nullptr, &st);
+                              *usrtau ? utau : nullptr, rad ? umu : nullptr, rad ? phi : nullptr,
+                              rfldir, rfldn, flup, dfdt, uavg, rad ? uuc.data() : nullptr, &st);
     g_last_status = rc ? rc : st;
     if (rc) return;
+    if (rad)      // UU(IU,LU,J), leading dimensions MAXUMU, MAXULV (disort.f:377)
+        for (int j = 0; j < d.nphi; j++)
+            for (int lu = 0; lu < NT; lu++)
+                for (int iu = 0; iu < d.numu; iu++)
+                    uu[iu + (size_t)*maxumu * (lu + (size_t)*maxulv * j)] =
+                        uuc[((size_t)j * NT + lu) * d.numu + iu];
     // visible argument mutations of the reference
     double tc = 0.0;
     if (!*usrtau) { *ntau = L + 1; utau[0] = 0.0; }

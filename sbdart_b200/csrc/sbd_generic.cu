@@ -42,7 +42,8 @@ __device__ __forceinline__ double warp_sum(double v)
 
 // ---- shared-memory carve-up ----------------------------------------------
 struct CtaShared {          // same for every warp of the CTA
-    double *mu, *wt, *sq, *dinv, *ylm;   // [n] x4, [N*n]
+    double *mu, *wt, *sq, *dinv;         // [n] each
+    const double *ylm;                   // [N*n] Y_l^m(mu_i) of the current azimuth mode
 };
 
 struct WarpShared {
@@ -489,6 +490,221 @@ __device__ int eliminate(double *W, int rows, int C, int ncols, int lane)
     return 0;
 }
 
+// Y_l^m(x) for l = 0..N-1 (zero below l = m): what LEPOLY (disort.f:5286) builds
+// mode by mode, with the diagonal term in closed-chain form.
+__device__ void lepoly_one(int m, int N, double x, double *y)
+{
+    if (m == 0) {
+        y[0] = 1.0;
+        if (N > 1) y[1] = x;
+        for (int l = 2; l < N; l++) y[l] = ((2 * l - 1) * x * y[l - 1] - (l - 1) * y[l - 2]) / l;
+        return;
+    }
+    double d = 1.0;
+    const double s = sqrt(1.0 - x * x);
+    for (int k = 1; k <= m; k++) d = -sqrt((double)(2 * k - 1)) / sqrt((double)(2 * k)) * s * d;
+    for (int l = 0; l < m && l < N; l++) y[l] = 0.0;
+    if (m < N) y[m] = d;
+    if (m + 1 < N) y[m + 1] = sqrt((double)(2 * m + 1)) * x * d;
+    for (int l = m + 2; l < N; l++) {
+        const double t1 = sqrt((double)(l - m)) * sqrt((double)(l + m));
+        const double t2 = sqrt((double)(l - m - 1)) * sqrt((double)(l + m - 1));
+        y[l] = ((2 * l - 1) * x * y[l - 1] - t2 * y[l - 2]) / t1;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// User-angle quantities of one layer for azimuth mode m (reference TERPEV
+// disort.f:3920 and TERPSO disort.f:3980): eigenvectors and particular
+// solutions re-expanded at the user cosines through the Legendre sum.
+// Expects the layer record in buffer set s of shared memory and x_lc in w.xc.
+// Writes GU(iu,col)*LL(col), ZBEAM, Z0U, Z1U into the scratch record.
+// ---------------------------------------------------------------------------
+__device__ void user_terms(const BinCtx &c, const CtaShared &cs, WarpShared &w,
+                           const LayerLayout &ll, double *rec, const double *ylmu_m, int NU,
+                           int lc, int s, double xr0, double xr1, int lane)
+{
+    const int N = c.N, n = c.n, m = c.mazim;
+    double ss = c.ssalb[lc];
+    if (ss == 1.0) ss = 1.0 - kDither;
+    const double f = c.pmom[(size_t)lc * c.ldp + N];
+    const double oprim = ss * (1. - f) / (1. - f * ss);
+    for (int l = lane; l < N; l += 32) {
+        double pm = (l == 0) ? 1.0 : c.pmom[(size_t)lc * c.ldp + l];
+        w.gl[l] = (2 * l + 1) * oprim * (pm - f) / (1. - f);
+    }
+    __syncwarp();
+    // E[l][col] = 0.5 g_l sum_jq w_jq Y_l(mu_jq) EVECC(jq, col)
+    double *E = w.W;
+    for (int e = lane; e < N * N; e += 32) {
+        const int l = e / N, col = e - l * N;
+        double acc = 0.0;
+        if (l >= m) {
+            const double sg = ((l - m) & 1) ? -1.0 : 1.0;
+            const bool plus = col >= n;
+            const int j = plus ? col - n : n - 1 - col;
+            for (int i = 0; i < n; i++) {
+                const double gp = w.Gp[s][i * n + j], gm = w.Gm[s][i * n + j];
+                const double ev = plus ? (gp + sg * gm) : -(gm + sg * gp);
+                acc += cs.wt[i] * cs.ylm[l * n + i] * ev;
+            }
+            acc *= 0.5 * w.gl[l];
+        }
+        E[e] = acc;
+    }
+    __syncwarp();
+    for (int e = lane; e < NU * N; e += 32) {
+        const int iu = e / N, col = e - iu * N;
+        double acc = 0.0;
+        for (int l = m; l < N; l++) acc += E[l * N + col] * ylmu_m[l * NU + iu];
+        rec[ll.off_gu + e] = acc * w.xc[col];          // GU * LL (disort.f:4496-4506)
+    }
+    // source terms: psi[l] for beam (v1), Planck Z0 (v2) and Z1 (v3)
+    for (int l = lane; l < N; l += 32) {
+        double pb = 0.0, p0 = 0.0, p1 = 0.0;
+        if (l >= m) {
+            const double sg = ((l - m) & 1) ? -1.0 : 1.0;
+            for (int i = 0; i < n; i++) {
+                const double wy = cs.wt[i] * cs.ylm[l * n + i];
+                pb += wy * (w.zz[s][n + i] + sg * w.zz[s][n - 1 - i]);
+                p0 += wy * (w.zp0[s][n + i] + sg * w.zp0[s][n - 1 - i]);
+                p1 += wy * (xr1 + sg * xr1);
+            }
+        }
+        w.v1[l] = 0.5 * w.gl[l] * pb;
+        w.v2[l] = 0.5 * w.gl[l] * p0;
+        w.v3[l] = 0.5 * w.gl[l] * p1;
+    }
+    __syncwarp();
+    const double fact = (2. - c.delm0) * c.fbeam / (4.0 * kPiRef);
+    for (int iu = lane; iu < NU; iu += 32) {
+        double zb = 0.0, z0 = 0.0, z1 = 0.0;
+        for (int l = m; l < N; l++) {
+            const double yu = ylmu_m[l * NU + iu];
+            if (c.fbeam > 0.0) zb += yu * (w.v1[l] + fact * w.gl[l] * w.y0[l]);
+            z0 += yu * w.v2[l];
+            z1 += yu * w.v3[l];
+        }
+        rec[ll.off_zb + iu] = zb;
+        if (c.plank && m == 0) {
+            rec[ll.off_z0u + iu] = z0 + (1. - oprim) * xr0;
+            rec[ll.off_z1u + iu] = z1 + (1. - oprim) * xr1;
+        } else {
+            rec[ll.off_z0u + iu] = 0.0;
+            rec[ll.off_z1u + iu] = 0.0;
+        }
+    }
+    __syncwarp();
+}
+
+// ---------------------------------------------------------------------------
+// Intensity of azimuth mode m at user angle umu and level (lu) by analytic
+// integration of the source function layer by layer (reference USRINT,
+// disort.f:4355-4793; Lambertian surface).  One call per (level, angle) lane.
+// ---------------------------------------------------------------------------
+__device__ double usrint_one(const BinCtx &c, const WarpShared &w, const LayerLayout &ll,
+                             const double *scr, int NU, int lu, int iu, double umu, double utpr,
+                             double fisot, double bnd_up /* surface term without the exp */)
+{
+    const int N = c.N, n = c.n, m = c.mazim, ncut = c.ncut, L = c.L;
+    const int lyu = w.layru[lu];
+    if (c.lyrcut && lyu > ncut) return 0.0;
+    const bool negumu = umu < 0.0;
+    const bool therm = c.plank && m == 0;
+    const double umu0 = c.umu0;
+    const double exp0 = (c.fbeam > 0.0) ? exp(-utpr / umu0) : 0.0;
+    int lyrstr, lyrend; double sgn;
+    if (negumu) { lyrstr = 1; lyrend = lyu - 1; sgn = -1.0; }
+    else { lyrstr = lyu + 1; lyrend = ncut; sgn = 1.0; }
+    double palint = 0.0, plkint = 0.0;
+    double exp1 = 0.0, exp2 = 0.0;
+    for (int lc = lyrstr; lc <= lyrend; lc++) {
+        const double *rec = scr + (size_t)(lc - 1) * ll.stride;
+        const double t0 = w.taucpr[lc - 1], t1 = w.taucpr[lc];
+        const double dtau = t1 - t0;
+        exp1 = exp((utpr - t0) / umu);
+        exp2 = exp((utpr - t1) / umu);
+        if (therm) {
+            const double f0n = sgn * (exp1 - exp2);
+            const double f1n = sgn * ((t0 + umu) * exp1 - (t1 + umu) * exp2);
+            plkint += rec[ll.off_z0u + iu] * f0n + rec[ll.off_z1u + iu] * f1n;
+        }
+        if (c.fbeam > 0.0) {
+            const double denom = 1. + umu / umu0;
+            double expn;
+            if (fabs(denom) < 0.0001) expn = (dtau / umu0) * exp0;
+            else expn = (exp1 * exp(-t0 / umu0) - exp2 * exp(-t1 / umu0)) * sgn / denom;
+            palint += rec[ll.off_zb + iu] * expn;
+        }
+        for (int iq = 0; iq < n; iq++) {        // columns of the -k solutions
+            const double k = rec[ll.off_kk + n - 1 - iq], wk = rec[ll.off_ek + n - 1 - iq];
+            const double denom = 1.0 - umu * k;
+            double expn;
+            if (fabs(denom) < 0.0001) expn = dtau / umu * exp2;
+            else expn = sgn * (exp1 * wk - exp2) / denom;
+            palint += rec[ll.off_gu + iu * N + iq] * expn;
+        }
+        for (int iq = n; iq < N; iq++) {        // columns of the +k solutions
+            const double k = rec[ll.off_kk + iq - n], wk = rec[ll.off_ek + iq - n];
+            const double denom = 1.0 + umu * k;
+            double expn;
+            if (fabs(denom) < 0.0001) expn = -dtau / umu * exp1;
+            else expn = sgn * (exp1 - exp2 * wk) / denom;
+            palint += rec[ll.off_gu + iu * N + iq] * expn;
+        }
+    }
+    // the layer that contains the level (disort.f:4623-4729)
+    {
+        const double *rec = scr + (size_t)(lyu - 1) * ll.stride;
+        const double t0 = w.taucpr[lyu - 1], t1 = w.taucpr[lyu];
+        const double dtau1 = utpr - t0, dtau2 = utpr - t1, dtau = t1 - t0;
+        const bool skip = (fabs(dtau1) < 1.e-6 && negumu) || (fabs(dtau2) < 1.e-6 && !negumu);
+        if (!skip) {
+            if (negumu) exp1 = exp(dtau1 / umu); else exp2 = exp(dtau2 / umu);
+            if (c.fbeam > 0.0) {
+                const double denom = 1. + umu / umu0;
+                double expn;
+                if (fabs(denom) < 0.0001) expn = (dtau1 / umu0) * exp0;
+                else if (negumu) expn = (exp0 - exp(-t0 / umu0) * exp1) / denom;
+                else expn = (exp0 - exp(-t1 / umu0) * exp2) / denom;
+                palint += rec[ll.off_zb + iu] * expn;
+            }
+            for (int iq = 0; iq < n; iq++) {
+                const double kq = -rec[ll.off_kk + n - 1 - iq];
+                const double denom = 1. + umu * kq;
+                double expn;
+                if (fabs(denom) < 0.0001) expn = -dtau2 / umu * exp2;
+                else if (negumu) expn = (exp(-kq * dtau2) - exp(kq * dtau) * exp1) / denom;
+                else expn = (exp(-kq * dtau2) - exp2) / denom;
+                palint += rec[ll.off_gu + iu * N + iq] * expn;
+            }
+            for (int iq = n; iq < N; iq++) {
+                const double kq = rec[ll.off_kk + iq - n];
+                const double denom = 1. + umu * kq;
+                double expn;
+                if (fabs(denom) < 0.0001) expn = -dtau1 / umu * exp1;
+                else if (negumu) expn = (exp(-kq * dtau1) - exp1) / denom;
+                else expn = (exp(-kq * dtau1) - exp(-kq * dtau) * exp2) / denom;
+                palint += rec[ll.off_gu + iu * N + iq] * expn;
+            }
+            if (therm) {
+                double expn, fact;
+                if (negumu) { expn = exp1; fact = t0 + umu; }
+                else { expn = exp2; fact = t1 + umu; }
+                const double f0n = 1. - expn;
+                const double f1n = utpr + umu - fact * expn;
+                plkint += rec[ll.off_z0u + iu] * f0n + rec[ll.off_z1u + iu] * f1n;
+            }
+        }
+    }
+    // boundary contributions (disort.f:4735-4781)
+    double bndint = 0.0;
+    if (negumu && m == 0) bndint = (fisot + c.tplank) * exp(utpr / umu);
+    else if (!negumu && !(c.lyrcut || m > 0))
+        bndint = bnd_up * exp((utpr - w.taucpr[L]) / umu);
+    return palint + plkint + bndint;
+}
+
 // ---------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------
@@ -507,7 +723,8 @@ disort_generic_kernel(const LaunchArgs a)
 
     CtaShared cs;
     cs.mu = smem_dyn; cs.wt = cs.mu + n; cs.sq = cs.wt + n; cs.dinv = cs.sq + n;
-    cs.ylm = cs.dinv + n;
+    double *ylm_s = cs.dinv + n;
+    cs.ylm = ylm_s;
     WarpShared w;
     const int NTs = NT > 8 ? NT : 8;
     carve(smem_dyn + cta_shared_doubles(N) + (size_t)warp * warp_shared_doubles(N, L, NTs),
@@ -520,7 +737,7 @@ disort_generic_kernel(const LaunchArgs a)
         cs.dinv[i] = 1.0 / sqrt(wt * mu);
     }
     // flux path: azimuth mode 0 only
-    for (int e = threadIdx.x; e < N * n; e += blockDim.x) cs.ylm[e] = a.ylmc[e];
+    for (int e = threadIdx.x; e < N * n; e += blockDim.x) ylm_s[e] = a.ylmc[e];
     __syncthreads();
 
     const int slot = blockIdx.x * warps + warp;
@@ -622,15 +839,6 @@ disort_generic_kernel(const LaunchArgs a)
             c.tplank = bp.temis * plkavg_dev(bp.wvnmlo, bp.wvnmhi, bp.ttemp);
             c.bplank = plkavg_dev(bp.wvnmlo, bp.wvnmhi, bp.btemp);
         }
-        // Y_l^0(-mu0) by the Legendre recurrence (LEPOLY, disort.f:5354-5370)
-        if (lane == 0 && c.fbeam > 0.0) {
-            double x = -c.umu0;
-            w.y0[0] = 1.0; w.y0[1] = x;
-            for (int l = 2; l < N; l++)
-                w.y0[l] = ((2 * l - 1) * x * w.y0[l - 1] - (l - 1) * w.y0[l - 2]) / l;
-        }
-        __syncwarp();
-
         // zero the outputs (ZEROAL, disort.f:518); levels below NCUT stay 0
         for (int lu = lane; lu < NT; lu += 32) {
             if (o_rfldir) o_rfldir[lu] = 0.0;
@@ -639,10 +847,36 @@ disort_generic_kernel(const LaunchArgs a)
             if (o_dfdt) o_dfdt[lu] = 0.0;
             if (o_uavg) o_uavg[lu] = 0.0;
         }
+        double *o_uu = (NU > 0 && a.uu) ? a.uu + (size_t)bin * a.d.nphi * NT * NU : nullptr;
+        if (o_uu)
+            for (int e = lane; e < a.d.nphi * NT * NU; e += 32) o_uu[e] = 0.0;
 
+        // number of azimuth modes (disort.f:577-586); flux-only runs need m = 0 only
+        int naz = 0;
+        if (NU > 0) {
+            naz = N - 1;
+            const double u0 = a.umu[0], u1 = NU > 1 ? a.umu[1] : 0.0;
+            if (c.fbeam == 0.0 || fabs(1. - c.umu0) < 1.e-5 ||
+                (NU == 1 && fabs(1. - u0) < 1.e-5) || (NU == 1 && fabs(1. + u0) < 1.e-5) ||
+                (NU == 2 && fabs(1. + u0) < 1.e-5 && fabs(1. - u1) < 1.e-5))
+                naz = 0;
+        }
         const int R = n + N, C = 2 * N + 1;
+        const double *ylm_smem = cs.ylm;
+        int kconv = 0;
+
+      for (int mazim = 0; mazim <= naz && !status; mazim++) {
+        c.mazim = mazim;
+        c.delm0 = (mazim == 0) ? 1.0 : 0.0;
+        cs.ylm = (mazim == 0) ? ylm_smem : a.ylmc + (size_t)mazim * N * n;
+        const double *ylmu_m = (NU > 0) ? a.ylmu + (size_t)mazim * N * NU : nullptr;
+        // Y_l^m(-mu0) (LEPOLY, disort.f:599-605)
+        if (lane == 0 && c.fbeam > 0.0) lepoly_one(mazim, N, -c.umu0, w.y0);
+        __syncwarp();
+
         double xr0c = 0, xr1c = 0, xr0n = 0, xr1n = 0;
         int cur = 0;
+        double bnd_up = 0.0;
 
         // ================= downward sweep ================================
         if (!status) status = solve_layer(c, cs, w, 0, cur, xr0c, xr1c, lane);
@@ -658,7 +892,8 @@ disort_generic_kernel(const LaunchArgs a)
                 } else if (j < 2 * N) {
                     v = 0.0;
                 } else {
-                    v = c.fisot + c.tplank - w.zz[cur][r] - w.zp0[cur][r];
+                    // disort.f:3445 (m > 0) / :3547-3550 (m = 0)
+                    v = (mazim == 0 ? c.fisot + c.tplank : 0.0) - w.zz[cur][r] - w.zp0[cur][r];
                 }
                 w.W[r * C + j] = v;
             }
@@ -712,7 +947,8 @@ disort_generic_kernel(const LaunchArgs a)
             const int lc = ncut - 1;
             const double tb = w.taucpr[ncut];
             const double eb = (c.fbeam > 0.0) ? exp(-tb / c.umu0) : 0.0;
-            const int refl = !c.lyrcut;     // Lambertian, m = 0 (disort.f:2929-2947)
+            // Lambertian surface reflects the m = 0 mode only (disort.f:2929-2947)
+            const int refl = !c.lyrcut && mazim == 0;
             // sum_k w_k mu_k GC(-mu_k, j): one value per column, and for the rhs
             for (int j = lane; j <= N; j += 32) {
                 double sacc = 0.0;
@@ -776,8 +1012,31 @@ disort_generic_kernel(const LaunchArgs a)
                 for (int j = lane; j < N; j += 32) { LLs[(size_t)lc * N + j] = w.xc[j]; }
                 __syncwarp();
 
-                // fluxes at the levels that live in this layer (FLUXES)
-                for (int lu = 0; lu < NT; lu++) {
+                if (NU > 0) {
+                    // surface-reflected term of USRINT (disort.f:4747-4778): downward
+                    // intensities at the bottom boundary, Lambertian, m = 0 only
+                    if (lc == ncut - 1 && mazim == 0 && !c.lyrcut) {
+                        const double tb = w.taucpr[ncut];
+                        const double eb = (c.fbeam > 0.0) ? exp(-tb / c.umu0) : 0.0;
+                        double dn = 0.0;
+                        for (int i = lane; i < n; i += 32) {
+                            double ud = 0.0;
+                            for (int j = 0; j < n; j++)
+                                ud += w.Gm[cur][i * n + j] * w.xc[n + j] * w.ek[cur][j] -
+                                      w.Gp[cur][i * n + j] * w.xc[n - 1 - j];
+                            ud += w.zz[cur][n - 1 - i] * eb + w.zp0[cur][n - 1 - i] + xr1c * tb;
+                            dn += cs.wt[i] * cs.mu[i] * ud;
+                        }
+                        dn = warp_sum(dn);
+                        bnd_up = 2.0 * c.albedo * dn + c.umu0 * c.fbeam / kPiRef * c.albedo * eb +
+                                 (1.0 - c.albedo) * c.bplank;
+                    }
+                    user_terms(c, cs, w, ll, scr + (size_t)lc * ll.stride, ylmu_m, NU, lc, cur,
+                               xr0c, xr1c, lane);
+                }
+
+                // fluxes at the levels that live in this layer (FLUXES), m = 0 only
+                for (int lu = 0; lu < NT && mazim == 0; lu++) {
                     if (w.layru[lu] != lc + 1) continue;
                     double ut = a.d.ntau > 0 ? a.utau[(size_t)bin * NT + lu] : w.tauc[lu];
                     if (a.d.ntau > 0 && fabs(ut - w.tauc[L]) <= 1.e-4) ut = w.tauc[L];
@@ -830,6 +1089,49 @@ disort_generic_kernel(const LaunchArgs a)
                 __syncwarp();
             }
         }
+
+        // ================= intensities at the user angles ====================
+        if (!status && NU > 0) {
+            __threadfence_block();
+            const double rpd = kPiRef / 180.0;
+            double azerr = 0.0;
+            for (int e = lane; e < NT * NU; e += 32) {
+                const int lu = e / NU, iu = e - lu * NU;
+                const int lyu = w.layru[lu];
+                double ut = a.d.ntau > 0 ? a.utau[(size_t)bin * NT + lu] : w.tauc[lu];
+                if (a.d.ntau > 0 && fabs(ut - w.tauc[L]) <= 1.e-4) ut = w.tauc[L];
+                double ss = c.ssalb[lyu - 1]; if (ss == 1.0) ss = 1.0 - kDither;
+                const double f = c.pmom[(size_t)(lyu - 1) * ldp + N];
+                const double utp = w.taucpr[lyu - 1] + (1. - ss * f) * (ut - w.tauc[lyu - 1]);
+                const double val = usrint_one(c, w, ll, scr, NU, lu, iu, a.umu[iu], utp, c.fisot, bnd_up);
+                // Fourier sum over azimuth (disort.f:767-825)
+                for (int j = 0; j < a.d.nphi; j++) {
+                    double *pu = o_uu + ((size_t)j * NT + lu) * NU + iu;
+                    if (mazim == 0) {
+                        *pu = val;
+                    } else {
+                        const double azterm = val * cos(mazim * (rpd * (a.phi[j] - bp.phi0)));
+                        const double unew = *pu + azterm;
+                        *pu = unew;
+                        // RATIO(|AZTERM|, |UU|), disort.f:6159
+                        const double aa = fabs(azterm), bb = fabs(unew);
+                        double rr;
+                        if (aa == 0.0) rr = (bb == 0.0) ? 1.0 : 0.0;
+                        else if (bb == 0.0) rr = 1.79e308;
+                        else rr = aa / bb;
+                        azerr = fmax(azerr, rr);
+                    }
+                }
+            }
+            if (mazim > 0) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) azerr = fmax(azerr, __shfl_xor_sync(FULLMASK, azerr, o));
+                if (azerr <= bp.accur) kconv++;
+                if (kconv >= 2) break;       // disort.f:821-823
+            }
+            __syncwarp();
+        }
+      }   // azimuth modes
         if (lane == 0) a.status[bin] = status;
         __syncwarp();
     }

@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header():
     import ctypes as C
     assert C.sizeof(sb.SbdDims) == 8 * 4
-    assert C.sizeof(sb.SbdBin) == 10 * 8 + 2 * 4
+    assert C.sizeof(sb.SbdBin) == 11 * 8 + 2 * 4
     assert sb.BIN_DTYPE.itemsize == C.sizeof(sb.SbdBin)
     b = sb.make_bins(3, fbeam=[1, 2, 3], umu0=0.5, plank=[0, 1, 0])
     raw = np.frombuffer(b.tobytes(), dtype=np.uint8).reshape(3, -1)

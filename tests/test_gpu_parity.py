@@ -98,3 +98,95 @@ def test_conservative_scattering_layers(solver, nstr):
     ref = oracle_flux(w)
     assert (ref["status"] == 0).all()
     assert_close(got, ref, rtol=1e-6, atol_scale=1e-9)
+
+
+def oracle_radiance(w, umu, phi, accur=0.0):
+    b = w["bins"]
+    outs = []
+    for i in range(len(b)):
+        r = oracle.disort(
+            w["dtauc"][i], w["ssalb"][i], w["pmom"][i], nstr=w["nstr"],
+            temper=None if w["temper"] is None else w["temper"][b["col"][i]],
+            umu=umu, phi=phi, fbeam=b["fbeam"][i], umu0=b["umu0"][i], phi0=b["phi0"][i],
+            fisot=b["fisot"][i], albedo=b["albedo"][i], btemp=b["btemp"][i], ttemp=b["ttemp"][i],
+            temis=b["temis"][i], wvnmlo=b["wvnmlo"][i], wvnmhi=b["wvnmhi"][i],
+            plank=bool(b["plank"][i]), onlyfl=False, corint=False, accur=accur)
+        outs.append(r)
+    return outs
+
+
+def assert_radiance_close(got, refs, rtol=1e-7, atol_scale=1e-9):
+    for i, r in enumerate(refs):
+        assert got["status"][i] == r["status"], i
+        if r["status"] != 0:
+            continue
+        scale = max(np.abs(r["uu"]).max(), np.abs(r["flup"]).max() / np.pi, 1e-300)
+        err = np.abs(got["uu"][i] - r["uu"]) - atol_scale * scale
+        assert (err <= rtol * np.abs(r["uu"])).all(), (i, np.abs(got["uu"][i] - r["uu"]).max(), scale)
+        for k in ("rfldir", "rfldn", "flup"):
+            np.testing.assert_allclose(got[k][i], r[k], rtol=1e-7, atol=1e-9 * max(np.abs(r[k]).max(), 1e-300))
+
+
+@pytest.mark.parametrize("nstr,nlyr", [(8, 6), (16, 12), (20, 33)])
+def test_radiances_match_oracle(solver, nstr, nlyr):
+    """User-angle intensities (TERPEV/TERPSO/USRINT + azimuth sum)."""
+    w = workloads.retrieval_batch(12, nstr=nstr, nlyr=nlyr, ncols=4, seed=100 + nstr)
+    w["bins"]["phi0"] = 30.0
+    umu = np.array([-1.0, -0.8, -0.5, -0.2, -0.05, 0.05, 0.3, 0.6, 0.9, 1.0])
+    phi = np.array([0.0, 60.0, 180.0])
+    got = solver.disort_batch(w["dtauc"], w["ssalb"], w["pmom"], w["bins"], nstr=nstr, umu=umu, phi=phi)
+    assert_radiance_close(got, oracle_radiance(w, umu, phi))
+
+
+def test_thermal_radiances_match_oracle(solver):
+    """Thermal IR shape of config C3: NSTR=8, Planck source, no beam (one azimuth mode)."""
+    w = workloads.mls_shortwave(nstr=8, wlinf=4.0, wlsup=12.0, wlinc=0.5)
+    w["bins"]["fbeam"] = 0.0
+    w["bins"]["temis"] = 0.3
+    umu = np.cos(np.deg2rad(np.array([180, 160, 140, 120, 100, 80, 60, 40, 20, 0.0])))
+    umu = np.sort(umu)
+    phi = np.array([0.0])
+    got = solver.disort_batch(w["dtauc"], w["ssalb"], w["pmom"], w["bins"], nstr=8,
+                              temper=w["temper"], umu=umu, phi=phi)
+    assert_radiance_close(got, oracle_radiance(w, umu, phi))
+
+
+def test_disort_entry_matches_oracle_flux_and_radiance():
+    """The gfortran-ABI entry disort_ with the reference's argument list."""
+    rng = np.random.default_rng(3)
+    L, N, nmom = 5, 8, 10
+    dtauc = 10.0 ** rng.uniform(-2, 0.3, L)
+    ssalb = rng.uniform(0.3, 1.0, L); ssalb[2] = 1.0
+    pm = workloads.hg_moments(rng.uniform(0, 0.8, L), nmom)          # [L][nmom+1]
+    pmom_f = np.zeros((nmom + 1, L), order="F"); pmom_f[:, :] = pm.T
+    common = dict(nlyr=L, dtauc=dtauc, ssalb=ssalb, nmom=nmom, pmom=pmom_f, temper=np.linspace(220, 290, L + 1),
+                  wvnmlo=800.0, wvnmhi=900.0, usrtau=False, ntau=0, utau=None, nstr=N, ibcnd=0, fbeam=2.0,
+                  umu0=0.7, phi0=10.0, fisot=0.1, lamber=True, albedo=0.25, btemp=295.0, ttemp=200.0,
+                  temis=0.2, plank=True)
+    o = sb.disort(**common, usrang=False, numu=0, umu=None, nphi=0, phi=None, onlyfl=True)
+    r = oracle.disort(dtauc, ssalb, pm, nstr=N, temper=common["temper"], fbeam=2.0, umu0=0.7, phi0=10.0,
+                      fisot=0.1, albedo=0.25, btemp=295.0, ttemp=200.0, temis=0.2, wvnmlo=800.0,
+                      wvnmhi=900.0, plank=True, onlyfl=True)
+    assert o["status"] == 0 and o["ntau"] == L + 1 and o["numu"] == N
+    for k in ("rfldir", "rfldn", "flup", "dfdt", "uavg"):
+        np.testing.assert_allclose(o[k][:L + 1], r[k], rtol=1e-8, atol=1e-10 * np.abs(r[k]).max())
+    assert o["ssalb"][2] < 1.0                        # SSALB=1 -> 1-DITHER mutation is visible
+    np.testing.assert_allclose(o["utau"][:L + 1], np.concatenate([[0], np.cumsum(dtauc)]))
+    umu = np.array([-0.9, -0.3, 0.2, 0.8]); phi = np.array([0.0, 90.0])
+    o = sb.disort(**common, usrang=True, numu=4, umu=umu, nphi=2, phi=phi, onlyfl=False)
+    r = oracle.disort(dtauc, ssalb, pm, nstr=N, temper=common["temper"], umu=umu, phi=phi, fbeam=2.0,
+                      umu0=0.7, phi0=10.0, fisot=0.1, albedo=0.25, btemp=295.0, ttemp=200.0, temis=0.2,
+                      wvnmlo=800.0, wvnmhi=900.0, plank=True, onlyfl=False)
+    assert o["status"] == 0
+    uu = np.transpose(o["uu"][:4, :L + 1, :2], (2, 1, 0))     # UU(iu,lu,j) -> [j][lu][iu]
+    np.testing.assert_allclose(uu, r["uu"], rtol=1e-7, atol=1e-9 * np.abs(r["uu"]).max())
+
+
+def test_beam_angle_clash_is_reported_for_retry(solver):
+    """UMU0 on a quadrature node => status 1 (the host retries with NSTR-2 / NSTR+2, drt.f:536-554)."""
+    mu, _ = sb.quadrature(4)
+    w = workloads.retrieval_batch(4, nstr=8, nlyr=5, ncols=1, seed=1)
+    w["bins"]["umu0"] = [mu[1], 0.5, mu[3] * (1 + 5e-5), 0.9]
+    got = solver.disort_batch(w["dtauc"], w["ssalb"], w["pmom"], w["bins"], nstr=8)
+    ref = oracle_flux(w)
+    assert list(got["status"]) == [1, 0, 1, 0] == list(ref["status"])
