@@ -1,0 +1,33 @@
+"""solve(batch) adapters for sbdart_b200.frontend.Sbdart.run: CPU oracle and CUDA."""
+import numpy as np
+
+from oracle import oracle
+
+
+def solve_oracle(b, nthreads=8):
+    bins = b["bins"]
+    if "umu" not in b:
+        return oracle.disort_flux_batch(
+            b["dtauc"], b["ssalb"], b["pmom"], nstr=b["nstr"], fbeam=bins["fbeam"], umu0=bins["umu0"],
+            albedo=bins["albedo"], plank=bins["plank"], wvnmlo=bins["wvnmlo"], wvnmhi=bins["wvnmhi"],
+            btemp=bins["btemp"], ttemp=bins["ttemp"], temis=bins["temis"], fisot=bins["fisot"],
+            temper=b["temper"], col=bins["col"], nthreads=nthreads)
+    outs = {k: [] for k in ("rfldir", "rfldn", "flup", "uu", "status")}
+    for i in range(len(bins)):
+        r = oracle.disort(
+            b["dtauc"][i], b["ssalb"][i], b["pmom"][i], nstr=b["nstr"], temper=b["temper"][0],
+            umu=b["umu"], phi=b["phi"], fbeam=bins["fbeam"][i], umu0=bins["umu0"][i],
+            phi0=bins["phi0"][i], fisot=bins["fisot"][i], albedo=bins["albedo"][i],
+            btemp=bins["btemp"][i], ttemp=bins["ttemp"][i], temis=bins["temis"][i],
+            wvnmlo=bins["wvnmlo"][i], wvnmhi=bins["wvnmhi"][i], plank=bool(bins["plank"][i]),
+            onlyfl=False)
+        for k in outs:
+            outs[k].append(r[k])
+    return {k: np.array(v) for k, v in outs.items()}
+
+
+def make_solve_cuda(solver):
+    def solve(b):
+        return solver.disort_batch(b["dtauc"], b["ssalb"], b["pmom"], b["bins"], nstr=b["nstr"],
+                                   temper=b["temper"], umu=b.get("umu"), phi=b.get("phi"))
+    return solve
