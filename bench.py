@@ -2,9 +2,9 @@
 """bench.py -- DISORT spectral-points/sec on B200 (BASELINE.json metric).
 
 Workload (config C2): shortwave 0.25-4.0 um at 0.005 um, NSTR=16,
-33 layers; the bin set (one bin per wavelength x k-term) is replicated R times
-so that one step is one batched launch over R complete spectra.  Inputs are
-synthetic optical properties of that shape (sbdart_b200/workloads.py).
+33 layers (mid-latitude summer); the bin set (one bin per wavelength x k-term,
+2037 bins, produced by the SBDART front end sbdart_b200/frontend) is replicated
+R times so that one step is one batched launch over R complete spectra.
 
 A step = one pass of the hot path (one batched DISORT solve of every bin).
   value : bins/s with inputs resident in HBM (device pointers, CUDA events
@@ -99,9 +99,17 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples)}
 
 
+C2_NAMELIST = "&INPUT idatm=2, wlinf=.25, wlsup=4.0, wlinc=.005, nstr=16, iout=1 /"
+
+
 def build_workload(replicate):
-    from sbdart_b200 import workloads
-    w = workloads.mls_shortwave(nstr=16, nlyr=33, wlinf=0.25, wlsup=4.0, wlinc=0.005)
+    """Config C2: the bins SBDART itself would hand to DISORT for the
+    mid-latitude-summer atmosphere, 0.25-4.0 um at 0.005 um, NSTR=16 -- produced by
+    the front end (LOWTRAN7 band model + 3-term k-distribution + Rayleigh)."""
+    from sbdart_b200.frontend import Sbdart
+    run = Sbdart(C2_NAMELIST)
+    w = run.batch(run.bins())
+    w["name"] = "sbdart_C2_mls_0.25-4.0um@0.005_nstr16_L33"
     base = w["dtauc"].shape[0]
     if replicate > 1:
         for k in ("dtauc", "ssalb", "pmom"):
@@ -137,7 +145,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dtm * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic",
+        "data": "synthetic (no dataset: optical properties computed by the SBDART front end from the MLS model atmosphere)",
         "config": {"workload": w["name"], "bins_per_step": int(sample),
                    "note": "CPU restatement of disort.f (oracle/, OpenMP over bins); "
                            "no Fortran compiler in the image so the reference itself cannot be built"},
@@ -155,7 +163,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--replicate", type=int, default=64, help="spectra per step per GPU")
+    ap.add_argument("--replicate", type=int, default=40, help="spectra per step per GPU")
     ap.add_argument("--ref-bins", type=int, default=8192, help="bins per CPU reference step")
     ap.add_argument("--cpu-sample", type=int, default=16384, help="bins for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -302,7 +310,7 @@ def main():
             "metric": METRIC, "value": world * B / (ms_dev * 1e-3), "unit": UNIT,
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic",
+            "data": "synthetic (no dataset: optical properties computed by the SBDART front end from the MLS model atmosphere)",
             "config": {"workload": w["name"], "bins_per_gpu_per_step": int(B),
                        "spectra_per_step": args.replicate, "bins_per_spectrum": int(w["base_bins"]),
                        "levels_out": NT,
