@@ -108,6 +108,8 @@ struct Tables {
 struct sbd_handle {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;   // H2D / D2H overlap in the host-buffer call
+    cudaEvent_t ev_in[8] = {}, ev_k[8] = {};
     int sm_count = 0;
     size_t smem_optin = 0;
     int64_t launches = 0;
@@ -167,6 +169,12 @@ extern "C" int sbd_create(sbd_handle **out, int device)
     h->sm_count = prop.multiProcessorCount;
     h->smem_optin = prop.sharedMemPerBlockOptin;
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return SBD_ERR_CUDA; }
+    if (cudaStreamCreateWithFlags(&h->copy_in, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h->copy_out, cudaStreamNonBlocking) != cudaSuccess) { delete h; return SBD_ERR_CUDA; }
+    for (int i = 0; i < 8; i++) {
+        cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&h->ev_k[i], cudaEventDisableTiming);
+    }
     if (h->counter.reserve(256) != cudaSuccess) { delete h; return SBD_ERR_CUDA; }
     *out = h;
     return SBD_SUCCESS;
@@ -182,6 +190,9 @@ extern "C" void sbd_destroy(sbd_handle *h)
                        &h->d_pmom, &h->d_bins, &h->d_temper, &h->d_utau, &h->d_out, &h->d_uu,
                        &h->d_status };
     for (DevBuf *b : bufs) b->release();
+    for (int i = 0; i < 8; i++) { cudaEventDestroy(h->ev_in[i]); cudaEventDestroy(h->ev_k[i]); }
+    cudaStreamDestroy(h->copy_in);
+    cudaStreamDestroy(h->copy_out);
     cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -342,11 +353,7 @@ extern "C" int sbd_disort_batch(sbd_handle *h, const sbd_dims *dims, const doubl
     CK(h->d_bins.reserve(B * sizeof(sbd_bin)));
     CK(h->d_out.reserve(5 * B * NT * 8));
     CK(h->d_status.reserve(B * 4));
-    CK(cudaMemcpyAsync(h->d_dtauc.p, dtauc, B * L * 8, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(h->d_ssalb.p, ssalb, B * L * 8, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(h->d_pmom.p, pmom, B * L * ldp * 8, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(h->d_bins.p, bins, B * sizeof(sbd_bin), cudaMemcpyHostToDevice, st));
-    const double *d_temper = nullptr, *d_utau = nullptr;
+    const double *d_temper = nullptr;
     if (temper && dims->ncol > 0) {
         CK(h->d_temper.reserve((size_t)dims->ncol * (L + 1) * 8));
         CK(cudaMemcpyAsync(h->d_temper.p, temper, (size_t)dims->ncol * (L + 1) * 8,
@@ -356,25 +363,54 @@ extern "C" int sbd_disort_batch(sbd_handle *h, const sbd_dims *dims, const doubl
     if (dims->ntau > 0) {
         if (!utau) return SBD_ERR_ARG;
         CK(h->d_utau.reserve(B * NT * 8));
-        CK(cudaMemcpyAsync(h->d_utau.p, utau, B * NT * 8, cudaMemcpyHostToDevice, st));
-        d_utau = (const double *)h->d_utau.p;
     }
-    double *o = (double *)h->d_out.p;
     const size_t per = B * NT;
-    const size_t nuu = (size_t)dims->numu * dims->nphi * B * NT;
-    if (nuu) CK(h->d_uu.reserve(nuu * 8));
-    rc = sbd_disort_batch_device(h, dims, (const double *)h->d_dtauc.p, (const double *)h->d_ssalb.p,
-                                 (const double *)h->d_pmom.p, (const sbd_bin *)h->d_bins.p, d_temper,
-                                 d_utau, umu, phi, o, o + per, o + 2 * per, o + 3 * per,
-                                 o + 4 * per, nuu ? (double *)h->d_uu.p : nullptr,
-                                 (int32_t *)h->d_status.p, st);
-    if (rc) return rc;
-    if (nuu) CK(cudaMemcpyAsync(uu, h->d_uu.p, nuu * 8, cudaMemcpyDeviceToHost, st));
+    const size_t nuu1 = (size_t)dims->numu * dims->nphi * NT;      // uu doubles per bin
+    if (nuu1) CK(h->d_uu.reserve(nuu1 * B * 8));
+    double *o = (double *)h->d_out.p;
     double *dst[5] = { rfldir, rfldn, flup, dfdt, uavg };
-    for (int k = 0; k < 5; k++)
-        if (dst[k]) CK(cudaMemcpyAsync(dst[k], o + k * per, per * 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(status, h->d_status.p, B * 4, cudaMemcpyDeviceToHost, st));
+    // Pipeline over chunks of bins: H2D of chunk c+1 and D2H of chunk c-1 overlap the
+    // kernel of chunk c (three streams, events between them).
+    int nchunk = (int)(B / 16384);
+    if (nchunk < 1) nchunk = 1;
+    if (nchunk > 8) nchunk = 8;
+    CK(cudaStreamSynchronize(h->copy_out));
+    for (int c = 0; c < nchunk; c++) {
+        const size_t b0 = B * c / nchunk, b1 = B * (c + 1) / nchunk, nb = b1 - b0;
+        cudaStream_t si = nchunk > 1 ? h->copy_in : st;
+        CK(cudaMemcpyAsync((double *)h->d_dtauc.p + b0 * L, dtauc + b0 * L, nb * L * 8, cudaMemcpyHostToDevice, si));
+        CK(cudaMemcpyAsync((double *)h->d_ssalb.p + b0 * L, ssalb + b0 * L, nb * L * 8, cudaMemcpyHostToDevice, si));
+        CK(cudaMemcpyAsync((double *)h->d_pmom.p + b0 * L * ldp, pmom + b0 * L * ldp, nb * L * ldp * 8,
+                           cudaMemcpyHostToDevice, si));
+        CK(cudaMemcpyAsync((sbd_bin *)h->d_bins.p + b0, bins + b0, nb * sizeof(sbd_bin), cudaMemcpyHostToDevice, si));
+        if (dims->ntau > 0)
+            CK(cudaMemcpyAsync((double *)h->d_utau.p + b0 * NT, utau + b0 * NT, nb * NT * 8, cudaMemcpyHostToDevice, si));
+        if (nchunk > 1) {
+            CK(cudaEventRecord(h->ev_in[c], si));
+            CK(cudaStreamWaitEvent(st, h->ev_in[c], 0));
+        }
+        sbd_dims dc = *dims;
+        dc.nbins = (int32_t)nb;
+        rc = sbd_disort_batch_device(
+            h, &dc, (const double *)h->d_dtauc.p + b0 * L, (const double *)h->d_ssalb.p + b0 * L,
+            (const double *)h->d_pmom.p + b0 * L * ldp, (const sbd_bin *)h->d_bins.p + b0, d_temper,
+            dims->ntau > 0 ? (const double *)h->d_utau.p + b0 * NT : nullptr, umu, phi,
+            o + b0 * NT, o + per + b0 * NT, o + 2 * per + b0 * NT, o + 3 * per + b0 * NT,
+            o + 4 * per + b0 * NT, nuu1 ? (double *)h->d_uu.p + b0 * nuu1 : nullptr,
+            (int32_t *)h->d_status.p + b0, st);
+        if (rc) return rc;
+        cudaStream_t so = nchunk > 1 ? h->copy_out : st;
+        if (nchunk > 1) {
+            CK(cudaEventRecord(h->ev_k[c], st));
+            CK(cudaStreamWaitEvent(so, h->ev_k[c], 0));
+        }
+        for (int k = 0; k < 5; k++)
+            if (dst[k]) CK(cudaMemcpyAsync(dst[k] + b0 * NT, o + k * per + b0 * NT, nb * NT * 8, cudaMemcpyDeviceToHost, so));
+        if (nuu1) CK(cudaMemcpyAsync(uu + b0 * nuu1, (double *)h->d_uu.p + b0 * nuu1, nb * nuu1 * 8, cudaMemcpyDeviceToHost, so));
+        CK(cudaMemcpyAsync(status + b0, (int32_t *)h->d_status.p + b0, nb * 4, cudaMemcpyDeviceToHost, so));
+    }
     CK(cudaStreamSynchronize(st));
+    if (nchunk > 1) CK(cudaStreamSynchronize(h->copy_out));
 #undef CK
     return SBD_SUCCESS;
 }

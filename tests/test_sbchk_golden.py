@@ -33,3 +33,18 @@ def test_cuda_reproduces_sbchk(n):
     assert worst <= 1.5e-4 and nexact >= 0.85 * nval
     assert s.kernel_launches >= len(case_inputs(n))
     s.close()
+
+
+@pytest.mark.gpu
+def test_sbdart_executable_drop_in(tmp_path):
+    """bin/sbdart: ./INPUT in, IOUT records on stdout (TestRuns/test_runs:29-37)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    (tmp_path / "INPUT").write_text(case_inputs(1)[0])
+    r = subprocess.run([sys.executable, os.path.join(root, "bin", "sbdart")], cwd=tmp_path,
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    nval, nexact, worst = compare_records(r.stdout, golden_text(1))
+    assert worst <= 1.5e-4
