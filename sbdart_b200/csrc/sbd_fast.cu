@@ -41,8 +41,10 @@ struct FastLayout {
     static constexpr int off_zp0 = off_zz + N;
     static constexpr int off_xr = off_zp0 + N;
     static constexpr int rec = ((off_xr + 2 + 1) / 2) * 2;
-    static constexpr int urow = ((C + 1) / 2) * 2;        // padded pivot-row length
-    static constexpr int ublk = N * urow;
+    // pivot rows, packed: row j keeps columns j..2N (C-j entries) in a slice of even length
+    __host__ __device__ static constexpr int ulen(int j) { return C + 1 - j - (j & 1); }
+    __host__ __device__ static constexpr int uoff(int j) { return (C + 1) * j - j * (j - 1) / 2 - j / 2; }
+    static constexpr int ublk = (C + 1) * N - N * (N - 1) / 2 - N / 2;      // = uoff(N), even
     __host__ __device__ static size_t slot_doubles(int L) { return (size_t)L * (rec + ublk); }
     // shared memory (doubles)
     static constexpr int cta = 4 * n + N * n;
@@ -52,8 +54,11 @@ struct FastLayout {
     {
         // pivot-row double buffer, y0, taucpr/tauc/pk(+2 boundary temps), prologue
         // work, level map, per-task areas; kept even for 16-byte alignment
-        size_t d = (size_t)4 * (N + 1) + N + 3 * (L + 1) + 2 + 3 * L + (NT + 1) / 2 +
-                   (size_t)tasks * task;
+        size_t work = (size_t)tasks * task;              // phase 1: per-task areas
+        size_t p2 = 3 * (size_t)rec, p3 = 2 * (size_t)(ublk + rec);   // phase 2 / 3 staging
+        if (p2 > work) work = p2;
+        if (p3 > work) work = p3;
+        size_t d = (size_t)4 * (N + 1) + N + 3 * (L + 1) + 2 + 3 * L + (NT + 1) / 2 + 2 + work;
         return (d + 1) & ~(size_t)1;
     }
 };
@@ -61,6 +66,21 @@ struct FastLayout {
 __device__ __forceinline__ double shfl_d(double v, int src, int width)
 {
     return __shfl_sync(FULLMASK, v, src, width);
+}
+
+// ---- asynchronous global -> shared staging (LDGSTS) ------------------------
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
+{
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_one() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+// the warp copies `ndoubles` (even, both sides 16-byte aligned) doubles
+__device__ __forceinline__ void warp_copy_async(double *dst, const double *src, int ndoubles, int lane)
+{
+    for (int i = lane; i < ndoubles / 2; i += 32) cp_async16(dst + 2 * i, src + 2 * i);
 }
 
 // 1/x to ~1 ulp without the IEEE slow paths of the division operator:
@@ -177,6 +197,12 @@ __device__ __forceinline__ int phase1_layers(
     // Only A is rotated: with A V = U S, the vectors needed downstream are
     // P = L V = K^-T (A V) and Q = L^-T V = (L L^T)^-1 P, so V is never formed.
     if (n > 1) {
+        // squared column norm, carried along analytically (a'_pp = a_pp - t a_pq,
+        // a'_qq = a_qq + t a_pq); only used for the rotation angles -- the singular
+        // value itself is recomputed from the column after convergence
+        double own2 = 0.0;
+#pragma unroll
+        for (int i = 0; i < n; i++) own2 = fma(a[i], a[i], own2);
         for (int sweep = 0; sweep < 40; sweep++) {
             int did = 0;
 #pragma unroll 1
@@ -190,17 +216,19 @@ __device__ __forceinline__ int phase1_layers(
                     if (partner >= n - 1) partner -= n - 1;
                 }
                 double pa[n];
-                double own2 = 0.0, oth2 = 0.0, gam = 0.0;
+                double g0 = 0.0, g1 = 0.0;
+                const double oth2 = shfl_d(own2, partner, n);
 #pragma unroll
                 for (int i = 0; i < n; i++) {
                     pa[i] = shfl_d(a[i], partner, n);
-                    own2 = fma(a[i], a[i], own2);
-                    oth2 = fma(pa[i], pa[i], oth2);
-                    gam = fma(a[i], pa[i], gam);
+                    if (i & 1) g1 = fma(a[i], pa[i], g1); else g0 = fma(a[i], pa[i], g0);
                 }
+                const double gam = g0 + g1;
                 const bool lo = g < partner;
                 const double alpha = lo ? own2 : oth2, beta = lo ? oth2 : own2;
-                if (gam * gam > 1.0e-28 * (alpha * beta) && fabs(gam) > 1.0e-300) {
+                // rotate unless the pair is orthogonal to 1e-12 (eigenvectors then carry
+                // errors ~1e-12, far below the 1e-5 target)
+                if (gam * gam > 1.0e-24 * (alpha * beta) && fabs(gam) > 1.0e-300) {
                     did = 1;
                     const double dl = 0.5 * (beta - alpha);
                     const double h2 = fma(dl, dl, gam * gam);
@@ -208,11 +236,16 @@ __device__ __forceinline__ int phase1_layers(
                     const double t = gam * fast_rcp(dl + (dl >= 0.0 ? hy : -hy));
                     const double cc = rsqrt(fma(t, t, 1.0));
                     const double sn = lo ? -t * cc : t * cc;
+                    own2 = lo ? fma(-t, gam, own2) : fma(t, gam, own2);
 #pragma unroll
                     for (int i = 0; i < n; i++) a[i] = fma(sn, pa[i], cc * a[i]);
                 }
             }
             if (!__any_sync(FULLMASK, did)) break;
+            // refresh the carried norms once per sweep (cheap, stops drift)
+            own2 = 0.0;
+#pragma unroll
+            for (int i = 0; i < n; i++) own2 = fma(a[i], a[i], own2);
         }
     }
 
@@ -383,7 +416,8 @@ disort_fast_kernel(const LaunchArgs a)
     double *y0 = wsm + 4 * (N + 1), *taucpr = y0 + N, *tauc = taucpr + (L + 1), *pk = tauc + (L + 1);
     double *lw = pk + (L + 3);                                   // 3 x L prologue work values
     int *layru = (int *)(lw + 3 * L);
-    double *tsm_base = lw + 3 * L + (NT + 1) / 2;
+    // 16-byte aligned work area: per-task areas in phase 1, cp.async staging afterwards
+    double *tsm_base = wsm + ((((lw + 3 * L + (NT + 1) / 2) - wsm) + 1) & ~(ptrdiff_t)1);
 
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         double mu = a.quad[i], wt = a.quad[n + i];
@@ -533,18 +567,31 @@ disort_fast_kernel(const LaunchArgs a)
         // lane = matrix row.  Rows not yet used as pivots are "live".
         double w[C + 1];            // +1: pad so that columns pair up for 16-byte moves
         unsigned live = 0;          // rows currently holding an equation
+        // Layer records are staged global -> shared with cp.async, three slots deep:
+        // stage lc uses records lc and lc+1 while record lc+2 is in flight.
+        double *rslot = tsm_base;   // phase-1 task areas are idle now
         if (!status) {
+            warp_copy_async(rslot, recs, FL::rec, lane);
+            if (ncut > 1) warp_copy_async(rslot + FL::rec, recs + FL::rec, FL::rec, lane);
+            cp_async_commit();
+            cp_async_wait_all();
+            __syncwarp();
             // top boundary rows on lanes 0..n-1 (disort.f:2887-2915, :3547-3550)
 #pragma unroll
             for (int c = 0; c < C + 1; c++) w[c] = 0.0;
             if (lane < n) {
-                gc_row_scaled<n>(recs, lane, false, w);
-                w[2 * N] = bp.fisot + tplank - recs[FL::off_zz + lane] - recs[FL::off_zp0 + lane];
+                gc_row_scaled<n>(rslot, lane, false, w);
+                w[2 * N] = bp.fisot + tplank - rslot[FL::off_zz + lane] - rslot[FL::off_zp0 + lane];
             }
             live = (1u << n) - 1u;
             for (int lc = 0; lc < ncut; lc++) {
                 const bool last = (lc == ncut - 1);
-                const double *rc = recs + (size_t)lc * FL::rec;
+                if (lc + 2 < ncut) {
+                    warp_copy_async(rslot + ((lc + 2) % 3) * FL::rec, recs + (size_t)(lc + 2) * FL::rec,
+                                    FL::rec, lane);
+                    cp_async_commit();
+                }
+                const double *rc = rslot + (lc % 3) * FL::rec;
                 const double tb = taucpr[lc + 1];
                 const double eb = (fbeam > 0.0) ? exp(-tb / umu0) : 0.0;
                 // free lanes take the new equations: N interface rows, or n bottom rows
@@ -554,7 +601,7 @@ disort_fast_kernel(const LaunchArgs a)
                 const bool isnew = ((freem >> lane) & 1u) && rank < nnew;
                 if (isnew) {
                     if (!last) {
-                        const double *rn = rc + FL::rec;
+                        const double *rn = rslot + ((lc + 1) % 3) * FL::rec;
                         const int r = rank;
                         gc_row_scaled<n>(rc, r, true, w);
                         double tmp[N];
@@ -634,11 +681,14 @@ disort_fast_kernel(const LaunchArgs a)
                     act &= ~(1u << pl);
                 }
                 if (status) break;
-                // pivot rows -> scratch: row j holds columns j..2N at entries 0..2N-j
+                // pivot rows -> scratch, packed: row j holds columns j..2N at entries
+                // 0..2N-j of a slice of even length starting at uoff(j)
                 if (mycol >= 0) {
-                    double2 *u2 = reinterpret_cast<double2 *>(ublk + ((size_t)lc * N + mycol) * FL::urow);
+                    double2 *u2 = reinterpret_cast<double2 *>(ublk + (size_t)lc * FL::ublk + FL::uoff(mycol));
+                    const int len2 = FL::ulen(mycol) / 2;
 #pragma unroll
-                    for (int c2 = 0; c2 <= N; c2++) u2[c2] = make_double2(w[2 * c2], w[2 * c2 + 1]);
+                    for (int c2 = 0; c2 <= N; c2++)
+                        if (c2 < len2) u2[c2] = make_double2(w[2 * c2], w[2 * c2 + 1]);
                 }
                 live = act;      // the n rows that were never pivots carry over:
                                  // their next-layer coefficients already sit in w[0..N-1]
@@ -647,8 +697,11 @@ disort_fast_kernel(const LaunchArgs a)
 #pragma unroll
                     for (int j = N; j < 2 * N; j++) w[j] = 0.0;
                 }
+                cp_async_wait_all();       // record lc+2 has landed
+                __syncwarp();
             }
         }
+        cp_async_wait_all();
         __syncwarp();
         __threadfence_block();
 
@@ -658,15 +711,30 @@ disort_fast_kernel(const LaunchArgs a)
 #pragma unroll
             for (int j = 0; j < N; j++) xs[j] = 0.0;
             int lu_next = NT - 1;  // levels are visited bottom-up when the map is monotone
+            // pivot rows + record of layer lc-1 stream into the other half of a double
+            // buffer (cp.async) while layer lc is being solved
+            constexpr int kSlot = FL::ublk + FL::rec;
+            auto fetch_layer = [&](int lyr, int buf) {
+                double *dstp = tsm_base + buf * kSlot;
+                warp_copy_async(dstp, ublk + (size_t)lyr * FL::ublk, FL::ublk, lane);
+                warp_copy_async(dstp + FL::ublk, recs + (size_t)lyr * FL::rec, FL::rec, lane);
+                cp_async_commit();
+            };
+            fetch_layer(ncut - 1, 0);
             for (int lc = ncut - 1; lc >= 0; lc--) {
-                const double *rc = recs + (size_t)lc * FL::rec;
+                const int buf = (ncut - 1 - lc) & 1;
+                if (lc > 0) { fetch_layer(lc - 1, buf ^ 1); cp_async_wait_one(); }
+                else cp_async_wait_all();
+                __syncwarp();
+                const double *ubuf = tsm_base + buf * kSlot;
+                const double *rc = ubuf + FL::ublk;
                 double acc = 0.0, diag = 1.0;
                 double ur[N];      // row `lane` of the upper triangle
 #pragma unroll
                 for (int j = 0; j < N; j++) ur[j] = 0.0;
                 if (lane < N) {
                     // stored row `lane`: entry i is column lane+i (see phase 2)
-                    const double *u = ublk + ((size_t)lc * N + lane) * FL::urow - lane;
+                    const double *u = ubuf + FL::uoff(lane) - lane;
                     acc = u[2 * N];
 #pragma unroll
                     for (int j = 0; j < N; j++) acc = fma(-u[N + j], xs[j], acc);
@@ -746,8 +814,10 @@ disort_fast_kernel(const LaunchArgs a)
                         if (o_dfdt) o_dfdt[lu] = (1. - ss) * 4. * pi * (uavg - plsorc);
                     }
                 }
+                __syncwarp();     // everyone is done with this half of the double buffer
             }
         }
+        cp_async_wait_all();
         if (lane == 0) a.status[bin] = status;
         __syncwarp();
     }
