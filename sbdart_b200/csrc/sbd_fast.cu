@@ -50,15 +50,15 @@ struct FastLayout {
     static constexpr int cta = 4 * n + N * n;
     static constexpr int tasks = 32 / n;
     static constexpr int task = N + 4 * n * n + 4 * n;     // gl, K, L, G1, G2, vectors
+    // work area shared by the phases: per-task areas (phase 1), 3 records (phase 2),
+    // 2 x (pivot rows + record) (phase 3)
+    static constexpr int cmax(int a, int b) { return a > b ? a : b; }
+    static constexpr int work = cmax(cmax(tasks * task, 3 * rec), 2 * (ublk + rec));
     __host__ __device__ static size_t warp_doubles(int L, int NT)
     {
         // pivot-row double buffer, y0, taucpr/tauc/pk(+2 boundary temps), prologue
         // work, level map, per-task areas; kept even for 16-byte alignment
-        size_t work = (size_t)tasks * task;              // phase 1: per-task areas
-        size_t p2 = 3 * (size_t)rec, p3 = 2 * (size_t)(ublk + rec);   // phase 2 / 3 staging
-        if (p2 > work) work = p2;
-        if (p3 > work) work = p3;
-        size_t d = (size_t)4 * (N + 1) + N + 3 * (L + 1) + 2 + 3 * L + (NT + 1) / 2 + 2 + work;
+        size_t d = (size_t)4 * (N + 1) + N + work + 3 * (L + 1) + 2 + 3 * L + (NT + 1) / 2 + 2;
         return (d + 1) & ~(size_t)1;
     }
 };
@@ -399,6 +399,44 @@ __device__ __forceinline__ void gc_row_scaled(const double *rec, int r, bool bot
     }
 }
 
+// One column of the sliding-window elimination (lane = matrix row, w[0] = current
+// column).  W2 = highest pair index still alive.  Returns 0 or SBD_BIN_SINGULAR.
+template <int N, int W2>
+__device__ __forceinline__ int elim_column(double (&w)[2 * N + 2], double2 *pb, unsigned &act,
+                                           int &mycol, int j, int lane)
+{
+    const bool cand = (act >> lane) & 1u;
+    const double av = cand ? fabs(w[0]) : -1.0;
+    // pivot: largest |a| by high word (any near-maximal pivot is as stable)
+    const int hi = cand ? __double2hiint(av) : -1;
+    const int mx = __reduce_max_sync(FULLMASK, hi);
+    const unsigned who = __ballot_sync(FULLMASK, hi == mx && cand);
+    if (mx <= 0 || who == 0) return SBD_BIN_SINGULAR;
+    const int pl = __ffs(who) - 1;
+    const bool ispiv = (lane == pl);
+    // the pivot row travels through shared memory (double-buffered by column
+    // parity): 16-byte stores by one lane, broadcast 16-byte loads
+    if (ispiv) {
+#pragma unroll
+        for (int c2 = 0; c2 <= W2; c2++) pb[c2] = make_double2(w[2 * c2], w[2 * c2 + 1]);
+        mycol = j;      // this row now rests (entry i = column j+i)
+    }
+    __syncwarp();
+    if (cand && !ispiv) {
+        const double2 p0 = pb[0];
+        const double mlt = w[0] * fast_rcp(p0.x);
+        w[0] = fma(-mlt, p0.y, w[1]);
+#pragma unroll
+        for (int c2 = 1; c2 <= W2; c2++) {
+            const double2 p = pb[c2];
+            w[2 * c2 - 1] = fma(-mlt, p.x, w[2 * c2]);
+            w[2 * c2] = fma(-mlt, p.y, w[2 * c2 + 1]);
+        }
+    }
+    act &= ~(1u << pl);
+    return 0;
+}
+
 template <int n>
 __global__ void __launch_bounds__(128, 4)
 disort_fast_kernel(const LaunchArgs a)
@@ -412,12 +450,14 @@ disort_fast_kernel(const LaunchArgs a)
     extern __shared__ double smem_fast[];
     double *cmu = smem_fast, *cwt = cmu + n, *csq = cwt + n, *cdinv = csq + n, *cylm = cdinv + n;
     double *wsm = smem_fast + FL::cta + (size_t)warp * FL::warp_doubles(L, NT);
+    // fixed-offset areas first (addresses are wsm + constant), run-time sized arrays last
     double2 *prow2 = reinterpret_cast<double2 *>(wsm);          // 2 x (N+1) pairs, 16-byte aligned
-    double *y0 = wsm + 4 * (N + 1), *taucpr = y0 + N, *tauc = taucpr + (L + 1), *pk = tauc + (L + 1);
+    double *y0 = wsm + 4 * (N + 1);
+    // 16-byte aligned work area: per-task areas in phase 1, cp.async staging afterwards
+    double *tsm_base = y0 + N;
+    double *taucpr = tsm_base + FL::work, *tauc = taucpr + (L + 1), *pk = tauc + (L + 1);
     double *lw = pk + (L + 3);                                   // 3 x L prologue work values
     int *layru = (int *)(lw + 3 * L);
-    // 16-byte aligned work area: per-task areas in phase 1, cp.async staging afterwards
-    double *tsm_base = wsm + ((((lw + 3 * L + (NT + 1) / 2) - wsm) + 1) & ~(ptrdiff_t)1);
 
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         double mu = a.quad[i], wt = a.quad[n + i];
@@ -647,39 +687,14 @@ disort_fast_kernel(const LaunchArgs a)
                 // leading entry, so the current column is always w[0] and ONE copy
                 // of the loop body serves all N columns (I-cache friendly).
                 int mycol = -1;     // which pivot column this lane's row became
+                // the live width shrinks by one per column: the second half of the columns
+                // only touches 3N/4 + 1 pairs
 #pragma unroll 1
-                for (int j = 0; j < N; j++) {
-                    const bool cand = (act >> lane) & 1u;
-                    const double av = cand ? fabs(w[0]) : -1.0;
-                    // pivot: largest |a| by high word (any near-maximal pivot is as stable)
-                    int hi = cand ? __double2hiint(av) : -1;
-                    int mx = __reduce_max_sync(FULLMASK, hi);
-                    unsigned who = __ballot_sync(FULLMASK, hi == mx && cand);
-                    if (mx <= 0 || who == 0) { status = SBD_BIN_SINGULAR; break; }
-                    const int pl = __ffs(who) - 1;
-                    const bool ispiv = (lane == pl);
-                    // the pivot row travels through shared memory (double-buffered by
-                    // column parity): 16-byte stores by one lane, broadcast 16-byte loads
-                    double2 *pb = prow2 + (j & 1) * (N + 1);
-                    if (ispiv) {
-#pragma unroll
-                        for (int c2 = 0; c2 <= N; c2++) pb[c2] = make_double2(w[2 * c2], w[2 * c2 + 1]);
-                        mycol = j;      // this row now rests (entry i = column j+i)
-                    }
-                    __syncwarp();
-                    if (cand && !ispiv) {
-                        const double2 p0 = pb[0];
-                        const double mlt = w[0] * fast_rcp(p0.x);
-                        w[0] = fma(-mlt, p0.y, w[1]);
-#pragma unroll
-                        for (int c2 = 1; c2 <= N; c2++) {
-                            const double2 p = pb[c2];
-                            w[2 * c2 - 1] = fma(-mlt, p.x, w[2 * c2]);
-                            w[2 * c2] = fma(-mlt, p.y, w[2 * c2 + 1]);
-                        }
-                    }
-                    act &= ~(1u << pl);
-                }
+                for (int j = 0; j < N / 2 && !status; j++)
+                    status = elim_column<N, N>(w, prow2 + (j & 1) * (N + 1), act, mycol, j, lane);
+#pragma unroll 1
+                for (int j = N / 2; j < N && !status; j++)
+                    status = elim_column<N, N - N / 4>(w, prow2 + (j & 1) * (N + 1), act, mycol, j, lane);
                 if (status) break;
                 // pivot rows -> scratch, packed: row j holds columns j..2N at entries
                 // 0..2N-j of a slice of even length starting at uoff(j)
@@ -777,17 +792,31 @@ disort_fast_kernel(const LaunchArgs a)
                         const double *gp = rc + FL::off_gp + i * n, *gm = rc + FL::off_gm + i * n;
                         const bool atbot = (a.d.ntau == 0 && lu == lc + 1);
                         const bool attop = (a.d.ntau == 0 && lu == lc);
-                        double s = 0.0;
+                        // a_j = x+_j exp(-k_j (t - t_top)), b_j = x-_j exp(-k_j (t_bot - t)); at a
+                        // layer boundary the factors are 1 and the stored exp(-k dtau')
+                        double s0 = 0.0, s1 = 0.0;
+                        if (atbot || attop) {
 #pragma unroll
-                        for (int j = 0; j < n; j++) {
-                            const double k = rc[FL::off_kk + j], e = rc[FL::off_ek + j];
-                            double ep, em;     // exp(-k(t - t_top)), exp(-k(t_bot - t))
-                            if (atbot) { ep = e; em = 1.0; }
-                            else if (attop) { ep = 1.0; em = e; }
-                            else { ep = exp(-k * (utp - taucpr[lc])); em = exp(-k * (taucpr[lc + 1] - utp)); }
-                            const double aj = xs[n + j] * ep, bj = xs[n - 1 - j] * em;
-                            s += up ? (gp[j] * aj - gm[j] * bj) : (gm[j] * aj - gp[j] * bj);
+                            for (int j = 0; j < n; j++) {
+                                const double e = rc[FL::off_ek + j];
+                                const double pj = up ? gp[j] : gm[j], mj = up ? gm[j] : gp[j];
+                                s0 = fma(pj, xs[n + j] * (atbot ? e : 1.0), s0);
+                                s1 = fma(mj, xs[n - 1 - j] * (atbot ? 1.0 : e), s1);
+                            }
+                        } else {     // level inside a layer (USRTAU): rolled loop, x from local memory
+                            const double d1 = utp - taucpr[lc], d2 = taucpr[lc + 1] - utp;
+                            double xl[N];
+#pragma unroll
+                            for (int j = 0; j < N; j++) xl[j] = xs[j];
+#pragma unroll 1
+                            for (int j = 0; j < n; j++) {
+                                const double k = rc[FL::off_kk + j];
+                                const double pj = up ? gp[j] : gm[j], mj = up ? gm[j] : gp[j];
+                                s0 = fma(pj, xl[n + j] * exp(-k * d1), s0);
+                                s1 = fma(mj, xl[n - 1 - j] * exp(-k * d2), s1);
+                            }
                         }
+                        const double s = s0 - s1;
                         const int r = up ? n + i : n - 1 - i;
                         uval = s + rc[FL::off_zz + r] * fact + rc[FL::off_zp0 + r] + xr1 * utp;
                         wgt = cwt[i]; wm = cwt[i] * cmu[i];
