@@ -137,6 +137,70 @@ int64_t sbd_kernel_launches(const sbd_handle *h);
  * (same rule as QGAUSN, disort.f:5984). Host-only helper. */
 int sbd_quadrature(int m, double *mu, double *wt);
 
+/* ------------------------------------------------------------------------
+ * Whole-spectrum path: the optical-property producers of the wavelength loop
+ * (gasset/taugas/kdistr/taucor taugas.f:7392,2236,1802,7650; taucloud/cloudpar
+ * taucloud.f:10,344; rayleigh spectra.f:206; normom drt.f:1366; depthscl
+ * taugas.f:7512; solirr/salbedo/wllimits) run in a GPU kernel that writes the
+ * DISORT inputs of every (wavelength, k-term) bin straight into HBM; the solve
+ * kernel follows on the same stream.  Only the per-run setup (atmosphere,
+ * absorber amounts uu(63,nz) of absint, cloud layer list, tables) comes from
+ * the host.  Covers what the reference does for iaer=0, isat<=0, Lambertian
+ * surfaces (the configs of SURVEY section 8).
+ * ------------------------------------------------------------------------ */
+typedef struct sbd_optics_params {
+    int32_t nz;        /* levels = DISORT layers            */
+    int32_t nwl;       /* wavelengths (setfilt, spectra.f:3370-3384)               */
+    int32_t kdist;     /* 0..3 (taugas.f:7441, :7562-7590)                         */
+    int32_t nstr;      /* streams; nmom = min(nstr+2, 40) moments are produced      */
+    int32_t nf;        /* 0: unit solar flux, else the table wlsun/sun is used      */
+    int32_t nothrm;    /* <0: Planck for wl > 2 um; 0: always; >0: never (drt.f:463)*/
+    int32_t imomc;     /* cloud phase function model: 3 = Henyey-Greenstein         */
+    int32_t ncloud;    /* entries of the cloud layer list                           */
+    int32_t nalb, nsun;/* table lengths                                             */
+    int32_t night;     /* sza >= 90: flxin = 0, amu0 = 1 (drt.f:456-459)            */
+    int32_t pad_;
+    double wl1, wl2, wlinc;      /* wavelength grid (wllimits, drt.f:1657)          */
+    double amu0, xo4, xrsc, solfac, phi0, fisot, temis, btemp, ttemp;
+} sbd_optics_params;
+
+/* One (cloud layer, DISORT layer) pair of taucloud's double loop
+ * (taucloud.f:61-124), resolved on the host because it does not depend on
+ * wavelength. */
+typedef struct sbd_cloud_entry {
+    int32_t layer;     /* DISORT layer j, 1-based from the top                      */
+    int32_t use_tau;   /* tcloud given: tau = tcld*qc/q550; else LWP form           */
+    double reff;       /* effective radius (um); < 0 selects ice                    */
+    double tcld;       /* optical depth share of this layer at 0.55 um              */
+    double lwpth;      /* liquid water path share (g/m2)                            */
+    double q550;       /* extinction efficiency at 0.55 um (first-call cache)       */
+} sbd_cloud_entry;
+
+/* Upload the packed table bundle (frontend/device.py); index = offsets then
+ * lengths, 2 x ntab int32.  Call once per handle. */
+int sbd_optics_upload_tables(sbd_handle *h, const double *tables, int64_t ntables_doubles,
+                             const int32_t *index, int32_t ntab);
+
+/* Produce every bin of a run on the device and solve it.  All array arguments
+ * are HOST pointers.  Outputs (host): nk[nwl], wl[nwl], dwl[nwl], wt[3*nwl]
+ * (slot 3*il+kd), *nbins = sum nk; fluxes compact per bin in loop order:
+ * rfldir, rfldn, flup [nbins][nz+1] (buffers sized for 3*nwl bins), uu
+ * [nbins][nphi][nz+1][numu] when numu > 0, status[nbins].  If inputs_out is
+ * non-NULL the produced DISORT inputs are copied back too (parity tests):
+ * dtauc, ssalb [3 nwl][nz], pmom [3 nwl][nz][nmom+1], bins [3 nwl]. */
+typedef struct sbd_inputs_out {
+    double *dtauc, *ssalb, *pmom;
+    sbd_bin *bins;
+} sbd_inputs_out;
+
+int sbd_spectrum_run(sbd_handle *h, const sbd_optics_params *p, const double *z, const double *pr,
+                     const double *t, const double *uu, const sbd_cloud_entry *clouds,
+                     const double *wlalb, const double *alb, const double *wlsun, const double *sun,
+                     int32_t numu, const double *umu, int32_t nphi, const double *phi,
+                     int32_t *nk, double *wl, double *dwl, double *wt, int32_t *nbins,
+                     double *rfldir, double *rfldn, double *flup, double *uuout, int32_t *status,
+                     const sbd_inputs_out *inputs_out);
+
 /* Diagnostic: sustained FP64 FMA throughput of the device in TFLOP/s (FMA = 2
  * flops), best of `reps` launches of a register-resident DFMA loop.  Used as
  * the roofline denominator of the solver kernel in bench.py. */

@@ -30,7 +30,7 @@ EXPORTS = (
     "sbd_create", "sbd_destroy", "sbd_disort_batch", "sbd_disort_batch_device",
     "sbd_synchronize", "sbd_stream", "sbd_kernel_launches", "sbd_quadrature",
     "sbd_status_string", "sbd_abi_version", "disort_", "sbd_disort_last_status",
-    "sbd_measure_fp64_peak",
+    "sbd_measure_fp64_peak", "sbd_optics_upload_tables", "sbd_spectrum_run",
 )
 
 

@@ -11,6 +11,7 @@
 #include <mutex>
 #include <vector>
 
+#include "sbd_handle.h"
 #include "sbd_internal.h"
 
 using namespace sbd;
@@ -82,43 +83,7 @@ void legendre_table(int M, int lmax, int nx, const double *x, double *out)
     }
 }
 
-struct DevBuf {
-    void *p = nullptr;
-    size_t cap = 0;
-    cudaError_t reserve(size_t bytes)
-    {
-        if (bytes <= cap) return cudaSuccess;
-        if (p) cudaFree(p);
-        p = nullptr; cap = 0;
-        size_t want = bytes + bytes / 4 + 256;
-        cudaError_t e = cudaMalloc(&p, want);
-        if (e == cudaSuccess) cap = want;
-        return e;
-    }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
-};
-
-struct Tables {
-    double *quad = nullptr;   // [2n]
-    double *ylmc = nullptr;   // [N][N][n]
-};
-
 }  // namespace
-
-struct sbd_handle {
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    cudaStream_t copy_in = nullptr, copy_out = nullptr;   // H2D / D2H overlap in the host-buffer call
-    cudaEvent_t ev_in[8] = {}, ev_k[8] = {};
-    int sm_count = 0;
-    size_t smem_optin = 0;
-    int64_t launches = 0;
-    std::map<int, Tables> tables;          // per NSTR
-    DevBuf scratch, counter, ylmu, angles;
-    // staging for the host-pointer API
-    DevBuf d_dtauc, d_ssalb, d_pmom, d_bins, d_temper, d_utau, d_out, d_uu, d_status;
-    std::vector<double> h_umu_key;
-};
 
 static int check_dims(const sbd_dims *d)
 {
@@ -186,10 +151,10 @@ extern "C" void sbd_destroy(sbd_handle *h)
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     for (auto &kv : h->tables) { cudaFree(kv.second.quad); cudaFree(kv.second.ylmc); }
-    DevBuf *bufs[] = { &h->scratch, &h->counter, &h->ylmu, &h->angles, &h->d_dtauc, &h->d_ssalb,
+    SbdDevBuf *bufs[] = { &h->scratch, &h->counter, &h->ylmu, &h->angles, &h->d_dtauc, &h->d_ssalb,
                        &h->d_pmom, &h->d_bins, &h->d_temper, &h->d_utau, &h->d_out, &h->d_uu,
-                       &h->d_status };
-    for (DevBuf *b : bufs) b->release();
+                       &h->d_status, &h->opt_tables, &h->opt_atm, &h->opt_misc, &h->opt_map };
+    for (SbdDevBuf *b : bufs) b->release();
     for (int i = 0; i < 8; i++) { cudaEventDestroy(h->ev_in[i]); cudaEventDestroy(h->ev_k[i]); }
     cudaStreamDestroy(h->copy_in);
     cudaStreamDestroy(h->copy_out);
@@ -207,7 +172,7 @@ extern "C" void *sbd_stream(sbd_handle *h) { return h ? (void *)h->stream : null
 
 extern "C" int64_t sbd_kernel_launches(const sbd_handle *h) { return h ? h->launches : 0; }
 
-static int get_tables(sbd_handle *h, int N, Tables &t, cudaStream_t st)
+int sbd_get_tables(sbd_handle *h, int N, SbdTables &t, cudaStream_t st)
 {
     auto it = h->tables.find(N);
     if (it != h->tables.end()) { t = it->second; return SBD_SUCCESS; }
@@ -215,7 +180,7 @@ static int get_tables(sbd_handle *h, int N, Tables &t, cudaStream_t st)
     std::vector<double> quad(2 * n), ylm((size_t)N * N * n);
     gauss01(n, quad.data(), quad.data() + n);
     legendre_table(N, N - 1, n, quad.data(), ylm.data());
-    Tables nt;
+    SbdTables nt;
     if (cudaMalloc(&nt.quad, quad.size() * 8) != cudaSuccess) return SBD_ERR_CUDA;
     if (cudaMalloc(&nt.ylmc, ylm.size() * 8) != cudaSuccess) return SBD_ERR_CUDA;
     cudaMemcpyAsync(nt.quad, quad.data(), quad.size() * 8, cudaMemcpyHostToDevice, st);
@@ -255,8 +220,8 @@ extern "C" int sbd_disort_batch_device(sbd_handle *h, const sbd_dims *dims, cons
 
     const int N = dims->nstr, L = dims->nlyr;
     const int NT = dims->ntau > 0 ? dims->ntau : L + 1;
-    Tables tb;
-    rc = get_tables(h, N, tb, st);
+    SbdTables tb;
+    rc = sbd_get_tables(h, N, tb, st);
     if (rc) return rc;
 
     size_t smem_limit = h->smem_optin ? h->smem_optin : 48 * 1024;
@@ -307,6 +272,8 @@ extern "C" int sbd_disort_batch_device(sbd_handle *h, const sbd_dims *dims, cons
     }
     a.rfldir = rfldir; a.rfldn = rfldn; a.flup = flup; a.dfdt = dfdt; a.uavg = uavg; a.uu = uu;
     a.status = status;
+    a.binmap = h->pending_binmap;      // set by the spectrum path for exactly one launch
+    h->pending_binmap = nullptr;
     a.quad = tb.quad; a.ylmc = tb.ylmc;
     a.nslots = grid * warps;
     a.slot_stride = slot;

@@ -478,10 +478,11 @@ disort_fast_kernel(const LaunchArgs a)
         if (lane == 0) bin = atomicAdd(a.work_counter, 1);
         bin = __shfl_sync(FULLMASK, bin, 0);
         if (bin >= a.d.nbins) break;
-        const sbd_bin bp = a.bins[bin];
-        const double *dtauc = a.dtauc + (size_t)bin * L;
-        const double *ssalb = a.ssalb + (size_t)bin * L;
-        const double *pmom = a.pmom + (size_t)bin * L * ldp;
+        const int src = a.binmap ? a.binmap[bin] : bin;     // input slot of this bin
+        const sbd_bin bp = a.bins[src];
+        const double *dtauc = a.dtauc + (size_t)src * L;
+        const double *ssalb = a.ssalb + (size_t)src * L;
+        const double *pmom = a.pmom + (size_t)src * L * ldp;
         const double fbeam = bp.fbeam, umu0 = bp.umu0, albedo = bp.albedo;
         const bool plank = bp.plank != 0;
         double *o_rfldir = a.rfldir ? a.rfldir + (size_t)bin * NT : nullptr;
@@ -543,7 +544,7 @@ disort_fast_kernel(const LaunchArgs a)
         __syncwarp();
         int badtau = 0;
         for (int lu = lane; lu < NT; lu += 32) {
-            double ut = a.d.ntau > 0 ? a.utau[(size_t)bin * NT + lu] : tauc[lu];
+            double ut = a.d.ntau > 0 ? a.utau[(size_t)src * NT + lu] : tauc[lu];
             if (a.d.ntau > 0 && fabs(ut - tauc[L]) <= 1.e-4) ut = tauc[L];
             if (a.d.ntau > 0 && !(ut >= 0.0 && ut <= tauc[L])) badtau = 1;
             int lc;
@@ -771,7 +772,7 @@ disort_fast_kernel(const LaunchArgs a)
                 for (int lu = fastmap ? lu_next : NT - 1; lu >= 0; lu--) {
                     if (layru[lu] != lc + 1) { if (fastmap) break; else continue; }
                     if (fastmap) lu_next = lu - 1;
-                    double ut = a.d.ntau > 0 ? a.utau[(size_t)bin * NT + lu] : tauc[lu];
+                    double ut = a.d.ntau > 0 ? a.utau[(size_t)src * NT + lu] : tauc[lu];
                     if (a.d.ntau > 0 && fabs(ut - tauc[L]) <= 1.e-4) ut = tauc[L];
                     double ss = ssalb[lc]; if (ss == 1.0) ss = 1.0 - kDither;
                     const double f = pmom[(size_t)lc * ldp + N];

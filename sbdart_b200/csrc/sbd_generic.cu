@@ -750,14 +750,15 @@ disort_generic_kernel(const LaunchArgs a)
         bin = __shfl_sync(FULLMASK, bin, 0);
         if (bin >= a.d.nbins) break;
 
-        const sbd_bin bp = a.bins[bin];
+        const int src = a.binmap ? a.binmap[bin] : bin;     // input slot of this bin
+        const sbd_bin bp = a.bins[src];
         BinCtx c;
         c.N = N; c.n = n; c.L = L; c.NT = NT; c.mazim = 0; c.delm0 = 1.0;
         c.fbeam = bp.fbeam; c.umu0 = bp.umu0; c.albedo = bp.albedo; c.fisot = bp.fisot;
         c.plank = bp.plank;
-        c.dtauc = a.dtauc + (size_t)bin * L;
-        c.ssalb = a.ssalb + (size_t)bin * L;
-        c.pmom = a.pmom + (size_t)bin * L * ldp;
+        c.dtauc = a.dtauc + (size_t)src * L;
+        c.ssalb = a.ssalb + (size_t)src * L;
+        c.pmom = a.pmom + (size_t)src * L * ldp;
         c.ldp = ldp;
         double *o_rfldir = a.rfldir ? a.rfldir + (size_t)bin * NT : nullptr;
         double *o_rfldn = a.rfldn ? a.rfldn + (size_t)bin * NT : nullptr;
@@ -819,7 +820,7 @@ disort_generic_kernel(const LaunchArgs a)
         // level -> layer map and scaled level depths (disort.f:2610-2625)
         int badtau = 0;
         for (int lu = lane; lu < NT; lu += 32) {
-            double ut = a.d.ntau > 0 ? a.utau[(size_t)bin * NT + lu] : w.tauc[lu];
+            double ut = a.d.ntau > 0 ? a.utau[(size_t)src * NT + lu] : w.tauc[lu];
             if (a.d.ntau > 0 && fabs(ut - w.tauc[L]) <= 1.e-4) ut = w.tauc[L];
             if (a.d.ntau > 0 && !(ut >= 0.0 && ut <= w.tauc[L])) badtau = 1;
             int lc;
@@ -1038,7 +1039,7 @@ disort_generic_kernel(const LaunchArgs a)
                 // fluxes at the levels that live in this layer (FLUXES), m = 0 only
                 for (int lu = 0; lu < NT && mazim == 0; lu++) {
                     if (w.layru[lu] != lc + 1) continue;
-                    double ut = a.d.ntau > 0 ? a.utau[(size_t)bin * NT + lu] : w.tauc[lu];
+                    double ut = a.d.ntau > 0 ? a.utau[(size_t)src * NT + lu] : w.tauc[lu];
                     if (a.d.ntau > 0 && fabs(ut - w.tauc[L]) <= 1.e-4) ut = w.tauc[L];
                     double ss = c.ssalb[lc]; if (ss == 1.0) ss = 1.0 - kDither;
                     const double f = c.pmom[(size_t)lc * ldp + N];
@@ -1098,7 +1099,7 @@ disort_generic_kernel(const LaunchArgs a)
             for (int e = lane; e < NT * NU; e += 32) {
                 const int lu = e / NU, iu = e - lu * NU;
                 const int lyu = w.layru[lu];
-                double ut = a.d.ntau > 0 ? a.utau[(size_t)bin * NT + lu] : w.tauc[lu];
+                double ut = a.d.ntau > 0 ? a.utau[(size_t)src * NT + lu] : w.tauc[lu];
                 if (a.d.ntau > 0 && fabs(ut - w.tauc[L]) <= 1.e-4) ut = w.tauc[L];
                 double ss = c.ssalb[lyu - 1]; if (ss == 1.0) ss = 1.0 - kDither;
                 const double f = c.pmom[(size_t)(lyu - 1) * ldp + N];

@@ -1,0 +1,49 @@
+// The opaque solver handle of the C ABI: a CUDA stream plus grow-only device buffers.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <map>
+#include <vector>
+
+#include "sbd_internal.h"
+#include "sbd_optics.cuh"
+
+struct SbdDevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct SbdTables {
+    double *quad = nullptr;   // [2n]
+    double *ylmc = nullptr;   // [N][N][n]
+};
+
+struct sbd_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;   // H2D / D2H overlap in the host-buffer call
+    cudaEvent_t ev_in[8] = {}, ev_k[8] = {};
+    int sm_count = 0;
+    size_t smem_optin = 0;
+    int64_t launches = 0;
+    std::map<int, SbdTables> tables;          // per NSTR
+    SbdDevBuf scratch, counter, ylmu, angles;
+    // staging for the host-pointer API
+    SbdDevBuf d_dtauc, d_ssalb, d_pmom, d_bins, d_temper, d_utau, d_out, d_uu, d_status;
+    // whole-spectrum path (sbd_spectrum.cu)
+    SbdDevBuf opt_tables, opt_atm, opt_misc, opt_map;
+    sbd::OpticsTables opt_index = {};
+    bool opt_ready = false;
+    const int32_t *pending_binmap = nullptr;   // device bin -> slot map for the next solve launch
+};

@@ -29,6 +29,8 @@ struct LaunchArgs {
     int nslots;           // number of concurrently resident warps
     int nmodes;           // azimuth modes to run (1 for flux-only)
     int *work_counter;    // dynamic bin scheduler
+    const int32_t *binmap; // optional: bin b reads its inputs from slot binmap[b]
+    const int32_t *nbins_dev; // optional: number of bins lives on the device (spectrum path)
 };
 
 // Per-layer record kept in scratch between the downward elimination sweep

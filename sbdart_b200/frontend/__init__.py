@@ -1198,6 +1198,31 @@ class Sbdart:
     def run(self, solve):
         """solve(batch) -> dict(rfldir, rfldn, flup [B][nz+1][, uu [B][nphi][nz+1][numu]], status)."""
         rows = self.bins()
+        res = None
+        if rows:
+            # ff == 0 bins are skipped by the reference (drt.f:539); none for isat <= 0
+            b = self.batch(rows)
+            res = solve(b)
+            bad = np.asarray(res["status"]) != 0
+            if bad.any():
+                res = self._retry(b, res, solve)
+        return self.records(rows, res)
+
+    def run_device(self, solver):
+        """Whole-spectrum GPU path: the optical properties of every bin are produced
+        by the K2 kernel and never leave the device (frontend/device.py)."""
+        from .device import run_spectrum
+        rows, res = run_spectrum(self, solver)
+        if (res["status"] != 0).any():
+            # beam / quadrature clash (drt.f:536-554): fall back to the host-side batch
+            # for the retry logic (rare: one NSTR-dependent angle)
+            return self.run(lambda b: solver.disort_batch(
+                b["dtauc"], b["ssalb"], b["pmom"], b["bins"], nstr=b["nstr"], temper=b["temper"],
+                umu=b.get("umu"), phi=b.get("phi")))
+        return self.records(rows, res)
+
+    def records(self, rows, res):
+        """stdout0/1/2 (drt.f:892-1165): ordered accumulation and IOUT records."""
         out = []
         iout, nz = self.p["iout"], self.nz
         if iout in (1, 5, 6):
@@ -1208,13 +1233,6 @@ class Sbdart:
             out.append("")
             out.append('"fzw')
             out.append(f"{nz:15d}")
-        if rows:
-            # ff == 0 bins are skipped by the reference (drt.f:539); none for isat <= 0
-            b = self.batch(rows)
-            res = solve(b)
-            bad = np.asarray(res["status"]) != 0
-            if bad.any():
-                res = self._retry(b, res, solve)
         ntop, nbot = self.ntop - 1, self.nbot - 1          # 0-based level indices
         topdn = topup = topdir = botdn = botup = botdir = 0.0
         weq = wfull = phidw = 0.0

@@ -1,0 +1,190 @@
+"""Whole-spectrum GPU path: pack the tables for the producer kernel (K2,
+csrc/sbd_optics.cu), hand the per-run setup to sbd_spectrum_run and feed the
+per-bin fluxes back into the record formatter of frontend.Sbdart.
+
+Table order = enum OpticsTable in csrc/sbd_optics.cuh.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from .. import BIN_DTYPE, SbdError, lib
+from . import (NCLDZ, T, _BANDS, _MOLS, Sbdart, cloudpar, f32, levrng)
+
+
+class OpticsParams(C.Structure):
+    """struct sbd_optics_params (include/sbdart_b200.h)."""
+
+    _fields_ = [(k, C.c_int32) for k in (
+        "nz", "nwl", "kdist", "nstr", "nf", "nothrm", "imomc", "ncloud", "nalb", "nsun", "night",
+        "pad_")] + [(k, C.c_double) for k in (
+            "wl1", "wl2", "wlinc", "amu0", "xo4", "xrsc", "solfac", "phi0", "fisot", "temis",
+            "btemp", "ttemp")]
+
+
+CLOUD_DTYPE = np.dtype([("layer", "<i4"), ("use_tau", "<i4"), ("reff", "<f8"), ("tcld", "<f8"),
+                        ("lwpth", "<f8"), ("q550", "<f8")])
+
+
+class InputsOut(C.Structure):
+    _fields_ = [("dtauc", C.c_void_p), ("ssalb", C.c_void_p), ("pmom", C.c_void_p),
+                ("bins", C.c_void_p)]
+
+
+def pack_tables():
+    """Flat float64 bundle + (offsets, lengths) in enum OpticsTable order."""
+    parts = [
+        T("taugas/slf296/s"), T("taugas/slf260/s"), T("taugas/frn296/f"),
+        T("taugas/c4dta/c4"), T("taugas/hno3/h1"), T("taugas/hno3/h2"), T("taugas/hno3/h3"),
+        T("taugas/o2cont/o2s0"), T("taugas/o2cont/o2a"), T("taugas/o2cont/o2b"),
+        T("taugas/o4cont/sig"),
+        T("taugas/o3hht/s0"), T("taugas/o3hht/s1"), T("taugas/o3hht/s2"), T("taugas/o3uv/s"),
+        T("taugas/c8dta/c8"), T("taugas/schrun/shn"), T("taugas/kdistr/fac"),
+    ]
+    for nm in ("qq", "ww", "gg", "qqi", "wwi", "ggi"):
+        parts.append(np.ascontiguousarray(T(f"taucloud/cloudpar/{nm}").T).ravel())   # [re][wl]
+    for pre in ("taugas/gasblk/cp", "taugas/gasblk/iwl", "taugas/gasblk/iwh", "taugas/abcdta/a",
+                "taugas/abcdta/aa", "taugas/abcdta/bb", "taugas/abcdta/cc"):
+        for m in _MOLS:
+            parts.append(np.atleast_1d(T(pre + m)).astype(float))
+    quads = []
+    for imol in sorted(_BANDS):
+        for iw, rngs in _BANDS[imol]:
+            for lo, hi in rngs:
+                quads += [imol, iw, lo, hi]
+    parts.append(np.array(quads, dtype=float))
+    parts = [np.asarray(p, dtype=np.float64).ravel() for p in parts]
+    lens = np.array([len(p) for p in parts], dtype=np.int32)
+    # every table starts on an even index (16-byte alignment is not required, but harmless)
+    offs = np.zeros(len(parts), dtype=np.int32)
+    flat = []
+    pos = 0
+    for i, p in enumerate(parts):
+        offs[i] = pos
+        flat.append(p)
+        pos += len(p)
+        if pos & 1:
+            flat.append(np.zeros(1))
+            pos += 1
+    return np.concatenate(flat), np.concatenate([offs, lens]).astype(np.int32)
+
+
+def cloud_entries(clouds):
+    """Resolve taucloud's (cloud layer i, DISORT layer j) loop (taucloud.f:61-124);
+    everything here is independent of wavelength."""
+    out = []
+    tcl, lw, nre = clouds.tcloud, clouds.lwp, clouds.nre
+    q550 = {}
+    for i in range(1, NCLDZ + 1):
+        lbot, ltop = levrng(clouds.lcld, i)
+        if lbot == 0 or (tcl[i - 1] == 0. and lw[i - 1] == 0.):
+            continue
+        for j in range(ltop, lbot + 1):
+            if ltop == lbot:
+                reff, tcld, lwpth = nre[i - 1], tcl[i - 1], lw[i - 1]
+            else:
+                wt = float(np.float32(j - ltop) / np.float32(lbot - ltop))
+                reff = nre[i] * (nre[i - 1] / nre[i]) ** wt
+                if tcl[i] == 0.:
+                    tcld = tcl[i - 1] / (lbot - ltop + 1)
+                else:
+                    tcld = 2 * tcl[i - 1] / ((lbot - ltop + 1) * (1. + tcl[i]))
+                    tcld = tcld + (lbot - j) * tcld * (tcl[i] - 1.) / (lbot - ltop)
+                if lw[i] == 0.:
+                    lwpth = lw[i - 1] / (lbot - ltop + 1)
+                else:
+                    lwpth = 2 * lw[i - 1] / ((lbot - ltop + 1) * (1. + lw[i]))
+                    lwpth = lwpth + (lbot - j) * lwpth * (lw[i] - 1.) / (lbot - ltop)
+            use_tau = int(tcl[i - 1] != 0.)
+            if use_tau and j not in q550:
+                q550[j] = cloudpar(f32(0.55), reff)[0]     # first-call cache of the reference
+            out.append((j, use_tau, reff, tcld, lwpth, q550.get(j, 1.0)))
+    return np.array(out, dtype=CLOUD_DTYPE) if out else np.zeros(0, dtype=CLOUD_DTYPE)
+
+
+_UPLOADED = set()
+
+
+def _bind(L):
+    if getattr(L, "_spectrum_bound", False):
+        return
+    L.sbd_optics_upload_tables.restype = C.c_int
+    L.sbd_optics_upload_tables.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int32]
+    L.sbd_spectrum_run.restype = C.c_int
+    L.sbd_spectrum_run.argtypes = ([C.c_void_p, C.POINTER(OpticsParams)] + [C.c_void_p] * 9 +
+                                   [C.c_int32, C.c_void_p, C.c_int32, C.c_void_p] + [C.c_void_p] * 10 +
+                                   [C.POINTER(InputsOut)])
+    L._spectrum_bound = True
+
+
+def run_spectrum(run: Sbdart, solver, want_inputs=False):
+    """All bins of `run` produced and solved on the GPU.  Returns (rows, result[, inputs])
+    shaped like Sbdart.bins() / a solve() result, in loop order."""
+    L = lib()
+    _bind(L)
+    if not getattr(solver, "_optics_tables_uploaded", False):
+        tab, index = pack_tables()
+        rc = L.sbd_optics_upload_tables(solver._h, tab.ctypes.data, len(tab), index.ctypes.data,
+                                        len(index) // 2)
+        if rc:
+            raise SbdError(rc, "sbd_optics_upload_tables")
+        solver._optics_tables_uploaded = True
+    p, nz, nwl = run.p, run.nz, run.nwl
+    P = OpticsParams()
+    P.nz, P.nwl, P.kdist, P.nstr, P.nf, P.nothrm, P.imomc = nz, nwl, run.kdist, p["nstr"], p["nf"], p["nothrm"], p["imomc"]
+    ce = cloud_entries(run.clouds) if run.clouds.mcldz > 0 else np.zeros(0, dtype=CLOUD_DTYPE)
+    wlalb = np.ascontiguousarray(run.albedo.wl, dtype=float)
+    alb = np.ascontiguousarray(run.albedo.alb, dtype=float)
+    wlsun = np.ascontiguousarray(run.sun.wl, dtype=float) if p["nf"] != 0 else np.zeros(2)
+    sun = np.ascontiguousarray(run.sun.s, dtype=float) if p["nf"] != 0 else np.zeros(2)
+    P.ncloud, P.nalb, P.nsun, P.night = len(ce), len(alb), len(sun), int(run.sza >= 90.)
+    P.wl1, P.wl2, P.wlinc, P.amu0 = run.wl1, run.wl2, run.wlinc, run.amu0
+    P.xo4, P.xrsc, P.solfac, P.phi0 = p["xo4"], p["xrsc"], p["solfac"], run.phi0
+    P.fisot, P.temis, P.btemp, P.ttemp = p["fisot"], p["temis"], run.btemp, run.ttemp
+    nmom = min(p["nstr"] + 2, 40)
+    nslot, NT = 3 * nwl, nz + 1
+    nk = np.zeros(nwl, np.int32)
+    wl, dwl, wt = np.zeros(nwl), np.zeros(nwl), np.zeros(nslot)
+    nbins = C.c_int32(0)
+    rfldir, rfldn, flup = (np.zeros((nslot, NT)) for _ in range(3))
+    status = np.zeros(nslot, np.int32)
+    numu = nphi = 0
+    umu = phi = uu = None
+    if run.radcalc:
+        umu, phi = np.ascontiguousarray(run.umu), np.ascontiguousarray(run.phi)
+        numu, nphi = len(umu), len(phi)
+        uu = np.zeros((nslot, nphi, NT, numu))
+    io = None
+    inputs = None
+    if want_inputs:
+        inputs = dict(dtauc=np.zeros((nslot, nz)), ssalb=np.zeros((nslot, nz)),
+                      pmom=np.zeros((nslot, nz, nmom + 1)), bins=np.zeros(nslot, dtype=BIN_DTYPE))
+        io = InputsOut(inputs["dtauc"].ctypes.data, inputs["ssalb"].ctypes.data,
+                       inputs["pmom"].ctypes.data, inputs["bins"].ctypes.data)
+    z, pr, t = (np.ascontiguousarray(a, dtype=float) for a in (run.z, run.pr, run.t))
+    uua = np.ascontiguousarray(run.uu, dtype=float)
+    ptr = lambda a: None if a is None else a.ctypes.data  # noqa: E731
+    rc = L.sbd_spectrum_run(
+        solver._h, C.byref(P), ptr(z), ptr(pr), ptr(t), ptr(uua), ptr(ce) if len(ce) else None,
+        ptr(wlalb), ptr(alb), ptr(wlsun), ptr(sun), numu, ptr(umu), nphi, ptr(phi), ptr(nk), ptr(wl),
+        ptr(dwl), ptr(wt), C.byref(nbins), ptr(rfldir), ptr(rfldn), ptr(flup), ptr(uu), ptr(status),
+        C.byref(io) if io is not None else None)
+    if rc:
+        raise SbdError(rc, "sbd_spectrum_run")
+    B = nbins.value
+    rows = []
+    slots = []
+    for il in range(nwl):
+        for kd in range(nk[il]):
+            rows.append(dict(il=il, kd=kd, nk=int(nk[il]), wl=wl[il], dwl=dwl[il], wt=wt[3 * il + kd], ff=1.0))
+            slots.append(3 * il + kd)
+    res = dict(rfldir=rfldir[:B], rfldn=rfldn[:B], flup=flup[:B], status=status[:B])
+    if uu is not None:
+        res["uu"] = uu[:B]
+    if want_inputs:
+        sl = np.array(slots)
+        inputs = {k: v[sl] for k, v in inputs.items()}
+        return rows, res, inputs
+    return rows, res
