@@ -306,15 +306,17 @@ optics_kernel(const OpticsArgs a)
     {
         const double wi = (double)il, nm1 = (double)(P.nwl - 1);
         if (P.wlinc > 1) {
-            auto f = [&](double x) { const double xx = x / nm1; return P.wl1 * P.wl2 / ((1. - xx) * P.wl2 + xx * P.wl1); };
+            auto f = [&](double x) { const double xx = x / nm1; // no FMA contraction: int(1e4/wl) below must land on the same side of a table
+                // boundary as the host front end when the grid hits exact wavenumbers
+                return __dmul_rn(P.wl1, P.wl2) / __dadd_rn(__dmul_rn(1. - xx, P.wl2), __dmul_rn(xx, P.wl1)); };
             wl = f(wi); ww1 = f(wi - .5); ww2 = f(wi + .5);
         } else if (P.wlinc < 0.) {
             const double wr = P.wl2 / P.wl1;
             auto f = [&](double x) { return P.wl1 * pow(wr, x / nm1); };
             wl = f(wi); ww1 = f(wi - .5); ww2 = f(wi + .5);
         } else {
-            wl = P.wl1 + wi * P.wlinc;
-            ww1 = wl - .5 * P.wlinc; ww2 = wl + .5 * P.wlinc;
+            wl = __dadd_rn(P.wl1, __dmul_rn(wi, P.wlinc));
+            ww1 = __dadd_rn(wl, -__dmul_rn(.5, P.wlinc)); ww2 = __dadd_rn(wl, __dmul_rn(.5, P.wlinc));
         }
         if (il == 0 && il != P.nwl - 1) ww1 = wl;
         if (il == P.nwl - 1 && il != 0) ww2 = wl;
