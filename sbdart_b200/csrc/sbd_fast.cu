@@ -1,7 +1,9 @@
 // Register-resident warp-per-bin discrete-ordinate kernel for NSTR = 4, 8, 16.
 //
 // Same mathematics as sbd_generic.cu (see the header comment there) but laid
-// out for the hardware:
+// out for the hardware.  The measured limiter of this kernel is the SM's
+// shared-memory / shuffle pipe (MIO), not the FP64 pipe, so every phase is
+// organised to move as few words between lanes as possible:
 //   phase 1  per-layer eigen / particular solutions.  A warp works on 32/n
 //            layers of its bin at once; each layer is owned by a group of n
 //            lanes, lane j holding ROW j (Cholesky factors) or COLUMN j
@@ -10,14 +12,21 @@
 //            T = L^T Pe~ L is solved as the SVD of A = K^T L (Pe~ = K K^T)
 //            by one-sided (Hestenes) Jacobi with round-robin pairing: the
 //            singular values are the DISORT eigenvalues k_j themselves.
-//   phase 2  downward elimination of the block-bidiagonal boundary system,
-//            one matrix row per lane ((n+N) x (2N+1) window in registers),
-//            pivot row broadcast by shuffles, pivot choice by REDUX on the
-//            high word of |a|.
-//   phase 3  upward back-substitution (row per lane) fused with the flux
-//            evaluation at the layer boundaries.
-// Per-layer records and pivot rows travel between the phases through a
-// per-warp scratch slot in global memory.
+//            Besides the layer record (eigenvectors, particular solutions)
+//            the phase emits the FLUX FUNCTIONALS of the layer: the quadrature
+//            sums of FLUXES (disort.f:1926-2006) applied to the eigenvectors,
+//            so that a level flux is later a dot product with the solution.
+//   phase 2  downward elimination of the block-bidiagonal boundary system with
+//            partial pivoting.  The (n+N) x (2N+1) window is tiled 2-D over the
+//            warp: 8 row groups x 4 column groups, each lane holding up to 3
+//            rows x n columns (+ the right-hand sides).  A pivot step moves only
+//            the lane's own column slice of the pivot row (one shuffle serves
+//            all four column groups) and its three multipliers; rows never
+//            travel through shared memory.
+//   phase 3  upward back-substitution (row per lane) and the level fluxes as
+//            dot products with the flux functionals.
+// Layer records, flux records and pivot rows travel between the phases through
+// a per-warp scratch slot in global memory, staged with cp.async.
 #include <math.h>
 
 #include "sbd_internal.h"
@@ -31,8 +40,7 @@ namespace sbd {
 template <int n>
 struct FastLayout {
     static constexpr int N = 2 * n;
-    static constexpr int C = 2 * N + 1;
-    // per-layer record (doubles)
+    // ---- per-layer record for assembling the boundary system (doubles) ----
     static constexpr int off_kk = 0;
     static constexpr int off_ek = n;
     static constexpr int off_gp = 2 * n;
@@ -41,24 +49,33 @@ struct FastLayout {
     static constexpr int off_zp0 = off_zz + N;
     static constexpr int off_xr = off_zp0 + N;
     static constexpr int rec = ((off_xr + 2 + 1) / 2) * 2;
-    // pivot rows, packed: row j keeps columns j..2N (C-j entries) in a slice of even length
-    __host__ __device__ static constexpr int ulen(int j) { return C + 1 - j - (j & 1); }
-    __host__ __device__ static constexpr int uoff(int j) { return (C + 1) * j - j * (j - 1) / 2 - j / 2; }
-    static constexpr int ublk = (C + 1) * N - N * (N - 1) / 2 - N / 2;      // = uoff(N), even
-    __host__ __device__ static size_t slot_doubles(int L) { return (size_t)L * (rec + ublk); }
-    // shared memory (doubles)
-    static constexpr int cta = 4 * n + N * n;
+    // ---- per-layer flux record (phase 3) ----
+    static constexpr int f_cu = 0;              // [3][N]: up, down, mean-intensity functionals
+    static constexpr int f_ek = 3 * N;          // [n] exp(-k dtau')
+    static constexpr int f_kk = 3 * N + n;      // [n] k
+    static constexpr int f_sc = 3 * N + 2 * n;  // zzw[3], zp0w[3], xr0, xr1, 1-w, 1-w f
+    static constexpr int frec = f_sc + 10;      // even
+    // ---- 2-D tiling of the elimination window ----
+    static constexpr int KS = (3 * n + 7) / 8;  // row slots per row group (8 groups)
+    static constexpr int LC = n;                // window columns per lane (4 column groups)
+    static constexpr int LH = n / 2;            // ... of which belong to the current layer
+    static constexpr int US = 4 * LC + 2;       // stored pivot row: [cg][l], rhs, pad
+    static constexpr int ublk = N * US;
+    static constexpr unsigned slotmask = (KS * 8 >= 32) ? 0xffffffffu : ((1u << (KS * 8)) - 1u);
+    __host__ __device__ static size_t slot_doubles(int L) { return (size_t)L * (rec + frec + ublk); }
+    // ---- shared memory (doubles) ----
+    static constexpr int cta = 4 * n + N * n + 2;   // cmu cwt csq cdinv, ylm, sum(w mu), sum(w)
     static constexpr int tasks = 32 / n;
     static constexpr int task = N + 4 * n * n + 4 * n;     // gl, K, L, G1, G2, vectors
     // work area shared by the phases: per-task areas (phase 1), 3 records (phase 2),
-    // 2 x (pivot rows + record) (phase 3)
+    // 2 x (pivot rows + flux record) (phase 3)
     static constexpr int cmax(int a, int b) { return a > b ? a : b; }
-    static constexpr int work = cmax(cmax(tasks * task, 3 * rec), 2 * (ublk + rec));
+    static constexpr int work = cmax(cmax(tasks * task, 3 * rec), 2 * (ublk + frec));
     __host__ __device__ static size_t warp_doubles(int L, int NT)
     {
-        // pivot-row double buffer, y0, taucpr/tauc/pk(+2 boundary temps), prologue
-        // work, level map, per-task areas; kept even for 16-byte alignment
-        size_t d = (size_t)4 * (N + 1) + N + work + 3 * (L + 1) + 2 + 3 * L + (NT + 1) / 2 + 2;
+        // y0, work area, taucpr/tauc, beam transmissions (2), pk(+2 boundary temps),
+        // prologue work values, level map; kept even for 16-byte alignment
+        size_t d = (size_t)N + work + 4 * (L + 1) + (L + 3) + 3 * L + (NT + 1) / 2 + 2;
         return (d + 1) & ~(size_t)1;
     }
 };
@@ -94,6 +111,15 @@ __device__ __forceinline__ double fast_rcp(double x)
     return y;
 }
 
+// sum over the n lanes of a layer group
+template <int n>
+__device__ __forceinline__ double group_sum(double v)
+{
+#pragma unroll
+    for (int o = n / 2; o > 0; o >>= 1) v += __shfl_xor_sync(FULLMASK, v, o, n);
+    return v;
+}
+
 // ---------------------------------------------------------------------------
 // phase 1: one layer per group of n lanes
 // ---------------------------------------------------------------------------
@@ -102,11 +128,12 @@ __device__ __forceinline__ int phase1_layers(
     const double *__restrict__ dtauc, const double *__restrict__ ssalb,
     const double *__restrict__ pmom, int ldp, int lc, bool active, int mazim,
     double fbeam, double umu0, bool plank, double delm0,
-    const double *cmu, const double *csq, const double *cdinv, const double *cylm,
+    const double *cmu, const double *cwt, const double *csq, const double *cdinv, const double *cylm,
     const double *y0, const double *taucpr, const double *pk,
     double *tsm /* per-task shared */, double *rec /* scratch record of this layer */,
-    int g /* lane in group */)
+    double *frec /* flux record of this layer */, int g /* lane in group */)
 {
+    using FL = FastLayout<n>;
     constexpr int N = 2 * n;
     double *sgl = tsm, *sK = sgl + N, *sL = sK + n * n, *sG1 = sL + n * n, *sG2 = sG1 + n * n,
            *sv = sG2 + n * n;   // sv: 4 vectors of n
@@ -204,7 +231,11 @@ __device__ __forceinline__ int phase1_layers(
 #pragma unroll
         for (int i = 0; i < n; i++) own2 = fma(a[i], a[i], own2);
         for (int sweep = 0; sweep < 40; sweep++) {
-            int did = 0;
+            // `big`: some pair of this sweep was still more than 1e-5 away from
+            // orthogonal.  The cyclic method converges quadratically, so a sweep
+            // without such a pair leaves residual cosines ~1e-10 and no checking
+            // sweep is needed.
+            int big = 0;
 #pragma unroll 1
             for (int r = 0; r < n - 1; r++) {     // not unrolled: keeps the code in the I-cache
                 int partner;
@@ -226,12 +257,13 @@ __device__ __forceinline__ int phase1_layers(
                 const double gam = g0 + g1;
                 const bool lo = g < partner;
                 const double alpha = lo ? own2 : oth2, beta = lo ? oth2 : own2;
+                const double gg = gam * gam, ab = alpha * beta;
                 // rotate unless the pair is orthogonal to 1e-12 (eigenvectors then carry
                 // errors ~1e-12, far below the 1e-5 target)
-                if (gam * gam > 1.0e-24 * (alpha * beta) && fabs(gam) > 1.0e-300) {
-                    did = 1;
+                if (gg > 1.0e-24 * ab && fabs(gam) > 1.0e-300) {
+                    if (gg > 1.0e-10 * ab) big = 1;
                     const double dl = 0.5 * (beta - alpha);
-                    const double h2 = fma(dl, dl, gam * gam);
+                    const double h2 = fma(dl, dl, gg);
                     const double hy = h2 * rsqrt(h2);
                     const double t = gam * fast_rcp(dl + (dl >= 0.0 ? hy : -hy));
                     const double cc = rsqrt(fma(t, t, 1.0));
@@ -241,7 +273,7 @@ __device__ __forceinline__ int phase1_layers(
                     for (int i = 0; i < n; i++) a[i] = fma(sn, pa[i], cc * a[i]);
                 }
             }
-            if (!__any_sync(FULLMASK, did)) break;
+            if (!__any_sync(FULLMASK, big)) break;
             // refresh the carried norms once per sweep (cheap, stops drift)
             own2 = 0.0;
 #pragma unroll
@@ -284,21 +316,34 @@ __device__ __forceinline__ int phase1_layers(
     // G+ - G- = D^-1 Q ; G+ + G- = -D^-1 P / k   (disort.f:3273-3301)
     const double rk = 1.0 / kk;
     double gs[n], gd[n];
+    // flux functionals of mode g (FLUXES, disort.f:1926-2006): quadrature sums of the
+    // eigenvector over the upward / downward hemispheres and over all directions
+    double fA = 0.0, fB = 0.0, fC = 0.0;
 #pragma unroll
     for (int i = 0; i < n; i++) {
         gd[i] = cdinv[i] * Q[i];
         gs[i] = -cdinv[i] * P[i] * rk;
         sG1[g * n + i] = gs[i];      // [mode j][direction i]
         sG2[g * n + i] = gd[i];
+        const double gpi = 0.5 * (gs[i] + gd[i]), gmi = 0.5 * (gs[i] - gd[i]);
+        const double wm = cwt[i] * cmu[i];
+        fA = fma(wm, gpi, fA);
+        fB = fma(wm, gmi, fB);
+        fC = fma(cwt[i], gs[i], fC);
+        if (active) {
+            rec[FL::off_gp + i * n + g] = gpi;
+            rec[FL::off_gm + i * n + g] = gmi;
+        }
     }
     if (active) {
-        rec[FastLayout<n>::off_kk + g] = kk;
-        rec[FastLayout<n>::off_ek + g] = ek;
-#pragma unroll
-        for (int i = 0; i < n; i++) {
-            rec[FastLayout<n>::off_gp + i * n + g] = 0.5 * (gs[i] + gd[i]);
-            rec[FastLayout<n>::off_gm + i * n + g] = 0.5 * (gs[i] - gd[i]);
-        }
+        rec[FL::off_kk + g] = kk;
+        rec[FL::off_ek + g] = ek;
+        // solution column n+g belongs to +k_g, column n-1-g to -k_g (disort.f:3264-3312)
+        frec[FL::f_cu + n + g] = fA;          frec[FL::f_cu + n - 1 - g] = -fB;
+        frec[FL::f_cu + N + n + g] = fB;      frec[FL::f_cu + N + n - 1 - g] = -fA;
+        frec[FL::f_cu + 2 * N + n + g] = fC;  frec[FL::f_cu + 2 * N + n - 1 - g] = -fC;
+        frec[FL::f_ek + g] = ek;
+        frec[FL::f_kk + g] = kk;
     }
 
     // ---- beam particular solution: spectral form of UPBEAM (disort.f:4130) ----
@@ -368,94 +413,157 @@ __device__ __forceinline__ int phase1_layers(
             if (i == g) q = cdinv[i] * z[i];
         }
     }
+    // quadrature sums of the particular solutions (same functionals as above)
+    {
+        const double wmg = cwt[g] * cmu[g];
+        const double Zu = group_sum<n>(wmg * zup);
+        const double Zd = group_sum<n>(wmg * zdn);
+        const double Za = group_sum<n>(cwt[g] * (zup + zdn));
+        const double Q1 = (plank && mazim == 0) ? group_sum<n>(wmg * q) : 0.0;
+        if (active && g == 0) {
+            const double W = cylm[-2], SW = cylm[-1];      // sum(w mu), sum(w): see the kernel
+            double *sc = frec + FL::f_sc;
+            sc[0] = Zu; sc[1] = Zd; sc[2] = Za;
+            sc[3] = fma(xr1, Q1, xr0 * W); sc[4] = fma(-xr1, Q1, xr0 * W); sc[5] = 2.0 * xr0 * SW;
+            sc[6] = xr0; sc[7] = xr1; sc[8] = 1.0 - ss; sc[9] = 1.0 - ss * f;
+        }
+    }
     if (active) {
-        rec[FastLayout<n>::off_zz + n + g] = zup;
-        rec[FastLayout<n>::off_zz + n - 1 - g] = zdn;
-        rec[FastLayout<n>::off_zp0 + n + g] = xr0 + xr1 * q;
-        rec[FastLayout<n>::off_zp0 + n - 1 - g] = xr0 - xr1 * q;
-        if (g == 0) { rec[FastLayout<n>::off_xr] = xr0; rec[FastLayout<n>::off_xr + 1] = xr1; }
+        rec[FL::off_zz + n + g] = zup;
+        rec[FL::off_zz + n - 1 - g] = zdn;
+        rec[FL::off_zp0 + n + g] = xr0 + xr1 * q;
+        rec[FL::off_zp0 + n - 1 - g] = xr0 - xr1 * q;
+        if (g == 0) { rec[FL::off_xr] = xr0; rec[FL::off_xr + 1] = xr1; }
     }
     __syncwarp();
     return (bad && active) ? SBD_BIN_EIG_FAIL : 0;
 }
 
-// row r of GC times the layer-bottom (bottom=true) or layer-top exponential
-// factors, from a layer record (disort.f:2846-2882)
+// ---------------------------------------------------------------------------
+// phase 2 helpers
+// ---------------------------------------------------------------------------
+// Entry (r, c) of the layer's eigenvector matrix GC times the exponential factors
+// of the layer bottom (bottom = true) or top (disort.f:2846-2882): column n+j
+// belongs to +k_j, column n-1-j to -k_j; rows r >= n are the upward directions.
 template <int n>
-__device__ __forceinline__ void gc_row_scaled(const double *rec, int r, bool bottom, double *out)
+__device__ __forceinline__ double gc_entry(const double *rec, int r, int c, bool bottom)
 {
-    const bool up = r >= n;
+    using FL = FastLayout<n>;
+    const bool up = r >= n, plus = c >= n;
     const int i = up ? r - n : n - 1 - r;
-    const double *gp = rec + FastLayout<n>::off_gp + i * n;
-    const double *gm = rec + FastLayout<n>::off_gm + i * n;
-    const double *ek = rec + FastLayout<n>::off_ek;
-#pragma unroll
-    for (int j = 0; j < n; j++) {
-        const double p = gp[j], m = gm[j], e = ek[j];
-        const double plus = up ? p : m;      // column n+j  (+k_j)
-        const double minus = up ? -m : -p;   // column n-1-j (-k_j)
-        out[n + j] = bottom ? plus * e : plus;
-        out[n - 1 - j] = bottom ? minus : minus * e;
-    }
+    const int j = plus ? c - n : n - 1 - c;
+    double v = rec[((up == plus) ? FL::off_gp : FL::off_gm) + i * n + j];
+    if (!plus) v = -v;
+    if (plus == bottom) v *= rec[FL::off_ek + j];
+    return v;
 }
 
-// One column of the sliding-window elimination (lane = matrix row, w[0] = current
-// column).  W2 = highest pair index still alive.  Returns 0 or SBD_BIN_SINGULAR.
-template <int N, int W2>
-__device__ __forceinline__ int elim_column(double (&w)[2 * N + 2], double2 *pb, unsigned &act,
-                                           int &mycol, int j, int lane)
+// One pivot step of the 2-D tiled elimination.  LJ = this column's index inside
+// the lane's column slice (static), cgj = column group that owns it.
+// Returns true when no usable pivot exists.
+template <int n, int LJ>
+__device__ __forceinline__ bool elim_step(double (&w)[FastLayout<n>::KS][FastLayout<n>::LC],
+                                          double (&rhs)[FastLayout<n>::KS], unsigned &act,
+                                          int (&mycol)[FastLayout<n>::KS], int j, int cgj, int rg, int cg)
 {
-    const bool cand = (act >> lane) & 1u;
-    const double av = cand ? fabs(w[0]) : -1.0;
-    // pivot: largest |a| by high word (any near-maximal pivot is as stable)
-    const int hi = cand ? __double2hiint(av) : -1;
-    const int mx = __reduce_max_sync(FULLMASK, hi);
-    const unsigned who = __ballot_sync(FULLMASK, hi == mx && cand);
-    if (mx <= 0 || who == 0) return SBD_BIN_SINGULAR;
-    const int pl = __ffs(who) - 1;
-    const bool ispiv = (lane == pl);
-    // the pivot row travels through shared memory (double-buffered by column
-    // parity): 16-byte stores by one lane, broadcast 16-byte loads
-    if (ispiv) {
+    constexpr int KS = FastLayout<n>::KS, LC = FastLayout<n>::LC;
+    const bool owner = cg == cgj;
+    // column-j entries of this row group's rows, from the group's owner lane
+    double colj[KS];
 #pragma unroll
-        for (int c2 = 0; c2 <= W2; c2++) pb[c2] = make_double2(w[2 * c2], w[2 * c2 + 1]);
-        mycol = j;      // this row now rests (entry i = column j+i)
-    }
-    __syncwarp();
-    if (cand && !ispiv) {
-        const double2 p0 = pb[0];
-        const double mlt = w[0] * fast_rcp(p0.x);
-        w[0] = fma(-mlt, p0.y, w[1]);
+    for (int k = 0; k < KS; k++) colj[k] = __shfl_sync(FULLMASK, w[k][LJ], (rg << 2) | cgj);
+    // pivot: largest |a| by high word (any near-maximal pivot is as stable); the two
+    // low bits carry the row slot so that the reduction returns it as well
+    int best = -1;
+    double bval = 1.0;
 #pragma unroll
-        for (int c2 = 1; c2 <= W2; c2++) {
-            const double2 p = pb[c2];
-            w[2 * c2 - 1] = fma(-mlt, p.x, w[2 * c2]);
-            w[2 * c2] = fma(-mlt, p.y, w[2 * c2 + 1]);
-        }
+    for (int k = 0; k < KS; k++) {
+        const bool a = owner && ((act >> (k * 8 + rg)) & 1u);
+        const int h = a ? ((__double2hiint(fabs(w[k][LJ])) & ~3) | (KS - 1 - k)) : -1;
+        if (h > best) { best = h; bval = w[k][LJ]; }
     }
-    act &= ~(1u << pl);
-    return 0;
+    const double rloc = fast_rcp(bval);          // speculative: off the critical path
+    const int mx = __reduce_max_sync(FULLMASK, best);
+    const unsigned who = __ballot_sync(FULLMASK, best == mx);
+    if ((mx >> 2) <= 0) return true;
+    const int pl = __ffs(who) - 1, kp = KS - 1 - (mx & 3), rgp = pl >> 2;
+    const double rp = __shfl_sync(FULLMASK, rloc, pl);
+    double m[KS];
+#pragma unroll
+    for (int k = 0; k < KS; k++) {
+        const bool a = ((act >> (k * 8 + rg)) & 1u) && !(rg == rgp && k == kp);
+        m[k] = a ? -colj[k] * rp : 0.0;
+    }
+    // this lane's column slice of the pivot row: one shuffle serves all 4 column groups
+    double p[LC - LJ], pr;
+    const int src = (rgp << 2) | cg;
+    if (KS == 1 || kp == 0) {
+#pragma unroll
+        for (int l = LJ; l < LC; l++) p[l - LJ] = __shfl_sync(FULLMASK, w[0][l], src);
+        pr = __shfl_sync(FULLMASK, rhs[0], src);
+    } else if (KS == 2 || kp == 1) {
+#pragma unroll
+        for (int l = LJ; l < LC; l++) p[l - LJ] = __shfl_sync(FULLMASK, w[KS > 1 ? 1 : 0][l], src);
+        pr = __shfl_sync(FULLMASK, rhs[KS > 1 ? 1 : 0], src);
+    } else {
+#pragma unroll
+        for (int l = LJ; l < LC; l++) p[l - LJ] = __shfl_sync(FULLMASK, w[KS > 2 ? 2 : 0][l], src);
+        pr = __shfl_sync(FULLMASK, rhs[KS > 2 ? 2 : 0], src);
+    }
+#pragma unroll
+    for (int k = 0; k < KS; k++) {
+#pragma unroll
+        for (int l = LJ; l < LC; l++) w[k][l] = fma(m[k], p[l - LJ], w[k][l]);
+        rhs[k] = fma(m[k], pr, rhs[k]);
+        if (rg == rgp && k == kp) mycol[k] = j;
+    }
+    act &= ~(1u << (kp * 8 + rgp));
+    return false;
 }
+
+template <int n, int LJ>
+struct ElimLayer {
+    // the N columns of one layer: LH slices x 4 column groups
+    __device__ static __forceinline__ bool run(double (&w)[FastLayout<n>::KS][FastLayout<n>::LC],
+                                               double (&rhs)[FastLayout<n>::KS], unsigned &act,
+                                               int (&mycol)[FastLayout<n>::KS], int rg, int cg)
+    {
+#pragma unroll 1
+        for (int cgj = 0; cgj < 4; cgj++)
+            if (elim_step<n, LJ>(w, rhs, act, mycol, 4 * LJ + cgj, cgj, rg, cg)) return true;
+        return ElimLayer<n, LJ + 1>::run(w, rhs, act, mycol, rg, cg);
+    }
+};
+template <int n>
+struct ElimLayer<n, n / 2> {
+    __device__ static __forceinline__ bool run(double (&)[FastLayout<n>::KS][FastLayout<n>::LC],
+                                               double (&)[FastLayout<n>::KS], unsigned &,
+                                               int (&)[FastLayout<n>::KS], int, int)
+    {
+        return false;
+    }
+};
 
 template <int n>
 __global__ void __launch_bounds__(128, 4)
 disort_fast_kernel(const LaunchArgs a)
 {
     using FL = FastLayout<n>;
-    constexpr int N = 2 * n, C = 2 * N + 1, R = n + N, TASKS = 32 / n;
+    constexpr int N = 2 * n, TASKS = 32 / n, KS = FL::KS, LC = FL::LC, LH = FL::LH, US = FL::US;
     const int L = a.d.nlyr;
     const int NT = a.d.ntau > 0 ? a.d.ntau : L + 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
     const int ldp = a.d.nmom + 1;
     extern __shared__ double smem_fast[];
-    double *cmu = smem_fast, *cwt = cmu + n, *csq = cwt + n, *cdinv = csq + n, *cylm = cdinv + n;
+    double *cmu = smem_fast, *cwt = cmu + n, *csq = cwt + n, *cdinv = csq + n;
+    double *cylm = cdinv + n + 2;       // cylm[-2] = sum(w mu), cylm[-1] = sum(w)
     double *wsm = smem_fast + FL::cta + (size_t)warp * FL::warp_doubles(L, NT);
-    // fixed-offset areas first (addresses are wsm + constant), run-time sized arrays last
-    double2 *prow2 = reinterpret_cast<double2 *>(wsm);          // 2 x (N+1) pairs, 16-byte aligned
-    double *y0 = wsm + 4 * (N + 1);
+    double *y0 = wsm;
     // 16-byte aligned work area: per-task areas in phase 1, cp.async staging afterwards
     double *tsm_base = y0 + N;
-    double *taucpr = tsm_base + FL::work, *tauc = taucpr + (L + 1), *pk = tauc + (L + 1);
+    double *taucpr = tsm_base + FL::work, *tauc = taucpr + (L + 1);
+    double *ebeam = tauc + (L + 1), *edir = ebeam + (L + 1);   // exp(-tau'/mu0), exp(-tau/mu0)
+    double *pk = edir + (L + 1);
     double *lw = pk + (L + 3);                                   // 3 x L prologue work values
     int *layru = (int *)(lw + 3 * L);
 
@@ -463,15 +571,23 @@ disort_fast_kernel(const LaunchArgs a)
         double mu = a.quad[i], wt = a.quad[n + i];
         cmu[i] = mu; cwt[i] = wt; csq[i] = sqrt(wt / mu); cdinv[i] = 1.0 / sqrt(wt * mu);
     }
+    if (threadIdx.x == 0) {
+        double W = 0.0, SW = 0.0;
+        for (int i = 0; i < n; i++) { W += a.quad[n + i] * a.quad[i]; SW += a.quad[n + i]; }
+        cylm[-2] = W; cylm[-1] = SW;
+    }
     for (int e = threadIdx.x; e < N * n; e += blockDim.x) cylm[e] = a.ylmc[e];
     __syncthreads();
+    const double Wq = cylm[-2], SWq = cylm[-1];
 
     const int slot = blockIdx.x * warps + warp;
     double *scr = a.scratch + (size_t)slot * a.slot_stride;
-    double *recs = scr;                        // [L][rec]
-    double *ublk = scr + (size_t)L * FL::rec;  // [L][N][urow]
+    double *recs = scr;                                   // [L][rec]
+    double *frecs = scr + (size_t)L * FL::rec;            // [L][frec]
+    double *ublk = frecs + (size_t)L * FL::frec;          // [L][N][US]
     const int g = lane % n, task = lane / n;
     double *tsm = tsm_base + (size_t)task * FL::task;
+    const int rg = lane >> 2, cg = lane & 3;              // 2-D tiling of phase 2
 
     for (;;) {
         int bin = 0;
@@ -542,6 +658,12 @@ disort_fast_kernel(const LaunchArgs a)
         monotone = __shfl_sync(FULLMASK, monotone, 0);
         const bool fastmap = (a.d.ntau == 0) && monotone;
         __syncwarp();
+        // beam transmission to every layer boundary: scaled depth (EXPBEA, disort.f:2592)
+        // and true depth (the direct flux that is reported, disort.f:1998)
+        for (int lev = lane; lev <= L; lev += 32) {
+            ebeam[lev] = fbeam > 0.0 ? exp(-taucpr[lev] / umu0) : 0.0;
+            edir[lev] = fbeam > 0.0 ? exp(-tauc[lev] / umu0) : 0.0;
+        }
         int badtau = 0;
         for (int lu = lane; lu < NT; lu += 32) {
             double ut = a.d.ntau > 0 ? a.utau[(size_t)src * NT + lu] : tauc[lu];
@@ -596,8 +718,8 @@ disort_fast_kernel(const LaunchArgs a)
                 const bool active = lc < ncut;
                 if (!active) lc = ncut - 1;
                 int st = phase1_layers<n>(dtauc, ssalb, pmom, ldp, lc, active, 0, fbeam, umu0, plank,
-                                          1.0, cmu, csq, cdinv, cylm, y0, taucpr, pk, tsm,
-                                          recs + (size_t)lc * FL::rec, g);
+                                          1.0, cmu, cwt, csq, cdinv, cylm, y0, taucpr, pk, tsm,
+                                          recs + (size_t)lc * FL::rec, frecs + (size_t)lc * FL::frec, g);
                 if (__any_sync(FULLMASK, st != 0)) { status = SBD_BIN_EIG_FAIL; break; }
             }
         }
@@ -605,26 +727,38 @@ disort_fast_kernel(const LaunchArgs a)
         __threadfence_block();
 
         // ===================== phase 2: downward elimination ================
-        // lane = matrix row.  Rows not yet used as pivots are "live".
-        double w[C + 1];            // +1: pad so that columns pair up for 16-byte moves
-        unsigned live = 0;          // rows currently holding an equation
+        // The window rows live in slots (rg, k), k < KS; slot s = k*8 + rg.  `act`
+        // (warp-uniform) marks the slots that hold an equation not yet used as a pivot.
         // Layer records are staged global -> shared with cp.async, three slots deep:
         // stage lc uses records lc and lc+1 while record lc+2 is in flight.
         double *rslot = tsm_base;   // phase-1 task areas are idle now
         if (!status) {
+            double w[KS][LC], rhs[KS];
+            int mycol[KS];
+            unsigned act = 0;
             warp_copy_async(rslot, recs, FL::rec, lane);
             if (ncut > 1) warp_copy_async(rslot + FL::rec, recs + FL::rec, FL::rec, lane);
             cp_async_commit();
             cp_async_wait_all();
             __syncwarp();
-            // top boundary rows on lanes 0..n-1 (disort.f:2887-2915, :3547-3550)
 #pragma unroll
-            for (int c = 0; c < C + 1; c++) w[c] = 0.0;
-            if (lane < n) {
-                gc_row_scaled<n>(rslot, lane, false, w);
-                w[2 * N] = bp.fisot + tplank - rslot[FL::off_zz + lane] - rslot[FL::off_zp0 + lane];
+            for (int k = 0; k < KS; k++) {
+                mycol[k] = -1;
+                rhs[k] = 0.0;
+#pragma unroll
+                for (int l = 0; l < LC; l++) w[k][l] = 0.0;
             }
-            live = (1u << n) - 1u;
+            // top boundary rows r = 0..n-1 in slots 0..n-1 (disort.f:2887-2915, :3547-3550)
+#pragma unroll
+            for (int k = 0; k < KS; k++) {
+                const int r = k * 8 + rg;
+                if (r < n) {
+#pragma unroll
+                    for (int l = 0; l < LH; l++) w[k][l] = gc_entry<n>(rslot, r, 4 * l + cg, false);
+                    rhs[k] = bp.fisot + tplank - rslot[FL::off_zz + r] - rslot[FL::off_zp0 + r];
+                }
+            }
+            act = (1u << n) - 1u;
             for (int lc = 0; lc < ncut; lc++) {
                 const bool last = (lc == ncut - 1);
                 if (lc + 2 < ncut) {
@@ -633,85 +767,87 @@ disort_fast_kernel(const LaunchArgs a)
                     cp_async_commit();
                 }
                 const double *rc = rslot + (lc % 3) * FL::rec;
+                const double *rn = rslot + ((lc + 1) % 3) * FL::rec;
                 const double tb = taucpr[lc + 1];
-                const double eb = (fbeam > 0.0) ? exp(-tb / umu0) : 0.0;
-                // free lanes take the new equations: N interface rows, or n bottom rows
-                const unsigned freem = ~live & ((R >= 32) ? 0xffffffffu : ((1u << R) - 1u));
-                const int rank = __popc(freem & ((1u << lane) - 1u));
+                const double eb = ebeam[lc + 1];
+                // free slots take the new equations: N interface rows, or n bottom rows
+                const unsigned freem = ~act & FL::slotmask;
                 const int nnew = last ? n : N;
-                const bool isnew = ((freem >> lane) & 1u) && rank < nnew;
-                if (isnew) {
-                    if (!last) {
-                        const double *rn = rslot + ((lc + 1) % 3) * FL::rec;
-                        const int r = rank;
-                        gc_row_scaled<n>(rc, r, true, w);
-                        double tmp[N];
-                        gc_row_scaled<n>(rn, r, false, tmp);
-#pragma unroll
-                        for (int j = 0; j < N; j++) w[N + j] = -tmp[j];
-                        w[2 * N] = (rn[FL::off_zz + r] - rc[FL::off_zz + r]) * eb +
-                                   rn[FL::off_zp0 + r] - rc[FL::off_zp0 + r] +
-                                   (rn[FL::off_xr + 1] - rc[FL::off_xr + 1]) * tb;
-                    } else {
-                        // bottom boundary, Lambertian m = 0 (disort.f:2919-2990, :3552-3578)
-                        const int r = n + rank;
-                        const double xr1 = rc[FL::off_xr + 1];
-                        gc_row_scaled<n>(rc, r, true, w);
-                        double rhs = -rc[FL::off_zz + r] * eb - rc[FL::off_zp0 + r] - xr1 * tb;
-                        if (!lyrcut) {
-                            double refl[N];
-#pragma unroll
-                            for (int j = 0; j < N; j++) refl[j] = 0.0;
-                            double rsum = 0.0;
+                unsigned newm = freem;
+                if (__popc(freem) > nnew) {          // keep the lowest nnew free slots
+                    newm = 0;
+                    unsigned f = freem;
+                    for (int i = 0; i < nnew; i++) { const unsigned b = f & (0u - f); newm |= b; f ^= b; }
+                }
+                double rsum = 0.0;
+                if (last && !lyrcut) {
+                    const double xr1 = rc[FL::off_xr + 1];
 #pragma unroll 1
-                            for (int k = 0; k < n; k++) {
-                                double tmp[N];
-                                gc_row_scaled<n>(rc, n - 1 - k, true, tmp);
-                                const double wm = cwt[k] * cmu[k];
+                    for (int k = 0; k < n; k++)
+                        rsum = fma(cwt[k] * cmu[k], rc[FL::off_zz + n - 1 - k] * eb +
+                                                        rc[FL::off_zp0 + n - 1 - k] + xr1 * tb, rsum);
+                }
 #pragma unroll
-                                for (int j = 0; j < N; j++) refl[j] = fma(wm, tmp[j], refl[j]);
-                                rsum = fma(wm, rc[FL::off_zz + n - 1 - k] * eb + rc[FL::off_zp0 + n - 1 - k] + xr1 * tb, rsum);
+                for (int k = 0; k < KS; k++) {
+                    const int s = k * 8 + rg;
+                    if ((newm >> s) & 1u) {
+                        const int rank = __popc(freem & ((1u << s) - 1u));
+                        if (!last) {
+                            const int r = rank;
+#pragma unroll
+                            for (int l = 0; l < LH; l++) {
+                                w[k][l] = gc_entry<n>(rc, r, 4 * l + cg, true);
+                                w[k][LH + l] = -gc_entry<n>(rn, r, 4 * l + cg, false);
                             }
+                            rhs[k] = (rn[FL::off_zz + r] - rc[FL::off_zz + r]) * eb +
+                                     rn[FL::off_zp0 + r] - rc[FL::off_zp0 + r] +
+                                     (rn[FL::off_xr + 1] - rc[FL::off_xr + 1]) * tb;
+                        } else {
+                            // bottom boundary, Lambertian m = 0 (disort.f:2919-2990, :3552-3578)
+                            const int r = n + rank;
+                            const double xr1 = rc[FL::off_xr + 1];
+                            double v = -rc[FL::off_zz + r] * eb - rc[FL::off_zp0 + r] - xr1 * tb;
 #pragma unroll
-                            for (int j = 0; j < N; j++) w[j] = fma(-2.0 * albedo, refl[j], w[j]);
-                            rhs += 2.0 * albedo * rsum + albedo * umu0 * fbeam / kPiRef * eb +
-                                   (1.0 - albedo) * bplank;
+                            for (int l = 0; l < LH; l++) {
+                                const int c = 4 * l + cg;
+                                double e = gc_entry<n>(rc, r, c, true);
+                                if (!lyrcut) {
+                                    double refl = 0.0;
+#pragma unroll 1
+                                    for (int kk = 0; kk < n; kk++)
+                                        refl = fma(cwt[kk] * cmu[kk], gc_entry<n>(rc, n - 1 - kk, c, true), refl);
+                                    e = fma(-2.0 * albedo, refl, e);
+                                }
+                                w[k][l] = e;
+                                w[k][LH + l] = 0.0;
+                            }
+                            if (!lyrcut)
+                                v += 2.0 * albedo * rsum + albedo * umu0 * fbeam / kPiRef * eb +
+                                     (1.0 - albedo) * bplank;
+                            rhs[k] = v;
                         }
-#pragma unroll
-                        for (int j = 0; j < N; j++) w[N + j] = 0.0;
-                        w[2 * N] = rhs;
                     }
                 }
-                unsigned act = live | __ballot_sync(FULLMASK, isnew);
+                act |= newm;
                 // eliminate the N columns of layer lc
-                // The window slides: after each column every live row drops its
-                // leading entry, so the current column is always w[0] and ONE copy
-                // of the loop body serves all N columns (I-cache friendly).
-                int mycol = -1;     // which pivot column this lane's row became
-                // the live width shrinks by one per column: the second half of the columns
-                // only touches 3N/4 + 1 pairs
-#pragma unroll 1
-                for (int j = 0; j < N / 2 && !status; j++)
-                    status = elim_column<N, N>(w, prow2 + (j & 1) * (N + 1), act, mycol, j, lane);
-#pragma unroll 1
-                for (int j = N / 2; j < N && !status; j++)
-                    status = elim_column<N, N - N / 4>(w, prow2 + (j & 1) * (N + 1), act, mycol, j, lane);
-                if (status) break;
-                // pivot rows -> scratch, packed: row j holds columns j..2N at entries
-                // 0..2N-j of a slice of even length starting at uoff(j)
-                if (mycol >= 0) {
-                    double2 *u2 = reinterpret_cast<double2 *>(ublk + (size_t)lc * FL::ublk + FL::uoff(mycol));
-                    const int len2 = FL::ulen(mycol) / 2;
+                if (ElimLayer<n, 0>::run(w, rhs, act, mycol, rg, cg)) { status = SBD_BIN_SINGULAR; break; }
+                // pivot rows -> scratch: row j as [cg][l] slices, then the right-hand side
+                double *ul = ublk + (size_t)lc * FL::ublk;
 #pragma unroll
-                    for (int c2 = 0; c2 <= N; c2++)
-                        if (c2 < len2) u2[c2] = make_double2(w[2 * c2], w[2 * c2 + 1]);
-                }
-                live = act;      // the n rows that were never pivots carry over:
-                                 // their next-layer coefficients already sit in w[0..N-1]
-                if (!last && ((live >> lane) & 1u)) {
-                    w[2 * N] = w[N];
+                for (int k = 0; k < KS; k++) {
+                    if (mycol[k] >= 0) {
+                        double *dst = ul + mycol[k] * US + cg * LC;
 #pragma unroll
-                    for (int j = N; j < 2 * N; j++) w[j] = 0.0;
+                        for (int l2 = 0; l2 < LC / 2; l2++)
+                            reinterpret_cast<double2 *>(dst)[l2] = make_double2(w[k][2 * l2], w[k][2 * l2 + 1]);
+                        if (cg == 0) ul[mycol[k] * US + 4 * LC] = rhs[k];
+                        mycol[k] = -1;
+                    } else if (!last) {
+                        // a row that was never a pivot carries over: its next-layer
+                        // coefficients move to the front of the slice
+#pragma unroll
+                        for (int l = 0; l < LH; l++) { w[k][l] = w[k][LH + l]; w[k][LH + l] = 0.0; }
+                    }
                 }
                 cp_async_wait_all();       // record lc+2 has landed
                 __syncwarp();
@@ -727,13 +863,13 @@ disort_fast_kernel(const LaunchArgs a)
 #pragma unroll
             for (int j = 0; j < N; j++) xs[j] = 0.0;
             int lu_next = NT - 1;  // levels are visited bottom-up when the map is monotone
-            // pivot rows + record of layer lc-1 stream into the other half of a double
-            // buffer (cp.async) while layer lc is being solved
-            constexpr int kSlot = FL::ublk + FL::rec;
+            // pivot rows + flux record of layer lc-1 stream into the other half of a
+            // double buffer (cp.async) while layer lc is being solved
+            constexpr int kSlot = FL::ublk + FL::frec;
             auto fetch_layer = [&](int lyr, int buf) {
                 double *dstp = tsm_base + buf * kSlot;
                 warp_copy_async(dstp, ublk + (size_t)lyr * FL::ublk, FL::ublk, lane);
-                warp_copy_async(dstp + FL::ublk, recs + (size_t)lyr * FL::rec, FL::rec, lane);
+                warp_copy_async(dstp + FL::ublk, frecs + (size_t)lyr * FL::frec, FL::frec, lane);
                 cp_async_commit();
             };
             fetch_layer(ncut - 1, 0);
@@ -743,19 +879,20 @@ disort_fast_kernel(const LaunchArgs a)
                 else cp_async_wait_all();
                 __syncwarp();
                 const double *ubuf = tsm_base + buf * kSlot;
-                const double *rc = ubuf + FL::ublk;
+                const double *fr = ubuf + FL::ublk;
                 double acc = 0.0, diag = 1.0;
                 double ur[N];      // row `lane` of the upper triangle
 #pragma unroll
                 for (int j = 0; j < N; j++) ur[j] = 0.0;
                 if (lane < N) {
-                    // stored row `lane`: entry i is column lane+i (see phase 2)
-                    const double *u = ubuf + FL::uoff(lane) - lane;
-                    acc = u[2 * N];
+                    // stored row `lane`: window column c sits at (c & 3) * LC + (c >> 2)
+                    const double *u = ubuf + lane * US;
+                    acc = u[4 * LC];
 #pragma unroll
-                    for (int j = 0; j < N; j++) acc = fma(-u[N + j], xs[j], acc);
+                    for (int j = 0; j < N; j++)
+                        acc = fma(-u[((N + j) & 3) * LC + ((N + j) >> 2)], xs[j], acc);
 #pragma unroll
-                    for (int c = 0; c < N; c++) if (c >= lane) ur[c] = u[c];
+                    for (int c = 0; c < N; c++) if (c >= lane) ur[c] = u[(c & 3) * LC + (c >> 2)];
                 }
 #pragma unroll
                 for (int j = 0; j < N; j++) if (j == lane) diag = ur[j];
@@ -772,76 +909,86 @@ disort_fast_kernel(const LaunchArgs a)
                 for (int lu = fastmap ? lu_next : NT - 1; lu >= 0; lu--) {
                     if (layru[lu] != lc + 1) { if (fastmap) break; else continue; }
                     if (fastmap) lu_next = lu - 1;
-                    double ut = a.d.ntau > 0 ? a.utau[(size_t)src * NT + lu] : tauc[lu];
-                    if (a.d.ntau > 0 && fabs(ut - tauc[L]) <= 1.e-4) ut = tauc[L];
-                    double ss = ssalb[lc]; if (ss == 1.0) ss = 1.0 - kDither;
-                    const double f = pmom[(size_t)lc * ldp + N];
-                    const double utp = taucpr[lc] + (1. - ss * f) * (ut - tauc[lc]);
-                    const double xr0 = rc[FL::off_xr], xr1 = rc[FL::off_xr + 1];
-                    double fact = 0.0, dirint = 0.0, fldir = 0.0, rfldir = 0.0;
-                    if (fbeam > 0.0) {
-                        fact = exp(-utp / umu0);
-                        dirint = fbeam * fact;
-                        fldir = umu0 * (fbeam * fact);
-                        rfldir = umu0 * fbeam * exp(-ut / umu0);
+                    const bool atbot = (a.d.ntau == 0 && lu == lc + 1);
+                    const bool attop = (a.d.ntau == 0 && lu == lc);
+                    const double *sc = fr + FL::f_sc;
+                    double ut, utp, fact, edr;
+                    if (atbot || attop) {
+                        ut = tauc[lu]; utp = taucpr[lu]; fact = ebeam[lu]; edr = edir[lu];
+                    } else {
+                        ut = a.d.ntau > 0 ? a.utau[(size_t)src * NT + lu] : tauc[lu];
+                        if (a.d.ntau > 0 && fabs(ut - tauc[L]) <= 1.e-4) ut = tauc[L];
+                        utp = taucpr[lc] + sc[9] * (ut - tauc[lc]);
+                        fact = fbeam > 0.0 ? exp(-utp / umu0) : 0.0;
+                        edr = fbeam > 0.0 ? exp(-ut / umu0) : 0.0;
                     }
-                    // lanes 0..n-1: upward direction i, lanes n..N-1: downward direction i
-                    double uval = 0.0, wgt = 0.0, wm = 0.0;
-                    if (lane < N) {
-                        const bool up = lane < n;
-                        const int i = up ? lane : lane - n;
-                        const double *gp = rc + FL::off_gp + i * n, *gm = rc + FL::off_gm + i * n;
-                        const bool atbot = (a.d.ntau == 0 && lu == lc + 1);
-                        const bool attop = (a.d.ntau == 0 && lu == lc);
-                        // a_j = x+_j exp(-k_j (t - t_top)), b_j = x-_j exp(-k_j (t_bot - t)); at a
-                        // layer boundary the factors are 1 and the stored exp(-k dtau')
-                        double s0 = 0.0, s1 = 0.0;
-                        if (atbot || attop) {
+                    // S_t = sum_j cu[t][j] x_j f_j, t = up, down, mean; f_j = attenuation of
+                    // mode j between its reference boundary and the level
+                    double dot = 0.0;
+                    if (atbot || attop) {
+                        // lanes 0..2 take one functional each; x is uniform
+                        double xe[N];
 #pragma unroll
-                            for (int j = 0; j < n; j++) {
-                                const double e = rc[FL::off_ek + j];
-                                const double pj = up ? gp[j] : gm[j], mj = up ? gm[j] : gp[j];
-                                s0 = fma(pj, xs[n + j] * (atbot ? e : 1.0), s0);
-                                s1 = fma(mj, xs[n - 1 - j] * (atbot ? 1.0 : e), s1);
-                            }
-                        } else {     // level inside a layer (USRTAU): rolled loop, x from local memory
-                            const double d1 = utp - taucpr[lc], d2 = taucpr[lc + 1] - utp;
-                            double xl[N];
-#pragma unroll
-                            for (int j = 0; j < N; j++) xl[j] = xs[j];
-#pragma unroll 1
-                            for (int j = 0; j < n; j++) {
-                                const double k = rc[FL::off_kk + j];
-                                const double pj = up ? gp[j] : gm[j], mj = up ? gm[j] : gp[j];
-                                s0 = fma(pj, xl[n + j] * exp(-k * d1), s0);
-                                s1 = fma(mj, xl[n - 1 - j] * exp(-k * d2), s1);
-                            }
+                        for (int j = 0; j < n; j++) {
+                            const double e = fr[FL::f_ek + j];
+                            xe[n + j] = atbot ? xs[n + j] * e : xs[n + j];
+                            xe[n - 1 - j] = atbot ? xs[n - 1 - j] : xs[n - 1 - j] * e;
                         }
-                        const double s = s0 - s1;
-                        const int r = up ? n + i : n - 1 - i;
-                        uval = s + rc[FL::off_zz + r] * fact + rc[FL::off_zp0 + r] + xr1 * utp;
-                        wgt = cwt[i]; wm = cwt[i] * cmu[i];
-                    }
-                    double fu = (lane < n) ? wm * uval : 0.0;
-                    double fd = (lane >= n && lane < N) ? wm * uval : 0.0;
-                    double av = wgt * uval;
+                        if (lane < 3) {
+                            const double2 *cu2 = reinterpret_cast<const double2 *>(fr + FL::f_cu + lane * N);
+                            double d0 = 0.0, d1 = 0.0;
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        fu += __shfl_xor_sync(FULLMASK, fu, o);
-                        fd += __shfl_xor_sync(FULLMASK, fd, o);
-                        av += __shfl_xor_sync(FULLMASK, av, o);
+                            for (int j2 = 0; j2 < n; j2++) {
+                                const double2 c = cu2[j2];
+                                d0 = fma(c.x, xe[2 * j2], d0);
+                                d1 = fma(c.y, xe[2 * j2 + 1], d1);
+                            }
+                            dot = d0 + d1;
+                        }
+                    } else {     // level inside a layer (USRTAU): one mode per lane
+                        double xl[N];
+#pragma unroll
+                        for (int j = 0; j < N; j++) xl[j] = xs[j];
+                        double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+                        if (lane < N) {
+                            const bool plusm = lane >= n;
+                            const int jm = plusm ? lane - n : n - 1 - lane;
+                            const double k = fr[FL::f_kk + jm];
+                            const double d = plusm ? utp - taucpr[lc] : taucpr[lc + 1] - utp;
+                            const double xf = xl[lane] * exp(-k * d);
+                            t0 = fr[FL::f_cu + lane] * xf;
+                            t1 = fr[FL::f_cu + N + lane] * xf;
+                            t2 = fr[FL::f_cu + 2 * N + lane] * xf;
+                        }
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) {
+                            t0 += __shfl_xor_sync(FULLMASK, t0, o);
+                            t1 += __shfl_xor_sync(FULLMASK, t1, o);
+                            t2 += __shfl_xor_sync(FULLMASK, t2, o);
+                        }
+                        dot = lane == 0 ? t0 : (lane == 1 ? t1 : t2);
                     }
+                    // particular solutions: beam, thermal constant and slope
+                    if (lane < 3) {
+                        const double wsum = lane < 2 ? Wq : 2.0 * SWq;
+                        dot += sc[lane] * fact + sc[3 + lane] + sc[7] * utp * wsum;
+                    }
+                    const double sdn = __shfl_sync(FULLMASK, dot, 1);
+                    const double sav = __shfl_sync(FULLMASK, dot, 2);
                     if (lane == 0) {
                         const double pi = kPiRef;
-                        const double flup = 2. * pi * fu, fldn = 2. * pi * fd;
+                        const double dirint = fbeam * fact;
+                        const double fldir = umu0 * (fbeam * fact);
+                        const double rfldir = umu0 * fbeam * edr;
+                        const double flup = 2. * pi * dot, fldn = 2. * pi * sdn;
                         const double fdntot = fldn + fldir;
-                        const double uavg = (2. * pi * av + dirint) / (4. * pi);
-                        const double plsorc = xr0 + xr1 * utp;
+                        const double uavg = (2. * pi * sav + dirint) / (4. * pi);
+                        const double plsorc = sc[6] + sc[7] * utp;
                         if (o_rfldir) o_rfldir[lu] = rfldir;
                         if (o_rfldn) o_rfldn[lu] = fdntot - rfldir;
                         if (o_flup) o_flup[lu] = flup;
                         if (o_uavg) o_uavg[lu] = uavg;
-                        if (o_dfdt) o_dfdt[lu] = (1. - ss) * 4. * pi * (uavg - plsorc);
+                        if (o_dfdt) o_dfdt[lu] = sc[8] * 4. * pi * (uavg - plsorc);
                     }
                 }
                 __syncwarp();     // everyone is done with this half of the double buffer
