@@ -67,10 +67,10 @@ struct FastLayout {
     static constexpr int cta = 4 * n + N * n + 2;   // cmu cwt csq cdinv, ylm, sum(w mu), sum(w)
     static constexpr int tasks = 32 / n;
     static constexpr int task = N + 4 * n * n + 4 * n;     // gl, K, L, G1, G2, vectors
-    // work area shared by the phases: per-task areas (phase 1), 3 records (phase 2),
+    // work area shared by the phases: per-task areas (phase 1), 3 records + assembled rows (phase 2),
     // 2 x (pivot rows + flux record) (phase 3)
     static constexpr int cmax(int a, int b) { return a > b ? a : b; }
-    static constexpr int work = cmax(cmax(tasks * task, 3 * rec), 2 * (ublk + frec));
+    static constexpr int work = cmax(cmax(tasks * task, 3 * rec + ublk), 2 * (ublk + frec));
     __host__ __device__ static size_t warp_doubles(int L, int NT)
     {
         // y0, work area, taucpr/tauc, beam transmissions (2), pk(+2 boundary temps),
@@ -442,26 +442,59 @@ __device__ __forceinline__ int phase1_layers(
 // ---------------------------------------------------------------------------
 // phase 2 helpers
 // ---------------------------------------------------------------------------
-// Entry (r, c) of the layer's eigenvector matrix GC times the exponential factors
-// of the layer bottom (bottom = true) or top (disort.f:2846-2882): column n+j
-// belongs to +k_j, column n-1-j to -k_j; rows r >= n are the upward directions.
+// Rows of the boundary system are assembled by the whole warp into a staging
+// area in shared memory, one window column per lane (2N divides 32), in the
+// layout the pivot rows are stored in: row r at r*US, window column c at
+// (c & 3) * LC + (c >> 2), right-hand side at 4*LC.
+//
+// Entry (r, c) of a layer's eigenvector matrix GC times the exponential factors
+// of the layer bottom or top (disort.f:2846-2882): column n+j belongs to +k_j,
+// column n-1-j to -k_j; rows r >= n are the upward directions.  recA/bottomA
+// describe the block of the current layer (columns < N), recB (top of the next
+// layer, negated; may be null) the block of columns >= N.
+// refl != 0: bottom boundary rows r0.. with the Lambertian reflection of the
+// downward directions folded in (disort.f:2919-2990).
 template <int n>
-__device__ __forceinline__ double gc_entry(const double *rec, int r, int c, bool bottom)
+__device__ __forceinline__ void stage_rows(double *stg, const double *recA, bool bottomA,
+                                           const double *recB, int r0, int nrows, double refl,
+                                           const double *cwt, const double *cmu, int lane)
 {
     using FL = FastLayout<n>;
-    const bool up = r >= n, plus = c >= n;
-    const int i = up ? r - n : n - 1 - r;
-    const int j = plus ? c - n : n - 1 - c;
-    double v = rec[((up == plus) ? FL::off_gp : FL::off_gm) + i * n + j];
-    if (!plus) v = -v;
-    if (plus == bottom) v *= rec[FL::off_ek + j];
-    return v;
+    constexpr int N = 2 * n, LC = FL::LC, US = FL::US;
+    const int c = lane % (2 * N);
+    const bool isB = c >= N;
+    const int cc = isB ? c - N : c;
+    const bool plus = cc >= n;
+    const int j = plus ? cc - n : n - 1 - cc;
+    const double *rec = (isB && recB) ? recB : recA;
+    const bool bottom = isB ? false : bottomA;
+    double fac = (plus == bottom) ? rec[FL::off_ek + j] : 1.0;
+    if (!plus) fac = -fac;
+    if (isB) fac = recB ? -fac : 0.0;
+    // reflected part: sum over the downward directions (rows n-1-k, i = k) of this column
+    double rsum = 0.0;
+    if (refl != 0.0) {
+        const double *gdn = rec + (plus ? FL::off_gm : FL::off_gp) + j;
+#pragma unroll 1
+        for (int k = 0; k < n; k++) rsum = fma(cwt[k] * cmu[k], gdn[k * n], rsum);
+    }
+    const int pos = (c & 3) * LC + (c >> 2);
+    const int rstep = 32 / (2 * N);
+#pragma unroll 1
+    for (int rr = lane / (2 * N); rr < nrows; rr += rstep) {
+        const int r = r0 + rr;
+        const bool up = r >= n;
+        const int i = up ? r - n : n - 1 - r;
+        double v = rec[((up == plus) ? FL::off_gp : FL::off_gm) + i * n + j];
+        if (refl != 0.0) v = fma(-refl, rsum, v);
+        stg[rr * US + pos] = v * fac;
+    }
 }
 
-// One pivot step of the 2-D tiled elimination.  LJ = this column's index inside
-// the lane's column slice (static), cgj = column group that owns it.
-// Returns true when no usable pivot exists.
-template <int n, int LJ>
+// One pivot step of the 2-D tiled elimination on the leading column of the
+// lanes' column slices; cgj = column group that owns it.  Returns true when no
+// usable pivot exists.
+template <int n>
 __device__ __forceinline__ bool elim_step(double (&w)[FastLayout<n>::KS][FastLayout<n>::LC],
                                           double (&rhs)[FastLayout<n>::KS], unsigned &act,
                                           int (&mycol)[FastLayout<n>::KS], int j, int cgj, int rg, int cg)
@@ -471,7 +504,7 @@ __device__ __forceinline__ bool elim_step(double (&w)[FastLayout<n>::KS][FastLay
     // column-j entries of this row group's rows, from the group's owner lane
     double colj[KS];
 #pragma unroll
-    for (int k = 0; k < KS; k++) colj[k] = __shfl_sync(FULLMASK, w[k][LJ], (rg << 2) | cgj);
+    for (int k = 0; k < KS; k++) colj[k] = __shfl_sync(FULLMASK, w[k][0], (rg << 2) | cgj);
     // pivot: largest |a| by high word (any near-maximal pivot is as stable); the two
     // low bits carry the row slot so that the reduction returns it as well
     int best = -1;
@@ -479,8 +512,8 @@ __device__ __forceinline__ bool elim_step(double (&w)[FastLayout<n>::KS][FastLay
 #pragma unroll
     for (int k = 0; k < KS; k++) {
         const bool a = owner && ((act >> (k * 8 + rg)) & 1u);
-        const int h = a ? ((__double2hiint(fabs(w[k][LJ])) & ~3) | (KS - 1 - k)) : -1;
-        if (h > best) { best = h; bval = w[k][LJ]; }
+        const int h = a ? ((__double2hiint(fabs(w[k][0])) & ~3) | (KS - 1 - k)) : -1;
+        if (h > best) { best = h; bval = w[k][0]; }
     }
     const double rloc = fast_rcp(bval);          // speculative: off the critical path
     const int mx = __reduce_max_sync(FULLMASK, best);
@@ -493,63 +526,50 @@ __device__ __forceinline__ bool elim_step(double (&w)[FastLayout<n>::KS][FastLay
     for (int k = 0; k < KS; k++) {
         const bool a = ((act >> (k * 8 + rg)) & 1u) && !(rg == rgp && k == kp);
         m[k] = a ? -colj[k] * rp : 0.0;
+        if (rg == rgp && k == kp) mycol[k] = j;
     }
     // this lane's column slice of the pivot row: one shuffle serves all 4 column groups
-    double p[LC - LJ], pr;
+    double p[LC], pr;
     const int src = (rgp << 2) | cg;
     if (KS == 1 || kp == 0) {
 #pragma unroll
-        for (int l = LJ; l < LC; l++) p[l - LJ] = __shfl_sync(FULLMASK, w[0][l], src);
+        for (int l = 0; l < LC; l++) p[l] = __shfl_sync(FULLMASK, w[0][l], src);
         pr = __shfl_sync(FULLMASK, rhs[0], src);
     } else if (KS == 2 || kp == 1) {
 #pragma unroll
-        for (int l = LJ; l < LC; l++) p[l - LJ] = __shfl_sync(FULLMASK, w[KS > 1 ? 1 : 0][l], src);
+        for (int l = 0; l < LC; l++) p[l] = __shfl_sync(FULLMASK, w[KS > 1 ? 1 : 0][l], src);
         pr = __shfl_sync(FULLMASK, rhs[KS > 1 ? 1 : 0], src);
     } else {
 #pragma unroll
-        for (int l = LJ; l < LC; l++) p[l - LJ] = __shfl_sync(FULLMASK, w[KS > 2 ? 2 : 0][l], src);
+        for (int l = 0; l < LC; l++) p[l] = __shfl_sync(FULLMASK, w[KS > 2 ? 2 : 0][l], src);
         pr = __shfl_sync(FULLMASK, rhs[KS > 2 ? 2 : 0], src);
     }
+    act &= ~(1u << (kp * 8 + rgp));
+    // update; after the last column group of a slice position the live rows drop
+    // their leading entry, so the current column is always entry 0 of the slice
+    const bool slide = cgj == 3;
 #pragma unroll
     for (int k = 0; k < KS; k++) {
-#pragma unroll
-        for (int l = LJ; l < LC; l++) w[k][l] = fma(m[k], p[l - LJ], w[k][l]);
+        const bool live = (act >> (k * 8 + rg)) & 1u;
         rhs[k] = fma(m[k], pr, rhs[k]);
-        if (rg == rgp && k == kp) mycol[k] = j;
+        if (slide && live) {
+#pragma unroll
+            for (int l = 0; l + 1 < LC; l++) w[k][l] = fma(m[k], p[l + 1], w[k][l + 1]);
+            w[k][LC - 1] = 0.0;
+        } else {
+#pragma unroll
+            for (int l = 0; l < LC; l++) w[k][l] = fma(m[k], p[l], w[k][l]);
+        }
     }
-    act &= ~(1u << (kp * 8 + rgp));
     return false;
 }
-
-template <int n, int LJ>
-struct ElimLayer {
-    // the N columns of one layer: LH slices x 4 column groups
-    __device__ static __forceinline__ bool run(double (&w)[FastLayout<n>::KS][FastLayout<n>::LC],
-                                               double (&rhs)[FastLayout<n>::KS], unsigned &act,
-                                               int (&mycol)[FastLayout<n>::KS], int rg, int cg)
-    {
-#pragma unroll 1
-        for (int cgj = 0; cgj < 4; cgj++)
-            if (elim_step<n, LJ>(w, rhs, act, mycol, 4 * LJ + cgj, cgj, rg, cg)) return true;
-        return ElimLayer<n, LJ + 1>::run(w, rhs, act, mycol, rg, cg);
-    }
-};
-template <int n>
-struct ElimLayer<n, n / 2> {
-    __device__ static __forceinline__ bool run(double (&)[FastLayout<n>::KS][FastLayout<n>::LC],
-                                               double (&)[FastLayout<n>::KS], unsigned &,
-                                               int (&)[FastLayout<n>::KS], int, int)
-    {
-        return false;
-    }
-};
 
 template <int n>
 __global__ void __launch_bounds__(128, 4)
 disort_fast_kernel(const LaunchArgs a)
 {
     using FL = FastLayout<n>;
-    constexpr int N = 2 * n, TASKS = 32 / n, KS = FL::KS, LC = FL::LC, LH = FL::LH, US = FL::US;
+    constexpr int N = 2 * n, TASKS = 32 / n, KS = FL::KS, LC = FL::LC, US = FL::US;
     const int L = a.d.nlyr;
     const int NT = a.d.ntau > 0 ? a.d.ntau : L + 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
@@ -732,33 +752,36 @@ disort_fast_kernel(const LaunchArgs a)
         // Layer records are staged global -> shared with cp.async, three slots deep:
         // stage lc uses records lc and lc+1 while record lc+2 is in flight.
         double *rslot = tsm_base;   // phase-1 task areas are idle now
+        double *stg = tsm_base + 3 * FL::rec;     // assembled rows of the current layer
         if (!status) {
             double w[KS][LC], rhs[KS];
             int mycol[KS];
-            unsigned act = 0;
             warp_copy_async(rslot, recs, FL::rec, lane);
             if (ncut > 1) warp_copy_async(rslot + FL::rec, recs + FL::rec, FL::rec, lane);
             cp_async_commit();
             cp_async_wait_all();
             __syncwarp();
-#pragma unroll
-            for (int k = 0; k < KS; k++) {
-                mycol[k] = -1;
-                rhs[k] = 0.0;
-#pragma unroll
-                for (int l = 0; l < LC; l++) w[k][l] = 0.0;
-            }
             // top boundary rows r = 0..n-1 in slots 0..n-1 (disort.f:2887-2915, :3547-3550)
+            stage_rows<n>(stg, rslot, false, nullptr, 0, n, 0.0, cwt, cmu, lane);
+            if (lane < n)
+                stg[lane * US + 4 * LC] = bp.fisot + tplank - rslot[FL::off_zz + lane] - rslot[FL::off_zp0 + lane];
+            __syncwarp();
 #pragma unroll
             for (int k = 0; k < KS; k++) {
                 const int r = k * 8 + rg;
+                mycol[k] = -1;
                 if (r < n) {
 #pragma unroll
-                    for (int l = 0; l < LH; l++) w[k][l] = gc_entry<n>(rslot, r, 4 * l + cg, false);
-                    rhs[k] = bp.fisot + tplank - rslot[FL::off_zz + r] - rslot[FL::off_zp0 + r];
+                    for (int l = 0; l < LC; l++) w[k][l] = stg[r * US + cg * LC + l];
+                    rhs[k] = stg[r * US + 4 * LC];
+                } else {
+                    rhs[k] = 0.0;
+#pragma unroll
+                    for (int l = 0; l < LC; l++) w[k][l] = 0.0;
                 }
             }
-            act = (1u << n) - 1u;
+            unsigned act = (1u << n) - 1u;
+            __syncwarp();
             for (int lc = 0; lc < ncut; lc++) {
                 const bool last = (lc == ncut - 1);
                 if (lc + 2 < ncut) {
@@ -779,59 +802,54 @@ disort_fast_kernel(const LaunchArgs a)
                     unsigned f = freem;
                     for (int i = 0; i < nnew; i++) { const unsigned b = f & (0u - f); newm |= b; f ^= b; }
                 }
-                double rsum = 0.0;
-                if (last && !lyrcut) {
-                    const double xr1 = rc[FL::off_xr + 1];
+                if (!last) {
+                    // interface lc | lc+1: u_lc(bottom) = u_lc+1(top)  (disort.f:2846-2882, :3585-3593)
+                    stage_rows<n>(stg, rc, true, rn, 0, N, 0.0, cwt, cmu, lane);
+                    if (lane < N)
+                        stg[lane * US + 4 * LC] = (rn[FL::off_zz + lane] - rc[FL::off_zz + lane]) * eb +
+                                                  rn[FL::off_zp0 + lane] - rc[FL::off_zp0 + lane] +
+                                                  (rn[FL::off_xr + 1] - rc[FL::off_xr + 1]) * tb;
+                } else {
+                    // bottom boundary, Lambertian m = 0 (disort.f:2919-2990, :3552-3578)
+                    stage_rows<n>(stg, rc, true, nullptr, n, n, lyrcut ? 0.0 : 2.0 * albedo, cwt, cmu, lane);
+                    if (lane < n) {
+                        const int r = n + lane;
+                        const double xr1 = rc[FL::off_xr + 1];
+                        double v = -rc[FL::off_zz + r] * eb - rc[FL::off_zp0 + r] - xr1 * tb;
+                        if (!lyrcut) {
+                            double rsum = 0.0;
 #pragma unroll 1
-                    for (int k = 0; k < n; k++)
-                        rsum = fma(cwt[k] * cmu[k], rc[FL::off_zz + n - 1 - k] * eb +
-                                                        rc[FL::off_zp0 + n - 1 - k] + xr1 * tb, rsum);
+                            for (int k = 0; k < n; k++)
+                                rsum = fma(cwt[k] * cmu[k], rc[FL::off_zz + n - 1 - k] * eb +
+                                                                rc[FL::off_zp0 + n - 1 - k] + xr1 * tb, rsum);
+                            v += 2.0 * albedo * rsum + albedo * umu0 * fbeam / kPiRef * eb +
+                                 (1.0 - albedo) * bplank;
+                        }
+                        stg[lane * US + 4 * LC] = v;
+                    }
                 }
+                __syncwarp();
 #pragma unroll
                 for (int k = 0; k < KS; k++) {
                     const int s = k * 8 + rg;
                     if ((newm >> s) & 1u) {
-                        const int rank = __popc(freem & ((1u << s) - 1u));
-                        if (!last) {
-                            const int r = rank;
+                        const double *row = stg + __popc(freem & ((1u << s) - 1u)) * US;
 #pragma unroll
-                            for (int l = 0; l < LH; l++) {
-                                w[k][l] = gc_entry<n>(rc, r, 4 * l + cg, true);
-                                w[k][LH + l] = -gc_entry<n>(rn, r, 4 * l + cg, false);
-                            }
-                            rhs[k] = (rn[FL::off_zz + r] - rc[FL::off_zz + r]) * eb +
-                                     rn[FL::off_zp0 + r] - rc[FL::off_zp0 + r] +
-                                     (rn[FL::off_xr + 1] - rc[FL::off_xr + 1]) * tb;
-                        } else {
-                            // bottom boundary, Lambertian m = 0 (disort.f:2919-2990, :3552-3578)
-                            const int r = n + rank;
-                            const double xr1 = rc[FL::off_xr + 1];
-                            double v = -rc[FL::off_zz + r] * eb - rc[FL::off_zp0 + r] - xr1 * tb;
-#pragma unroll
-                            for (int l = 0; l < LH; l++) {
-                                const int c = 4 * l + cg;
-                                double e = gc_entry<n>(rc, r, c, true);
-                                if (!lyrcut) {
-                                    double refl = 0.0;
-#pragma unroll 1
-                                    for (int kk = 0; kk < n; kk++)
-                                        refl = fma(cwt[kk] * cmu[kk], gc_entry<n>(rc, n - 1 - kk, c, true), refl);
-                                    e = fma(-2.0 * albedo, refl, e);
-                                }
-                                w[k][l] = e;
-                                w[k][LH + l] = 0.0;
-                            }
-                            if (!lyrcut)
-                                v += 2.0 * albedo * rsum + albedo * umu0 * fbeam / kPiRef * eb +
-                                     (1.0 - albedo) * bplank;
-                            rhs[k] = v;
+                        for (int l2 = 0; l2 < LC / 2; l2++) {
+                            const double2 v = reinterpret_cast<const double2 *>(row + cg * LC)[l2];
+                            w[k][2 * l2] = v.x; w[k][2 * l2 + 1] = v.y;
                         }
+                        rhs[k] = row[4 * LC];
                     }
                 }
                 act |= newm;
-                // eliminate the N columns of layer lc
-                if (ElimLayer<n, 0>::run(w, rhs, act, mycol, rg, cg)) { status = SBD_BIN_SINGULAR; break; }
-                // pivot rows -> scratch: row j as [cg][l] slices, then the right-hand side
+                // eliminate the N columns of layer lc: one loop body serves all of them
+                // (the slices slide, see elim_step)
+                bool sing = false;
+#pragma unroll 1
+                for (int j = 0; j < N && !sing; j++) sing = elim_step<n>(w, rhs, act, mycol, j, j & 3, rg, cg);
+                if (sing) { status = SBD_BIN_SINGULAR; break; }
+                // pivot rows -> scratch: row j as [cg][l - j/4] slices, then the right-hand side
                 double *ul = ublk + (size_t)lc * FL::ublk;
 #pragma unroll
                 for (int k = 0; k < KS; k++) {
@@ -842,11 +860,6 @@ disort_fast_kernel(const LaunchArgs a)
                             reinterpret_cast<double2 *>(dst)[l2] = make_double2(w[k][2 * l2], w[k][2 * l2 + 1]);
                         if (cg == 0) ul[mycol[k] * US + 4 * LC] = rhs[k];
                         mycol[k] = -1;
-                    } else if (!last) {
-                        // a row that was never a pivot carries over: its next-layer
-                        // coefficients move to the front of the slice
-#pragma unroll
-                        for (int l = 0; l < LH; l++) { w[k][l] = w[k][LH + l]; w[k][LH + l] = 0.0; }
                     }
                 }
                 cp_async_wait_all();       // record lc+2 has landed
@@ -885,9 +898,10 @@ disort_fast_kernel(const LaunchArgs a)
 #pragma unroll
                 for (int j = 0; j < N; j++) ur[j] = 0.0;
                 if (lane < N) {
-                    // stored row `lane`: window column c sits at (c & 3) * LC + (c >> 2)
-                    const double *u = ubuf + lane * US;
-                    acc = u[4 * LC];
+                    // stored row `lane`: window column c sits at (c & 3) * LC + (c >> 2) - lane / 4
+                    // (the slices had slid lane/4 times when the row became a pivot)
+                    const double *u = ubuf + lane * US - (lane >> 2);
+                    acc = ubuf[lane * US + 4 * LC];
 #pragma unroll
                     for (int j = 0; j < N; j++)
                         acc = fma(-u[((N + j) & 3) * LC + ((N + j) >> 2)], xs[j], acc);
