@@ -229,11 +229,12 @@ extern "C" int sbd_disort_batch_device(sbd_handle *h, const sbd_dims *dims, cons
     int warps, grid;
     size_t slot;
     if (fast) {
-        warps = 4;
+        warps = fast_warps();
         size_t smem = fast_smem_bytes(N, L, NT, warps);
+        while (smem > smem_limit && warps > 4) { warps /= 2; smem = fast_smem_bytes(N, L, NT, warps); }
         if (smem > smem_limit) return SBD_ERR_UNSUPPORTED;
         int cta_per_sm = (int)((smem_limit + 1024) / (smem + 1024));
-        if (cta_per_sm > 4) cta_per_sm = 4;
+        if (cta_per_sm > 16 / warps) cta_per_sm = 16 / warps;
         if (cta_per_sm < 1) cta_per_sm = 1;
         grid = h->sm_count * cta_per_sm;
         slot = fast_slot_doubles(N, L);

@@ -28,6 +28,7 @@
 // Layer records, flux records and pivot rows travel between the phases through
 // a per-warp scratch slot in global memory, staged with cp.async.
 #include <math.h>
+#include <stdlib.h>
 
 #include "sbd_internal.h"
 #include "sbd_planck.cuh"
@@ -564,8 +565,12 @@ __device__ __forceinline__ bool elim_step(double (&w)[FastLayout<n>::KS][FastLay
     return false;
 }
 
-template <int n>
-__global__ void __launch_bounds__(128, 4)
+// WARPS warps per CTA, 16 warps per SM.  SYNC: the warps of a CTA move through the
+// phases together (CTA barriers between them), so that at any time they execute the
+// same code and share its instruction-cache lines; a warp that found no bin left
+// keeps attending the barriers until every warp of the CTA is out of work.
+template <int n, int WARPS, bool SYNC>
+__global__ void __launch_bounds__(WARPS * 32, 16 / WARPS)
 disort_fast_kernel(const LaunchArgs a)
 {
     using FL = FastLayout<n>;
@@ -613,21 +618,23 @@ disort_fast_kernel(const LaunchArgs a)
         int bin = 0;
         if (lane == 0) bin = atomicAdd(a.work_counter, 1);
         bin = __shfl_sync(FULLMASK, bin, 0);
-        if (bin >= a.d.nbins) break;
-        const int src = a.binmap ? a.binmap[bin] : bin;     // input slot of this bin
+        const bool have = bin < a.d.nbins;
+        if (SYNC) { if (!__syncthreads_or(have)) break; }
+        else if (!have) break;
+        const int src = !have ? 0 : (a.binmap ? a.binmap[bin] : bin);     // input slot of this bin
         const sbd_bin bp = a.bins[src];
         const double *dtauc = a.dtauc + (size_t)src * L;
         const double *ssalb = a.ssalb + (size_t)src * L;
         const double *pmom = a.pmom + (size_t)src * L * ldp;
         const double fbeam = bp.fbeam, umu0 = bp.umu0, albedo = bp.albedo;
         const bool plank = bp.plank != 0;
-        double *o_rfldir = a.rfldir ? a.rfldir + (size_t)bin * NT : nullptr;
-        double *o_rfldn = a.rfldn ? a.rfldn + (size_t)bin * NT : nullptr;
-        double *o_flup = a.flup ? a.flup + (size_t)bin * NT : nullptr;
-        double *o_dfdt = a.dfdt ? a.dfdt + (size_t)bin * NT : nullptr;
-        double *o_uavg = a.uavg ? a.uavg + (size_t)bin * NT : nullptr;
+        double *o_rfldir = (a.rfldir && have) ? a.rfldir + (size_t)bin * NT : nullptr;
+        double *o_rfldn = (a.rfldn && have) ? a.rfldn + (size_t)bin * NT : nullptr;
+        double *o_flup = (a.flup && have) ? a.flup + (size_t)bin * NT : nullptr;
+        double *o_dfdt = (a.dfdt && have) ? a.dfdt + (size_t)bin * NT : nullptr;
+        double *o_uavg = (a.uavg && have) ? a.uavg + (size_t)bin * NT : nullptr;
 
-        int status = 0;
+        int status = have ? 0 : -1;
         {   // CHEKIN subset (disort.f:4920-5155)
             int badl = 0;
             for (int lc = lane; lc < L; lc += 32) {
@@ -745,6 +752,7 @@ disort_fast_kernel(const LaunchArgs a)
         }
         __syncwarp();
         __threadfence_block();
+        if (SYNC) __syncthreads();
 
         // ===================== phase 2: downward elimination ================
         // The window rows live in slots (rg, k), k < KS; slot s = k*8 + rg.  `act`
@@ -869,6 +877,7 @@ disort_fast_kernel(const LaunchArgs a)
         cp_async_wait_all();
         __syncwarp();
         __threadfence_block();
+        if (SYNC) __syncthreads();
 
         // ===================== phase 3: back substitution + fluxes ===========
         if (!status) {
@@ -1009,22 +1018,48 @@ disort_fast_kernel(const LaunchArgs a)
             }
         }
         cp_async_wait_all();
-        if (lane == 0) a.status[bin] = status;
+        if (lane == 0 && have) a.status[bin] = status;
         __syncwarp();
     }
 }
 
 // ---- host-side launch helpers ---------------------------------------------
+// CTA shape: 8 warps with phase barriers by default (measured best); SBD_FAST_WARPS = 4 | 8 | 16 and
+// SBD_FAST_SYNC = 0 | 1 override it (tuning knobs, not API).
+int fast_warps()
+{
+    const char *e = getenv("SBD_FAST_WARPS");
+    const int w = e ? atoi(e) : 8;
+    return (w == 4 || w == 8 || w == 16) ? w : 8;
+}
+static bool fast_sync(int warps)
+{
+    const char *e = getenv("SBD_FAST_SYNC");
+    return e ? atoi(e) != 0 : warps > 4;
+}
+
+template <int n, int WARPS, bool SYNC>
+static cudaError_t launch_fast_k(const LaunchArgs &a, int grid, size_t smem, cudaStream_t st)
+{
+    cudaError_t e = cudaFuncSetAttribute(disort_fast_kernel<n, WARPS, SYNC>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    disort_fast_kernel<n, WARPS, SYNC><<<grid, WARPS * 32, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
 template <int n>
 static cudaError_t launch_fast_t(const LaunchArgs &a, int warps, int grid, cudaStream_t st)
 {
     const int L = a.d.nlyr, NT = a.d.ntau > 0 ? a.d.ntau : L + 1;
     size_t smem = 8 * (FastLayout<n>::cta + (size_t)warps * FastLayout<n>::warp_doubles(L, NT));
-    cudaError_t e = cudaFuncSetAttribute(disort_fast_kernel<n>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    disort_fast_kernel<n><<<grid, warps * 32, smem, st>>>(a);
-    return cudaGetLastError();
+    const bool sync = fast_sync(warps);
+    switch (warps) {
+    case 4: return sync ? launch_fast_k<n, 4, true>(a, grid, smem, st) : launch_fast_k<n, 4, false>(a, grid, smem, st);
+    case 8: return launch_fast_k<n, 8, true>(a, grid, smem, st);
+    case 16: return launch_fast_k<n, 16, true>(a, grid, smem, st);
+    }
+    return cudaErrorInvalidValue;
 }
 
 bool fast_supported(int N) { return N == 4 || N == 8 || N == 16; }

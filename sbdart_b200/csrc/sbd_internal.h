@@ -66,6 +66,7 @@ cudaError_t launch_generic(const LaunchArgs &a, int warps, int grid,
 
 // register-resident kernel for NSTR in {4, 8, 16} (sbd_fast.cu)
 bool fast_supported(int N);
+int fast_warps();
 size_t fast_slot_doubles(int N, int L);
 size_t fast_smem_bytes(int N, int L, int NT, int warps);
 cudaError_t launch_fast(const LaunchArgs &a, int warps, int grid, cudaStream_t st);
