@@ -493,15 +493,18 @@ __device__ __forceinline__ void stage_rows(double *stg, const double *recA, bool
 }
 
 // One pivot step of the 2-D tiled elimination on the leading column of the
-// lanes' column slices; cgj = column group that owns it.  Returns true when no
-// usable pivot exists.
+// lanes' column slices; cgj = column group that owns it.  The pivot row is
+// written to `urow` (global scratch) on the way.  Returns true when no usable
+// pivot exists.
 template <int n>
 __device__ __forceinline__ bool elim_step(double (&w)[FastLayout<n>::KS][FastLayout<n>::LC],
                                           double (&rhs)[FastLayout<n>::KS], unsigned &act,
-                                          int (&mycol)[FastLayout<n>::KS], int j, int cgj, int rg, int cg)
+                                          double *urow, int cgj, int rg, int cg)
 {
     constexpr int KS = FastLayout<n>::KS, LC = FastLayout<n>::LC;
-    const bool owner = cg == cgj;
+    // bit 8k: slot k of this row group holds a live equation
+    const unsigned myact = (act >> rg) & 0x010101u;
+    const unsigned cand = (cg == cgj) ? myact : 0u;
     // column-j entries of this row group's rows, from the group's owner lane
     double colj[KS];
 #pragma unroll
@@ -512,8 +515,7 @@ __device__ __forceinline__ bool elim_step(double (&w)[FastLayout<n>::KS][FastLay
     double bval = 1.0;
 #pragma unroll
     for (int k = 0; k < KS; k++) {
-        const bool a = owner && ((act >> (k * 8 + rg)) & 1u);
-        const int h = a ? ((__double2hiint(fabs(w[k][0])) & ~3) | (KS - 1 - k)) : -1;
+        const int h = ((cand >> (8 * k)) & 1u) ? ((__double2hiint(w[k][0]) & 0x7ffffffc) | (KS - 1 - k)) : -1;
         if (h > best) { best = h; bval = w[k][0]; }
     }
     const double rloc = fast_rcp(bval);          // speculative: off the critical path
@@ -521,14 +523,12 @@ __device__ __forceinline__ bool elim_step(double (&w)[FastLayout<n>::KS][FastLay
     const unsigned who = __ballot_sync(FULLMASK, best == mx);
     if ((mx >> 2) <= 0) return true;
     const int pl = __ffs(who) - 1, kp = KS - 1 - (mx & 3), rgp = pl >> 2;
-    const double rp = __shfl_sync(FULLMASK, rloc, pl);
+    const double rp = -__shfl_sync(FULLMASK, rloc, pl);
+    // rows to update: the live ones except the pivot row itself
+    const unsigned um = (rg == rgp) ? (myact & ~(1u << (8 * kp))) : myact;
     double m[KS];
 #pragma unroll
-    for (int k = 0; k < KS; k++) {
-        const bool a = ((act >> (k * 8 + rg)) & 1u) && !(rg == rgp && k == kp);
-        m[k] = a ? -colj[k] * rp : 0.0;
-        if (rg == rgp && k == kp) mycol[k] = j;
-    }
+    for (int k = 0; k < KS; k++) m[k] = ((um >> (8 * k)) & 1u) ? colj[k] * rp : 0.0;
     // this lane's column slice of the pivot row: one shuffle serves all 4 column groups
     double p[LC], pr;
     const int src = (rgp << 2) | cg;
@@ -546,18 +546,28 @@ __device__ __forceinline__ bool elim_step(double (&w)[FastLayout<n>::KS][FastLay
         pr = __shfl_sync(FULLMASK, rhs[KS > 2 ? 2 : 0], src);
     }
     act &= ~(1u << (kp * 8 + rgp));
-    // update; after the last column group of a slice position the live rows drop
-    // their leading entry, so the current column is always entry 0 of the slice
-    const bool slide = cgj == 3;
+    // the pivot row goes to scratch (row group 0 holds a copy of every slice)
+    if (rg == 0) {
 #pragma unroll
-    for (int k = 0; k < KS; k++) {
-        const bool live = (act >> (k * 8 + rg)) & 1u;
-        rhs[k] = fma(m[k], pr, rhs[k]);
-        if (slide && live) {
+        for (int l2 = 0; l2 < LC / 2; l2++)
+            reinterpret_cast<double2 *>(urow + cg * LC)[l2] = make_double2(p[2 * l2], p[2 * l2 + 1]);
+        if (cg == 0) urow[4 * LC] = pr;
+    }
+    // update; after the last column group of a slice position every row drops its
+    // leading entry, so the current column is always entry 0 of the slice (dead
+    // slots slide along: their contents are never used again)
+#pragma unroll
+    for (int k = 0; k < KS; k++) rhs[k] = fma(m[k], pr, rhs[k]);
+    if (cgj == 3) {
+#pragma unroll
+        for (int k = 0; k < KS; k++) {
 #pragma unroll
             for (int l = 0; l + 1 < LC; l++) w[k][l] = fma(m[k], p[l + 1], w[k][l + 1]);
             w[k][LC - 1] = 0.0;
-        } else {
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < KS; k++) {
 #pragma unroll
             for (int l = 0; l < LC; l++) w[k][l] = fma(m[k], p[l], w[k][l]);
         }
@@ -763,7 +773,6 @@ disort_fast_kernel(const LaunchArgs a)
         double *stg = tsm_base + 3 * FL::rec;     // assembled rows of the current layer
         if (!status) {
             double w[KS][LC], rhs[KS];
-            int mycol[KS];
             warp_copy_async(rslot, recs, FL::rec, lane);
             if (ncut > 1) warp_copy_async(rslot + FL::rec, recs + FL::rec, FL::rec, lane);
             cp_async_commit();
@@ -777,7 +786,6 @@ disort_fast_kernel(const LaunchArgs a)
 #pragma unroll
             for (int k = 0; k < KS; k++) {
                 const int r = k * 8 + rg;
-                mycol[k] = -1;
                 if (r < n) {
 #pragma unroll
                     for (int l = 0; l < LC; l++) w[k][l] = stg[r * US + cg * LC + l];
@@ -853,23 +861,12 @@ disort_fast_kernel(const LaunchArgs a)
                 act |= newm;
                 // eliminate the N columns of layer lc: one loop body serves all of them
                 // (the slices slide, see elim_step)
+                // pivot row j lands in scratch as [cg][l - j/4] slices, then the right-hand side
+                double *ul = ublk + (size_t)lc * FL::ublk;
                 bool sing = false;
 #pragma unroll 1
-                for (int j = 0; j < N && !sing; j++) sing = elim_step<n>(w, rhs, act, mycol, j, j & 3, rg, cg);
+                for (int j = 0; j < N && !sing; j++) sing = elim_step<n>(w, rhs, act, ul + j * US, j & 3, rg, cg);
                 if (sing) { status = SBD_BIN_SINGULAR; break; }
-                // pivot rows -> scratch: row j as [cg][l - j/4] slices, then the right-hand side
-                double *ul = ublk + (size_t)lc * FL::ublk;
-#pragma unroll
-                for (int k = 0; k < KS; k++) {
-                    if (mycol[k] >= 0) {
-                        double *dst = ul + mycol[k] * US + cg * LC;
-#pragma unroll
-                        for (int l2 = 0; l2 < LC / 2; l2++)
-                            reinterpret_cast<double2 *>(dst)[l2] = make_double2(w[k][2 * l2], w[k][2 * l2 + 1]);
-                        if (cg == 0) ul[mycol[k] * US + 4 * LC] = rhs[k];
-                        mycol[k] = -1;
-                    }
-                }
                 cp_async_wait_all();       // record lc+2 has landed
                 __syncwarp();
             }
