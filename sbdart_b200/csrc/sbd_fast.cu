@@ -502,9 +502,9 @@ __device__ __forceinline__ bool elim_step(double (&w)[FastLayout<n>::KS][FastLay
                                           double *urow, int cgj, int rg, int cg)
 {
     constexpr int KS = FastLayout<n>::KS, LC = FastLayout<n>::LC;
-    // bit 8k: slot k of this row group holds a live equation
-    const unsigned myact = (act >> rg) & 0x010101u;
-    const unsigned cand = (cg == cgj) ? myact : 0u;
+    // bit 8k: slot k of this row group holds a live equation (pivot candidates: the
+    // owner lanes' live rows)
+    const unsigned cand = (cg == cgj) ? ((act >> rg) & 0x010101u) : 0u;
     // column-j entries of this row group's rows, from the group's owner lane
     double colj[KS];
 #pragma unroll
@@ -524,11 +524,13 @@ __device__ __forceinline__ bool elim_step(double (&w)[FastLayout<n>::KS][FastLay
     if ((mx >> 2) <= 0) return true;
     const int pl = __ffs(who) - 1, kp = KS - 1 - (mx & 3), rgp = pl >> 2;
     const double rp = -__shfl_sync(FULLMASK, rloc, pl);
-    // rows to update: the live ones except the pivot row itself
-    const unsigned um = (rg == rgp) ? (myact & ~(1u << (8 * kp))) : myact;
+    // Every slot is updated, dead ones included: a row that served as a pivot
+    // annihilates itself to rounding level (multiplier -1) and only carries finite
+    // residue afterwards; it is never a pivot candidate again and is overwritten
+    // when the slot receives a new equation.
     double m[KS];
 #pragma unroll
-    for (int k = 0; k < KS; k++) m[k] = ((um >> (8 * k)) & 1u) ? colj[k] * rp : 0.0;
+    for (int k = 0; k < KS; k++) m[k] = colj[k] * rp;
     // this lane's column slice of the pivot row: one shuffle serves all 4 column groups
     double p[LC], pr;
     const int src = (rgp << 2) | cg;
