@@ -338,13 +338,24 @@ extern "C" int sbd_disort_batch(sbd_handle *h, const sbd_dims *dims, const doubl
     double *o = (double *)h->d_out.p;
     double *dst[5] = { rfldir, rfldn, flup, dfdt, uavg };
     // Pipeline over chunks of bins: H2D of chunk c+1 and D2H of chunk c-1 overlap the
-    // kernel of chunk c (three streams, events between them).
-    int nchunk = (int)(B / 16384);
-    if (nchunk < 1) nchunk = 1;
-    if (nchunk > 8) nchunk = 8;
+    // kernel of chunk c (three streams, events between them).  Only the first copy in
+    // and the last copy out are exposed, so the chunks start small and double
+    // (4096, 8192, ... bins), and the remainder is cut into at most 4 equal parts.
+    size_t cuts[9];
+    int nchunk = 0;
+    cuts[0] = 0;
+    {
+        size_t pos = 0, step = 4096;
+        while (pos < B && nchunk < 4 && B - pos > 2 * step) { pos += step; cuts[++nchunk] = pos; step *= 2; }
+        const size_t rest = B - pos;
+        int parts = (int)((rest + 32767) / 32768);
+        if (parts < 1) parts = 1;
+        if (parts > 4) parts = 4;
+        for (int i = 1; i <= parts; i++) cuts[++nchunk] = pos + rest * i / parts;
+    }
     CK(cudaStreamSynchronize(h->copy_out));
     for (int c = 0; c < nchunk; c++) {
-        const size_t b0 = B * c / nchunk, b1 = B * (c + 1) / nchunk, nb = b1 - b0;
+        const size_t b0 = cuts[c], b1 = cuts[c + 1], nb = b1 - b0;
         cudaStream_t si = nchunk > 1 ? h->copy_in : st;
         CK(cudaMemcpyAsync((double *)h->d_dtauc.p + b0 * L, dtauc + b0 * L, nb * L * 8, cudaMemcpyHostToDevice, si));
         CK(cudaMemcpyAsync((double *)h->d_ssalb.p + b0 * L, ssalb + b0 * L, nb * L * 8, cudaMemcpyHostToDevice, si));
