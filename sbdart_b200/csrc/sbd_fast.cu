@@ -480,15 +480,17 @@ __device__ __forceinline__ void stage_rows(double *stg, const double *recA, bool
         for (int k = 0; k < n; k++) rsum = fma(cwt[k] * cmu[k], gdn[k * n], rsum);
     }
     const int pos = (c & 3) * LC + (c >> 2);
-    const int rstep = 32 / (2 * N);
+    constexpr int rstep = 32 / (2 * N);
+    // rows r < n are the downward directions i = n-1-r, rows r >= n the upward ones
+    // i = r-n; for a "+k" column the upward rows read G+ and the downward rows G-
+    const double *gup = rec + (plus ? FL::off_gp : FL::off_gm) + j;
+    const double *gdw = rec + (plus ? FL::off_gm : FL::off_gp) + j;
+    const double rfl = refl * rsum;
 #pragma unroll 1
     for (int rr = lane / (2 * N); rr < nrows; rr += rstep) {
         const int r = r0 + rr;
-        const bool up = r >= n;
-        const int i = up ? r - n : n - 1 - r;
-        double v = rec[((up == plus) ? FL::off_gp : FL::off_gm) + i * n + j];
-        if (refl != 0.0) v = fma(-refl, rsum, v);
-        stg[rr * US + pos] = v * fac;
+        const double v = r >= n ? gup[(r - n) * n] : gdw[(n - 1 - r) * n];
+        stg[rr * US + pos] = (v - rfl) * fac;
     }
 }
 
@@ -499,7 +501,7 @@ __device__ __forceinline__ void stage_rows(double *stg, const double *recA, bool
 template <int n>
 __device__ __forceinline__ bool elim_step(double (&w)[FastLayout<n>::KS][FastLayout<n>::LC],
                                           double (&rhs)[FastLayout<n>::KS], unsigned &act,
-                                          double *urow, int cgj, int rg, int cg)
+                                          double *uslice /* urow + cg*LC */, int cgj, int rg, int cg)
 {
     constexpr int KS = FastLayout<n>::KS, LC = FastLayout<n>::LC;
     // bit 8k: slot k of this row group holds a live equation (pivot candidates: the
@@ -552,8 +554,8 @@ __device__ __forceinline__ bool elim_step(double (&w)[FastLayout<n>::KS][FastLay
     if (rg == 0) {
 #pragma unroll
         for (int l2 = 0; l2 < LC / 2; l2++)
-            reinterpret_cast<double2 *>(urow + cg * LC)[l2] = make_double2(p[2 * l2], p[2 * l2 + 1]);
-        if (cg == 0) urow[4 * LC] = pr;
+            reinterpret_cast<double2 *>(uslice)[l2] = make_double2(p[2 * l2], p[2 * l2 + 1]);
+        if (cg == 0) uslice[4 * LC] = pr;
     }
     // update; after the last column group of a slice position every row drops its
     // leading entry, so the current column is always entry 0 of the slice (dead
@@ -864,10 +866,10 @@ disort_fast_kernel(const LaunchArgs a)
                 // eliminate the N columns of layer lc: one loop body serves all of them
                 // (the slices slide, see elim_step)
                 // pivot row j lands in scratch as [cg][l - j/4] slices, then the right-hand side
-                double *ul = ublk + (size_t)lc * FL::ublk;
+                double *uslice = ublk + (size_t)lc * FL::ublk + cg * LC;
                 bool sing = false;
 #pragma unroll 1
-                for (int j = 0; j < N && !sing; j++) sing = elim_step<n>(w, rhs, act, ul + j * US, j & 3, rg, cg);
+                for (int j = 0; j < N && !sing; j++, uslice += US) sing = elim_step<n>(w, rhs, act, uslice, j & 3, rg, cg);
                 if (sing) { status = SBD_BIN_SINGULAR; break; }
                 cp_async_wait_all();       // record lc+2 has landed
                 __syncwarp();
@@ -902,22 +904,20 @@ disort_fast_kernel(const LaunchArgs a)
                 const double *ubuf = tsm_base + buf * kSlot;
                 const double *fr = ubuf + FL::ublk;
                 double acc = 0.0, diag = 1.0;
-                double ur[N];      // row `lane` of the upper triangle
-#pragma unroll
-                for (int j = 0; j < N; j++) ur[j] = 0.0;
-                if (lane < N) {
+                double ur[N];      // row `lane` of the upper triangle (entries left of the diagonal unused)
+                {
                     // stored row `lane`: window column c sits at (c & 3) * LC + (c >> 2) - lane / 4
                     // (the slices had slid lane/4 times when the row became a pivot)
-                    const double *u = ubuf + lane * US - (lane >> 2);
-                    acc = ubuf[lane * US + 4 * LC];
+                    const int row = lane < N ? lane : 0;
+                    const double *u = ubuf + row * US - (row >> 2);
+                    acc = ubuf[row * US + 4 * LC];
 #pragma unroll
                     for (int j = 0; j < N; j++)
                         acc = fma(-u[((N + j) & 3) * LC + ((N + j) >> 2)], xs[j], acc);
 #pragma unroll
-                    for (int c = 0; c < N; c++) if (c >= lane) ur[c] = u[(c & 3) * LC + (c >> 2)];
+                    for (int c = 1; c < N; c++) ur[c] = u[(c & 3) * LC + (c >> 2)];
+                    diag = u[(row & 3) * LC + (row >> 2)];
                 }
-#pragma unroll
-                for (int j = 0; j < N; j++) if (j == lane) diag = ur[j];
                 const double dinv = fast_rcp(diag);
 #pragma unroll
                 for (int c = N - 1; c >= 0; c--) {
@@ -950,11 +950,18 @@ disort_fast_kernel(const LaunchArgs a)
                     if (atbot || attop) {
                         // lanes 0..2 take one functional each; x is uniform
                         double xe[N];
+                        if (atbot) {
 #pragma unroll
-                        for (int j = 0; j < n; j++) {
-                            const double e = fr[FL::f_ek + j];
-                            xe[n + j] = atbot ? xs[n + j] * e : xs[n + j];
-                            xe[n - 1 - j] = atbot ? xs[n - 1 - j] : xs[n - 1 - j] * e;
+                            for (int j = 0; j < n; j++) {
+                                xe[n + j] = xs[n + j] * fr[FL::f_ek + j];
+                                xe[n - 1 - j] = xs[n - 1 - j];
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < n; j++) {
+                                xe[n + j] = xs[n + j];
+                                xe[n - 1 - j] = xs[n - 1 - j] * fr[FL::f_ek + j];
+                            }
                         }
                         if (lane < 3) {
                             const double2 *cu2 = reinterpret_cast<const double2 *>(fr + FL::f_cu + lane * N);
