@@ -112,6 +112,16 @@ __device__ __forceinline__ double fast_rcp(double x)
     return y;
 }
 
+// 1/sqrt(x) to ~1 ulp: MUFU.RSQ64H seed (2^-26) + one third-order correction
+// (x must be normal and positive).
+__device__ __forceinline__ double fast_rsqrt(double x)
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double e = fma(-x, y * y, 1.0);
+    return fma(fma(e, 0.375, 0.5), y * e, y);
+}
+
 // sum over the n lanes of a layer group
 template <int n>
 __device__ __forceinline__ double group_sum(double v)
@@ -119,6 +129,27 @@ __device__ __forceinline__ double group_sum(double v)
 #pragma unroll
     for (int o = n / 2; o > 0; o >>= 1) v += __shfl_xor_sync(FULLMASK, v, o, n);
     return v;
+}
+
+// Round-robin (tournament) pairing of the one-sided Jacobi sweeps: the partner of
+// lane g in round r, 3 bits per round (n <= 8).
+template <int n>
+__device__ __forceinline__ unsigned jacobi_partners(int g)
+{
+    unsigned pk = 0;
+#pragma unroll
+    for (int r = 0; r < n - 1; r++) {
+        int partner;
+        if (g == n - 1) partner = r;
+        else if (g == r) partner = n - 1;
+        else {
+            partner = 2 * r - g + (n - 1);
+            if (partner >= n - 1) partner -= n - 1;
+            if (partner >= n - 1) partner -= n - 1;
+        }
+        pk |= (unsigned)partner << (3 * r);
+    }
+    return pk;
 }
 
 // ---------------------------------------------------------------------------
@@ -132,7 +163,8 @@ __device__ __forceinline__ int phase1_layers(
     const double *cmu, const double *cwt, const double *csq, const double *cdinv, const double *cylm,
     const double *y0, const double *taucpr, const double *pk,
     double *tsm /* per-task shared */, double *rec /* scratch record of this layer */,
-    double *frec /* flux record of this layer */, int g /* lane in group */)
+    double *frec /* flux record of this layer */, int g /* lane in group */,
+    unsigned jpart /* Jacobi partners of this lane, see jacobi_partners */)
 {
     using FL = FastLayout<n>;
     constexpr int N = 2 * n;
@@ -197,7 +229,7 @@ __device__ __forceinline__ int phase1_layers(
         // Pe~ is only semidefinite when w' -> 1: keep the factor real
         const double floor_e = 1.0e-30;
         if (!(pive > floor_e)) pive = floor_e;
-        const double rie = rsqrt(pive), rio = rsqrt(pivo);
+        const double rie = fast_rsqrt(pive), rio = fast_rsqrt(pivo);
         rK[j] = rie; rL[j] = rio;
         pe[j] = (g == j) ? pive * rie : ((g > j) ? nume * rie : 0.0);
         po[j] = (g == j) ? pivo * rio : ((g > j) ? numo * rio : 0.0);
@@ -239,14 +271,7 @@ __device__ __forceinline__ int phase1_layers(
             int big = 0;
 #pragma unroll 1
             for (int r = 0; r < n - 1; r++) {     // not unrolled: keeps the code in the I-cache
-                int partner;
-                if (g == n - 1) partner = r;
-                else if (g == r) partner = n - 1;
-                else {
-                    partner = 2 * r - g + (n - 1);
-                    if (partner >= n - 1) partner -= n - 1;
-                    if (partner >= n - 1) partner -= n - 1;
-                }
+                const int partner = (jpart >> (3 * r)) & 7;
                 double pa[n];
                 double g0 = 0.0, g1 = 0.0;
                 const double oth2 = shfl_d(own2, partner, n);
@@ -257,19 +282,23 @@ __device__ __forceinline__ int phase1_layers(
                 }
                 const double gam = g0 + g1;
                 const bool lo = g < partner;
-                const double alpha = lo ? own2 : oth2, beta = lo ? oth2 : own2;
-                const double gg = gam * gam, ab = alpha * beta;
+                const double gg = gam * gam, ab = own2 * oth2;
                 // rotate unless the pair is orthogonal to 1e-12 (eigenvectors then carry
                 // errors ~1e-12, far below the 1e-5 target)
-                if (gg > 1.0e-24 * ab && fabs(gam) > 1.0e-300) {
+                if (gg > 1.0e-24 * ab && gg > 1.0e-290) {
                     if (gg > 1.0e-10 * ab) big = 1;
-                    const double dl = 0.5 * (beta - alpha);
-                    const double h2 = fma(dl, dl, gg);
-                    const double hy = h2 * rsqrt(h2);
-                    const double t = gam * fast_rcp(dl + (dl >= 0.0 ? hy : -hy));
-                    const double cc = rsqrt(fma(t, t, 1.0));
-                    const double sn = lo ? -t * cc : t * cc;
-                    own2 = lo ? fma(-t, gam, own2) : fma(t, gam, own2);
+                    // rotation by theta, |theta| <= pi/4: cos 2theta = |dl| / h, sin 2theta = gam / h
+                    // with dl = (beta - alpha) / 2, h = sqrt(dl^2 + gam^2); no division:
+                    // c = sqrt(x), x = (1 + cos 2theta) / 2, s = sin 2theta / (2 c), t = s / c
+                    const double dl = lo ? 0.5 * (oth2 - own2) : 0.5 * (own2 - oth2);
+                    const double rh = fast_rsqrt(fma(dl, dl, gg));
+                    const double x = fma(0.5 * fabs(dl), rh, 0.5);
+                    const double rc = fast_rsqrt(x);
+                    const double cc = x * rc;
+                    double sn = gam * (0.5 * rh) * rc;       // sign of gam
+                    if ((dl < 0.0) != lo) sn = -sn;          // sign(dl), and the low column takes -s
+                    // squared norms follow analytically: alpha' = alpha - t gam, beta' = beta + t gam
+                    own2 = fma(sn * rc, gam, own2);
 #pragma unroll
                     for (int i = 0; i < n; i++) a[i] = fma(sn, pa[i], cc * a[i]);
                 }
@@ -627,6 +656,7 @@ disort_fast_kernel(const LaunchArgs a)
     const int g = lane % n, task = lane / n;
     double *tsm = tsm_base + (size_t)task * FL::task;
     const int rg = lane >> 2, cg = lane & 3;              // 2-D tiling of phase 2
+    const unsigned jpart = jacobi_partners<n>(g);
 
     for (;;) {
         int bin = 0;
@@ -760,7 +790,7 @@ disort_fast_kernel(const LaunchArgs a)
                 if (!active) lc = ncut - 1;
                 int st = phase1_layers<n>(dtauc, ssalb, pmom, ldp, lc, active, 0, fbeam, umu0, plank,
                                           1.0, cmu, cwt, csq, cdinv, cylm, y0, taucpr, pk, tsm,
-                                          recs + (size_t)lc * FL::rec, frecs + (size_t)lc * FL::frec, g);
+                                          recs + (size_t)lc * FL::rec, frecs + (size_t)lc * FL::frec, g, jpart);
                 if (__any_sync(FULLMASK, st != 0)) { status = SBD_BIN_EIG_FAIL; break; }
             }
         }
