@@ -286,7 +286,10 @@ __device__ __forceinline__ int phase1_layers(
                 // rotate unless the pair is orthogonal to 1e-12 (eigenvectors then carry
                 // errors ~1e-12, far below the 1e-5 target)
                 if (gg > 1.0e-24 * ab && gg > 1.0e-290) {
-                    if (gg > 1.0e-10 * ab) big = 1;
+#ifndef SBD_JACOBI_BIG
+#define SBD_JACOBI_BIG 1.0e-10
+#endif
+                    if (gg > SBD_JACOBI_BIG * ab) big = 1;
                     // rotation by theta, |theta| <= pi/4: cos 2theta = |dl| / h, sin 2theta = gam / h
                     // with dl = (beta - alpha) / 2, h = sqrt(dl^2 + gam^2); no division:
                     // c = sqrt(x), x = (1 + cos 2theta) / 2, s = sin 2theta / (2 c), t = s / c

@@ -1,0 +1,96 @@
+"""Throughput of the other BASELINE.json configurations (not the headline bench line).
+
+bench.py measures config C2.  This script times the same C-ABI host call
+(sbd_disort_batch: pinned-free numpy host buffers, H2D + kernel + D2H inside) on
+bin sets shaped like C1, C3, C4 and C5 and checks a sample of every
+set against the CPU oracle.  One JSON line per configuration.
+
+    python tools/bench_configs.py [--quick]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import sbdart_b200 as sb                      # noqa: E402
+from sbdart_b200 import workloads            # noqa: E402
+from oracle import oracle                    # noqa: E402
+
+
+def tile(w, rep):
+    if rep <= 1:
+        return w
+    w = dict(w)
+    for k in ("dtauc", "ssalb", "pmom"):
+        w[k] = np.tile(w[k], (rep,) + (1,) * (w[k].ndim - 1))
+    w["bins"] = np.tile(w["bins"], rep)
+    return w
+
+
+def check(w, got, nsample, umu=None, phi=None):
+    """Largest relative flux mismatch against the oracle on the first nsample bins."""
+    idx = np.arange(min(nsample, len(w["bins"])))
+    b = w["bins"][idx]
+    ref = oracle.disort_flux_batch(
+        w["dtauc"][idx], w["ssalb"][idx], w["pmom"][idx], nstr=w["nstr"], fbeam=b["fbeam"],
+        umu0=b["umu0"], albedo=b["albedo"], plank=b["plank"], wvnmlo=b["wvnmlo"],
+        wvnmhi=b["wvnmhi"], btemp=b["btemp"], ttemp=b["ttemp"], temis=b["temis"],
+        fisot=b["fisot"], temper=w["temper"], col=b["col"], nthreads=os.cpu_count() or 1)
+    ok = ref["status"] == 0
+    worst = 0.0
+    for k in ("rfldir", "rfldn", "flup"):
+        scale = np.abs(ref["flup"][ok]).max(axis=1, keepdims=True) + np.abs(ref["rfldir"][ok]).max(axis=1, keepdims=True)
+        err = np.abs(got[k][idx][ok] - ref[k][ok]) / (np.abs(ref[k][ok]) + 1e-9 * scale)
+        worst = max(worst, float(err.max()))
+    return worst, int((got["status"][idx] != ref["status"]).sum())
+
+
+def run(name, w, solver, reps=3, nsample=64, **kw):
+    t = []
+    got = None
+    for _ in range(reps + 1):
+        t0 = time.perf_counter()
+        got = solver.disort_batch(w["dtauc"], w["ssalb"], w["pmom"], w["bins"], nstr=w["nstr"],
+                                  temper=w["temper"], **kw)
+        t.append(time.perf_counter() - t0)
+    dt = min(t[1:])
+    worst, stat_mismatch = check(w, got, nsample)
+    B = len(w["bins"])
+    print(json.dumps({"config": name, "bins": B, "nstr": w["nstr"], "nlyr": int(w["dtauc"].shape[1]),
+                      "e2e_bins_per_s": B / dt, "ms": dt * 1e3, "bad_bins": int((got["status"] != 0).sum()),
+                      "max_rel_flux_err_vs_oracle": worst, "status_mismatch": stat_mismatch,
+                      "oracle_sample": min(nsample, B), **{k: (len(v) if hasattr(v, "__len__") else v) for k, v in kw.items()}}),
+          flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--quick", action="store_true")
+    a = ap.parse_args()
+    s = sb.Solver(0)
+    q = 8 if a.quick else 1
+    # C1: NSTR=4, 33 layers, 151 wavelengths (x k-terms), replicated
+    w = workloads.mls_shortwave(nstr=4, wlinf=0.25, wlsup=1.0, wlinc=0.005)
+    run("C1 nstr4 L33 shortwave", tile(w, 256 // q), s)
+    # C3: NSTR=8 thermal, radiances at 10 zenith angles (generic kernel), and its flux-only twin
+    w = workloads.mls_shortwave(nstr=8, wlinf=4.0, wlsup=20.0, wlinc=0.05)
+    umu = np.cos(np.deg2rad(np.linspace(5.0, 85.0, 10)))[::-1].copy()
+    run("C3 nstr8 L33 thermal flux", tile(w, 64 // q), s)
+    run("C3 nstr8 L33 thermal radiance 10 zenith x 1 azimuth", tile(w, 4 // min(q, 4)), s,
+        umu=np.sort(umu), phi=np.array([0.0]))
+    # C4: NSTR=32, 65 layers (generic kernel)
+    w = workloads.mls_shortwave(nstr=32, nlyr=65, wlinf=0.25, wlsup=4.0, wlinc=0.02, cloud_tau=10.0)
+    run("C4 nstr32 L65 cloud", tile(w, 4 // min(q, 4)), s, nsample=32)
+    # C5: retrieval batch, NSTR=16, one GPU's share of 10^6 bins
+    w = workloads.retrieval_batch(125000 // q, nstr=16, nlyr=33, ncols=125 // q or 1)
+    run("C5 nstr16 L33 retrieval (1/8 of 1e6 bins)", w, s)
+    s.close()
+
+
+if __name__ == "__main__":
+    main()
