@@ -190,3 +190,33 @@ def test_beam_angle_clash_is_reported_for_retry(solver):
     got = solver.disort_batch(w["dtauc"], w["ssalb"], w["pmom"], w["bins"], nstr=8)
     ref = oracle_flux(w)
     assert list(got["status"]) == [1, 0, 1, 0] == list(ref["status"])
+
+
+@pytest.mark.parametrize("nstr", [8, 16])
+def test_user_optical_depths_inside_layers(solver, nstr):
+    """USRTAU: output levels inside layers and on boundaries (disort.f:2534-2543,
+    :2610-2625); SBDART itself never uses it, the drop-in disort_ must still honour it."""
+    rng = np.random.default_rng(11)
+    w = workloads.mls_shortwave(nstr=nstr, wlinf=1.9, wlsup=2.4, wlinc=0.1)   # beam, and beam + Planck
+    B, L = w["dtauc"].shape
+    tot = w["dtauc"].sum(axis=1)
+    frac = np.sort(rng.uniform(0, 1, size=(B, 5)), axis=1)
+    frac[:, 0] = 0.0
+    frac[:, -1] = 1.0
+    utau = frac * tot[:, None]
+    utau[:, 2] = np.cumsum(w["dtauc"], axis=1)[:, L // 2]           # exactly on a boundary
+    utau = np.sort(utau, axis=1)
+    got = solver.disort_batch(w["dtauc"], w["ssalb"], w["pmom"], w["bins"], nstr=nstr,
+                              temper=w["temper"], utau=utau)
+    b = w["bins"]
+    for i in range(B):
+        r = oracle.disort(w["dtauc"][i], w["ssalb"][i], w["pmom"][i], nstr=nstr, temper=w["temper"][0],
+                          utau=utau[i], fbeam=b["fbeam"][i], umu0=b["umu0"][i], albedo=b["albedo"][i],
+                          btemp=b["btemp"][i], ttemp=b["ttemp"][i], temis=b["temis"][i],
+                          wvnmlo=b["wvnmlo"][i], wvnmhi=b["wvnmhi"][i], plank=bool(b["plank"][i]),
+                          onlyfl=True)
+        assert got["status"][i] == r["status"] == 0
+        scale = max(np.abs(r["flup"]).max(), np.abs(r["rfldir"]).max())
+        for k in KEYS:
+            a = 2e-9 * scale * (4 * np.pi if k == "dfdt" else 1.0)
+            np.testing.assert_allclose(got[k][i], r[k], rtol=1e-7, atol=a, err_msg=f"bin {i} {k}")
