@@ -229,13 +229,18 @@ extern "C" int sbd_disort_batch_device(sbd_handle *h, const sbd_dims *dims, cons
     int warps, grid;
     size_t slot;
     if (fast) {
+        // CTA shape: the preferred one (8 warps) unless 4-warp CTAs keep more warps
+        // resident per SM under the shared-memory limit (deep atmospheres)
         warps = fast_warps();
-        size_t smem = fast_smem_bytes(N, L, NT, warps);
-        while (smem > smem_limit && warps > 4) { warps /= 2; smem = fast_smem_bytes(N, L, NT, warps); }
-        if (smem > smem_limit) return SBD_ERR_UNSUPPORTED;
-        int cta_per_sm = (int)((smem_limit + 1024) / (smem + 1024));
-        if (cta_per_sm > 16 / warps) cta_per_sm = 16 / warps;
-        if (cta_per_sm < 1) cta_per_sm = 1;
+        int cta_per_sm = 0;
+        for (int wtry = warps; wtry >= 4; wtry /= 2) {
+            const size_t smem = fast_smem_bytes(N, L, NT, wtry);
+            if (smem > smem_limit) continue;
+            int c = (int)((smem_limit + 1024) / (smem + 1024));
+            if (c > 16 / wtry) c = 16 / wtry;
+            if (c * wtry > cta_per_sm * warps || cta_per_sm == 0) { cta_per_sm = c; warps = wtry; }
+        }
+        if (cta_per_sm == 0) return SBD_ERR_UNSUPPORTED;
         grid = h->sm_count * cta_per_sm;
         slot = fast_slot_doubles(N, L);
     } else {

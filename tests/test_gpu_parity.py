@@ -220,3 +220,15 @@ def test_user_optical_depths_inside_layers(solver, nstr):
         for k in KEYS:
             a = 2e-9 * scale * (4 * np.pi if k == "dfdt" else 1.0)
             np.testing.assert_allclose(got[k][i], r[k], rtol=1e-7, atol=a, err_msg=f"bin {i} {k}")
+
+
+@pytest.mark.parametrize("nstr", [8, 16])
+def test_deep_atmosphere_65_layers(solver, nstr):
+    """65 layers (SBDART ngrid=65, the layer count of config C4) with a cloud layer: the
+    register kernel falls back to 4-warp CTAs to fit shared memory."""
+    w = workloads.mls_shortwave(nstr=nstr, nlyr=65, wlinf=0.4, wlsup=3.0, wlinc=0.1, cloud_tau=10.0)
+    got = solver.disort_batch(w["dtauc"], w["ssalb"], w["pmom"], w["bins"], nstr=nstr,
+                              temper=w["temper"])
+    ref = oracle_flux(w)
+    assert (ref["status"] == 0).all()
+    assert_close(got, ref, rtol=1e-7, atol_scale=2e-9)

@@ -33,7 +33,8 @@ def tile(w, rep):
 
 
 def check(w, got, nsample, umu=None, phi=None):
-    """Largest relative flux mismatch against the oracle on the first nsample bins."""
+    """Largest flux mismatch against the oracle on the first nsample bins, relative to the
+    bin's largest flux."""
     idx = np.arange(min(nsample, len(w["bins"])))
     b = w["bins"][idx]
     ref = oracle.disort_flux_batch(
@@ -45,7 +46,7 @@ def check(w, got, nsample, umu=None, phi=None):
     worst = 0.0
     for k in ("rfldir", "rfldn", "flup"):
         scale = np.abs(ref["flup"][ok]).max(axis=1, keepdims=True) + np.abs(ref["rfldir"][ok]).max(axis=1, keepdims=True)
-        err = np.abs(got[k][idx][ok] - ref[k][ok]) / (np.abs(ref[k][ok]) + 1e-9 * scale)
+        err = np.abs(got[k][idx][ok] - ref[k][ok]) / np.maximum(scale, 1e-300)
         worst = max(worst, float(err.max()))
     return worst, int((got["status"][idx] != ref["status"]).sum())
 
@@ -63,7 +64,7 @@ def run(name, w, solver, reps=3, nsample=64, **kw):
     B = len(w["bins"])
     print(json.dumps({"config": name, "bins": B, "nstr": w["nstr"], "nlyr": int(w["dtauc"].shape[1]),
                       "e2e_bins_per_s": B / dt, "ms": dt * 1e3, "bad_bins": int((got["status"] != 0).sum()),
-                      "max_rel_flux_err_vs_oracle": worst, "status_mismatch": stat_mismatch,
+                      "max_flux_err_over_bin_scale_vs_oracle": worst, "status_mismatch": stat_mismatch,
                       "oracle_sample": min(nsample, B), **{k: (len(v) if hasattr(v, "__len__") else v) for k, v in kw.items()}}),
           flush=True)
 
@@ -81,11 +82,11 @@ def main():
     w = workloads.mls_shortwave(nstr=8, wlinf=4.0, wlsup=20.0, wlinc=0.05)
     umu = np.cos(np.deg2rad(np.linspace(5.0, 85.0, 10)))[::-1].copy()
     run("C3 nstr8 L33 thermal flux", tile(w, 64 // q), s)
-    run("C3 nstr8 L33 thermal radiance 10 zenith x 1 azimuth", tile(w, 4 // min(q, 4)), s,
+    run("C3 nstr8 L33 thermal radiance 10 zenith x 1 azimuth", tile(w, 64 // q), s,
         umu=np.sort(umu), phi=np.array([0.0]))
     # C4: NSTR=32, 65 layers (generic kernel)
     w = workloads.mls_shortwave(nstr=32, nlyr=65, wlinf=0.25, wlsup=4.0, wlinc=0.02, cloud_tau=10.0)
-    run("C4 nstr32 L65 cloud", tile(w, 4 // min(q, 4)), s, nsample=32)
+    run("C4 nstr32 L65 cloud", tile(w, 16 // min(q, 4)), s, nsample=32)
     # C5: retrieval batch, NSTR=16, one GPU's share of 10^6 bins
     w = workloads.retrieval_batch(125000 // q, nstr=16, nlyr=33, ncols=125 // q or 1)
     run("C5 nstr16 L33 retrieval (1/8 of 1e6 bins)", w, s)
