@@ -37,6 +37,21 @@ namespace sbd {
 
 #define FULLMASK 0xffffffffu
 
+#ifdef SBD_PHASE_TIMING
+// debug build only: SM-clock ticks spent between the phase barriers, summed over CTAs
+__device__ unsigned long long g_phase_ticks[4];
+#define SBD_TICK(i)                                                                     \
+    do {                                                                                \
+        if (threadIdx.x == 0) {                                                         \
+            const long long tnow = clock64();                                           \
+            atomicAdd(&g_phase_ticks[i], (unsigned long long)(tnow - tphase));          \
+            tphase = tnow;                                                              \
+        }                                                                               \
+    } while (0)
+#else
+#define SBD_TICK(i) do { } while (0)
+#endif
+
 
 template <int n>
 struct FastLayout {
@@ -668,6 +683,9 @@ disort_fast_kernel(const LaunchArgs a)
         const bool have = bin < a.d.nbins;
         if (SYNC) { if (!__syncthreads_or(have)) break; }
         else if (!have) break;
+#ifdef SBD_PHASE_TIMING
+        long long tphase = clock64();
+#endif
         const int src = !have ? 0 : (a.binmap ? a.binmap[bin] : bin);     // input slot of this bin
         const sbd_bin bp = a.bins[src];
         const double *dtauc = a.dtauc + (size_t)src * L;
@@ -785,6 +803,7 @@ disort_fast_kernel(const LaunchArgs a)
         }
         __syncwarp();
 
+        SBD_TICK(0);
         // ===================== phase 1 =====================================
         if (!status) {
             for (int lc0 = 0; lc0 < ncut; lc0 += TASKS) {
@@ -800,6 +819,7 @@ disort_fast_kernel(const LaunchArgs a)
         __syncwarp();
         __threadfence_block();
         if (SYNC) __syncthreads();
+        SBD_TICK(1);
 
         // ===================== phase 2: downward elimination ================
         // The window rows live in slots (rg, k), k < KS; slot s = k*8 + rg.  `act`
@@ -912,6 +932,7 @@ disort_fast_kernel(const LaunchArgs a)
         __syncwarp();
         __threadfence_block();
         if (SYNC) __syncthreads();
+        SBD_TICK(2);
 
         // ===================== phase 3: back substitution + fluxes ===========
         if (!status) {
@@ -1059,8 +1080,20 @@ disort_fast_kernel(const LaunchArgs a)
         cp_async_wait_all();
         if (lane == 0 && have) a.status[bin] = status;
         __syncwarp();
+#ifdef SBD_PHASE_TIMING
+        if (SYNC) __syncthreads();
+        SBD_TICK(3);
+#endif
     }
 }
+
+#ifdef SBD_PHASE_TIMING
+extern "C" void sbd_debug_phase_ticks(unsigned long long *out, int reset)
+{
+    cudaMemcpyFromSymbol(out, g_phase_ticks, sizeof(g_phase_ticks));
+    if (reset) { unsigned long long z[4] = {0, 0, 0, 0}; cudaMemcpyToSymbol(g_phase_ticks, z, sizeof z); }
+}
+#endif
 
 // ---- host-side launch helpers ---------------------------------------------
 // CTA shape: 8 warps with phase barriers by default (measured best); SBD_FAST_WARPS = 4 | 8 and
