@@ -140,7 +140,9 @@ extern "C" int sbd_create(sbd_handle **out, int device)
         cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&h->ev_k[i], cudaEventDisableTiming);
     }
-    if (h->counter.reserve(256) != cudaSuccess) { delete h; return SBD_ERR_CUDA; }
+    if (h->counter.reserve(256) != cudaSuccess || h->counter2.reserve(256) != cudaSuccess) { delete h; return SBD_ERR_CUDA; }
+    if (cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking) != cudaSuccess) { delete h; return SBD_ERR_CUDA; }
+    cudaEventCreateWithFlags(&h->ev_misc, cudaEventDisableTiming);
     *out = h;
     return SBD_SUCCESS;
 }
@@ -151,11 +153,14 @@ extern "C" void sbd_destroy(sbd_handle *h)
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     for (auto &kv : h->tables) { cudaFree(kv.second.quad); cudaFree(kv.second.ylmc); }
-    SbdDevBuf *bufs[] = { &h->scratch, &h->counter, &h->ylmu, &h->angles, &h->d_dtauc, &h->d_ssalb,
+    cudaStreamSynchronize(h->stream2);
+    SbdDevBuf *bufs[] = { &h->scratch, &h->counter, &h->scratch2, &h->counter2, &h->ylmu, &h->angles, &h->d_dtauc, &h->d_ssalb,
                        &h->d_pmom, &h->d_bins, &h->d_temper, &h->d_utau, &h->d_out, &h->d_uu,
                        &h->d_status, &h->opt_tables, &h->opt_atm, &h->opt_misc, &h->opt_map };
     for (SbdDevBuf *b : bufs) b->release();
     for (int i = 0; i < 8; i++) { cudaEventDestroy(h->ev_in[i]); cudaEventDestroy(h->ev_k[i]); }
+    cudaEventDestroy(h->ev_misc);
+    cudaStreamDestroy(h->stream2);
     cudaStreamDestroy(h->copy_in);
     cudaStreamDestroy(h->copy_out);
     cudaStreamDestroy(h->stream);
@@ -284,9 +289,11 @@ extern "C" int sbd_disort_batch_device(sbd_handle *h, const sbd_dims *dims, cons
     a.nslots = grid * warps;
     a.slot_stride = slot;
     a.nmodes = 1;
-    if (h->scratch.reserve(a.slot_stride * (size_t)a.nslots * 8) != cudaSuccess) return SBD_ERR_CUDA;
-    a.scratch = (double *)h->scratch.p;
-    a.work_counter = (int *)h->counter.p;
+    SbdDevBuf &scr = h->scratch_set ? h->scratch2 : h->scratch;
+    SbdDevBuf &ctr = h->scratch_set ? h->counter2 : h->counter;
+    if (scr.reserve(a.slot_stride * (size_t)a.nslots * 8) != cudaSuccess) return SBD_ERR_CUDA;
+    a.scratch = (double *)scr.p;
+    a.work_counter = (int *)ctr.p;
     if (cudaMemsetAsync(a.work_counter, 0, sizeof(int), st) != cudaSuccess) return SBD_ERR_CUDA;
     cudaError_t le = fast ? launch_fast(a, warps, grid, st) : launch_generic(a, warps, grid, st);
     if (le != cudaSuccess) return SBD_ERR_CUDA;
@@ -343,25 +350,42 @@ extern "C" int sbd_disort_batch(sbd_handle *h, const sbd_dims *dims, const doubl
     double *o = (double *)h->d_out.p;
     double *dst[5] = { rfldir, rfldn, flup, dfdt, uavg };
     // Pipeline over chunks of bins: H2D of chunk c+1 and D2H of chunk c-1 overlap the
-    // kernel of chunk c (three streams, events between them).  Only the first copy in
-    // and the last copy out are exposed, so the chunks start small and double
-    // (4096, 8192, ... bins), and the remainder is cut into at most 4 equal parts.
+    // kernel of chunk c (copy-in, copy-out and two alternating compute streams, events
+    // between them).  Only the first copy in and the last copy out are exposed, so the
+    // chunks ramp up at the front (4096, 8192, 16384 bins) and down at the back
+    // (8192, 4096); the middle is cut into at most 3 equal parts.
     size_t cuts[9];
     int nchunk = 0;
     cuts[0] = 0;
     {
-        size_t pos = 0, step = 4096;
-        while (pos < B && nchunk < 4 && B - pos > 2 * step) { pos += step; cuts[++nchunk] = pos; step *= 2; }
-        const size_t rest = B - pos;
+        const size_t front[3] = { 4096, 8192, 16384 }, back[2] = { 8192, 4096 };
+        size_t lo = 0, hi = B;
+        int nb_back = 0;
+        if (B >= 4 * 4096) {
+            for (int i = 0; i < 3 && hi - lo > 2 * front[i]; i++) { lo += front[i]; cuts[++nchunk] = lo; }
+            for (int i = 1; i >= 0 && hi - lo > 2 * back[i]; i--) { hi -= back[i]; nb_back++; }
+        }
+        const size_t rest = hi - lo;
         int parts = (int)((rest + 32767) / 32768);
         if (parts < 1) parts = 1;
-        if (parts > 4) parts = 4;
-        for (int i = 1; i <= parts; i++) cuts[++nchunk] = pos + rest * i / parts;
+        if (parts > 3) parts = 3;
+        for (int i = 1; i <= parts; i++) cuts[++nchunk] = lo + rest * i / parts;
+        // back ramp: the larger chunk first
+        if (nb_back == 2) { cuts[nchunk + 1] = hi + back[0]; nchunk++; }
+        if (nb_back >= 1) cuts[++nchunk] = B;
     }
     CK(cudaStreamSynchronize(h->copy_out));
+    // flux runs alternate between two compute streams (each with its own scratch set)
+    const bool two = nchunk > 1 && dims->numu == 0;
+    if (two) {       // the second stream sees the temperature upload
+        CK(cudaEventRecord(h->ev_misc, st));
+        CK(cudaStreamWaitEvent(h->stream2, h->ev_misc, 0));
+    }
     for (int c = 0; c < nchunk; c++) {
         const size_t b0 = cuts[c], b1 = cuts[c + 1], nb = b1 - b0;
         cudaStream_t si = nchunk > 1 ? h->copy_in : st;
+        cudaStream_t sk = (two && (c & 1)) ? h->stream2 : st;
+        h->scratch_set = (two && (c & 1)) ? 1 : 0;
         CK(cudaMemcpyAsync((double *)h->d_dtauc.p + b0 * L, dtauc + b0 * L, nb * L * 8, cudaMemcpyHostToDevice, si));
         CK(cudaMemcpyAsync((double *)h->d_ssalb.p + b0 * L, ssalb + b0 * L, nb * L * 8, cudaMemcpyHostToDevice, si));
         CK(cudaMemcpyAsync((double *)h->d_pmom.p + b0 * L * ldp, pmom + b0 * L * ldp, nb * L * ldp * 8,
@@ -371,7 +395,7 @@ extern "C" int sbd_disort_batch(sbd_handle *h, const sbd_dims *dims, const doubl
             CK(cudaMemcpyAsync((double *)h->d_utau.p + b0 * NT, utau + b0 * NT, nb * NT * 8, cudaMemcpyHostToDevice, si));
         if (nchunk > 1) {
             CK(cudaEventRecord(h->ev_in[c], si));
-            CK(cudaStreamWaitEvent(st, h->ev_in[c], 0));
+            CK(cudaStreamWaitEvent(sk, h->ev_in[c], 0));
         }
         sbd_dims dc = *dims;
         dc.nbins = (int32_t)nb;
@@ -381,11 +405,12 @@ extern "C" int sbd_disort_batch(sbd_handle *h, const sbd_dims *dims, const doubl
             dims->ntau > 0 ? (const double *)h->d_utau.p + b0 * NT : nullptr, umu, phi,
             o + b0 * NT, o + per + b0 * NT, o + 2 * per + b0 * NT, o + 3 * per + b0 * NT,
             o + 4 * per + b0 * NT, nuu1 ? (double *)h->d_uu.p + b0 * nuu1 : nullptr,
-            (int32_t *)h->d_status.p + b0, st);
+            (int32_t *)h->d_status.p + b0, sk);
+        h->scratch_set = 0;
         if (rc) return rc;
         cudaStream_t so = nchunk > 1 ? h->copy_out : st;
         if (nchunk > 1) {
-            CK(cudaEventRecord(h->ev_k[c], st));
+            CK(cudaEventRecord(h->ev_k[c], sk));
             CK(cudaStreamWaitEvent(so, h->ev_k[c], 0));
         }
         for (int k = 0; k < 5; k++)
@@ -394,6 +419,7 @@ extern "C" int sbd_disort_batch(sbd_handle *h, const sbd_dims *dims, const doubl
         CK(cudaMemcpyAsync(status + b0, (int32_t *)h->d_status.p + b0, nb * 4, cudaMemcpyDeviceToHost, so));
     }
     CK(cudaStreamSynchronize(st));
+    if (two) CK(cudaStreamSynchronize(h->stream2));
     if (nchunk > 1) CK(cudaStreamSynchronize(h->copy_out));
 #undef CK
     return SBD_SUCCESS;

@@ -39,6 +39,13 @@ struct sbd_handle {
     int64_t launches = 0;
     std::map<int, SbdTables> tables;          // per NSTR
     SbdDevBuf scratch, counter, ylmu, angles;
+    // second scratch set + stream: consecutive chunk kernels of the host-buffer call
+    // run on alternating streams, so the next chunk's CTAs fill the SMs the previous
+    // chunk's tail leaves idle
+    SbdDevBuf scratch2, counter2;
+    cudaStream_t stream2 = nullptr;
+    cudaEvent_t ev_misc = nullptr;
+    int scratch_set = 0;                       // set used by the next device-level launch
     // staging for the host-pointer API
     SbdDevBuf d_dtauc, d_ssalb, d_pmom, d_bins, d_temper, d_utau, d_out, d_uu, d_status;
     // whole-spectrum path (sbd_spectrum.cu)
