@@ -710,7 +710,7 @@ __device__ double usrint_one(const BinCtx &c, const WarpShared &w, const LayerLa
 // ---------------------------------------------------------------------------
 extern __shared__ double smem_dyn[];
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128, 4)
 disort_generic_kernel(const LaunchArgs a)
 {
     const int N = a.d.nstr, n = N / 2, L = a.d.nlyr;
