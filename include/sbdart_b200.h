@@ -127,6 +127,14 @@ int sbd_disort_batch_device(sbd_handle *h, const sbd_dims *dims,
 /* Block until everything enqueued on the handle's stream has finished. */
 int sbd_synchronize(sbd_handle *h);
 
+/* Levels at which intensities (uu) are wanted by the following batched calls on
+ * this handle: indices into the NT output levels, n = 0 restores "all levels".
+ * SBDART consumes the radiances of one or two levels only (ntop / nbot,
+ * drt.f:1008-1016, :1143-1151) while DISORT's USRINT (disort.f:4355) integrates
+ * the source function for every level; unselected levels of uu are returned as
+ * zeros.  Fluxes are not affected. */
+int sbd_set_radiance_levels(sbd_handle *h, const int32_t *levels, int32_t n);
+
 /* cudaStream_t of the handle (as void*), for event timing by the caller. */
 void *sbd_stream(sbd_handle *h);
 

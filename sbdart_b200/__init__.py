@@ -31,6 +31,7 @@ EXPORTS = (
     "sbd_synchronize", "sbd_stream", "sbd_kernel_launches", "sbd_quadrature",
     "sbd_status_string", "sbd_abi_version", "disort_", "sbd_disort_last_status",
     "sbd_measure_fp64_peak", "sbd_optics_upload_tables", "sbd_spectrum_run",
+    "sbd_set_radiance_levels",
 )
 
 
@@ -96,6 +97,8 @@ def lib():
     L.sbd_status_string.restype = C.c_char_p
     L.sbd_status_string.argtypes = [C.c_int]
     L.sbd_abi_version.restype = C.c_int
+    L.sbd_set_radiance_levels.restype = C.c_int
+    L.sbd_set_radiance_levels.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
     L.sbd_measure_fp64_peak.restype = C.c_int
     L.sbd_measure_fp64_peak.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
     L.sbd_disort_last_status.restype = C.c_int
@@ -173,8 +176,17 @@ class Solver:
             raise SbdError(rc, "sbd_synchronize")
 
     # -- host-buffer call: the reference-facing path (H2D + kernel + D2H) ----
+    def set_radiance_levels(self, levels=None):
+        """Restrict the intensities (uu) of the following calls to these output levels
+        (None / empty: all levels).  SBDART prints one or two levels only."""
+        lv = None if levels is None else np.ascontiguousarray(levels, dtype=np.int32)
+        rc = lib().sbd_set_radiance_levels(self._h, None if lv is None or lv.size == 0 else lv.ctypes.data,
+                                           0 if lv is None else int(lv.size))
+        if rc:
+            raise SbdError(rc, "sbd_set_radiance_levels")
+
     def disort_batch(self, dtauc, ssalb, pmom, bins, *, nstr, temper=None, utau=None,
-                     umu=None, phi=None, out=None):
+                     umu=None, phi=None, out=None, uu_levels=None):
         """Batched DISORT on host arrays.
 
         dtauc, ssalb [B][L]; pmom [B][L][nmom+1]; bins = make_bins(...);
@@ -209,10 +221,16 @@ class Solver:
             if d.numu > 0:
                 out["uu"] = np.empty((B, d.nphi, NT, d.numu))
         p = lambda a: None if a is None else a.ctypes.data  # noqa: E731
-        rc = lib().sbd_disort_batch(
-            self._h, C.byref(d), p(dtauc), p(ssalb), p(pmom), p(bins), p(tp), p(ut), p(um),
-            p(ph), p(out["rfldir"]), p(out["rfldn"]), p(out["flup"]), p(out["dfdt"]),
-            p(out["uavg"]), p(out.get("uu")), p(out["status"]))
+        if uu_levels is not None:
+            self.set_radiance_levels(uu_levels)
+        try:
+            rc = lib().sbd_disort_batch(
+                self._h, C.byref(d), p(dtauc), p(ssalb), p(pmom), p(bins), p(tp), p(ut), p(um),
+                p(ph), p(out["rfldir"]), p(out["rfldn"]), p(out["flup"]), p(out["dfdt"]),
+                p(out["uavg"]), p(out.get("uu")), p(out["status"]))
+        finally:
+            if uu_levels is not None:
+                self.set_radiance_levels(None)
         if rc:
             raise SbdError(rc, "sbd_disort_batch")
         return out

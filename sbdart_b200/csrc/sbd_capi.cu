@@ -173,6 +173,19 @@ extern "C" int sbd_synchronize(sbd_handle *h)
     return cudaStreamSynchronize(h->stream) == cudaSuccess ? SBD_SUCCESS : SBD_ERR_CUDA;
 }
 
+extern "C" int sbd_set_radiance_levels(sbd_handle *h, const int32_t *levels, int32_t n)
+{
+    if (!h || n < 0 || (n > 0 && !levels)) return SBD_ERR_ARG;
+    if (n == 0) { h->uu_mask[0] = h->uu_mask[1] = ~0ull; return SBD_SUCCESS; }
+    unsigned long long m[2] = { 0, 0 };
+    for (int i = 0; i < n; i++) {
+        if (levels[i] < 0 || levels[i] >= 128) return SBD_ERR_ARG;
+        m[levels[i] >> 6] |= 1ull << (levels[i] & 63);
+    }
+    h->uu_mask[0] = m[0]; h->uu_mask[1] = m[1];
+    return SBD_SUCCESS;
+}
+
 extern "C" void *sbd_stream(sbd_handle *h) { return h ? (void *)h->stream : nullptr; }
 
 extern "C" int64_t sbd_kernel_launches(const sbd_handle *h) { return h ? h->launches : 0; }
@@ -289,6 +302,7 @@ extern "C" int sbd_disort_batch_device(sbd_handle *h, const sbd_dims *dims, cons
     a.nslots = grid * warps;
     a.slot_stride = slot;
     a.nmodes = 1;
+    a.uu_mask[0] = h->uu_mask[0]; a.uu_mask[1] = h->uu_mask[1];
     SbdDevBuf &scr = h->scratch_set ? h->scratch2 : h->scratch;
     SbdDevBuf &ctr = h->scratch_set ? h->counter2 : h->counter;
     if (scr.reserve(a.slot_stride * (size_t)a.nslots * 8) != cudaSuccess) return SBD_ERR_CUDA;

@@ -1098,6 +1098,12 @@ disort_generic_kernel(const LaunchArgs a)
             double azerr = 0.0;
             for (int e = lane; e < NT * NU; e += 32) {
                 const int lu = e / NU, iu = e - lu * NU;
+                if (lu < 128 && !((a.uu_mask[lu >> 6] >> (lu & 63)) & 1ull)) {
+                    // level not wanted (sbd_set_radiance_levels): zeros, no source integration
+                    if (mazim == 0)
+                        for (int j = 0; j < a.d.nphi; j++) o_uu[((size_t)j * NT + lu) * NU + iu] = 0.0;
+                    continue;
+                }
                 const int lyu = w.layru[lu];
                 double ut = a.d.ntau > 0 ? a.utau[(size_t)src * NT + lu] : w.tauc[lu];
                 if (a.d.ntau > 0 && fabs(ut - w.tauc[L]) <= 1.e-4) ut = w.tauc[L];

@@ -45,7 +45,8 @@ struct sbd_handle {
     SbdDevBuf scratch2, counter2;
     cudaStream_t stream2 = nullptr;
     cudaEvent_t ev_misc = nullptr;
-    int scratch_set = 0;                       // set used by the next device-level launch
+    int scratch_set = 0;
+    unsigned long long uu_mask[2] = { ~0ull, ~0ull };   // levels at which uu is wanted                       // set used by the next device-level launch
     // staging for the host-pointer API
     SbdDevBuf d_dtauc, d_ssalb, d_pmom, d_bins, d_temper, d_utau, d_out, d_uu, d_status;
     // whole-spectrum path (sbd_spectrum.cu)

@@ -31,6 +31,7 @@ struct LaunchArgs {
     int *work_counter;    // dynamic bin scheduler
     const int32_t *binmap; // optional: bin b reads its inputs from slot binmap[b]
     const int32_t *nbins_dev; // optional: number of bins lives on the device (spectrum path)
+    unsigned long long uu_mask[2]; // bit lu: intensities wanted at output level lu
 };
 
 // Per-layer record kept in scratch between the downward elimination sweep

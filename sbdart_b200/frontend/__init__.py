@@ -1192,6 +1192,13 @@ class Sbdart:
                  nstr=self.p["nstr"], group=g("il"))
         if self.radcalc:
             d["umu"], d["phi"] = self.umu, self.phi
+            # output levels whose intensities the records consume (drt.f:1008-1016,
+            # :1143-1151): iout 5/20 the top level, 6/21 the bottom, 23 both
+            iout = self.p["iout"]
+            lv = {5: [self.ntop - 1], 20: [self.ntop - 1], 6: [self.nbot - 1], 21: [self.nbot - 1],
+                  23: [self.ntop - 1, self.nbot - 1]}.get(iout)
+            if lv is not None:
+                d["uu_levels"] = sorted(set(lv))
         return d
 
     # ---- accumulation and records (stdout0/1/2, drt.f:892-1165)
@@ -1218,7 +1225,7 @@ class Sbdart:
             # for the retry logic (rare: one NSTR-dependent angle)
             return self.run(lambda b: solver.disort_batch(
                 b["dtauc"], b["ssalb"], b["pmom"], b["bins"], nstr=b["nstr"], temper=b["temper"],
-                umu=b.get("umu"), phi=b.get("phi")))
+                umu=b.get("umu"), phi=b.get("phi"), uu_levels=b.get("uu_levels")))
         return self.records(rows, res)
 
     def records(self, rows, res):

@@ -166,11 +166,22 @@ def run_spectrum(run: Sbdart, solver, want_inputs=False):
     z, pr, t = (np.ascontiguousarray(a, dtype=float) for a in (run.z, run.pr, run.t))
     uua = np.ascontiguousarray(run.uu, dtype=float)
     ptr = lambda a: None if a is None else a.ctypes.data  # noqa: E731
-    rc = L.sbd_spectrum_run(
-        solver._h, C.byref(P), ptr(z), ptr(pr), ptr(t), ptr(uua), ptr(ce) if len(ce) else None,
-        ptr(wlalb), ptr(alb), ptr(wlsun), ptr(sun), numu, ptr(umu), nphi, ptr(phi), ptr(nk), ptr(wl),
-        ptr(dwl), ptr(wt), C.byref(nbins), ptr(rfldir), ptr(rfldn), ptr(flup), ptr(uu), ptr(status),
-        C.byref(io) if io is not None else None)
+    # intensities only at the levels the records consume (see Sbdart.batch)
+    lv = None
+    if run.radcalc:
+        lv = {5: [run.ntop - 1], 20: [run.ntop - 1], 6: [run.nbot - 1], 21: [run.nbot - 1],
+              23: [run.ntop - 1, run.nbot - 1]}.get(run.p["iout"])
+    if lv is not None:
+        solver.set_radiance_levels(sorted(set(lv)))
+    try:
+        rc = L.sbd_spectrum_run(
+            solver._h, C.byref(P), ptr(z), ptr(pr), ptr(t), ptr(uua), ptr(ce) if len(ce) else None,
+            ptr(wlalb), ptr(alb), ptr(wlsun), ptr(sun), numu, ptr(umu), nphi, ptr(phi), ptr(nk), ptr(wl),
+            ptr(dwl), ptr(wt), C.byref(nbins), ptr(rfldir), ptr(rfldn), ptr(flup), ptr(uu), ptr(status),
+            C.byref(io) if io is not None else None)
+    finally:
+        if lv is not None:
+            solver.set_radiance_levels(None)
     if rc:
         raise SbdError(rc, "sbd_spectrum_run")
     B = nbins.value

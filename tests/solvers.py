@@ -29,5 +29,5 @@ def solve_oracle(b, nthreads=8):
 def make_solve_cuda(solver):
     def solve(b):
         return solver.disort_batch(b["dtauc"], b["ssalb"], b["pmom"], b["bins"], nstr=b["nstr"],
-                                   temper=b["temper"], umu=b.get("umu"), phi=b.get("phi"))
+                                   temper=b["temper"], umu=b.get("umu"), phi=b.get("phi"), uu_levels=b.get("uu_levels"))
     return solve

@@ -232,3 +232,23 @@ def test_deep_atmosphere_65_layers(solver, nstr):
     ref = oracle_flux(w)
     assert (ref["status"] == 0).all()
     assert_close(got, ref, rtol=1e-7, atol_scale=2e-9)
+
+
+def test_radiance_level_selection(solver):
+    """sbd_set_radiance_levels: intensities only at the levels SBDART's records consume;
+    the selected levels are bit-identical to the full computation, the others are zero,
+    fluxes are untouched."""
+    w = workloads.retrieval_batch(24, nstr=8, nlyr=12, ncols=4, seed=21)
+    w["bins"]["phi0"] = 20.0
+    umu = np.array([-0.9, -0.4, -0.1, 0.2, 0.7, 1.0])
+    phi = np.array([0.0, 45.0])
+    full = solver.disort_batch(w["dtauc"], w["ssalb"], w["pmom"], w["bins"], nstr=8, umu=umu, phi=phi)
+    sel = solver.disort_batch(w["dtauc"], w["ssalb"], w["pmom"], w["bins"], nstr=8, umu=umu, phi=phi,
+                              uu_levels=[0, 12])
+    assert (sel["status"] == 0).all()
+    assert np.array_equal(sel["uu"][:, :, [0, 12], :], full["uu"][:, :, [0, 12], :])
+    assert (sel["uu"][:, :, 1:12, :] == 0.0).all()
+    for k in KEYS:
+        assert np.array_equal(sel[k], full[k]), k
+    again = solver.disort_batch(w["dtauc"], w["ssalb"], w["pmom"], w["bins"], nstr=8, umu=umu, phi=phi)
+    assert np.array_equal(again["uu"], full["uu"])          # the selection does not stick

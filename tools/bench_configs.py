@@ -82,8 +82,10 @@ def main():
     w = workloads.mls_shortwave(nstr=8, wlinf=4.0, wlsup=20.0, wlinc=0.05)
     umu = np.cos(np.deg2rad(np.linspace(5.0, 85.0, 10)))[::-1].copy()
     run("C3 nstr8 L33 thermal flux", tile(w, 64 // q), s)
-    run("C3 nstr8 L33 thermal radiance 10 zenith x 1 azimuth", tile(w, 64 // q), s,
+    run("C3 nstr8 L33 thermal radiance 10 zenith x 1 azimuth, all 34 levels", tile(w, 64 // q), s,
         umu=np.sort(umu), phi=np.array([0.0]))
+    run("C3 nstr8 L33 thermal radiance 10 zenith x 1 azimuth, top level only (what iout=20 prints)",
+        tile(w, 64 // q), s, umu=np.sort(umu), phi=np.array([0.0]), uu_levels=[0])
     # C4: NSTR=32, 65 layers (generic kernel)
     w = workloads.mls_shortwave(nstr=32, nlyr=65, wlinf=0.25, wlsup=4.0, wlinc=0.02, cloud_tau=10.0)
     run("C4 nstr32 L65 cloud", tile(w, 16 // min(q, 4)), s, nsample=32)
