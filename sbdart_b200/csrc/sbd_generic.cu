@@ -710,6 +710,7 @@ __device__ double usrint_one(const BinCtx &c, const WarpShared &w, const LayerLa
 // ---------------------------------------------------------------------------
 extern __shared__ double smem_dyn[];
 
+template <bool SYNC>
 __global__ void __launch_bounds__(128, 4)
 disort_generic_kernel(const LaunchArgs a)
 {
@@ -748,9 +749,14 @@ disort_generic_kernel(const LaunchArgs a)
         int bin = 0;
         if (lane == 0) bin = atomicAdd(a.work_counter, 1);
         bin = __shfl_sync(FULLMASK, bin, 0);
-        if (bin >= a.d.nbins) break;
+        // The warps of a CTA move through bins, azimuth modes and layers together
+        // (CTA barriers with per-warp "active" flags): they then execute the same code
+        // at the same time and share its instruction-cache lines -- free-running warps
+        // of this 150 KB kernel spend 40 % of their time waiting for instructions.
+        const bool have = bin < a.d.nbins;
+        if (!(SYNC ? __syncthreads_or(have) : (int)have)) break;
 
-        const int src = a.binmap ? a.binmap[bin] : bin;     // input slot of this bin
+        const int src = !have ? 0 : (a.binmap ? a.binmap[bin] : bin);     // input slot of this bin
         const sbd_bin bp = a.bins[src];
         BinCtx c;
         c.N = N; c.n = n; c.L = L; c.NT = NT; c.mazim = 0; c.delm0 = 1.0;
@@ -760,13 +766,13 @@ disort_generic_kernel(const LaunchArgs a)
         c.ssalb = a.ssalb + (size_t)src * L;
         c.pmom = a.pmom + (size_t)src * L * ldp;
         c.ldp = ldp;
-        double *o_rfldir = a.rfldir ? a.rfldir + (size_t)bin * NT : nullptr;
-        double *o_rfldn = a.rfldn ? a.rfldn + (size_t)bin * NT : nullptr;
-        double *o_flup = a.flup ? a.flup + (size_t)bin * NT : nullptr;
-        double *o_dfdt = a.dfdt ? a.dfdt + (size_t)bin * NT : nullptr;
-        double *o_uavg = a.uavg ? a.uavg + (size_t)bin * NT : nullptr;
+        double *o_rfldir = (a.rfldir && have) ? a.rfldir + (size_t)bin * NT : nullptr;
+        double *o_rfldn = (a.rfldn && have) ? a.rfldn + (size_t)bin * NT : nullptr;
+        double *o_flup = (a.flup && have) ? a.flup + (size_t)bin * NT : nullptr;
+        double *o_dfdt = (a.dfdt && have) ? a.dfdt + (size_t)bin * NT : nullptr;
+        double *o_uavg = (a.uavg && have) ? a.uavg + (size_t)bin * NT : nullptr;
 
-        int status = 0;
+        int status = have ? 0 : -1;
         // ---- input checks (subset of CHEKIN, disort.f:4920-5155) ----------
         {
             int badl = 0;
@@ -848,7 +854,7 @@ disort_generic_kernel(const LaunchArgs a)
             if (o_dfdt) o_dfdt[lu] = 0.0;
             if (o_uavg) o_uavg[lu] = 0.0;
         }
-        double *o_uu = (NU > 0 && a.uu) ? a.uu + (size_t)bin * a.d.nphi * NT * NU : nullptr;
+        double *o_uu = (NU > 0 && a.uu && have) ? a.uu + (size_t)bin * a.d.nphi * NT * NU : nullptr;
         if (o_uu)
             for (int e = lane; e < a.d.nphi * NT * NU; e += 32) o_uu[e] = 0.0;
 
@@ -866,7 +872,9 @@ disort_generic_kernel(const LaunchArgs a)
         const double *ylm_smem = cs.ylm;
         int kconv = 0;
 
-      for (int mazim = 0; mazim <= naz && !status; mazim++) {
+      for (int mazim = 0; ; mazim++) {
+        const bool mact = !status && mazim <= naz;       // this warp still has a mode to do
+        if (!(SYNC ? __syncthreads_or(mact) : (int)mact)) break;
         c.mazim = mazim;
         c.delm0 = (mazim == 0) ? 1.0 : 0.0;
         cs.ylm = (mazim == 0) ? ylm_smem : a.ylmc + (size_t)mazim * N * n;
@@ -880,8 +888,8 @@ disort_generic_kernel(const LaunchArgs a)
         double bnd_up = 0.0;
 
         // ================= downward sweep ================================
-        if (!status) status = solve_layer(c, cs, w, 0, cur, xr0c, xr1c, lane);
-        if (!status) {
+        if (mact) status = solve_layer(c, cs, w, 0, cur, xr0c, xr1c, lane);
+        if (mact && !status) {
             store_layer(ll, scr, w, cur, xr0c, xr1c, lane);
             // top boundary rows (disort.f:2887-2915, :3547-3550)
             for (int e = lane; e < n * C; e += 32) {
@@ -899,10 +907,13 @@ disort_generic_kernel(const LaunchArgs a)
                 w.W[r * C + j] = v;
             }
         }
-        for (int lc = 0; lc < ncut - 1 && !status; lc++) {
+        for (int lc = 0; ; lc++) {
+            const bool lact = mact && !status && lc < ncut - 1;
+            if (!(SYNC ? __syncthreads_or(lact) : (int)lact)) break;
+            if (!lact) continue;
             const int nxt = cur ^ 1;
             status = solve_layer(c, cs, w, lc + 1, nxt, xr0n, xr1n, lane);
-            if (status) break;
+            if (status) continue;
             store_layer(ll, scr + (size_t)(lc + 1) * ll.stride, w, nxt, xr0n, xr1n, lane);
             // interface rows between layer lc and lc+1 (disort.f:2846-2882, :3585-3593)
             const double tb = w.taucpr[lc + 1];
@@ -925,7 +936,7 @@ disort_generic_kernel(const LaunchArgs a)
             }
             __syncwarp();
             status = eliminate(w.W, R, C, N, lane);
-            if (status) break;
+            if (status) continue;
             // keep the N pivot rows, carry the n remaining rows
             double *U = scr + (size_t)lc * ll.stride + ll.off_u;
             for (int e = lane; e < N * C; e += 32) U[e] = w.W[e];
@@ -944,7 +955,7 @@ disort_generic_kernel(const LaunchArgs a)
         }
 
         // ================= bottom boundary + last layer ====================
-        if (!status) {
+        if (mact && !status) {
             const int lc = ncut - 1;
             const double tb = w.taucpr[ncut];
             const double eb = (c.fbeam > 0.0) ? exp(-tb / c.umu0) : 0.0;
@@ -987,7 +998,7 @@ disort_generic_kernel(const LaunchArgs a)
         }
 
         // ================= upward sweep: back substitution + fluxes ========
-        if (!status) {
+        if (mact && !status) {
             for (int lc = ncut - 1; lc >= 0; lc--) {
                 if (lc < ncut - 1) {
                     const double *U = scr + (size_t)lc * ll.stride + ll.off_u;
@@ -1092,7 +1103,7 @@ disort_generic_kernel(const LaunchArgs a)
         }
 
         // ================= intensities at the user angles ====================
-        if (!status && NU > 0) {
+        if (mact && !status && NU > 0) {
             __threadfence_block();
             const double rpd = kPiRef / 180.0;
             double azerr = 0.0;
@@ -1134,12 +1145,12 @@ disort_generic_kernel(const LaunchArgs a)
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) azerr = fmax(azerr, __shfl_xor_sync(FULLMASK, azerr, o));
                 if (azerr <= bp.accur) kconv++;
-                if (kconv >= 2) break;       // disort.f:821-823
+                if (kconv >= 2) naz = mazim;       // converged: no further modes (disort.f:821-823)
             }
             __syncwarp();
         }
       }   // azimuth modes
-        if (lane == 0) a.status[bin] = status;
+        if (lane == 0 && have) a.status[bin] = status;
         __syncwarp();
     }
 }
@@ -1148,10 +1159,14 @@ cudaError_t launch_generic(const LaunchArgs &a, int warps, int grid, cudaStream_
 {
     size_t smem = generic_smem_bytes(a.d.nstr, a.d.nlyr,
                                      a.d.ntau > 0 ? a.d.ntau : a.d.nlyr + 1, warps);
-    cudaError_t e = cudaFuncSetAttribute(disort_generic_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    // CTA-synchronous loops pay off when several CTAs share an SM (small NSTR: +27 % on
+    // the NSTR=8 radiance set); at NSTR=32 one 4-warp CTA fills the SM's shared memory
+    // and the barriers only add idle time (-10 %)
+    const bool sync = a.d.nstr <= 20;
+    auto kern = sync ? disort_generic_kernel<true> : disort_generic_kernel<false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    disort_generic_kernel<<<grid, warps * 32, smem, st>>>(a);
+    kern<<<grid, warps * 32, smem, st>>>(a);
     return cudaGetLastError();
 }
 
