@@ -545,7 +545,8 @@ __device__ __forceinline__ void stage_rows(double *stg, const double *recA, bool
 // lanes' column slices; cgj = column group that owns it.  The pivot row is
 // written to `urow` (global scratch) on the way.  Returns true when no usable
 // pivot exists.
-template <int n>
+// W = slice entries that can still be non-zero: LC, fewer once the slices have slid.
+template <int n, int W>
 __device__ __forceinline__ bool elim_step(double (&w)[FastLayout<n>::KS][FastLayout<n>::LC],
                                           double (&rhs)[FastLayout<n>::KS], unsigned &act,
                                           double *uslice /* urow + cg*LC */, int cgj, int rg, int cg)
@@ -581,26 +582,26 @@ __device__ __forceinline__ bool elim_step(double (&w)[FastLayout<n>::KS][FastLay
 #pragma unroll
     for (int k = 0; k < KS; k++) m[k] = colj[k] * rp;
     // this lane's column slice of the pivot row: one shuffle serves all 4 column groups
-    double p[LC], pr;
+    double p[W], pr;
     const int src = (rgp << 2) | cg;
     if (KS == 1 || kp == 0) {
 #pragma unroll
-        for (int l = 0; l < LC; l++) p[l] = __shfl_sync(FULLMASK, w[0][l], src);
+        for (int l = 0; l < W; l++) p[l] = __shfl_sync(FULLMASK, w[0][l], src);
         pr = __shfl_sync(FULLMASK, rhs[0], src);
     } else if (KS == 2 || kp == 1) {
 #pragma unroll
-        for (int l = 0; l < LC; l++) p[l] = __shfl_sync(FULLMASK, w[KS > 1 ? 1 : 0][l], src);
+        for (int l = 0; l < W; l++) p[l] = __shfl_sync(FULLMASK, w[KS > 1 ? 1 : 0][l], src);
         pr = __shfl_sync(FULLMASK, rhs[KS > 1 ? 1 : 0], src);
     } else {
 #pragma unroll
-        for (int l = 0; l < LC; l++) p[l] = __shfl_sync(FULLMASK, w[KS > 2 ? 2 : 0][l], src);
+        for (int l = 0; l < W; l++) p[l] = __shfl_sync(FULLMASK, w[KS > 2 ? 2 : 0][l], src);
         pr = __shfl_sync(FULLMASK, rhs[KS > 2 ? 2 : 0], src);
     }
     act &= ~(1u << (kp * 8 + rgp));
     // the pivot row goes to scratch (row group 0 holds a copy of every slice)
     if (rg == 0) {
 #pragma unroll
-        for (int l2 = 0; l2 < LC / 2; l2++)
+        for (int l2 = 0; l2 < W / 2; l2++)
             reinterpret_cast<double2 *>(uslice)[l2] = make_double2(p[2 * l2], p[2 * l2 + 1]);
         if (cg == 0) uslice[4 * LC] = pr;
     }
@@ -613,14 +614,14 @@ __device__ __forceinline__ bool elim_step(double (&w)[FastLayout<n>::KS][FastLay
 #pragma unroll
         for (int k = 0; k < KS; k++) {
 #pragma unroll
-            for (int l = 0; l + 1 < LC; l++) w[k][l] = fma(m[k], p[l + 1], w[k][l + 1]);
-            w[k][LC - 1] = 0.0;
+            for (int l = 0; l + 1 < W; l++) w[k][l] = fma(m[k], p[l + 1], w[k][l + 1]);
+            w[k][W - 1] = 0.0;
         }
     } else {
 #pragma unroll
         for (int k = 0; k < KS; k++) {
 #pragma unroll
-            for (int l = 0; l < LC; l++) w[k][l] = fma(m[k], p[l], w[k][l]);
+            for (int l = 0; l < W; l++) w[k][l] = fma(m[k], p[l], w[k][l]);
         }
     }
     return false;
@@ -921,8 +922,13 @@ disort_fast_kernel(const LaunchArgs a)
                 // pivot row j lands in scratch as [cg][l - j/4] slices, then the right-hand side
                 double *uslice = ublk + (size_t)lc * FL::ublk + cg * LC;
                 bool sing = false;
+                // second half of the layer's columns: the slices have slid LH/2 times, their
+                // last LH/2 entries are zero in every live row -- a narrower loop body
+                constexpr int W2 = ((LC - FL::LH / 2) % 2 == 0 && FL::LH >= 2) ? LC - FL::LH / 2 : LC;
 #pragma unroll 1
-                for (int j = 0; j < N && !sing; j++, uslice += US) sing = elim_step<n>(w, rhs, act, uslice, j & 3, rg, cg);
+                for (int j = 0; j < N / 2 && !sing; j++, uslice += US) sing = elim_step<n, LC>(w, rhs, act, uslice, j & 3, rg, cg);
+#pragma unroll 1
+                for (int j = N / 2; j < N && !sing; j++, uslice += US) sing = elim_step<n, W2>(w, rhs, act, uslice, j & 3, rg, cg);
                 if (sing) { status = SBD_BIN_SINGULAR; break; }
                 cp_async_wait_all();       // record lc+2 has landed
                 __syncwarp();
