@@ -963,25 +963,28 @@ disort_fast_kernel(const LaunchArgs a)
                 __syncwarp();
                 const double *ubuf = tsm_base + buf * kSlot;
                 const double *fr = ubuf + FL::ublk;
-                double acc = 0.0, diag = 1.0;
-                double ur[N];      // row `lane` of the upper triangle (entries left of the diagonal unused)
+                double acc, dinv;
+                double ur[N];      // row `lane` of the upper triangle, pre-divided by the diagonal
+                                   // (entries left of the diagonal unused)
                 {
                     // stored row `lane`: window column c sits at (c & 3) * LC + (c >> 2) - lane / 4
                     // (the slices had slid lane/4 times when the row became a pivot)
                     const int row = lane < N ? lane : 0;
                     const double *u = ubuf + row * US - (row >> 2);
-                    acc = ubuf[row * US + 4 * LC];
+                    dinv = fast_rcp(u[(row & 3) * LC + (row >> 2)]);
+                    // rhs - U[:, N:2N] x_below: four partial sums (a 16-long FMA chain otherwise)
+                    double a4[4] = { ubuf[row * US + 4 * LC], 0.0, 0.0, 0.0 };
 #pragma unroll
                     for (int j = 0; j < N; j++)
-                        acc = fma(-u[((N + j) & 3) * LC + ((N + j) >> 2)], xs[j], acc);
+                        a4[j & 3] = fma(-u[((N + j) & 3) * LC + ((N + j) >> 2)], xs[j], a4[j & 3]);
+                    acc = ((a4[0] + a4[1]) + (a4[2] + a4[3])) * dinv;
 #pragma unroll
-                    for (int c = 1; c < N; c++) ur[c] = u[(c & 3) * LC + (c >> 2)];
-                    diag = u[(row & 3) * LC + (row >> 2)];
+                    for (int c = 1; c < N; c++) ur[c] = u[(c & 3) * LC + (c >> 2)] * dinv;
                 }
-                const double dinv = fast_rcp(diag);
+                // x_c = acc of lane c; the chain per step is one shuffle + one FMA
 #pragma unroll
                 for (int c = N - 1; c >= 0; c--) {
-                    const double xc = __shfl_sync(FULLMASK, acc * dinv, c);
+                    const double xc = __shfl_sync(FULLMASK, acc, c);
                     xs[c] = xc;
                     if (lane < c) acc = fma(-ur[c], xc, acc);
                 }
@@ -1025,14 +1028,19 @@ disort_fast_kernel(const LaunchArgs a)
                         }
                         if (lane < 3) {
                             const double2 *cu2 = reinterpret_cast<const double2 *>(fr + FL::f_cu + lane * N);
-                            double d0 = 0.0, d1 = 0.0;
+                            double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
 #pragma unroll
-                            for (int j2 = 0; j2 < n; j2++) {
+                            for (int j2 = 0; j2 < n; j2 += 2) {
                                 const double2 c = cu2[j2];
                                 d0 = fma(c.x, xe[2 * j2], d0);
                                 d1 = fma(c.y, xe[2 * j2 + 1], d1);
+                                if (j2 + 1 < n) {
+                                    const double2 e2 = cu2[j2 + 1];
+                                    d2 = fma(e2.x, xe[2 * j2 + 2], d2);
+                                    d3 = fma(e2.y, xe[2 * j2 + 3], d3);
+                                }
                             }
-                            dot = d0 + d1;
+                            dot = (d0 + d1) + (d2 + d3);
                         }
                     } else {     // level inside a layer (USRTAU): one mode per lane
                         double xl[N];
