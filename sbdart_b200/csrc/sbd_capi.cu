@@ -136,7 +136,7 @@ extern "C" int sbd_create(sbd_handle **out, int device)
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return SBD_ERR_CUDA; }
     if (cudaStreamCreateWithFlags(&h->copy_in, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&h->copy_out, cudaStreamNonBlocking) != cudaSuccess) { delete h; return SBD_ERR_CUDA; }
-    for (int i = 0; i < 8; i++) {
+    for (int i = 0; i < sbd_handle::kMaxChunks; i++) {
         cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&h->ev_k[i], cudaEventDisableTiming);
     }
@@ -158,7 +158,7 @@ extern "C" void sbd_destroy(sbd_handle *h)
                        &h->d_pmom, &h->d_bins, &h->d_temper, &h->d_utau, &h->d_out, &h->d_uu,
                        &h->d_status, &h->opt_tables, &h->opt_atm, &h->opt_misc, &h->opt_map };
     for (SbdDevBuf *b : bufs) b->release();
-    for (int i = 0; i < 8; i++) { cudaEventDestroy(h->ev_in[i]); cudaEventDestroy(h->ev_k[i]); }
+    for (int i = 0; i < sbd_handle::kMaxChunks; i++) { cudaEventDestroy(h->ev_in[i]); cudaEventDestroy(h->ev_k[i]); }
     cudaEventDestroy(h->ev_misc);
     cudaStreamDestroy(h->stream2);
     cudaStreamDestroy(h->copy_in);
@@ -367,8 +367,8 @@ extern "C" int sbd_disort_batch(sbd_handle *h, const sbd_dims *dims, const doubl
     // kernel of chunk c (copy-in, copy-out and two alternating compute streams, events
     // between them).  Only the first copy in and the last copy out are exposed, so the
     // chunks ramp up at the front (4096, 8192, 16384 bins) and down at the back
-    // (8192, 4096); the middle is cut into at most 3 equal parts.
-    size_t cuts[9];
+    // (8192, 4096); the middle is cut into equal parts of at most 32768 bins (27 at most).
+    size_t cuts[sbd_handle::kMaxChunks + 1];
     int nchunk = 0;
     cuts[0] = 0;
     {
@@ -382,7 +382,7 @@ extern "C" int sbd_disort_batch(sbd_handle *h, const sbd_dims *dims, const doubl
         const size_t rest = hi - lo;
         int parts = (int)((rest + 32767) / 32768);
         if (parts < 1) parts = 1;
-        if (parts > 3) parts = 3;
+        if (parts > sbd_handle::kMaxChunks - 5) parts = sbd_handle::kMaxChunks - 5;
         for (int i = 1; i <= parts; i++) cuts[++nchunk] = lo + rest * i / parts;
         // back ramp: the larger chunk first
         if (nb_back == 2) { cuts[nchunk + 1] = hi + back[0]; nchunk++; }

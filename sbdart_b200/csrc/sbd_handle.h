@@ -33,7 +33,8 @@ struct sbd_handle {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t copy_in = nullptr, copy_out = nullptr;   // H2D / D2H overlap in the host-buffer call
-    cudaEvent_t ev_in[8] = {}, ev_k[8] = {};
+    static constexpr int kMaxChunks = 32;
+    cudaEvent_t ev_in[kMaxChunks] = {}, ev_k[kMaxChunks] = {};
     int sm_count = 0;
     size_t smem_optin = 0;
     int64_t launches = 0;
