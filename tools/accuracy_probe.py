@@ -7,7 +7,11 @@ import bench
 import sbdart_b200 as sb
 from oracle import oracle
 
-w = bench.build_workload(1)
+if len(sys.argv) > 2 and sys.argv[2] == "smoke":
+    from sbdart_b200 import workloads
+    w = workloads.mls_shortwave(nstr=16, wlinc=0.25)        # the workload of __graft_entry__.smoke()
+else:
+    w = bench.build_workload(1)
 idx = np.arange(0, w["dtauc"].shape[0], int(sys.argv[1]) if len(sys.argv) > 1 else 7)
 b = w["bins"][idx]
 s = sb.Solver(0)

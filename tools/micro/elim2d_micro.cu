@@ -66,7 +66,16 @@ __device__ __forceinline__ bool step_var(double (&w)[FL::KS][FL::LC], double (&r
         pr = __shfl_sync(FULLMASK, rhs[2], src);
     }
     act &= ~(1u << (kp * 8 + rgp));
-    if (VAR & 64) {            // streaming stores
+    if (!(VAR & 512)) {
+    if (VAR & 256) {           // transposed slice layout: one STG.128 writes 64 contiguous bytes
+        if (rg == 0) {
+            double *rowbase = uslice - cg * LC;
+#pragma unroll
+            for (int l2 = 0; l2 < W / 2; l2++)
+                reinterpret_cast<double2 *>(rowbase + l2 * 8)[cg] = make_double2(p[2 * l2], p[2 * l2 + 1]);
+            if (cg == 0) rowbase[4 * LC] = pr;
+        }
+    } else if (VAR & 64) {            // streaming stores
         if (rg == 0) {
 #pragma unroll
             for (int l2 = 0; l2 < W / 2; l2++)
@@ -86,6 +95,7 @@ __device__ __forceinline__ bool step_var(double (&w)[FL::KS][FL::LC], double (&r
             reinterpret_cast<double2 *>(uslice)[l2] = make_double2(p[2 * l2], p[2 * l2 + 1]);
         if (cg == 0) uslice[4 * LC] = pr;
     }
+    }
 #pragma unroll
     for (int k = 0; k < KS; k++) rhs[k] = fma(m[k], pr, rhs[k]);
     if (cgj == 3) {
@@ -101,6 +111,12 @@ __device__ __forceinline__ bool step_var(double (&w)[FL::KS][FL::LC], double (&r
 #pragma unroll
             for (int l = 0; l < W; l++) w[k][l] = fma(m[k], p[l], w[k][l]);
         }
+    }
+    if ((VAR & 512) && rg == 0) {     // pivot row stored after the update stream
+#pragma unroll
+        for (int l2 = 0; l2 < W / 2; l2++)
+            reinterpret_cast<double2 *>(uslice)[l2] = make_double2(p[2 * l2], p[2 * l2 + 1]);
+        if (cg == 0) uslice[4 * LC] = pr;
     }
     return false;
 }
@@ -186,7 +202,7 @@ void run(int c)
 int main()
 {
     for (int c = 4; c <= 4; c *= 2) {
-        run<0>(c); run<64>(c); run<128>(c); run<2>(c);
+        run<0>(c); run<512>(c); run<2>(c);
     }
     return 0;
 }
