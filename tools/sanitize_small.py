@@ -1,0 +1,21 @@
+"""Tiny mixed run (flux NSTR 4/8/16 incl. thermal and truncated bins, USRTAU, radiances) for compute-sanitizer."""
+import sys; sys.path.insert(0, '.')
+import numpy as np
+import sbdart_b200 as sb
+from sbdart_b200 import workloads
+s = sb.Solver(0)
+for nstr in (4, 8, 16):
+    w = workloads.retrieval_batch(40, nstr=nstr, nlyr=33, ncols=4, seed=nstr)
+    o = s.disort_batch(w["dtauc"], w["ssalb"], w["pmom"], w["bins"], nstr=nstr)
+    print(nstr, "retrieval bad", int((o["status"] != 0).sum()))
+w = workloads.mls_shortwave(nstr=16, wlinc=0.25)
+o = s.disort_batch(w["dtauc"], w["ssalb"], w["pmom"], w["bins"], nstr=16, temper=w["temper"])
+print("thermal bad", int((o["status"] != 0).sum()))
+tot = w["dtauc"].sum(axis=1)
+utau = np.stack([0 * tot, 0.3 * tot, tot], axis=1)
+o = s.disort_batch(w["dtauc"], w["ssalb"], w["pmom"], w["bins"], nstr=16, temper=w["temper"], utau=utau)
+print("usrtau bad", int((o["status"] != 0).sum()))
+w = workloads.retrieval_batch(6, nstr=8, nlyr=6, ncols=2, seed=3)
+o = s.disort_batch(w["dtauc"], w["ssalb"], w["pmom"], w["bins"], nstr=8, umu=np.array([-0.5, 0.5]), phi=np.array([0.0, 90.0]))
+print("radiance bad", int((o["status"] != 0).sum()))
+s.close()
