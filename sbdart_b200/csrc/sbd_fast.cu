@@ -1,9 +1,11 @@
 // Register-resident warp-per-bin discrete-ordinate kernel for NSTR = 4, 8, 16.
 //
 // Same mathematics as sbd_generic.cu (see the header comment there) but laid
-// out for the hardware.  The measured limiter of this kernel is the SM's
-// shared-memory / shuffle pipe (MIO), not the FP64 pipe, so every phase is
-// organised to move as few words between lanes as possible:
+// out for the hardware.  The measured limiters of this kernel are the issue slots
+// and the SM's shared-memory / shuffle pipe (MIO), not the FP64 pipe,
+// so every phase is organised to move as few words between lanes as possible and
+// the warps of a CTA walk through the phases together (one instruction stream in
+// the I-cache at a time):
 //   phase 1  per-layer eigen / particular solutions.  A warp works on 32/n
 //            layers of its bin at once; each layer is owned by a group of n
 //            lanes, lane j holding ROW j (Cholesky factors) or COLUMN j
@@ -39,7 +41,7 @@ namespace sbd {
 
 #ifdef SBD_PHASE_TIMING
 // debug build only: SM-clock ticks spent between the phase barriers, summed over CTAs
-__device__ unsigned long long g_phase_ticks[4];
+__device__ unsigned long long g_phase_ticks[8];
 #define SBD_TICK(i)                                                                     \
     do {                                                                                \
         if (threadIdx.x == 0) {                                                         \
@@ -136,6 +138,14 @@ __device__ __forceinline__ double fast_rsqrt(double x)
     const double e = fma(-x, y * y, 1.0);
     return fma(fma(e, 0.375, 0.5), y * e, y);
 }
+
+// One-sided Jacobi: a sweep in which every pair's squared cosine stayed below this
+// is the last one (tools/accuracy_probe.py: tightening it does not change the result).
+#ifdef SBD_JACOBI_BIG
+constexpr double kJacobiBig = SBD_JACOBI_BIG;
+#else
+constexpr double kJacobiBig = 1.0e-10;
+#endif
 
 // sum over the n lanes of a layer group
 template <int n>
@@ -301,10 +311,7 @@ __device__ __forceinline__ int phase1_layers(
                 // rotate unless the pair is orthogonal to 1e-12 (eigenvectors then carry
                 // errors ~1e-12, far below the 1e-5 target)
                 if (gg > 1.0e-24 * ab && gg > 1.0e-290) {
-#ifndef SBD_JACOBI_BIG
-#define SBD_JACOBI_BIG 1.0e-10
-#endif
-                    if (gg > SBD_JACOBI_BIG * ab) big = 1;
+                    if (gg > kJacobiBig * ab) big = 1;
                     // rotation by theta, |theta| <= pi/4: cos 2theta = |dl| / h, sin 2theta = gam / h
                     // with dl = (beta - alpha) / 2, h = sqrt(dl^2 + gam^2); no division:
                     // c = sqrt(x), x = (1 + cos 2theta) / 2, s = sin 2theta / (2 c), t = s / c
@@ -958,9 +965,15 @@ disort_fast_kernel(const LaunchArgs a)
             fetch_layer(ncut - 1, 0);
             for (int lc = ncut - 1; lc >= 0; lc--) {
                 const int buf = (ncut - 1 - lc) & 1;
+#ifdef SBD_PHASE_TIMING
+                long long tsub = clock64();
+#endif
                 if (lc > 0) { fetch_layer(lc - 1, buf ^ 1); cp_async_wait_one(); }
                 else cp_async_wait_all();
                 __syncwarp();
+#ifdef SBD_PHASE_TIMING
+                if (threadIdx.x == 0) { const long long t = clock64(); atomicAdd(&g_phase_ticks[4], (unsigned long long)(t - tsub)); tsub = t; }
+#endif
                 const double *ubuf = tsm_base + buf * kSlot;
                 const double *fr = ubuf + FL::ublk;
                 double acc, dinv;
@@ -988,6 +1001,9 @@ disort_fast_kernel(const LaunchArgs a)
                     xs[c] = xc;
                     if (lane < c) acc = fma(-ur[c], xc, acc);
                 }
+#ifdef SBD_PHASE_TIMING
+                if (threadIdx.x == 0) { const long long t = clock64(); atomicAdd(&g_phase_ticks[5], (unsigned long long)(t - tsub)); tsub = t; }
+#endif
                 // ---- fluxes at the levels living in this layer (FLUXES, disort.f:1780) ----
                 if (fastmap)
                     while (lu_next >= 0 && layru[lu_next] > lc + 1) lu_next--;
@@ -1089,6 +1105,9 @@ disort_fast_kernel(const LaunchArgs a)
                     }
                 }
                 __syncwarp();     // everyone is done with this half of the double buffer
+#ifdef SBD_PHASE_TIMING
+                if (threadIdx.x == 0) { const long long t = clock64(); atomicAdd(&g_phase_ticks[6], (unsigned long long)(t - tsub)); tsub = t; }
+#endif
             }
         }
         cp_async_wait_all();
@@ -1105,7 +1124,7 @@ disort_fast_kernel(const LaunchArgs a)
 extern "C" void sbd_debug_phase_ticks(unsigned long long *out, int reset)
 {
     cudaMemcpyFromSymbol(out, g_phase_ticks, sizeof(g_phase_ticks));
-    if (reset) { unsigned long long z[4] = {0, 0, 0, 0}; cudaMemcpyToSymbol(g_phase_ticks, z, sizeof z); }
+    if (reset) { unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0}; cudaMemcpyToSymbol(g_phase_ticks, z, sizeof z); }
 }
 #endif
 
