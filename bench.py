@@ -165,7 +165,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--replicate", type=int, default=128, help="spectra per step per GPU (SURVEY 8d asks for a large replication of the 2037-bin spectrum)")
     ap.add_argument("--ref-bins", type=int, default=8192, help="bins per CPU reference step")
-    ap.add_argument("--cpu-sample", type=int, default=16384, help="bins for cpu_baseline")
+    ap.add_argument("--cpu-sample", type=int, default=262144, help="bins for cpu_baseline (about 10 s of host work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
