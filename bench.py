@@ -126,7 +126,7 @@ def run_reference(args, rank, world):
     from oracle import oracle
     w = build_workload(1)
     cores = os.cpu_count() or 1
-    sample = min(args.ref_bins, w["dtauc"].shape[0] * 8)
+    sample = min(args.ref_bins, w["dtauc"].shape[0] * 32)
     rep = -(-sample // w["dtauc"].shape[0])
     idx = np.arange(sample) % w["dtauc"].shape[0]
     b = w["bins"][idx]
@@ -164,7 +164,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--replicate", type=int, default=128, help="spectra per step per GPU (SURVEY 8d asks for a large replication of the 2037-bin spectrum)")
-    ap.add_argument("--ref-bins", type=int, default=8192, help="bins per CPU reference step")
+    ap.add_argument("--ref-bins", type=int, default=65536, help="bins per CPU reference step (~2.5 s on 16 threads)")
     ap.add_argument("--cpu-sample", type=int, default=262144, help="bins for cpu_baseline (about 10 s of host work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
