@@ -153,8 +153,8 @@ int sbd_quadrature(int m, double *mu, double *wt);
  * DISORT inputs of every (wavelength, k-term) bin straight into HBM; the solve
  * kernel follows on the same stream.  Only the per-run setup (atmosphere,
  * absorber amounts uu(63,nz) of absint, cloud layer list, tables) comes from
- * the host.  Covers what the reference does for iaer=0, isat<=0, Lambertian
- * surfaces (the configs of SURVEY section 8).
+ * the host.  Covers Lambertian surfaces, flat filters (isat 0/-2) and, through
+ * sbd_spectrum_set_aerosols, the standard and user aerosol models.
  * ------------------------------------------------------------------------ */
 typedef struct sbd_optics_params {
     int32_t nz;        /* levels = DISORT layers            */
@@ -200,6 +200,35 @@ typedef struct sbd_inputs_out {
     double *dtauc, *ssalb, *pmom;
     sbd_bin *bins;
 } sbd_inputs_out;
+
+/* Aerosols of the following sbd_spectrum_run calls (tauaero, tauaero.f:1175-1358).
+ * The wavelength-independent part of the reference's first call (denprfl
+ * tauaero.f:1361: vertical profile, humidity-interpolated spectral model,
+ * normalisation to vis / tbaer; zlayer of the stratospheric layers) is done by
+ * the host front end; the producer kernel evaluates aerbwi (tauaero.f:177),
+ * aestrat (:253), getmom and the moment mixing per wavelength.  All pointers are
+ * HOST pointers; p == NULL switches aerosols off again. */
+#define SBD_NAERW 47           /* wavelengths of the standard models (naerw, tauaero.f:21) */
+#define SBD_NAERZ 5            /* stratospheric layers (naerz, tauaero.f:19)               */
+typedef struct sbd_aerosol_params {
+    int32_t nwlbaer;   /* spectral points of the boundary-layer model, 0: none (iaer=0)  */
+    int32_t imoma;     /* phase function of the boundary-layer aerosol: 2 or 3 (getmom)  */
+    int32_t nosct;     /* 0 normal, 1/2/3 no-scattering variants (tauaero.f:1266-1275)    */
+    int32_t nstrat;    /* stratospheric layers in use, <= SBD_NAERZ                       */
+    int32_t nz;        /* length of dtsv = levels of the run                              */
+    int32_t pad_;
+    double abaer;      /* Angstrom exponent outside the tabulated range                   */
+} sbd_aerosol_params;
+
+typedef struct sbd_strat_entry {
+    double layer;      /* DISORT layer, 1-based from the top (laer, tauaero.f:1216)       */
+    double taerst;     /* optical depth at 0.55 um                                        */
+    double ext[SBD_NAERW], absb[SBD_NAERW], asym[SBD_NAERW];   /* aerstr(:,1:3,jaer)      */
+} sbd_strat_entry;
+
+int sbd_spectrum_set_aerosols(sbd_handle *h, const sbd_aerosol_params *p, const double *wlbaer,
+                              const double *aerext, const double *aerabs, const double *aerasm,
+                              const double *dtsv, const double *awl, const sbd_strat_entry *strat);
 
 int sbd_spectrum_run(sbd_handle *h, const sbd_optics_params *p, const double *z, const double *pr,
                      const double *t, const double *uu, const sbd_cloud_entry *clouds,

@@ -156,7 +156,7 @@ extern "C" void sbd_destroy(sbd_handle *h)
     cudaStreamSynchronize(h->stream2);
     SbdDevBuf *bufs[] = { &h->scratch, &h->counter, &h->scratch2, &h->counter2, &h->ylmu, &h->angles, &h->d_dtauc, &h->d_ssalb,
                        &h->d_pmom, &h->d_bins, &h->d_temper, &h->d_utau, &h->d_out, &h->d_uu,
-                       &h->d_status, &h->opt_tables, &h->opt_atm, &h->opt_misc, &h->opt_map };
+                       &h->d_status, &h->opt_tables, &h->opt_atm, &h->opt_misc, &h->opt_map, &h->opt_aero };
     for (SbdDevBuf *b : bufs) b->release();
     for (int i = 0; i < sbd_handle::kMaxChunks; i++) { cudaEventDestroy(h->ev_in[i]); cudaEventDestroy(h->ev_k[i]); }
     cudaEventDestroy(h->ev_misc);

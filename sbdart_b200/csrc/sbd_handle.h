@@ -51,7 +51,9 @@ struct sbd_handle {
     // staging for the host-pointer API
     SbdDevBuf d_dtauc, d_ssalb, d_pmom, d_bins, d_temper, d_utau, d_out, d_uu, d_status;
     // whole-spectrum path (sbd_spectrum.cu)
-    SbdDevBuf opt_tables, opt_atm, opt_misc, opt_map;
+    SbdDevBuf opt_tables, opt_atm, opt_misc, opt_map, opt_aero;
+    sbd_aerosol_params aero = {};             // aerosols of the next spectrum runs
+    bool aero_on = false;
     sbd::OpticsTables opt_index = {};
     bool opt_ready = false;
     const int32_t *pending_binmap = nullptr;   // device bin -> slot map for the next solve launch

@@ -293,6 +293,35 @@ __device__ void cloudpar_dev(const OpticsTables &T, double wl, double re, double
     qc = out[0]; wc = out[1]; gc = out[2];
 }
 
+// aerbwi / aestrat (tauaero.f:177-250, :253-403): log-log interpolation of extinction and
+// absorption, linear in the asymmetry factor; power-law continuation outside the table.
+// `wl_hi_ref` is the wavelength the upper continuation is scaled from (the last point for
+// the boundary-layer model, awl(1) for the stratospheric models -- as in the reference).
+__device__ void aer_interp_dev(const double *wlb, const double *ext, const double *ab, const double *as,
+                               int n, double wl, double abaer, double wl_hi_ref, bool linear_abs_guard,
+                               double &extinc, double &wa, double &ga)
+{
+    wa = 0.0;
+    if (wl <= wlb[0]) {
+        extinc = ext[0] * pow(wlb[0] / wl, abaer);
+        wa = 1. - ab[0] / ext[0];
+        ga = as[0];
+    } else if (wl >= wlb[n - 1]) {
+        extinc = ext[n - 1] * pow(wl_hi_ref / wl, abaer);
+        wa = 1. - ab[n - 1] / ext[n - 1];
+        ga = as[n - 1];
+    } else {
+        const int l = locate_dev(wlb, n, wl);
+        const double wt = log(wl / wlb[l - 1]) / log(wlb[l] / wlb[l - 1]);
+        extinc = ext[l - 1] * pow(ext[l] / ext[l - 1], wt);
+        double absorp;
+        if (!linear_abs_guard || (ab[l - 1] > 0. && ab[l] > 0.)) absorp = ab[l - 1] * pow(ab[l] / ab[l - 1], wt);
+        else absorp = ab[l - 1] * (1. - wt) + ab[l] * wt;
+        if (extinc > 0.) wa = fmax(0.0, fmin(1. - absorp / extinc, 1.0));
+        ga = (1. - wt) * as[l - 1] + wt * as[l];
+    }
+}
+
 __global__ void __launch_bounds__(64)
 optics_kernel(const OpticsArgs a)
 {
@@ -435,6 +464,34 @@ optics_kernel(const OpticsArgs a)
             else taucld[j] += F32(.75) * qc * ce.lwpth / ce.reff;
         }
     }
+    // ---- aerosols (tauaero, tauaero.f:1223-1331): per-wavelength scattering parameters
+    double dtaua[kMaxZ], waer[kMaxZ];
+    for (int j = 0; j < nz; j++) { dtaua[j] = 0.; waer[j] = 0.; }
+    double bl_ext = 0., bl_wa = 0., bl_ga = 0.;
+    const double *dtsv = nullptr, *awl = nullptr, *strat = nullptr;
+    double st_dt[SBD_NAERZ], st_wa[SBD_NAERZ], st_ga[SBD_NAERZ];
+    int st_layer[SBD_NAERZ];
+    const int nbl = a.aero ? a.aer.nwlbaer : 0, nst = a.aero ? a.aer.nstrat : 0;
+    if (a.aero) {
+        const double *wlb = a.aero, *ext = wlb + nbl, *ab = ext + nbl, *as = ab + nbl;
+        dtsv = as + nbl; awl = dtsv + nz; strat = awl + SBD_NAERW;
+        if (nbl > 0) {
+            aer_interp_dev(wlb, ext, ab, as, nbl, wl, a.aer.abaer, wlb[nbl - 1], true, bl_ext, bl_wa, bl_ga);
+            if (a.aer.nosct == 1) bl_ext *= 1. - bl_wa;
+            if (a.aer.nosct == 3) bl_ext *= 1. - bl_wa * bl_ga;
+            if (a.aer.nosct != 0) { bl_wa = 0.; bl_ga = 0.; }
+            for (int j = 0; j < nz; j++) { dtaua[j] = bl_ext * dtsv[j]; waer[j] = bl_wa; }
+        }
+        const int per = (int)(sizeof(sbd_strat_entry) / 8);
+        for (int e = 0; e < nst; e++) {
+            const double *se = strat + (size_t)e * per;
+            double qa;
+            aer_interp_dev(awl, se + 2, se + 2 + SBD_NAERW, se + 2 + 2 * SBD_NAERW, SBD_NAERW, wl, a.aer.abaer,
+                           awl[0], false, qa, st_wa[e], st_ga[e]);
+            st_layer[e] = (int)se[0] - 1;
+            st_dt[e] = se[1] * qa;
+        }
+    }
     // ---- rayleigh (spectra.f:206-247), normom (drt.f:1366-1397)
     double dtaur[kMaxZ];
     {
@@ -457,8 +514,24 @@ optics_kernel(const OpticsArgs a)
             for (int k = 1; k <= nmom; k++)
                 pm0[(size_t)j * ldp + k] = taucld[j] * wcld[j] * pm0[(size_t)j * ldp + k] / icnt[j];
         }
+        if (nbl > 0) {                               // boundary-layer aerosol, getmom(imoma)
+            const double dab = dtaua[j];
+            double gp = 1.0;
+            for (int k = 1; k <= nmom; k++) {
+                gp *= bl_ga;
+                const double pmk = (a.aer.imoma == 2) ? (k == 2 ? F32(0.1) : 0.0) : gp;
+                pm0[(size_t)j * ldp + k] += pmk * dab * bl_wa;
+            }
+        }
+        for (int e = 0; e < nst; e++) {              // stratospheric layers, Henyey-Greenstein
+            if (st_layer[e] != j) continue;
+            double gp = 1.0;
+            for (int k = 1; k <= nmom; k++) { gp *= st_ga[e]; pm0[(size_t)j * ldp + k] += gp * st_dt[e] * st_wa[e]; }
+            waer[j] = (waer[j] * dtaua[j] + st_wa[e] * st_dt[e]) / (dtaua[j] + st_dt[e]);
+            dtaua[j] += st_dt[e];
+        }
         pm0[(size_t)j * ldp + 2] += F32(.1) * dtaur[j];
-        const double dtsct = taucld[j] * wcld[j] + dtaur[j];
+        const double dtsct = taucld[j] * wcld[j] + dtaua[j] * waer[j] + dtaur[j];
         if (dtsct != 0.)
             for (int k = 0; k <= nmom; k++) pm0[(size_t)j * ldp + k] /= dtsct;
         pm0[(size_t)j * ldp] = 1.;
@@ -473,7 +546,7 @@ optics_kernel(const OpticsArgs a)
         if (P.kdist == 0 || nk == 1) wt = 1.;
         for (int i = 0; i < nz; i++) {
             double dtaug;
-            tsc += dtaur[i] + taucld[i];
+            tsc += dtaur[i] + taucld[i] + dtaua[i];
             if (P.kdist == 0 || nk == 1) {
                 tglv += dtk[i][0]; tgls += dk2[i][0];
                 double afac = 1.;
@@ -487,9 +560,9 @@ optics_kernel(const OpticsArgs a)
                 const double ramp = rolloff_dev(wl, tsc);
                 dtaug = dtcv[i] + dtk[i][kd] * (1. - ramp) + dk2[i][kd] * ramp;
             }
-            const double dtau = dtaug + taucld[i] + 0.0 + dtaur[i];
+            const double dtau = dtaug + taucld[i] + dtaua[i] + dtaur[i];
             od[i] = dtau;
-            os[i] = (dtau > 2.2250738585072014e-308) ? (taucld[i] * wcld[i] + dtaur[i]) / dtau : 0.0;
+            os[i] = (dtau > 2.2250738585072014e-308) ? (taucld[i] * wcld[i] + dtaua[i] * waer[i] + dtaur[i]) / dtau : 0.0;
         }
         if (kd > 0) {
             double *pk = a.pmom + slot * nz * ldp;

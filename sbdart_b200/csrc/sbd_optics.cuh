@@ -42,6 +42,9 @@ struct OpticsArgs {
     const double *z, *p_, *t, *uu;               // [nz], [nz], [nz], [64][nz+1]
     const sbd_cloud_entry *clouds;               // [p.ncloud]
     const double *wlalb, *alb, *wlsun, *sun;     // surface albedo and solar tables
+    // aerosols (sbd_spectrum_set_aerosols): packed [wlb n][ext n][abs n][asm n][dtsv nz][awl 47][strat...]
+    sbd_aerosol_params aer;
+    const double *aero;                          // nullptr: no aerosols
     // outputs: slot = 3 * il + kd
     double *dtauc, *ssalb, *pmom;                // [3 nwl][nz], [3 nwl][nz], [3 nwl][nz][nmom+1]
     sbd_bin *bins;                               // [3 nwl]

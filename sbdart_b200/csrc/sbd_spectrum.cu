@@ -27,6 +27,45 @@ extern "C" int sbd_optics_upload_tables(sbd_handle *h, const double *tables, int
     return SBD_SUCCESS;
 }
 
+extern "C" int sbd_spectrum_set_aerosols(sbd_handle *h, const sbd_aerosol_params *p, const double *wlbaer,
+                                         const double *aerext, const double *aerabs, const double *aerasm,
+                                         const double *dtsv, const double *awl, const sbd_strat_entry *strat)
+{
+    if (!h) return SBD_ERR_ARG;
+    if (!p) { h->aero_on = false; return SBD_SUCCESS; }
+    const int n = p->nwlbaer, nz = p->nz, ns = p->nstrat;
+    if (n < 0 || n == 1 || n > 150 || nz < 2 || nz > 65 || ns < 0 || ns > SBD_NAERZ) return SBD_ERR_ARG;
+    if (n > 0 && (!wlbaer || !aerext || !aerabs || !aerasm || !dtsv)) return SBD_ERR_ARG;
+    if (ns > 0 && (!awl || !strat)) return SBD_ERR_ARG;
+    if (n > 0 && p->imoma != 2 && p->imoma != 3) return SBD_ERR_UNSUPPORTED;
+    for (int i = 0; i < ns; i++)
+        if (!(strat[i].layer >= 1 && strat[i].layer <= nz)) return SBD_ERR_ARG;
+    if (cudaSetDevice(h->device) != cudaSuccess) return SBD_ERR_CUDA;
+    // packed: [wlb n][ext n][abs n][asm n][dtsv nz][awl 47][strat ns]
+    const size_t per = sizeof(sbd_strat_entry) / 8;
+    std::vector<double> pk(4 * (size_t)n + nz + SBD_NAERW + per * ns, 0.0);
+    double *q = pk.data();
+    if (n > 0) {
+        memcpy(q, wlbaer, 8 * (size_t)n); q += n;
+        memcpy(q, aerext, 8 * (size_t)n); q += n;
+        memcpy(q, aerabs, 8 * (size_t)n); q += n;
+        memcpy(q, aerasm, 8 * (size_t)n); q += n;
+        memcpy(q, dtsv, 8 * (size_t)nz);
+    }
+    q = pk.data() + 4 * (size_t)n + nz;
+    if (ns > 0) {
+        memcpy(q, awl, 8 * SBD_NAERW); q += SBD_NAERW;
+        memcpy(q, strat, sizeof(sbd_strat_entry) * ns);
+    }
+    if (h->opt_aero.reserve(pk.size() * 8) != cudaSuccess) return SBD_ERR_CUDA;
+    if (cudaMemcpyAsync(h->opt_aero.p, pk.data(), pk.size() * 8, cudaMemcpyHostToDevice, h->stream) != cudaSuccess)
+        return SBD_ERR_CUDA;
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess) return SBD_ERR_CUDA;   // pk is a temporary
+    h->aero = *p;
+    h->aero_on = true;
+    return SBD_SUCCESS;
+}
+
 extern "C" int sbd_spectrum_run(sbd_handle *h, const sbd_optics_params *p, const double *z,
                                 const double *pr, const double *t, const double *uu,
                                 const sbd_cloud_entry *clouds, const double *wlalb, const double *alb,
@@ -88,6 +127,11 @@ extern "C" int sbd_spectrum_run(sbd_handle *h, const sbd_optics_params *p, const
     a.wlalb = a.uu + 64 * (size_t)(nz + 1); a.alb = a.wlalb + p->nalb;
     a.wlsun = a.alb + p->nalb; a.sun = a.wlsun + p->nsun;
     a.clouds = d_clouds;
+    if (h->aero_on) {
+        if (h->aero.nz != nz) return SBD_ERR_ARG;
+        a.aer = h->aero;
+        a.aero = (const double *)h->opt_aero.p;
+    }
     a.dtauc = (double *)h->d_dtauc.p; a.ssalb = (double *)h->d_ssalb.p; a.pmom = (double *)h->d_pmom.p;
     a.bins = (sbd_bin *)h->d_bins.p;
     a.nk = d_nk; a.wl = d_wl; a.dwl = d_dwl; a.wt = d_wt;

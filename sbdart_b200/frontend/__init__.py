@@ -15,8 +15,9 @@ by tools/extract_tables.py (tables.npz).  The radiative-transfer solve itself
 is NOT here: `run()` takes a `solve(batch)` callable -- the CUDA batch solver
 (Solver.disort_batch); the golden tests also pass their CPU checker.
 
-Not covered yet: user files (atms.dat, albedo.dat, ...), aerosols (iaer != 0,
-jaer), BRDF surfaces (isalb 7-9), sensor filters (isat > 0), zgrid, kdist=-1.
+Aerosols, zgrid, in-cloud humidity, zensun and the sensor filters live in extras.py.
+Not covered: user files (atms.dat, albedo.dat, aerosol.dat, filter.dat, solar.dat,
+usrcld.dat, CKTAU), BRDF surfaces (isalb 7-9), kdist=-1, spowder.
 """
 from __future__ import annotations
 
@@ -89,6 +90,10 @@ DEFAULTS = dict(
     zout=[0.0, 100.0], iout=10, temis=0.0, nstr=0, nzen=0, uzen=[ZIP] * NSTRMS,
     vzen=[90.0] * NSTRMS, nphi=0, phi=[ZIP] * NSTRMS, saza=180.0, imomc=3, ttemp=ZIP, btemp=ZIP,
     corint=False, ibcnd=0, fisot=0.0,
+    # module aeroblk (tauaero.f:27-47)
+    zaer=[0.0] * 5, taerst=[0.0] * 5, jaer=[0] * 5, zbaer=[ZIP] * MXLY, dbaer=[ZIP] * MXLY, vis=ZIP,
+    tbaer=ZIP, abaer=0.0, wlbaer=[ZIP] * 150, qbaer=[ZIP] * 150, wbaer=[ZIP] * 150, gbaer=[ZIP] * 150,
+    pmaer=[ZIP], rhaer=ZIP, imoma=3,
 )
 
 
@@ -746,8 +751,12 @@ class Sun:
         elif nf == 1:   # sun1s: 0.25..4.0 um, 751 points
             self.s = T("spectra/sun1s/sun1")
             self.wl = f32(.25) + (4.0 - f32(.25)) * _f32ramp(751)
-        elif nf == 3:
-            raise NotImplementedError("nf=3 (MODTRAN3 solar table) not wired yet")
+        elif nf == 3:   # sunmod, spectra.f:2884-2893: 100-49960 cm-1 every 20 cm-1
+            s3 = T("spectra/sunmod/sun3")
+            n = 2494
+            r = ((n - 1 - np.arange(n)).astype(np.float32) / np.float32(n - 1)).astype(float)
+            self.wl = 10000. / (100. + (49960. - 100.) * r)
+            self.s = s3[::-1]
         elif nf != 0:
             raise NotImplementedError("nf=-1 solar.dat")
 
@@ -782,8 +791,14 @@ class Albedo:
         return interp_table(self.wl, self.alb, wl)
 
 
-def setfilt(isat, wlinf, wlsup, wlinc):
-    """spectra.f:3240-3387 for isat = 0 / -2.  Returns wlmin, wlmax, nwl, wlinc."""
+def setfilt(isat, wlinf, wlsup, wlinc, want_filter=False):
+    """spectra.f:3240-3387.  Returns wlmin, wlmax, nwl, wlinc [, filter function]."""
+    if want_filter:
+        from .extras import Filter, filter_table
+        if isat in (0, -2):
+            return setfilt(isat, wlinf, wlsup, wlinc) + (Filter(),)
+        wlmin, wlmax, filt = filter_table(isat, wlinf, wlsup)
+        return _setfilt_grid(wlmin, wlmax, wlinc) + (filt,)
     if isat == 0:
         wlmin, wlmax = wlinf, wlsup
         if wlinf == wlsup:
@@ -793,7 +808,13 @@ def setfilt(isat, wlinf, wlsup, wlinc):
         if wlsup == 0.:
             return wlmin, wlmax, 1, f32(.001)
     else:
-        raise NotImplementedError(f"isat={isat}")
+        from .extras import filter_table
+        wlmin, wlmax, _ = filter_table(isat, wlinf, wlsup)
+    return _setfilt_grid(wlmin, wlmax, wlinc)
+
+
+def _setfilt_grid(wlmin, wlmax, wlinc):
+    """Number of wavelength steps (spectra.f:3358-3385)."""
     if wlmin < f32(0.199):
         raise ValueError("Error in SETFILT -- illegal wavelength limits")
     if wlinc > 1.:
@@ -1028,8 +1049,9 @@ class Sbdart:
     # ---- setup part of the main program (drt.f:233-421)
     def _setup(self):
         p = self.p
-        if p["iaer"] != 0 or p["ngrid"] != 0 or p["iday"] != 0 or p["amix"] > -1.0:
-            raise NotImplementedError("iaer / ngrid / iday / amix")
+        from . import extras
+        if p["amix"] > -1.0 or p["idatm"] == 0:
+            raise NotImplementedError("atms.dat (idatm=0 / amix)")
         iout = p["iout"]
         self.radcalc = iout in (5, 6, 20, 21, 22, 23)
         self.onlyfl = not self.radcalc
@@ -1042,22 +1064,35 @@ class Sbdart:
             self._vuangles()
         sza = p["sza"]
         dtor = PI_KR / 180.
-        if p["csza"] != ZIP:
+        if p["iday"] != 0:                                  # drt.f:276-277
+            if p["iday"] < 0:
+                raise NotImplementedError("iday < 0 (print the solar geometry and stop)")
+            sza, p["saza"], p["solfac"] = extras.zensun(abs(p["iday"]), p["time"], p["alat"], p["alon"])
+        elif p["csza"] != ZIP:
             sza = math.acos(p["csza"]) / dtor
         if abs(sza - 90) < f32(.01):
             sza = 95.
         self.sza = sza
         self.phi0 = math.fmod(p["saza"] - 180.0 + 360.0, 360.0)
-        self.wl1, self.wl2, self.nwl, self.wlinc = setfilt(p["isat"], p["wlinf"], p["wlsup"], p["wlinc"])
+        self.wl1, self.wl2, self.nwl, self.wlinc, self.filter = setfilt(
+            p["isat"], p["wlinf"], p["wlsup"], p["wlinc"], want_filter=True)
         kdist = 0 if iout == 2 else p["kdist"]
         self.kdist = kdist
         z, pr, t, wh, wo = atms(p["idatm"])
+        if p["ngrid"] != 0:                                 # drt.f:307
+            if p["ngrid"] < 0:
+                raise NotImplementedError("ngrid < 0 (print the regridded atmosphere and stop)")
+            z, pr, t, wh, wo = extras.zgrid(z, pr, t, wh, wo, p["zgrid1"], p["zgrid2"], p["ngrid"])
         if p["zpres"] != ZIP:
             j = locate(z, p["zpres"])
             fj = (p["zpres"] - z[j - 1]) / (z[j] - z[j - 1])
             p["pbar"] = pr[j - 1] * (pr[j] / pr[j - 1]) ** fj
         modatm(z, pr, wh, wo, p["sclh2o"], p["uw"], p["uo3"], p["o3trp"], p["ztrp"], p["pbar"])
         self.trace = TraceGases(p)
+        rhaer = p["rhaer"]
+        if rhaer < 0.:                                      # drt.f:319
+            rhaer = extras.relhum(t[0], wh[0])
+        self.rhaer = rhaer
         self.z, self.pr, self.t, self.wh, self.wo = z, pr, t, wh, wo
         nz = len(z)
         self.nz = nz
@@ -1066,8 +1101,11 @@ class Sbdart:
         self.ttemp = self.temper[0] if p["ttemp"] < 0. else p["ttemp"]
         self.nstrsv = p["nstr"]
         self.clouds = Clouds(z, p["zcloud"], p["tcloud"], p["lwp"], p["nre"], p["imomc"])
-        if p["rhcld"] >= 0:
-            raise NotImplementedError("rhcld")
+        if p["rhcld"] >= 0:                                 # drt.f:358-364
+            if int(p["krhclr"]) == 1:
+                extras.satcloud(self.clouds.lcld, t, p["rhcld"], wh)
+            else:
+                extras.saturate(self.clouds.lcld, z, t, p["rhcld"], wh)
         self.uu = absint(z, pr, t, wh, wo, self.trace)
         zout = np.abs(p["zout"]) if p["zout"].min() < 0 else p["zout"]
         nbot = self._nearest(z, zout[0])
@@ -1091,6 +1129,7 @@ class Sbdart:
         self.albedo = Albedo(p["isalb"], p["albcon"], self.sc)
         self.amu0 = math.cos(sza * dtor)
         self.sun = Sun(p["nf"])
+        self.aerosols = extras.Aerosols(p, z, self.rhaer)
 
     @staticmethod
     def _nearest(xx, x):
@@ -1153,7 +1192,7 @@ class Sbdart:
                 flxin = 0.
                 amu0 = 1.
                 self.amu0 = 1.          # the reference overwrites amu0 for good (drt.f:456-459)
-            ff = 1.0                    # filter(wl) for isat <= 0
+            ff = self.filter(wl)
             plank = (wl > 2.) if p["nothrm"] < 0 else (p["nothrm"] == 0)
             rsfc = max(0.0, min(self.albedo(wl), 1.0))
             pmom = np.zeros((nz, nmom + 1))
@@ -1161,6 +1200,8 @@ class Sbdart:
             if self.clouds.mcldz > 0:
                 dtauc, wcld, pmom = self.clouds(wl, nmom)
             dtaua, waer = np.zeros(nz), np.zeros(nz)
+            if self.aerosols.active:
+                dtaua, waer = self.aerosols(wl, nmom, pmom)
             dtaur = rayleigh(wl, self.z, self.pr, self.t)
             if p["xrsc"] != 1.0:
                 dtaur = p["xrsc"] * dtaur
@@ -1218,7 +1259,13 @@ class Sbdart:
     def run_device(self, solver):
         """Whole-spectrum GPU path: the optical properties of every bin are produced
         by the K2 kernel and never leave the device (frontend/device.py)."""
-        from .device import run_spectrum
+        from .device import device_aerosols_supported, run_spectrum
+        host_solve = lambda b: solver.disort_batch(  # noqa: E731
+            b["dtauc"], b["ssalb"], b["pmom"], b["bins"], nstr=b["nstr"], temper=b["temper"],
+            umu=b.get("umu"), phi=b.get("phi"), uu_levels=b.get("uu_levels"))
+        if not device_aerosols_supported(self.aerosols) or self.p["imomc"] not in (2, 3):
+            # table phase functions (getmom 4/5, pmaer): optical properties on the host, solve on the GPU
+            return self.run(host_solve)
         rows, res = run_spectrum(self, solver)
         if (res["status"] != 0).any():
             # beam / quadrature clash (drt.f:536-554): fall back to the host-side batch
@@ -1322,7 +1369,7 @@ class Sbdart:
                 out += self._rows([zz, pp, _r4(fxdn[i]), _r4(fxup[i]), _r4(fxdir[i]), _r4(dfdz),
                                    _r4(heat)], 10)
         if iout in (10, 20, 21, 23):
-            out.append(_f(p["wlinf"], 11, 4) + _f(p["wlsup"], 11, 4) + _f(phidw, 11, 4) + "".join(
+            out.append(_f(self.wl1, 11, 4) + _f(self.wl2, 11, 4) + _f(phidw, 11, 4) + "".join(
                 _es(_r4(x), 12, 4) for x in (topdn, topup, topdir, botdn, botup, botdir)))
         if iout in (20, 21, 23):
             out.append(f"{self.nphi:4d}{self.nzen:4d}")

@@ -28,6 +28,50 @@ CLOUD_DTYPE = np.dtype([("layer", "<i4"), ("use_tau", "<i4"), ("reff", "<f8"), (
                         ("lwpth", "<f8"), ("q550", "<f8")])
 
 
+class AerosolParams(C.Structure):
+    """struct sbd_aerosol_params (include/sbdart_b200.h)."""
+
+    _fields_ = [(k, C.c_int32) for k in ("nwlbaer", "imoma", "nosct", "nstrat", "nz", "pad_")] + [
+        ("abaer", C.c_double)]
+
+
+STRAT_DTYPE = np.dtype([("layer", "<f8"), ("taerst", "<f8"), ("ext", "<f8", 47), ("absb", "<f8", 47),
+                        ("asym", "<f8", 47)])
+
+
+def device_aerosols_supported(aer):
+    """The producer kernel evaluates getmom(2|3) only; table phase functions (imoma 4, 5)
+    and user moments (pmaer) stay on the host path."""
+    return (not aer.active) or aer.iaer <= 0 or aer.imoma in (2, 3)
+
+
+def set_aerosols(L, solver, aer):
+    """Hand the wavelength-independent aerosol setup (extras.Aerosols) to the handle."""
+    if not aer.active:
+        rc = L.sbd_spectrum_set_aerosols(solver._h, None, None, None, None, None, None, None, None)
+        if rc:
+            raise SbdError(rc, "sbd_spectrum_set_aerosols")
+        return
+    A = AerosolParams()
+    A.nz, A.nosct, A.abaer, A.imoma = aer.nz, aer.nosct, aer.abaer, aer.imoma
+    cd = lambda v: np.ascontiguousarray(v, dtype=float)  # noqa: E731
+    wlb = ext = ab = asm = dtsv = None
+    if aer.iaer > 0:
+        n = aer.nwlbaer
+        A.nwlbaer = n
+        wlb, ext, ab, asm, dtsv = cd(aer.wlb[:n]), cd(aer.aerext[:n]), cd(aer.aerabs[:n]), cd(aer.aerasm[:n]), cd(aer.dtsv)
+    ent = [(aer.laer[i], aer.taerst[i], aer.aerstr[:, 0, aer.jaer[i] - 1], aer.aerstr[:, 1, aer.jaer[i] - 1],
+            aer.aerstr[:, 2, aer.jaer[i] - 1]) for i in range(5) if aer.jaer[i] != 0 and aer.taerst[i] > 0.]
+    strat = np.array(ent, dtype=STRAT_DTYPE) if ent else None
+    A.nstrat = len(ent)
+    awl = cd(aer.awl)
+    ptr = lambda a: None if a is None else a.ctypes.data  # noqa: E731
+    rc = L.sbd_spectrum_set_aerosols(solver._h, C.byref(A), ptr(wlb), ptr(ext), ptr(ab), ptr(asm), ptr(dtsv),
+                                     ptr(awl), ptr(strat))
+    if rc:
+        raise SbdError(rc, "sbd_spectrum_set_aerosols")
+
+
 class InputsOut(C.Structure):
     _fields_ = [("dtauc", C.c_void_p), ("ssalb", C.c_void_p), ("pmom", C.c_void_p),
                 ("bins", C.c_void_p)]
@@ -116,6 +160,8 @@ def _bind(L):
     L.sbd_spectrum_run.argtypes = ([C.c_void_p, C.POINTER(OpticsParams)] + [C.c_void_p] * 9 +
                                    [C.c_int32, C.c_void_p, C.c_int32, C.c_void_p] + [C.c_void_p] * 10 +
                                    [C.POINTER(InputsOut)])
+    L.sbd_spectrum_set_aerosols.restype = C.c_int
+    L.sbd_spectrum_set_aerosols.argtypes = [C.c_void_p, C.POINTER(AerosolParams)] + [C.c_void_p] * 7
     L._spectrum_bound = True
 
 
@@ -173,6 +219,7 @@ def run_spectrum(run: Sbdart, solver, want_inputs=False):
               23: [run.ntop - 1, run.nbot - 1]}.get(run.p["iout"])
     if lv is not None:
         solver.set_radiance_levels(sorted(set(lv)))
+    set_aerosols(L, solver, run.aerosols)
     try:
         rc = L.sbd_spectrum_run(
             solver._h, C.byref(P), ptr(z), ptr(pr), ptr(t), ptr(uua), ptr(ce) if len(ce) else None,
@@ -182,6 +229,8 @@ def run_spectrum(run: Sbdart, solver, want_inputs=False):
     finally:
         if lv is not None:
             solver.set_radiance_levels(None)
+        if run.aerosols.active:
+            L.sbd_spectrum_set_aerosols(solver._h, None, None, None, None, None, None, None, None)
     if rc:
         raise SbdError(rc, "sbd_spectrum_run")
     B = nbins.value
@@ -189,7 +238,8 @@ def run_spectrum(run: Sbdart, solver, want_inputs=False):
     slots = []
     for il in range(nwl):
         for kd in range(nk[il]):
-            rows.append(dict(il=il, kd=kd, nk=int(nk[il]), wl=wl[il], dwl=dwl[il], wt=wt[3 * il + kd], ff=1.0))
+            rows.append(dict(il=il, kd=kd, nk=int(nk[il]), wl=wl[il], dwl=dwl[il], wt=wt[3 * il + kd],
+                             ff=run.filter(wl[il])))
             slots.append(3 * il + kd)
     res = dict(rfldir=rfldir[:B], rfldn=rfldn[:B], flup=flup[:B], status=status[:B])
     if uu is not None:

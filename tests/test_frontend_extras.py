@@ -1,0 +1,234 @@
+"""Front-end options no stored output of the reference exercises (aerosols, zgrid,
+in-cloud humidity, zensun, sensor filters; sbdart_b200/frontend/extras.py).
+
+There is no golden for them, so the checks are the properties the
+reference's own code guarantees: normalisation identities of denprfl (tauaero.f:1425-1443),
+the grid end points of zgrid (atms.f:566-585), conservation of the water column in
+saturate (atms.f:196-213), Beer's law through the full solve, and the byte format of
+the records.  The solve is done by the CPU checker (tests/solvers.py).
+"""
+import math
+
+import numpy as np
+import pytest
+
+from sbdart_b200.frontend import Sbdart, atms, extras, f32, setfilt
+from solvers import solve_oracle
+
+
+def _tau_aer(run, wl, nmom=6):
+    pm = np.zeros((run.nz, nmom + 1))
+    dtaua, waer = run.aerosols(wl, nmom, pm)
+    return dtaua, waer, pm
+
+
+# ------------------------------------------------------------------ zgrid
+def test_zgrid_end_points_and_spacing():
+    z, p, t, wh, wo = atms(2)
+    zz, pp, tt, hh, oo = extras.zgrid(z, p, t, wh, wo, 1.0, 30.0, 65)
+    assert len(zz) == 65 and zz[0] == 0.0 and abs(zz[-1] - z[-1]) < 1e-9
+    assert (np.diff(zz) > 0).all()
+    assert abs((zz[-1] - zz[-2]) - 30.0) < 1e-6          # zgrid2 = thickness of the top layer
+    assert abs((zz[1] - zz[0]) - 1.0) < 1e-3             # zgrid1 = resolution at the bottom
+    # the first points coincide with original levels 0, 1, 2 km: the fields are reproduced there
+    for k in range(3):
+        assert abs(pp[k] - p[k]) <= 1e-12 * p[k] and abs(tt[k] - t[k]) <= 1e-12 * t[k]
+    assert (np.diff(pp) < 0).all() and pp.min() > 0 and hh.min() >= 0 and oo.min() >= 0
+
+
+def test_zgrid_run_has_65_layers_and_close_fluxes():
+    a = Sbdart("&INPUT idatm=2, wlinf=0.55, wlsup=0.55, iout=10 /")
+    b = Sbdart("&INPUT idatm=2, wlinf=0.55, wlsup=0.55, iout=10, ngrid=65 /")
+    assert a.nz == 33 and b.nz == 65 and len(b.temper) == 66
+    fa = [float(x) for x in a.run(solve_oracle).split()[3:]]
+    fb = [float(x) for x in b.run(solve_oracle).split()[3:]]
+    # same atmosphere on a finer grid: top-of-atmosphere and surface fluxes agree to ~0.1 %
+    for x, y in zip(fa, fb):
+        if abs(x) > 1e-6:
+            assert abs(x - y) <= 3e-3 * abs(x)
+
+
+# ------------------------------------------------------------------ aerosols
+@pytest.mark.parametrize("iaer", [1, 2, 3, 4])
+def test_tbaer_is_the_optical_depth_at_055(iaer):
+    run = Sbdart(f"&INPUT idatm=2, iaer={iaer}, tbaer=0.37, wlinf=0.55, wlsup=0.55, iout=10 /")
+    dtaua, waer, pm = _tau_aer(run, f32(0.55))
+    assert abs(dtaua.sum() - 0.37) < 1e-12                # tauaero.f:1431-1433
+    assert (waer > 0).all() and (waer <= 1).all()
+    # Henyey-Greenstein moments weighted with the scattering depth (tauaero.f:1296-1301)
+    g = pm[:, 1] / (dtaua * waer)
+    assert np.allclose(pm[:, 2], g ** 2 * dtaua * waer, rtol=1e-12)
+    assert 0.5 < g[0] < 0.85
+
+
+def test_visibility_normalisation():
+    run = Sbdart("&INPUT idatm=2, iaer=1, vis=23, wlinf=0.55, wlsup=0.55, iout=10 /")
+    aer = run.aerosols
+    dtaua, _, _ = _tau_aer(run, f32(0.55))
+    # sigma = 3.912 / (ext55 vis n(0)), tau = sigma sum n dz (tauaero.f:1434-1440), n from the
+    # 23 km profile whatever vis is (inverted test in aerzstd, tauaero.f:129-134)
+    nd = aer._aervint()
+    assert aer.aeroden(0.0) == pytest.approx(2828.0)
+    assert dtaua.sum() == pytest.approx(f32(3.912) / 23. * nd.sum() / 2828.0, rel=1e-12)
+    assert nd[0] == pytest.approx(aer.aeroden(100.) * 5.)
+    # a thicker haze scales every layer by the same factor
+    run5 = Sbdart("&INPUT idatm=2, iaer=1, vis=5, wlinf=0.55, wlsup=0.55, iout=10 /")
+    d5, _, _ = _tau_aer(run5, f32(0.55))
+    assert np.allclose(d5, dtaua * 23. / 5., rtol=1e-12)
+
+
+def test_aerosol_spectral_dependence_and_humidity():
+    dry = Sbdart("&INPUT idatm=2, iaer=1, vis=23, rhaer=0.0, wlinf=0.55, wlsup=0.55, iout=10 /").aerosols
+    wet = Sbdart("&INPUT idatm=2, iaer=1, vis=23, rhaer=0.95, wlinf=0.55, wlsup=0.55, iout=10 /").aerosols
+    for a in (dry, wet):
+        e = [a.aerbwi(w)[0] for w in (0.3, 0.55, 1.0, 2.0, 10.0)]
+        assert e[0] > e[1] > e[2] > e[3] > e[4] > 0          # rural aerosol: extinction falls with wavelength
+        assert a.aerbwi(f32(0.55))[0] == pytest.approx(1.0, abs=2e-4)   # tables are normalised at 0.55 um
+    assert wet.aerbwi(0.55)[1] > dry.aerbwi(0.55)[1]         # wet particles absorb less
+    # the table end points continue as a power law with exponent abaer = 0 for the standard models
+    assert dry.aerbwi(0.1)[0] == pytest.approx(dry.aerext[0])
+    assert dry.aerbwi(500.)[0] == pytest.approx(dry.aerext[-1])
+
+
+def test_stratospheric_layer():
+    run = Sbdart("&INPUT idatm=2, jaer=1, zaer=20, taerst=0.05, wlinf=0.55, wlsup=0.55, iout=10 /")
+    dtaua, waer, pm = _tau_aer(run, f32(0.55))
+    nl = run.aerosols.laer[0]
+    assert run.z[run.nz - nl] <= 20.0 + 1e-3 < run.z[run.nz - nl + 1]
+    assert np.count_nonzero(dtaua) == 1
+    assert dtaua[nl - 1] == pytest.approx(0.05, rel=1e-6)   # background model: extinction 1 at 0.55 um
+    assert 0.99 < waer[nl - 1] <= 1.0
+    # on top of a boundary-layer aerosol the single-scattering albedo is the depth-weighted mean
+    both = Sbdart("&INPUT idatm=2, iaer=2, tbaer=0.3, jaer=3, zaer=20, taerst=0.05, wlinf=0.55, wlsup=0.55, iout=10 /")
+    d2, w2, _ = _tau_aer(both, f32(0.55))
+    bl = Sbdart("&INPUT idatm=2, iaer=2, tbaer=0.3, wlinf=0.55, wlsup=0.55, iout=10 /")
+    d1, w1, _ = _tau_aer(bl, f32(0.55))
+    qa, wa, _ = both.aerosols.aestrat(3, f32(0.55))
+    j = both.aerosols.laer[0] - 1
+    assert d2[j] == pytest.approx(d1[j] + 0.05 * qa, rel=1e-12)
+    assert w2[j] == pytest.approx((w1[j] * d1[j] + wa * 0.05 * qa) / d2[j], rel=1e-12)
+    assert np.allclose(np.delete(d2, j), np.delete(d1, j))
+
+
+def test_user_aerosol_model():
+    run = Sbdart("&INPUT idatm=2, iaer=5, wlbaer=0.4,0.55,1.0, qbaer=1.5,1.0,0.4, wbaer=0.9,0.92,0.95,"
+                 " gbaer=0.7,0.68,0.6, wlinf=0.55, wlsup=0.55, iout=10 /")
+    dtaua, waer, _ = _tau_aer(run, f32(0.55))
+    assert dtaua.sum() == pytest.approx(1.0, rel=1e-6)      # tbaer defaults to q(0.55) (tauaero.f:1413)
+    assert waer[0] == pytest.approx(0.92, rel=1e-6)
+    e, w, g = run.aerosols.aerbwi(0.7416198487)             # geometric mean of 0.55 and 1.0
+    assert e == pytest.approx(math.sqrt(1.0 * 0.4), rel=1e-6) and g == pytest.approx(0.64, rel=1e-6)
+    with pytest.raises(ValueError):
+        Sbdart("&INPUT iaer=5, wlbaer=0.4,0.55, qbaer=1.5, wbaer=0.9,0.92, gbaer=.7,.7 /")
+    with pytest.raises(ValueError):
+        Sbdart("&INPUT iaer=1 /")                           # must specify either tbaer or vis
+
+
+def test_direct_beam_obeys_beers_law_through_the_solve():
+    """Monochromatic run with and without aerosol: the surface direct beam differs by
+    exp(-tau_aer / mu0) exactly; the diffuse field grows."""
+    base = "&INPUT idatm=2, wlinf=0.7, wlsup=0.7, sza=60, kdist=0, iout=10"
+    a = Sbdart(base + " /")
+    b = Sbdart(base + ", iaer=1, tbaer=0.4 /")
+    fa = [float(x) for x in a.run(solve_oracle).split()]
+    fb = [float(x) for x in b.run(solve_oracle).split()]
+    tau = _tau_aer(b, f32(0.7))[0].sum()
+    assert fb[8] / fa[8] == pytest.approx(math.exp(-tau / 0.5), rel=2e-4)   # botdir, 5 printed digits
+    assert fb[4] > fa[4]                                                     # more light scattered back to space
+    assert (fb[6] - fb[8]) > (fa[6] - fa[8])                                 # more diffuse light at the surface
+
+
+# ------------------------------------------------------------------ humidity in clouds
+def test_saturate_conserves_the_water_column():
+    def column(z, wh):
+        tot = 0.0
+        for i in range(len(z) - 1):
+            d1, d2, dz = wh[i], wh[i + 1], z[i + 1] - z[i]
+            tot += .5 * dz * (d1 + d2) if abs(d1 - d2) <= 1e-3 * d1 else dz * (d1 - d2) / math.log(d1 / d2)
+        return tot
+    clear = Sbdart("&INPUT idatm=2, tcloud=10, zcloud=2 /")
+    cloudy = Sbdart("&INPUT idatm=2, tcloud=10, zcloud=2, rhcld=1.0 /")
+    # the layer-mean column the routine starts from (atms.f:85-96) equals the log-mean column it ends with
+    z = clear.z
+    edges = np.concatenate([[z[0]], .5 * (z[1:] + z[:-1]), [z[-1]]])
+    assert column(z, cloudy.wh) == pytest.approx(float((np.diff(edges) * clear.wh).sum()), rel=1e-12)
+    # saturated at the cloud level relative to the levels around it
+    rh = [extras.relhum(cloudy.t[i], cloudy.wh[i]) for i in range(6)]
+    assert rh[2] > rh[0] and rh[2] > rh[4] and rh[2] == pytest.approx(rh[3], rel=1e-9)
+    forced = Sbdart("&INPUT idatm=2, tcloud=10, zcloud=2, rhcld=0.9, krhclr=1 /")
+    assert extras.relhum(forced.t[2], forced.wh[2]) == pytest.approx(0.9, rel=1e-12)
+    assert forced.wh[10] == clear.wh[10]
+
+
+# ------------------------------------------------------------------ solar geometry
+def test_zensun():
+    # equinox (day 80), local noon on the Greenwich meridian at the equator: sun near the zenith
+    zen, azm, solfac = extras.zensun(80, 12.0, 0.0, 0.0)
+    assert zen < 2.5
+    # summer solstice at 23.44 N: overhead sun; winter: 46.9 degrees from the zenith
+    assert extras.zensun(172, 12.0, 23.44, 0.0)[0] < 1.0
+    assert extras.zensun(355, 12.0, 23.44, 0.0)[0] == pytest.approx(46.88, abs=0.3)
+    # earth-sun distance: perihelion early January, aphelion early July
+    assert extras.zensun(2, 12., 0., 0.)[2] == pytest.approx(1.0 / (1 - 0.01671) ** 2, rel=1e-6)
+    assert extras.zensun(185, 12., 0., 0.)[2] == pytest.approx(1.0 / (1 + 0.01671) ** 2, rel=1e-4)
+    run = Sbdart("&INPUT iday=172, time=12, alat=23.44, alon=0, wlinf=.55, wlsup=.55 /")
+    assert run.sza < 1.0 and run.p["solfac"] < 1.0 and 0.0 <= run.phi0 < 360.0
+
+
+# ------------------------------------------------------------------ sensor filters
+def test_filters():
+    wl1, wl2, nwl, wlinc, filt = setfilt(1, 0.0, 0.0, 0.005, want_filter=True)      # METEOSAT
+    assert (wl1, wl2) == (f32(.355), f32(1.11)) and nwl == 152
+    assert filt(wl1) == pytest.approx(0.005) and filt(0.72) > 0.95 and filt(5.0) == filt(wl2)
+    assert setfilt(1, 0.0, 0.0, 0.005)[:3] == (wl1, wl2, nwl)
+    wl1, wl2, nwl, wlinc, tri = setfilt(-3, 0.6, 0.1, 0.01, want_filter=True)
+    assert (wl1, wl2, nwl) == (0.5, 0.7, 21)
+    assert tri(0.6) == 1.0 and tri(0.55) == pytest.approx(0.5) and tri(0.5) == 0.0
+    wl1, wl2, nwl, wlinc, gau = setfilt(-4, 0.6, 0.05, 0.01, want_filter=True)
+    assert gau(0.6) == pytest.approx(1.0, abs=1e-4) and gau(wl1) == pytest.approx(math.exp(-4 * math.pi), rel=1e-6)
+    with pytest.raises(ValueError):
+        setfilt(-3, 0.6, 0.0, 0.01, want_filter=True)
+    flat = setfilt(0, 0.3, 0.4, 0.01, want_filter=True)[4]
+    assert flat(0.35) == 1.0
+
+
+def test_filtered_run_is_the_weighted_mean():
+    """iout=10 with a triangular filter = sum of the unfiltered spectral fluxes times filter x dwl."""
+    run = Sbdart("&INPUT idatm=2, isat=-3, wlinf=0.6, wlsup=0.05, wlinc=0.01, kdist=0, iout=10 /")
+    out = [float(x) for x in run.run(solve_oracle).split()]
+    rows, res = run.last["rows"], run.last["result"]
+    assert len(rows) == 11 and rows[0]["ff"] == 0.0 and rows[5]["ff"] == 1.0
+    top = sum((res["rfldn"][i][run.ntop - 1] + res["rfldir"][i][run.ntop - 1]) * r["wt"] * r["ff"]
+              for i, r in enumerate(rows))
+    assert out[3] == pytest.approx(top, rel=1e-4)
+    assert out[2] == pytest.approx(sum(r["dwl"] * r["ff"] for r in rows), abs=5e-5)
+
+
+def test_modtran_solar_table():
+    from sbdart_b200.frontend import Sun
+    s3, s2 = Sun(3), Sun(2)
+    assert (np.diff(s3.wl) > 0).all() and len(s3.wl) == 2494
+    wl = np.linspace(0.3, 3.0, 200)
+    # two solar spectra: the same sun (W/m2/um) to a few per cent when integrated
+    i3 = np.trapezoid([s3(w) for w in wl], wl)
+    i2 = np.trapezoid([s2(w) for w in wl], wl)
+    assert i3 == pytest.approx(i2, rel=0.03) and 1200 < i3 < 1400
+
+
+# ------------------------------------------------------------------ the C4 namelist
+def test_c4_namelist_builds_bins():
+    """BASELINE.json config 4: NSTR=32, stratus cloud + rural aerosol, 65 layers (a slice of the spectrum)."""
+    run = Sbdart("&INPUT idatm=2, nstr=32, ngrid=65, tcloud=10, zcloud=1, iaer=1, vis=23, wlinf=.5, wlsup=.6,"
+                 " wlinc=.02, iout=10 /")
+    rows = run.bins()
+    b = run.batch(rows)
+    assert b["dtauc"].shape[1] == 65 and b["pmom"].shape[2] == 35 and b["nstr"] == 32
+    assert (b["ssalb"] >= 0).all() and (b["ssalb"] <= 1).all() and (b["dtauc"] >= 0).all()
+    assert np.allclose(b["pmom"][:, :, 0], 1.0)
+    lc = run.clouds.lcld[0] - 1
+    assert b["dtauc"][0, lc] > 9.0                            # the cloud layer
+    assert b["dtauc"][0].sum() - b["dtauc"][0, lc] > 0.3      # aerosol + Rayleigh + gas
+    res = solve_oracle(b)
+    assert (res["status"] == 0).all()
+    txt = run.records(rows, res)
+    assert len(txt.split()) == 9

@@ -1,0 +1,107 @@
+"""GPU parity for the front-end options of frontend/extras.py: aerosols in the
+producer kernel (K2) against the host front end, and whole runs (K2 + solve, and
+host optical properties + GPU solve) against the CPU checker.
+
+Tolerances: the K2 inputs are compared at 1e-9 relative (same formulas, different
+pow/exp implementations); fluxes and radiances at the 1e-5 of BASELINE.json's north
+star, through the printed records (5 digits) and directly on the arrays."""
+import numpy as np
+import pytest
+
+import sbdart_b200 as sb
+from sbdart_b200.frontend import Sbdart
+from sbchk_cases import compare_records
+from solvers import make_solve_cuda, solve_oracle
+
+pytestmark = pytest.mark.gpu
+
+AEROSOL_RUNS = [
+    # C4 slice: rural aerosol by visibility, stratus cloud, 65-level grid
+    "&INPUT idatm=2, nstr=8, ngrid=65, tcloud=10, zcloud=1, iaer=1, vis=23, wlinf=.3, wlsup=3.0, wlinc=.05, iout=1 /",
+    # oceanic aerosol by optical depth, thermal range in wavenumber steps
+    "&INPUT idatm=1, nstr=4, iaer=3, tbaer=0.25, rhaer=0.85, wlinf=4, wlsup=40, wlinc=20, sza=95, iout=1 /",
+    # two stratospheric layers on top of an urban boundary layer, wavelengths beyond both table ends
+    "&INPUT idatm=3, nstr=4, iaer=2, vis=10, jaer=2,4, zaer=18,25, taerst=0.1,0.02, wlinf=.21, wlsup=.8,"
+    " wlinc=.01, sza=50, iout=1 /",
+    # stratospheric aerosol only (iaer=0)
+    "&INPUT idatm=4, nstr=4, jaer=3, zaer=22, taerst=0.2, wlinf=.4, wlsup=2.5, wlinc=.1, iout=1 /",
+    # user model with an Angstrom continuation; Rayleigh-like phase function; no-scattering option
+    "&INPUT idatm=2, nstr=4, iaer=5, wlbaer=.4,.55,1., qbaer=1.5,1.,.4, wbaer=.9,.92,.95, gbaer=.7,.68,.6,"
+    " abaer=1.3, tbaer=.5, wlinf=.3, wlsup=2., wlinc=.05, iout=1 /",
+    "&INPUT idatm=2, nstr=4, iaer=4, tbaer=.2, imoma=2, wlinf=.3, wlsup=1., wlinc=.05, iout=1 /",
+    "&INPUT idatm=2, nstr=4, iaer=1, vis=15, nosct=3, wlinf=.3, wlsup=1., wlinc=.05, iout=1 /",
+]
+
+
+@pytest.mark.parametrize("nl", AEROSOL_RUNS)
+def test_producer_kernel_aerosols_match_host_front_end(nl):
+    from sbdart_b200.frontend.device import run_spectrum
+    s = sb.Solver(0)
+    run = Sbdart(nl)
+    assert run.aerosols.active
+    ref = run.batch(run.bins())
+    rows, res, dev = run_spectrum(Sbdart(nl), s, want_inputs=True)
+    assert len(rows) == len(ref["bins"])
+    for k in ("dtauc", "ssalb", "pmom"):
+        np.testing.assert_allclose(dev[k], ref[k], rtol=1e-9, atol=1e-13 * np.abs(ref[k]).max())
+    # and the aerosol setting does not leak into the next run on the same handle
+    clean = "&INPUT idatm=2, nstr=4, wlinf=.3, wlsup=1., wlinc=.05, iout=1 /"
+    ref0 = Sbdart(clean)
+    ref0 = ref0.batch(ref0.bins())
+    _, _, dev0 = run_spectrum(Sbdart(clean), s, want_inputs=True)
+    np.testing.assert_allclose(dev0["dtauc"], ref0["dtauc"], rtol=1e-9, atol=1e-13 * ref0["dtauc"].max())
+    s.close()
+
+
+@pytest.mark.parametrize("nl", [
+    # BASELINE.json config 4 on a slice of its spectrum: NSTR=32, 65 layers, cloud + aerosol
+    "&INPUT idatm=2, nstr=32, ngrid=65, tcloud=10, zcloud=1, iaer=1, vis=23, wlinf=.4, wlsup=.7, wlinc=.02, iout=1 /",
+    "&INPUT idatm=2, nstr=32, ngrid=65, tcloud=10, zcloud=1, iaer=1, vis=23, wlinf=8, wlsup=12, wlinc=20, iout=11 /",
+    # NSTR=16 with aerosol (fast kernel), sensor filter, date/place geometry, in-cloud humidity
+    "&INPUT idatm=2, nstr=16, iaer=3, tbaer=.3, isat=4, wlinc=.005, iday=172, time=18, alat=34.4, alon=-119.8,"
+    " tcloud=5, zcloud=1, rhcld=1., iout=10 /",
+])
+def test_whole_runs_match_the_cpu_checker(nl):
+    s = sb.Solver(0)
+    want = Sbdart(nl).run(solve_oracle)
+    got_dev = Sbdart(nl).run_device(s)
+    got_host = Sbdart(nl).run(make_solve_cuda(s))
+    for got in (got_dev, got_host):
+        nval, nexact, worst = compare_records(got, want, rel=1.2e-4)
+        assert nval >= 9 and worst <= 1.2e-4
+    # the arrays themselves at the north-star tolerance
+    run = Sbdart(nl)
+    b = run.batch(run.bins())
+    r_gpu, r_cpu = make_solve_cuda(s)(b), solve_oracle(b)
+    assert (r_gpu["status"] == r_cpu["status"]).all()
+    for k in ("rfldir", "rfldn", "flup"):
+        scale = np.abs(r_cpu["flup"]).max(axis=1, keepdims=True) + np.abs(r_cpu["rfldn"]).max(axis=1, keepdims=True) \
+            + np.abs(r_cpu["rfldir"]).max(axis=1, keepdims=True)
+        assert (np.abs(r_gpu[k] - r_cpu[k]) <= 1e-5 * np.abs(r_cpu[k]) + 1e-9 * scale).all(), k
+    assert s.kernel_launches >= 3
+    s.close()
+
+
+def test_radiance_run_with_aerosol_and_filter():
+    """iout=20 radiances (generic kernel, all azimuth modes) through K2 with aerosols."""
+    nl = ("&INPUT idatm=2, nstr=8, iaer=1, vis=23, isat=-3, wlinf=.65, wlsup=.05, wlinc=.01, sza=30, iout=20,"
+          " uzen=0,20,40,60,80, phi=0,90,180 /")
+    s = sb.Solver(0)
+    want = Sbdart(nl).run(solve_oracle)
+    got = Sbdart(nl).run_device(s)
+    nval, nexact, worst = compare_records(got, want, rel=1.2e-4)
+    assert nval > 20 and worst <= 1.2e-4
+    s.close()
+
+
+def test_table_phase_function_takes_the_host_property_path():
+    """imoma=4 (haze-L table moments) is not evaluated by K2: optical properties on the
+    host, the solve still on the GPU."""
+    nl = "&INPUT idatm=2, nstr=8, iaer=1, vis=23, imoma=4, wlinf=.5, wlsup=.6, wlinc=.02, iout=10 /"
+    s = sb.Solver(0)
+    n0 = s.kernel_launches
+    got = Sbdart(nl).run_device(s)
+    assert s.kernel_launches > n0
+    nval, nexact, worst = compare_records(got, Sbdart(nl).run(solve_oracle), rel=1.2e-4)
+    assert worst <= 1.2e-4
+    s.close()

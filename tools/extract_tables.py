@@ -293,6 +293,42 @@ def extract_file(path):
     return out
 
 
+def extract_extras():
+    """Tables the generic DATA parser does not see: array-constructor initialisers
+    (`x = (/ ... /)`), DATA statements on array sections (`data aerstr(1:naerw,k,j) /../`)
+    and the wavelength limits of the sensor filters (named PARAMETERs)."""
+    out = {}
+
+    def f32s(txt):
+        return np.array([float(np.float32(float(t))) for t in re.split(r"[\s,]+", txt.strip()) if t])
+
+    # tauaero.f: awl (aeroblk), alt / aden05 / aden23 (aerzstd), aerstr (aestrat)
+    text = " ".join(logical_lines(os.path.join(REF, "tauaero.f")))
+    for unit, name in (("aeroblk", "awl"), ("aerzstd", "alt"), ("aerzstd", "aden05"), ("aerzstd", "aden23")):
+        m = re.search(r"\b" + name + r"\s*=\s*\(/(.*?)/\)", text, re.S)
+        out[f"tauaero/{unit}/{name}"] = f32s(m.group(1))
+    aer = np.zeros((47, 3, 4))
+    for m in re.finditer(r"data\s+aerstr\(1:naerw,(\d),(\d)\)\s*/(.*?)/", text, re.S | re.I):
+        v = f32s(m.group(3))
+        assert v.size == 47, (m.group(1), m.group(2), v.size)
+        aer[:, int(m.group(1)) - 1, int(m.group(2)) - 1] = v
+    out["tauaero/aestrat/aerstr"] = aer
+    # spectra.f: wmn / wmx of every sensor filter routine (spectra.f:3420-4430)
+    unit = None
+    for ln in logical_lines(os.path.join(REF, "spectra.f")):
+        low = ln.strip().lower()
+        m = re.match(r"^subroutine\s+(\w+)\s*\(srr,wmin,wmax,nnf\)", low)
+        if m:
+            unit = m.group(1)
+            continue
+        m = re.match(r"^real\(kr\),\s*parameter\s*::\s*wmn=([\d.]+)\s*,\s*wmx=([\d.]+)", low)
+        if m and unit:
+            out[f"spectra/{unit}/wmn"] = np.array(float(np.float32(float(m.group(1)))))
+            out[f"spectra/{unit}/wmx"] = np.array(float(np.float32(float(m.group(2)))))
+            unit = None
+    return out
+
+
 def main():
     dst = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
                        "sbdart_b200", "frontend", "tables.npz")
@@ -302,6 +338,9 @@ def main():
         t = extract_file(os.path.join(REF, f))
         print(f, len(t), "tables,", sum(v.size for v in t.values()), "values")
         allt.update(t)
+    ex = extract_extras()
+    print("extras", len(ex), "tables")
+    allt.update(ex)
     np.savez_compressed(dst, **allt)
     print("wrote", dst, os.path.getsize(dst) // 1024, "KiB")
 
