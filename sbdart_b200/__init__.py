@@ -31,7 +31,7 @@ EXPORTS = (
     "sbd_synchronize", "sbd_stream", "sbd_kernel_launches", "sbd_quadrature",
     "sbd_status_string", "sbd_abi_version", "disort_", "sbd_disort_last_status",
     "sbd_measure_fp64_peak", "sbd_optics_upload_tables", "sbd_spectrum_run",
-    "sbd_set_radiance_levels",
+    "sbd_set_radiance_levels", "sbd_spectrum_set_aerosols",
 )
 
 
