@@ -135,6 +135,14 @@ int sbd_synchronize(sbd_handle *h);
  * zeros.  Fluxes are not affected. */
 int sbd_set_radiance_levels(sbd_handle *h, const int32_t *levels, int32_t n);
 
+/* CORINT of DISORT (disort.f:112-118, INTCOR disort.f:2044-2297) for the following
+ * batched radiance calls on this handle: 0 (default) off, 1 on.  When on, the
+ * Nakajima-Tanaka TMS and IMS corrections are added to uu after the solve; pmom
+ * should then carry the full phase function (SBDART passes nmom = 299,
+ * drt.f:490-491).  As in the reference it has no effect on flux-only calls, for
+ * fbeam = 0 and for non-scattering media (disort.f:2695-2696). */
+int sbd_set_corint(sbd_handle *h, int32_t on);
+
 /* cudaStream_t of the handle (as void*), for event timing by the caller. */
 void *sbd_stream(sbd_handle *h);
 

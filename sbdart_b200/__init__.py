@@ -31,7 +31,7 @@ EXPORTS = (
     "sbd_synchronize", "sbd_stream", "sbd_kernel_launches", "sbd_quadrature",
     "sbd_status_string", "sbd_abi_version", "disort_", "sbd_disort_last_status",
     "sbd_measure_fp64_peak", "sbd_optics_upload_tables", "sbd_spectrum_run",
-    "sbd_set_radiance_levels", "sbd_spectrum_set_aerosols",
+    "sbd_set_radiance_levels", "sbd_spectrum_set_aerosols", "sbd_set_corint",
 )
 
 
@@ -97,6 +97,8 @@ def lib():
     L.sbd_status_string.restype = C.c_char_p
     L.sbd_status_string.argtypes = [C.c_int]
     L.sbd_abi_version.restype = C.c_int
+    L.sbd_set_corint.restype = C.c_int
+    L.sbd_set_corint.argtypes = [C.c_void_p, C.c_int32]
     L.sbd_set_radiance_levels.restype = C.c_int
     L.sbd_set_radiance_levels.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
     L.sbd_measure_fp64_peak.restype = C.c_int
@@ -186,7 +188,7 @@ class Solver:
             raise SbdError(rc, "sbd_set_radiance_levels")
 
     def disort_batch(self, dtauc, ssalb, pmom, bins, *, nstr, temper=None, utau=None,
-                     umu=None, phi=None, out=None, uu_levels=None):
+                     umu=None, phi=None, out=None, uu_levels=None, corint=False):
         """Batched DISORT on host arrays.
 
         dtauc, ssalb [B][L]; pmom [B][L][nmom+1]; bins = make_bins(...);
@@ -223,6 +225,8 @@ class Solver:
         p = lambda a: None if a is None else a.ctypes.data  # noqa: E731
         if uu_levels is not None:
             self.set_radiance_levels(uu_levels)
+        if corint:          # CORINT=.TRUE.: Nakajima-Tanaka corrections after the solve
+            lib().sbd_set_corint(self._h, 1)
         try:
             rc = lib().sbd_disort_batch(
                 self._h, C.byref(d), p(dtauc), p(ssalb), p(pmom), p(bins), p(tp), p(ut), p(um),
@@ -231,6 +235,8 @@ class Solver:
         finally:
             if uu_levels is not None:
                 self.set_radiance_levels(None)
+            if corint:
+                lib().sbd_set_corint(self._h, 0)
         if rc:
             raise SbdError(rc, "sbd_disort_batch")
         return out

@@ -186,6 +186,13 @@ extern "C" int sbd_set_radiance_levels(sbd_handle *h, const int32_t *levels, int
     return SBD_SUCCESS;
 }
 
+extern "C" int sbd_set_corint(sbd_handle *h, int32_t on)
+{
+    if (!h) return SBD_ERR_ARG;
+    h->corint = on != 0;
+    return SBD_SUCCESS;
+}
+
 extern "C" void *sbd_stream(sbd_handle *h) { return h ? (void *)h->stream : nullptr; }
 
 extern "C" int64_t sbd_kernel_launches(const sbd_handle *h) { return h ? h->launches : 0; }
@@ -312,6 +319,12 @@ extern "C" int sbd_disort_batch_device(sbd_handle *h, const sbd_dims *dims, cons
     cudaError_t le = fast ? launch_fast(a, warps, grid, st) : launch_generic(a, warps, grid, st);
     if (le != cudaSuccess) return SBD_ERR_CUDA;
     h->launches += 1;
+    if (NU > 0 && h->corint) {         // INTCOR (disort.f:827-835): layer boundaries only
+        if (dims->ntau > 0) return SBD_ERR_UNSUPPORTED;
+        if (intcor_smem_bytes(L, dims->nmom) > smem_limit) return SBD_ERR_UNSUPPORTED;
+        if (launch_intcor(a, st) != cudaSuccess) return SBD_ERR_CUDA;
+        h->launches += 1;
+    }
     return SBD_SUCCESS;
 }
 
@@ -469,9 +482,8 @@ extern "C" void disort_(int *nlyr, double *dtauc, double *ssalb, int *corint, in
     const int L = *nlyr, N = *nstr;
     const bool rad = !*onlyfl;
     // outside the hot path: IBCND=1, BRDF surfaces, intensities at the quadrature
-    // angles (USRANG=F, never used by SBDART) and the CORINT correction when it
-    // would be active (disort.f:2695-2696)
-    if (*ibcnd != 0 || !*lamber || (rad && !*usrang) || (rad && *corint && *fbeam > 0.0)) {
+    // angles (USRANG=F, never used by SBDART), CORINT with user levels
+    if (*ibcnd != 0 || !*lamber || (rad && !*usrang) || (rad && *corint && *usrtau)) {
         g_last_status = SBD_ERR_UNSUPPORTED;
         return;
     }
@@ -499,9 +511,11 @@ extern "C" void disort_(int *nlyr, double *dtauc, double *ssalb, int *corint, in
     if (NT > *maxulv) { g_last_status = SBD_ERR_ARG; return; }
     int32_t st = 0;
     std::vector<double> uuc(rad ? (size_t)d.nphi * NT * d.numu : 0);
+    g_handle->corint = rad && *corint;
     int rc = sbd_disort_batch(g_handle, &d, dtauc, ssalb, pm.data(), &b, temper,
                               *usrtau ? utau : nullptr, rad ? umu : nullptr, rad ? phi : nullptr,
                               rfldir, rfldn, flup, dfdt, uavg, rad ? uuc.data() : nullptr, &st);
+    g_handle->corint = false;
     g_last_status = rc ? rc : st;
     if (rc) return;
     if (rad)      // UU(IU,LU,J), leading dimensions MAXUMU, MAXULV (disort.f:377)

@@ -54,6 +54,7 @@ struct sbd_handle {
     SbdDevBuf opt_tables, opt_atm, opt_misc, opt_map, opt_aero;
     sbd_aerosol_params aero = {};             // aerosols of the next spectrum runs
     bool aero_on = false;
+    bool corint = false;                      // INTCOR after radiance launches (sbd_set_corint)
     sbd::OpticsTables opt_index = {};
     bool opt_ready = false;
     const int32_t *pending_binmap = nullptr;   // device bin -> slot map for the next solve launch

@@ -65,6 +65,10 @@ int generic_pick_warps(int N, int L, int NT, size_t smem_limit);
 cudaError_t launch_generic(const LaunchArgs &a, int warps, int grid,
                            cudaStream_t st);
 
+// Nakajima-Tanaka intensity corrections after a radiance launch (sbd_intcor.cu)
+size_t intcor_smem_bytes(int L, int nmom);
+cudaError_t launch_intcor(const LaunchArgs &a, cudaStream_t st);
+
 // register-resident kernel for NSTR in {4, 8, 16} (sbd_fast.cu)
 bool fast_supported(int N);
 int fast_warps();

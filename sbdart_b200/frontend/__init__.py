@@ -36,7 +36,7 @@ PZERO, TZERO, RE = f32(1013.25), f32(273.15), f32(6371.2)
 PMO, GRAV, ALOSCH = f32(2.6568e-23), f32(9.80665), f32(2.6868e19)
 ZIP = -1.0
 PI_KR = 3.1415926536
-MXLY, NSTRMS, NCLDZ, MXQ = 65, 40, 5, 63
+MXLY, NSTRMS, NCLDZ, MXQ, MAXMOM = 65, 40, 5, 63, 299
 
 
 def tables():
@@ -1177,7 +1177,7 @@ class Sbdart:
         nstr = p["nstr"]
         nmom = min(nstr + 2, NSTRMS)
         if self.radcalc and p["corint"]:
-            raise NotImplementedError("corint")
+            nmom = MAXMOM                 # the full phase function for INTCOR (drt.f:490-491)
         rows = []
         for il in range(self.nwl):
             wl, wvnmhi, wvnmlo = wllimits(il, self.nwl, self.wlinc, self.wl1, self.wl2)
@@ -1233,6 +1233,7 @@ class Sbdart:
                  nstr=self.p["nstr"], group=g("il"))
         if self.radcalc:
             d["umu"], d["phi"] = self.umu, self.phi
+            d["corint"] = bool(self.p["corint"])
             # output levels whose intensities the records consume (drt.f:1008-1016,
             # :1143-1151): iout 5/20 the top level, 6/21 the bottom, 23 both
             iout = self.p["iout"]
@@ -1262,17 +1263,17 @@ class Sbdart:
         from .device import device_aerosols_supported, run_spectrum
         host_solve = lambda b: solver.disort_batch(  # noqa: E731
             b["dtauc"], b["ssalb"], b["pmom"], b["bins"], nstr=b["nstr"], temper=b["temper"],
-            umu=b.get("umu"), phi=b.get("phi"), uu_levels=b.get("uu_levels"))
-        if not device_aerosols_supported(self.aerosols) or self.p["imomc"] not in (2, 3):
-            # table phase functions (getmom 4/5, pmaer): optical properties on the host, solve on the GPU
+            umu=b.get("umu"), phi=b.get("phi"), uu_levels=b.get("uu_levels"), corint=b.get("corint", False))
+        if (not device_aerosols_supported(self.aerosols) or self.p["imomc"] not in (2, 3) or
+                (self.radcalc and self.p["corint"])):
+            # table phase functions (getmom 4/5, pmaer) and the 299-moment CORINT runs:
+            # optical properties on the host, solve on the GPU
             return self.run(host_solve)
         rows, res = run_spectrum(self, solver)
         if (res["status"] != 0).any():
             # beam / quadrature clash (drt.f:536-554): fall back to the host-side batch
             # for the retry logic (rare: one NSTR-dependent angle)
-            return self.run(lambda b: solver.disort_batch(
-                b["dtauc"], b["ssalb"], b["pmom"], b["bins"], nstr=b["nstr"], temper=b["temper"],
-                umu=b.get("umu"), phi=b.get("phi"), uu_levels=b.get("uu_levels")))
+            return self.run(host_solve)
         return self.records(rows, res)
 
     def records(self, rows, res):

@@ -20,7 +20,7 @@ def solve_oracle(b, nthreads=8):
             phi0=bins["phi0"][i], fisot=bins["fisot"][i], albedo=bins["albedo"][i],
             btemp=bins["btemp"][i], ttemp=bins["ttemp"][i], temis=bins["temis"][i],
             wvnmlo=bins["wvnmlo"][i], wvnmhi=bins["wvnmhi"][i], plank=bool(bins["plank"][i]),
-            onlyfl=False)
+            onlyfl=False, corint=b.get("corint", False))
         for k in outs:
             outs[k].append(r[k])
     return {k: np.array(v) for k, v in outs.items()}
@@ -29,5 +29,6 @@ def solve_oracle(b, nthreads=8):
 def make_solve_cuda(solver):
     def solve(b):
         return solver.disort_batch(b["dtauc"], b["ssalb"], b["pmom"], b["bins"], nstr=b["nstr"],
-                                   temper=b["temper"], umu=b.get("umu"), phi=b.get("phi"), uu_levels=b.get("uu_levels"))
+                                   temper=b["temper"], umu=b.get("umu"), phi=b.get("phi"), uu_levels=b.get("uu_levels"),
+                                   corint=b.get("corint", False))
     return solve

@@ -69,11 +69,59 @@ def run(name, w, solver, reps=3, nsample=64, **kw):
           flush=True)
 
 
+def namelist_workload(nl):
+    """Bins of a real SBDART run (front end on the host): the BASELINE.json namelists."""
+    from sbdart_b200.frontend import Sbdart
+    t0 = time.perf_counter()
+    r = Sbdart(nl)
+    b = r.batch(r.bins())
+    b["frontend_s"] = time.perf_counter() - t0
+    b["run"] = r
+    return b
+
+
+def run_namelists(s, quick):
+    """C3 and C4 exactly as BASELINE.md section 2 writes them, plus the whole-run
+    time of the device front end (K2 + solve + records) for the same namelist."""
+    from sbdart_b200.frontend import Sbdart
+    uz = ",".join(str(x) for x in np.linspace(5.0, 85.0, 10))
+    cases = [
+        ("C3 namelist thermal night (M=1), iout=20, 10 zenith angles",
+         f"&INPUT idatm=2, wlinf=4, wlsup=80, wlinc=20, nstr=8, iout=20, uzen={uz}, sza=95 /", 64),
+        ("C3 namelist sunlit (M=8 azimuth modes), iout=20, 10 zenith angles",
+         f"&INPUT idatm=2, wlinf=4, wlsup=80, wlinc=20, nstr=8, iout=20, uzen={uz}, sza=30 /", 64),
+        ("C4 namelist nstr32 ngrid65 stratus + rural aerosol, 0.25-100 um at 20 cm-1",
+         "&INPUT idatm=2, nstr=32, ngrid=65, tcloud=10, zcloud=1, iaer=1, vis=23, wlinf=.25, wlsup=100, wlinc=20,"
+         " iout=10 /", 8),
+    ]
+    for name, nl, rep in cases:
+        w = namelist_workload(nl)
+        kw = {}
+        if "umu" in w:
+            kw = dict(umu=w["umu"], phi=w["phi"], uu_levels=w.get("uu_levels"))
+        wt = tile({k: w[k] for k in ("dtauc", "ssalb", "pmom", "bins")}, max(1, rep // (4 if quick else 1)))
+        wt["nstr"], wt["temper"] = w["nstr"], w["temper"]
+        run(name + f" (x{len(wt['bins']) // len(w['bins'])})", wt, s, nsample=32, **kw)
+        t = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            txt = Sbdart(nl).run_device(s)
+            t.append(time.perf_counter() - t0)
+        print(json.dumps({"config": name, "whole_run_device_front_end_s": min(t), "bins": len(w["bins"]),
+                          "host_front_end_s": w["frontend_s"], "record": txt.splitlines()[0 if "iout=10" in nl else 0][:120]}),
+              flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--namelists", action="store_true", help="only the real-namelist C3 / C4 runs")
     a = ap.parse_args()
     s = sb.Solver(0)
+    if a.namelists:
+        run_namelists(s, a.quick)
+        s.close()
+        return
     q = 8 if a.quick else 1
     # C1: NSTR=4, 33 layers, 151 wavelengths (x k-terms), replicated
     w = workloads.mls_shortwave(nstr=4, wlinf=0.25, wlsup=1.0, wlinc=0.005)
