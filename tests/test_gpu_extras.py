@@ -78,8 +78,8 @@ def test_whole_runs_match_the_cpu_checker(nl):
         scale = np.abs(r_cpu["flup"]).max(axis=1, keepdims=True) + np.abs(r_cpu["rfldn"]).max(axis=1, keepdims=True) \
             + np.abs(r_cpu["rfldir"]).max(axis=1, keepdims=True)
         # floor: 2e-8 of the bin's flux scale (NSTR=32 with 65 layers leaves ~7e-9 of round-off on
-            # fluxes that are 1e-7 of the bin maximum; the NSTR <= 16 cases sit below 1e-10)
-            assert (np.abs(r_gpu[k] - r_cpu[k]) <= 1e-5 * np.abs(r_cpu[k]) + 2e-8 * scale).all(), k
+        # fluxes that are 1e-7 of the bin maximum; the NSTR <= 16 cases sit below 1e-10)
+        assert (np.abs(r_gpu[k] - r_cpu[k]) <= 1e-5 * np.abs(r_cpu[k]) + 2e-8 * scale).all(), k
     assert s.kernel_launches >= 3
     s.close()
 
