@@ -1293,6 +1293,7 @@ class Sbdart:
         weq = wfull = phidw = 0.0
         fxdn, fxup, fxdir = np.zeros(nz), np.zeros(nz), np.zeros(nz)
         uurs = np.zeros((self.nzen, self.nphi)) if self.radcalc else None
+        uurl = np.zeros((self.nphi, self.nzen, nz)) if iout == 22 else None
         for ib, r in enumerate(rows):
             rfldir, rfldn, flup = res["rfldir"][ib], res["rfldn"][ib], res["flup"][ib]
             dwt = r["wt"] * r["ff"]
@@ -1349,6 +1350,8 @@ class Sbdart:
             if iout in (20, 21):
                 j = ntop if iout == 20 else nbot
                 uurs += res["uu"][ib][:, j, :].T * dwt
+            if iout == 22:          # radiance at every level (drt.f:1065-1073)
+                uurl += np.transpose(res["uu"][ib][:, 1:nz + 1, :], (0, 2, 1)) * dwt
             if iout == 23:
                 for i in range(self.nzen):
                     j = ntop if self.uzen[self.nzen - 1 - i] < 90. else nbot
@@ -1378,6 +1381,15 @@ class Sbdart:
             out += self._rows(self.uzen, 10)
             for i in range(self.nzen - 1, -1, -1):
                 out += self._rows([_r4(x) for x in uurs[i]], 20)
+        if iout == 22:              # drt.f:1153-1163
+            out.append(f"{self.nphi:4d}{self.nzen:4d}{nz:4d}" + _es(phidw, 12, 4))
+            out += self._rows(self.phi, 10)
+            out += self._rows(self.uzen, 10)
+            out += self._rows(self.z[::-1], 10)
+            for arr in (fxdn, fxup, fxdir):
+                out += self._rows([_r4(x) for x in arr], 10)
+            out += self._rows([_r4(uurl[i, j, k]) for k in range(nz) for j in range(self.nzen - 1, -1, -1)
+                               for i in range(self.nphi)], 10)
         self.last = dict(rows=rows, result=res if rows else None)
         return "\n".join(out) + "\n"
 

@@ -232,3 +232,31 @@ def test_c4_namelist_builds_bins():
     assert (res["status"] == 0).all()
     txt = run.records(rows, res)
     assert len(txt.split()) == 9
+
+
+def test_iout22_holds_the_iout20_and_iout21_radiances():
+    """iout=22 prints fluxes and radiances at every level (drt.f:1153-1163); its first and last
+    level blocks are the iout=20 (top) and iout=21 (bottom) radiance tables."""
+    base = "&INPUT idatm=2, nstr=8, wlinf=.55, wlsup=.56, wlinc=.01, sza=30, uzen=10,100,170, phi=0,90, iout={} /"
+    t22, t20, t21 = (Sbdart(base.format(i)).run(solve_oracle).split() for i in (22, 20, 21))
+    assert t22[:3] == ["2", "3", "33"]
+    nz = 33
+    uurl = t22[4 + 2 + 3 + 4 * nz:]
+    assert len(uurl) == 2 * 3 * nz
+    assert uurl[:6] == t20[-6:] and uurl[-6:] == t21[-6:]
+    z = [float(x) for x in t22[9:9 + nz]]
+    assert z[0] == 100.0 and z[-1] == 0.0
+    fxdn = [float(x) for x in t22[9 + nz:9 + 2 * nz]]
+    assert fxdn[0] == pytest.approx(float(t20[3]), rel=1e-4) and fxdn[-1] == pytest.approx(float(t20[6]), rel=1e-4)
+
+
+def test_corint_restores_the_aureole():
+    """CORINT=.TRUE. (299 moments, INTCOR): the forward peak the delta-M truncation removes comes
+    back near the solar direction; far from it and in the fluxes nothing changes much."""
+    base = ("&INPUT idatm=2, nstr=8, tcloud=2, zcloud=2, wlinf=.55, wlsup=.55, sza=30, iout=21,"
+            " uzen=100,151,175, phi=0,180, corint={} /")
+    off, on = (Sbdart(base.format(c)).run(solve_oracle).split() for c in ("f", "t"))
+    assert off[:9] == on[:9]                                   # the flux record
+    r_off, r_on = [float(x) for x in off[-6:]], [float(x) for x in on[-6:]]
+    assert r_on[2] > 2.5 * r_off[2]                            # uzen=151, phi=0: one degree from the sun
+    assert abs(r_on[3] / r_off[3] - 1) < 0.15                  # same zenith angle, opposite azimuth
