@@ -46,6 +46,21 @@ module sbd_b200
        integer(c_int32_t), intent(out) :: status(*)
      end function sbd_disort_batch
 
+     ! CORINT (disort.f:112-118): Nakajima-Tanaka corrections on the following radiance calls
+     integer(c_int) function sbd_set_corint(h, on) bind(c, name='sbd_set_corint')
+       import :: c_ptr, c_int, c_int32_t
+       type(c_ptr), value :: h
+       integer(c_int32_t), value :: on
+     end function sbd_set_corint
+
+     ! intensities only at these output levels (ntop / nbot of drt.f:1008-1016)
+     integer(c_int) function sbd_set_radiance_levels(h, levels, n) bind(c, name='sbd_set_radiance_levels')
+       import :: c_ptr, c_int, c_int32_t
+       type(c_ptr), value :: h
+       integer(c_int32_t), intent(in) :: levels(*)
+       integer(c_int32_t), value :: n
+     end function sbd_set_radiance_levels
+
      integer(c_int) function sbd_synchronize(h) bind(c, name='sbd_synchronize')
        import
        type(c_ptr), value :: h

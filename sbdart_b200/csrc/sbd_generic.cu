@@ -68,7 +68,7 @@ __host__ __device__ inline size_t cta_shared_doubles(int N)
 __host__ __device__ inline size_t warp_shared_doubles(int N, int L, int NT)
 {
     int n = N / 2;
-    size_t o = 2 * N + 6 * (size_t)n * n + 2 * (2 * n + 2 * (size_t)n * n + 2 * N) +
+    size_t o = 2 * N + 4 * (size_t)n * n + 2 * (size_t)n * (n | 1) + 2 * (2 * n + 2 * (size_t)n * n + 2 * N) +
                (size_t)(n + N) * (2 * N + 1) + 2 * N + 4 * N + 3 * (size_t)(L + 1) +
                (n + 2);
     size_t ints = (size_t)NT + (n + 2);
@@ -102,8 +102,8 @@ __device__ void carve(double *base, int N, int L, int NT, WarpShared &w)
     w.y0 = p; p += N;
     w.Pe = p; p += n * n;
     w.Lo = p; p += n * n;
-    w.T = p; p += n * n;
-    w.V = p; p += n * n;
+    w.T = p; p += n * (n | 1);     // T and V: odd leading dimension (column walks of the
+    w.V = p; p += n * (n | 1);     // Jacobi rotations would otherwise hit one bank pair)
     w.X = p; p += n * n;
     w.P = p; p += n * n;
     for (int s = 0; s < 2; s++) {
@@ -129,6 +129,34 @@ __device__ void carve(double *base, int N, int L, int NT, WarpShared &w)
     w.pq = w.layru + NT;
 }
 
+
+// The structs above hold generic pointers; the device functions below are too large to be
+// inlined, so the compiler cannot see that every one of them points into shared memory and
+// emits generic LD/ST (slower, and tracked on the long scoreboard).  These hints restore
+// LDS/STS.  (Wrapping the dynamically indexed buffer pointers w.Gp[s] ... in a hinting helper
+// at every use miscompiled the radiance path with nvcc 12.9, so those stay generic.)
+#define SBD_SHARED(p) __builtin_assume(__isShared(p))
+
+__device__ __forceinline__ void hint_shared(const CtaShared &cs)
+{
+    // cs.ylm is NOT hinted: it points to global memory for azimuth modes m > 0
+    SBD_SHARED(cs.mu); SBD_SHARED(cs.wt); SBD_SHARED(cs.sq); SBD_SHARED(cs.dinv);
+}
+__device__ __forceinline__ void hint_shared(const WarpShared &w)
+{
+    SBD_SHARED(w.gl); SBD_SHARED(w.y0);
+    SBD_SHARED(w.Pe); SBD_SHARED(w.Lo); SBD_SHARED(w.T); SBD_SHARED(w.V); SBD_SHARED(w.X); SBD_SHARED(w.P);
+#pragma unroll
+    for (int s = 0; s < 2; s++) {
+        SBD_SHARED(w.kk[s]); SBD_SHARED(w.ek[s]); SBD_SHARED(w.Gp[s]); SBD_SHARED(w.Gm[s]);
+        SBD_SHARED(w.zz[s]); SBD_SHARED(w.zp0[s]);
+    }
+    SBD_SHARED(w.W); SBD_SHARED(w.xn); SBD_SHARED(w.xc);
+    SBD_SHARED(w.v1); SBD_SHARED(w.v2); SBD_SHARED(w.v3); SBD_SHARED(w.v4);
+    SBD_SHARED(w.taucpr); SBD_SHARED(w.tauc); SBD_SHARED(w.pk);
+    SBD_SHARED(w.layru); SBD_SHARED(w.cs); SBD_SHARED(w.pq);
+}
+
 // per-bin scalars held in registers by every lane
 struct BinCtx {
     int N, n, L, NT, ncut, lyrcut, plank, mazim;
@@ -147,6 +175,8 @@ __device__ int solve_layer(const BinCtx &c, const CtaShared &cs, WarpShared &w,
                            int lc, int s, double &xr0, double &xr1, int lane)
 {
     const int N = c.N, n = c.n, m = c.mazim;
+    const int ldt = n | 1;                             // leading dimension of T and V
+    hint_shared(cs); hint_shared(w);
     double ss = c.ssalb[lc];
     if (ss == 1.0) ss = 1.0 - kDither;                 // disort.f:486
     double dt = c.dtauc[lc];
@@ -215,8 +245,8 @@ __device__ int solve_layer(const BinCtx &c, const CtaShared &cs, WarpShared &w,
     __syncwarp();
     for (int e = lane; e < n * n; e += 32) {
         int i = e / n, j = e - i * n;
-        w.T[e] = 0.5 * (w.P[i * n + j] + w.P[j * n + i]);
-        w.V[e] = (i == j) ? 1.0 : 0.0;
+        w.T[i * ldt + j] = 0.5 * (w.P[i * n + j] + w.P[j * n + i]);
+        w.V[i * ldt + j] = (i == j) ? 1.0 : 0.0;
     }
     __syncwarp();
 
@@ -225,7 +255,7 @@ __device__ int solve_layer(const BinCtx &c, const CtaShared &cs, WarpShared &w,
         const int mm = (n & 1) ? n + 1 : n;    // players in the tournament
         const int np = mm / 2;
         double tr = 0.0;
-        for (int i = lane; i < n; i += 32) tr += fabs(w.T[i * n + i]);
+        for (int i = lane; i < n; i += 32) tr += fabs(w.T[i * ldt + i]);
         const double floor_abs = 1.0e-19 * warp_sum(tr);
         int sweep = 0;
         for (; sweep < 60; sweep++) {
@@ -239,7 +269,7 @@ __device__ int solve_layer(const BinCtx &c, const CtaShared &cs, WarpShared &w,
                     if (p > q) { int t = p; p = q; q = t; }
                     double cc = 1.0, sn = 0.0;
                     if (q < n) {
-                        double apq = w.T[p * n + q], app = w.T[p * n + p], aqq = w.T[q * n + q];
+                        double apq = w.T[p * ldt + q], app = w.T[p * ldt + p], aqq = w.T[q * ldt + q];
                         if (fabs(apq) > floor_abs &&
                             fabs(apq) > 1.1e-16 * sqrt(fabs(app) * fabs(aqq))) {
                             double th = (aqq - app) / (2.0 * apq);
@@ -261,12 +291,12 @@ __device__ int solve_layer(const BinCtx &c, const CtaShared &cs, WarpShared &w,
                     int p = w.pq[2 * k], q = w.pq[2 * k + 1];
                     if (p != q) {
                         double cc = w.cs[2 * k], sn = w.cs[2 * k + 1];
-                        double a = w.T[i * n + p], b = w.T[i * n + q];
-                        w.T[i * n + p] = cc * a - sn * b;
-                        w.T[i * n + q] = sn * a + cc * b;
-                        a = w.V[i * n + p]; b = w.V[i * n + q];
-                        w.V[i * n + p] = cc * a - sn * b;
-                        w.V[i * n + q] = sn * a + cc * b;
+                        double a = w.T[i * ldt + p], b = w.T[i * ldt + q];
+                        w.T[i * ldt + p] = cc * a - sn * b;
+                        w.T[i * ldt + q] = sn * a + cc * b;
+                        a = w.V[i * ldt + p]; b = w.V[i * ldt + q];
+                        w.V[i * ldt + p] = cc * a - sn * b;
+                        w.V[i * ldt + q] = sn * a + cc * b;
                     }
                 }
                 __syncwarp();
@@ -276,9 +306,9 @@ __device__ int solve_layer(const BinCtx &c, const CtaShared &cs, WarpShared &w,
                     int p = w.pq[2 * k], q = w.pq[2 * k + 1];
                     if (p != q) {
                         double cc = w.cs[2 * k], sn = w.cs[2 * k + 1];
-                        double a = w.T[p * n + j], b = w.T[q * n + j];
-                        w.T[p * n + j] = cc * a - sn * b;
-                        w.T[q * n + j] = sn * a + cc * b;
+                        double a = w.T[p * ldt + j], b = w.T[q * ldt + j];
+                        w.T[p * ldt + j] = cc * a - sn * b;
+                        w.T[q * ldt + j] = sn * a + cc * b;
                     }
                 }
                 __syncwarp();
@@ -290,14 +320,14 @@ __device__ int solve_layer(const BinCtx &c, const CtaShared &cs, WarpShared &w,
 
     // k_j = sqrt(|lambda_j|)  (disort.f:3264-3269)
     for (int j = lane; j < n; j += 32) {
-        double k = sqrt(fabs(w.T[j * n + j]));
+        double k = sqrt(fabs(w.T[j * ldt + j]));
         w.kk[s][j] = k;
         w.ek[s][j] = exp(-k * dtaucp);
     }
     // Q = L^-T V (into X), P = L V
     for (int j = lane; j < n; j += 32) {
         for (int i = n - 1; i >= 0; i--) {
-            double a = w.V[i * n + j];
+            double a = w.V[i * ldt + j];
             for (int k = i + 1; k < n; k++) a -= w.Lo[k * n + i] * w.X[k * n + j];
             w.X[i * n + j] = a / w.Lo[i * n + i];
         }
@@ -305,7 +335,7 @@ __device__ int solve_layer(const BinCtx &c, const CtaShared &cs, WarpShared &w,
     for (int e = lane; e < n * n; e += 32) {
         int i = e / n, j = e - i * n;
         double a = 0.0;
-        for (int k = 0; k <= i; k++) a += w.Lo[i * n + k] * w.V[k * n + j];
+        for (int k = 0; k <= i; k++) a += w.Lo[i * n + k] * w.V[k * ldt + j];
         w.P[e] = a;
     }
     __syncwarp();
@@ -349,15 +379,15 @@ __device__ int solve_layer(const BinCtx &c, const CtaShared &cs, WarpShared &w,
         __syncwarp();
         for (int j = lane; j < n; j += 32) {
             double a = 0.0;
-            for (int k = 0; k < n; k++) a += w.V[k * n + j] * w.v4[k];
-            double den = rmu0 * rmu0 - w.T[j * n + j];
+            for (int k = 0; k < n; k++) a += w.V[k * ldt + j] * w.v4[k];
+            double den = rmu0 * rmu0 - w.T[j * ldt + j];
             w.v3[j] = a / den;
         }
         __syncwarp();
         // y = V c
         for (int i = lane; i < n; i += 32) {
             double a = 0.0;
-            for (int k = 0; k < n; k++) a += w.V[i * n + k] * w.v3[k];
+            for (int k = 0; k < n; k++) a += w.V[i * ldt + k] * w.v3[k];
             w.v4[i] = a;
         }
         __syncwarp();
@@ -419,6 +449,7 @@ __device__ int solve_layer(const BinCtx &c, const CtaShared &cs, WarpShared &w,
 __device__ __forceinline__ double gc_elem(const double *Gp, const double *Gm,
                                           int n, int r, int j)
 {
+    SBD_SHARED(Gp); SBD_SHARED(Gm);
     if (r >= n) {
         int i = r - n;
         return (j >= n) ? Gp[i * n + (j - n)] : -Gm[i * n + (n - 1 - j)];
@@ -433,6 +464,7 @@ __device__ void store_layer(const LayerLayout &ll, double *rec, const WarpShared
                             int s, double xr0, double xr1, int lane)
 {
     const int n = ll.n, N = ll.N;
+    hint_shared(w);
     for (int e = lane; e < n; e += 32) { rec[ll.off_kk + e] = w.kk[s][e]; rec[ll.off_ek + e] = w.ek[s][e]; }
     for (int e = lane; e < n * n; e += 32) { rec[ll.off_gp + e] = w.Gp[s][e]; rec[ll.off_gm + e] = w.Gm[s][e]; }
     for (int e = lane; e < N; e += 32) { rec[ll.off_zz + e] = w.zz[s][e]; rec[ll.off_zp0 + e] = w.zp0[s][e]; }
@@ -443,6 +475,7 @@ __device__ void load_layer(const LayerLayout &ll, const double *rec, WarpShared 
                            int s, double &xr0, double &xr1, int lane)
 {
     const int n = ll.n, N = ll.N;
+    hint_shared(w);
     for (int e = lane; e < n; e += 32) { w.kk[s][e] = rec[ll.off_kk + e]; w.ek[s][e] = rec[ll.off_ek + e]; }
     for (int e = lane; e < n * n; e += 32) { w.Gp[s][e] = rec[ll.off_gp + e]; w.Gm[s][e] = rec[ll.off_gm + e]; }
     for (int e = lane; e < N; e += 32) { w.zz[s][e] = rec[ll.off_zz + e]; w.zp0[s][e] = rec[ll.off_zp0 + e]; }
@@ -454,6 +487,7 @@ __device__ void load_layer(const LayerLayout &ll, const double *rec, WarpShared 
 // returns 0 or SBD_BIN_SINGULAR
 __device__ int eliminate(double *W, int rows, int C, int ncols, int lane)
 {
+    SBD_SHARED(W);
     for (int j = 0; j < ncols; j++) {
         // pivot search in column j among rows j..rows-1
         double best = -1.0; int bi = j;
@@ -477,10 +511,22 @@ __device__ int eliminate(double *W, int rows, int C, int ncols, int lane)
         }
         __syncwarp();
         const double rp = 1.0 / W[j * C + j];
-        // lanes over columns, loop over rows
+        // lanes over columns, loop over rows; four rows per trip with all loads ahead of the
+        // stores (the compiler cannot prove that a store to column cidx leaves column j alone,
+        // so the plain loop is one load -> FMA -> store latency chain per row)
         for (int cidx = j + 1 + lane; cidx < C; cidx += 32) {
             const double pv = W[j * C + cidx];
-            for (int r = j + 1; r < rows; r++) {
+            int r = j + 1;
+            for (; r + 3 < rows; r += 4) {
+                double *p0 = W + r * C;
+                const double m0 = p0[j], m1 = p0[C + j], m2 = p0[2 * C + j], m3 = p0[3 * C + j];
+                const double v0 = p0[cidx], v1 = p0[C + cidx], v2 = p0[2 * C + cidx], v3 = p0[3 * C + cidx];
+                p0[cidx] = v0 - (m0 * rp) * pv;
+                p0[C + cidx] = v1 - (m1 * rp) * pv;
+                p0[2 * C + cidx] = v2 - (m2 * rp) * pv;
+                p0[3 * C + cidx] = v3 - (m3 * rp) * pv;
+            }
+            for (; r < rows; r++) {
                 double mlt = W[r * C + j] * rp;
                 W[r * C + cidx] -= mlt * pv;
             }
@@ -494,6 +540,7 @@ __device__ int eliminate(double *W, int rows, int C, int ncols, int lane)
 // mode by mode, with the diagonal term in closed-chain form.
 __device__ void lepoly_one(int m, int N, double x, double *y)
 {
+    SBD_SHARED(y);
     if (m == 0) {
         y[0] = 1.0;
         if (N > 1) y[1] = x;
@@ -525,6 +572,7 @@ __device__ void user_terms(const BinCtx &c, const CtaShared &cs, WarpShared &w,
                            int lc, int s, double xr0, double xr1, int lane)
 {
     const int N = c.N, n = c.n, m = c.mazim;
+    hint_shared(cs); hint_shared(w);
     double ss = c.ssalb[lc];
     if (ss == 1.0) ss = 1.0 - kDither;
     const double f = c.pmom[(size_t)lc * c.ldp + N];
@@ -607,6 +655,7 @@ __device__ double usrint_one(const BinCtx &c, const WarpShared &w, const LayerLa
                              double fisot, double bnd_up /* surface term without the exp */)
 {
     const int N = c.N, n = c.n, m = c.mazim, ncut = c.ncut, L = c.L;
+    hint_shared(w);
     const int lyu = w.layru[lu];
     if (c.lyrcut && lyu > ncut) return 0.0;
     const bool negumu = umu < 0.0;
@@ -730,6 +779,7 @@ disort_generic_kernel(const LaunchArgs a)
     const int NTs = NT > 8 ? NT : 8;
     carve(smem_dyn + cta_shared_doubles(N) + (size_t)warp * warp_shared_doubles(N, L, NTs),
           N, L, NTs, w);
+    hint_shared(cs); hint_shared(w);
 
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         double mu = a.quad[i], wt = a.quad[n + i];
