@@ -33,6 +33,11 @@ namespace sbd {
 
 #define FULLMASK 0xffffffffu
 
+// e / d for 0 <= e < 2^16 with the precomputed magic number ceil(2^32 / d): one IMAD.HI
+// instead of the ~20-instruction integer division by a run-time divisor
+__device__ __forceinline__ unsigned div_magic(int d) { return 0xFFFFFFFFu / (unsigned)d + 1u; }
+__device__ __forceinline__ int fdiv(int e, unsigned magic) { return (int)__umulhi((unsigned)e, magic); }
+
 __device__ __forceinline__ double warp_sum(double v)
 {
 #pragma unroll
@@ -176,6 +181,7 @@ __device__ int solve_layer(const BinCtx &c, const CtaShared &cs, WarpShared &w,
 {
     const int N = c.N, n = c.n, m = c.mazim;
     const int ldt = n | 1;                             // leading dimension of T and V
+    const unsigned rn = div_magic(n);
     hint_shared(cs); hint_shared(w);
     double ss = c.ssalb[lc];
     if (ss == 1.0) ss = 1.0 - kDither;                 // disort.f:486
@@ -194,7 +200,7 @@ __device__ int solve_layer(const BinCtx &c, const CtaShared &cs, WarpShared &w,
     // symmetrised even / odd parity operators
     //   Pe~ = M^-1/2 (I - 2 W^1/2 Se W^1/2) M^-1/2 , Po~ likewise with So
     for (int e = lane; e < n * n; e += 32) {
-        int i = e / n, j = e - i * n;
+        int i = fdiv(e, rn), j = e - i * n;
         double se = 0.0, so = 0.0;
         for (int l = m; l < N; l++) {
             double t = w.gl[l] * cs.ylm[l * n + i] * cs.ylm[l * n + j];
@@ -230,21 +236,21 @@ __device__ int solve_layer(const BinCtx &c, const CtaShared &cs, WarpShared &w,
 
     // X = Pe~ L ;  T = L^T X  (symmetric positive semidefinite, eigenvalues k^2)
     for (int e = lane; e < n * n; e += 32) {
-        int i = e / n, j = e - i * n;
+        int i = fdiv(e, rn), j = e - i * n;
         double a = 0.0;
         for (int k = j; k < n; k++) a += w.Pe[i * n + k] * w.Lo[k * n + j];
         w.X[e] = a;
     }
     __syncwarp();
     for (int e = lane; e < n * n; e += 32) {
-        int i = e / n, j = e - i * n;
+        int i = fdiv(e, rn), j = e - i * n;
         double a = 0.0;
         for (int k = i; k < n; k++) a += w.Lo[k * n + i] * w.X[k * n + j];
         w.P[e] = a;
     }
     __syncwarp();
     for (int e = lane; e < n * n; e += 32) {
-        int i = e / n, j = e - i * n;
+        int i = fdiv(e, rn), j = e - i * n;
         w.T[i * ldt + j] = 0.5 * (w.P[i * n + j] + w.P[j * n + i]);
         w.V[i * ldt + j] = (i == j) ? 1.0 : 0.0;
     }
@@ -287,7 +293,7 @@ __device__ int solve_layer(const BinCtx &c, const CtaShared &cs, WarpShared &w,
                 __syncwarp();
                 // column rotations of T and V
                 for (int e = lane; e < np * n; e += 32) {
-                    int k = e / n, i = e - k * n;
+                    int k = fdiv(e, rn), i = e - k * n;
                     int p = w.pq[2 * k], q = w.pq[2 * k + 1];
                     if (p != q) {
                         double cc = w.cs[2 * k], sn = w.cs[2 * k + 1];
@@ -302,7 +308,7 @@ __device__ int solve_layer(const BinCtx &c, const CtaShared &cs, WarpShared &w,
                 __syncwarp();
                 // row rotations of T
                 for (int e = lane; e < np * n; e += 32) {
-                    int k = e / n, j = e - k * n;
+                    int k = fdiv(e, rn), j = e - k * n;
                     int p = w.pq[2 * k], q = w.pq[2 * k + 1];
                     if (p != q) {
                         double cc = w.cs[2 * k], sn = w.cs[2 * k + 1];
@@ -333,7 +339,7 @@ __device__ int solve_layer(const BinCtx &c, const CtaShared &cs, WarpShared &w,
         }
     }
     for (int e = lane; e < n * n; e += 32) {
-        int i = e / n, j = e - i * n;
+        int i = fdiv(e, rn), j = e - i * n;
         double a = 0.0;
         for (int k = 0; k <= i; k++) a += w.Lo[i * n + k] * w.V[k * ldt + j];
         w.P[e] = a;
@@ -341,7 +347,7 @@ __device__ int solve_layer(const BinCtx &c, const CtaShared &cs, WarpShared &w,
     __syncwarp();
     // G+ - G- = e = D^-1 Q ; G+ + G- = (alpha-beta) e / k = -D^-1 P / k
     for (int e = lane; e < n * n; e += 32) {
-        int i = e / n, j = e - i * n;
+        int i = fdiv(e, rn), j = e - i * n;
         double gd = cs.dinv[i] * w.X[e];
         double gs = -cs.dinv[i] * w.P[e] / w.kk[s][j];
         w.Gp[s][e] = 0.5 * (gs + gd);
@@ -919,6 +925,7 @@ disort_generic_kernel(const LaunchArgs a)
                 naz = 0;
         }
         const int R = n + N, C = 2 * N + 1;
+        const unsigned rC = div_magic(C);
         const double *ylm_smem = cs.ylm;
         int kconv = 0;
 
@@ -943,7 +950,7 @@ disort_generic_kernel(const LaunchArgs a)
             store_layer(ll, scr, w, cur, xr0c, xr1c, lane);
             // top boundary rows (disort.f:2887-2915, :3547-3550)
             for (int e = lane; e < n * C; e += 32) {
-                int r = e / C, j = e - r * C;
+                int r = fdiv(e, rC), j = e - r * C;
                 double v;
                 if (j < N) {
                     double g = gc_elem(w.Gp[cur], w.Gm[cur], n, r, j);
@@ -969,7 +976,7 @@ disort_generic_kernel(const LaunchArgs a)
             const double tb = w.taucpr[lc + 1];
             const double eb = (c.fbeam > 0.0) ? exp(-tb / c.umu0) : 0.0;
             for (int e = lane; e < N * C; e += 32) {
-                int r = e / C, j = e - r * C;
+                int r = fdiv(e, rC), j = e - r * C;
                 double v;
                 if (j < N) {
                     double g = gc_elem(w.Gp[cur], w.Gm[cur], n, r, j);
@@ -992,7 +999,7 @@ disort_generic_kernel(const LaunchArgs a)
             for (int e = lane; e < N * C; e += 32) U[e] = w.W[e];
             __syncwarp();
             for (int e = lane; e < n * C; e += 32) {
-                int r = e / C, j = e - r * C;
+                int r = fdiv(e, rC), j = e - r * C;
                 double v;
                 if (j < N) v = w.W[(N + r) * C + N + j];
                 else if (j < 2 * N) v = 0.0;
@@ -1025,7 +1032,7 @@ disort_generic_kernel(const LaunchArgs a)
             }
             __syncwarp();
             for (int e = lane; e < n * C; e += 32) {
-                int i = e / C, j = e - i * C;
+                int i = fdiv(e, rC), j = e - i * C;
                 int r = n + i;
                 double v;
                 if (j < N) {
