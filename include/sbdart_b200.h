@@ -131,8 +131,10 @@ int sbd_synchronize(sbd_handle *h);
  * this handle: indices into the NT output levels, n = 0 restores "all levels".
  * SBDART consumes the radiances of one or two levels only (ntop / nbot,
  * drt.f:1008-1016, :1143-1151) while DISORT's USRINT (disort.f:4355) integrates
- * the source function for every level; unselected levels of uu are returned as
- * zeros.  Fluxes are not affected. */
+ * the source function for every level.  The device-pointer call writes zeros at
+ * the unselected levels of uu; the host-buffer call copies back the selected
+ * levels only and leaves the rest of the caller's uu untouched (the copy of all
+ * L+1 levels would dominate the call).  Fluxes are not affected. */
 int sbd_set_radiance_levels(sbd_handle *h, const int32_t *levels, int32_t n);
 
 /* CORINT of DISORT (disort.f:112-118, INTCOR disort.f:2044-2297) for the following

@@ -221,7 +221,8 @@ class Solver:
             out = {k: np.empty((B, NT)) for k in ("rfldir", "rfldn", "flup", "dfdt", "uavg")}
             out["status"] = np.empty(B, np.int32)
             if d.numu > 0:
-                out["uu"] = np.empty((B, d.nphi, NT, d.numu))
+                # selected levels only are copied back (sbd_set_radiance_levels): the rest stays zero
+                out["uu"] = (np.zeros if uu_levels is not None else np.empty)((B, d.nphi, NT, d.numu))
         p = lambda a: None if a is None else a.ctypes.data  # noqa: E731
         if uu_levels is not None:
             self.set_radiance_levels(uu_levels)

@@ -156,7 +156,8 @@ extern "C" void sbd_destroy(sbd_handle *h)
     cudaStreamSynchronize(h->stream2);
     SbdDevBuf *bufs[] = { &h->scratch, &h->counter, &h->scratch2, &h->counter2, &h->ylmu, &h->angles, &h->d_dtauc, &h->d_ssalb,
                        &h->d_pmom, &h->d_bins, &h->d_temper, &h->d_utau, &h->d_out, &h->d_uu,
-                       &h->d_status, &h->opt_tables, &h->opt_atm, &h->opt_misc, &h->opt_map, &h->opt_aero };
+                       &h->d_status, &h->opt_tables, &h->opt_atm, &h->opt_misc, &h->opt_map, &h->opt_aero,
+                       &h->d_uupack, &h->d_sel };
     for (SbdDevBuf *b : bufs) b->release();
     for (int i = 0; i < sbd_handle::kMaxChunks; i++) { cudaEventDestroy(h->ev_in[i]); cudaEventDestroy(h->ev_k[i]); }
     cudaEventDestroy(h->ev_misc);
@@ -328,6 +329,20 @@ extern "C" int sbd_disort_batch_device(sbd_handle *h, const sbd_dims *dims, cons
     return SBD_SUCCESS;
 }
 
+// uu[b][j][sel[s]][iu] -> pack[b][j][s][iu]: only the levels selected with
+// sbd_set_radiance_levels cross PCIe (SBDART reads one or two of the L+1 levels)
+__global__ void pack_levels_kernel(const double *uu, double *pack, const int32_t *sel, int nsel,
+                                   int NT, int NU, size_t total)
+{
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const int iu = (int)(e % NU);
+        const size_t t = e / NU;
+        const int s = (int)(t % nsel);
+        const size_t bj = t / nsel;
+        pack[e] = uu[(bj * NT + sel[s]) * NU + iu];
+    }
+}
+
 extern "C" int sbd_disort_batch(sbd_handle *h, const sbd_dims *dims, const double *dtauc,
                                 const double *ssalb, const double *pmom, const sbd_bin *bins,
                                 const double *temper, const double *utau, const double *umu,
@@ -374,6 +389,23 @@ extern "C" int sbd_disort_batch(sbd_handle *h, const sbd_dims *dims, const doubl
     const size_t per = B * NT;
     const size_t nuu1 = (size_t)dims->numu * dims->nphi * NT;      // uu doubles per bin
     if (nuu1) CK(h->d_uu.reserve(nuu1 * B * 8));
+    // level selection (sbd_set_radiance_levels): copy back a compact array and scatter on the host
+    std::vector<int32_t> sel;
+    std::vector<double> uustage;
+    size_t npack1 = 0;                                             // packed uu doubles per bin
+    if (nuu1) {
+        for (size_t lu = 0; lu < NT; lu++)
+            if (lu >= 128 || ((h->uu_mask[lu >> 6] >> (lu & 63)) & 1ull)) sel.push_back((int32_t)lu);
+        if (sel.size() == NT) sel.clear();                         // every level: plain copy
+        else if (sel.empty()) sel.push_back(0);
+    }
+    if (!sel.empty()) {
+        npack1 = (size_t)dims->nphi * sel.size() * dims->numu;
+        CK(h->d_uupack.reserve(npack1 * B * 8));
+        CK(h->d_sel.reserve(sel.size() * 4));
+        CK(cudaMemcpyAsync(h->d_sel.p, sel.data(), sel.size() * 4, cudaMemcpyHostToDevice, st));
+        uustage.resize(npack1 * B);
+    }
     double *o = (double *)h->d_out.p;
     double *dst[5] = { rfldir, rfldn, flup, dfdt, uavg };
     // Pipeline over chunks of bins: H2D of chunk c+1 and D2H of chunk c-1 overlap the
@@ -442,12 +474,31 @@ extern "C" int sbd_disort_batch(sbd_handle *h, const sbd_dims *dims, const doubl
         }
         for (int k = 0; k < 5; k++)
             if (dst[k]) CK(cudaMemcpyAsync(dst[k] + b0 * NT, o + k * per + b0 * NT, nb * NT * 8, cudaMemcpyDeviceToHost, so));
-        if (nuu1) CK(cudaMemcpyAsync(uu + b0 * nuu1, (double *)h->d_uu.p + b0 * nuu1, nb * nuu1 * 8, cudaMemcpyDeviceToHost, so));
+        if (nuu1 && sel.empty())
+            CK(cudaMemcpyAsync(uu + b0 * nuu1, (double *)h->d_uu.p + b0 * nuu1, nb * nuu1 * 8, cudaMemcpyDeviceToHost, so));
+        if (nuu1 && !sel.empty()) {
+            const size_t total = nb * npack1;
+            const int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
+            pack_levels_kernel<<<blocks, 256, 0, so>>>((const double *)h->d_uu.p + b0 * nuu1,
+                                                       (double *)h->d_uupack.p + b0 * npack1,
+                                                       (const int32_t *)h->d_sel.p, (int)sel.size(),
+                                                       (int)NT, dims->numu, total);
+            CK(cudaGetLastError());
+            CK(cudaMemcpyAsync(uustage.data() + b0 * npack1, (double *)h->d_uupack.p + b0 * npack1, total * 8,
+                               cudaMemcpyDeviceToHost, so));
+        }
         CK(cudaMemcpyAsync(status + b0, (int32_t *)h->d_status.p + b0, nb * 4, cudaMemcpyDeviceToHost, so));
     }
     CK(cudaStreamSynchronize(st));
     if (two) CK(cudaStreamSynchronize(h->stream2));
     if (nchunk > 1) CK(cudaStreamSynchronize(h->copy_out));
+    if (!sel.empty()) {                 // scatter the selected levels; the others are not written
+        const size_t NU = dims->numu, NP = dims->nphi, ns = sel.size();
+        for (size_t b = 0; b < B; b++)
+            for (size_t j = 0; j < NP; j++)
+                for (size_t s = 0; s < ns; s++)
+                    memcpy(uu + ((b * NP + j) * NT + sel[s]) * NU, uustage.data() + ((b * NP + j) * ns + s) * NU, NU * 8);
+    }
 #undef CK
     return SBD_SUCCESS;
 }

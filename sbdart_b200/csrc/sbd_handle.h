@@ -50,6 +50,7 @@ struct sbd_handle {
     unsigned long long uu_mask[2] = { ~0ull, ~0ull };   // levels at which uu is wanted                       // set used by the next device-level launch
     // staging for the host-pointer API
     SbdDevBuf d_dtauc, d_ssalb, d_pmom, d_bins, d_temper, d_utau, d_out, d_uu, d_status;
+    SbdDevBuf d_uupack, d_sel;                // selected-level intensities, compact, for the D2H copy
     // whole-spectrum path (sbd_spectrum.cu)
     SbdDevBuf opt_tables, opt_atm, opt_misc, opt_map, opt_aero;
     sbd_aerosol_params aero = {};             // aerosols of the next spectrum runs
