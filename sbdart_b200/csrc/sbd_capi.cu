@@ -272,7 +272,9 @@ extern "C" int sbd_disort_batch_device(sbd_handle *h, const sbd_dims *dims, cons
     } else {
         warps = generic_pick_warps(N, L, NT, smem_limit);
         if (warps == 0) return SBD_ERR_UNSUPPORTED;
-        if (warps > 4) warps = 4;
+        // small NSTR: several 4-warp CTAs per SM; large NSTR (one CTA fills the SM's shared
+        // memory): as many warps as fit
+        if (warps >= 8) warps = 4;
         size_t smem = generic_smem_bytes(N, L, NT, warps);
         int cta_per_sm = (int)((smem_limit + 1024) / (smem + 1024));
         if (cta_per_sm < 1) cta_per_sm = 1;

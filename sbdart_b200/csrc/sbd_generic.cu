@@ -73,7 +73,8 @@ __host__ __device__ inline size_t cta_shared_doubles(int N)
 __host__ __device__ inline size_t warp_shared_doubles(int N, int L, int NT)
 {
     int n = N / 2;
-    size_t o = 2 * N + 4 * (size_t)n * n + 2 * (size_t)n * (n | 1) + 2 * (2 * n + 2 * (size_t)n * n + 2 * N) +
+    // the eigenproblem scratch (Pe, Lo, T, V, X, P) lives inside W, see carve()
+    size_t o = 2 * N + 2 * (2 * n + 2 * (size_t)n * n + 2 * N) +
                (size_t)(n + N) * (2 * N + 1) + 2 * N + 4 * N + 3 * (size_t)(L + 1) +
                (n + 2);
     size_t ints = (size_t)NT + (n + 2);
@@ -105,12 +106,6 @@ __device__ void carve(double *base, int N, int L, int NT, WarpShared &w)
     double *p = base;
     w.gl = p; p += N;
     w.y0 = p; p += N;
-    w.Pe = p; p += n * n;
-    w.Lo = p; p += n * n;
-    w.T = p; p += n * (n | 1);     // T and V: odd leading dimension (column walks of the
-    w.V = p; p += n * (n | 1);     // Jacobi rotations would otherwise hit one bank pair)
-    w.X = p; p += n * n;
-    w.P = p; p += n * n;
     for (int s = 0; s < 2; s++) {
         w.kk[s] = p; p += n;
         w.ek[s] = p; p += n;
@@ -120,6 +115,19 @@ __device__ void carve(double *base, int N, int L, int NT, WarpShared &w)
         w.zp0[s] = p; p += N;
     }
     w.W = p; p += (n + N) * (2 * N + 1);
+    {
+        // Scratch of solve_layer, aliased onto rows n .. n+N-1 of the elimination window: while
+        // a layer's eigenproblem is solved only the n carried rows (rows 0 .. n-1) are live, the
+        // interface rows are assembled afterwards from Gp/Gm/kk/ek/zz/zp0; the upward sweep
+        // never calls solve_layer.  4 n^2 + 2 n (n|1) <= N (2N+1) doubles.
+        double *q = w.W + n * (2 * N + 1);
+        w.Pe = q; q += n * n;
+        w.Lo = q; q += n * n;
+        w.T = q; q += n * (n | 1);     // T and V: odd leading dimension (column walks of the
+        w.V = q; q += n * (n | 1);     // Jacobi rotations would otherwise hit one bank pair)
+        w.X = q; q += n * n;
+        w.P = q; q += n * n;
+    }
     w.xn = p; p += N;
     w.xc = p; p += N;
     w.v1 = p; p += N;
@@ -766,7 +774,7 @@ __device__ double usrint_one(const BinCtx &c, const WarpShared &w, const LayerLa
 extern __shared__ double smem_dyn[];
 
 template <bool SYNC>
-__global__ void __launch_bounds__(128, 4)
+__global__ void __launch_bounds__(256, 2)
 disort_generic_kernel(const LaunchArgs a)
 {
     const int N = a.d.nstr, n = N / 2, L = a.d.nlyr;
