@@ -75,3 +75,46 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".h", ".cpp")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in txt.replace("no CPU fallback", ""), f
+
+
+def test_aerosol_structs_match_header():
+    """sbd_aerosol_params / sbd_strat_entry (include/sbdart_b200.h) as packed by frontend/device.py."""
+    import ctypes as C
+    from sbdart_b200.frontend import device
+    assert C.sizeof(device.AerosolParams) == 6 * 4 + 8
+    assert device.STRAT_DTYPE.itemsize == (2 + 3 * 47) * 8
+    src = open(os.path.join(ROOT, "include", "sbdart_b200.h")).read()
+    assert "#define SBD_NAERW 47" in src and "double ext[SBD_NAERW], absb[SBD_NAERW], asym[SBD_NAERW]" in src
+
+
+def test_aerosol_setup_handed_to_the_producer_kernel():
+    """Host logic of device.set_aerosols: which arrays reach sbd_spectrum_set_aerosols for a
+    boundary-layer + stratospheric run, and that runs without aerosols clear the setting."""
+    import ctypes as C
+    from sbdart_b200.frontend import Sbdart, device
+
+    class FakeLib:
+        def __init__(self):
+            self.calls = []
+
+        def sbd_spectrum_set_aerosols(self, h, p, *arrays):
+            self.calls.append((p, arrays))
+            return 0
+
+    class FakeSolver:
+        _h = None
+
+    run = Sbdart("&INPUT idatm=2, iaer=2, vis=10, jaer=2,4, zaer=18,25, taerst=0.1,0.02, wlinf=.5, wlsup=.6, wlinc=.05 /")
+    L = FakeLib()
+    device.set_aerosols(L, FakeSolver(), run.aerosols)
+    p, arrays = L.calls[0]
+    par = C.cast(p, C.POINTER(device.AerosolParams)).contents if not isinstance(p, device.AerosolParams) else p
+    par = p._obj if hasattr(p, "_obj") else par
+    assert par.nwlbaer == 47 and par.nstrat == 2 and par.nz == run.nz and par.imoma == 3
+    assert all(a is not None for a in arrays)                 # wlb, ext, abs, asm, dtsv, awl, strat
+    assert device.device_aerosols_supported(run.aerosols)
+    clean = Sbdart("&INPUT idatm=2, wlinf=.5, wlsup=.6, wlinc=.05 /")
+    device.set_aerosols(L, FakeSolver(), clean.aerosols)
+    assert L.calls[1][0] is None
+    table = Sbdart("&INPUT idatm=2, iaer=1, vis=23, imoma=4, wlinf=.5, wlsup=.6, wlinc=.05 /")
+    assert not device.device_aerosols_supported(table.aerosols)
