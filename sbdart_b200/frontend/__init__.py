@@ -16,8 +16,9 @@ is NOT here: `run()` takes a `solve(batch)` callable -- the CUDA batch solver
 (Solver.disort_batch); the golden tests also pass their CPU checker.
 
 Aerosols, zgrid, in-cloud humidity, zensun and the sensor filters live in extras.py.
-Not covered: user files (atms.dat, albedo.dat, aerosol.dat, filter.dat, solar.dat,
-usrcld.dat, CKTAU), BRDF surfaces (isalb 7-9), kdist=-1, spowder.
+User files read from the working directory like the reference: atms.dat, albedo.dat,
+filter.dat, solar.dat.  Not covered: aerosol.dat, usrcld.dat, CKTAU (kdist=-1), BRDF
+surfaces (isalb 7-9), spowder.
 """
 from __future__ import annotations
 
@@ -757,8 +758,11 @@ class Sun:
             r = ((n - 1 - np.arange(n)).astype(np.float32) / np.float32(n - 1)).astype(float)
             self.wl = 10000. / (100. + (49960. - 100.) * r)
             self.s = s3[::-1]
+        elif nf == -1:  # solar.dat (wavelength um, W/m2/um)
+            from .extras import rdspec
+            self.wl, self.s = rdspec("solar.dat")
         elif nf != 0:
-            raise NotImplementedError("nf=-1 solar.dat")
+            raise ValueError(f"ERROR in solirr --- illegal value of nf {nf}")
 
     def __call__(self, wl):
         if self.nf == 0:
@@ -782,6 +786,9 @@ class Albedo:
             self.wl = f32(.25) + (4.0 - f32(.25)) * _f32ramp(751)
             self.alb = sum(T(f"spectra/{n}/albx") * sc[i]
                            for i, n in enumerate(("snow", "seaw", "sand", "vegeta")))
+        elif isalb == -1:   # albedo.dat
+            from .extras import rdspec
+            self.wl, self.alb = rdspec("albedo.dat")
         else:
             raise NotImplementedError(f"isalb={isalb}")
 
@@ -1050,8 +1057,6 @@ class Sbdart:
     def _setup(self):
         p = self.p
         from . import extras
-        if p["amix"] > -1.0 or p["idatm"] == 0:
-            raise NotImplementedError("atms.dat (idatm=0 / amix)")
         iout = p["iout"]
         self.radcalc = iout in (5, 6, 20, 21, 22, 23)
         self.onlyfl = not self.radcalc
@@ -1078,7 +1083,17 @@ class Sbdart:
             p["isat"], p["wlinf"], p["wlsup"], p["wlinc"], want_filter=True)
         kdist = 0 if iout == 2 else p["kdist"]
         self.kdist = kdist
-        z, pr, t, wh, wo = atms(p["idatm"])
+        if p["idatm"] == 0:                                 # atms.f:443
+            z, pr, t, wh, wo = extras.useratm()
+        else:
+            z, pr, t, wh, wo = atms(p["idatm"])
+        if p["amix"] > -1.:                                 # atms.f:451-463
+            zz, pp, tt, hh, oo = extras.useratm()
+            if len(zz) != len(z) or (np.abs(zz - z) > 0.01).any():
+                raise ValueError("atms -- vertical grids do not match")
+            am = p["amix"]
+            pr, t = pr * (1. - am) + pp * am, t * (1. - am) + tt * am
+            wh, wo = wh * (1. - am) + hh * am, wo * (1. - am) + oo * am
         if p["ngrid"] != 0:                                 # drt.f:307
             if p["ngrid"] < 0:
                 raise NotImplementedError("ngrid < 0 (print the regridded atmosphere and stop)")

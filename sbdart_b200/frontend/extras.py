@@ -27,6 +27,57 @@ NAERZ, NAERB, NAERW = 5, 150, 47
 WL55 = f32(0.55)
 
 
+# ------------------------------------------------------------------ user data files
+def _records(path, nitems):
+    """List-directed READ of `nitems` values per record: the first nitems numbers of every
+    non-blank line (a Fortran `read(13,*) a, b` ignores the rest of the line)."""
+    out = []
+    with open(path) as f:
+        for line in f:
+            tok = [t for t in line.replace(",", " ").split() if t]
+            if not tok:
+                continue
+            if len(tok) < nitems:
+                raise ValueError(f"{path}: expected {nitems} values per line, got {line.strip()!r}")
+            out.append([float(t.lower().replace("d", "e")) for t in tok[:nitems]])
+    return out
+
+
+def useratm(path="atms.dat"):
+    """User atmosphere (useratm, atms.f:468-503): nz, then nz lines z p t wh wo from the top
+    down (or bottom up: the arrays are reversed when needed).  Returns bottom-up arrays."""
+    with open(path) as f:
+        first = f.readline().replace(",", " ").split()
+    nz = int(float(first[0]))
+    if nz > MXLY:
+        raise ValueError(f"error in USERATM: {nz} layers specified in ATMS.DAT, but current limit is {MXLY}")
+    recs = []
+    with open(path) as f:
+        f.readline()
+        for line in f:
+            tok = [t for t in line.replace(",", " ").split() if t]
+            if tok:
+                recs.append([float(t.lower().replace("d", "e")) for t in tok[:5]])
+            if len(recs) == nz:
+                break
+    if len(recs) < nz:
+        raise ValueError("atms.dat: fewer levels than announced")
+    a = np.array(recs)[::-1]                    # read(13,*) z(i), ... for i = nz, 1, -1
+    if a[0, 0] > a[-1, 0]:
+        a = a[::-1]
+    return tuple(np.ascontiguousarray(a[:, k]) for k in range(5))
+
+
+def rdspec(path, nmax=5000):
+    """Two-column spectral file (rdspec, spectra.f:4382-4437): wavelength, value."""
+    recs = _records(path, 2)
+    if len(recs) > nmax:
+        raise ValueError(f"Error in rdspec -- file {path} should not specify more than {nmax} values")
+    a = np.array(recs)
+    a = a[a[:, 0] != 0.]
+    return np.ascontiguousarray(a[:, 0]), np.ascontiguousarray(a[:, 1])
+
+
 # ------------------------------------------------------------------ vertical grid
 def zgrid(z, p, t, wh, wo, zgrid1, zgrid2, ngrid):
     """Regrid the model atmosphere to |ngrid| levels (atms.f:505-617).  Arrays are
@@ -206,7 +257,10 @@ def filter_table(isat, wlinf, wlsup):
         wlmin, wlmax = float(T(f"spectra/{nm}/wmn")), float(T(f"spectra/{nm}/wmx"))
         # (wlmax-wlmin)*real(i-1)/(nnf-1) is evaluated left to right in double
         return wlmin, wlmax, Filter(wlmin + (wlmax - wlmin) * np.arange(len(sr)) / (len(sr) - 1), sr)
-    raise NotImplementedError(f"isat={isat}" + (" (filter.dat)" if isat == -1 else ""))
+    if isat == -1:                       # filter.dat
+        wlf, filt = rdspec("filter.dat", 1000)
+        return wlf[0], wlf[-1], Filter(wlf, filt)
+    raise ValueError(f"isat={isat} out of range")
 
 
 # ------------------------------------------------------------------ aerosols

@@ -260,3 +260,34 @@ def test_corint_restores_the_aureole():
     r_off, r_on = [float(x) for x in off[-6:]], [float(x) for x in on[-6:]]
     assert r_on[2] > 2.5 * r_off[2]                            # uzen=151, phi=0: one degree from the sun
     assert abs(r_on[3] / r_off[3] - 1) < 0.15                  # same zenith angle, opposite azimuth
+
+
+# ------------------------------------------------------------------ user data files
+def test_user_files_reproduce_the_built_in_tables(tmp_path, monkeypatch):
+    """atms.dat / albedo.dat / solar.dat / filter.dat written from the built-in tables give the
+    same run as the built-in options (useratm atms.f:468, rdspec spectra.f:4382)."""
+    from sbdart_b200.frontend import Albedo, Sun
+    monkeypatch.chdir(tmp_path)
+    z, p, t, wh, wo = atms(2)
+    rows = [f"{len(z)}"] + [f"{z[i]:.6f} {p[i]:.8e} {t[i]:.6f} {wh[i]:.8e} {wo[i]:.8e} trailing text ignored"
+                            for i in range(len(z) - 1, -1, -1)]
+    (tmp_path / "atms.dat").write_text("\n".join(rows) + "\n")
+    alb = Albedo(5, 0.0, [1, 0, 0, 0, 0])
+    (tmp_path / "albedo.dat").write_text("".join(f"{w:.9f}, {a:.9e}\n" for w, a in zip(alb.wl, alb.alb)))
+    sun = Sun(1)
+    (tmp_path / "solar.dat").write_text("".join(f"{w:.9f} {v:.9e}\n" for w, v in zip(sun.wl, sun.s)))
+    (tmp_path / "filter.dat").write_text("0.50 0.0\n0.60 1.0\n\n0.70 0.0\n")
+    want = Sbdart("&INPUT idatm=2, isalb=5, nf=1, isat=-3, wlinf=.6, wlsup=.1, wlinc=.02, sza=40, kdist=0, iout=10 /")
+    got = Sbdart("&INPUT idatm=0, isalb=-1, nf=-1, isat=-1, wlinc=.02, sza=40, kdist=0, iout=10 /")
+    assert got.nz == want.nz and np.allclose(got.z, want.z) and np.allclose(got.pr, want.pr, rtol=1e-8)
+    assert (got.wl1, got.wl2, got.nwl) == (0.5, 0.7, want.nwl)
+    a = [float(x) for x in want.run(solve_oracle).split()]
+    b = [float(x) for x in got.run(solve_oracle).split()]
+    assert b == pytest.approx(a, rel=2e-4)
+    # amix blends a user atmosphere into a standard one on the same grid (atms.f:451-463)
+    mixed = Sbdart("&INPUT idatm=4, amix=0.5 /")
+    z4, p4, t4, _, _ = atms(4)
+    assert np.allclose(mixed.t, 0.5 * (t + t4))
+    (tmp_path / "atms.dat").write_text("2\n10. 200. 220. 1. 1.\n0. 1000. 290. 5. 1.\n")
+    with pytest.raises(ValueError):
+        Sbdart("&INPUT idatm=4, amix=0.5 /")
