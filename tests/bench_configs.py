@@ -5,7 +5,7 @@ bench.py measures config C2.  This script times the same C-ABI host call
 bin sets shaped like C1, C3, C4 and C5 and checks a sample of every
 set against the CPU oracle.  One JSON line per configuration.
 
-    python tools/bench_configs.py [--quick]
+    python tests/bench_configs.py [--quick]
 """
 import argparse
 import json
@@ -15,7 +15,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))   # tests/ -> repo root
 sys.path.insert(0, ROOT)
 import sbdart_b200 as sb                      # noqa: E402
 from sbdart_b200 import workloads            # noqa: E402

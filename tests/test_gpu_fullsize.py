@@ -45,7 +45,7 @@ def _oracle_sample(w, got, idx):
         scale = (np.abs(ref["flup"][ok]).max(axis=1) + np.abs(ref["rfldir"][ok]).max(axis=1))[:, None]
         # floor 2e-9 x the bin's largest flux: on the thermal bins of the real C2 spectrum
         # every CUDA kernel generation (and the generic kernel) sits 3-5e-10 x scale away
-        # from the oracle (tools/accuracy_probe.py); 1e-5 is what the records resolve
+        # from the oracle (tests/accuracy_probe.py); 1e-5 is what the records resolve
         err = np.abs(got[k][idx][ok] - ref[k][ok]) - 2e-9 * scale
         assert (err <= 1e-7 * np.abs(ref[k][ok])).all(), k
 
