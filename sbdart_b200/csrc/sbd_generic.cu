@@ -473,6 +473,20 @@ __device__ __forceinline__ double gc_elem(const double *Gp, const double *Gm,
     }
 }
 
+// scratch (global) -> shared copy, four loads in flight per lane: written as a plain loop
+// the loads are issued one at a time behind their stores (the destination pointers that come
+// out of the run-time indexed buffer sets are generic, so the compiler assumes aliasing)
+__device__ __forceinline__ void copy_in(double *dst, const double *src, int count, int lane)
+{
+    int e = lane;
+    for (; e + 96 < count; e += 128) {
+        // plain (coherent) loads: the scratch slot was written by this warp earlier in the same launch
+        const double v0 = src[e], v1 = src[e + 32], v2 = src[e + 64], v3 = src[e + 96];
+        dst[e] = v0; dst[e + 32] = v1; dst[e + 64] = v2; dst[e + 96] = v3;
+    }
+    for (; e < count; e += 32) dst[e] = src[e];
+}
+
 // copy a layer record shared -> scratch
 __device__ void store_layer(const LayerLayout &ll, double *rec, const WarpShared &w,
                             int s, double xr0, double xr1, int lane)
@@ -490,9 +504,12 @@ __device__ void load_layer(const LayerLayout &ll, const double *rec, WarpShared 
 {
     const int n = ll.n, N = ll.N;
     hint_shared(w);
-    for (int e = lane; e < n; e += 32) { w.kk[s][e] = rec[ll.off_kk + e]; w.ek[s][e] = rec[ll.off_ek + e]; }
-    for (int e = lane; e < n * n; e += 32) { w.Gp[s][e] = rec[ll.off_gp + e]; w.Gm[s][e] = rec[ll.off_gm + e]; }
-    for (int e = lane; e < N; e += 32) { w.zz[s][e] = rec[ll.off_zz + e]; w.zp0[s][e] = rec[ll.off_zp0 + e]; }
+    copy_in(w.kk[s], rec + ll.off_kk, n, lane);
+    copy_in(w.ek[s], rec + ll.off_ek, n, lane);
+    copy_in(w.Gp[s], rec + ll.off_gp, n * n, lane);
+    copy_in(w.Gm[s], rec + ll.off_gm, n * n, lane);
+    copy_in(w.zz[s], rec + ll.off_zz, N, lane);
+    copy_in(w.zp0[s], rec + ll.off_zp0, N, lane);
     xr0 = rec[ll.off_xr]; xr1 = rec[ll.off_xr + 1];
 }
 
@@ -1067,7 +1084,7 @@ disort_generic_kernel(const LaunchArgs a)
             for (int lc = ncut - 1; lc >= 0; lc--) {
                 if (lc < ncut - 1) {
                     const double *U = scr + (size_t)lc * ll.stride + ll.off_u;
-                    for (int e = lane; e < N * C; e += 32) w.W[e] = U[e];
+                    copy_in(w.W, U, N * C, lane);
                     load_layer(ll, scr + (size_t)lc * ll.stride, w, cur, xr0c, xr1c, lane);
                     __syncwarp();
                     // rhs -= U[:, N:2N] x_{lc+1}
