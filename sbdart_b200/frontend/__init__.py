@@ -1067,6 +1067,7 @@ class Sbdart:
             self.sc = [1., 0., 0., 0., 0.] if sc is None else list(np.atleast_1d(sc)) + [0.] * 5
         if self.radcalc:
             self._vuangles()
+        self._chkin()
         sza = p["sza"]
         dtor = PI_KR / 180.
         if p["iday"] != 0:                                  # drt.f:276-277
@@ -1145,6 +1146,74 @@ class Sbdart:
         self.amu0 = math.cos(sza * dtor)
         self.sun = Sun(p["nf"])
         self.aerosols = extras.Aerosols(p, z, self.rhaer)
+
+    def _chkin(self):
+        """Range checks of the main program (chkin / ck, drt.f:568-735): the reference prints
+        the offending parameters and stops; here the same text is the message of a ValueError."""
+        p = self.p
+        msgs = []
+
+        def ck(name, rng, shown):
+            if not msgs:
+                msgs.append("CHKIN --- Errors detected in INPUT")
+            msgs.append(f"\n     Input parameter {name} not within {rng}")
+            msgs.append(f" {name}= {shown}")
+
+        self.warnings = []
+        if p["iaer"] == 0 and (p["vis"] != ZIP or p["tbaer"] != ZIP):
+            self.warnings.append("CHKIN--IAER=0, though VIS or TBAER set")             # errmsg 16
+        if p["corint"] and self.onlyfl:
+            self.warnings.append("CHKIN--CORINT=t, but flux output selected")          # errmsg 17
+        if not -6 <= p["idatm"] <= 6:
+            ck("idatm", "[-6,6]", p["idatm"])
+        if p["wlinf"] < f32(0.199):
+            ck("wlinf", "[0.2,-]", p["wlinf"])
+        if p["isat"] <= -2:
+            if p["wlsup"] < 0. or p["wlsup"] >= p["wlinf"]:
+                ck("wlsup", "[0,wlinf]", p["wlsup"])
+        elif p["wlsup"] < p["wlinf"] or p["wlsup"] > 100.:
+            ck("wlsup", "[wlinf,100]", p["wlsup"])
+        if not -4 <= p["isat"] <= 29:
+            ck("isat", "[-4,29]", p["isat"])
+        if p["solfac"] < 0.:
+            ck("solfac", "[0,inf]", p["solfac"])
+        if p["zcloud"].min() < -100. or p["zcloud"].max() > 100:
+            ck("zcloud", "[-100,100]", p["zcloud"])
+        if (np.abs(p["nre"]).min() < 2 or np.abs(p["nre"]).max() > 128) and p["nre"][0] != 0.:
+            ck("nre", "[2,128]", p["nre"])
+        if ((p["tcloud"] == 0) & (p["zcloud"] < 0)).any():
+            msgs += ["CHKIN --- Error detected in input", "TCLOUD(k)=0 when ZCLOUD(k)<0"]
+        if p["lwp"].min() < 0.:
+            ck("lwp", "[0,inf]", p["lwp"])
+        if np.abs(_arr(p["zaer"], 5, 0.0)).max() > 100.:
+            ck("zaer", "[-100,100]", p["zaer"])
+        if _arr(p["taerst"], 5, 0.0).min() < 0.:
+            ck("taerst", "[0,inf]", p["taerst"])
+        ja = _arr(p["jaer"], 5, 0.0)
+        if ja.min() < 0 or ja.max() > 4:
+            ck("jaer", "[0,4]", p["jaer"])
+        if not -2 <= p["nf"] <= 3:
+            ck("nf", "[-2,3]", p["nf"])
+        if not -1 <= p["iaer"] <= 5:
+            ck("iaer", "[-1,5]", p["iaer"])
+        if p["isalb"] not in (-7, -8, -9, -1, 0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10):
+            ck("isalb", "[-7,-8,-9,-1,0,1,2,3,4,5,6,7,8,9,10]", p["isalb"])
+        if p["isalb"] == 0 and p["albcon"] < 0.:
+            ck("albcon", "[0,inf]", p["albcon"])
+        if p["zout"].max() > 100:
+            ck("zout", "[0,100]", p["zout"])
+        if p["iout"] not in (1, 2, 5, 6, 7, 10, 11, 20, 21, 22, 23):
+            ck("iout", "[1,2,5,6,7,10,11,20,21,22,23]", p["iout"])
+        if not 0 <= p["nphi"] <= NSTRMS:
+            ck("nphi", "[0,nstrms]", p["nphi"])
+        if p["iout"] in (20, 21, 22, 23) and self.nzen == 0:
+            msgs.append(f" iout ={p['iout']:2d} implies radiance calculation, but nzen=0 produces no radiance output")
+        if p["zpres"] != ZIP and p["pbar"] != ZIP:
+            msgs.append(" set zpres or pbar but not both")
+        if numset(0.0, p["tcloud"]) != 0 and numset(0.0, p["lwp"]) != 0:
+            msgs.append(" set TCLOUD or LWP, but not both")
+        if msgs:
+            raise ValueError("\n".join(msgs))
 
     @staticmethod
     def _nearest(xx, x):

@@ -291,3 +291,16 @@ def test_user_files_reproduce_the_built_in_tables(tmp_path, monkeypatch):
     (tmp_path / "atms.dat").write_text("2\n10. 200. 220. 1. 1.\n0. 1000. 290. 5. 1.\n")
     with pytest.raises(ValueError):
         Sbdart("&INPUT idatm=4, amix=0.5 /")
+
+
+def test_chkin_rejects_what_the_reference_rejects():
+    """Range checks of drt.f:568-735 with the reference's wording."""
+    for nl, word in (("&INPUT iout=3 /", "iout"), ("&INPUT wlinf=0.1, wlsup=0.5 /", "wlinf"),
+                     ("&INPUT wlinf=0.6, wlsup=0.5 /", "wlsup"), ("&INPUT isat=40 /", "isat"),
+                     ("&INPUT nf=7 /", "nf"), ("&INPUT tcloud=5, lwp=10, zcloud=1 /", "TCLOUD or LWP"),
+                     ("&INPUT zpres=2, pbar=900 /", "zpres or pbar"), ("&INPUT nre=1, tcloud=5, zcloud=1 /", "nre"),
+                     ("&INPUT isalb=11 /", "isalb"), ("&INPUT jaer=5, zaer=20, taerst=.1 /", "jaer")):
+        with pytest.raises(ValueError, match=word):
+            Sbdart(nl)
+    ok = Sbdart("&INPUT vis=23 /")                       # a warning, not an error (errmsg 16)
+    assert ok.warnings == ["CHKIN--IAER=0, though VIS or TBAER set"]
