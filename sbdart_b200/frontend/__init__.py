@@ -1026,6 +1026,15 @@ def _r4(x):
 
 
 # ------------------------------------------------------------------ the driver
+class SbdartStop(Exception):
+    """The reference printed a diagnostic table and executed STOP (idatm < 0, ngrid < 0,
+    iday < 0): `text` is what it wrote to stdout."""
+
+    def __init__(self, text):
+        super().__init__(text)
+        self.text = text
+
+
 class Sbdart:
     """One SBDART run (program sbdart, drt.f:90-563)."""
 
@@ -1071,8 +1080,6 @@ class Sbdart:
         sza = p["sza"]
         dtor = PI_KR / 180.
         if p["iday"] != 0:                                  # drt.f:276-277
-            if p["iday"] < 0:
-                raise NotImplementedError("iday < 0 (print the solar geometry and stop)")
             sza, p["saza"], p["solfac"] = extras.zensun(abs(p["iday"]), p["time"], p["alat"], p["alon"])
         elif p["csza"] != ZIP:
             sza = math.acos(p["csza"]) / dtor
@@ -1080,6 +1087,16 @@ class Sbdart:
             sza = 95.
         self.sza = sza
         self.phi0 = math.fmod(p["saza"] - 180.0 + 360.0, 360.0)
+        if p["iday"] < 0:                                   # drt.f:285-299: print the geometry and stop
+            out = ["  day     time      lat      lon      sza      azm   solfac",
+                   f"{abs(p['iday']):5d}" + "".join(f"{v:9.3f}" for v in (p["time"], p["alat"], p["alon"], sza,
+                                                                          p["saza"], p["solfac"]))]
+            if self.radcalc:
+                out.append("      phi   rel_az")
+                for ph in self.phi:
+                    rel = ph + self.phi0 - (360. if self.phi0 > 180. and self.phi[-1] + self.phi0 > 360 else 0.)
+                    out.append(f"{ph:9.3f}{rel:9.3f}")
+            raise SbdartStop("\n".join(out) + "\n")
         self.wl1, self.wl2, self.nwl, self.wlinc, self.filter = setfilt(
             p["isat"], p["wlinf"], p["wlsup"], p["wlinc"], want_filter=True)
         kdist = 0 if iout == 2 else p["kdist"]
@@ -1096,8 +1113,6 @@ class Sbdart:
             pr, t = pr * (1. - am) + pp * am, t * (1. - am) + tt * am
             wh, wo = wh * (1. - am) + hh * am, wo * (1. - am) + oo * am
         if p["ngrid"] != 0:                                 # drt.f:307
-            if p["ngrid"] < 0:
-                raise NotImplementedError("ngrid < 0 (print the regridded atmosphere and stop)")
             z, pr, t, wh, wo = extras.zgrid(z, pr, t, wh, wo, p["zgrid1"], p["zgrid2"], p["ngrid"])
         if p["zpres"] != ZIP:
             j = locate(z, p["zpres"])
@@ -1122,6 +1137,9 @@ class Sbdart:
                 extras.satcloud(self.clouds.lcld, t, p["rhcld"], wh)
             else:
                 extras.saturate(self.clouds.lcld, z, t, p["rhcld"], wh)
+        if p["ngrid"] < 0 or p["idatm"] < 0:                # prnatm (drt.f:803-809)
+            raise SbdartStop(f"{nz:12d}\n" + "".join(
+                _f(z[i], 11, 3) + "".join(_es(v[i], 11, 3) for v in (pr, t, wh, wo)) + "\n" for i in range(nz)))
         self.uu = absint(z, pr, t, wh, wo, self.trace)
         zout = np.abs(p["zout"]) if p["zout"].min() < 0 else p["zout"]
         nbot = self._nearest(z, zout[0])
@@ -1200,7 +1218,7 @@ class Sbdart:
             ck("isalb", "[-7,-8,-9,-1,0,1,2,3,4,5,6,7,8,9,10]", p["isalb"])
         if p["isalb"] == 0 and p["albcon"] < 0.:
             ck("albcon", "[0,inf]", p["albcon"])
-        if p["zout"].max() > 100:
+        if p["zout"].min() < 0. or p["zout"].max() > 100:
             ck("zout", "[0,100]", p["zout"])
         if p["iout"] not in (1, 2, 5, 6, 7, 10, 11, 20, 21, 22, 23):
             ck("iout", "[1,2,5,6,7,10,11,20,21,22,23]", p["iout"])

@@ -304,3 +304,20 @@ def test_chkin_rejects_what_the_reference_rejects():
             Sbdart(nl)
     ok = Sbdart("&INPUT vis=23 /")                       # a warning, not an error (errmsg 16)
     assert ok.warnings == ["CHKIN--IAER=0, though VIS or TBAER set"]
+
+
+def test_print_and_stop_modes():
+    """idatm < 0 / ngrid < 0 print the (regridded) atmosphere (prnatm, drt.f:803-809), iday < 0 the
+    solar geometry (drt.f:285-299); the reference then executes STOP."""
+    from sbdart_b200.frontend import SbdartStop
+    with pytest.raises(SbdartStop) as e:
+        Sbdart("&INPUT idatm=-2 /")
+    lines = e.value.text.splitlines()
+    assert lines[0] == "          33" and len(lines) == 34
+    assert lines[1] == "      0.000  1.013E+03  2.940E+02  1.400E+01  6.000E-05"
+    with pytest.raises(SbdartStop) as e:
+        Sbdart("&INPUT idatm=2, ngrid=-20 /")
+    assert e.value.text.splitlines()[0].strip() == "20" and len(e.value.text.splitlines()) == 21
+    with pytest.raises(SbdartStop) as e:
+        Sbdart("&INPUT iday=-172, time=18, alat=34.4, alon=-119.8 /")
+    assert e.value.text.splitlines()[1].split()[:4] == ["172", "18.000", "34.400", "-119.800"]
