@@ -65,7 +65,7 @@ def test_whole_spectrum_gpu_path_reproduces_sbchk(n):
 @pytest.mark.parametrize("nl", [
     "&INPUT idatm=2, wlinf=.25, wlsup=4.0, wlinc=.005, nstr=16, iout=1 /",
     "&INPUT idatm=4, wlinf=4, wlsup=20, wlinc=-.01, sza=95, tcloud=5, zcloud=8, nre=10, iout=1 /",
-    "&INPUT idatm=1, wlinf=.3, wlsup=3.0, wlinc=.05, sza=40, tcloud=3,0,0, lwp=0,50,0, zcloud=1,4,0, nre=6,-20,8, isalb=6, kdist=2, iout=1 /",
+    "&INPUT idatm=1, wlinf=.3, wlsup=3.0, wlinc=.05, sza=40, lwp=20,50,0, zcloud=1,4,0, nre=6,-20,8, isalb=6, kdist=2, iout=1 /",
     "&INPUT idatm=6, wlinf=5, wlsup=50, wlinc=20, sza=20, kdist=1, nothrm=0, iout=1 /",
 ])
 def test_producer_kernel_matches_host_front_end(nl):
