@@ -1359,6 +1359,42 @@ class Sbdart:
                 res = self._retry(b, res, solve)
         return self.records(rows, res)
 
+    def run_sharded(self, solve, dist=None):
+        """One run over several GPUs: every rank builds the bin list, solves its
+        contiguous block (sharding.bin_partition never splits the k-terms of a wavelength), one
+        all-gather returns the per-bin outputs in loop order and every rank does the ordered
+        accumulation of drt.f:977-982 itself, so the records are byte-identical for any number of
+        ranks.  `dist` is torch.distributed (NCCL on the GPUs, gloo in the CPU tests)."""
+        import torch
+        from ..sharding import bin_partition, gather_outputs
+        rows = self.bins()
+        if not rows:
+            return self.records(rows, None)
+        b = self.batch(rows)
+        world = dist.get_world_size() if dist is not None and dist.is_initialized() else 1
+        rank = dist.get_rank() if world > 1 else 0
+        parts = bin_partition(len(rows), world, b["group"])
+        lo, hi = parts[rank]
+        NT = self.nz + 1
+        keys = ["rfldir", "rfldn", "flup"] + (["uu"] if self.radcalc else [])
+        if hi > lo:
+            sub = dict(b)
+            for k in ("dtauc", "ssalb", "pmom", "bins", "group"):
+                sub[k] = b[k][lo:hi]
+            res = solve(sub)
+            if (np.asarray(res["status"]) != 0).any():
+                res = self._retry(sub, res, solve)
+        else:
+            res = {k: np.zeros((0, NT)) for k in keys[:3]}
+            if self.radcalc:
+                res["uu"] = np.zeros((0, len(self.phi), NT, len(self.umu)))
+        if world == 1:
+            return self.records(rows, res)
+        dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+        full = {k: gather_outputs(torch.from_numpy(np.ascontiguousarray(res[k], dtype=np.float64)).to(dev),
+                                  parts, dist).cpu().numpy() for k in keys}
+        return self.records(rows, full)
+
     def run_device(self, solver):
         """Whole-spectrum GPU path: the optical properties of every bin are produced
         by the K2 kernel and never leave the device (frontend/device.py)."""

@@ -39,3 +39,39 @@ def _worker(rank, world, port, nbins):
 def test_two_rank_gather_restores_bin_order():
     port = 29500 + os.getpid() % 2000
     mp.spawn(_worker, args=(2, port, 1343), nprocs=2, join=True)
+
+
+def _run_worker(rank, world, port, nl, q):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from sbdart_b200.frontend import Sbdart
+    from solvers import solve_oracle
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    txt = Sbdart(nl).run_sharded(lambda b: solve_oracle(b, nthreads=2), dist)
+    q.put((rank, txt))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_run_prints_the_same_records():
+    """A whole SBDART run split over two ranks (bins solved by the CPU checker here, by the GPU
+    on the box): the records are byte-identical to the single-process run on every rank."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from sbdart_b200.frontend import Sbdart
+    from solvers import solve_oracle
+    for nl in ("&INPUT idatm=4, wlinf=.3, wlsup=.9, wlinc=.02, iout=1 /",
+               "&INPUT idatm=2, nstr=4, wlinf=.6, wlsup=.64, wlinc=.02, sza=30, iout=20, uzen=20,120, phi=0,90 /"):
+        want = Sbdart(nl).run(solve_oracle)
+        ctx = mp.get_context("spawn")
+        q = ctx.SimpleQueue()
+        port = 31000 + os.getpid() % 2000
+        procs = [ctx.Process(target=_run_worker, args=(r, 2, port, nl, q)) for r in range(2)]
+        for p in procs:
+            p.start()
+        got = dict(q.get() for _ in range(2))
+        for p in procs:
+            p.join(120)
+            assert p.exitcode == 0
+        assert got[0] == want and got[1] == want
