@@ -1,0 +1,127 @@
+"""Every bin of BASELINE.json's configurations against the CPU checker (oracle/).
+
+The oracle solves the 2 037 bins of C2 in about a second, the 3 406 NSTR=32 / 65-layer bins
+of C4 in a few seconds and C5's 125 000 bins in ~5 s on the GPU box's host cores, so nothing
+here is sampled: each test solves the COMPLETE bin set the reference's wavelength loop
+(drt.f:425-561) would hand to DISORT for that namelist, once through the C ABI on the GPU and
+once with the oracle, and compares every output value.
+
+Tolerances (BASELINE.json north star: 1e-5 relative):
+  fluxes     |gpu - ref| <= 1e-7 |ref| + floor x (largest flux of the bin);
+             floor 2e-9 at NSTR <= 16, 2e-8 at NSTR = 32 / 65 layers (different pivot
+             orders differ by cond x eps of the bin's flux scale);
+  radiances  |gpu - ref| <= 1e-5 |ref| + 1e-9 x (largest radiance of the bin).
+"""
+import numpy as np
+import pytest
+
+import sbdart_b200 as sb
+from sbdart_b200 import workloads
+from sbdart_b200.frontend import Sbdart
+from solvers import make_solve_cuda, solve_oracle
+
+pytestmark = pytest.mark.gpu
+
+UZ = ",".join(str(x) for x in np.linspace(5.0, 85.0, 10))
+C2 = "&INPUT idatm=2, wlinf=.25, wlsup=4.0, wlinc=.005, nstr=16, iout=1 /"
+C3_NIGHT = f"&INPUT idatm=2, wlinf=4, wlsup=80, wlinc=20, nstr=8, iout=20, uzen={UZ}, sza=95 /"
+C3_DAY = f"&INPUT idatm=2, wlinf=4, wlsup=80, wlinc=20, nstr=8, iout=20, uzen={UZ}, sza=30 /"
+C4 = ("&INPUT idatm=2, nstr=32, ngrid=65, tcloud=10, zcloud=1, iaer=1, vis=23, wlinf=.25, wlsup=100,"
+      " wlinc=20, iout=10 /")
+
+
+@pytest.fixture(scope="module")
+def solver():
+    s = sb.Solver(0)
+    yield s
+    s.close()
+
+
+def _compare_fluxes(got, ref, floor, keys=("rfldir", "rfldn", "flup", "dfdt", "uavg")):
+    assert (got["status"] == ref["status"]).all()
+    ok = ref["status"] == 0
+    assert ok.sum() > 0.99 * len(ok)
+    scale = np.max([np.abs(ref[k][ok]).max(axis=1) for k in ("rfldir", "rfldn", "flup")], axis=0)[:, None]
+    worst = 0.0
+    for k in keys:
+        if k not in ref or k not in got:
+            continue
+        # dfdt = (1 - ssalb) 4 pi (uavg - planck): its own scale is the mean intensity's
+        sc = scale * (4 * np.pi if k == "dfdt" else 1.0)
+        d = np.abs(got[k][ok] - ref[k][ok])
+        err = d - floor * sc
+        assert (err <= 1e-7 * np.abs(ref[k][ok])).all(), (k, float((d / sc).max()))
+        worst = max(worst, float((d / sc).max()))
+    return worst
+
+
+def _compare_radiances(got, ref):
+    ok = ref["status"] == 0
+    g, r = got["uu"][ok], ref["uu"][ok]
+    assert g.shape == r.shape
+    scale = np.abs(r).reshape(len(r), -1).max(axis=1).reshape((-1,) + (1,) * (r.ndim - 1))
+    err = np.abs(g - r) - 1e-9 * scale
+    assert (err <= 1e-5 * np.abs(r)).all(), float((np.abs(g - r) / np.maximum(scale, 1e-300)).max())
+
+
+def _batch(nl, all_levels=False):
+    run = Sbdart(nl)
+    b = run.batch(run.bins())
+    if all_levels:
+        b.pop("uu_levels", None)
+    return b
+
+
+def test_c2_every_bin(solver):
+    """Config C2, the bench workload: all 2 037 (wavelength, k-term) bins, all 34 levels,
+    all five flux outputs."""
+    b = _batch(C2)
+    assert len(b["bins"]) == 2037 and b["nstr"] == 16 and b["dtauc"].shape[1] == 33
+    got, ref = make_solve_cuda(solver)(b), solve_oracle(b)
+    _compare_fluxes(got, ref, 2e-9)
+
+
+@pytest.mark.parametrize("nl,modes", [(C3_NIGHT, 1), (C3_DAY, 8)])
+def test_c3_every_bin_fluxes_and_radiances(solver, nl, modes):
+    """Config C3 exactly as BASELINE.md writes it (20 cm-1 steps from 4 to 80 um, NSTR=8,
+    10 zenith angles x the 19 default azimuths): thermal only (sza=95, one azimuth mode)
+    and sunlit (sza=30, all NSTR-1 modes).  Fluxes and the intensities at ALL 34 levels."""
+    b = _batch(nl, all_levels=True)
+    assert len(b["bins"]) == 355 and len(b["umu"]) == 10 and len(b["phi"]) == 19
+    got, ref = make_solve_cuda(solver)(b), solve_oracle(b)
+    assert got["uu"].shape == (355, 19, 34, 10)
+    _compare_fluxes(got, ref, 2e-9, keys=("rfldir", "rfldn", "flup"))
+    _compare_radiances(got, ref)
+    if modes > 1:       # the sunlit run really has azimuth structure
+        top = ref["uu"][:, :, 0, :]
+        assert (np.abs(top[:, 0, :] - top[:, 9, :]) > 1e-3 * np.abs(top).max()).any()
+    # and the level selection the front end uses (ntop / nbot only) returns the same numbers
+    bsel = _batch(nl)
+    gsel = make_solve_cuda(solver)(bsel)
+    for lu in bsel["uu_levels"]:
+        assert np.array_equal(gsel["uu"][:, :, lu, :], got["uu"][:, :, lu, :])
+
+
+def test_c4_every_bin(solver):
+    """Config C4: NSTR=32, 65-layer grid, stratus cloud + rural aerosol, 0.25-100 um in
+    20 cm-1 steps -- all 3 406 bins."""
+    b = _batch(C4)
+    assert len(b["bins"]) == 3406 and b["nstr"] == 32 and b["dtauc"].shape[1] == 65
+    got, ref = make_solve_cuda(solver)(b), solve_oracle(b)
+    _compare_fluxes(got, ref, 2e-8)
+
+
+def test_c5_every_bin(solver):
+    """Config C5: one GPU's share (125 000 bins, 125 columns) of the 10^6-bin retrieval
+    batch, NSTR=16."""
+    w = workloads.retrieval_batch(125000, nstr=16, nlyr=33, ncols=125)
+    got = solver.disort_batch(w["dtauc"], w["ssalb"], w["pmom"], w["bins"], nstr=16)
+    b = w["bins"]
+    import os
+    from oracle import oracle
+    ref = oracle.disort_flux_batch(
+        w["dtauc"], w["ssalb"], w["pmom"], nstr=16, fbeam=b["fbeam"], umu0=b["umu0"],
+        albedo=b["albedo"], plank=b["plank"], wvnmlo=b["wvnmlo"], wvnmhi=b["wvnmhi"],
+        btemp=b["btemp"], ttemp=b["ttemp"], temis=b["temis"], fisot=b["fisot"], temper=None,
+        col=b["col"], nthreads=os.cpu_count() or 8)
+    _compare_fluxes(got, ref, 2e-9)
