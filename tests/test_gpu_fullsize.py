@@ -1,5 +1,6 @@
-"""Size-independent properties at BASELINE.json's full sizes (no oracle: it would
-take minutes).  Bins are independent, so every check is per bin:
+"""Size-independent properties at BASELINE.json's full sizes.  (The every-bin comparison
+with the oracle is tests/test_gpu_full_parity.py; these checks need no oracle.)  Bins are
+independent, so every check is per bin:
 
   * the reported direct beam is the analytic mu0 F exp(-tau/mu0) (disort.f:1998);
   * without a thermal source and with a black or grey surface the net flux
