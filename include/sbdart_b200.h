@@ -255,6 +255,10 @@ int sbd_measure_fp64_peak(sbd_handle *h, int reps, double *tflops);
 
 const char *sbd_status_string(int code);
 int sbd_abi_version(void);
+/* Hash of the sources and compiler flags this binary was built from (the build
+ * script passes it as -DSBD_BUILD_ID); the Python mirror refuses a library whose
+ * id differs from the sources next to it. */
+const char *sbd_build_id(void);
 
 /*
  * gfortran-compatible replacement for SUBROUTINE DISORT (disort.f:1-6), call

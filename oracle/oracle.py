@@ -34,6 +34,13 @@ def build(force: bool = False) -> str:
     return so
 
 
+def build_ref() -> bool:
+    """Try to build the untouched reference into oracle/_ref/sbdart (needs gfortran and
+    /root/reference; neither exists on the GPU box).  Returns True when the binary exists."""
+    subprocess.run(["make", "-C", _HERE, "_ref"], check=False, stdout=subprocess.DEVNULL)
+    return os.path.exists(os.path.join(_HERE, "_ref", "sbdart"))
+
+
 def lib():
     global _LIB
     if _LIB is None:

@@ -31,7 +31,7 @@ EXPORTS = (
     "sbd_synchronize", "sbd_stream", "sbd_kernel_launches", "sbd_quadrature",
     "sbd_status_string", "sbd_abi_version", "disort_", "sbd_disort_last_status",
     "sbd_measure_fp64_peak", "sbd_optics_upload_tables", "sbd_spectrum_run",
-    "sbd_set_radiance_levels", "sbd_spectrum_set_aerosols", "sbd_set_corint",
+    "sbd_set_radiance_levels", "sbd_spectrum_set_aerosols", "sbd_set_corint", "sbd_build_id",
 )
 
 
@@ -76,6 +76,14 @@ def lib():
             f"{LIB_PATH} not built; run `python -c 'import __graft_entry__ as g; g.build()'` "
             "(there is no CPU fallback)")
     L = C.CDLL(LIB_PATH)
+    L.sbd_build_id.restype = C.c_char_p
+    if os.path.isdir(os.path.join(_PKG, "csrc")) and not os.environ.get("SBD_SKIP_BUILD_ID_CHECK"):
+        from . import _build
+        have, want = L.sbd_build_id().decode(), _build.source_id()
+        if have != want:
+            raise ImportError(
+                f"{LIB_PATH} was built from other sources (build id {have}, sources {want}); "
+                "rebuild with `python -c 'import __graft_entry__ as g; g.build()'`")
     dp, ip = C.c_void_p, C.c_void_p
     L.sbd_create.restype = C.c_int
     L.sbd_create.argtypes = [C.POINTER(C.c_void_p), C.c_int]

@@ -98,6 +98,11 @@ static int check_dims(const sbd_dims *d)
 
 extern "C" int sbd_abi_version(void) { return SBD_ABI_VERSION; }
 
+#ifndef SBD_BUILD_ID
+#define SBD_BUILD_ID "unknown"
+#endif
+extern "C" const char *sbd_build_id(void) { return SBD_BUILD_ID; }
+
 extern "C" const char *sbd_status_string(int code)
 {
     switch (code) {

@@ -251,8 +251,9 @@ __device__ __forceinline__ int phase1_layers(
         }
         double pive = shfl_d(nume, j, n), pivo = shfl_d(numo, j, n);
         if (!(pivo > 0.0)) { bad = 1; pivo = 1.0; }
-        // Pe~ is only semidefinite when w' -> 1: keep the factor real
+        // Pe~ is only semidefinite when w' -> 1: keep the factor real (a NaN pivot is a failure)
         const double floor_e = 1.0e-30;
+        if (pive != pive) bad = 1;
         if (!(pive > floor_e)) pive = floor_e;
         const double rie = fast_rsqrt(pive), rio = fast_rsqrt(pivo);
         rK[j] = rie; rL[j] = rio;
@@ -714,6 +715,7 @@ disort_fast_kernel(const LaunchArgs a)
             for (int lc = lane; lc < L; lc += 32) {
                 double s = ssalb[lc];
                 if (!(s >= 0.0 && s <= 1.0)) badl = 1;
+                if (!(fabs(dtauc[lc]) <= 1.79e308)) badl = 1;      // NaN / Inf optical depth
                 for (int k = 1; k <= a.d.nmom; k++) {
                     double pm = pmom[(size_t)lc * ldp + k];
                     if (!(pm >= -1.0 && pm <= 1.0)) badl = 1;
@@ -723,6 +725,8 @@ disort_fast_kernel(const LaunchArgs a)
             if (!(albedo >= 0.0 && albedo <= 1.0) || bp.fisot < 0.0) badl = 1;
             if (plank && (bp.wvnmlo < 0.0 || bp.wvnmhi <= bp.wvnmlo || bp.temis < 0.0 ||
                           bp.temis > 1.0 || bp.btemp < 0.0 || bp.ttemp < 0.0)) badl = 1;
+            // device-pointer callers: a Planck bin needs a valid row of temper[ncol][L+1]
+            if (plank && (!a.temper || bp.col < 0 || bp.col >= a.d.ncol)) badl = 1;
             if (__any_sync(FULLMASK, badl)) status = SBD_BIN_BAD_INPUT;
             int clash = 0;
             if (fbeam > 0.0 && lane < n && fabs(umu0 - cmu[lane]) / umu0 < 1.e-4) clash = 1;

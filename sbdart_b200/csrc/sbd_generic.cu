@@ -860,6 +860,7 @@ disort_generic_kernel(const LaunchArgs a)
             for (int lc = lane; lc < L; lc += 32) {
                 double s = c.ssalb[lc];
                 if (!(s >= 0.0 && s <= 1.0)) badl = 1;
+                if (!(fabs(c.dtauc[lc]) <= 1.79e308)) badl = 1;    // NaN / Inf optical depth
                 for (int k = 1; k <= a.d.nmom; k++) {
                     double pm = c.pmom[(size_t)lc * ldp + k];
                     if (!(pm >= -1.0 && pm <= 1.0)) badl = 1;
@@ -869,6 +870,8 @@ disort_generic_kernel(const LaunchArgs a)
             if (!(c.albedo >= 0.0 && c.albedo <= 1.0) || c.fisot < 0.0) badl = 1;
             if (c.plank && (bp.wvnmlo < 0.0 || bp.wvnmhi <= bp.wvnmlo || bp.temis < 0.0 ||
                             bp.temis > 1.0 || bp.btemp < 0.0 || bp.ttemp < 0.0)) badl = 1;
+            // device-pointer callers: a Planck bin needs a valid row of temper[ncol][L+1]
+            if (c.plank && (!a.temper || bp.col < 0 || bp.col >= a.d.ncol)) badl = 1;
             if (__any_sync(FULLMASK, badl)) status = SBD_BIN_BAD_INPUT;
             // beam angle = quadrature angle (disort.f:2641-2650)
             int clash = 0;

@@ -53,15 +53,33 @@ def T(key):
 
 
 # ------------------------------------------------------------------ NAMELIST
-def parse_namelist(text, group="input"):
-    """Minimal Fortran NAMELIST reader: scalars, lists, repeat counts n*v,
-    logicals t/f, case-insensitive names (drt.f:200-231)."""
-    m = re.search(r"[&$]\s*" + group + r"\b(.*?)(?:^\s*/|\s/|&end|\$end)", text, re.I | re.S | re.M)
+# names of the two NAMELIST groups (drt.f:200-215); a name outside its group aborts the read
+INPUT_NAMES = frozenset("""idatm amix isat wlinf wlsup wlinc sza csza solfac nf iday time alat alon zpres pbar
+    sclh2o uw uo3 o3trp ztrp xrsc xn2 xo2 xco2 xch4 xn2o xco xno2 xso2 xnh3 xno xhno3 xo4 isalb albcon sc
+    zcloud tcloud lwp nre rhcld krhclr jaer zaer taerst iaer vis rhaer tbaer wlbaer qbaer abaer wbaer gbaer
+    pmaer zbaer dbaer nothrm nosct kdist zgrid1 zgrid2 ngrid idb zout iout prnt temis nstr nzen uzen vzen
+    nphi phi saza imomc imoma ttemp btemp corint spowder""".split())
+DINPUT_NAMES = frozenset("ibcnd phi0 prnt ipth fisot temis nstr nzen uzen vzen nphi phi ttemp btemp".split())
+
+
+def parse_namelist(text, group="input", names=None):
+    """Fortran NAMELIST reader for the subset SBDART's INPUT files use (drt.f:200-231):
+    scalars, lists, repeat counts n*v, logicals t/f, case-insensitive names, array
+    elements `name(k) = v1, v2, ...` (values fill elements k, k+1, ...), `/`, `&end` or
+    `$end` terminators with or without leading blanks, `!` comments.  Returns a list of
+    (name, first_element_or_None, values); None when the group is absent.  A name that
+    is not in `names` raises ValueError, as the Fortran read aborts on it."""
+    m = re.search(r"[&$]\s*" + group + r"\b(.*?)(?:/|&end|\$end)", text, re.I | re.S)
     if not m:
         return None
     body = re.sub(r"!.*", "", m.group(1))
-    out = {}
-    for name, val in re.findall(r"(\w+)\s*(?:\(\s*\d+\s*\))?\s*=\s*([^=]*?)(?=\s*\w+\s*(?:\(\s*\d+\s*\))?\s*=|\Z)", body, re.S):
+    items = []
+    lhs = r"([A-Za-z_]\w*)\s*(?:\(\s*(\d+)\s*\))?\s*="
+    ahead = r"[A-Za-z_]\w*\s*(?:\(\s*\d+\s*\))?\s*="
+    for name, sub, val in re.findall(lhs + r"\s*(.*?)(?=\s*" + ahead + r"|\Z)", body, re.S):
+        name = name.lower()
+        if names is not None and name not in names:
+            raise ValueError(f"namelist ${group.upper()}: unknown variable '{name}'")
         toks = [t for t in re.split(r"[\s,]+", val.strip()) if t]
         vals = []
         for t in toks:
@@ -75,10 +93,34 @@ def parse_namelist(text, group="input"):
             elif tl in ("f", "false"):
                 v = False
             else:
-                v = float(t.lower().replace("d", "e"))
+                try:
+                    v = float(t.lower().replace("d", "e"))
+                except ValueError:
+                    raise ValueError(f"namelist ${group.upper()}: bad value '{t}' for '{name}'") from None
             vals += [v] * rep
-        out[name.lower()] = vals[0] if len(vals) == 1 else vals
-    return out
+        if not vals:
+            raise ValueError(f"namelist ${group.upper()}: no value for '{name}'")
+        items.append((name, int(sub) if sub else None, vals))
+    return items
+
+
+def apply_namelist(p, items):
+    """Assign parsed NAMELIST items onto the parameter dict: whole-variable assignments
+    replace the leading elements of an array default (the rest keeps its default, as in
+    Fortran), `name(k) = ...` assigns elements k, k+1, ... (1-based)."""
+    for name, sub, vals in items:
+        cur = p.get(name)
+        if isinstance(cur, (list, np.ndarray)) or sub is not None:
+            base = list(cur) if isinstance(cur, (list, np.ndarray)) else ([] if cur is None else [cur])
+            k0 = (sub or 1) - 1
+            if len(base) < k0 + len(vals):
+                if name in DEFAULTS and isinstance(DEFAULTS[name], list) and name != "pmaer":
+                    raise ValueError(f"namelist: subscript of '{name}' out of range")
+                base += [ZIP] * (k0 + len(vals) - len(base))
+            base[k0:k0 + len(vals)] = vals
+            p[name] = base
+        else:
+            p[name] = vals[0] if len(vals) == 1 else vals
 
 
 DEFAULTS = dict(
@@ -792,9 +834,13 @@ class Albedo:
         else:
             raise NotImplementedError(f"isalb={isalb}")
 
-    def __call__(self, wl):
-        if wl < self.wl[0] or wl > self.wl[-1]:
-            raise ValueError("SALBEDO--spectral range error")
+    def __call__(self, wl, warn=None):
+        # spectra.f:44-56: outside the table a warning (errmsg 18) and the end value
+        if warn is not None:
+            if wl < self.wl[0]:
+                warn(18, "SALBEDO--spectral range error, wlinf lt " + f"{self.wl[0]:9.3f}")
+            if wl > self.wl[-1]:
+                warn(18, "SALBEDO--spectral range error, wlsup gt " + f"{self.wl[-1]:9.3f}")
         return interp_table(self.wl, self.alb, wl)
 
 
@@ -999,10 +1045,15 @@ class Clouds:
 # ------------------------------------------------------------------ Fortran formats
 def _es(x, w, d):
     """Fortran ESw.d of a value already rounded through REAL(4) when the reference does so."""
-    if x == 0 or not np.isfinite(x):
-        s = f"{0.0:.{d}E}"
-    else:
-        s = f"{x:.{d}E}"
+    if not np.isfinite(x):
+        # gfortran's edit of non-finite values: right-justified NaN / Infinity (Inf when the
+        # field is narrower than 8), so a solver failure is visible in the records
+        if np.isnan(x):
+            t = "NaN"
+        else:
+            t = ("-" if x < 0 else "") + ("Infinity" if w >= 8 + (x < 0) else "Inf")
+        return t.rjust(w) if len(t) <= w else "*" * w
+    s = f"{x:.{d}E}"
     mant, ex = s.split("E")
     e = int(ex)
     if abs(e) > 99:
@@ -1035,19 +1086,53 @@ class SbdartStop(Exception):
         self.text = text
 
 
+class SbdartFatal(Exception):
+    """errmsg(0, ...) of the reference (disutil.f:278-325): the run wrote SBDART_WARNING.00 and
+    stopped.  `text` is the message."""
+
+    def __init__(self, text):
+        super().__init__(text)
+        self.text = text
+
+
+def warning_file_text(num, message, input_text):
+    """Contents of SBDART_WARNING.nn (errmsg, disutil.f:297-321): the message, a rule of 70
+    '#', then a copy of the INPUT file with trailing blanks removed."""
+    head = ("ERROR  >>>>>>" if num == 0 else "WARNING >>>>>") + " " + message
+    body = "".join(ln.rstrip() + "\n" for ln in input_text.splitlines())
+    return head + "\n\n" + "#" * 70 + "\n\n" + body
+
+
+def write_warning_files(warnings, input_text, directory="."):
+    """One file per message number, as the reference leaves them in the working directory
+    (a number is reported once per run: msgset, disutil.f:295-299)."""
+    paths = []
+    for num, message in warnings:
+        path = os.path.join(directory, f"SBDART_WARNING.{num:02d}")
+        with open(path, "w") as fh:
+            fh.write(warning_file_text(num, message, input_text))
+        paths.append(path)
+    return paths
+
+
 class Sbdart:
     """One SBDART run (program sbdart, drt.f:90-563)."""
+
+    def _warn(self, num, message):
+        """errmsg(num > 0): remembered once per number (disutil.f:295-299)."""
+        if all(n != num for n, _ in self.warnings):
+            self.warnings.append((num, message))
 
     def __init__(self, namelist_text=None, **overrides):
         p = dict(DEFAULTS)
         if namelist_text is not None:
-            nl = parse_namelist(namelist_text)
+            nl = parse_namelist(namelist_text, "input", INPUT_NAMES)
             if nl is None:
                 raise ValueError("error: namelist block $INPUT not found")
-            p.update(nl)
-            dn = parse_namelist(namelist_text, "dinput")
+            apply_namelist(p, nl)
+            dn = parse_namelist(namelist_text, "dinput", DINPUT_NAMES)
             if dn:
-                p.update(dn)
+                apply_namelist(p, dn)
         p.update(overrides)
         for k in ("zcloud", "tcloud", "lwp"):
             p[k] = _arr(p[k], NCLDZ, 0.0)
@@ -1179,9 +1264,9 @@ class Sbdart:
 
         self.warnings = []
         if p["iaer"] == 0 and (p["vis"] != ZIP or p["tbaer"] != ZIP):
-            self.warnings.append("CHKIN--IAER=0, though VIS or TBAER set")             # errmsg 16
+            self._warn(16, "CHKIN--IAER=0, though VIS or TBAER set")                   # drt.f:583
         if p["corint"] and self.onlyfl:
-            self.warnings.append("CHKIN--CORINT=t, but flux output selected")          # errmsg 17
+            self._warn(17, "CHKIN--CORINT=t, but flux output selected")                # drt.f:586
         if not -6 <= p["idatm"] <= 6:
             ck("idatm", "[-6,6]", p["idatm"])
         if p["wlinf"] < f32(0.199):
@@ -1232,6 +1317,29 @@ class Sbdart:
             msgs.append(" set TCLOUD or LWP, but not both")
         if msgs:
             raise ValueError("\n".join(msgs))
+        # options of the reference this front end does not implement: fail loudly instead of
+        # running something else (module docstring, "not covered")
+        todo = []
+        if p["kdist"] < 0:
+            todo.append("kdist=-1 (CKATM/CKTAU k-distribution files, taugas.f:7297-7389)")
+        if p.get("spowder"):
+            todo.append("spowder (sub-surface layer, drt.f:340-352)")
+        if p["nre"][0] == 0.:
+            todo.append("nre(1)=0 (usrcld.dat, taucloud.f:142-274)")
+        if p["iaer"] == -1:
+            todo.append("iaer=-1 (aerosol.dat, tauaero.f:1526-1662)")
+        if p["isalb"] in (-7, -8, -9):
+            todo.append(f"isalb={p['isalb']} (dref, not in the reference source either)")
+        if int(p.get("ibcnd", 0)) != 0:
+            todo.append("ibcnd=1 (ALBTRN, disort.f:6718)")
+        todo += self._unsupported_surface()
+        if todo:
+            raise NotImplementedError("SBDART option not supported by this front end: " + "; ".join(todo))
+
+    def _unsupported_surface(self):
+        if self.p["isalb"] in (7, 8, 9):
+            return [f"isalb={self.p['isalb']} (BRDF surface, spectra.f:249-1357)"]
+        return []
 
     @staticmethod
     def _nearest(xx, x):
@@ -1296,7 +1404,7 @@ class Sbdart:
                 self.amu0 = 1.          # the reference overwrites amu0 for good (drt.f:456-459)
             ff = self.filter(wl)
             plank = (wl > 2.) if p["nothrm"] < 0 else (p["nothrm"] == 0)
-            rsfc = max(0.0, min(self.albedo(wl), 1.0))
+            rsfc = max(0.0, min(self.albedo(wl, self._warn), 1.0))
             pmom = np.zeros((nz, nmom + 1))
             dtauc, wcld = np.zeros(nz), np.zeros(nz)
             if self.clouds.mcldz > 0:
@@ -1333,6 +1441,7 @@ class Sbdart:
         d = dict(dtauc=np.stack([r["dtau"] for r in rows]), ssalb=np.stack([r["ssalb"] for r in rows]),
                  pmom=np.stack([r["pmom"] for r in rows]), bins=bins, temper=self.temper[None, :],
                  nstr=self.p["nstr"], group=g("il"))
+        self._chekin_warnings(d)
         if self.radcalc:
             d["umu"], d["phi"] = self.umu, self.phi
             d["corint"] = bool(self.p["corint"])
@@ -1344,6 +1453,31 @@ class Sbdart:
             if lv is not None:
                 d["uu_levels"] = sorted(set(lv))
         return d
+
+    def _chekin_warnings(self, d):
+        """The non-fatal messages of CHEKIN (disort.f:4938-4941, :5158-5172)."""
+        corint = bool(self.p["corint"]) and self.radcalc
+        nmom = d["pmom"].shape[2] - 1
+        if corint and nmom > 10 and (d["pmom"][:, :, nmom] > f32(1.e-3)).any():
+            self._warn(5, "CHEKIN-- phase function not sufficiently resolved for use with corint=.true.")
+        if d["bins"]["plank"].any() and (np.abs(np.diff(self.temper)) > 10.0).any():
+            self._warn(6, "CHEKIN--vertical temperature step may be too large for good accuracy")
+        if self.radcalc and not corint:
+            sun = d["bins"]["fbeam"] > 0.0
+            if sun.any() and (d["ssalb"][sun] > 0.0).any():      # YESSCT > 0, DELTAM
+                self._warn(7, "CHEKIN--intensity correction is off; intensities may be less accurate")
+
+    _FATAL = {-1: "DISORT--input and/or dimension errors", -2: "ASYMTX--convergence problems",
+              -3: "SOLVE0--boundary system singular"}
+
+    def _check_status(self, status):
+        """Per-bin failures are fatal in the reference (errmsg(0, ...) then STOP)."""
+        status = np.asarray(status)
+        if (status == 1).any():
+            self._warn(1, "SETDIS--beam angle=computational angle; change NSTR")
+        bad = status[status < 0]
+        if len(bad):
+            raise SbdartFatal(self._FATAL.get(int(bad[0]), f"DISORT--bin status {int(bad[0])}"))
 
     # ---- accumulation and records (stdout0/1/2, drt.f:892-1165)
     def run(self, solve):
@@ -1377,20 +1511,33 @@ class Sbdart:
         lo, hi = parts[rank]
         NT = self.nz + 1
         keys = ["rfldir", "rfldn", "flup"] + (["uu"] if self.radcalc else [])
+        empty = {k: np.zeros((0, NT)) for k in keys[:3]}
+        if self.radcalc:
+            empty["uu"] = np.zeros((0, len(self.phi), NT, len(self.umu)))
+        res, failure = empty, None
         if hi > lo:
             sub = dict(b)
             for k in ("dtauc", "ssalb", "pmom", "bins", "group"):
                 sub[k] = b[k][lo:hi]
-            res = solve(sub)
-            if (np.asarray(res["status"]) != 0).any():
-                res = self._retry(sub, res, solve)
-        else:
-            res = {k: np.zeros((0, NT)) for k in keys[:3]}
-            if self.radcalc:
-                res["uu"] = np.zeros((0, len(self.phi), NT, len(self.umu)))
+            try:
+                res = solve(sub)
+                if (np.asarray(res["status"]) != 0).any():
+                    res = self._retry(sub, res, solve)
+            except Exception as e:          # noqa: BLE001 -- reported on every rank below
+                if world == 1:
+                    raise
+                res, failure = empty, e
         if world == 1:
             return self.records(rows, res)
         dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+        # a rank whose solve failed must not leave the others waiting in the all-gather:
+        # exchange an ok flag first and raise on every rank
+        ok = torch.tensor([0 if failure is not None else 1], dtype=torch.int32, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            if failure is not None:
+                raise failure
+            raise RuntimeError("run_sharded: the solve failed on another rank")
         full = {k: gather_outputs(torch.from_numpy(np.ascontiguousarray(res[k], dtype=np.float64)).to(dev),
                                   parts, dist).cpu().numpy() for k in keys}
         return self.records(rows, full)
@@ -1408,6 +1555,14 @@ class Sbdart:
             # optical properties on the host, solve on the GPU
             return self.run(host_solve)
         rows, res = run_spectrum(self, solver)
+        # the CHEKIN / SALBEDO warnings the host-side batch would have raised
+        nothrm = self.p["nothrm"]
+        if (nothrm == 0 or (nothrm < 0 and self.wl2 > 2.0)) and (np.abs(np.diff(self.temper)) > 10.0).any():
+            self._warn(6, "CHEKIN--vertical temperature step may be too large for good accuracy")
+        if self.radcalc and not self.p["corint"] and self.sza < 90. and self.p["xrsc"] > 0.:
+            self._warn(7, "CHEKIN--intensity correction is off; intensities may be less accurate")
+        for wl in (self.wl1, self.wl2):
+            self.albedo(wl, self._warn)
         if (res["status"] != 0).any():
             # beam / quadrature clash (drt.f:536-554): fall back to the host-side batch
             # for the retry logic (rare: one NSTR-dependent angle)
@@ -1535,6 +1690,7 @@ class Sbdart:
         """NSTR dithering: bins that report the beam/quadrature clash are re-solved
         with NSTR-2, then NSTR+2 (drt.f:536-554)."""
         res = {k: np.array(v, copy=True) for k, v in res.items()}
+        self._check_status(res["status"])
         for j in (1, 2):
             idx = np.nonzero(res["status"] == 1)[0]
             if len(idx) == 0:
@@ -1547,10 +1703,11 @@ class Sbdart:
                 sub[k] = b[k][idx]
             sub["nstr"] = nstr
             r2 = solve(sub)
+            self._check_status(r2["status"])
             for k in res:
                 res[k][idx] = r2[k]
         if (res["status"] != 0).any():
-            raise RuntimeError("Error --- NSTR dithering procedure failed")
+            raise RuntimeError("Error --- NSTR dithering procedure failed")      # drt.f:550-553
         return res
 
     @staticmethod

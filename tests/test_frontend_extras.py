@@ -303,7 +303,7 @@ def test_chkin_rejects_what_the_reference_rejects():
         with pytest.raises(ValueError, match=word):
             Sbdart(nl)
     ok = Sbdart("&INPUT vis=23 /")                       # a warning, not an error (errmsg 16)
-    assert ok.warnings == ["CHKIN--IAER=0, though VIS or TBAER set"]
+    assert ok.warnings == [(16, "CHKIN--IAER=0, though VIS or TBAER set")]
 
 
 def test_print_and_stop_modes():

@@ -75,3 +75,41 @@ def test_sharded_run_prints_the_same_records():
             p.join(120)
             assert p.exitcode == 0
         assert got[0] == want and got[1] == want
+
+
+def _failing_worker(rank, world, port, nl, q):
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from sbdart_b200.frontend import Sbdart
+    from solvers import solve_oracle
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+
+    def solve(b):
+        if rank == 1:
+            raise RuntimeError("boom on rank 1")
+        return solve_oracle(b, nthreads=2)
+    try:
+        Sbdart(nl).run_sharded(solve, dist)
+        q.put((rank, "returned"))
+    except RuntimeError as e:
+        q.put((rank, str(e)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_run_raises_on_every_rank_when_one_rank_fails():
+    """A rank whose solve raises must not leave the other rank blocked in the all-gather."""
+    nl = "&INPUT idatm=4, wlinf=.3, wlsup=.5, wlinc=.02, iout=1 /"
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = 33000 + os.getpid() % 2000
+    procs = [ctx.Process(target=_failing_worker, args=(r, 2, port, nl, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0, "a rank hung or crashed"
+    got = dict(q.get() for _ in range(2))
+    assert got[1] == "boom on rank 1"
+    assert "another rank" in got[0]
