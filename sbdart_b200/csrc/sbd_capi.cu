@@ -256,7 +256,8 @@ extern "C" int sbd_disort_batch_device(sbd_handle *h, const sbd_dims *dims, cons
     if (rc) return rc;
 
     size_t smem_limit = h->smem_optin ? h->smem_optin : 48 * 1024;
-    const bool fast = fast_supported(N) && NU == 0 && !getenv("SBD_FORCE_GENERIC");
+    // register kernel: NSTR 4/8/16; radiances at the layer boundaries (the mode SBDART uses)
+    const bool fast = fast_supported(N) && (NU == 0 || dims->ntau == 0) && !getenv("SBD_FORCE_GENERIC");
     int warps, grid;
     size_t slot;
     if (fast) {
@@ -265,7 +266,7 @@ extern "C" int sbd_disort_batch_device(sbd_handle *h, const sbd_dims *dims, cons
         warps = fast_warps();
         int cta_per_sm = 0;
         for (int wtry = warps; wtry >= 4; wtry /= 2) {
-            const size_t smem = fast_smem_bytes(N, L, NT, wtry);
+            const size_t smem = fast_smem_bytes(N, L, NT, wtry, NU, dims->nphi);
             if (smem > smem_limit) continue;
             int c = (int)((smem_limit + 1024) / (smem + 1024));
             if (c > 16 / wtry) c = 16 / wtry;
@@ -273,7 +274,7 @@ extern "C" int sbd_disort_batch_device(sbd_handle *h, const sbd_dims *dims, cons
         }
         if (cta_per_sm == 0) return SBD_ERR_UNSUPPORTED;
         grid = h->sm_count * cta_per_sm;
-        slot = fast_slot_doubles(N, L);
+        slot = fast_slot_doubles(N, L, NU);
     } else {
         warps = generic_pick_warps(N, L, NT, smem_limit);
         if (warps == 0) return SBD_ERR_UNSUPPORTED;

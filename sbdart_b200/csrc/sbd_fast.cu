@@ -89,13 +89,26 @@ struct FastLayout {
     // 2 x (pivot rows + flux record) (phase 3)
     static constexpr int cmax(int a, int b) { return a > b ? a : b; }
     static constexpr int work = cmax(cmax(tasks * task, 3 * rec + ublk), 2 * (ublk + frec));
-    __host__ __device__ static size_t warp_doubles(int L, int NT)
+    // radiance runs also stage the layer record in phase 3 (eigenvectors at the user angles)
+    static constexpr int work_rad = cmax(work, 2 * (ublk + frec + rec));
+    static constexpr int ecols = N + 3;            // eigen-terms + beam, Planck Z0, Z1 sources
+    // user-angle work values: E[N][ecols], GU[NU][ecols], running intensity [NU], cos(m dphi) [NPHI], g_l [N]
+    __host__ __device__ static size_t rad_doubles(int NU, int NPHI)
+    {
+        size_t d = (size_t)N * ecols + (size_t)NU * ecols + NU + NPHI + N;
+        return (d + 1) & ~(size_t)1;
+    }
+    __host__ __device__ static size_t warp_doubles(int L, int NT, int NU = 0, int NPHI = 0)
     {
         // y0, work area, taucpr/tauc, beam transmissions (2), pk(+2 boundary temps),
         // prologue work values, level map; kept even for 16-byte alignment
-        size_t d = (size_t)N + work + 4 * (L + 1) + (L + 3) + 3 * L + (NT + 1) / 2 + 2;
-        return (d + 1) & ~(size_t)1;
+        size_t d = (size_t)N + (NU > 0 ? work_rad : work) + 4 * (L + 1) + (L + 3) + 3 * L + (NT + 1) / 2 + 2;
+        d = (d + 1) & ~(size_t)1;
+        return d + (NU > 0 ? rad_doubles(NU, NPHI) : 0);
     }
+    // global scratch per warp: records, flux records, pivot rows (+ the downward-intensity
+    // source and transmission of every layer for the top-down pass of radiance runs)
+    __host__ __device__ static size_t slot_doubles_rad(int L, int NU) { return slot_doubles(L) + (size_t)2 * L * NU; }
 };
 
 __device__ __forceinline__ double shfl_d(double v, int src, int width)
@@ -636,32 +649,187 @@ __device__ __forceinline__ bool elim_step(double (&w)[FastLayout<n>::KS][FastLay
     return false;
 }
 
+// ---------------------------------------------------------------------------
+// radiance runs (RAD): intensities at the user angles
+// ---------------------------------------------------------------------------
+// Y_l^m(x), l = 0..N-1 (zero below l = m), the functions LEPOLY builds mode by mode
+// (disort.f:5286-5408); one lane, N <= 16
+__device__ __forceinline__ void lepoly_mode(int m, int N, double x, double *y)
+{
+    if (m == 0) {
+        y[0] = 1.0; y[1] = x;
+        for (int l = 2; l < N; l++) y[l] = ((2 * l - 1) * x * y[l - 1] - (l - 1) * y[l - 2]) / l;
+        return;
+    }
+    double d = 1.0;
+    const double s = sqrt(1.0 - x * x);
+    for (int k = 1; k <= m; k++) d = -sqrt((double)(2 * k - 1)) / sqrt((double)(2 * k)) * s * d;
+    for (int l = 0; l < m && l < N; l++) y[l] = 0.0;
+    if (m < N) y[m] = d;
+    if (m + 1 < N) y[m + 1] = sqrt((double)(2 * m + 1)) * x * d;
+    for (int l = m + 2; l < N; l++) {
+        const double t1 = sqrt((double)(l - m)) * sqrt((double)(l + m));
+        const double t2 = sqrt((double)(l - m - 1)) * sqrt((double)(l + m - 1));
+        y[l] = ((2 * l - 1) * x * y[l - 1] - t2 * y[l - 2]) / t1;
+    }
+}
+
+// User-angle terms of one layer for azimuth mode m (TERPEV disort.f:3920, TERPSO :3980):
+// the eigenvectors times the solution coefficients, the beam and the Planck particular
+// solutions re-expanded at the user cosines through the Legendre sum.
+//   E [l][c]  = 1/2 g_l sum_i w_i Y_l^m(mu_i) V_c(mu_i)     c < N: eigenvector c times x_c;
+//               c = N beam (+ the direct term), N+1 / N+2 Planck Z0 / Z1
+//   GU[iu][c] = sum_l E[l][c] Y_l^m(umu_iu)
+// rec: the layer record (shared); xs: the layer's solution (uniform registers).
+template <int n>
+__device__ __forceinline__ void user_terms_fast(
+    const double *rec, const double (&xs)[2 * n], const double *gl, const double *cwt,
+    const double *cylm, const double *y0, const double *__restrict__ ylmu_m, int NU, int mazim,
+    bool beam, double fact, bool therm, double oprim, double *E, double *GU, int lane)
+{
+    using FL = FastLayout<n>;
+    constexpr int N = 2 * n, EC = FL::ecols;
+    const double *gp = rec + FL::off_gp, *gm = rec + FL::off_gm;
+    const double *zz = rec + FL::off_zz, *zp0 = rec + FL::off_zp0;
+    const double xr0 = rec[FL::off_xr], xr1 = rec[FL::off_xr + 1];
+    double xl[N];
+#pragma unroll
+    for (int j = 0; j < N; j++) xl[j] = xs[j];
+    for (int e = lane; e < N * EC; e += 32) {
+        const int l = e / EC, c = e - l * EC;
+        double acc = 0.0;
+        if (l >= mazim) {
+            const double sg = ((l - mazim) & 1) ? -1.0 : 1.0;
+            const double *yl = cylm + l * n;
+            if (c < N) {
+                const bool plus = c >= n;
+                const int j = plus ? c - n : n - 1 - c;
+#pragma unroll
+                for (int i = 0; i < n; i++) {
+                    const double a = gp[i * n + j], b = gm[i * n + j];
+                    const double ev = plus ? fma(sg, b, a) : -fma(sg, a, b);
+                    acc = fma(cwt[i] * yl[i], ev, acc);
+                }
+                // x_c: the register array is indexed with a run-time c through a select chain
+                double xc = 0.0;
+#pragma unroll
+                for (int j2 = 0; j2 < N; j2++) xc = (c == j2) ? xl[j2] : xc;
+                acc *= 0.5 * gl[l] * xc;
+            } else if (c == N) {
+                if (beam) {
+#pragma unroll
+                    for (int i = 0; i < n; i++) acc = fma(cwt[i] * yl[i], fma(sg, zz[n - 1 - i], zz[n + i]), acc);
+                    acc = 0.5 * gl[l] * acc + fact * gl[l] * y0[l];
+                }
+            } else if (therm) {
+                if (c == N + 1) {
+#pragma unroll
+                    for (int i = 0; i < n; i++) acc = fma(cwt[i] * yl[i], fma(sg, zp0[n - 1 - i], zp0[n + i]), acc);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < n; i++) acc = fma(cwt[i] * yl[i], xr1 + sg * xr1, acc);
+                }
+                acc *= 0.5 * gl[l];
+            }
+        }
+        E[e] = acc;
+    }
+    __syncwarp();
+    for (int e = lane; e < NU * EC; e += 32) {
+        const int iu = e / EC, c = e - iu * EC;
+        double acc = 0.0;
+        for (int l = mazim; l < N; l++) acc = fma(E[l * EC + c], __ldg(ylmu_m + l * NU + iu), acc);
+        if (therm && c == N + 1) acc += (1. - oprim) * xr0;
+        if (therm && c == N + 2) acc += (1. - oprim) * xr1;
+        GU[e] = acc;
+    }
+    __syncwarp();
+}
+
+// Source-function integral of one layer for one user angle (USRINT, disort.f:4355-4793,
+// in recurrence form): the intensity leaving the layer towards the viewer is
+//   I(near boundary) = T I(far boundary) + S,   T = exp(-dtau' / |umu|),
+// with S the analytic integral of the layer's source terms; same L'Hospital limits as the
+// reference (|1 +- umu k| < 1e-4, |1 + umu/umu0| < 1e-4).  up: umu > 0, the near boundary is
+// the layer top; else the layer bottom.
+template <int n>
+__device__ __forceinline__ double layer_source(const double *gu /* GU row of this angle */, const double *kk,
+                                               const double *ek, double umu, double t0, double t1,
+                                               double eb0, double eb1 /* beam transmission at t0, t1 */,
+                                               bool beam, double umu0, bool therm, double &T)
+{
+    constexpr int N = 2 * n;
+    const double dtau = t1 - t0;
+    const bool up = umu > 0.0;
+    const double rmu = 1.0 / umu;
+    T = exp(-dtau * fabs(rmu));
+    double s = 0.0;
+    if (beam) {
+        const double denom = 1. + umu / umu0;
+        double expn;
+        if (fabs(denom) < 0.0001) expn = (dtau / umu0) * (up ? eb0 : eb1);
+        else expn = up ? (eb0 - T * eb1) / denom : (eb1 - T * eb0) / denom;
+        s = gu[N] * expn;
+    }
+#pragma unroll 1
+    for (int j = 0; j < n; j++) {
+        const double k = kk[j], wk = ek[j];
+        // column n-1-j belongs to -k_j, column n+j to +k_j (disort.f:3264-3312)
+        const double dm = 1.0 - umu * k, dp = 1.0 + umu * k;
+        double em, ep;
+        if (up) {
+            em = (fabs(dm) < 0.0001) ? dtau * rmu * T : (wk - T) / dm;
+            ep = (1.0 - T * wk) / dp;
+        } else {
+            em = (1.0 - T * wk) / dm;
+            ep = (fabs(dp) < 0.0001) ? -dtau * rmu * T : (wk - T) / dp;
+        }
+        s = fma(gu[n - 1 - j], em, s);
+        s = fma(gu[n + j], ep, s);
+    }
+    if (therm) {
+        const double f0 = 1.0 - T;
+        const double f1 = up ? (t0 + umu) - (t1 + umu) * T : (t1 + umu) - (t0 + umu) * T;
+        s = fma(gu[N + 1], f0, s);
+        s = fma(gu[N + 2], f1, s);
+    }
+    return s;
+}
+
 // WARPS warps per CTA, 16 warps per SM.  SYNC: the warps of a CTA move through the
 // phases together (CTA barriers between them), so that at any time they execute the
 // same code and share its instruction-cache lines; a warp that found no bin left
 // keeps attending the barriers until every warp of the CTA is out of work.
-template <int n, int WARPS, bool SYNC>
+// RAD: intensities at user angles (a.d.numu > 0): the phases are repeated for every azimuth
+// mode, phase 3 also re-expands the layer solutions at the user cosines and integrates the
+// source function (levels = layer boundaries, a.d.ntau == 0; always CTA-synchronous).
+template <int n, int WARPS, bool SYNC, bool RAD>
 __global__ void __launch_bounds__(WARPS * 32, 16 / WARPS)
 disort_fast_kernel(const LaunchArgs a)
 {
     using FL = FastLayout<n>;
     constexpr int N = 2 * n, TASKS = 32 / n, KS = FL::KS, LC = FL::LC, US = FL::US;
+    static_assert(!RAD || SYNC, "radiance runs reload the CTA's Legendre table per azimuth mode");
     const int L = a.d.nlyr;
     const int NT = a.d.ntau > 0 ? a.d.ntau : L + 1;
+    const int NU = RAD ? a.d.numu : 0, NPHI = RAD ? a.d.nphi : 0;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
     const int ldp = a.d.nmom + 1;
     extern __shared__ double smem_fast[];
     double *cmu = smem_fast, *cwt = cmu + n, *csq = cwt + n, *cdinv = csq + n;
     double *cylm = cdinv + n + 2;       // cylm[-2] = sum(w mu), cylm[-1] = sum(w)
-    double *wsm = smem_fast + FL::cta + (size_t)warp * FL::warp_doubles(L, NT);
+    double *wsm = smem_fast + FL::cta + (size_t)warp * FL::warp_doubles(L, NT, NU, NPHI);
     double *y0 = wsm;
     // 16-byte aligned work area: per-task areas in phase 1, cp.async staging afterwards
     double *tsm_base = y0 + N;
-    double *taucpr = tsm_base + FL::work, *tauc = taucpr + (L + 1);
+    double *taucpr = tsm_base + (RAD ? FL::work_rad : FL::work), *tauc = taucpr + (L + 1);
     double *ebeam = tauc + (L + 1), *edir = ebeam + (L + 1);   // exp(-tau'/mu0), exp(-tau/mu0)
     double *pk = edir + (L + 1);
     double *lw = pk + (L + 3);                                   // 3 x L prologue work values
     int *layru = (int *)(lw + 3 * L);
+    // radiance work values, behind the level map
+    double *uE = wsm + (FL::warp_doubles(L, NT, NU, NPHI) - FL::rad_doubles(NU, NPHI));
+    double *uGU = uE + N * FL::ecols, *uI = uGU + NU * FL::ecols, *cosm = uI + NU, *ugl = cosm + NPHI;
 
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         double mu = a.quad[i], wt = a.quad[n + i];
@@ -681,6 +849,7 @@ disort_fast_kernel(const LaunchArgs a)
     double *recs = scr;                                   // [L][rec]
     double *frecs = scr + (size_t)L * FL::rec;            // [L][frec]
     double *ublk = frecs + (size_t)L * FL::frec;          // [L][N][US]
+    double *dscr = ublk + (size_t)L * FL::ublk;           // RAD: [L][2][NU] downward source, transmission
     const int g = lane % n, task = lane / n;
     double *tsm = tsm_base + (size_t)task * FL::task;
     const int rg = lane >> 2, cg = lane & 3;              // 2-D tiling of phase 2
@@ -814,17 +983,46 @@ disort_fast_kernel(const LaunchArgs a)
             if (o_dfdt) o_dfdt[lu] = 0.0;
             if (o_uavg) o_uavg[lu] = 0.0;
         }
+        double *o_uu = nullptr;
+        int naz = 0, kconv = 0;
+        if (RAD) {
+            if (have) {
+                o_uu = a.uu + (size_t)bin * NPHI * NT * NU;
+                for (int e = lane; e < NPHI * NT * NU; e += 32) o_uu[e] = 0.0;
+            }
+            // number of azimuth modes (disort.f:577-586)
+            naz = N - 1;
+            const double u0 = a.umu[0], u1 = NU > 1 ? a.umu[1] : 0.0;
+            if (fbeam == 0.0 || fabs(1. - umu0) < 1.e-5 ||
+                (NU == 1 && fabs(1. - u0) < 1.e-5) || (NU == 1 && fabs(1. + u0) < 1.e-5) ||
+                (NU == 2 && fabs(1. + u0) < 1.e-5 && fabs(1. - u1) < 1.e-5))
+                naz = 0;
+        }
         __syncwarp();
 
         SBD_TICK(0);
+      for (int mazim = 0; ; mazim++) {
+        if (RAD) {
+            // every warp of the CTA works on the same mode: the Legendre table of the mode is
+            // CTA-shared (a warp without a mode left keeps attending the barriers)
+            const bool mact = !status && mazim <= naz;
+            if (!__syncthreads_or(mact)) break;
+            for (int e = threadIdx.x; e < N * n; e += blockDim.x) cylm[e] = a.ylmc[(size_t)mazim * N * n + e];
+            if (lane == 0 && fbeam > 0.0 && mazim > 0) lepoly_mode(mazim, N, -umu0, y0);
+            __syncthreads();
+        } else if (mazim > 0) break;
+        const bool mrun = !RAD || mazim <= naz;      // false: parked, only attends the barriers
+        const bool m0 = !RAD || mazim == 0;
+        const double delm0 = m0 ? 1.0 : 0.0;
+        const double *ylmu_m = RAD ? a.ylmu + (size_t)mazim * N * NU : nullptr;
         // ===================== phase 1 =====================================
-        if (!status) {
+        if (mrun && !status) {
             for (int lc0 = 0; lc0 < ncut; lc0 += TASKS) {
                 int lc = lc0 + task;
                 const bool active = lc < ncut;
                 if (!active) lc = ncut - 1;
-                int st = phase1_layers<n>(dtauc, ssalb, pmom, ldp, lc, active, 0, fbeam, umu0, plank,
-                                          1.0, cmu, cwt, csq, cdinv, cylm, y0, taucpr, pk, tsm,
+                int st = phase1_layers<n>(dtauc, ssalb, pmom, ldp, lc, active, RAD ? mazim : 0, fbeam, umu0,
+                                          plank && m0, delm0, cmu, cwt, csq, cdinv, cylm, y0, taucpr, pk, tsm,
                                           recs + (size_t)lc * FL::rec, frecs + (size_t)lc * FL::frec, g, jpart);
                 if (__any_sync(FULLMASK, st != 0)) { status = SBD_BIN_EIG_FAIL; break; }
             }
@@ -841,7 +1039,7 @@ disort_fast_kernel(const LaunchArgs a)
         // stage lc uses records lc and lc+1 while record lc+2 is in flight.
         double *rslot = tsm_base;   // phase-1 task areas are idle now
         double *stg = tsm_base + 3 * FL::rec;     // assembled rows of the current layer
-        if (!status) {
+        if (mrun && !status) {
             double w[KS][LC], rhs[KS];
             warp_copy_async(rslot, recs, FL::rec, lane);
             if (ncut > 1) warp_copy_async(rslot + FL::rec, recs + FL::rec, FL::rec, lane);
@@ -851,7 +1049,7 @@ disort_fast_kernel(const LaunchArgs a)
             // top boundary rows r = 0..n-1 in slots 0..n-1 (disort.f:2887-2915, :3547-3550)
             stage_rows<n>(stg, rslot, false, nullptr, 0, n, 0.0, cwt, cmu, lane);
             if (lane < n)
-                stg[lane * US + 4 * LC] = bp.fisot + tplank - rslot[FL::off_zz + lane] - rslot[FL::off_zp0 + lane];
+                stg[lane * US + 4 * LC] = (m0 ? bp.fisot + tplank : 0.0) - rslot[FL::off_zz + lane] - rslot[FL::off_zp0 + lane];
             __syncwarp();
 #pragma unroll
             for (int k = 0; k < KS; k++) {
@@ -897,12 +1095,14 @@ disort_fast_kernel(const LaunchArgs a)
                                                   (rn[FL::off_xr + 1] - rc[FL::off_xr + 1]) * tb;
                 } else {
                     // bottom boundary, Lambertian m = 0 (disort.f:2919-2990, :3552-3578)
-                    stage_rows<n>(stg, rc, true, nullptr, n, n, lyrcut ? 0.0 : 2.0 * albedo, cwt, cmu, lane);
+                    // (the Lambertian surface reflects the m = 0 mode only, disort.f:3753-3763)
+                    const bool refl = !lyrcut && m0;
+                    stage_rows<n>(stg, rc, true, nullptr, n, n, refl ? 2.0 * albedo : 0.0, cwt, cmu, lane);
                     if (lane < n) {
                         const int r = n + lane;
                         const double xr1 = rc[FL::off_xr + 1];
                         double v = -rc[FL::off_zz + r] * eb - rc[FL::off_zp0 + r] - xr1 * tb;
-                        if (!lyrcut) {
+                        if (refl) {
                             double rsum = 0.0;
 #pragma unroll 1
                             for (int k = 0; k < n; k++)
@@ -953,19 +1153,45 @@ disort_fast_kernel(const LaunchArgs a)
         SBD_TICK(2);
 
         // ===================== phase 3: back substitution + fluxes ===========
-        if (!status) {
+        if (mrun && !status) {
             double xs[N];          // solution of the layer below (uniform)
 #pragma unroll
             for (int j = 0; j < N; j++) xs[j] = 0.0;
             int lu_next = NT - 1;  // levels are visited bottom-up when the map is monotone
             // pivot rows + flux record of layer lc-1 stream into the other half of a
             // double buffer (cp.async) while layer lc is being solved
-            constexpr int kSlot = FL::ublk + FL::frec;
+            constexpr int kSlot = FL::ublk + FL::frec + (RAD ? FL::rec : 0);
             auto fetch_layer = [&](int lyr, int buf) {
                 double *dstp = tsm_base + buf * kSlot;
                 warp_copy_async(dstp, ublk + (size_t)lyr * FL::ublk, FL::ublk, lane);
                 warp_copy_async(dstp + FL::ublk, frecs + (size_t)lyr * FL::frec, FL::frec, lane);
+                if (RAD) warp_copy_async(dstp + FL::ublk + FL::frec, recs + (size_t)lyr * FL::rec, FL::rec, lane);
                 cp_async_commit();
+            };
+            // RAD: upward intensities are carried bottom-up along with the back substitution
+            // (one user angle per lane); bnd_up = intensity leaving the surface (disort.f:4747-4778)
+            double bnd_up = 0.0, azerr = 0.0;
+            const double rpd = kPiRef / 180.0;
+            if (RAD) {
+                for (int j = lane; j < NPHI; j += 32) cosm[j] = cos(mazim * (rpd * (a.phi[j] - bp.phi0)));
+                __syncwarp();
+            }
+            // adds this mode's term of the azimuth series at (level, angle) (disort.f:767-825)
+            auto emit = [&](int lu, int iu, double val) {
+                if (lu < 128 && !((a.uu_mask[lu >> 6] >> (lu & 63)) & 1ull)) return;
+                for (int j = 0; j < NPHI; j++) {
+                    double *pu = o_uu + ((size_t)j * NT + lu) * NU + iu;
+                    if (mazim == 0) { *pu = val; continue; }
+                    const double azterm = val * cosm[j];
+                    const double unew = *pu + azterm;
+                    *pu = unew;
+                    const double aa = fabs(azterm), bb = fabs(unew);       // RATIO, disort.f:6159
+                    double rr;
+                    if (aa == 0.0) rr = (bb == 0.0) ? 1.0 : 0.0;
+                    else if (bb == 0.0) rr = 1.79e308;
+                    else rr = aa / bb;
+                    azerr = fmax(azerr, rr);
+                }
             };
             fetch_layer(ncut - 1, 0);
             for (int lc = ncut - 1; lc >= 0; lc--) {
@@ -1012,7 +1238,7 @@ disort_fast_kernel(const LaunchArgs a)
                 // ---- fluxes at the levels living in this layer (FLUXES, disort.f:1780) ----
                 if (fastmap)
                     while (lu_next >= 0 && layru[lu_next] > lc + 1) lu_next--;
-                for (int lu = fastmap ? lu_next : NT - 1; lu >= 0; lu--) {
+                for (int lu = fastmap ? lu_next : NT - 1; lu >= 0 && m0; lu--) {
                     if (layru[lu] != lc + 1) { if (fastmap) break; else continue; }
                     if (fastmap) lu_next = lu - 1;
                     const bool atbot = (a.d.ntau == 0 && lu == lc + 1);
@@ -1093,6 +1319,8 @@ disort_fast_kernel(const LaunchArgs a)
                     }
                     const double sdn = __shfl_sync(FULLMASK, dot, 1);
                     const double sav = __shfl_sync(FULLMASK, dot, 2);
+                    if (RAD && lu == L && !lyrcut)      // Lambertian surface, m = 0 (disort.f:4747-4778)
+                        bnd_up = 2.0 * albedo * sdn + umu0 * fbeam / kPiRef * albedo * fact + (1.0 - albedo) * bplank;
                     if (lane == 0) {
                         const double pi = kPiRef;
                         const double dirint = fbeam * fact;
@@ -1112,12 +1340,81 @@ disort_fast_kernel(const LaunchArgs a)
                         if (o_dfdt) o_dfdt[lu] = sc[8] * 4. * pi * (uavg - plsorc);
                     }
                 }
+                if (RAD) {
+                    // ---- intensities at the user angles (TERPEV, TERPSO, USRINT) ----
+                    const double *urec = fr + FL::frec;
+                    const double *sc = fr + FL::f_sc;
+                    double ss = ssalb[lc];
+                    if (ss == 1.0) ss = 1.0 - kDither;
+                    const double f = pmom[(size_t)lc * ldp + N];
+                    const double oprim = ss * (1. - f) / (1. - f * ss);
+                    (void)sc;
+                    if (lane < N) {                      // g_l of this layer (delta-M, disort.f:2583)
+                        const double pm = (lane == 0) ? 1.0 : pmom[(size_t)lc * ldp + lane];
+                        ugl[lane] = (2 * lane + 1) * oprim * (pm - f) / (1. - f);
+                    }
+                    __syncwarp();
+                    const bool therm = plank && m0;
+                    if (lc == ncut - 1)                   // intensity entering the bottom layer from below
+                        for (int iu = lane; iu < NU; iu += 32) uI[iu] = (a.umu[iu] > 0.0 && m0 && !lyrcut) ? bnd_up : 0.0;
+                    // level at the bottom of the bottom layer
+                    if (lc == ncut - 1)
+                        for (int iu = lane; iu < NU; iu += 32)
+                            if (a.umu[iu] > 0.0) emit(ncut, iu, uI[iu]);
+                    __syncwarp();
+                    user_terms_fast<n>(urec, xs, ugl, cwt, cylm, y0, ylmu_m, NU, mazim, fbeam > 0.0,
+                                       (2. - delm0) * fbeam / (4.0 * kPiRef), therm, oprim, uE, uGU, lane);
+                    for (int iu = lane; iu < NU; iu += 32) {
+                        const double umu = a.umu[iu];
+                        double T;
+                        const double S = layer_source<n>(uGU + iu * FL::ecols, urec + FL::off_kk, urec + FL::off_ek,
+                                                         umu, taucpr[lc], taucpr[lc + 1], ebeam[lc], ebeam[lc + 1],
+                                                         fbeam > 0.0, umu0, therm, T);
+                        if (umu > 0.0) {
+                            const double below = T * uI[iu];
+                            const double v = below + S;
+                            uI[iu] = v;
+                            // level lc = top of layer lc.  The reference drops the source integral of
+                            // the layer that contains the level when the level lies within 1e-6
+                            // (scaled depth) of the boundary the light leaves through
+                            // (disort.f:4635-4641); with levels at the layer boundaries that is the
+                            // top layer seen from level 0 -- kept so that thin cap layers agree
+                            emit(lc, iu, (lc == 0 && taucpr[1] - taucpr[0] < 1.e-6) ? below : v);
+                        } else {                          // kept for the top-down pass
+                            dscr[((size_t)lc * 2) * NU + iu] = S;
+                            dscr[((size_t)lc * 2 + 1) * NU + iu] = T;
+                        }
+                    }
+                }
                 __syncwarp();     // everyone is done with this half of the double buffer
 #ifdef SBD_PHASE_TIMING
                 if (threadIdx.x == 0) { const long long t = clock64(); atomicAdd(&g_phase_ticks[6], (unsigned long long)(t - tsub)); tsub = t; }
 #endif
             }
+            if (RAD) {
+                // downward intensities, top-down (disort.f:4735-4741: the top boundary emits
+                // FISOT + TPLANK in the m = 0 mode)
+                for (int iu = lane; iu < NU; iu += 32) {
+                    if (a.umu[iu] > 0.0) continue;
+                    double v = m0 ? bp.fisot + tplank : 0.0;
+                    emit(0, iu, v);
+                    for (int lc = 0; lc < ncut; lc++) {
+                        const double above = dscr[((size_t)lc * 2 + 1) * NU + iu] * v;
+                        v = above + dscr[((size_t)lc * 2) * NU + iu];
+                        // (same rule: a layer thinner than 1e-6 directly above the level, disort.f:4635-4641)
+                        emit(lc + 1, iu, (taucpr[lc + 1] - taucpr[lc] < 1.e-6) ? above : v);
+                    }
+                }
+                if (mazim > 0) {
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) azerr = fmax(azerr, __shfl_xor_sync(FULLMASK, azerr, o));
+                    if (azerr <= bp.accur) kconv++;
+                    if (kconv >= 2) naz = mazim;       // converged: no further modes (disort.f:821-823)
+                }
+                __syncwarp();
+            }
         }
+      }   // azimuth modes
         cp_async_wait_all();
         if (lane == 0 && have) a.status[bin] = status;
         __syncwarp();
@@ -1152,13 +1449,13 @@ static bool fast_sync(int warps)
     return e ? atoi(e) != 0 : warps > 4;
 }
 
-template <int n, int WARPS, bool SYNC>
+template <int n, int WARPS, bool SYNC, bool RAD>
 static cudaError_t launch_fast_k(const LaunchArgs &a, int grid, size_t smem, cudaStream_t st)
 {
-    cudaError_t e = cudaFuncSetAttribute(disort_fast_kernel<n, WARPS, SYNC>,
+    cudaError_t e = cudaFuncSetAttribute(disort_fast_kernel<n, WARPS, SYNC, RAD>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    disort_fast_kernel<n, WARPS, SYNC><<<grid, WARPS * 32, smem, st>>>(a);
+    disort_fast_kernel<n, WARPS, SYNC, RAD><<<grid, WARPS * 32, smem, st>>>(a);
     return cudaGetLastError();
 }
 
@@ -1166,33 +1463,40 @@ template <int n>
 static cudaError_t launch_fast_t(const LaunchArgs &a, int warps, int grid, cudaStream_t st)
 {
     const int L = a.d.nlyr, NT = a.d.ntau > 0 ? a.d.ntau : L + 1;
-    size_t smem = 8 * (FastLayout<n>::cta + (size_t)warps * FastLayout<n>::warp_doubles(L, NT));
+    size_t smem = 8 * (FastLayout<n>::cta + (size_t)warps * FastLayout<n>::warp_doubles(L, NT, a.d.numu, a.d.nphi));
+    if (a.d.numu > 0) {      // radiance runs: CTA-synchronous always
+        switch (warps) {
+        case 4: return launch_fast_k<n, 4, true, true>(a, grid, smem, st);
+        case 8: return launch_fast_k<n, 8, true, true>(a, grid, smem, st);
+        }
+        return cudaErrorInvalidValue;
+    }
     const bool sync = fast_sync(warps);
     switch (warps) {
-    case 4: return sync ? launch_fast_k<n, 4, true>(a, grid, smem, st) : launch_fast_k<n, 4, false>(a, grid, smem, st);
-    case 8: return launch_fast_k<n, 8, true>(a, grid, smem, st);
+    case 4: return sync ? launch_fast_k<n, 4, true, false>(a, grid, smem, st) : launch_fast_k<n, 4, false, false>(a, grid, smem, st);
+    case 8: return launch_fast_k<n, 8, true, false>(a, grid, smem, st);
     }
     return cudaErrorInvalidValue;
 }
 
 bool fast_supported(int N) { return N == 4 || N == 8 || N == 16; }
 
-size_t fast_slot_doubles(int N, int L)
+size_t fast_slot_doubles(int N, int L, int NU)
 {
     switch (N) {
-    case 4: return FastLayout<2>::slot_doubles(L);
-    case 8: return FastLayout<4>::slot_doubles(L);
-    case 16: return FastLayout<8>::slot_doubles(L);
+    case 4: return FastLayout<2>::slot_doubles_rad(L, NU);
+    case 8: return FastLayout<4>::slot_doubles_rad(L, NU);
+    case 16: return FastLayout<8>::slot_doubles_rad(L, NU);
     }
     return 0;
 }
 
-size_t fast_smem_bytes(int N, int L, int NT, int warps)
+size_t fast_smem_bytes(int N, int L, int NT, int warps, int NU, int NPHI)
 {
     switch (N) {
-    case 4: return 8 * (FastLayout<2>::cta + (size_t)warps * FastLayout<2>::warp_doubles(L, NT));
-    case 8: return 8 * (FastLayout<4>::cta + (size_t)warps * FastLayout<4>::warp_doubles(L, NT));
-    case 16: return 8 * (FastLayout<8>::cta + (size_t)warps * FastLayout<8>::warp_doubles(L, NT));
+    case 4: return 8 * (FastLayout<2>::cta + (size_t)warps * FastLayout<2>::warp_doubles(L, NT, NU, NPHI));
+    case 8: return 8 * (FastLayout<4>::cta + (size_t)warps * FastLayout<4>::warp_doubles(L, NT, NU, NPHI));
+    case 16: return 8 * (FastLayout<8>::cta + (size_t)warps * FastLayout<8>::warp_doubles(L, NT, NU, NPHI));
     }
     return 0;
 }

@@ -100,7 +100,7 @@ def test_c3_every_bin_fluxes_and_radiances(solver, nl, modes):
     _compare_radiances(got, ref, 2e-6)
     if modes > 1:       # the sunlit run really has azimuth structure
         top = ref["uu"][:, :, 0, :]
-        assert (np.abs(top[:, 0, :] - top[:, 9, :]) > 1e-3 * np.abs(top).max()).any()
+        assert (np.abs(top[:, 0, :] - top[:, 9, :]) > 1e-5 * np.abs(top[:, 0, :])).any()
     # and the level selection the front end uses (ntop / nbot only) returns the same numbers
     bsel = _batch(nl)
     gsel = make_solve_cuda(solver)(bsel)
