@@ -137,6 +137,13 @@ int sbd_synchronize(sbd_handle *h);
  * L+1 levels would dominate the call).  Fluxes are not affected. */
 int sbd_set_radiance_levels(sbd_handle *h, const int32_t *levels, int32_t n);
 
+/* Layout of uu in the following batched calls while a level selection is active:
+ * packed = 0 (default) the full layout uu[B][nphi][NT][numu] described above;
+ * packed = 1 the selected levels only, ascending: uu[B][nphi][nsel][numu] -- host-buffer and
+ * device-pointer calls alike (no zero fill, no scatter: what a caller that reads one or two
+ * levels per bin wants).  Without a selection uu is always the full layout. */
+int sbd_set_radiance_layout(sbd_handle *h, int32_t packed);
+
 /* CORINT of DISORT (disort.f:112-118, INTCOR disort.f:2044-2297) for the following
  * batched radiance calls on this handle: 0 (default) off, 1 on.  When on, the
  * Nakajima-Tanaka TMS and IMS corrections are added to uu after the solve; pmom

@@ -31,7 +31,7 @@ EXPORTS = (
     "sbd_synchronize", "sbd_stream", "sbd_kernel_launches", "sbd_quadrature",
     "sbd_status_string", "sbd_abi_version", "disort_", "sbd_disort_last_status",
     "sbd_measure_fp64_peak", "sbd_optics_upload_tables", "sbd_spectrum_run",
-    "sbd_set_radiance_levels", "sbd_spectrum_set_aerosols", "sbd_set_corint", "sbd_build_id",
+    "sbd_set_radiance_levels", "sbd_spectrum_set_aerosols", "sbd_set_corint", "sbd_build_id", "sbd_set_radiance_layout",
 )
 
 
@@ -109,6 +109,8 @@ def lib():
     L.sbd_set_corint.argtypes = [C.c_void_p, C.c_int32]
     L.sbd_set_radiance_levels.restype = C.c_int
     L.sbd_set_radiance_levels.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
+    L.sbd_set_radiance_layout.restype = C.c_int
+    L.sbd_set_radiance_layout.argtypes = [C.c_void_p, C.c_int32]
     L.sbd_measure_fp64_peak.restype = C.c_int
     L.sbd_measure_fp64_peak.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
     L.sbd_disort_last_status.restype = C.c_int
@@ -196,12 +198,14 @@ class Solver:
             raise SbdError(rc, "sbd_set_radiance_levels")
 
     def disort_batch(self, dtauc, ssalb, pmom, bins, *, nstr, temper=None, utau=None,
-                     umu=None, phi=None, out=None, uu_levels=None, corint=False):
+                     umu=None, phi=None, out=None, uu_levels=None, corint=False, uu_packed=False):
         """Batched DISORT on host arrays.
 
         dtauc, ssalb [B][L]; pmom [B][L][nmom+1]; bins = make_bins(...);
         temper [ncol][L+1]; utau [B][ntau] (USRTAU) or None (layer boundaries).
-        Returns dict(rfldir, rfldn, flup, dfdt, uavg [B][NT], status [B]).
+        Returns dict(rfldir, rfldn, flup, dfdt, uavg [B][NT], status [B]) and, for radiance
+        runs, uu [B][nphi][NT][numu]; with uu_levels and uu_packed=True uu holds the selected
+        levels only, ascending ([B][nphi][nsel][numu], returned with "uu_levels").
         """
         dtauc, ssalb, pmom = _f64(dtauc), _f64(ssalb), _f64(pmom)
         B, L = dtauc.shape
@@ -228,7 +232,11 @@ class Solver:
         if out is None:
             out = {k: np.empty((B, NT)) for k in ("rfldir", "rfldn", "flup", "dfdt", "uavg")}
             out["status"] = np.empty(B, np.int32)
-            if d.numu > 0:
+            if d.numu > 0 and uu_levels is not None and uu_packed:
+                lv = sorted(set(int(v) for v in uu_levels))
+                out["uu"] = np.empty((B, d.nphi, len(lv), d.numu))
+                out["uu_levels"] = lv
+            elif d.numu > 0:
                 # selected levels only are copied back (sbd_set_radiance_levels): the rest stays zero
                 out["uu"] = (np.zeros if uu_levels is not None else np.empty)((B, d.nphi, NT, d.numu))
         p = lambda a: None if a is None else a.ctypes.data  # noqa: E731
@@ -236,6 +244,9 @@ class Solver:
             self.set_radiance_levels(uu_levels)
         if corint:          # CORINT=.TRUE.: Nakajima-Tanaka corrections after the solve
             lib().sbd_set_corint(self._h, 1)
+        packed = bool(uu_packed and uu_levels is not None and d.numu > 0)
+        if packed:
+            lib().sbd_set_radiance_layout(self._h, 1)
         try:
             rc = lib().sbd_disort_batch(
                 self._h, C.byref(d), p(dtauc), p(ssalb), p(pmom), p(bins), p(tp), p(ut), p(um),
@@ -246,6 +257,8 @@ class Solver:
                 self.set_radiance_levels(None)
             if corint:
                 lib().sbd_set_corint(self._h, 0)
+            if packed:
+                lib().sbd_set_radiance_layout(self._h, 0)
         if rc:
             raise SbdError(rc, "sbd_disort_batch")
         return out

@@ -192,6 +192,22 @@ extern "C" int sbd_set_radiance_levels(sbd_handle *h, const int32_t *levels, int
     return SBD_SUCCESS;
 }
 
+extern "C" int sbd_set_radiance_layout(sbd_handle *h, int32_t packed)
+{
+    if (!h) return SBD_ERR_ARG;
+    h->uu_packed = packed != 0;
+    return SBD_SUCCESS;
+}
+
+// levels selected with sbd_set_radiance_levels, ascending
+static std::vector<int32_t> selected_levels(const sbd_handle *h, int NT)
+{
+    std::vector<int32_t> sel;
+    for (int lu = 0; lu < NT; lu++)
+        if (lu >= 128 || ((h->uu_mask[lu >> 6] >> (lu & 63)) & 1ull)) sel.push_back(lu);
+    return sel;
+}
+
 extern "C" int sbd_set_corint(sbd_handle *h, int32_t on)
 {
     if (!h) return SBD_ERR_ARG;
@@ -319,6 +335,13 @@ extern "C" int sbd_disort_batch_device(sbd_handle *h, const sbd_dims *dims, cons
     a.slot_stride = slot;
     a.nmodes = 1;
     a.uu_mask[0] = h->uu_mask[0]; a.uu_mask[1] = h->uu_mask[1];
+    {   // where each output level's intensities go
+        const std::vector<int32_t> sel = selected_levels(h, NT);
+        const bool packed = (h->uu_packed || h->uu_packed_once) && (int)sel.size() < NT;
+        for (int lu = 0; lu < SBD_MAX_NLYR + 2; lu++) a.uu_slot[lu] = -1;
+        for (size_t s = 0; s < sel.size(); s++) a.uu_slot[sel[s]] = (short)(packed ? (int)s : sel[s]);
+        a.uu_nt = packed ? (int)sel.size() : NT;
+    }
     SbdDevBuf &scr = h->scratch_set ? h->scratch2 : h->scratch;
     SbdDevBuf &ctr = h->scratch_set ? h->counter2 : h->counter;
     if (scr.reserve(a.slot_stride * (size_t)a.nslots * 8) != cudaSuccess) return SBD_ERR_CUDA;
@@ -335,20 +358,6 @@ extern "C" int sbd_disort_batch_device(sbd_handle *h, const sbd_dims *dims, cons
         h->launches += 1;
     }
     return SBD_SUCCESS;
-}
-
-// uu[b][j][sel[s]][iu] -> pack[b][j][s][iu]: only the levels selected with
-// sbd_set_radiance_levels cross PCIe (SBDART reads one or two of the L+1 levels)
-__global__ void pack_levels_kernel(const double *uu, double *pack, const int32_t *sel, int nsel,
-                                   int NT, int NU, size_t total)
-{
-    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
-        const int iu = (int)(e % NU);
-        const size_t t = e / NU;
-        const int s = (int)(t % nsel);
-        const size_t bj = t / nsel;
-        pack[e] = uu[(bj * NT + sel[s]) * NU + iu];
-    }
 }
 
 extern "C" int sbd_disort_batch(sbd_handle *h, const sbd_dims *dims, const double *dtauc,
@@ -396,23 +405,22 @@ extern "C" int sbd_disort_batch(sbd_handle *h, const sbd_dims *dims, const doubl
     }
     const size_t per = B * NT;
     const size_t nuu1 = (size_t)dims->numu * dims->nphi * NT;      // uu doubles per bin
-    if (nuu1) CK(h->d_uu.reserve(nuu1 * B * 8));
-    // level selection (sbd_set_radiance_levels): copy back a compact array and scatter on the host
+    // level selection (sbd_set_radiance_levels): the kernels write the selected levels only
+    // (packed layout) and only those cross PCIe; with the full layout on the caller's side
+    // they are scattered into uu on the host, the other levels of uu are left untouched
     std::vector<int32_t> sel;
     std::vector<double> uustage;
     size_t npack1 = 0;                                             // packed uu doubles per bin
     if (nuu1) {
-        for (size_t lu = 0; lu < NT; lu++)
-            if (lu >= 128 || ((h->uu_mask[lu >> 6] >> (lu & 63)) & 1ull)) sel.push_back((int32_t)lu);
+        sel = selected_levels(h, (int)NT);
         if (sel.size() == NT) sel.clear();                         // every level: plain copy
-        else if (sel.empty()) sel.push_back(0);
     }
+    if (nuu1 && sel.empty()) CK(h->d_uu.reserve(nuu1 * B * 8));
+    const bool caller_packed = h->uu_packed && !sel.empty();
     if (!sel.empty()) {
         npack1 = (size_t)dims->nphi * sel.size() * dims->numu;
         CK(h->d_uupack.reserve(npack1 * B * 8));
-        CK(h->d_sel.reserve(sel.size() * 4));
-        CK(cudaMemcpyAsync(h->d_sel.p, sel.data(), sel.size() * 4, cudaMemcpyHostToDevice, st));
-        uustage.resize(npack1 * B);
+        if (!caller_packed) uustage.resize(npack1 * B);
     }
     double *o = (double *)h->d_out.p;
     double *dst[5] = { rfldir, rfldn, flup, dfdt, uavg };
@@ -466,13 +474,16 @@ extern "C" int sbd_disort_batch(sbd_handle *h, const sbd_dims *dims, const doubl
         }
         sbd_dims dc = *dims;
         dc.nbins = (int32_t)nb;
+        h->uu_packed_once = !sel.empty();
         rc = sbd_disort_batch_device(
             h, &dc, (const double *)h->d_dtauc.p + b0 * L, (const double *)h->d_ssalb.p + b0 * L,
             (const double *)h->d_pmom.p + b0 * L * ldp, (const sbd_bin *)h->d_bins.p + b0, d_temper,
             dims->ntau > 0 ? (const double *)h->d_utau.p + b0 * NT : nullptr, umu, phi,
             o + b0 * NT, o + per + b0 * NT, o + 2 * per + b0 * NT, o + 3 * per + b0 * NT,
-            o + 4 * per + b0 * NT, nuu1 ? (double *)h->d_uu.p + b0 * nuu1 : nullptr,
+            o + 4 * per + b0 * NT,
+            !nuu1 ? nullptr : (sel.empty() ? (double *)h->d_uu.p + b0 * nuu1 : (double *)h->d_uupack.p + b0 * npack1),
             (int32_t *)h->d_status.p + b0, sk);
+        h->uu_packed_once = false;
         h->scratch_set = 0;
         if (rc) return rc;
         cudaStream_t so = nchunk > 1 ? h->copy_out : st;
@@ -484,23 +495,15 @@ extern "C" int sbd_disort_batch(sbd_handle *h, const sbd_dims *dims, const doubl
             if (dst[k]) CK(cudaMemcpyAsync(dst[k] + b0 * NT, o + k * per + b0 * NT, nb * NT * 8, cudaMemcpyDeviceToHost, so));
         if (nuu1 && sel.empty())
             CK(cudaMemcpyAsync(uu + b0 * nuu1, (double *)h->d_uu.p + b0 * nuu1, nb * nuu1 * 8, cudaMemcpyDeviceToHost, so));
-        if (nuu1 && !sel.empty()) {
-            const size_t total = nb * npack1;
-            const int blocks = (int)((total + 255) / 256 < 4096 ? (total + 255) / 256 : 4096);
-            pack_levels_kernel<<<blocks, 256, 0, so>>>((const double *)h->d_uu.p + b0 * nuu1,
-                                                       (double *)h->d_uupack.p + b0 * npack1,
-                                                       (const int32_t *)h->d_sel.p, (int)sel.size(),
-                                                       (int)NT, dims->numu, total);
-            CK(cudaGetLastError());
-            CK(cudaMemcpyAsync(uustage.data() + b0 * npack1, (double *)h->d_uupack.p + b0 * npack1, total * 8,
-                               cudaMemcpyDeviceToHost, so));
-        }
+        if (nuu1 && !sel.empty())
+            CK(cudaMemcpyAsync((caller_packed ? uu : uustage.data()) + b0 * npack1,
+                               (double *)h->d_uupack.p + b0 * npack1, nb * npack1 * 8, cudaMemcpyDeviceToHost, so));
         CK(cudaMemcpyAsync(status + b0, (int32_t *)h->d_status.p + b0, nb * 4, cudaMemcpyDeviceToHost, so));
     }
     CK(cudaStreamSynchronize(st));
     if (two) CK(cudaStreamSynchronize(h->stream2));
     if (nchunk > 1) CK(cudaStreamSynchronize(h->copy_out));
-    if (!sel.empty()) {                 // scatter the selected levels; the others are not written
+    if (!sel.empty() && !caller_packed) {   // scatter the selected levels; the others are not written
         const size_t NU = dims->numu, NP = dims->nphi, ns = sel.size();
         for (size_t b = 0; b < B; b++)
             for (size_t j = 0; j < NP; j++)

@@ -987,8 +987,8 @@ disort_fast_kernel(const LaunchArgs a)
         int naz = 0, kconv = 0;
         if (RAD) {
             if (have) {
-                o_uu = a.uu + (size_t)bin * NPHI * NT * NU;
-                for (int e = lane; e < NPHI * NT * NU; e += 32) o_uu[e] = 0.0;
+                o_uu = a.uu + (size_t)bin * NPHI * a.uu_nt * NU;
+                for (int e = lane; e < NPHI * a.uu_nt * NU; e += 32) o_uu[e] = 0.0;
             }
             // number of azimuth modes (disort.f:577-586)
             naz = N - 1;
@@ -1178,9 +1178,10 @@ disort_fast_kernel(const LaunchArgs a)
             }
             // adds this mode's term of the azimuth series at (level, angle) (disort.f:767-825)
             auto emit = [&](int lu, int iu, double val) {
-                if (lu < 128 && !((a.uu_mask[lu >> 6] >> (lu & 63)) & 1ull)) return;
+                const int slot = a.uu_slot[lu];
+                if (slot < 0) return;
                 for (int j = 0; j < NPHI; j++) {
-                    double *pu = o_uu + ((size_t)j * NT + lu) * NU + iu;
+                    double *pu = o_uu + ((size_t)j * a.uu_nt + slot) * NU + iu;
                     if (mazim == 0) { *pu = val; continue; }
                     const double azterm = val * cosm[j];
                     const double unew = *pu + azterm;

@@ -938,9 +938,9 @@ disort_generic_kernel(const LaunchArgs a)
             if (o_dfdt) o_dfdt[lu] = 0.0;
             if (o_uavg) o_uavg[lu] = 0.0;
         }
-        double *o_uu = (NU > 0 && a.uu && have) ? a.uu + (size_t)bin * a.d.nphi * NT * NU : nullptr;
+        double *o_uu = (NU > 0 && a.uu && have) ? a.uu + (size_t)bin * a.d.nphi * a.uu_nt * NU : nullptr;
         if (o_uu)
-            for (int e = lane; e < a.d.nphi * NT * NU; e += 32) o_uu[e] = 0.0;
+            for (int e = lane; e < a.d.nphi * a.uu_nt * NU; e += 32) o_uu[e] = 0.0;
 
         // number of azimuth modes (disort.f:577-586); flux-only runs need m = 0 only
         int naz = 0;
@@ -1194,12 +1194,8 @@ disort_generic_kernel(const LaunchArgs a)
             double azerr = 0.0;
             for (int e = lane; e < NT * NU; e += 32) {
                 const int lu = e / NU, iu = e - lu * NU;
-                if (lu < 128 && !((a.uu_mask[lu >> 6] >> (lu & 63)) & 1ull)) {
-                    // level not wanted (sbd_set_radiance_levels): zeros, no source integration
-                    if (mazim == 0)
-                        for (int j = 0; j < a.d.nphi; j++) o_uu[((size_t)j * NT + lu) * NU + iu] = 0.0;
-                    continue;
-                }
+                const int slot = a.uu_slot[lu];
+                if (slot < 0) continue;     // level not wanted (sbd_set_radiance_levels): stays zero
                 const int lyu = w.layru[lu];
                 double ut = a.d.ntau > 0 ? a.utau[(size_t)src * NT + lu] : w.tauc[lu];
                 if (a.d.ntau > 0 && fabs(ut - w.tauc[L]) <= 1.e-4) ut = w.tauc[L];
@@ -1209,7 +1205,7 @@ disort_generic_kernel(const LaunchArgs a)
                 const double val = usrint_one(c, w, ll, scr, NU, lu, iu, a.umu[iu], utp, c.fisot, bnd_up);
                 // Fourier sum over azimuth (disort.f:767-825)
                 for (int j = 0; j < a.d.nphi; j++) {
-                    double *pu = o_uu + ((size_t)j * NT + lu) * NU + iu;
+                    double *pu = o_uu + ((size_t)j * a.uu_nt + slot) * NU + iu;
                     if (mazim == 0) {
                         *pu = val;
                     } else {

@@ -47,6 +47,8 @@ struct sbd_handle {
     cudaStream_t stream2 = nullptr;
     cudaEvent_t ev_misc = nullptr;
     int scratch_set = 0;
+    bool uu_packed = false;                   // uu holds the selected levels only (sbd_set_radiance_layout)
+    bool uu_packed_once = false;              // host-buffer call: one packed device launch, then back to uu_packed
     unsigned long long uu_mask[2] = { ~0ull, ~0ull };   // levels at which uu is wanted                       // set used by the next device-level launch
     // staging for the host-pointer API
     SbdDevBuf d_dtauc, d_ssalb, d_pmom, d_bins, d_temper, d_utau, d_out, d_uu, d_status;

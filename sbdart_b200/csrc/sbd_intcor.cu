@@ -57,7 +57,7 @@ intcor_kernel(const LaunchArgs a)
     if (!(fbeam > 0.0)) return;
     const double *dtauc = a.dtauc + (size_t)src * L, *ssalb = a.ssalb + (size_t)src * L;
     const double *pmom = a.pmom + (size_t)src * L * ldp;
-    double *uu = a.uu + (size_t)bin * NP * NT * NU;
+    double *uu = a.uu + (size_t)bin * NP * a.uu_nt * NU;
 
     // ---- per-bin layer quantities (SETDIS, disort.f:2546-2625)
     double *ss = sm, *dt = ss + L, *tauc = dt + L, *taucpr = tauc + (L + 1), *flyr = taucpr + (L + 1),
@@ -125,7 +125,8 @@ intcor_kernel(const LaunchArgs a)
 
         // ---- TMS (two SINSCA calls of the reference folded into one sum)
         for (int lu = 0; lu < NT; lu++) {
-            if (lu < 128 && !((a.uu_mask[lu >> 6] >> (lu & 63)) & 1ull)) continue;
+            const int slot = a.uu_slot[lu];
+            if (slot < 0) continue;
             // level -> layer: the first layer whose interval holds the level (disort.f:2610-2625)
             int lyu = 1;
             const double ut = tauc[lu];
@@ -156,7 +157,7 @@ intcor_kernel(const LaunchArgs a)
                 pref = fbeam / (4. * pi * (1. + umu / umu0));
             }
             s = wsum(s);
-            if (lane == 0) uu[((size_t)jp * NT + lu) * NU + iu] += pref * s;
+            if (lane == 0) uu[((size_t)jp * a.uu_nt + slot) * NU + iu] += pref * s;
         }
 
         // ---- IMS: aureole within 10 degrees of the direct beam, downward directions
@@ -164,7 +165,8 @@ intcor_kernel(const LaunchArgs a)
             const double theta0 = acos(-umu0) / rpd, thetap = acos(umu) / rpd;
             if (fabs(theta0 - thetap) <= 10.) {
                 for (int lu = 1; lu < NT; lu++) {        // level 0 has utau = 0 <= DITHER: skipped
-                    if (lu < 128 && !((a.uu_mask[lu >> 6] >> (lu & 63)) & 1ull)) continue;
+                    const int slot = a.uu_slot[lu];
+                    if (slot < 0) continue;
                     int lyu = 1;
                     const double ut = tauc[lu];
                     while (lyu < L && !(ut >= tauc[lyu - 1] && ut <= tauc[lyu])) lyu++;
@@ -197,7 +199,7 @@ intcor_kernel(const LaunchArgs a)
                         const double umu0p = umu0 / (1. - fbar * wbar);
                         const double d = fbeam / (4. * pi) * (fbar * wbar) * (fbar * wbar) / (1. - fbar * wbar) *
                                          pspike * xifunc_eq(-umu, umu0p, ut);
-                        uu[((size_t)jp * NT + lu) * NU + iu] -= d;
+                        uu[((size_t)jp * a.uu_nt + slot) * NU + iu] -= d;
                     }
                 }
             }

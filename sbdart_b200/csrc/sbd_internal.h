@@ -32,6 +32,10 @@ struct LaunchArgs {
     const int32_t *binmap; // optional: bin b reads its inputs from slot binmap[b]
     const int32_t *nbins_dev; // optional: number of bins lives on the device (spectrum path)
     unsigned long long uu_mask[2]; // bit lu: intensities wanted at output level lu
+    // layout of uu: [bin][nphi][uu_nt][numu]; output level lu lives in slot uu_slot[lu]
+    // (-1: not wanted).  Full layout: uu_nt = NT, slot = level; packed: the wanted levels only.
+    int uu_nt;
+    short uu_slot[SBD_MAX_NLYR + 2];
 };
 
 // Per-layer record kept in scratch between the downward elimination sweep

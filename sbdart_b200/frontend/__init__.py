@@ -1512,8 +1512,9 @@ class Sbdart:
         NT = self.nz + 1
         keys = ["rfldir", "rfldn", "flup"] + (["uu"] if self.radcalc else [])
         empty = {k: np.zeros((0, NT)) for k in keys[:3]}
+        lv = b.get("uu_levels")             # levels the records consume: only those are gathered
         if self.radcalc:
-            empty["uu"] = np.zeros((0, len(self.phi), NT, len(self.umu)))
+            empty["uu"] = np.zeros((0, len(self.phi), NT if lv is None else len(lv), len(self.umu)))
         res, failure = empty, None
         if hi > lo:
             sub = dict(b)
@@ -1523,10 +1524,14 @@ class Sbdart:
                 res = solve(sub)
                 if (np.asarray(res["status"]) != 0).any():
                     res = self._retry(sub, res, solve)
+                if lv is not None and "uu_levels" not in res:
+                    res = dict(res, uu=np.ascontiguousarray(res["uu"][:, :, lv, :]))
             except Exception as e:          # noqa: BLE001 -- reported on every rank below
                 if world == 1:
                     raise
                 res, failure = empty, e
+        if lv is not None:
+            res = dict(res, uu_levels=lv)
         if world == 1:
             return self.records(rows, res)
         dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
@@ -1540,6 +1545,8 @@ class Sbdart:
             raise RuntimeError("run_sharded: the solve failed on another rank")
         full = {k: gather_outputs(torch.from_numpy(np.ascontiguousarray(res[k], dtype=np.float64)).to(dev),
                                   parts, dist).cpu().numpy() for k in keys}
+        if lv is not None:
+            full["uu_levels"] = lv
         return self.records(rows, full)
 
     def run_device(self, solver):
@@ -1548,7 +1555,8 @@ class Sbdart:
         from .device import device_aerosols_supported, run_spectrum
         host_solve = lambda b: solver.disort_batch(  # noqa: E731
             b["dtauc"], b["ssalb"], b["pmom"], b["bins"], nstr=b["nstr"], temper=b["temper"],
-            umu=b.get("umu"), phi=b.get("phi"), uu_levels=b.get("uu_levels"), corint=b.get("corint", False))
+            umu=b.get("umu"), phi=b.get("phi"), uu_levels=b.get("uu_levels"), corint=b.get("corint", False),
+            uu_packed=True)
         if (not device_aerosols_supported(self.aerosols) or self.p["imomc"] not in (2, 3) or
                 (self.radcalc and self.p["corint"])):
             # table phase functions (getmom 4/5, pmaer) and the 299-moment CORINT runs:
@@ -1571,6 +1579,9 @@ class Sbdart:
 
     def records(self, rows, res):
         """stdout0/1/2 (drt.f:892-1165): ordered accumulation and IOUT records."""
+        # a solver that returns the selected levels only (packed layout of the C ABI) says which
+        lv = None if res is None else res.get("uu_levels")
+        uslot = (lambda j: j) if lv is None else (lambda j: list(lv).index(j))
         out = []
         iout, nz = self.p["iout"], self.nz
         if iout in (1, 5, 6):
@@ -1612,7 +1623,7 @@ class Sbdart:
                     j = ntop if iout == 5 else nbot
                     if kd == 1:
                         uurs[:] = 0.
-                    uurs += res["uu"][ib][:, j, :].T * dwt
+                    uurs += res["uu"][ib][:, uslot(j), :].T * dwt
                     if kd == nk:
                         out.append(f"{self.nphi:4d}{self.nzen:4d}")
                         out += self._rows([_r4(x) for x in self.phi], 10)
@@ -1642,13 +1653,13 @@ class Sbdart:
                 botdir += rfldir[nbot] * dwt
             if iout in (20, 21):
                 j = ntop if iout == 20 else nbot
-                uurs += res["uu"][ib][:, j, :].T * dwt
+                uurs += res["uu"][ib][:, uslot(j), :].T * dwt
             if iout == 22:          # radiance at every level (drt.f:1065-1073)
                 uurl += np.transpose(res["uu"][ib][:, 1:nz + 1, :], (0, 2, 1)) * dwt
             if iout == 23:
                 for i in range(self.nzen):
                     j = ntop if self.uzen[self.nzen - 1 - i] < 90. else nbot
-                    uurs[i] += res["uu"][ib][:, j, i] * dwt
+                    uurs[i] += res["uu"][ib][:, uslot(j), i] * dwt
         # stdout2
         p = self.p
         if iout == 11:
@@ -1689,7 +1700,7 @@ class Sbdart:
     def _retry(self, b, res, solve):
         """NSTR dithering: bins that report the beam/quadrature clash are re-solved
         with NSTR-2, then NSTR+2 (drt.f:536-554)."""
-        res = {k: np.array(v, copy=True) for k, v in res.items()}
+        res = {k: (np.array(v, copy=True) if k != "uu_levels" else v) for k, v in res.items()}
         self._check_status(res["status"])
         for j in (1, 2):
             idx = np.nonzero(res["status"] == 1)[0]
@@ -1705,7 +1716,8 @@ class Sbdart:
             r2 = solve(sub)
             self._check_status(r2["status"])
             for k in res:
-                res[k][idx] = r2[k]
+                if k != "uu_levels":
+                    res[k][idx] = r2[k]
         if (res["status"] != 0).any():
             raise RuntimeError("Error --- NSTR dithering procedure failed")      # drt.f:550-553
         return res

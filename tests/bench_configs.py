@@ -32,39 +32,49 @@ def tile(w, rep):
     return w
 
 
-def check(w, got, nsample, umu=None, phi=None):
-    """Largest flux mismatch against the oracle on the first nsample bins, relative to the
-    bin's largest flux."""
+def check(w, got, nsample, kw):
+    """Largest mismatch against the oracle on the first nsample bins, relative to the bin's
+    largest flux (and, for radiance runs, largest intensity)."""
     idx = np.arange(min(nsample, len(w["bins"])))
-    b = w["bins"][idx]
-    ref = oracle.disort_flux_batch(
-        w["dtauc"][idx], w["ssalb"][idx], w["pmom"][idx], nstr=w["nstr"], fbeam=b["fbeam"],
-        umu0=b["umu0"], albedo=b["albedo"], plank=b["plank"], wvnmlo=b["wvnmlo"],
-        wvnmhi=b["wvnmhi"], btemp=b["btemp"], ttemp=b["ttemp"], temis=b["temis"],
-        fisot=b["fisot"], temper=w["temper"], col=b["col"], nthreads=os.cpu_count() or 1)
+    sub = {k: (w[k][idx] if k in ("dtauc", "ssalb", "pmom", "bins") else w[k]) for k in w}
+    sub["nstr"] = w["nstr"]
+    if kw.get("umu") is not None:
+        sub.update(umu=kw["umu"], phi=kw["phi"])
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from solvers import solve_oracle
+    ref = solve_oracle(sub, nthreads=os.cpu_count() or 1)
     ok = ref["status"] == 0
     worst = 0.0
     for k in ("rfldir", "rfldn", "flup"):
         scale = np.abs(ref["flup"][ok]).max(axis=1, keepdims=True) + np.abs(ref["rfldir"][ok]).max(axis=1, keepdims=True)
         err = np.abs(got[k][idx][ok] - ref[k][ok]) / np.maximum(scale, 1e-300)
         worst = max(worst, float(err.max()))
-    return worst, int((got["status"][idx] != ref["status"]).sum())
+    worst_uu = None
+    if "uu" in ref and "uu" in got:
+        lv = got.get("uu_levels") or list(range(ref["uu"].shape[2]))
+        r = ref["uu"][ok][:, :, lv, :]
+        scale = np.abs(r).reshape(len(r), -1).max(axis=1).reshape(-1, 1, 1, 1)
+        worst_uu = float((np.abs(got["uu"][idx][ok] - r) / np.maximum(scale, 1e-300)).max())
+    return worst, worst_uu, int((got["status"][idx] != ref["status"]).sum())
 
 
 def run(name, w, solver, reps=3, nsample=64, **kw):
-    t = []
-    got = None
-    for _ in range(reps + 1):
-        t0 = time.perf_counter()
-        got = solver.disort_batch(w["dtauc"], w["ssalb"], w["pmom"], w["bins"], nstr=w["nstr"],
-                                  temper=w["temper"], **kw)
-        t.append(time.perf_counter() - t0)
-    dt = min(t[1:])
-    worst, stat_mismatch = check(w, got, nsample)
+    """Device-resident and end-to-end (pinned host buffers, packed intensities) rates of one
+    batched call, and the mismatch of its results against the oracle on a sample."""
+    from sbdart_b200.timing import BatchTimer
+    t = BatchTimer(solver, w, umu=kw.get("umu"), phi=kw.get("phi"), uu_levels=kw.get("uu_levels"))
+    ms_dev = t.device_ms(steps=reps, warmup=2)
+    ms_e2e = t.e2e_ms(steps=reps, warmup=1)
+    got = t.results(device=False)
+    worst, worst_uu, stat_mismatch = check(w, got, nsample, kw)
     B = len(w["bins"])
     print(json.dumps({"config": name, "bins": B, "nstr": w["nstr"], "nlyr": int(w["dtauc"].shape[1]),
-                      "e2e_bins_per_s": B / dt, "ms": dt * 1e3, "bad_bins": int((got["status"] != 0).sum()),
-                      "max_flux_err_over_bin_scale_vs_oracle": worst, "status_mismatch": stat_mismatch,
+                      "device_bins_per_s": B / (ms_dev * 1e-3), "device_ms": ms_dev,
+                      "e2e_bins_per_s": B / (ms_e2e * 1e-3), "e2e_ms": ms_e2e,
+                      "h2d_bytes": t.h2d_bytes, "d2h_bytes": t.d2h_bytes,
+                      "bad_bins": int((got["status"] != 0).sum()),
+                      "max_flux_err_over_bin_scale_vs_oracle": worst,
+                      "max_radiance_err_over_bin_scale_vs_oracle": worst_uu, "status_mismatch": stat_mismatch,
                       "oracle_sample": min(nsample, B), **{k: (len(v) if hasattr(v, "__len__") else v) for k, v in kw.items()}}),
           flush=True)
 

@@ -26,9 +26,10 @@ def solve_oracle(b, nthreads=8):
     return {k: np.array(v) for k, v in outs.items()}
 
 
-def make_solve_cuda(solver):
+def make_solve_cuda(solver, packed=False):
+    """packed: with a level selection, uu comes back as [B][nphi][nsel][numu] (+ "uu_levels")."""
     def solve(b):
         return solver.disort_batch(b["dtauc"], b["ssalb"], b["pmom"], b["bins"], nstr=b["nstr"],
                                    temper=b["temper"], umu=b.get("umu"), phi=b.get("phi"), uu_levels=b.get("uu_levels"),
-                                   corint=b.get("corint", False))
+                                   corint=b.get("corint", False), uu_packed=packed)
     return solve
