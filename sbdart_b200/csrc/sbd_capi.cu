@@ -274,9 +274,20 @@ extern "C" int sbd_disort_batch_device(sbd_handle *h, const sbd_dims *dims, cons
     size_t smem_limit = h->smem_optin ? h->smem_optin : 48 * 1024;
     // register kernel: NSTR 4/8/16; radiances at the layer boundaries (the mode SBDART uses)
     const bool fast = fast_supported(N) && (NU == 0 || dims->ntau == 0) && !getenv("SBD_FORCE_GENERIC");
+    // CTA-per-bin register kernel: NSTR 20/24/32, fluxes
+    const bool wide = !fast && wide_supported(N) && NU == 0 && !getenv("SBD_FORCE_GENERIC") &&
+                      wide_smem_bytes(N, L, NT) <= smem_limit;
     int warps, grid;
     size_t slot;
-    if (fast) {
+    if (wide) {
+        const size_t smem = wide_smem_bytes(N, L, NT);
+        int cta_per_sm = (int)((smem_limit + 1024) / (smem + 1024));
+        if (cta_per_sm > 2) cta_per_sm = 2;          // register budget (launch bounds)
+        if (cta_per_sm < 1) cta_per_sm = 1;
+        grid = h->sm_count * cta_per_sm;
+        warps = 1;                                   // scratch slots and work items per CTA
+        slot = wide_slot_doubles(N, L);
+    } else if (fast) {
         // CTA shape: the preferred one (8 warps) unless 4-warp CTAs keep more warps
         // resident per SM under the shared-memory limit (deep atmospheres)
         warps = fast_warps();
@@ -348,7 +359,8 @@ extern "C" int sbd_disort_batch_device(sbd_handle *h, const sbd_dims *dims, cons
     a.scratch = (double *)scr.p;
     a.work_counter = (int *)ctr.p;
     if (cudaMemsetAsync(a.work_counter, 0, sizeof(int), st) != cudaSuccess) return SBD_ERR_CUDA;
-    cudaError_t le = fast ? launch_fast(a, warps, grid, st) : launch_generic(a, warps, grid, st);
+    cudaError_t le = wide ? launch_wide(a, grid, st)
+                          : (fast ? launch_fast(a, warps, grid, st) : launch_generic(a, warps, grid, st));
     if (le != cudaSuccess) return SBD_ERR_CUDA;
     h->launches += 1;
     if (NU > 0 && h->corint) {         // INTCOR (disort.f:827-835): layer boundaries only

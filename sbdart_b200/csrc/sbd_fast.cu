@@ -34,10 +34,9 @@
 
 #include "sbd_internal.h"
 #include "sbd_planck.cuh"
+#include "sbd_devutil.cuh"
 
 namespace sbd {
-
-#define FULLMASK 0xffffffffu
 
 #ifdef SBD_PHASE_TIMING
 // debug build only: SM-clock ticks spent between the phase barriers, summed over CTAs
@@ -110,55 +109,6 @@ struct FastLayout {
     // source and transmission of every layer for the top-down pass of radiance runs)
     __host__ __device__ static size_t slot_doubles_rad(int L, int NU) { return slot_doubles(L) + (size_t)2 * L * NU; }
 };
-
-__device__ __forceinline__ double shfl_d(double v, int src, int width)
-{
-    return __shfl_sync(FULLMASK, v, src, width);
-}
-
-// ---- asynchronous global -> shared staging (LDGSTS) ------------------------
-__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
-{
-    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_one() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
-// the warp copies `ndoubles` (even, both sides 16-byte aligned) doubles
-__device__ __forceinline__ void warp_copy_async(double *dst, const double *src, int ndoubles, int lane)
-{
-    for (int i = lane; i < ndoubles / 2; i += 32) cp_async16(dst + 2 * i, src + 2 * i);
-}
-
-// 1/x to ~1 ulp without the IEEE slow paths of the division operator:
-// MUFU.RCP64H seed + two Newton steps (x must be normal and non-zero).
-__device__ __forceinline__ double fast_rcp(double x)
-{
-    double y;
-    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    y = fma(y, fma(-x, y, 1.0), y);
-    y = fma(y, fma(-x, y, 1.0), y);
-    return y;
-}
-
-// 1/sqrt(x) to ~1 ulp: MUFU.RSQ64H seed (2^-26) + one third-order correction
-// (x must be normal and positive).
-__device__ __forceinline__ double fast_rsqrt(double x)
-{
-    double y;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    const double e = fma(-x, y * y, 1.0);
-    return fma(fma(e, 0.375, 0.5), y * e, y);
-}
-
-// One-sided Jacobi: a sweep in which every pair's squared cosine stayed below this
-// is the last one (tools/accuracy_probe.py: tightening it does not change the result).
-#ifdef SBD_JACOBI_BIG
-constexpr double kJacobiBig = SBD_JACOBI_BIG;
-#else
-constexpr double kJacobiBig = 1.0e-10;
-#endif
 
 // sum over the n lanes of a layer group
 template <int n>
