@@ -14,7 +14,8 @@ import os
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libsbdart_b200.so")
+# SBD_LIB_PATH: an alternative build of the same sources (tuning experiments)
+LIB_PATH = os.environ.get("SBD_LIB_PATH") or os.path.join(_PKG, "libsbdart_b200.so")
 
 SBD_SUCCESS = 0
 SBD_ERR_CUDA = -100

@@ -282,7 +282,7 @@ extern "C" int sbd_disort_batch_device(sbd_handle *h, const sbd_dims *dims, cons
     if (wide) {
         const size_t smem = wide_smem_bytes(N, L, NT);
         int cta_per_sm = (int)((smem_limit + 1024) / (smem + 1024));
-        if (cta_per_sm > 2) cta_per_sm = 2;          // register budget (launch bounds)
+        if (cta_per_sm > wide_ctas_per_sm()) cta_per_sm = wide_ctas_per_sm();     // register budget (launch bounds)
         if (cta_per_sm < 1) cta_per_sm = 1;
         grid = h->sm_count * cta_per_sm;
         warps = 1;                                   // scratch slots and work items per CTA

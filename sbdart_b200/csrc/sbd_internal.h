@@ -82,6 +82,7 @@ cudaError_t launch_fast(const LaunchArgs &a, int warps, int grid, cudaStream_t s
 
 // one-CTA-per-bin register kernel for NSTR in {20, 24, 32}, fluxes (sbd_wide.cu)
 bool wide_supported(int N);
+int wide_ctas_per_sm();
 size_t wide_smem_bytes(int N, int L, int NT);
 size_t wide_slot_doubles(int N, int L);
 cudaError_t launch_wide(const LaunchArgs &a, int grid, cudaStream_t st);

@@ -55,7 +55,7 @@ struct WideLayout {
     // shared memory (doubles)
     static constexpr int cta = 4 * n + N * n + 2;             // cmu cwt csq cdinv, sum(w mu), sum(w), ylm
     static constexpr int tasks = 2 * WARPS;
-    static constexpr int task = N + 4 * n * n + 6 * n;        // gl, K, L, G1, G2, vectors, 1/diagonals
+    static constexpr int task = N + 2 * n * n + 6 * n;        // gl, K, L, vectors, 1/diagonals
     static constexpr int xch = 2 * (KS * G + 4);              // double-buffered pivot exchange
     static constexpr int cmax(int a, int b) { return a > b ? a : b; }
     static constexpr int work = cmax(cmax(tasks * task, 3 * rec + ublk + xch), 2 * (ublk + frec));
@@ -112,8 +112,8 @@ __device__ __forceinline__ int wide_phase1(
     constexpr int N = 2 * n;
     const int g = glane < n ? glane : n - 1;
     const bool wr = active && glane < n;          // this lane publishes results
-    double *sgl = tsm, *sK = sgl + N, *sL = sK + n * n, *sG1 = sL + n * n, *sG2 = sG1 + n * n,
-           *sv = sG2 + n * n, *srd = sv + 4 * n;   // sv: 4 vectors of n; srd: 1/diag(K), 1/diag(L)
+    double *sgl = tsm, *sK = sgl + N, *sL = sK + n * n,
+           *sv = sL + n * n, *srd = sv + 4 * n;    // sv: 4 vectors of n; srd: 1/diag(K), 1/diag(L)
 
     double ss = ssalb[lc];
     if (ss == 1.0) ss = 1.0 - kDither;
@@ -274,7 +274,6 @@ __device__ __forceinline__ int wide_phase1(
     for (int i = 0; i < n; i++) {
         const double gd = cdinv[i] * Q[i];
         const double gs = -cdinv[i] * a[i] * rk;
-        if (glane < n) { sG1[g * n + i] = gs; sG2[g * n + i] = gd; }
         const double gpi = 0.5 * (gs + gd), gmi = 0.5 * (gs - gd);
         const double wm = cwt[i] * cmu[i];
         fA = fma(wm, gpi, fA);
@@ -326,11 +325,15 @@ __device__ __forceinline__ int wide_phase1(
         cj = cj * fast_rcp(rmu0 * rmu0 - s2);
         if (glane < n) { sv[3 * n + g] = cj; sv[g] = cj * kk; }
         __syncwarp();
+        // d_i = sum_j Gd(i,j) c_j, s_i = sum_j Gs(i,j) k_j c_j: lane j holds column j of Gd = D^-1 Q and
+        // Gs = -D^-1 P / k in registers; the sums over the lanes go to the lane of direction i
         double dv = 0.0, sv2 = 0.0;
-#pragma unroll 4
-        for (int j = 0; j < n; j++) {
-            dv = fma(sG2[j * n + g], sv[3 * n + j], dv);
-            sv2 = fma(sG1[j * n + g], sv[j], sv2);
+        const double cm = glane < n ? cj : 0.0;
+#pragma unroll
+        for (int i = 0; i < n; i++) {
+            const double td = group16_sum(cdinv[i] * Q[i] * cm);
+            const double ts = group16_sum(-cdinv[i] * a[i] * cm);       // (k_j c_j) Gs(i,j) = -D^-1 P c_j
+            if (i == g) { dv = td; sv2 = ts; }
         }
         sv2 = umu0 * (cdinv[g] * bd + sv2);
         zup = 0.5 * (sv2 + dv);
@@ -424,8 +427,15 @@ __device__ __forceinline__ void wide_stage_rows(double *stg, const double *recA,
     }
 }
 
+// resident CTAs per SM the register budget is sized for (4: 128 registers per thread; measured on the
+// NSTR=32 / 65-layer set: 2 CTAs 162 k, 3 CTAs 215 k, 4 CTAs 239 k bins/s -- occupancy beats the spills)
+#ifndef SBD_WIDE_MINB
+#define SBD_WIDE_MINB 4
+#endif
+int wide_ctas_per_sm() { return SBD_WIDE_MINB; }
+
 template <int n>
-__global__ void __launch_bounds__(WideLayout<n>::NTHR, 2)
+__global__ void __launch_bounds__(WideLayout<n>::NTHR, SBD_WIDE_MINB)
 disort_wide_kernel(const LaunchArgs a)
 {
     using WL = WideLayout<n>;

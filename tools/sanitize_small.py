@@ -15,6 +15,22 @@ tot = w["dtauc"].sum(axis=1)
 utau = np.stack([0 * tot, 0.3 * tot, tot], axis=1)
 o = s.disort_batch(w["dtauc"], w["ssalb"], w["pmom"], w["bins"], nstr=16, temper=w["temper"], utau=utau)
 print("usrtau bad", int((o["status"] != 0).sum()))
+# NSTR 20 / 24 / 32: the CTA-per-bin register kernel (beam, and beam + Planck on a 65-layer grid)
+for nstr in (20, 24, 32):
+    w = workloads.retrieval_batch(12, nstr=nstr, nlyr=33, ncols=3, seed=nstr)
+    o = s.disort_batch(w["dtauc"], w["ssalb"], w["pmom"], w["bins"], nstr=nstr)
+    print(nstr, "wide retrieval bad", int((o["status"] != 0).sum()))
+w = workloads.mls_shortwave(nstr=32, nlyr=65, wlinf=1.8, wlsup=2.2, wlinc=0.1, cloud_tau=10.0)
+o = s.disort_batch(w["dtauc"], w["ssalb"], w["pmom"], w["bins"], nstr=32, temper=w["temper"])
+print("wide thermal bad", int((o["status"] != 0).sum()))
+# radiances: register kernel (NSTR 8, azimuth modes, packed levels) and generic kernel (NSTR 20)
+w = workloads.retrieval_batch(6, nstr=8, nlyr=6, ncols=2, seed=3)
+o = s.disort_batch(w["dtauc"], w["ssalb"], w["pmom"], w["bins"], nstr=8, umu=np.array([-0.5, 0.5]), phi=np.array([0.0, 90.0]),
+                   uu_levels=[0, 6], uu_packed=True)
+print("packed radiance bad", int((o["status"] != 0).sum()))
+w = workloads.retrieval_batch(4, nstr=20, nlyr=6, ncols=2, seed=5)
+o = s.disort_batch(w["dtauc"], w["ssalb"], w["pmom"], w["bins"], nstr=20, umu=np.array([-0.5, 0.5]), phi=np.array([0.0, 90.0]))
+print("generic radiance bad", int((o["status"] != 0).sum()))
 w = workloads.retrieval_batch(6, nstr=8, nlyr=6, ncols=2, seed=3)
 o = s.disort_batch(w["dtauc"], w["ssalb"], w["pmom"], w["bins"], nstr=8, umu=np.array([-0.5, 0.5]), phi=np.array([0.0, 90.0]))
 print("radiance bad", int((o["status"] != 0).sum()))
