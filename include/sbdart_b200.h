@@ -144,6 +144,13 @@ int sbd_set_radiance_levels(sbd_handle *h, const int32_t *levels, int32_t n);
  * levels per bin wants).  Without a selection uu is always the full layout. */
 int sbd_set_radiance_layout(sbd_handle *h, int32_t packed);
 
+/* Output levels of the flux arrays in the following HOST-buffer calls (sbd_disort_batch,
+ * sbd_spectrum_run*): n > 0 strictly ascending indices into the NT output levels -- rfldir,
+ * rfldn, flup, dfdt, uavg are then [B][n] and only those levels cross PCIe (SBDART's records
+ * read ntop and nbot, drt.f:977-982); n = 0 restores the full [B][NT] layout.  Device-pointer
+ * calls are not affected. */
+int sbd_set_flux_levels(sbd_handle *h, const int32_t *levels, int32_t n);
+
 /* CORINT of DISORT (disort.f:112-118, INTCOR disort.f:2044-2297) for the following
  * batched radiance calls on this handle: 0 (default) off, 1 on.  When on, the
  * Nakajima-Tanaka TMS and IMS corrections are added to uu after the solve; pmom
@@ -254,6 +261,25 @@ int sbd_spectrum_run(sbd_handle *h, const sbd_optics_params *p, const double *z,
                      int32_t *nk, double *wl, double *dwl, double *wt, int32_t *nbins,
                      double *rfldir, double *rfldn, double *flup, double *uuout, int32_t *status,
                      const sbd_inputs_out *inputs_out);
+
+/* The same for ncol independent atmospheric columns sharing the spectral grid, clouds,
+ * surface and aerosol settings (retrieval batches): z, pr, t are [ncol][nz], uu
+ * [ncol][64][nz+1]; p->btemp / p->ttemp < 0 take each column's own surface / top temperature
+ * (drt.f:334-335).  One producer launch makes the bins of every (column, wavelength), one
+ * solve launch follows on the same stream; nothing but the setup arrays goes to the device and
+ * nothing but nk [ncol nwl], wt [3 ncol nwl], the fluxes and status come back, with ONE
+ * synchronisation at the end.  Flux-only.  Fluxes and status are in loop order (column, then
+ * wavelength, then k-term), sized for 3 ncol nwl bins; with sbd_set_flux_levels they are
+ * [bin][nsel]. */
+int sbd_spectrum_run_columns(sbd_handle *h, const sbd_optics_params *p, int32_t ncol, const double *z,
+                             const double *pr, const double *t, const double *uu,
+                             const sbd_cloud_entry *clouds, const double *wlalb, const double *alb,
+                             const double *wlsun, const double *sun, int32_t *nk, double *wl, double *dwl,
+                             double *wt, int32_t *nbins, double *rfldir, double *rfldn, double *flup,
+                             int32_t *status);
+
+/* Bytes the last sbd_spectrum_run* call moved over PCIe (setup arrays in, results out). */
+int sbd_last_transfer_bytes(const sbd_handle *h, int64_t *h2d, int64_t *d2h);
 
 /* Diagnostic: sustained FP64 FMA throughput of the device in TFLOP/s (FMA = 2
  * flops), best of `reps` launches of a register-resident DFMA loop.  Used as

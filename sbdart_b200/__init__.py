@@ -32,7 +32,8 @@ EXPORTS = (
     "sbd_synchronize", "sbd_stream", "sbd_kernel_launches", "sbd_quadrature",
     "sbd_status_string", "sbd_abi_version", "disort_", "sbd_disort_last_status",
     "sbd_measure_fp64_peak", "sbd_optics_upload_tables", "sbd_spectrum_run",
-    "sbd_set_radiance_levels", "sbd_spectrum_set_aerosols", "sbd_set_corint", "sbd_build_id", "sbd_set_radiance_layout",
+    "sbd_set_radiance_levels", "sbd_spectrum_set_aerosols", "sbd_set_corint", "sbd_build_id", "sbd_set_radiance_layout", "sbd_set_flux_levels",
+    "sbd_spectrum_run_columns", "sbd_last_transfer_bytes",
 )
 
 
@@ -110,6 +111,10 @@ def lib():
     L.sbd_set_corint.argtypes = [C.c_void_p, C.c_int32]
     L.sbd_set_radiance_levels.restype = C.c_int
     L.sbd_set_radiance_levels.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
+    L.sbd_set_flux_levels.restype = C.c_int
+    L.sbd_set_flux_levels.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
+    L.sbd_last_transfer_bytes.restype = C.c_int
+    L.sbd_last_transfer_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.sbd_set_radiance_layout.restype = C.c_int
     L.sbd_set_radiance_layout.argtypes = [C.c_void_p, C.c_int32]
     L.sbd_measure_fp64_peak.restype = C.c_int

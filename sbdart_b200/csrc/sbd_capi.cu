@@ -162,8 +162,9 @@ extern "C" void sbd_destroy(sbd_handle *h)
     SbdDevBuf *bufs[] = { &h->scratch, &h->counter, &h->scratch2, &h->counter2, &h->ylmu, &h->angles, &h->d_dtauc, &h->d_ssalb,
                        &h->d_pmom, &h->d_bins, &h->d_temper, &h->d_utau, &h->d_out, &h->d_uu,
                        &h->d_status, &h->opt_tables, &h->opt_atm, &h->opt_misc, &h->opt_map, &h->opt_aero,
-                       &h->d_uupack, &h->d_sel };
+                       &h->d_uupack, &h->d_sel, &h->d_fluxpack };
     for (SbdDevBuf *b : bufs) b->release();
+    if (h->host_stage) cudaFreeHost(h->host_stage);
     for (int i = 0; i < sbd_handle::kMaxChunks; i++) { cudaEventDestroy(h->ev_in[i]); cudaEventDestroy(h->ev_k[i]); }
     cudaEventDestroy(h->ev_misc);
     cudaStreamDestroy(h->stream2);
@@ -340,7 +341,9 @@ extern "C" int sbd_disort_batch_device(sbd_handle *h, const sbd_dims *dims, cons
     a.rfldir = rfldir; a.rfldn = rfldn; a.flup = flup; a.dfdt = dfdt; a.uavg = uavg; a.uu = uu;
     a.status = status;
     a.binmap = h->pending_binmap;      // set by the spectrum path for exactly one launch
+    a.nbins_dev = h->pending_nbins_dev;
     h->pending_binmap = nullptr;
+    h->pending_nbins_dev = nullptr;
     a.quad = tb.quad; a.ylmc = tb.ylmc;
     a.nslots = grid * warps;
     a.slot_stride = slot;
@@ -436,6 +439,14 @@ extern "C" int sbd_disort_batch(sbd_handle *h, const sbd_dims *dims, const doubl
     }
     double *o = (double *)h->d_out.p;
     double *dst[5] = { rfldir, rfldn, flup, dfdt, uavg };
+    // flux-level selection (sbd_set_flux_levels): the host arrays are [B][nsel]
+    const int nfsel = (int)h->flux_levels.size();
+    if (nfsel > 0) {
+        for (int i = 0; i < nfsel; i++) if (h->flux_levels[i] >= (int)NT) return SBD_ERR_ARG;
+        CK(h->d_sel.reserve((size_t)nfsel * 4));
+        CK(cudaMemcpyAsync(h->d_sel.p, h->flux_levels.data(), (size_t)nfsel * 4, cudaMemcpyHostToDevice, st));
+        CK(h->d_fluxpack.reserve(5 * B * nfsel * 8));
+    }
     // Pipeline over chunks of bins: H2D of chunk c+1 and D2H of chunk c-1 overlap the
     // kernel of chunk c (copy-in, copy-out and two alternating compute streams, events
     // between them).  Only the first copy in and the last copy out are exposed, so the
@@ -503,8 +514,15 @@ extern "C" int sbd_disort_batch(sbd_handle *h, const sbd_dims *dims, const doubl
             CK(cudaEventRecord(h->ev_k[c], sk));
             CK(cudaStreamWaitEvent(so, h->ev_k[c], 0));
         }
-        for (int k = 0; k < 5; k++)
-            if (dst[k]) CK(cudaMemcpyAsync(dst[k] + b0 * NT, o + k * per + b0 * NT, nb * NT * 8, cudaMemcpyDeviceToHost, so));
+        if (nfsel > 0) {
+            double *pkc = (double *)h->d_fluxpack.p + 5 * b0 * nfsel;       // this chunk: [5][nb][nsel]
+            CK(sbd_launch_pack_flux(o + b0 * NT, pkc, (const int32_t *)h->d_sel.p, nfsel, (int)NT, per, nb, 5, so));
+            for (int k = 0; k < 5; k++)
+                if (dst[k]) CK(cudaMemcpyAsync(dst[k] + b0 * nfsel, pkc + k * nb * nfsel, nb * nfsel * 8, cudaMemcpyDeviceToHost, so));
+        } else {
+            for (int k = 0; k < 5; k++)
+                if (dst[k]) CK(cudaMemcpyAsync(dst[k] + b0 * NT, o + k * per + b0 * NT, nb * NT * 8, cudaMemcpyDeviceToHost, so));
+        }
         if (nuu1 && sel.empty())
             CK(cudaMemcpyAsync(uu + b0 * nuu1, (double *)h->d_uu.p + b0 * nuu1, nb * nuu1 * 8, cudaMemcpyDeviceToHost, so));
         if (nuu1 && !sel.empty())

@@ -801,6 +801,8 @@ disort_fast_kernel(const LaunchArgs a)
     double *ublk = frecs + (size_t)L * FL::frec;          // [L][N][US]
     double *dscr = ublk + (size_t)L * FL::ublk;           // RAD: [L][2][NU] downward source, transmission
     const int g = lane % n, task = lane / n;
+    // the spectrum path keeps the bin count on the device (a.d.nbins is then an upper bound)
+    const int nbins_all = a.nbins_dev ? *a.nbins_dev : a.d.nbins;
     double *tsm = tsm_base + (size_t)task * FL::task;
     const int rg = lane >> 2, cg = lane & 3;              // 2-D tiling of phase 2
     const unsigned jpart = jacobi_partners<n>(g);
@@ -809,7 +811,7 @@ disort_fast_kernel(const LaunchArgs a)
         int bin = 0;
         if (lane == 0) bin = atomicAdd(a.work_counter, 1);
         bin = __shfl_sync(FULLMASK, bin, 0);
-        const bool have = bin < a.d.nbins;
+        const bool have = bin < nbins_all;
         if (SYNC) { if (!__syncthreads_or(have)) break; }
         else if (!have) break;
 #ifdef SBD_PHASE_TIMING

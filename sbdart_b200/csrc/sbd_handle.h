@@ -61,4 +61,10 @@ struct sbd_handle {
     sbd::OpticsTables opt_index = {};
     bool opt_ready = false;
     const int32_t *pending_binmap = nullptr;   // device bin -> slot map for the next solve launch
+    const int32_t *pending_nbins_dev = nullptr; // ... and its bin count, on the device
+    std::vector<int32_t> flux_levels;          // sbd_set_flux_levels: host-side flux outputs are [bin][nsel]
+    SbdDevBuf d_fluxpack;
+    void *host_stage = nullptr;                // pinned staging of the whole-spectrum setup arrays
+    size_t host_stage_cap = 0;
+    size_t last_h2d_bytes = 0, last_d2h_bytes = 0;
 };

@@ -50,6 +50,7 @@ intcor_kernel(const LaunchArgs a)
     const int N = a.d.nstr, L = a.d.nlyr, NT = L + 1, NU = a.d.numu, NP = a.d.nphi;
     const int nmom = a.d.nmom, ldp = nmom + 1;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (bin >= (a.nbins_dev ? *a.nbins_dev : a.d.nbins)) return;
     if (a.status[bin] != 0) return;
     const int src = a.binmap ? a.binmap[bin] : bin;
     const sbd_bin bp = a.bins[src];

@@ -88,3 +88,7 @@ size_t wide_slot_doubles(int N, int L);
 cudaError_t launch_wide(const LaunchArgs &a, int grid, cudaStream_t st);
 
 }  // namespace sbd
+
+// out[k][b][s] = in[k * per_in + b * NT + sel[s]] for narr arrays (sbd_spectrum.cu)
+cudaError_t sbd_launch_pack_flux(const double *in, double *out, const int32_t *sel, int nsel, int NT,
+                                 size_t per_in, size_t nbins, int narr, cudaStream_t st);

@@ -1,4 +1,4 @@
-// K2: optical-property producer.  One thread per wavelength runs what the
+// K2: optical-property producer.  One WARP per (column, wavelength), lanes over the layers, runs what the
 // reference does between `wllimits` and `CALL DISORT` (drt.f:432-533) and
 // writes the DISORT inputs of the wavelength's 1 or 3 k-distribution bins
 // straight into the batch arrays in HBM:
@@ -98,150 +98,6 @@ __device__ void abcdta_dev(const OpticsTables &T, int iv, BandState &s)
 
 __device__ double raysig_dev(double v) { return v * v * v * v / (F32(9.38076e+18) + F32(-1.08426e+09) * v * v); }
 
-// taugas (taugas.f:2236-2534): continuum and band-model depth increments, top-down
-__device__ void taugas_dev(const OpticsArgs &a, double wl, double amu0, double *dtauc, double *dtaul,
-                           BandState &s)
-{
-    const OpticsTables &T = a.tab;
-    const int nz = a.p.nz;
-    const int iv = 5 * ((int)(10000.0 / wl) / 5);
-    const double v = 10000. / wl;
-    double s0 = sint_dev(T, T_SLF296, v), s1 = sint_dev(T, T_SLF260, v);
-    const double fh2o = sint_dev(T, T_FRN296, v);
-    const double t0 = 296., t1 = 260.;
-    if (s0 > 0.) {
-        const double alpha2 = 200. * 200.;
-        const double xh2o = 1. - F32(0.2333) * (alpha2 / ((v - 1050.) * (v - 1050.) + alpha2));
-        s0 *= xh2o; s1 *= xh2o;
-    }
-    double radfn0, radfn1;
-    if ((v / F32(0.6952)) / t1 <= 87.) {
-        double xd = exp(-v / (t0 * F32(0.6952)));
-        radfn0 = v * (1. - xd) / (1. + xd);
-        xd = exp(-v / (t1 * F32(0.6952)));
-        radfn1 = v * (1. - xd) / (1. + xd);
-    } else { radfn0 = v; radfn1 = v; }
-    const double wfac = F32(1.e-20);
-    const double ya = exp(-log(F32(1.025) * F32(3.159e-8)) + F32(2.75e-4) * v);
-    const double yb = exp(-log(F32(8.97e-6)) + F32(1.300e-3) * v);
-    const double fdg = 1. / (ya + yb);
-    // c4dta, hno3, hertda, o2cont, o4cont
-    double abn2 = 0.0;
-    if (v >= 2080. && v <= 2740.) abn2 = tg(T, T_C4, ((int)v - 2080) / 5);
-    double abno3 = 0.0;
-    if (v >= 850. && v <= 920.) abno3 = tg(T, T_H1, (int)((v - 845.) / 5.) - 1);
-    else if (v >= 1275. && v <= 1350.) abno3 = tg(T, T_H2, (int)((v - 1270.) / 5.) - 1);
-    else if (v >= 1675. && v <= 1735.) abno3 = tg(T, T_H3, (int)((v - 1670.) / 5.) - 1);
-    double abo2 = 0.0;
-    if (v > 36000.) {
-        double corr = 0.0;
-        if (v <= 40000.) corr = ((40000. - v) / 4000.) * F32(7.917e-27);
-        const double rlosch = F32(2.6868e24) * F32(1.0e-5), yr = v / 48811.0, ly = log(yr);
-        abo2 = (F32(6.884e-24) * yr * exp(F32(-69.738) * ly * ly) - corr) * rlosch;
-    }
-    double sigo20 = 0.0, sigo2a = 0.0, sigo2b = 0.0;
-    if (v >= 1395 && v <= 1760) {
-        const int i = (int)((v - 1395.0) / 5.0 + F32(1.00001));
-        double c = 0., aa = 0., b = 0.;
-        if (i >= 1 && i <= 74) { c = tg(T, T_O2S0, i - 1); aa = tg(T, T_O2A, i - 1); b = tg(T, T_O2B, i - 1); }
-        sigo20 = c / F32(0.20946); sigo2a = aa; sigo2b = aa * aa / 2. + b;
-    }
-    double sigo4 = 0.0;
-    {
-        const double wnm = 1000. * wl;
-        int inm = (int)wnm;
-        const double f = wnm - inm;
-        inm = inm - 335 + 1;
-        if (inm >= 1 && inm <= 1015) {
-            const double fraco2 = F32(.209), fracn2 = F32(.781), effn2 = F32(.2);
-            double factor = fraco2 * fraco2;
-            if (wl > F32(1.2)) factor = fraco2 * (fraco2 + effn2 * fracn2);
-            sigo4 = a.p.xo4 * factor * (tg(T, T_O4SIG, inm - 1) * (1. - f) + tg(T, T_O4SIG, inm) * f);
-        }
-    }
-    double doz1 = 0., doz2 = 0., doz3 = 0.;
-    if (v > 40800) {            // o3uv
-        const int i0 = (int)((v - 40800.) / 100. + F32(1.00001));
-        double c = 0.0;
-        if (i0 >= 1 && i0 <= 133) {
-            int i = i0;
-            const double vr = i * 100. + 40800.;
-            if (vr <= v + F32(.1) && vr >= v - F32(.1)) c = tg(T, T_O3UV, i - 1);
-            else {
-                if (i == 133) i = 132;
-                const double am = (tg(T, T_O3UV, i) - tg(T, T_O3UV, i - 1)) / 100.;
-                c = am * v + (tg(T, T_O3UV, i - 1) - am * vr);
-            }
-        }
-        doz1 = F32(.269) * c;
-    } else if (v > 24370) {     // o3hht (table starts at 27370: zeros in between, as the reference)
-        const int i = (int)((v - 27370.) / 5. + F32(1.00001));
-        if (i >= 1 && i <= 2687) {
-            const double c0 = tg(T, T_O3S0, i - 1);
-            doz1 = F32(.269) * c0; doz2 = c0 * tg(T, T_O3S1, i - 1); doz3 = c0 * tg(T, T_O3S2, i - 1);
-        }
-    } else if (v >= 13000. && v <= 24200) {   // c8dta
-        const int ivv = (int)v;
-        if (!(ivv > 24200 && ivv < 27500)) {
-            double xi = (v - 13000.0) / 200.0 + 1.;
-            if (ivv >= 27500) xi = (v - 27500.0) / 500. + 57.;
-            const int nn = (int)(xi + F32(1.001));
-            const double xd = xi - (double)nn;
-            doz1 = tg(T, T_C8, nn - 1) + xd * (tg(T, T_C8, nn - 1) - tg(T, T_C8, nn - 2));
-        }
-    }
-    for (int m = 1; m <= 11; m++) s.cps[m] = cxdta_dev(T, m, v);
-    abcdta_dev(T, iv, s);
-    if (v > 49600) {            // schrun
-        const int i = (int)((v - 49600.) / 5. + F32(1.0001));
-        s.cps[7] = (i >= 1 && i <= 423) ? tg(T, T_SHN, i - 1) : -20.;
-    }
-
-    // species whose slant-weighted amounts are needed: continua + active bands
-    const int cont[13] = { 1, 2, 3, 4, 5, 8, 9, 10, 11, 58, 59, 60, 63 };
-    double wc[13], wb[12];
-    for (int q = 0; q < 13; q++) wc[q] = 0.0;
-    for (int m = 1; m <= 11; m++) wb[m] = 0.0;
-    const double re = F32(6371.2);
-    const int ld = nz + 1;
-    double taucp = 0.0, taulp = 0.0;
-    for (int im = 1; im <= nz; im++) {
-        const int i = nz - im;      // 0-based level index, from the top
-        const double zb = (i == nz - 1) ? a.z[i] : 0.5 * (a.z[i] + a.z[i + 1]);
-        const double rr = re / (re + zb);
-        const double ramu = 1.0 / sqrt(1. - (1. - amu0 * amu0) * rr * rr);
-        for (int q = 0; q < 13; q++) {
-            const int k = cont[q];
-            wc[q] += (a.uu[k * ld + i] - a.uu[k * ld + i + 1]) * ramu;
-        }
-        for (int m = 1; m <= 11; m++) {
-            const int ib = s.ibnd[m];
-            if (ib > 0) wb[m] += (a.uu[ib * ld + i] - a.uu[ib * ld + i + 1]) * ramu;
-        }
-        // wc: 0:w1 1:w2 2:w3 3:w4 4:w5 5:w8 6:w9 7:w10 8:w11 9:w58 10:w59 11:w60 12:w63
-        const double tcunif = sigo4 * wc[2] + abn2 * wc[3] +
-                              sigo20 * (wc[12] + sigo2a * (wc[0] - 220 * wc[12]) + sigo2b * wc[1]) +
-                              abo2 * wc[9];
-        const double tch2o = s0 * radfn0 * (wfac * wc[4]) +
-                             ((s1 * radfn1) - (s0 * radfn0)) * (wfac * wc[6]) +
-                             (fh2o + fdg) * radfn0 * (wfac * wc[7]);
-        const double tco3 = doz1 * wc[5] + doz2 * wc[10] + doz3 * wc[11];
-        const double tctrc = abno3 * wc[8];
-        const double tauc = tcunif + tch2o + tco3 + tctrc;
-        double taul = 0.0;
-        for (int m = 1; m <= 11; m++) {
-            if (s.ibnd[m] > 0 && s.cps[m] > -20. && wb[m] > 1.e-20) {
-                double awl = s.bms[m] * (s.cps[m] + log10(wb[m]));
-                awl = fmin(awl, 20.);
-                taul += exp10(awl);
-            }
-        }
-        dtauc[im - 1] = tauc - taucp;
-        dtaul[im - 1] = taul - taulp;
-        taucp = tauc; taulp = taul;
-    }
-}
-
 // taucor (taugas.f:7650-7692); returns false when the Newton iteration fails
 __device__ bool taucor_dev(const double *gwk, const double *tau, double amu, double utau, double &cf)
 {
@@ -322,13 +178,203 @@ __device__ void aer_interp_dev(const double *wlb, const double *ext, const doubl
     }
 }
 
-__global__ void __launch_bounds__(64)
+
+// ---------------------------------------------------------------------------
+// K2: one WARP per (column, wavelength); lanes over the layers.
+// ---------------------------------------------------------------------------
+constexpr int kOptWarps = 4;                 // warps per CTA
+constexpr int kLayerArrays = 15;             // per-warp shared arrays of kMaxZ doubles
+
+// Everything of taugas (taugas.f:2236-2534) that depends on the wavelength only: continuum
+// coefficients, band-model parameters of the 11 molecules.
+struct GasCoef {
+    double s0r0, ds1, fh, sigo4, abn2, sigo20, sigo2a, sigo2b, abo2, doz1, doz2, doz3, abno3;
+    BandState b;
+};
+
+__device__ void gas_coefficients(const OpticsArgs &a, double wl, GasCoef &c)
+{
+    const OpticsTables &T = a.tab;
+    const int iv = 5 * ((int)(10000.0 / wl) / 5);
+    const double v = 10000. / wl;
+    double s0 = sint_dev(T, T_SLF296, v), s1 = sint_dev(T, T_SLF260, v);
+    const double fh2o = sint_dev(T, T_FRN296, v);
+    const double t0 = 296., t1 = 260.;
+    if (s0 > 0.) {
+        const double alpha2 = 200. * 200.;
+        const double xh2o = 1. - F32(0.2333) * (alpha2 / ((v - 1050.) * (v - 1050.) + alpha2));
+        s0 *= xh2o; s1 *= xh2o;
+    }
+    double radfn0, radfn1;
+    if ((v / F32(0.6952)) / t1 <= 87.) {
+        double xd = exp(-v / (t0 * F32(0.6952)));
+        radfn0 = v * (1. - xd) / (1. + xd);
+        xd = exp(-v / (t1 * F32(0.6952)));
+        radfn1 = v * (1. - xd) / (1. + xd);
+    } else { radfn0 = v; radfn1 = v; }
+    const double wfac = F32(1.e-20);
+    const double ya = exp(-log(F32(1.025) * F32(3.159e-8)) + F32(2.75e-4) * v);
+    const double yb = exp(-log(F32(8.97e-6)) + F32(1.300e-3) * v);
+    const double fdg = 1. / (ya + yb);
+    c.s0r0 = s0 * radfn0 * wfac;
+    c.ds1 = ((s1 * radfn1) - (s0 * radfn0)) * wfac;
+    c.fh = (fh2o + fdg) * radfn0 * wfac;
+    c.abn2 = 0.0;
+    if (v >= 2080. && v <= 2740.) c.abn2 = tg(T, T_C4, ((int)v - 2080) / 5);
+    c.abno3 = 0.0;
+    if (v >= 850. && v <= 920.) c.abno3 = tg(T, T_H1, (int)((v - 845.) / 5.) - 1);
+    else if (v >= 1275. && v <= 1350.) c.abno3 = tg(T, T_H2, (int)((v - 1270.) / 5.) - 1);
+    else if (v >= 1675. && v <= 1735.) c.abno3 = tg(T, T_H3, (int)((v - 1670.) / 5.) - 1);
+    c.abo2 = 0.0;
+    if (v > 36000.) {
+        double corr = 0.0;
+        if (v <= 40000.) corr = ((40000. - v) / 4000.) * F32(7.917e-27);
+        const double rlosch = F32(2.6868e24) * F32(1.0e-5), yr = v / 48811.0, ly = log(yr);
+        c.abo2 = (F32(6.884e-24) * yr * exp(F32(-69.738) * ly * ly) - corr) * rlosch;
+    }
+    c.sigo20 = 0.0; c.sigo2a = 0.0; c.sigo2b = 0.0;
+    if (v >= 1395 && v <= 1760) {
+        const int i = (int)((v - 1395.0) / 5.0 + F32(1.00001));
+        double cc = 0., aa = 0., b = 0.;
+        if (i >= 1 && i <= 74) { cc = tg(T, T_O2S0, i - 1); aa = tg(T, T_O2A, i - 1); b = tg(T, T_O2B, i - 1); }
+        c.sigo20 = cc / F32(0.20946); c.sigo2a = aa; c.sigo2b = aa * aa / 2. + b;
+    }
+    c.sigo4 = 0.0;
+    {
+        const double wnm = 1000. * wl;
+        int inm = (int)wnm;
+        const double f = wnm - inm;
+        inm = inm - 335 + 1;
+        if (inm >= 1 && inm <= 1015) {
+            const double fraco2 = F32(.209), fracn2 = F32(.781), effn2 = F32(.2);
+            double factor = fraco2 * fraco2;
+            if (wl > F32(1.2)) factor = fraco2 * (fraco2 + effn2 * fracn2);
+            c.sigo4 = a.p.xo4 * factor * (tg(T, T_O4SIG, inm - 1) * (1. - f) + tg(T, T_O4SIG, inm) * f);
+        }
+    }
+    c.doz1 = 0.; c.doz2 = 0.; c.doz3 = 0.;
+    if (v > 40800) {            // o3uv
+        const int i0 = (int)((v - 40800.) / 100. + F32(1.00001));
+        double cc = 0.0;
+        if (i0 >= 1 && i0 <= 133) {
+            int i = i0;
+            const double vr = i * 100. + 40800.;
+            if (vr <= v + F32(.1) && vr >= v - F32(.1)) cc = tg(T, T_O3UV, i - 1);
+            else {
+                if (i == 133) i = 132;
+                const double am = (tg(T, T_O3UV, i) - tg(T, T_O3UV, i - 1)) / 100.;
+                cc = am * v + (tg(T, T_O3UV, i - 1) - am * vr);
+            }
+        }
+        c.doz1 = F32(.269) * cc;
+    } else if (v > 24370) {     // o3hht (table starts at 27370: zeros in between, as the reference)
+        const int i = (int)((v - 27370.) / 5. + F32(1.00001));
+        if (i >= 1 && i <= 2687) {
+            const double c0 = tg(T, T_O3S0, i - 1);
+            c.doz1 = F32(.269) * c0; c.doz2 = c0 * tg(T, T_O3S1, i - 1); c.doz3 = c0 * tg(T, T_O3S2, i - 1);
+        }
+    } else if (v >= 13000. && v <= 24200) {   // c8dta
+        const int ivv = (int)v;
+        if (!(ivv > 24200 && ivv < 27500)) {
+            double xi = (v - 13000.0) / 200.0 + 1.;
+            if (ivv >= 27500) xi = (v - 27500.0) / 500. + 57.;
+            const int nn = (int)(xi + F32(1.001));
+            const double xd = xi - (double)nn;
+            c.doz1 = tg(T, T_C8, nn - 1) + xd * (tg(T, T_C8, nn - 1) - tg(T, T_C8, nn - 2));
+        }
+    }
+    for (int m = 1; m <= 11; m++) c.b.cps[m] = cxdta_dev(T, m, v);
+    abcdta_dev(T, iv, c.b);
+    if (v > 49600) {            // schrun
+        const int i = (int)((v - 49600.) / 5. + F32(1.0001));
+        c.b.cps[7] = (i >= 1 && i <= 423) ? tg(T, T_SHN, i - 1) : -20.;
+    }
+}
+
+__device__ __forceinline__ double warp_incl_scan(double v, int lane)
+{
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
+
+__device__ __forceinline__ double warp_sum_d(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Depth increments of the layers (top-down, one layer per lane and pass) for a path of
+// cosine amu0: continuum dtc[] (linear in the absorber amounts of the layer) and band-model
+// dtl[] (difference of the cumulative band transmission functions, taugas.f:2463-2476).
+__device__ void taugas_warp(const OpticsArgs &a, const GasCoef &c, const double *z, const double *uu,
+                            double amu0, double *dtc, double *dtl, int lane)
+{
+    const int nz = a.p.nz, ld = nz + 1;
+    const double re = F32(6371.2);
+    double carry[12], taulp = 0.0;
+    for (int m = 1; m <= 11; m++) carry[m] = 0.0;
+    for (int im0 = 0; im0 < nz; im0 += 32) {
+        const int im = im0 + lane;
+        const bool ok = im < nz;
+        const int i = ok ? nz - 1 - im : 0;           // 0-based level index, from the top
+        const double zb = (i == nz - 1) ? z[i] : 0.5 * (z[i] + z[i + 1]);
+        const double rr = re / (re + zb);
+        const double ramu = 1.0 / sqrt(1. - (1. - amu0 * amu0) * rr * rr);
+        auto d = [&](int k) { return ok ? (uu[k * ld + i] - uu[k * ld + i + 1]) * ramu : 0.0; };
+        if (ok) {
+            const double w1 = d(1), w2 = d(2), w3 = d(3), w4 = d(4), w5 = d(5), w8 = d(8), w9 = d(9),
+                         w10 = d(10), w11 = d(11), w58 = d(58), w59 = d(59), w60 = d(60), w63 = d(63);
+            const double tcunif = c.sigo4 * w3 + c.abn2 * w4 +
+                                  c.sigo20 * (w63 + c.sigo2a * (w1 - 220 * w63) + c.sigo2b * w2) + c.abo2 * w58;
+            const double tch2o = c.s0r0 * w5 + c.ds1 * w9 + c.fh * w10;
+            const double tco3 = c.doz1 * w8 + c.doz2 * w59 + c.doz3 * w60;
+            dtc[im] = tcunif + tch2o + tco3 + c.abno3 * w11;
+        }
+        // band model: cumulative amounts of the active species
+        double taul = 0.0;
+        for (int m = 1; m <= 11; m++) {
+            const int ib = c.b.ibnd[m];
+            if (!(ib > 0 && c.b.cps[m] > -20.)) continue;        // uniform over the warp
+            const double wb = warp_incl_scan(d(ib), lane) + carry[m];
+            carry[m] = __shfl_sync(0xffffffffu, wb, 31);
+            if (wb > 1.e-20) {
+                double awl = c.b.bms[m] * (c.b.cps[m] + log10(wb));
+                awl = fmin(awl, 20.);
+                taul += exp10(awl);
+            }
+        }
+        double prev = __shfl_up_sync(0xffffffffu, taul, 1);
+        if (lane == 0) prev = taulp;
+        if (ok) dtl[im] = taul - prev;
+        // cumulative value of the last valid layer of this pass
+        const int lastl = (nz - im0 < 32) ? nz - im0 - 1 : 31;
+        taulp = __shfl_sync(0xffffffffu, taul, lastl);
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(kOptWarps * 32)
 optics_kernel(const OpticsArgs a)
 {
-    const int il = blockIdx.x * blockDim.x + threadIdx.x;
+    extern __shared__ double sm_opt[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const sbd_optics_params &P = a.p;
-    if (il >= P.nwl) return;
+    const int ncol = a.ncol > 0 ? a.ncol : 1;
+    const int item = blockIdx.x * kOptWarps + warp;          // (column, wavelength)
+    if (item >= ncol * P.nwl) return;
+    const int col = item / P.nwl, il = item - col * P.nwl;
     const int nz = P.nz, nmom = (P.nstr + 2 < 40) ? P.nstr + 2 : 40, ldp = nmom + 1;
+    const double *z = a.z + (size_t)col * nz, *pr = a.p_ + (size_t)col * nz, *tt = a.t + (size_t)col * nz;
+    const double *uu = a.uu + (size_t)col * 64 * (nz + 1);
+    double *ws = sm_opt + (size_t)warp * kLayerArrays * kMaxZ;
+    double *dtcv = ws, *dtlv = dtcv + kMaxZ, *dtls = dtlv + kMaxZ, *dtk = dtls + kMaxZ /* [3][kMaxZ] */,
+           *dk2 = dtk + 3 * kMaxZ /* [3][kMaxZ] */, *taucld = dk2 + 3 * kMaxZ, *wcld = taucld + kMaxZ,
+           *dtaua = wcld + kMaxZ, *waer = dtaua + kMaxZ, *dtaur = waer + kMaxZ;      // 14 arrays
 
     // ---- wllimits (drt.f:1657-1740)
     double wl, ww1, ww2;
@@ -358,31 +404,33 @@ optics_kernel(const OpticsArgs a)
     double amu0 = (P.night && il > 0) ? 1.0 : P.amu0;
 
     // ---- gasset (taugas.f:7392-7510)
-    double dtcv[kMaxZ], dtlv[kMaxZ], dtls[kMaxZ], dtk[kMaxZ][3], dk2[kMaxZ][3];
-    BandState st, st2;
-    taugas_dev(a, wl, 1.0, dtcv, dtlv, st);
+    GasCoef gc;
+    gas_coefficients(a, wl, gc);
+    const BandState &st = gc.b;
+    taugas_warp(a, gc, z, uu, 1.0, dtcv, dtlv, lane);
     if (amu0 > 0.) {
-        double dtcs[kMaxZ];
-        taugas_dev(a, wl, amu0, dtcs, dtls, st2);
+        taugas_warp(a, gc, z, uu, amu0, dk2 /* continuum of the slant path: unused */, dtls, lane);
     } else {
-        for (int j = 0; j < nz; j++) dtls[j] = dtlv[j];
+        for (int j = lane; j < nz; j += 32) dtls[j] = dtlv[j];
     }
+    __syncwarp();
     int nk = 1;
     double gwk[3] = { 1., 0., 0. };
     double sumlv = 0.0;
-    for (int j = 0; j < nz; j++) sumlv += dtlv[j];
+    for (int j = lane; j < nz; j += 32) sumlv += dtlv[j];
+    sumlv = warp_sum_d(sumlv);
     bool usek = false;
     if (!(P.kdist == 0 || sumlv < F32(.01))) {
-        // kdistr (taugas.f:1802-1920)
+        // kdistr (taugas.f:1802-1920): one layer per lane
         const int ld = nz + 1;
         double tk[3] = { 0, 0, 0 }, gw[3] = { 0, 0, 0 };
-        for (int nn = 0; nn < nz; nn++) {
+        for (int nn = lane; nn < nz; nn += 32) {
             const int i = nz - 1 - nn;
             double dt3[3] = { 0, 0, 0 }, tw3[3] = { 0, 0, 0 };
             for (int m = 1; m <= 11; m++) {
                 const int ib = st.ibnd[m];
                 if (ib < 0) continue;
-                const double duu = a.uu[ib * ld + i] - a.uu[ib * ld + i + 1];
+                const double duu = uu[ib * ld + i] - uu[ib * ld + i + 1];
                 const double cp1 = exp10(st.cps[m]);
                 for (int k = 0; k < 3; k++) {
                     const double gk = tg(a.tab, T_KFAC, k) * st.bmc[m];
@@ -392,15 +440,16 @@ optics_kernel(const OpticsArgs a)
                     tw3[k] += wpth * cp1 * dp;
                 }
             }
-            double wk3[3], sm = 0.0;
-            for (int k = 0; k < 3; k++) { wk3[k] = dt3[k] != 0 ? tw3[k] / dt3[k] : 1. / 3.; sm += wk3[k]; }
+            double wk3[3], smm = 0.0;
+            for (int k = 0; k < 3; k++) { wk3[k] = dt3[k] != 0 ? tw3[k] / dt3[k] : 1. / 3.; smm += wk3[k]; }
             for (int k = 0; k < 3; k++) {
-                wk3[k] /= sm;
-                dtk[nn][k] = dt3[k];
+                wk3[k] /= smm;
+                dtk[k * kMaxZ + nn] = dt3[k];
                 tk[k] += dt3[k];
                 gw[k] += dtlv[nn] * wk3[k];
             }
         }
+        for (int k = 0; k < 3; k++) { tk[k] = warp_sum_d(tk[k]); gw[k] = warp_sum_d(gw[k]); }
         if (fmax(tk[0], fmax(tk[1], tk[2])) >= F32(0.01)) {
             nk = 3; usek = true;
             const double wn = gw[0] + gw[1] + gw[2];
@@ -408,26 +457,29 @@ optics_kernel(const OpticsArgs a)
             else for (int k = 0; k < 3; k++) gwk[k] = gw[k] / wn;
         }
     }
+    __syncwarp();
     // dtauk(:,1:3) -> dtk, dtauk(:,4:6) -> dk2
     if (!usek) {
-        for (int j = 0; j < nz; j++) { dtk[j][0] = dtlv[j]; dk2[j][0] = amu0 * dtls[j]; }
+        for (int j = lane; j < nz; j += 32) { dtk[j] = dtlv[j]; dk2[j] = amu0 * dtls[j]; }
     } else {
-        for (int j = 0; j < nz; j++)
-            for (int k = 0; k < 3; k++) dk2[j][k] = dtk[j][k];
-        if (P.kdist >= 2 && amu0 > 0.) {
+        for (int j = lane; j < nz; j += 32)
+            for (int k = 0; k < 3; k++) dk2[k * kMaxZ + j] = dtk[k * kMaxZ + j];
+        __syncwarp();
+        if (P.kdist >= 2 && amu0 > 0. && lane == 0) {
+            // slant-path correction: a Newton solve per layer on running sums (sequential)
             double tauls = 0., tglc[3] = { 0, 0, 0 };
             for (int j = 0; j < nz; j++) {
                 tauls += dtls[j];
-                for (int k = 0; k < 3; k++) tglc[k] += dtk[j][k];
+                for (int k = 0; k < 3; k++) tglc[k] += dtk[k * kMaxZ + j];
                 double cf;
                 taucor_dev(gwk, tglc, amu0, tauls, cf);
-                for (int k = 0; k < 3; k++) { dk2[j][k] = tglc[k] * (cf - 1.0) + dtk[j][k]; tglc[k] *= cf; }
+                for (int k = 0; k < 3; k++) { dk2[k * kMaxZ + j] = tglc[k] * (cf - 1.0) + dtk[k * kMaxZ + j]; tglc[k] *= cf; }
             }
         }
     }
-
+    __syncwarp();
     if (amu0 <= 0.)      // taugas.f:7491 -- applies to the first slant column whatever nk is
-        for (int j = 0; j < nz; j++) dk2[j][0] = dtlv[j];
+        for (int j = lane; j < nz; j += 32) dk2[j] = dtlv[j];
 
     // ---- solar flux, surface albedo, Planck switch (drt.f:448-486)
     double flxin = (P.nf == 0) ? dwl : interp_dev(a.wlsun, a.sun, P.nsun, wl) * dwl * P.solfac;
@@ -437,36 +489,33 @@ optics_kernel(const OpticsArgs a)
     rsfc = fmax(0.0, fmin(rsfc, 1.0));
 
     // ---- clouds (taucloud.f:10-140); slot 0 of pmom is the accumulation buffer
-    const size_t s0i = (size_t)3 * il;
+    const size_t s0i = (size_t)3 * item;
     double *pm0 = a.pmom + s0i * nz * ldp;
-    double taucld[kMaxZ], wcld[kMaxZ];
-    int icnt[kMaxZ];
-    for (int j = 0; j < nz; j++) {
-        taucld[j] = 0.; wcld[j] = 0.; icnt[j] = 0;
-        for (int k = 0; k <= nmom; k++) pm0[(size_t)j * ldp + k] = 0.0;
-    }
+    int *icnt = (int *)(dtaur + kMaxZ);            // 15th array
+    for (int j = lane; j < nz; j += 32) { taucld[j] = 0.; wcld[j] = 0.; icnt[j] = 0; dtaua[j] = 0.; waer[j] = 0.; }
+    for (int e = lane; e < nz * ldp; e += 32) pm0[e] = 0.0;
+    __syncwarp();
     for (int c = 0; c < P.ncloud; c++) {
         const sbd_cloud_entry ce = a.clouds[c];
         const int j = ce.layer - 1;
-        double qc, wc, gc;
-        cloudpar_dev(a.tab, wl, ce.reff, qc, wc, gc);
-        double gp = 1.0;
-        for (int k = 1; k <= nmom; k++) {          // getmom, HG (iphas = 3) or Rayleigh (2)
-            gp *= gc;
-            const double pmk = (P.imomc == 2) ? (k == 2 ? F32(0.1) : 0.0) : gp;
+        double qc, wc, gcl;
+        cloudpar_dev(a.tab, wl, ce.reff, qc, wc, gcl);
+        for (int k = 1 + lane; k <= nmom; k += 32) {     // getmom, HG (iphas = 3) or Rayleigh (2)
+            const double pmk = (P.imomc == 2) ? (k == 2 ? F32(0.1) : 0.0) : pow(gcl, (double)k);
             pm0[(size_t)j * ldp + k] += pmk;
         }
-        wcld[j] += wc;
-        icnt[j] += 1;
-        if (ce.use_tau) taucld[j] += ce.tcld * qc / ce.q550;
-        else if (ce.lwpth != 0.) {
-            if (ce.reff < 0.) taucld[j] += F32(-.75) * qc * ce.lwpth / ce.reff / F32(.917);
-            else taucld[j] += F32(.75) * qc * ce.lwpth / ce.reff;
+        if (lane == 0) {
+            wcld[j] += wc;
+            icnt[j] += 1;
+            if (ce.use_tau) taucld[j] += ce.tcld * qc / ce.q550;
+            else if (ce.lwpth != 0.) {
+                if (ce.reff < 0.) taucld[j] += F32(-.75) * qc * ce.lwpth / ce.reff / F32(.917);
+                else taucld[j] += F32(.75) * qc * ce.lwpth / ce.reff;
+            }
         }
+        __syncwarp();
     }
     // ---- aerosols (tauaero, tauaero.f:1223-1331): per-wavelength scattering parameters
-    double dtaua[kMaxZ], waer[kMaxZ];
-    for (int j = 0; j < nz; j++) { dtaua[j] = 0.; waer[j] = 0.; }
     double bl_ext = 0., bl_wa = 0., bl_ga = 0.;
     const double *dtsv = nullptr, *awl = nullptr, *strat = nullptr;
     double st_dt[SBD_NAERZ], st_wa[SBD_NAERZ], st_ga[SBD_NAERZ];
@@ -480,7 +529,6 @@ optics_kernel(const OpticsArgs a)
             if (a.aer.nosct == 1) bl_ext *= 1. - bl_wa;
             if (a.aer.nosct == 3) bl_ext *= 1. - bl_wa * bl_ga;
             if (a.aer.nosct != 0) { bl_wa = 0.; bl_ga = 0.; }
-            for (int j = 0; j < nz; j++) { dtaua[j] = bl_ext * dtsv[j]; waer[j] = bl_wa; }
         }
         const int per = (int)(sizeof(sbd_strat_entry) / 8);
         for (int e = 0; e < nst; e++) {
@@ -492,114 +540,160 @@ optics_kernel(const OpticsArgs a)
             st_dt[e] = se[1] * qa;
         }
     }
-    // ---- rayleigh (spectra.f:206-247), normom (drt.f:1366-1397)
-    double dtaur[kMaxZ];
-    {
-        const double sig = raysig_dev(10000. / wl);
+    // ---- per-layer scalars: rayleigh (spectra.f:206-247), cloud averages, aerosol layers
+    const double sig = raysig_dev(10000. / wl);
+    for (int j = lane; j < nz; j += 32) {
         const double pz = F32(1013.25), tz = F32(273.15);
-        dtaur[0] = sig * (a.p_[nz - 1] / pz) / (a.t[nz - 1] / tz) * 5.;
-        for (int i = 2; i <= nz; i++) {
-            const int im = nz - i + 1;
-            const double rhom = (a.p_[im - 1] / pz) / (a.t[im - 1] / tz);
-            const double rhop = (a.p_[im] / pz) / (a.t[im] / tz);
-            const double dz = a.z[im] - a.z[im - 1];
-            dtaur[i - 1] = (rhom == rhop) ? .5 * sig * dz * (rhom + rhop)
-                                          : sig * dz * (rhop - rhom) / log(rhop / rhom);
+        double dr;
+        if (j == 0) dr = sig * (pr[nz - 1] / pz) / (tt[nz - 1] / tz) * 5.;
+        else {
+            const int im = nz - j;                  // i = j + 1 of the reference loop: im = nz - i + 1
+            const double rhom = (pr[im - 1] / pz) / (tt[im - 1] / tz);
+            const double rhop = (pr[im] / pz) / (tt[im] / tz);
+            const double dz = z[im] - z[im - 1];
+            dr = (rhom == rhop) ? .5 * sig * dz * (rhom + rhop) : sig * dz * (rhop - rhom) / log(rhop / rhom);
         }
-        if (P.xrsc != 1.0) for (int j = 0; j < nz; j++) dtaur[j] *= P.xrsc;
-    }
-    for (int j = 0; j < nz; j++) {
-        if (icnt[j]) {
-            wcld[j] /= icnt[j];
-            for (int k = 1; k <= nmom; k++)
-                pm0[(size_t)j * ldp + k] = taucld[j] * wcld[j] * pm0[(size_t)j * ldp + k] / icnt[j];
-        }
-        if (nbl > 0) {                               // boundary-layer aerosol, getmom(imoma)
-            const double dab = dtaua[j];
-            double gp = 1.0;
-            for (int k = 1; k <= nmom; k++) {
-                gp *= bl_ga;
-                const double pmk = (a.aer.imoma == 2) ? (k == 2 ? F32(0.1) : 0.0) : gp;
-                pm0[(size_t)j * ldp + k] += pmk * dab * bl_wa;
-            }
-        }
-        for (int e = 0; e < nst; e++) {              // stratospheric layers, Henyey-Greenstein
+        if (P.xrsc != 1.0) dr *= P.xrsc;
+        dtaur[j] = dr;
+        if (icnt[j]) wcld[j] /= icnt[j];
+        double da = 0., wa = 0.;
+        if (nbl > 0) { da = bl_ext * dtsv[j]; wa = bl_wa; }
+        // dtk[2*kMaxZ + ...] is free when nk == 1; the boundary-layer depth is kept in registers instead
+        for (int e = 0; e < nst; e++) {
             if (st_layer[e] != j) continue;
-            double gp = 1.0;
-            for (int k = 1; k <= nmom; k++) { gp *= st_ga[e]; pm0[(size_t)j * ldp + k] += gp * st_dt[e] * st_wa[e]; }
-            waer[j] = (waer[j] * dtaua[j] + st_wa[e] * st_dt[e]) / (dtaua[j] + st_dt[e]);
-            dtaua[j] += st_dt[e];
+            wa = (wa * da + st_wa[e] * st_dt[e]) / (da + st_dt[e]);
+            da += st_dt[e];
         }
-        pm0[(size_t)j * ldp + 2] += F32(.1) * dtaur[j];
-        const double dtsct = taucld[j] * wcld[j] + dtaua[j] * waer[j] + dtaur[j];
-        if (dtsct != 0.)
-            for (int k = 0; k <= nmom; k++) pm0[(size_t)j * ldp + k] /= dtsct;
-        pm0[(size_t)j * ldp] = 1.;
+        dtaua[j] = da; waer[j] = wa;
     }
+    __syncwarp();
+    // ---- normom (drt.f:1366-1397) and the moment mixing: lanes over (layer, moment)
+    for (int e = lane; e < nz * ldp; e += 32) {
+        const int j = e / ldp, k = e - j * ldp;
+        double v = 1.0;
+        if (k > 0) {
+            v = pm0[e];
+            if (icnt[j]) v = taucld[j] * wcld[j] * v / icnt[j];
+            if (nbl > 0) {                             // boundary-layer aerosol, getmom(imoma)
+                const double pmk = (a.aer.imoma == 2) ? (k == 2 ? F32(0.1) : 0.0) : pow(bl_ga, (double)k);
+                v += pmk * (bl_ext * dtsv[j]) * bl_wa;
+            }
+            for (int s2 = 0; s2 < nst; s2++)           // stratospheric layers, Henyey-Greenstein
+                if (st_layer[s2] == j) v += pow(st_ga[s2], (double)k) * st_dt[s2] * st_wa[s2];
+            if (k == 2) v += F32(.1) * dtaur[j];
+            const double dtsct = taucld[j] * wcld[j] + dtaua[j] * waer[j] + dtaur[j];
+            if (dtsct != 0.) v /= dtsct;
+        }
+        pm0[e] = v;
+    }
+    __syncwarp();
 
     // ---- depthscl per k term (taugas.f:7512-7621) and the per-bin scalars
     for (int kd = 0; kd < nk; kd++) {
         const size_t slot = s0i + kd;
         double *od = a.dtauc + slot * nz, *os = a.ssalb + slot * nz;
         double wt = gwk[kd];
-        double tsc = 0., tglv = 0., tgls = 0.;
         if (P.kdist == 0 || nk == 1) wt = 1.;
-        for (int i = 0; i < nz; i++) {
-            double dtaug;
-            tsc += dtaur[i] + taucld[i] + dtaua[i];
+        double c_tsc = 0., c_glv = 0., c_gls = 0.;
+        for (int i0 = 0; i0 < nz; i0 += 32) {
+            const int i = i0 + lane;
+            const bool ok = i < nz;
+            const double sct = ok ? dtaur[i] + taucld[i] + dtaua[i] : 0.0;
+            const double tsc = warp_incl_scan(sct, lane) + c_tsc;
+            c_tsc = __shfl_sync(0xffffffffu, tsc, 31);
+            double dtaug = 0.0;
             if (P.kdist == 0 || nk == 1) {
-                tglv += dtk[i][0]; tgls += dk2[i][0];
-                double afac = 1.;
-                if (tglv > F32(.001)) afac = tgls / tglv;
-                const double ramp = rolloff_dev(wl, tsc);
-                afac = afac * ramp + 1. - ramp;
-                dtaug = dtcv[i] + dtk[i][0] * afac;
-            } else if (P.kdist == 1) dtaug = dtcv[i] + dtk[i][kd];
-            else if (P.kdist == 2) dtaug = dtcv[i] + dk2[i][kd];
-            else {
-                const double ramp = rolloff_dev(wl, tsc);
-                dtaug = dtcv[i] + dtk[i][kd] * (1. - ramp) + dk2[i][kd] * ramp;
+                const double tglv = warp_incl_scan(ok ? dtk[i] : 0.0, lane) + c_glv;
+                const double tgls = warp_incl_scan(ok ? dk2[i] : 0.0, lane) + c_gls;
+                c_glv = __shfl_sync(0xffffffffu, tglv, 31);
+                c_gls = __shfl_sync(0xffffffffu, tgls, 31);
+                if (ok) {
+                    double afac = 1.;
+                    if (tglv > F32(.001)) afac = tgls / tglv;
+                    const double ramp = rolloff_dev(wl, tsc);
+                    afac = afac * ramp + 1. - ramp;
+                    dtaug = dtcv[i] + dtk[i] * afac;
+                }
+            } else if (ok) {
+                if (P.kdist == 1) dtaug = dtcv[i] + dtk[kd * kMaxZ + i];
+                else if (P.kdist == 2) dtaug = dtcv[i] + dk2[kd * kMaxZ + i];
+                else {
+                    const double ramp = rolloff_dev(wl, tsc);
+                    dtaug = dtcv[i] + dtk[kd * kMaxZ + i] * (1. - ramp) + dk2[kd * kMaxZ + i] * ramp;
+                }
             }
-            const double dtau = dtaug + taucld[i] + dtaua[i] + dtaur[i];
-            od[i] = dtau;
-            os[i] = (dtau > 2.2250738585072014e-308) ? (taucld[i] * wcld[i] + dtaua[i] * waer[i] + dtaur[i]) / dtau : 0.0;
+            if (ok) {
+                const double dtau = dtaug + taucld[i] + dtaua[i] + dtaur[i];
+                od[i] = dtau;
+                os[i] = (dtau > 2.2250738585072014e-308) ? (taucld[i] * wcld[i] + dtaua[i] * waer[i] + dtaur[i]) / dtau : 0.0;
+            }
         }
         if (kd > 0) {
             double *pk = a.pmom + slot * nz * ldp;
-            for (int e = 0; e < nz * ldp; e++) pk[e] = pm0[e];
+            for (int e = lane; e < nz * ldp; e += 32) pk[e] = pm0[e];
         }
-        sbd_bin b;
-        b.fbeam = flxin; b.umu0 = amu0; b.phi0 = P.phi0; b.fisot = P.fisot; b.albedo = rsfc;
-        b.btemp = P.btemp; b.ttemp = P.ttemp; b.temis = P.temis; b.wvnmlo = wvnmlo; b.wvnmhi = wvnmhi;
-        b.accur = 0.0; b.plank = plank; b.col = 0;
-        a.bins[slot] = b;
-        a.wt[slot] = wt;
+        if (lane == 0) {
+            sbd_bin b;
+            b.fbeam = flxin; b.umu0 = amu0; b.phi0 = P.phi0; b.fisot = P.fisot; b.albedo = rsfc;
+            b.btemp = a.btemp ? a.btemp[col] : P.btemp; b.ttemp = a.ttemp ? a.ttemp[col] : P.ttemp;
+            b.temis = P.temis; b.wvnmlo = wvnmlo; b.wvnmhi = wvnmhi;
+            b.accur = 0.0; b.plank = plank; b.col = col;
+            a.bins[slot] = b;
+            a.wt[slot] = wt;
+        }
     }
-    a.nk[il] = nk;
-    a.wl[il] = wl;
-    a.dwl[il] = dwl;
+    if (lane == 0) {
+        a.nk[item] = nk;
+        if (col == 0) { a.wl[il] = wl; a.dwl[il] = dwl; }
+    }
 }
 
-// bin -> slot map in loop order (wavelength-major, k-terms together)
-__global__ void binmap_kernel(const int32_t *nk, int nwl, int32_t *binmap, int32_t *nbins)
+// bin -> slot map in loop order (column-major, then wavelength, k-terms together): a
+// single-CTA parallel scan over nk[]
+__global__ void __launch_bounds__(1024)
+binmap_kernel(const int32_t *nk, int nitem, int32_t *binmap, int32_t *nbins)
 {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    int b = 0;
-    for (int il = 0; il < nwl; il++)
-        for (int kd = 0; kd < nk[il]; kd++) binmap[b++] = 3 * il + kd;
-    *nbins = b;
+    __shared__ int wsum[32];
+    __shared__ int base;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) base = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < nitem; i0 += 1024) {
+        const int i = i0 + tid;
+        const int v = i < nitem ? nk[i] : 0;
+        int s = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, s, o); if (lane >= o) s += t; }
+        if (lane == 31) wsum[warp] = s;
+        __syncthreads();
+        if (warp == 0) {
+            int w = wsum[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
+            wsum[lane] = w;
+        }
+        __syncthreads();
+        const int off = base + (warp > 0 ? wsum[warp - 1] : 0) + s - v;
+        for (int kd = 0; kd < v; kd++) binmap[off + kd] = 3 * i + kd;
+        __syncthreads();
+        if (tid == 0) base += wsum[31];
+        __syncthreads();
+    }
+    if (tid == 0) *nbins = base;
 }
 
 cudaError_t launch_optics(const OpticsArgs &a, cudaStream_t st)
 {
-    const int threads = 64, blocks = (a.p.nwl + threads - 1) / threads;
-    optics_kernel<<<blocks, threads, 0, st>>>(a);
+    const int ncol = a.ncol > 0 ? a.ncol : 1;
+    const int items = ncol * a.p.nwl, blocks = (items + kOptWarps - 1) / kOptWarps;
+    const size_t smem = (size_t)kOptWarps * kLayerArrays * kMaxZ * 8;
+    optics_kernel<<<blocks, kOptWarps * 32, smem, st>>>(a);
     return cudaGetLastError();
 }
 
-cudaError_t launch_binmap(const int32_t *nk, int nwl, int32_t *binmap, int32_t *nbins, cudaStream_t st)
+cudaError_t launch_binmap(const int32_t *nk, int nitem, int32_t *binmap, int32_t *nbins, cudaStream_t st)
 {
-    binmap_kernel<<<1, 32, 0, st>>>(nk, nwl, binmap, nbins);
+    binmap_kernel<<<1, 1024, 0, st>>>(nk, nitem, binmap, nbins);
     return cudaGetLastError();
 }
 

@@ -39,20 +39,22 @@ struct OpticsTables {
 struct OpticsArgs {
     sbd_optics_params p;
     OpticsTables tab;
-    const double *z, *p_, *t, *uu;               // [nz], [nz], [nz], [64][nz+1]
+    int32_t ncol;                                // atmospheric columns (0 / 1: one)
+    const double *z, *p_, *t, *uu;               // [ncol][nz] x 3, [ncol][64][nz+1]
+    const double *btemp, *ttemp;                 // [ncol] boundary temperatures, or null: p.btemp / p.ttemp
     const sbd_cloud_entry *clouds;               // [p.ncloud]
     const double *wlalb, *alb, *wlsun, *sun;     // surface albedo and solar tables
     // aerosols (sbd_spectrum_set_aerosols): packed [wlb n][ext n][abs n][asm n][dtsv nz][awl 47][strat...]
     sbd_aerosol_params aer;
     const double *aero;                          // nullptr: no aerosols
-    // outputs: slot = 3 * il + kd
+    // outputs: slot = 3 * (col * nwl + il) + kd
     double *dtauc, *ssalb, *pmom;                // [3 nwl][nz], [3 nwl][nz], [3 nwl][nz][nmom+1]
     sbd_bin *bins;                               // [3 nwl]
-    int32_t *nk;                                 // [nwl]
-    double *wl, *dwl, *wt;                       // [nwl], [nwl], [3 nwl]
+    int32_t *nk;                                 // [ncol nwl]
+    double *wl, *dwl, *wt;                       // [nwl], [nwl], [3 ncol nwl]
 };
 
 cudaError_t launch_optics(const OpticsArgs &a, cudaStream_t st);
-cudaError_t launch_binmap(const int32_t *nk, int nwl, int32_t *binmap, int32_t *nbins, cudaStream_t st);
+cudaError_t launch_binmap(const int32_t *nk, int nitem, int32_t *binmap, int32_t *nbins, cudaStream_t st);
 
 }  // namespace sbd

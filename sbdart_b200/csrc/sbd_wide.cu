@@ -484,7 +484,7 @@ disort_wide_kernel(const LaunchArgs a)
         if (tid == 0) misc[0] = atomicAdd(a.work_counter, 1);
         __syncthreads();
         const int bin = misc[0];
-        if (bin >= a.d.nbins) break;
+        if (bin >= (a.nbins_dev ? *a.nbins_dev : a.d.nbins)) break;
         const int src = a.binmap ? a.binmap[bin] : bin;
         const sbd_bin bp = a.bins[src];
         const double *dtauc = a.dtauc + (size_t)src * L;
