@@ -9,8 +9,13 @@ R times so that one step is one batched launch over R complete spectra.
 A step = one pass of the hot path (one batched DISORT solve of every bin).
   value : bins/s with inputs resident in HBM (device pointers, CUDA events
           on the solver's stream), max over ranks.
-  e2e   : the same through the host-buffer C-ABI call sbd_disort_batch
-          (pinned host inputs -> H2D -> kernel -> D2H of all fluxes).
+  e2e   : the same spectra through the whole-spectrum C-ABI call
+          sbd_spectrum_run_columns with HOST buffers: the setup arrays of every column go
+          in, the optical properties are produced on the device (K2), the solve follows, and
+          the top / bottom fluxes the record reads come back (copies inside the timed region).
+          e2e_host_buffers keeps the round-1 route (sbd_disort_batch: every bin's optical
+          properties over PCIe, all levels back).
+  configs : C3 / C4 / C5 of BASELINE.json as ONE job split over the ranks (strong scaling).
   --impl reference : the CPU restatement (oracle/) on the host cores.
 """
 from __future__ import annotations
@@ -157,6 +162,33 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def config_workloads(world, rank):
+    """The other BASELINE.json configurations as this rank's contiguous share of ONE job
+    (strong scaling: C3 and C4 are single SBDART runs, C5 is the 10^6-bin retrieval batch)."""
+    from sbdart_b200 import workloads
+    from sbdart_b200.frontend import Sbdart
+    from sbdart_b200.sharding import bin_partition
+    uz = ",".join(str(x) for x in np.linspace(5.0, 85.0, 10))
+    out = []
+    for name, nl in (
+            ("C3_thermal_radiances_nstr8_10zen", f"&INPUT idatm=2, wlinf=4, wlsup=80, wlinc=20, nstr=8, iout=20, uzen={uz}, sza=95 /"),
+            ("C4_nstr32_65layers_cloud_aerosol", "&INPUT idatm=2, nstr=32, ngrid=65, tcloud=10, zcloud=1, iaer=1, vis=23,"
+                                                 " wlinf=.25, wlsup=100, wlinc=20, iout=10 /")):
+        run = Sbdart(nl)
+        b = run.batch(run.bins())
+        lo, hi = bin_partition(len(b["bins"]), world, b["group"])[rank]
+        w = {k: b[k][lo:hi] for k in ("dtauc", "ssalb", "pmom", "bins")}
+        w["temper"], w["nstr"] = b["temper"], b["nstr"]
+        out.append(dict(name=name, total=len(b["bins"]), w=w, umu=b.get("umu"), phi=b.get("phi"),
+                        uu_levels=b.get("uu_levels")))
+    total = 1000000
+    lo, hi = bin_partition(total, world)[rank]
+    # every rank draws its own share (same distributions, SURVEY 8d; rank-dependent seed)
+    w = workloads.retrieval_batch(hi - lo, nstr=16, nlyr=33, ncols=max(1, (hi - lo) // 1000), seed=20261017 + rank)
+    out.append(dict(name="C5_retrieval_1e6bins_nstr16", total=total, w=w, umu=None, phi=None, uu_levels=None))
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -167,6 +199,7 @@ def main():
     ap.add_argument("--ref-bins", type=int, default=65536, help="bins per CPU reference step (~2.5 s on 16 threads)")
     ap.add_argument("--cpu-sample", type=int, default=262144, help="bins for cpu_baseline (about 10 s of host work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the C3 / C4 / C5 strong-scaling lines")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
@@ -182,6 +215,9 @@ def main():
     import torch
     import torch.distributed as dist
     import sbdart_b200 as sb
+    from sbdart_b200.frontend import Sbdart
+    from sbdart_b200.frontend.device import ColumnRunner
+    from sbdart_b200.timing import BatchTimer
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (there is no CPU fallback for the product arm)")
@@ -191,41 +227,26 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     w = build_workload(args.replicate)
+    w["nstr"] = 16
     B, L = w["dtauc"].shape
     NT = L + 1
     nmom = w["pmom"].shape[2] - 1
     solver = sb.Solver(local_rank)
     ext = torch.cuda.ExternalStream(solver.stream, device=dev)
 
-    # ---- pinned host copies (e2e arm) and device-resident copies (value arm) ----
-    def pinned(a):
-        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
-        return t
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
 
-    h_dt, h_ss, h_pm = pinned(w["dtauc"]), pinned(w["ssalb"]), pinned(w["pmom"])
-    h_bins = torch.from_numpy(w["bins"].view(np.uint8).reshape(B, -1).copy()).pin_memory()
-    h_tp = pinned(w["temper"])
-    h_out = {k: torch.empty((B, NT), dtype=torch.float64).pin_memory()
-             for k in ("rfldir", "rfldn", "flup", "dfdt", "uavg")}
-    h_status = torch.empty(B, dtype=torch.int32).pin_memory()
-
-    d_dt, d_ss, d_pm = h_dt.to(dev), h_ss.to(dev), h_pm.to(dev)
-    d_bins, d_tp = h_bins.to(dev), h_tp.to(dev)
-    d_out = {k: torch.empty((B, NT), dtype=torch.float64, device=dev) for k in h_out}
-    d_status = torch.empty(B, dtype=torch.int32, device=dev)
+    # ---- value: device-resident inputs, CUDA events on the solver stream ------------
+    bt = BatchTimer(solver, w, device=local_rank)
+    d_out = bt.d
     # compact top/bottom spectrum gathered at the end of a step
     d_spec = torch.empty((B, 6), dtype=torch.float64, device=dev)
     g_spec = torch.empty((world * B, 6), dtype=torch.float64, device=dev) if world > 1 else None
-    torch.cuda.synchronize()
 
-    dims = sb.SbdDims()
-    dims.nbins, dims.nlyr, dims.nstr, dims.nmom, dims.ncol = B, L, 16, nmom, 1
-    ptrs = dict(dtauc=d_dt.data_ptr(), ssalb=d_ss.data_ptr(), pmom=d_pm.data_ptr(),
-                bins=d_bins.data_ptr(), temper=d_tp.data_ptr(), status=d_status.data_ptr(),
-                **{k: v.data_ptr() for k, v in d_out.items()})
-
-    def step_device():
-        solver.disort_batch_device(dims, ptrs)
+    def gather_device():
         if world > 1:
             with torch.cuda.stream(ext):
                 torch.stack([d_out["rfldn"][:, 0], d_out["flup"][:, 0], d_out["rfldir"][:, 0],
@@ -233,55 +254,108 @@ def main():
                             dim=1, out=d_spec)
                 dist.all_gather_into_tensor(g_spec, d_spec)
 
-    hp = lambda t: t.data_ptr()  # noqa: E731
-
-    def step_host():
-        rc = sb.lib().sbd_disort_batch(
-            solver._h, dims, hp(h_dt), hp(h_ss), hp(h_pm), hp(h_bins), hp(h_tp), None, None,
-            None, hp(h_out["rfldir"]), hp(h_out["rfldn"]), hp(h_out["flup"]), hp(h_out["dfdt"]),
-            hp(h_out["uavg"]), None, hp(h_status))
-        if rc:
-            raise sb.SbdError(rc, "sbd_disort_batch")
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---- value: device-resident inputs, CUDA events on the solver stream ----
-    for _ in range(args.warmup):
-        step_device()
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
     l0 = solver.kernel_launches
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with torch.cuda.stream(ext):
-        e0.record(ext)
-    for _ in range(args.steps):
-        step_device()
-    with torch.cuda.stream(ext):
-        e1.record(ext)
+    ms_dev = bt.device_ms(steps=args.steps, warmup=args.warmup, after_step=gather_device)
     barrier()
     clocks = sampler.stop()
-    launches = solver.kernel_launches - l0
-    ms_dev = e0.elapsed_time(e1) / args.steps
-    bad = int((d_status != 0).sum().item())
+    launches = solver.kernel_launches - l0 - args.warmup * ((solver.kernel_launches - l0) // (args.steps + args.warmup))
+    bad = int((d_out["status"] != 0).sum().item())
 
-    # ---- e2e: host buffers through the C ABI (H2D + kernel + D2H inside) ----
-    for _ in range(2):
-        step_host()
+    # ---- e2e, production route: R atmospheric columns through the whole-spectrum C-ABI call.
+    # Host buffers in (setup arrays of every column), host buffers out (the top / bottom fluxes
+    # the iout=1 record reads); optical properties are produced on the device (K2) and never
+    # cross PCIe; multi-GPU: the ranks' spectra are all-gathered on the device.
+    run = Sbdart(C2_NAMELIST)
+    pin = lambda shape, dtype: torch.empty(shape, dtype=getattr(torch, np.dtype(dtype).name)).pin_memory().numpy()  # noqa: E731
+    cr = ColumnRunner(run, solver, args.replicate, levels=[run.ntop - 1, run.nbot - 1], alloc=pin)
+    g_e2e = [None]
+
+    class _Dev:
+        def __init__(self, ptr, n):
+            self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 3}
+
+    import ctypes as C
+    sb.lib().sbd_spectrum_device_fluxes.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
+
+    def step_e2e():
+        cr.step()
+        if world > 1:
+            ptr, n = C.c_void_p(), C.c_int64()
+            sb.lib().sbd_spectrum_device_fluxes(solver._h, C.byref(ptr), C.byref(n))
+            mine = torch.as_tensor(_Dev(ptr.value, n.value), device=dev)
+            if g_e2e[0] is None or g_e2e[0].numel() != world * n.value:
+                g_e2e[0] = torch.empty(world * n.value, dtype=torch.float64, device=dev)
+            dist.all_gather_into_tensor(g_e2e[0], mine)
+            torch.cuda.synchronize()
+
+    for _ in range(3):
+        step_e2e()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        step_host()
+        step_e2e()
     barrier()
     ms_e2e = (time.perf_counter() - t0) * 1e3 / args.steps
+    nb_e2e = cr.nbins.value
+    h2d_e2e, d2h_e2e = cr.transfer_bytes()
+    # the production route must reproduce the device arm's fluxes (first spectrum, top / bottom)
+    nb1 = int(w["base_bins"])
+    ref_top = d_out["flup"][:nb1, 0].cpu().numpy()
+    ref_bot = (d_out["rfldn"][:nb1, -1] + d_out["rfldir"][:nb1, -1]).cpu().numpy()
+    got_top, got_bot = cr.flup[:nb1, 0], cr.rfldn[:nb1, 1] + cr.rfldir[:nb1, 1]
+    scale = max(np.abs(ref_bot).max(), 1e-300)
+    e2e_check = float(max(np.abs(got_top - ref_top).max(), np.abs(got_bot - ref_bot).max()) / scale)
+    e2e_bad = int((cr.status[:nb_e2e] != 0).sum())
 
-    t_dev = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device=dev)
+    # ---- e2e through the host-buffer batch call (every optical property over PCIe, all
+    # levels back): the number the previous round reported, kept beside the production one
+    ms_hb = bt.e2e_ms(steps=max(2, args.steps // 2), warmup=2)
+    barrier()
+
+    t_dev = torch.tensor([ms_dev, ms_e2e, ms_hb], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
-    ms_dev, ms_e2e = float(t_dev[0]), float(t_dev[1])
+    ms_dev, ms_e2e, ms_hb = (float(x) for x in t_dev)
+
+    # ---- the other configurations: this rank's share of one job (strong scaling) --------
+    cfg_lines = {}
+    if not args.no_configs:
+        for c in config_workloads(world, rank):
+            wc = c["w"]
+            nb = len(wc["bins"])
+            t = BatchTimer(solver, wc, umu=c["umu"], phi=c["phi"], uu_levels=c["uu_levels"], device=local_rank)
+            gat = None
+            if world > 1:        # one all-gather of the top / bottom fluxes per step (padded to the largest share)
+                nmax = -(-c["total"] // world) + 4
+                mine = torch.zeros((nmax, 6), dtype=torch.float64, device=dev)
+                allr = torch.empty((world * nmax, 6), dtype=torch.float64, device=dev)
+
+                def gat(t=t, mine=mine, allr=allr, nb=nb):
+                    with torch.cuda.stream(ext):
+                        torch.stack([t.d["rfldn"][:, 0], t.d["flup"][:, 0], t.d["rfldir"][:, 0], t.d["rfldn"][:, -1],
+                                     t.d["flup"][:, -1], t.d["rfldir"][:, -1]], dim=1, out=mine[:nb])
+                        dist.all_gather_into_tensor(allr, mine)
+            barrier()
+            msd = t.device_ms(steps=3, warmup=2, after_step=gat)
+            barrier()
+            mse = t.e2e_ms(steps=3, warmup=1)
+            barrier()
+            tt = torch.tensor([msd, mse], dtype=torch.float64, device=dev)
+            nbad = torch.tensor([int((t.results(True)["status"] != 0).sum())], device=dev)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                dist.all_reduce(nbad)
+            cfg_lines[c["name"]] = {
+                "bins_total": c["total"], "bins_this_rank": nb, "scaling": "strong",
+                "value": c["total"] / (float(tt[0]) * 1e-3), "ms_per_step": float(tt[0]),
+                "e2e_value": c["total"] / (float(tt[1]) * 1e-3), "e2e_ms_per_step": float(tt[1]),
+                "unit": UNIT, "bad_bins": int(nbad[0]),
+                "note": "device-timed incl. the all-gather of the top/bottom fluxes; e2e = host-buffer C-ABI call "
+                        "of this rank's share (pinned buffers), max over ranks"}
+            del t
 
     if rank == 0:
         h2d = (w["dtauc"].nbytes + w["ssalb"].nbytes + w["pmom"].nbytes + w["bins"].nbytes +
@@ -318,9 +392,16 @@ def main():
                        "parallelism": f"bins sharded over {world} GPU(s), one all-gather of the "
                                       "top/bottom spectrum per step" if world > 1 else "1 GPU"},
             "clocks": clocks,
-            "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": UNIT,
-                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": ms_e2e},
+            "e2e": {"value": world * nb_e2e / (ms_e2e * 1e-3), "unit": UNIT,
+                    "h2d_bytes_per_step": int(h2d_e2e), "d2h_bytes_per_step": int(d2h_e2e),
+                    "ms_per_step": ms_e2e, "bins_per_gpu_per_step": int(nb_e2e),
+                    "route": "sbd_spectrum_run_columns: host setup arrays of every column in, top/bottom fluxes "
+                             "out; optical properties produced on the device (K2), solve, level pack"
+                             + (", device all-gather of the ranks' spectra" if world > 1 else ""),
+                    "max_flux_diff_vs_device_arm_over_scale": e2e_check, "bad_bins": e2e_bad},
+            "e2e_host_buffers": {"value": world * B / (ms_hb * 1e-3), "unit": UNIT, "ms_per_step": ms_hb,
+                                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                                 "route": "sbd_disort_batch: every bin's dtauc/ssalb/pmom over PCIe, all levels back"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak,
                          "unit": "TFLOP/s", "frac": achieved / fp64_peak if fp64_peak else None,
@@ -334,6 +415,8 @@ def main():
                                  "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}},
             "bad_bins": bad,
         }
+        if cfg_lines:
+            line["configs"] = cfg_lines
         if not args.no_cpu_baseline and world >= 1:
             from oracle import oracle
             cores = os.cpu_count() or 1

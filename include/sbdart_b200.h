@@ -278,6 +278,11 @@ int sbd_spectrum_run_columns(sbd_handle *h, const sbd_optics_params *p, int32_t 
                              double *wt, int32_t *nbins, double *rfldir, double *rfldn, double *flup,
                              int32_t *status);
 
+/* Device copy of the flux results of the last sbd_spectrum_run* call on this handle
+ * ([3][3 ncol nwl][nsel] with a level selection, else [3][3 ncol nwl][nz+1]: rfldir, rfldn,
+ * flup), valid until the next call: what a multi-GPU caller hands to its all-gather. */
+int sbd_spectrum_device_fluxes(sbd_handle *h, void **ptr, int64_t *ndoubles);
+
 /* Bytes the last sbd_spectrum_run* call moved over PCIe (setup arrays in, results out). */
 int sbd_last_transfer_bytes(const sbd_handle *h, int64_t *h2d, int64_t *d2h);
 

@@ -33,7 +33,7 @@ EXPORTS = (
     "sbd_status_string", "sbd_abi_version", "disort_", "sbd_disort_last_status",
     "sbd_measure_fp64_peak", "sbd_optics_upload_tables", "sbd_spectrum_run",
     "sbd_set_radiance_levels", "sbd_spectrum_set_aerosols", "sbd_set_corint", "sbd_build_id", "sbd_set_radiance_layout", "sbd_set_flux_levels",
-    "sbd_spectrum_run_columns", "sbd_last_transfer_bytes",
+    "sbd_spectrum_run_columns", "sbd_last_transfer_bytes", "sbd_spectrum_device_fluxes",
 )
 
 

@@ -67,4 +67,6 @@ struct sbd_handle {
     void *host_stage = nullptr;                // pinned staging of the whole-spectrum setup arrays
     size_t host_stage_cap = 0;
     size_t last_h2d_bytes = 0, last_d2h_bytes = 0;
+    void *last_flux_dev = nullptr;             // device copy of the last spectrum run's flux results
+    size_t last_flux_doubles = 0;
 };

@@ -237,10 +237,12 @@ static int spectrum_core(sbd_handle *h, const sbd_optics_params *p, int ncol, co
         h->launches += 1;
         const size_t one = nslot * nsel * 8;
         const double *pk = (const double *)h->d_fluxpack.p;
+        h->last_flux_dev = h->d_fluxpack.p; h->last_flux_doubles = 3 * nslot * nsel;
         if (rfldir) { CK(cudaMemcpyAsync(rfldir, pk, one, cudaMemcpyDeviceToHost, st)); d2h += one; }
         if (rfldn) { CK(cudaMemcpyAsync(rfldn, pk + nslot * nsel, one, cudaMemcpyDeviceToHost, st)); d2h += one; }
         if (flup) { CK(cudaMemcpyAsync(flup, pk + 2 * nslot * nsel, one, cudaMemcpyDeviceToHost, st)); d2h += one; }
     } else {
+        h->last_flux_dev = o; h->last_flux_doubles = 3 * per;
         if (rfldir) { CK(cudaMemcpyAsync(rfldir, o, per * 8, cudaMemcpyDeviceToHost, st)); d2h += per * 8; }
         if (rfldn) { CK(cudaMemcpyAsync(rfldn, o + per, per * 8, cudaMemcpyDeviceToHost, st)); d2h += per * 8; }
         if (flup) { CK(cudaMemcpyAsync(flup, o + 2 * per, per * 8, cudaMemcpyDeviceToHost, st)); d2h += per * 8; }
@@ -288,6 +290,14 @@ extern "C" int sbd_spectrum_run_columns(sbd_handle *h, const sbd_optics_params *
 {
     return spectrum_core(h, p, ncol, z, pr, t, uu, clouds, wlalb, alb, wlsun, sun, 0, nullptr, 0, nullptr, nk, wl,
                          dwl, wt, nbins, rfldir, rfldn, flup, nullptr, status, nullptr);
+}
+
+extern "C" int sbd_spectrum_device_fluxes(sbd_handle *h, void **ptr, int64_t *ndoubles)
+{
+    if (!h || !ptr || !ndoubles) return SBD_ERR_ARG;
+    *ptr = h->last_flux_dev;
+    *ndoubles = (int64_t)h->last_flux_doubles;
+    return SBD_SUCCESS;
 }
 
 extern "C" int sbd_last_transfer_bytes(const sbd_handle *h, int64_t *h2d, int64_t *d2h)

@@ -160,16 +160,15 @@ def _bind(L):
     L.sbd_spectrum_run.argtypes = ([C.c_void_p, C.POINTER(OpticsParams)] + [C.c_void_p] * 9 +
                                    [C.c_int32, C.c_void_p, C.c_int32, C.c_void_p] + [C.c_void_p] * 10 +
                                    [C.POINTER(InputsOut)])
+    L.sbd_spectrum_run_columns.restype = C.c_int
+    L.sbd_spectrum_run_columns.argtypes = ([C.c_void_p, C.POINTER(OpticsParams), C.c_int32] + [C.c_void_p] * 9 +
+                                           [C.c_void_p] * 4 + [C.POINTER(C.c_int32)] + [C.c_void_p] * 4)
     L.sbd_spectrum_set_aerosols.restype = C.c_int
     L.sbd_spectrum_set_aerosols.argtypes = [C.c_void_p, C.POINTER(AerosolParams)] + [C.c_void_p] * 7
     L._spectrum_bound = True
 
 
-def run_spectrum(run: Sbdart, solver, want_inputs=False):
-    """All bins of `run` produced and solved on the GPU.  Returns (rows, result[, inputs])
-    shaped like Sbdart.bins() / a solve() result, in loop order."""
-    L = lib()
-    _bind(L)
+def _ensure_tables(L, solver):
     if not getattr(solver, "_optics_tables_uploaded", False):
         tab, index = pack_tables()
         rc = L.sbd_optics_upload_tables(solver._h, tab.ctypes.data, len(tab), index.ctypes.data,
@@ -177,6 +176,10 @@ def run_spectrum(run: Sbdart, solver, want_inputs=False):
         if rc:
             raise SbdError(rc, "sbd_optics_upload_tables")
         solver._optics_tables_uploaded = True
+
+
+def optics_setup(run: Sbdart):
+    """struct sbd_optics_params and the wavelength-independent tables of a run."""
     p, nz, nwl = run.p, run.nz, run.nwl
     P = OpticsParams()
     P.nz, P.nwl, P.kdist, P.nstr, P.nf, P.nothrm, P.imomc = nz, nwl, run.kdist, p["nstr"], p["nf"], p["nothrm"], p["imomc"]
@@ -189,6 +192,76 @@ def run_spectrum(run: Sbdart, solver, want_inputs=False):
     P.wl1, P.wl2, P.wlinc, P.amu0 = run.wl1, run.wl2, run.wlinc, run.amu0
     P.xo4, P.xrsc, P.solfac, P.phi0 = p["xo4"], p["xrsc"], p["solfac"], run.phi0
     P.fisot, P.temis, P.btemp, P.ttemp = p["fisot"], p["temis"], run.btemp, run.ttemp
+    return P, ce, wlalb, alb, wlsun, sun
+
+
+class ColumnRunner:
+    """Whole-spectrum runs of `ncol` atmospheric columns in one call (sbd_spectrum_run_columns):
+    the columns share the run's spectral grid, clouds, surface and aerosols; z / pr / t / uu may
+    differ per column (default: the run's own atmosphere replicated).  Host buffers in, host
+    buffers out; with `levels` the flux arrays hold those output levels only ([bin][nsel]).
+    `alloc(shape, dtype)` lets the caller supply pinned memory."""
+
+    def __init__(self, run: Sbdart, solver, ncol, levels=None, columns=None, alloc=None):
+        L = lib()
+        _bind(L)
+        _ensure_tables(L, solver)
+        self.L, self.run, self.solver, self.ncol = L, run, solver, int(ncol)
+        self.P, self.ce, self.wlalb, self.alb, self.wlsun, self.sun = optics_setup(run)
+        nz, nwl = run.nz, run.nwl
+        alloc = alloc or (lambda shape, dtype: np.zeros(shape, dtype))
+        tile = lambda a: np.ascontiguousarray(np.broadcast_to(np.asarray(a, dtype=float), (self.ncol,) + np.shape(a)))  # noqa: E731
+        if columns is None:
+            self.z, self.pr, self.t, self.uu = tile(run.z), tile(run.pr), tile(run.t), tile(run.uu)
+        else:
+            self.z, self.pr, self.t, self.uu = (np.ascontiguousarray(columns[k], dtype=float) for k in ("z", "pr", "t", "uu"))
+            self.P.btemp = self.P.ttemp = -1.0      # each column's own boundary temperatures
+        assert self.z.shape == (self.ncol, nz) and self.uu.shape == (self.ncol, 64, nz + 1), (self.uu.shape, nz)
+        self.levels = None if levels is None else np.ascontiguousarray(sorted(set(levels)), dtype=np.int32)
+        nlev = nz + 1 if self.levels is None else len(self.levels)
+        nitem = self.ncol * nwl
+        self.nslot = 3 * nitem
+        self.nk = alloc((nitem,), np.int32)
+        self.wl, self.dwl = alloc((nwl,), np.float64), alloc((nwl,), np.float64)
+        self.wt = alloc((self.nslot,), np.float64)
+        self.rfldir, self.rfldn, self.flup = (alloc((self.nslot, nlev), np.float64) for _ in range(3))
+        self.status = alloc((self.nslot,), np.int32)
+        self.nbins = C.c_int32(0)
+
+    def step(self):
+        L, ptr = self.L, (lambda a: a.ctypes.data)
+        if self.levels is not None:
+            L.sbd_set_flux_levels(self.solver._h, self.levels.ctypes.data, len(self.levels))
+        set_aerosols(L, self.solver, self.run.aerosols)
+        try:
+            rc = L.sbd_spectrum_run_columns(
+                self.solver._h, C.byref(self.P), self.ncol, ptr(self.z), ptr(self.pr), ptr(self.t), ptr(self.uu),
+                ptr(self.ce) if len(self.ce) else None, ptr(self.wlalb), ptr(self.alb), ptr(self.wlsun),
+                ptr(self.sun), ptr(self.nk), ptr(self.wl), ptr(self.dwl), ptr(self.wt), C.byref(self.nbins),
+                ptr(self.rfldir), ptr(self.rfldn), ptr(self.flup), ptr(self.status))
+        finally:
+            if self.levels is not None:
+                L.sbd_set_flux_levels(self.solver._h, None, 0)
+            if self.run.aerosols.active:
+                L.sbd_spectrum_set_aerosols(self.solver._h, None, None, None, None, None, None, None, None)
+        if rc:
+            raise SbdError(rc, "sbd_spectrum_run_columns")
+        return self.nbins.value
+
+    def transfer_bytes(self):
+        h2d, d2h = C.c_int64(0), C.c_int64(0)
+        self.L.sbd_last_transfer_bytes(self.solver._h, C.byref(h2d), C.byref(d2h))
+        return h2d.value, d2h.value
+
+
+def run_spectrum(run: Sbdart, solver, want_inputs=False):
+    """All bins of `run` produced and solved on the GPU.  Returns (rows, result[, inputs])
+    shaped like Sbdart.bins() / a solve() result, in loop order."""
+    L = lib()
+    _bind(L)
+    _ensure_tables(L, solver)
+    p, nz, nwl = run.p, run.nz, run.nwl
+    P, ce, wlalb, alb, wlsun, sun = optics_setup(run)
     nmom = min(p["nstr"] + 2, 40)
     nslot, NT = 3 * nwl, nz + 1
     nk = np.zeros(nwl, np.int32)
