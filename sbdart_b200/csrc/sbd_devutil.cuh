@@ -28,6 +28,40 @@ __device__ __forceinline__ void warp_copy_async(double *dst, const double *src, 
     for (int i = lane; i < ndoubles / 2; i += 32) cp_async16(dst + 2 * i, src + 2 * i);
 }
 
+// ---- bulk asynchronous copies (TMA engine, cp.async.bulk) completing on an mbarrier ------
+// One instruction by one lane moves a whole record (global -> shared) instead of one LDGSTS
+// per 16 bytes and lane.  Sizes and both addresses must be multiples of 16 bytes.
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *smem, const void *gmem, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem), "r"(bytes),
+                   "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+// waits for the phase with the given parity; gives up after ~1 s (returns false)
+__device__ __forceinline__ bool mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    const unsigned b = (unsigned)__cvta_generic_to_shared(bar);
+#pragma unroll 1
+    for (int spin = 0; spin < (1 << 26); spin++) {
+        unsigned done;
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(b), "r"(parity) : "memory");
+        if (done) return true;
+    }
+    return false;
+}
+// orders this thread's earlier generic-proxy accesses (ordinary loads / stores) before its
+// later async-proxy operations (the bulk copies)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
 // 1/x to ~1 ulp without the IEEE slow paths of the division operator:
 // MUFU.RCP64H seed + two Newton steps (x must be normal and non-zero).
 __device__ __forceinline__ double fast_rcp(double x)

@@ -36,6 +36,20 @@
 #include "sbd_planck.cuh"
 #include "sbd_devutil.cuh"
 
+// Staging of scratch data between the phases (global -> shared): bulk asynchronous copies
+// (cp.async.bulk: the TMA engine, one instruction by one lane, completion on an mbarrier) or
+// cp.async (LDGSTS, 16 bytes per lane and instruction).  Measured on the C2 bench (M bins/s,
+// same box, two runs each): LDGSTS everywhere 4.20 / 4.21; bulk copies for the phase-3 pivot rows
+// + flux records (4.9 KB per layer) 4.26 / 4.26; for the phase-2 record prefetch (1.4 KB per
+// layer) 4.00 / 3.99; for both 4.20 / 4.19.  The phase-3 staging ships as bulk copies.
+#ifndef SBD_TMA_P2
+#define SBD_TMA_P2 0
+#endif
+#ifndef SBD_TMA_P3
+#define SBD_TMA_P3 1
+#endif
+#define SBD_USE_TMA (SBD_TMA_P2 || SBD_TMA_P3)
+
 namespace sbd {
 
 #ifdef SBD_PHASE_TIMING
@@ -101,7 +115,8 @@ struct FastLayout {
     {
         // y0, work area, taucpr/tauc, beam transmissions (2), pk(+2 boundary temps),
         // prologue work values, level map; kept even for 16-byte alignment
-        size_t d = (size_t)N + (NU > 0 ? work_rad : work) + 4 * (L + 1) + (L + 3) + 3 * L + (NT + 1) / 2 + 2;
+        // (+ three mbarriers of the bulk-copy staging and a spare)
+        size_t d = (size_t)N + (NU > 0 ? work_rad : work) + 4 * (L + 1) + (L + 3) + 3 * L + (NT + 1) / 2 + 4;
         d = (d + 1) & ~(size_t)1;
         return d + (NU > 0 ? rad_doubles(NU, NPHI) : 0);
     }
@@ -777,6 +792,10 @@ disort_fast_kernel(const LaunchArgs a)
     double *pk = edir + (L + 1);
     double *lw = pk + (L + 3);                                   // 3 x L prologue work values
     int *layru = (int *)(lw + 3 * L);
+#if SBD_USE_TMA
+    // mbarriers of the bulk-copy staging: [0], [1] phase-3 double buffer, [2] phase-2 record prefetch
+    unsigned long long *mbar = reinterpret_cast<unsigned long long *>(lw + 3 * L + (NT + 1) / 2);
+#endif
     // radiance work values, behind the level map
     double *uE = wsm + (FL::warp_doubles(L, NT, NU, NPHI) - FL::rad_doubles(NU, NPHI));
     double *uGU = uE + N * FL::ecols, *uI = uGU + NU * FL::ecols, *cosm = uI + NU, *ugl = cosm + NPHI;
@@ -806,6 +825,18 @@ disort_fast_kernel(const LaunchArgs a)
     double *tsm = tsm_base + (size_t)task * FL::task;
     const int rg = lane >> 2, cg = lane & 3;              // 2-D tiling of phase 2
     const unsigned jpart = jacobi_partners<n>(g);
+#if SBD_USE_TMA
+    if (lane == 0) { mbar_init(mbar, 1); mbar_init(mbar + 1, 1); mbar_init(mbar + 2, 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
+    unsigned mphase = 0;      // bit b: parity of the next completion of mbarrier b
+    // One lane issues the bulk copies.  Their sources (scratch records written with ordinary
+    // stores earlier in the launch) are ordered before them by ONE proxy fence at the start of
+    // phases 2 and 3 (after the phase barrier); a destination buffer is reused only after the
+    // warp has finished reading it (__syncwarp), as in any mbarrier pipeline.  (A proxy fence
+    // before every issue also waits for the lane's outstanding pivot-row stores: -8 %.)
+#define SBD_BULK_BEGIN(bar, bytes) mbar_expect_tx(bar, bytes)
+#endif
 
     for (;;) {
         int bin = 0;
@@ -993,11 +1024,24 @@ disort_fast_kernel(const LaunchArgs a)
         double *stg = tsm_base + 3 * FL::rec;     // assembled rows of the current layer
         if (mrun && !status) {
             double w[KS][LC], rhs[KS];
+#if SBD_TMA_P2
+            __syncwarp();
+            fence_proxy_async();
+            if (lane == 0) {
+                const int nr = ncut > 1 ? 2 : 1;          // records 0 and 1 are contiguous
+                SBD_BULK_BEGIN(mbar + 2, 8u * FL::rec * nr);
+                bulk_g2s(rslot, recs, 8u * FL::rec * nr, mbar + 2);
+            }
+            if (!mbar_wait(mbar + 2, (mphase >> 2) & 1u)) status = SBD_BIN_SINGULAR;    // never expected
+            mphase ^= 4u;
+            __syncwarp();
+#else
             warp_copy_async(rslot, recs, FL::rec, lane);
             if (ncut > 1) warp_copy_async(rslot + FL::rec, recs + FL::rec, FL::rec, lane);
             cp_async_commit();
             cp_async_wait_all();
             __syncwarp();
+#endif
             // top boundary rows r = 0..n-1 in slots 0..n-1 (disort.f:2887-2915, :3547-3550)
             stage_rows<n>(stg, rslot, false, nullptr, 0, n, 0.0, cwt, cmu, lane);
             if (lane < n)
@@ -1020,11 +1064,18 @@ disort_fast_kernel(const LaunchArgs a)
             __syncwarp();
             for (int lc = 0; lc < ncut; lc++) {
                 const bool last = (lc == ncut - 1);
+#if SBD_TMA_P2
+                if (lc + 2 < ncut && lane == 0) {      // (the slot was last read two layers ago)
+                    SBD_BULK_BEGIN(mbar + 2, 8u * FL::rec);
+                    bulk_g2s(rslot + ((lc + 2) % 3) * FL::rec, recs + (size_t)(lc + 2) * FL::rec, 8u * FL::rec, mbar + 2);
+                }
+#else
                 if (lc + 2 < ncut) {
                     warp_copy_async(rslot + ((lc + 2) % 3) * FL::rec, recs + (size_t)(lc + 2) * FL::rec,
                                     FL::rec, lane);
                     cp_async_commit();
                 }
+#endif
                 const double *rc = rslot + (lc % 3) * FL::rec;
                 const double *rn = rslot + ((lc + 1) % 3) * FL::rec;
                 const double tb = taucpr[lc + 1];
@@ -1094,7 +1145,14 @@ disort_fast_kernel(const LaunchArgs a)
 #pragma unroll 1
                 for (int j = N / 2; j < N && !sing; j++, uslice += US) sing = elim_step<n, W2>(w, rhs, act, uslice, j & 3, rg, cg);
                 if (sing) { status = SBD_BIN_SINGULAR; break; }
+#if SBD_TMA_P2
+                if (lc + 2 < ncut) {       // record lc+2 has landed
+                    if (!mbar_wait(mbar + 2, (mphase >> 2) & 1u)) { status = SBD_BIN_SINGULAR; break; }
+                    mphase ^= 4u;
+                }
+#else
                 cp_async_wait_all();       // record lc+2 has landed
+#endif
                 __syncwarp();
             }
         }
@@ -1115,10 +1173,19 @@ disort_fast_kernel(const LaunchArgs a)
             constexpr int kSlot = FL::ublk + FL::frec + (RAD ? FL::rec : 0);
             auto fetch_layer = [&](int lyr, int buf) {
                 double *dstp = tsm_base + buf * kSlot;
+#if SBD_TMA_P3
+                if (lane == 0) {
+                    SBD_BULK_BEGIN(mbar + buf, 8u * kSlot);
+                    bulk_g2s(dstp, ublk + (size_t)lyr * FL::ublk, 8u * FL::ublk, mbar + buf);
+                    bulk_g2s(dstp + FL::ublk, frecs + (size_t)lyr * FL::frec, 8u * FL::frec, mbar + buf);
+                    if (RAD) bulk_g2s(dstp + FL::ublk + FL::frec, recs + (size_t)lyr * FL::rec, 8u * FL::rec, mbar + buf);
+                }
+#else
                 warp_copy_async(dstp, ublk + (size_t)lyr * FL::ublk, FL::ublk, lane);
                 warp_copy_async(dstp + FL::ublk, frecs + (size_t)lyr * FL::frec, FL::frec, lane);
                 if (RAD) warp_copy_async(dstp + FL::ublk + FL::frec, recs + (size_t)lyr * FL::rec, FL::rec, lane);
                 cp_async_commit();
+#endif
             };
             // RAD: upward intensities are carried bottom-up along with the back substitution
             // (one user angle per lane); bnd_up = intensity leaving the surface (disort.f:4747-4778)
@@ -1146,14 +1213,23 @@ disort_fast_kernel(const LaunchArgs a)
                     azerr = fmax(azerr, rr);
                 }
             };
+#if SBD_TMA_P3
+            fence_proxy_async();      // pivot rows and flux records: ordinary stores of phases 1 and 2
+#endif
             fetch_layer(ncut - 1, 0);
             for (int lc = ncut - 1; lc >= 0; lc--) {
                 const int buf = (ncut - 1 - lc) & 1;
 #ifdef SBD_PHASE_TIMING
                 long long tsub = clock64();
 #endif
+#if SBD_TMA_P3
+                if (lc > 0) fetch_layer(lc - 1, buf ^ 1);
+                if (!mbar_wait(mbar + buf, (mphase >> buf) & 1u)) status = SBD_BIN_SINGULAR;   // never expected
+                mphase ^= 1u << buf;
+#else
                 if (lc > 0) { fetch_layer(lc - 1, buf ^ 1); cp_async_wait_one(); }
                 else cp_async_wait_all();
+#endif
                 __syncwarp();
 #ifdef SBD_PHASE_TIMING
                 if (threadIdx.x == 0) { const long long t = clock64(); atomicAdd(&g_phase_ticks[4], (unsigned long long)(t - tsub)); tsub = t; }
