@@ -1,0 +1,968 @@
+// Flux kernel for NSTR = 4, 8, 16 (levels at the layer boundaries): one warp per bin, the
+// boundary-value problem of DISORT solved layer by layer with reflection / transmission
+// operators instead of the N L x N L band system (SETMTX / SOLVE0, disort.f:2702, :3322).
+//
+// Same discrete-ordinate equations, same delta-M scaling, truncation, sources and boundary
+// conditions as the reference (tests/adding_model.py states the
+// algorithm in numpy and tests/test_adding_math_cpu.py checks it against the CPU oracle).
+//
+// In the flux-weighted variables u^ = sqrt(w mu) u the sums s^ = u^+ + u^- and differences
+// d^ = u^+ - u^- obey d s^/d tau = Po d^, d d^/d tau = Pe s^ with the symmetric operators of
+// the reduced eigenproblem (disort.f:3221-3269).  With Po = L L^T, L^T Pe L = V K^2 V^T (the
+// SVD of K^T L, as in sbd_fast.cu) and P = L V, a layer of scaled depth 2h has
+//     R + T = I - 2 (I + P diag(coth(kh)/k) P^T)^-1,   R - T = I - 2 (I + P diag(tanh(kh)/k) P^T)^-1,
+// evaluated in mode space:  M+- = P (P^T P + diag(k tanh(kh) | k coth(kh)))^-1 P^T,
+//     R = -I + M+ + M-,   T = M+ - M-
+// (two SPD inversions without pivoting; finite for k -> 0 and h -> 0).  Interaction principle:
+//     u+_top = R u-_top + T u+_bot + s_up,     u-_bot = T u-_top + R u+_bot + s_dn
+// with the sources from the particular solutions of UPBEAM / UPISOT (disort.f:4130, :4247).
+//
+//   phase 1  32/n layers at a time, n lanes per layer: eigenproblem, R, T, s_up, s_dn -> scratch
+//   phase 2  bottom-up over the layers, the whole warp on one layer (2-D tiles of the n x n
+//            matrices): reflection Rb / emission sb of everything below each interface,
+//            (I - R Rb) Y = [T | R sb + s_dn] by Gauss-Jordan with partial pivoting in registers
+//   phase 3  top-down: downward intensities d <- Y d + y, fluxes at every level as four dot
+//            products (FLUXES, disort.f:1926-2006)
+// Scratch per resident warp: L (2 n^2 + 2 n) doubles (38 KB at NSTR=16 / 33 layers; all
+// resident warps together stay inside the L2).
+#include <math.h>
+#include <stdlib.h>
+
+#include "sbd_internal.h"
+#include "sbd_planck.cuh"
+#include "sbd_devutil.cuh"
+
+namespace sbd {
+
+#ifdef SBD_PHASE_TIMING
+__device__ unsigned long long g_add_ticks[8];
+#define ADD_TICK(i)                                                                     \
+    do {                                                                                \
+        if (threadIdx.x == 0) {                                                         \
+            const long long tnow = clock64();                                           \
+            atomicAdd(&g_add_ticks[i], (unsigned long long)(tnow - tphase));            \
+            tphase = tnow;                                                              \
+        }                                                                               \
+    } while (0)
+#else
+#define ADD_TICK(i) do { } while (0)
+#endif
+
+template <int n>
+struct AddLayout {
+    static constexpr int N = 2 * n;
+    // phase-1 record of a layer (global scratch): R[n][n], T[n][n], s_up[n], s_dn[n]
+    static constexpr int r_R = 0, r_T = n * n, r_su = 2 * n * n, r_sd = 2 * n * n + n;
+    static constexpr int rec = 2 * n * n + 2 * n;
+    // phase-2 record (overwrites the phase-1 record of the layer): Y[n][n], y[n], and the flux
+    // functionals of the layer's top interface: fu = D^T Rb, cu = c^T Rb, D^T sb, c^T sb
+    static constexpr int o_Y = 0, o_y = n * n, o_fu = n * n + n, o_cu = n * n + 2 * n, o_f0 = n * n + 3 * n;
+    static_assert(n * n + 3 * n + 2 <= rec, "phase-2 record must fit into the phase-1 record");
+    // 2-D tiling of phase 2: n rows x CG column groups, CW columns per lane
+    static constexpr int CG = n >= 4 ? 4 : n;
+    static constexpr int CW = n / CG;
+    // phase-1 shared memory per layer group: gl[N], K, L, P, X [n][n], 4 vectors
+    static constexpr int tasks = 32 / n;
+    static constexpr int task0 = N + 4 * n * n + 4 * n;
+    // padded to 4 (mod 16) doubles: the groups' areas start 8 banks apart, so the four
+    // addresses of a group-wide broadcast load never share a bank
+    static constexpr int task = ((task0 + 11) / 16) * 16 + 4;
+    // phase-2 shared memory: Rb, sb, Y, y, W, w, two records
+    static constexpr int p2 = 3 * n * n + 3 * n + 2 * rec;
+    static constexpr int work = tasks * task > p2 ? tasks * task : p2;
+    __host__ __device__ static size_t warp_doubles(int L)
+    {
+        // y0, work area, taucpr / tauc / beam transmissions (2), pk (+2 boundary temperatures),
+        // three prologue work values per layer, level map
+        size_t d = (size_t)N + work + 4 * (L + 1) + (L + 3) + 3 * L + (L + 2) / 2 + 2;
+        return (d + 1) & ~(size_t)1;
+    }
+    static constexpr int cta = 4 * n + N * n + 2;     // cmu cwt csq cd, ylm, sum(w mu), sum(w)
+    __host__ __device__ static size_t slot_doubles(int L) { return (size_t)L * rec; }
+};
+
+template <int n>
+__device__ __forceinline__ double add_group_sum(double v)
+{
+#pragma unroll
+    for (int o = n / 2; o > 0; o >>= 1) v += __shfl_xor_sync(FULLMASK, v, o, n);
+    return v;
+}
+
+template <int n>
+__device__ __forceinline__ unsigned add_jacobi_partners(int g)
+{
+    unsigned pk = 0;
+#pragma unroll
+    for (int r = 0; r < n - 1; r++) {
+        int partner;
+        if (g == n - 1) partner = r;
+        else if (g == r) partner = n - 1;
+        else {
+            partner = 2 * r - g + (n - 1);
+            if (partner >= n - 1) partner -= n - 1;
+            if (partner >= n - 1) partner -= n - 1;
+        }
+        pk |= (unsigned)partner << (3 * r);
+    }
+    return pk;
+}
+
+// ---------------------------------------------------------------------------
+// phase 1: one layer per group of n lanes; lane g holds row g / column g / mode g
+// ---------------------------------------------------------------------------
+template <int n>
+__device__ __forceinline__ int phase1_adding(
+    const double *__restrict__ dtauc, const double *__restrict__ ssalb,
+    const double *__restrict__ pmom, int ldp, int lc, bool active,
+    double fbeam, double umu0, bool plank,
+    const double *cmu, const double *csq, const double *cd, const double *cylm,
+    const double *y0, const double *ebeam, const double *pk,
+    double *tsm, double *rec, int g, unsigned jpart)
+{
+    using AL = AddLayout<n>;
+    constexpr int N = 2 * n;
+    double *sgl = tsm, *sK = sgl + N, *sL = sK + n * n, *sP = sL + n * n, *sX = sP + n * n, *sv = sX + n * n;
+
+    double ss = ssalb[lc];
+    if (ss == 1.0) ss = 1.0 - kDither;
+    double dt = dtauc[lc];
+    if (dt < 0.0) dt = 0.0;
+    const double f = pmom[(size_t)lc * ldp + N];
+    const double oprim = ss * (1. - f) * fast_rcp(1. - f * ss);
+    const double dtaucp = (1. - f * ss) * dt;
+    const double rf = fast_rcp(1. - f);
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        int l = g + h * n;
+        double pm = (l == 0) ? 1.0 : pmom[(size_t)lc * ldp + l];
+        sgl[l] = (2 * l + 1) * oprim * (pm - f) * rf;
+    }
+    __syncwarp();
+
+    // rows g of Pe and Po (even / odd Legendre sums; disort.f:3197-3216 in symmetric form)
+    double pe[n], po[n];
+#pragma unroll
+    for (int j = 0; j < n; j++) { pe[j] = 0.0; po[j] = 0.0; }
+#pragma unroll
+    for (int l = 0; l < N; l++) {
+        const double t = sgl[l] * cylm[l * n + g];
+        if (l & 1) {
+#pragma unroll
+            for (int j = 0; j < n; j++) po[j] = fma(t, cylm[l * n + j], po[j]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < n; j++) pe[j] = fma(t, cylm[l * n + j], pe[j]);
+        }
+    }
+    const double sqg = csq[g], rmu = fast_rcp(cmu[g]);
+#pragma unroll
+    for (int j = 0; j < n; j++) {
+        const double sc = sqg * csq[j];
+        const double dg = (j == g) ? rmu : 0.0;
+        pe[j] = dg - sc * pe[j];
+        po[j] = dg - sc * po[j];
+    }
+
+    // row Cholesky of both operators: Po = L L^T, Pe = K K^T (lane g = row g)
+    int bad = 0;
+    double rK[n], rL[n];
+#pragma unroll
+    for (int j = 0; j < n; j++) {
+        double nume = pe[j], numo = po[j];
+#pragma unroll
+        for (int k = 0; k < j; k++) {
+            nume = fma(-pe[k], shfl_d(pe[k], j, n), nume);
+            numo = fma(-po[k], shfl_d(po[k], j, n), numo);
+        }
+        double pive = shfl_d(nume, j, n), pivo = shfl_d(numo, j, n);
+        if (!(pivo > 0.0)) { bad = 1; pivo = 1.0; }
+        // Pe is only semidefinite when w' -> 1: keep the factor real (a NaN pivot is a failure)
+        const double floor_e = 1.0e-30;
+        if (pive != pive) bad = 1;
+        if (!(pive > floor_e)) pive = floor_e;
+        const double rie = fast_rsqrt(pive), rio = fast_rsqrt(pivo);
+        rK[j] = rie; rL[j] = rio;
+        pe[j] = (g == j) ? pive * rie : ((g > j) ? nume * rie : 0.0);
+        po[j] = (g == j) ? pivo * rio : ((g > j) ? numo * rio : 0.0);
+    }
+#pragma unroll
+    for (int j = 0; j < n; j++) { sK[g * n + j] = pe[j]; sL[g * n + j] = po[j]; }
+    __syncwarp();
+
+    // column g of A = K^T L
+    double a[n];
+    {
+        double lcol[n];
+#pragma unroll
+        for (int k = 0; k < n; k++) lcol[k] = sL[k * n + g];
+#pragma unroll
+        for (int i = 0; i < n; i++) {
+            double acc = 0.0;
+#pragma unroll
+            for (int k = i; k < n; k++) acc = fma(sK[k * n + i], lcol[k], acc);
+            a[i] = acc;
+        }
+    }
+
+    // one-sided Jacobi (round-robin pairing): A V = U S, S = the eigenvalues k (see sbd_fast.cu)
+    if (n > 1) {
+        double own2 = 0.0;
+#pragma unroll
+        for (int i = 0; i < n; i++) own2 = fma(a[i], a[i], own2);
+        for (int sweep = 0; sweep < 40; sweep++) {
+            int big = 0;
+#pragma unroll 1
+            for (int r = 0; r < n - 1; r++) {
+                const int partner = (jpart >> (3 * r)) & 7;
+                double pa[n];
+                double g0 = 0.0, g1 = 0.0;
+                const double oth2 = shfl_d(own2, partner, n);
+#pragma unroll
+                for (int i = 0; i < n; i++) {
+                    pa[i] = shfl_d(a[i], partner, n);
+                    if (i & 1) g1 = fma(a[i], pa[i], g1); else g0 = fma(a[i], pa[i], g0);
+                }
+                const double gam = g0 + g1;
+                const bool lo = g < partner;
+                const double gg = gam * gam, ab = own2 * oth2;
+                if (gg > 1.0e-24 * ab && gg > 1.0e-290) {
+                    if (gg > kJacobiBig * ab) big = 1;
+                    const double dl = lo ? 0.5 * (oth2 - own2) : 0.5 * (own2 - oth2);
+                    const double rh = fast_rsqrt(fma(dl, dl, gg));
+                    const double x = fma(0.5 * fabs(dl), rh, 0.5);
+                    const double rc = fast_rsqrt(x);
+                    const double cc = x * rc;
+                    double sn = gam * (0.5 * rh) * rc;
+                    if ((dl < 0.0) != lo) sn = -sn;
+                    own2 = fma(sn * rc, gam, own2);
+#pragma unroll
+                    for (int i = 0; i < n; i++) a[i] = fma(sn, pa[i], cc * a[i]);
+                }
+            }
+            if (!__any_sync(FULLMASK, big)) break;
+            own2 = 0.0;
+#pragma unroll
+            for (int i = 0; i < n; i++) own2 = fma(a[i], a[i], own2);
+        }
+    }
+    double s2 = 0.0;
+#pragma unroll
+    for (int i = 0; i < n; i++) s2 = fma(a[i], a[i], s2);
+    const double kk = sqrt(s2);
+    // column g of P = L V = K^-T (A V)
+    double P[n];
+#pragma unroll
+    for (int i = n - 1; i >= 0; i--) {
+        double acc = a[i];
+#pragma unroll
+        for (int k = i + 1; k < n; k++) acc = fma(-sK[k * n + i], P[k], acc);
+        P[i] = acc * rK[i];
+    }
+#pragma unroll
+    for (int i = 0; i < n; i++) sP[g * n + i] = P[i];         // [mode][direction]
+
+    // ---- particular solutions in the scaled variables (u^ = D u) ------------------------
+    // beam (UPBEAM, disort.f:4130, spectral form): with c_j = (P^T r)_j / (1/mu0^2 - k_j^2),
+    //   d^ = Po^-1 (P c),  s^ = mu0 (b_d - P c),  z^up = (s^ + d^)/2, z^dn = (s^ - d^)/2
+    // thermal (UPISOT, disort.f:4247): p+-(tau) = D B(tau) +- b1 q^, q^ = Po^-1 D 1
+    double zup = 0.0, zdn = 0.0;
+    const bool beam = fbeam > 0.0;
+    double tg = 0.0, bdg = 0.0;
+    if (beam) {
+        const double fac = fbeam * (1.0 / (4. * kPiRef));
+        const double rmu0 = fast_rcp(umu0);
+        double be = 0.0, bo = 0.0;
+#pragma unroll
+        for (int l = 0; l < N; l++) {
+            const double t = sgl[l] * cylm[l * n + g] * y0[l];
+            if (l & 1) bo += t; else be += t;
+        }
+        const double bs = 2.0 * fac * sqg * be;
+        bdg = 2.0 * fac * sqg * bo;
+        sv[g] = bdg;
+        __syncwarp();
+        double t1 = 0.0;                                    // (K^T b_d)_g
+#pragma unroll
+        for (int k = 0; k < n; k++) t1 = fma(sK[k * n + g], sv[k], t1);
+        sv[n + g] = t1;
+        __syncwarp();
+        double t2 = 0.0;                                    // (K K^T b_d)_g
+#pragma unroll
+        for (int k = 0; k < n; k++) t2 = fma(sK[g * n + k], sv[n + k], t2);
+        sv[2 * n + g] = bs * rmu0 - t2;                     // r_g
+        __syncwarp();
+        double cj = 0.0;
+#pragma unroll
+        for (int i = 0; i < n; i++) cj = fma(P[i], sv[2 * n + i], cj);
+        cj = cj * fast_rcp(rmu0 * rmu0 - s2);
+        sv[3 * n + g] = cj;
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < n; j++) tg = fma(sP[j * n + g], sv[3 * n + j], tg);     // (P c)_g
+        sv[g] = tg;
+    } else {
+        __syncwarp();
+    }
+    sv[n + g] = cmu[g] * csq[g];                            // D_g
+    __syncwarp();
+    // Po^-1 [P c | D 1]: every lane runs both triangular solves (L y = b, L^T z = y)
+    double zq[n];                                            // q^ (all entries, uniform in the group)
+    {
+        double y1[n], y2[n], z1[n];
+#pragma unroll
+        for (int i = 0; i < n; i++) {
+            double a1 = sv[i], a2 = sv[n + i];
+#pragma unroll
+            for (int k = 0; k < i; k++) {
+                const double lik = sL[i * n + k];
+                a1 = fma(-lik, y1[k], a1);
+                a2 = fma(-lik, y2[k], a2);
+            }
+            y1[i] = a1 * rL[i]; y2[i] = a2 * rL[i];
+        }
+        double dg = 0.0;
+#pragma unroll
+        for (int i = n - 1; i >= 0; i--) {
+            double a1 = y1[i], a2 = y2[i];
+#pragma unroll
+            for (int k = i + 1; k < n; k++) {
+                const double lki = sL[k * n + i];
+                a1 = fma(-lki, z1[k], a1);
+                a2 = fma(-lki, zq[k], a2);
+            }
+            z1[i] = a1 * rL[i]; zq[i] = a2 * rL[i];
+            if (i == g) dg = z1[i];
+        }
+        if (beam) {
+            const double sg = umu0 * (bdg - tg);
+            zup = 0.5 * (sg + dg);
+            zdn = 0.5 * (sg - dg);
+        }
+    }
+
+    // ---- B+- = P^T P + diag(k tanh(kh) | k coth(kh)), row g (mode g) ---------------------
+    double bp[n], bm[n];
+#pragma unroll
+    for (int j = 0; j < n; j++) {
+        double acc = 0.0;
+#pragma unroll
+        for (int i = 0; i < n; i++) acc = fma(P[i], sP[j * n + i], acc);
+        bp[j] = acc; bm[j] = acc;
+    }
+    {
+        const double x = expm1(-kk * dtaucp);               // e^{-2kh} - 1
+        const double th = -x / (2.0 + x);                   // tanh(kh)
+        const double lam_p = kk * th;
+        const double lam_m = (th > 1.0e-280) ? kk / th : 1.0e100;
+#pragma unroll
+        for (int j = 0; j < n; j++)
+            if (j == g) { bp[j] += lam_p; bm[j] += lam_m; }
+    }
+    // in-place Gauss-Jordan inversion of both SPD matrices (no pivoting), row per lane
+#pragma unroll
+    for (int j = 0; j < n; j++) {
+        double pr[n], qr[n];
+#pragma unroll
+        for (int c = 0; c < n; c++) { pr[c] = shfl_d(bp[c], j, n); qr[c] = shfl_d(bm[c], j, n); }
+        const double rp = fast_rcp(pr[j]), rq = fast_rcp(qr[j]);
+        if (!(pr[j] > 0.0) || !(qr[j] > 0.0)) bad = 1;
+        const double mp = bp[j] * rp, mq = bm[j] * rq;
+        if (g == j) {
+#pragma unroll
+            for (int c = 0; c < n; c++) {
+                bp[c] = (c == j) ? rp : pr[c] * rp;
+                bm[c] = (c == j) ? rq : qr[c] * rq;
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < n; c++) {
+                bp[c] = (c == j) ? -mp : fma(-mp, pr[c], bp[c]);
+                bm[c] = (c == j) ? -mq : fma(-mq, qr[c], bm[c]);
+            }
+        }
+    }
+    // U+- = B+-^-1 P^T (row g), stored over K and X
+    {
+        double up[n], um[n];
+#pragma unroll
+        for (int b = 0; b < n; b++) { up[b] = 0.0; um[b] = 0.0; }
+#pragma unroll
+        for (int j = 0; j < n; j++) {
+#pragma unroll
+            for (int b = 0; b < n; b++) {
+                const double pj = sP[j * n + b];
+                up[b] = fma(bp[j], pj, up[b]);
+                um[b] = fma(bm[j], pj, um[b]);
+            }
+        }
+        __syncwarp();           // everyone is done reading K
+#pragma unroll
+        for (int b = 0; b < n; b++) { sK[g * n + b] = up[b]; sX[g * n + b] = um[b]; }
+    }
+    sv[g] = zup; sv[n + g] = zdn;
+    __syncwarp();
+    // M+- = P U+- (row a = g): R = -I + M+ + M-, T = M+ - M-
+    double R[n], T[n], mm[n];
+    {
+        double mp[n];
+#pragma unroll
+        for (int b = 0; b < n; b++) { mp[b] = 0.0; mm[b] = 0.0; }
+#pragma unroll
+        for (int j = 0; j < n; j++) {
+            const double pa = sP[j * n + g];
+#pragma unroll
+            for (int b = 0; b < n; b++) {
+                mp[b] = fma(pa, sK[j * n + b], mp[b]);
+                mm[b] = fma(pa, sX[j * n + b], mm[b]);
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < n; b++) {
+            R[b] = mp[b] + mm[b] - ((b == g) ? 1.0 : 0.0);
+            T[b] = mp[b] - mm[b];
+        }
+    }
+    // sources: s_up = p+_top - R p-_top - T p+_bot,  s_dn = p-_bot - T p-_top - R p+_bot
+    double s_up = 0.0, s_dn = 0.0;
+    if (beam) {
+        double Rzd = 0.0, Tzu = 0.0, Tzd = 0.0, Rzu = 0.0;
+#pragma unroll
+        for (int b = 0; b < n; b++) {
+            const double zu = sv[b], zd = sv[n + b];
+            Rzd = fma(R[b], zd, Rzd); Tzu = fma(T[b], zu, Tzu);
+            Tzd = fma(T[b], zd, Tzd); Rzu = fma(R[b], zu, Rzu);
+        }
+        const double et = ebeam[lc], eb = ebeam[lc + 1];
+        s_up = et * (zup - Rzd) - eb * Tzu;
+        s_dn = eb * (zdn - Rzu) - et * Tzd;
+    }
+    if (plank) {
+        // the b1 q^ terms of the four boundary values combine to b1 (I + R - T) q^ = 2 b1 M- q^,
+        // finite for dtau' -> 0 (b1 = dB / dtau' grows, M- ~ h shrinks)
+        double b1 = 0.0;
+        if (dtaucp > 1.0e-200) b1 = (pk[lc + 1] - pk[lc]) * fast_rcp(dtaucp);
+        else if (dtaucp > 0.0) b1 = (pk[lc + 1] - pk[lc]) / dtaucp;
+        double RD = 0.0, TD = 0.0, e = 0.0;
+#pragma unroll
+        for (int b = 0; b < n; b++) {
+            const double Db = cmu[b] * csq[b];
+            RD = fma(R[b], Db, RD); TD = fma(T[b], Db, TD);
+            e = fma(mm[b], zq[b], e);
+        }
+        e *= 2.0 * b1;
+        const double Dg = cmu[g] * csq[g];
+        s_up += (Dg - RD) * pk[lc] - TD * pk[lc + 1] + e;
+        s_dn += (Dg - RD) * pk[lc + 1] - TD * pk[lc] - e;
+    }
+    if (active) {
+#pragma unroll
+        for (int b = 0; b < n; b += 2) {
+            reinterpret_cast<double2 *>(rec + AL::r_R + g * n)[b / 2] = make_double2(R[b], R[b + 1]);
+            reinterpret_cast<double2 *>(rec + AL::r_T + g * n)[b / 2] = make_double2(T[b], T[b + 1]);
+        }
+        rec[AL::r_su + g] = s_up;
+        rec[AL::r_sd + g] = s_dn;
+    }
+    __syncwarp();
+    return (bad && active) ? SBD_BIN_EIG_FAIL : 0;
+}
+
+// WARPS warps per CTA, 16 warps per SM; the warps of a CTA move through the phases together
+// (one instruction stream in the I-cache at a time, see sbd_fast.cu).
+template <int n, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 16 / WARPS)
+disort_adding_kernel(const LaunchArgs a)
+{
+    using AL = AddLayout<n>;
+    constexpr int N = 2 * n, TASKS = 32 / n, CG = AL::CG, CW = AL::CW;
+    const int L = a.d.nlyr;
+    const int NT = L + 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+    const int ldp = a.d.nmom + 1;
+    extern __shared__ __align__(16) double smem_add[];
+    double *cmu = smem_add, *cwt = cmu + n, *csq = cwt + n, *cd = csq + n;
+    double *cylm = cd + n + 2;          // cylm[-2] = sum(w mu), cylm[-1] = sum(w)
+    double *wsm = smem_add + AL::cta + (size_t)warp * AL::warp_doubles(L);
+    double *y0 = wsm;
+    double *work = y0 + N;
+    double *taucpr = work + AL::work, *tauc = taucpr + (L + 1);
+    double *ebeam = tauc + (L + 1), *edir = ebeam + (L + 1);
+    double *pk = edir + (L + 1);
+    double *lw = pk + (L + 3);
+    int *layru = (int *)(lw + 3 * L);
+
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        double mu = a.quad[i], wt = a.quad[n + i];
+        cmu[i] = mu; cwt[i] = wt; csq[i] = sqrt(wt / mu); cd[i] = sqrt(wt * mu);
+    }
+    if (threadIdx.x == 0) {
+        double W = 0.0, SW = 0.0;
+        for (int i = 0; i < n; i++) { W += a.quad[n + i] * a.quad[i]; SW += a.quad[n + i]; }
+        cylm[-2] = W; cylm[-1] = SW;
+    }
+    for (int e = threadIdx.x; e < N * n; e += blockDim.x) cylm[e] = a.ylmc[e];
+    __syncthreads();
+    const double Wq = cylm[-2], SWq = cylm[-1];
+
+    const int slot = blockIdx.x * warps + warp;
+    double *recs = a.scratch + (size_t)slot * a.slot_stride;      // [L][rec]
+    const int g = lane % n, task = lane / n;
+    const int nbins_all = a.nbins_dev ? *a.nbins_dev : a.d.nbins;
+    double *tsm = work + (size_t)task * AL::task;
+    const unsigned jpart = add_jacobi_partners<n>(g);
+    // phase-2 tiling: row i2, column group p2 (lanes beyond n*CG shadow the last row)
+    const bool act2 = lane < n * CG;
+    const int i2 = act2 ? lane / CG : n - 1, p2 = lane % CG, c0 = p2 * CW;
+    // phase-2 shared memory
+    double *sRb = work, *ssb = sRb + n * n, *sY = ssb + n, *sy = sY + n * n, *sW = sy + n, *sw = sW + n * n;
+    double *rbuf = sw + n;
+
+    for (;;) {
+        int bin = 0;
+        if (lane == 0) bin = atomicAdd(a.work_counter, 1);
+        bin = __shfl_sync(FULLMASK, bin, 0);
+        const bool have = bin < nbins_all;
+        if (!__syncthreads_or(have)) break;
+#ifdef SBD_PHASE_TIMING
+        long long tphase = clock64();
+#endif
+        const int src = !have ? 0 : (a.binmap ? a.binmap[bin] : bin);
+        const sbd_bin bp = a.bins[src];
+        const double *dtauc = a.dtauc + (size_t)src * L;
+        const double *ssalb = a.ssalb + (size_t)src * L;
+        const double *pmom = a.pmom + (size_t)src * L * ldp;
+        const double fbeam = bp.fbeam, umu0 = bp.umu0, albedo = bp.albedo;
+        const bool plank = bp.plank != 0;
+        double *o_rfldir = (a.rfldir && have) ? a.rfldir + (size_t)bin * NT : nullptr;
+        double *o_rfldn = (a.rfldn && have) ? a.rfldn + (size_t)bin * NT : nullptr;
+        double *o_flup = (a.flup && have) ? a.flup + (size_t)bin * NT : nullptr;
+        double *o_dfdt = (a.dfdt && have) ? a.dfdt + (size_t)bin * NT : nullptr;
+        double *o_uavg = (a.uavg && have) ? a.uavg + (size_t)bin * NT : nullptr;
+
+        int status = have ? 0 : -1;
+        {   // CHEKIN subset (disort.f:4920-5155)
+            int badl = 0;
+            for (int lc = lane; lc < L; lc += 32) {
+                double s = ssalb[lc];
+                if (!(s >= 0.0 && s <= 1.0)) badl = 1;
+                if (!(fabs(dtauc[lc]) <= 1.79e308)) badl = 1;
+                for (int k = 1; k <= a.d.nmom; k++) {
+                    double pm = pmom[(size_t)lc * ldp + k];
+                    if (!(pm >= -1.0 && pm <= 1.0)) badl = 1;
+                }
+            }
+            if (fbeam < 0.0 || (fbeam > 0.0 && !(umu0 > 0.0 && umu0 <= 1.0))) badl = 1;
+            if (!(albedo >= 0.0 && albedo <= 1.0) || bp.fisot < 0.0) badl = 1;
+            if (plank && (bp.wvnmlo < 0.0 || bp.wvnmhi <= bp.wvnmlo || bp.temis < 0.0 ||
+                          bp.temis > 1.0 || bp.btemp < 0.0 || bp.ttemp < 0.0)) badl = 1;
+            if (plank && (!a.temper || bp.col < 0 || bp.col >= a.d.ncol)) badl = 1;
+            if (__any_sync(FULLMASK, badl)) status = SBD_BIN_BAD_INPUT;
+            int clash = 0;
+            if (fbeam > 0.0 && lane < n && fabs(umu0 - cmu[lane]) / umu0 < 1.e-4) clash = 1;
+            if (!status && __any_sync(FULLMASK, clash)) status = SBD_BIN_ANGLE_CLASH;
+        }
+        int ncut = L, lyrcut = 0, monotone = 1;
+        // SETDIS prologue (disort.f:2546-2605), accumulated in the reference's order by lane 0
+        for (int lc = lane; lc < L; lc += 32) {
+            double s = ssalb[lc];
+            if (s == 1.0) s = 1.0 - kDither;
+            const double dtr = dtauc[lc];
+            const double dt = dtr < 0.0 ? 0.0 : dtr;
+            const double f = pmom[(size_t)lc * ldp + N];
+            lw[lc] = dtr; lw[L + lc] = (1. - s) * dt; lw[2 * L + lc] = (1. - f * s) * dt;
+        }
+        __syncwarp();
+        if (lane == 0) {
+            double tc = 0.0, tp = 0.0, abstau = 0.0;
+            tauc[0] = 0.0; taucpr[0] = 0.0;
+            for (int lc = 0; lc < L; lc++) {
+                if (lw[lc] < 0.0) monotone = 0;
+                tc += lw[lc];
+                if (abstau < 10.0) ncut = lc + 1;
+                abstau += lw[L + lc];
+                tp += lw[2 * L + lc];
+                tauc[lc + 1] = tc; taucpr[lc + 1] = tp;
+            }
+            lyrcut = (abstau >= 10.0 && !plank && L > 1);
+            if (!lyrcut) ncut = L;
+        }
+        ncut = __shfl_sync(FULLMASK, ncut, 0);
+        lyrcut = __shfl_sync(FULLMASK, lyrcut, 0);
+        monotone = __shfl_sync(FULLMASK, monotone, 0);
+        __syncwarp();
+        // Negative optical depths (legal upstream, taugas.f:7485) make TAUC non-monotone
+        // (disort.f:487 accumulates before CHEKIN clips), and the reference then evaluates
+        // levels INSIDE earlier layers: such bins go to the elimination kernel (sbd_fast.cu),
+        // which keeps the layer solutions.
+        if (!monotone && !status && have) {
+            if (lane == 0) {
+                const int k = atomicAdd(a.redo_count, 1);
+                a.redo_list[k] = bin;
+            }
+            status = -100;          // parked: no phases, no status write
+        }
+        for (int lev = lane; lev <= L; lev += 32) {
+            ebeam[lev] = fbeam > 0.0 ? exp(-taucpr[lev] / umu0) : 0.0;
+            edir[lev] = fbeam > 0.0 ? exp(-tauc[lev] / umu0) : 0.0;
+        }
+        // the level belongs to the first layer whose interval contains it (disort.f:2610-2625)
+        for (int lu = lane; lu < NT; lu += 32) {
+            const double ut = tauc[lu];
+            int lc;
+            if (lu >= 1 && tauc[lu - 1] < ut) lc = lu;
+            else {
+                for (lc = 1; lc <= L; lc++)
+                    if (ut >= tauc[lc - 1] && ut <= tauc[lc]) break;
+                if (lc > L) lc = L;
+            }
+            layru[lu] = lc;
+        }
+        double tplank = 0.0, bplank = 0.0;
+        if (plank && !status) {
+            const double *tp = a.temper + (size_t)bp.col * (L + 1);
+            for (int lev = lane; lev <= L + 2; lev += 32) {
+                const double t = lev <= L ? tp[lev] : (lev == L + 1 ? bp.ttemp : bp.btemp);
+                pk[lev] = plkavg_dev(bp.wvnmlo, bp.wvnmhi, t);
+            }
+            __syncwarp();
+            tplank = bp.temis * pk[L + 1];
+            bplank = pk[L + 2];
+        }
+        if (lane == 0 && fbeam > 0.0) {   // Y_l^0(-mu0), LEPOLY m = 0
+            double x = -umu0;
+            y0[0] = 1.0; y0[1] = x;
+            double pm2 = 1.0, pm1 = x;
+#pragma unroll
+            for (int l = 2; l < N; l++) {
+                const double p = ((2 * l - 1) * x * pm1 - (l - 1) * pm2) * (1.0 / l);
+                y0[l] = p; pm2 = pm1; pm1 = p;
+            }
+        }
+        if (status != -100)
+            for (int lu = lane; lu < NT; lu += 32) {
+                if (o_rfldir) o_rfldir[lu] = 0.0;
+                if (o_rfldn) o_rfldn[lu] = 0.0;
+                if (o_flup) o_flup[lu] = 0.0;
+                if (o_dfdt) o_dfdt[lu] = 0.0;
+                if (o_uavg) o_uavg[lu] = 0.0;
+            }
+        __syncwarp();
+        ADD_TICK(0);
+
+        // ===================== phase 1 =====================================
+        if (!status) {
+            for (int lc0 = 0; lc0 < ncut; lc0 += TASKS) {
+                int lc = lc0 + task;
+                const bool active = lc < ncut;
+                if (!active) lc = ncut - 1;
+                int st = phase1_adding<n>(dtauc, ssalb, pmom, ldp, lc, active, fbeam, umu0, plank,
+                                          cmu, csq, cd, cylm, y0, ebeam, pk, tsm,
+                                          recs + (size_t)lc * AL::rec, g, jpart);
+                if (__any_sync(FULLMASK, st != 0)) { status = SBD_BIN_EIG_FAIL; break; }
+            }
+        }
+        __syncwarp();
+        __threadfence_block();
+        __syncthreads();
+        ADD_TICK(1);
+
+        // ===================== phase 2: bottom-up adding ===================
+        // functionals of the bottom interface (level ncut), kept for phase 3 by lanes n, n+1
+        double fnB[n], fnB0 = 0.0;
+#pragma unroll
+        for (int c = 0; c < n; c++) fnB[c] = 0.0;
+        if (!status) {
+            // bottom boundary (disort.f:2919-2990, :3552-3578): Lambertian, or no upwelling
+            // radiation at the truncation level
+            const double refl = lyrcut ? 0.0 : 2.0 * albedo;
+            const double emis = lyrcut ? 0.0 : albedo * umu0 * fbeam / kPiRef * ebeam[ncut] + (1.0 - albedo) * bplank;
+            for (int e = lane; e < n * n; e += 32) sRb[e] = refl * cd[e / n] * cd[e % n];
+            if (lane < n) ssb[lane] = cd[lane] * emis;
+            if (lane == n || lane == n + 1) {
+                const double s = (lane == n) ? Wq : SWq;     // D^T D, c^T D
+#pragma unroll
+                for (int c = 0; c < n; c++) fnB[c] = refl * s * cd[c];
+                fnB0 = s * emis;
+            }
+            warp_copy_async(rbuf, recs + (size_t)(ncut - 1) * AL::rec, AL::rec, lane);
+            cp_async_commit();
+            __syncwarp();
+            for (int lc = ncut - 1; lc >= 0; lc--) {
+                const int buf = (ncut - 1 - lc) & 1;
+                if (lc > 0) {
+                    warp_copy_async(rbuf + (buf ^ 1) * AL::rec, recs + (size_t)(lc - 1) * AL::rec, AL::rec, lane);
+                    cp_async_commit();
+                    cp_async_wait_one();
+                } else {
+                    cp_async_wait_all();
+                }
+                __syncwarp();
+                const double *rc = rbuf + buf * AL::rec;
+                const double *Rr = rc + AL::r_R + i2 * n, *Tr = rc + AL::r_T + i2 * n;
+                // ---- B = I - R Rb (my CW columns of row i2), t = T, v = (R sb + s_dn)_i2 ----
+                double b[CW], t[CW], v;
+                {
+                    double r[n];
+#pragma unroll
+                    for (int k = 0; k < n; k++) r[k] = Rr[k];
+#pragma unroll
+                    for (int s = 0; s < CW; s++) b[s] = (c0 + s == i2) ? 1.0 : 0.0;
+                    v = rc[AL::r_sd + i2];
+#pragma unroll
+                    for (int k = 0; k < n; k++) {
+#pragma unroll
+                        for (int s = 0; s < CW; s++) b[s] = fma(-r[k], sRb[k * n + c0 + s], b[s]);
+                        v = fma(r[k], ssb[k], v);
+                    }
+#pragma unroll
+                    for (int s = 0; s < CW; s++) t[s] = Tr[c0 + s];
+                }
+                // ---- Gauss-Jordan with partial pivoting on [B | T | v], rows in registers ----
+                unsigned used = 0;
+                int myj = 0, sing = 0;
+#pragma unroll
+                for (int j = 0; j < n; j++) {
+                    const int pj = j / CW, sj = j % CW;
+                    const double colv = __shfl_sync(FULLMASK, b[sj], (lane & ~(CG - 1)) | pj);
+                    const int key = (act2 && !((used >> i2) & 1u))
+                                        ? ((__double2hiint(colv) & 0x7ffffff8) | (7 - i2)) : -1;
+                    const int mx = __reduce_max_sync(FULLMASK, key);
+                    if ((mx >> 3) <= 0) sing = 1;
+                    const int ip = 7 - (mx & 7);
+                    used |= 1u << ip;
+                    const int srcl = ip * CG + p2;
+                    const double rp = fast_rcp(__shfl_sync(FULLMASK, colv, ip * CG));
+                    double pb[CW], pt[CW];
+#pragma unroll
+                    for (int s = 0; s < CW; s++) {
+                        pb[s] = __shfl_sync(FULLMASK, b[s], srcl) * rp;
+                        pt[s] = __shfl_sync(FULLMASK, t[s], srcl) * rp;
+                    }
+                    const double pv = __shfl_sync(FULLMASK, v, srcl) * rp;
+                    if (i2 == ip) {
+#pragma unroll
+                        for (int s = 0; s < CW; s++) { b[s] = pb[s]; t[s] = pt[s]; }
+                        v = pv;
+                        myj = j;
+                    } else {
+#pragma unroll
+                        for (int s = 0; s < CW; s++) { b[s] = fma(-colv, pb[s], b[s]); t[s] = fma(-colv, pt[s], t[s]); }
+                        v = fma(-colv, pv, v);
+                    }
+                }
+                if (sing) { status = SBD_BIN_SINGULAR; break; }
+                // row i2 now holds row myj of Y = (I - R Rb)^-1 T and of y
+                double *orec = recs + (size_t)lc * AL::rec;      // (the phase-1 record is in shared memory)
+                if (act2) {
+#pragma unroll
+                    for (int s = 0; s < CW; s++) { sY[myj * n + c0 + s] = t[s]; orec[AL::o_Y + myj * n + c0 + s] = t[s]; }
+                    if (p2 == 0) { sy[myj] = v; orec[AL::o_y + myj] = v; }
+                }
+                __syncwarp();
+                // ---- W = Rb [Y | y] + [0 | sb] ----
+                {
+                    double rb[n], w[CW], wv = ssb[i2];
+#pragma unroll
+                    for (int k = 0; k < n; k++) rb[k] = sRb[i2 * n + k];
+#pragma unroll
+                    for (int s = 0; s < CW; s++) w[s] = 0.0;
+#pragma unroll
+                    for (int k = 0; k < n; k++) {
+#pragma unroll
+                        for (int s = 0; s < CW; s++) w[s] = fma(rb[k], sY[k * n + c0 + s], w[s]);
+                        wv = fma(rb[k], sy[k], wv);
+                    }
+                    if (act2) {
+#pragma unroll
+                        for (int s = 0; s < CW; s++) sW[i2 * n + c0 + s] = w[s];
+                        if (p2 == 0) sw[i2] = wv;
+                    }
+                }
+                __syncwarp();
+                // ---- [Rb | sb] <- [R | s_up] + T W ----
+                {
+                    double tr[n], nr[CW], ns = rc[AL::r_su + i2];
+#pragma unroll
+                    for (int k = 0; k < n; k++) tr[k] = Tr[k];
+#pragma unroll
+                    for (int s = 0; s < CW; s++) nr[s] = Rr[c0 + s];
+#pragma unroll
+                    for (int k = 0; k < n; k++) {
+#pragma unroll
+                        for (int s = 0; s < CW; s++) nr[s] = fma(tr[k], sW[k * n + c0 + s], nr[s]);
+                        ns = fma(tr[k], sw[k], ns);
+                    }
+                    if (act2) {
+#pragma unroll
+                        for (int s = 0; s < CW; s++) sRb[i2 * n + c0 + s] = nr[s];
+                        if (p2 == 0) ssb[i2] = ns;
+                    }
+                }
+                __syncwarp();
+                // ---- flux functionals of interface lc: D^T Rb, c^T Rb, D^T sb, c^T sb ----
+                if (lane < 2 * n) {
+                    const double *wv = (lane < n) ? cd : csq;
+                    const int c = lane % n;
+                    double acc = 0.0;
+#pragma unroll
+                    for (int k = 0; k < n; k++) acc = fma(wv[k], sRb[k * n + c], acc);
+                    orec[(lane < n ? AL::o_fu : AL::o_cu) + c] = acc;
+                } else if (lane < 2 * n + 2) {
+                    const double *wv = (lane == 2 * n) ? cd : csq;
+                    double acc = 0.0;
+#pragma unroll
+                    for (int k = 0; k < n; k++) acc = fma(wv[k], ssb[k], acc);
+                    orec[AL::o_f0 + (lane - 2 * n)] = acc;
+                }
+            }
+        }
+        cp_async_wait_all();
+        __syncwarp();
+        __threadfence_block();
+        __syncthreads();
+        ADD_TICK(2);
+
+        // ===================== phase 3: top-down intensities + fluxes ======
+        // lane r < n: row r of Y (new downward intensity r); lanes n .. n+3: the four flux
+        // functionals (D^T u+, c^T u+, D^T u-, c^T u-); every lane forms  s0 + vv . d
+        if (!status) {
+            double d[n], vv[n], s0 = 0.0;
+            const int role = lane - n;
+#pragma unroll
+            for (int c = 0; c < n; c++) d[c] = cd[c] * (bp.fisot + tplank);
+            auto load_rec = [&](int lev) {
+                // record `lev` = layer lev+1 (top interface = level lev); lev == ncut: the boundary
+                if (lev < ncut) {
+                    const double *orec = recs + (size_t)lev * AL::rec;
+                    if (lane < n) {
+#pragma unroll
+                        for (int c = 0; c < n; c += 2) {
+                            const double2 q = reinterpret_cast<const double2 *>(orec + AL::o_Y + lane * n)[c / 2];
+                            vv[c] = q.x; vv[c + 1] = q.y;
+                        }
+                        s0 = orec[AL::o_y + lane];
+                    } else if (role < 2) {
+#pragma unroll
+                        for (int c = 0; c < n; c += 2) {
+                            const double2 q = reinterpret_cast<const double2 *>(orec + (role == 0 ? AL::o_fu : AL::o_cu))[c / 2];
+                            vv[c] = q.x; vv[c + 1] = q.y;
+                        }
+                        s0 = orec[AL::o_f0 + role];
+                    }
+                } else if (role == 0 || role == 1) {
+#pragma unroll
+                    for (int c = 0; c < n; c++) vv[c] = fnB[c];
+                    s0 = fnB0;
+                }
+            };
+#pragma unroll
+            for (int c = 0; c < n; c++) vv[c] = (role == 2) ? cd[c] : ((role == 3) ? csq[c] : 0.0);
+            load_rec(0);
+            for (int lev = 0; lev <= ncut; lev++) {
+                double x = s0;
+#pragma unroll
+                for (int c = 0; c < n; c++) x = fma(vv[c], d[c], x);
+                if (lev < ncut) load_rec(lev + 1);           // next record while this level finishes
+                const double xcu = __shfl_sync(FULLMASK, x, n + 1);
+                const double xdn = __shfl_sync(FULLMASK, x, n + 2);
+                const double xcd = __shfl_sync(FULLMASK, x, n + 3);
+                if (lane == n) {
+                    const double pi = kPiRef;
+                    const double fact = ebeam[lev];
+                    const double dirint = fbeam * fact;
+                    const double fldir = umu0 * (fbeam * fact);
+                    const double rfldir = umu0 * fbeam * edir[lev];
+                    const double flup = 2. * pi * x, fldn = 2. * pi * xdn;
+                    const double fdntot = fldn + fldir;
+                    constexpr double inv4pi = 1.0 / (4. * kPiRef);
+                    const double uavg = (2. * pi * (xcu + xcd) + dirint) * inv4pi;
+                    // the layer the level belongs to (its single-scattering albedo and Planck value)
+                    const int lyr = layru[lev] - 1;
+                    double ssl = ssalb[lyr];
+                    if (ssl == 1.0) ssl = 1.0 - kDither;
+                    double plsorc = 0.0;
+                    if (plank) plsorc = (lev == 0) ? pk[0] : ((taucpr[lyr + 1] - taucpr[lyr] > 0.0) ? pk[lyr + 1] : pk[lyr]);
+                    if (o_rfldir) o_rfldir[lev] = rfldir;
+                    if (o_rfldn) o_rfldn[lev] = fdntot - rfldir;
+                    if (o_flup) o_flup[lev] = flup;
+                    if (o_uavg) o_uavg[lev] = uavg;
+                    if (o_dfdt) o_dfdt[lev] = (1.0 - ssl) * 4. * pi * (uavg - plsorc);
+                }
+                // the new downward intensities to everyone
+#pragma unroll
+                for (int c = 0; c < n; c++) d[c] = __shfl_sync(FULLMASK, x, c);
+            }
+        }
+        if (lane == 0 && have && status != -100) a.status[bin] = status;
+        __syncwarp();
+#ifdef SBD_PHASE_TIMING
+        __syncthreads();
+        ADD_TICK(3);
+#endif
+    }
+}
+
+#ifdef SBD_PHASE_TIMING
+extern "C" void sbd_debug_add_ticks(unsigned long long *out, int reset)
+{
+    cudaMemcpyFromSymbol(out, g_add_ticks, sizeof(g_add_ticks));
+    if (reset) { unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0}; cudaMemcpyToSymbol(g_add_ticks, z, sizeof z); }
+}
+#endif
+
+// ---- host-side launch helpers ---------------------------------------------
+bool adding_supported(int N) { return N == 4 || N == 8 || N == 16; }
+
+size_t adding_slot_doubles(int N, int L)
+{
+    switch (N) {
+    case 4: return AddLayout<2>::slot_doubles(L);
+    case 8: return AddLayout<4>::slot_doubles(L);
+    case 16: return AddLayout<8>::slot_doubles(L);
+    }
+    return 0;
+}
+
+size_t adding_smem_bytes(int N, int L, int warps)
+{
+    switch (N) {
+    case 4: return 8 * (AddLayout<2>::cta + (size_t)warps * AddLayout<2>::warp_doubles(L));
+    case 8: return 8 * (AddLayout<4>::cta + (size_t)warps * AddLayout<4>::warp_doubles(L));
+    case 16: return 8 * (AddLayout<8>::cta + (size_t)warps * AddLayout<8>::warp_doubles(L));
+    }
+    return 0;
+}
+
+template <int n, int WARPS>
+static cudaError_t launch_adding_k(const LaunchArgs &a, int grid, size_t smem, cudaStream_t st)
+{
+    cudaError_t e = cudaFuncSetAttribute(disort_adding_kernel<n, WARPS>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    disort_adding_kernel<n, WARPS><<<grid, WARPS * 32, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
+template <int n>
+static cudaError_t launch_adding_t(const LaunchArgs &a, int warps, int grid, cudaStream_t st)
+{
+    const size_t smem = 8 * (AddLayout<n>::cta + (size_t)warps * AddLayout<n>::warp_doubles(a.d.nlyr));
+    switch (warps) {
+    case 4: return launch_adding_k<n, 4>(a, grid, smem, st);
+    case 8: return launch_adding_k<n, 8>(a, grid, smem, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_adding(const LaunchArgs &a, int warps, int grid, cudaStream_t st)
+{
+    switch (a.d.nstr) {
+    case 4: return launch_adding_t<2>(a, warps, grid, st);
+    case 8: return launch_adding_t<4>(a, warps, grid, st);
+    case 16: return launch_adding_t<8>(a, warps, grid, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace sbd

@@ -159,7 +159,7 @@ extern "C" void sbd_destroy(sbd_handle *h)
     cudaStreamSynchronize(h->stream);
     for (auto &kv : h->tables) { cudaFree(kv.second.quad); cudaFree(kv.second.ylmc); }
     cudaStreamSynchronize(h->stream2);
-    SbdDevBuf *bufs[] = { &h->scratch, &h->counter, &h->scratch2, &h->counter2, &h->ylmu, &h->angles, &h->d_dtauc, &h->d_ssalb,
+    SbdDevBuf *bufs[] = { &h->redo, &h->redo2, &h->redo_scratch, &h->redo_scratch2, &h->scratch, &h->counter, &h->scratch2, &h->counter2, &h->ylmu, &h->angles, &h->d_dtauc, &h->d_ssalb,
                        &h->d_pmom, &h->d_bins, &h->d_temper, &h->d_utau, &h->d_out, &h->d_uu,
                        &h->d_status, &h->opt_tables, &h->opt_atm, &h->opt_misc, &h->opt_map, &h->opt_aero,
                        &h->d_uupack, &h->d_sel, &h->d_fluxpack };
@@ -275,6 +275,9 @@ extern "C" int sbd_disort_batch_device(sbd_handle *h, const sbd_dims *dims, cons
     size_t smem_limit = h->smem_optin ? h->smem_optin : 48 * 1024;
     // register kernel: NSTR 4/8/16; radiances at the layer boundaries (the mode SBDART uses)
     const bool fast = fast_supported(N) && (NU == 0 || dims->ntau == 0) && !getenv("SBD_FORCE_GENERIC");
+    // adding kernel: NSTR 4/8/16, fluxes at the layer boundaries (SBD_FORCE_ELIM: the elimination
+    // kernel instead -- a tuning / comparison knob, not API)
+    const bool adding = fast && adding_supported(N) && NU == 0 && dims->ntau == 0 && !getenv("SBD_FORCE_ELIM");
     // CTA-per-bin register kernel: NSTR 20/24/32, fluxes
     const bool wide = !fast && wide_supported(N) && NU == 0 && !getenv("SBD_FORCE_GENERIC") &&
                       wide_smem_bytes(N, L, NT) <= smem_limit;
@@ -294,7 +297,7 @@ extern "C" int sbd_disort_batch_device(sbd_handle *h, const sbd_dims *dims, cons
         warps = fast_warps();
         int cta_per_sm = 0;
         for (int wtry = warps; wtry >= 4; wtry /= 2) {
-            const size_t smem = fast_smem_bytes(N, L, NT, wtry, NU, dims->nphi);
+            const size_t smem = adding ? adding_smem_bytes(N, L, wtry) : fast_smem_bytes(N, L, NT, wtry, NU, dims->nphi);
             if (smem > smem_limit) continue;
             int c = (int)((smem_limit + 1024) / (smem + 1024));
             if (c > 16 / wtry) c = 16 / wtry;
@@ -302,7 +305,7 @@ extern "C" int sbd_disort_batch_device(sbd_handle *h, const sbd_dims *dims, cons
         }
         if (cta_per_sm == 0) return SBD_ERR_UNSUPPORTED;
         grid = h->sm_count * cta_per_sm;
-        slot = fast_slot_doubles(N, L, NU);
+        slot = adding ? adding_slot_doubles(N, L) : fast_slot_doubles(N, L, NU);
     } else {
         warps = generic_pick_warps(N, L, NT, smem_limit);
         if (warps == 0) return SBD_ERR_UNSUPPORTED;
@@ -361,9 +364,37 @@ extern "C" int sbd_disort_batch_device(sbd_handle *h, const sbd_dims *dims, cons
     if (scr.reserve(a.slot_stride * (size_t)a.nslots * 8) != cudaSuccess) return SBD_ERR_CUDA;
     a.scratch = (double *)scr.p;
     a.work_counter = (int *)ctr.p;
-    if (cudaMemsetAsync(a.work_counter, 0, sizeof(int), st) != cudaSuccess) return SBD_ERR_CUDA;
-    cudaError_t le = wide ? launch_wide(a, grid, st)
-                          : (fast ? launch_fast(a, warps, grid, st) : launch_generic(a, warps, grid, st));
+    if (cudaMemsetAsync(a.work_counter, 0, 4 * sizeof(int), st) != cudaSuccess) return SBD_ERR_CUDA;
+    cudaError_t le;
+    if (adding) {
+        // bins whose TAUC is not monotone (negative optical depths) are appended to a list and
+        // solved by the elimination kernel launched behind (normally the list stays empty and
+        // that launch ends at once)
+        SbdDevBuf &rl = h->scratch_set ? h->redo2 : h->redo;
+        SbdDevBuf &rs = h->scratch_set ? h->redo_scratch2 : h->redo_scratch;
+        if (rl.reserve((size_t)dims->nbins * sizeof(int)) != cudaSuccess) return SBD_ERR_CUDA;
+        a.redo_count = a.work_counter + 1;
+        a.redo_list = (int *)rl.p;
+        le = launch_adding(a, warps, grid, st);
+        if (le != cudaSuccess) return SBD_ERR_CUDA;
+        h->launches += 1;
+        LaunchArgs a2 = a;
+        int w2 = fast_warps();
+        if (fast_smem_bytes(N, L, NT, w2, 0, 0) > smem_limit) w2 = 4;
+        if (fast_smem_bytes(N, L, NT, w2, 0, 0) > smem_limit) return SBD_ERR_UNSUPPORTED;
+        int g2 = 16;
+        if (g2 > (dims->nbins + w2 - 1) / w2) g2 = (dims->nbins + w2 - 1) / w2;
+        a2.redo_consume = true;
+        a2.work_counter = a.work_counter + 2;
+        a2.slot_stride = fast_slot_doubles(N, L, 0);
+        a2.nslots = g2 * w2;
+        if (rs.reserve(a2.slot_stride * (size_t)a2.nslots * 8) != cudaSuccess) return SBD_ERR_CUDA;
+        a2.scratch = (double *)rs.p;
+        le = launch_fast(a2, w2, g2, st);
+    } else {
+        le = wide ? launch_wide(a, grid, st)
+                  : (fast ? launch_fast(a, warps, grid, st) : launch_generic(a, warps, grid, st));
+    }
     if (le != cudaSuccess) return SBD_ERR_CUDA;
     h->launches += 1;
     if (NU > 0 && h->corint) {         // INTCOR (disort.f:827-835): layer boundaries only

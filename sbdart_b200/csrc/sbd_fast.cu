@@ -821,7 +821,7 @@ disort_fast_kernel(const LaunchArgs a)
     double *dscr = ublk + (size_t)L * FL::ublk;           // RAD: [L][2][NU] downward source, transmission
     const int g = lane % n, task = lane / n;
     // the spectrum path keeps the bin count on the device (a.d.nbins is then an upper bound)
-    const int nbins_all = a.nbins_dev ? *a.nbins_dev : a.d.nbins;
+    const int nbins_all = a.redo_consume ? *a.redo_count : (a.nbins_dev ? *a.nbins_dev : a.d.nbins);
     double *tsm = tsm_base + (size_t)task * FL::task;
     const int rg = lane >> 2, cg = lane & 3;              // 2-D tiling of phase 2
     const unsigned jpart = jacobi_partners<n>(g);
@@ -845,6 +845,7 @@ disort_fast_kernel(const LaunchArgs a)
         const bool have = bin < nbins_all;
         if (SYNC) { if (!__syncthreads_or(have)) break; }
         else if (!have) break;
+        if (a.redo_consume && have) bin = a.redo_list[bin];      // bins handed over by the adding kernel
 #ifdef SBD_PHASE_TIMING
         long long tphase = clock64();
 #endif

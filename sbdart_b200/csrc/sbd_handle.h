@@ -44,6 +44,8 @@ struct sbd_handle {
     // run on alternating streams, so the next chunk's CTAs fill the SMs the previous
     // chunk's tail leaves idle
     SbdDevBuf scratch2, counter2;
+    // adding kernel: list of bins handed to the elimination kernel, and that kernel's scratch
+    SbdDevBuf redo, redo2, redo_scratch, redo_scratch2;
     cudaStream_t stream2 = nullptr;
     cudaEvent_t ev_misc = nullptr;
     int scratch_set = 0;

@@ -31,6 +31,11 @@ struct LaunchArgs {
     int *work_counter;    // dynamic bin scheduler
     const int32_t *binmap; // optional: bin b reads its inputs from slot binmap[b]
     const int32_t *nbins_dev; // optional: number of bins lives on the device (spectrum path)
+    // bins the adding kernel hands to the elimination kernel (non-monotone TAUC): the adding
+    // kernel appends, the elimination kernel launched behind it works through the list
+    int *redo_count;
+    int *redo_list;
+    bool redo_consume;        // this launch takes its bins from the list
     unsigned long long uu_mask[2]; // bit lu: intensities wanted at output level lu
     // layout of uu: [bin][nphi][uu_nt][numu]; output level lu lives in slot uu_slot[lu]
     // (-1: not wanted).  Full layout: uu_nt = NT, slot = level; packed: the wanted levels only.
@@ -79,6 +84,12 @@ int fast_warps();
 size_t fast_slot_doubles(int N, int L, int NU);
 size_t fast_smem_bytes(int N, int L, int NT, int warps, int NU, int NPHI);
 cudaError_t launch_fast(const LaunchArgs &a, int warps, int grid, cudaStream_t st);
+
+// adding kernel: NSTR in {4, 8, 16}, fluxes at the layer boundaries (sbd_adding.cu)
+bool adding_supported(int N);
+size_t adding_slot_doubles(int N, int L);
+size_t adding_smem_bytes(int N, int L, int warps);
+cudaError_t launch_adding(const LaunchArgs &a, int warps, int grid, cudaStream_t st);
 
 // one-CTA-per-bin register kernel for NSTR in {20, 24, 32}, fluxes (sbd_wide.cu)
 bool wide_supported(int N);
