@@ -33,7 +33,7 @@ enum {
     SBD_SUCCESS = 0,
     SBD_ERR_CUDA = -100,      /* no device / CUDA runtime failure            */
     SBD_ERR_ARG = -101,       /* bad dims or NULL pointer                    */
-    SBD_ERR_UNSUPPORTED = -102 /* IBCND=1, BRDF surface, USRTAU w/ radiances  */
+    SBD_ERR_UNSUPPORTED = -102 /* IBCND=1, USRTAU w/ radiances                 */
 };
 
 /* per-bin status written to status[B]; numbering follows the reference's
@@ -70,7 +70,8 @@ typedef struct sbd_bin {
     double umu0;    /* UMU0   */
     double phi0;    /* PHI0   (degrees)                                       */
     double fisot;   /* FISOT  */
-    double albedo;  /* ALBEDO (Lambertian)                                    */
+    double albedo;  /* ALBEDO (Lambertian); SBD_SURFACE(s) selects the BRDF
+                       surface s of sbd_set_surfaces (LAMBER = .FALSE.)       */
     double btemp;   /* BTEMP  */
     double ttemp;   /* TTEMP  */
     double temis;   /* TEMIS  */
@@ -320,6 +321,30 @@ void disort_(int *nlyr, double *dtauc, double *ssalb, int *corint, int *nmom,
              int *maxmom, double *rfldir, double *rfldn, double *flup,
              double *dfdt, double *uavg, double *uu, double *albmed,
              double *trnmed, size_t header_len);
+
+/*
+ * Non-Lambertian surfaces (LAMBER = .FALSE.; replaces SURFAC's calls of the host function
+ * BDREF, disort.f:3765-3907, spectra.f:249): the caller supplies SURFAC's tables,
+ *   bdr [nsurf][nmodes][n][n+1]   BDR(iq, 0:n) of azimuth mode m (column 0: incidence at UMU0)
+ *   bem [nsurf][n]                BEM(iq)
+ *   rmu [nsurf][nmodes][numu][n+1], emu [nsurf][numu]   RMU / EMU at the user angles (radiance
+ *                                 runs; NULL for flux runs),
+ * n = nstr/2, nmodes = 1 (fluxes) or nstr (all azimuth modes).  HOST arrays, copied to the
+ * device; they stay set until the next call (nsurf = 0 clears them).  A bin selects surface s
+ * with bins[b].albedo = SBD_SURFACE(s).  Flux runs with NSTR 4/8/16 and all radiance runs
+ * support it (the latter on the general kernel).
+ */
+#define SBD_SURFACE(s) (-(double)((s) + 1))
+int sbd_set_surfaces(sbd_handle *h, int32_t nsurf, int32_t nstr, int32_t nmodes, int32_t numu,
+                     const double *bdr, const double *bem, const double *rmu, const double *emu);
+
+/* LAMBER = .FALSE. through disort_(): the library calls the host program's BDREF
+ * (spectra.f:249: REAL(KR) FUNCTION BDREF(WVNMLO, WVNMHI, MUR, MUI, PHIR), kr = 8) -- the
+ * symbol `bdref_` of the executable when it is exported (link with -rdynamic), or the function
+ * handed over here. */
+void sbd_set_bdref_callback(double (*bdref)(const double *wvnmlo, const double *wvnmhi,
+                                            const double *mur, const double *mui,
+                                            const double *phir));
 
 /* status of the last disort_() call on this thread (SBD_BIN_* or SBD_ERR_*) */
 int sbd_disort_last_status(void);

@@ -652,7 +652,8 @@ typedef struct {
     double *kk, *ll, *zz, *zplk0, *zplk1; /* [L][N]                          */
     double *xr0, *xr1;                 /* [L]                                */
     double *zbeam, *z0u, *z1u;         /* [L][NU]                            */
-    double *bdr, *bem, *rmu, *emu;     /* Lambertian surface arrays          */
+    double *bdr, *bem, *rmu, *emu;     /* surface arrays (SURFAC)            */
+    int lamber;                        /* LAMBER                             */
     double *wk, *z0, *z1, *zj, *psi0, *psi1; /* [N+1] scratch                */
     double *cband, *b;                 /* band matrix and rhs                */
     int *ipvt;
@@ -920,7 +921,7 @@ static int setmtx_solve0(work_t *w, int mazim, double delm0, double fbeam,
     /* bottom boundary (:2919-2990); Lambertian BDR = albedo for m=0 */
     int nncol = ncol - N;
     jcol = 0;
-    const int noreflect = lyrcut || (delm0 == 0.0); /* LAMBER .AND. DELM0.EQ.0 */
+    const int noreflect = lyrcut || (w->lamber && delm0 == 0.0); /* disort.f:2929 */
     for (int iq = 1; iq <= n; iq++) {
         nncol++;
         int irow = nshift - jcol + N;
@@ -967,10 +968,17 @@ static int setmtx_solve0(work_t *w, int mazim, double delm0, double fbeam,
     const double *expbea = w->expbea, *taucpr = w->taucpr, *cwt = w->cwt,
                  *cmu = w->cmu;
     if (mazim > 0 && fbeam > 0.0) {
-        /* LAMBER is always true here */
+        /* azimuth-dependent case (disort.f:3436-3471) */
         for (int iq = 1; iq <= n; iq++) {
             B(iq) = -ZZ(n - iq, 0);
-            B(ncol - n + iq) = -ZZ(iq + n - 1, ncut - 1) * expbea[ncut];
+            if (lyrcut || w->lamber) {
+                B(ncol - n + iq) = -ZZ(iq + n - 1, ncut - 1) * expbea[ncut];
+            } else {
+                double sum = 0.;
+                for (int jq = 1; jq <= n; jq++)
+                    sum += cwt[jq - 1] * cmu[jq - 1] * BDR(iq, jq) * ZZ(n - jq, ncut - 1) * expbea[ncut];
+                B(ncol - n + iq) = sum + (BDR(iq, 0) * umu0 * fbeam / pi - ZZ(iq + n - 1, ncut - 1)) * expbea[ncut];
+            }
         }
         int it = n;
         for (int lc = 1; lc <= ncut - 1; lc++)
@@ -1229,7 +1237,7 @@ static void usrint(work_t *w, int mazim, double delm0, double fbeam,
             if (negumu && mazim == 0) {
                 bndint = (fisot + tplank) * exp(utaupr[lu] / umu[iu]);
             } else if (!negumu) {
-                if (!(lyrcut || mazim > 0)) {  /* LAMBER .AND. MAZIM.GT.0 */
+                if (!(lyrcut || (w->lamber && mazim > 0))) {  /* disort.f:4744 */
                     for (int jq = n; jq < N; jq++)
                         w->wk[jq] = exp(-KK(jq, L - 1) * dtaucp[L - 1]);
                     double bnddfu = 0.0;
@@ -1429,6 +1437,192 @@ static double ratio(double a, double b)
 /* ------------------------------------------------------------------ */
 /* DISORT main (disort.f:472-871)                                      */
 /* ------------------------------------------------------------------ */
+/* ------------------------------------------------------------------------------------------
+ * BDREF (spectra.f:249-296) and its three models, for non-Lambertian surfaces (LAMBER = 0).
+ * The model and its parameters live in file-scope state like the reference's module albblk
+ * (spectra.f:20-26); the ocean model's wavelength-dependent terms (INDWAT spectra.f:594,
+ * MORCASIWAT spectra.f:467: table look-ups) are handed over by the caller.
+ * ------------------------------------------------------------------------------------------ */
+static struct {
+    int ibdrf;                 /* 1 ocean, 2 Hapke, 3 Ross-Li (spectra.f:139-162) */
+    double p[5];               /* sc(1..5) as suralb stores them                  */
+    double nr, ni, rsw;        /* ocean: refractive index, sub-surface reflectance */
+} g_sfc;
+
+void sbdo_set_bdref(int ibdrf, const double *sc, double nr, double ni, double rsw)
+{
+    g_sfc.ibdrf = ibdrf;
+    for (int i = 0; i < 5; i++) g_sfc.p[i] = sc ? sc[i] : 0.0;
+    g_sfc.nr = nr; g_sfc.ni = ni; g_sfc.rsw = rsw;
+}
+
+static const double kPiParams = 3.1415926536;      /* params.f:29 */
+
+/* fresnel, spectra.f:1320-1352 */
+static double bd_fresnel(double nr, double ni, double coschi, double sinchi)
+{
+    double a1 = fabs(nr * nr - ni * ni - sinchi * sinchi);
+    double a2 = sqrt(pow(nr * nr - ni * ni - sinchi * sinchi, 2.) + 4 * nr * nr * ni * ni);
+    double u = sqrt(0.5 * (a1 + a2)), v = sqrt(0.5 * (-a1 + a2));
+    double rr2 = ((coschi - u) * (coschi - u) + v * v) / ((coschi + u) * (coschi + u) + v * v);
+    double b1 = (nr * nr - ni * ni) * coschi, b2 = 2 * nr * ni * coschi;
+    double rl2 = ((b1 - u) * (b1 - u) + (b2 + v) * (b2 + v)) / ((b1 + u) * (b1 + u) + (b2 - v) * (b2 - v));
+    return (rr2 + rl2) / 2.;
+}
+
+/* sunglint, spectra.f:1224-1316 (wind-direction average of the Cox-Munk distribution) */
+static double bd_sunglint(double wndspd, double nr, double ni, double csin, double cvin, double phi)
+{
+    const double pi = kPiParams;
+    double cs = csin > (double)0.05f ? csin : (double)0.05f;
+    double cv = cvin > (double)0.05f ? cvin : (double)0.05f;
+    double ss = sqrt(1. - cs * cs), sv = sqrt(1. - cv * cv);
+    double zx = -sv * sin(pi - phi) / (cs + cv);
+    double zy = (ss + sv * cos(pi - phi)) / (cs + cv);
+    double tilt = atan(sqrt(zx * zx + zy * zy));
+    double sigmac = (double)0.003f + (double)0.00192f * wndspd;
+    double sigmau = (double)0.00316f * wndspd;
+    double c40 = (double)0.40f, c22 = (double)0.12f, c04 = (double)0.23f;
+    double r2 = zx * zx + zy * zy;
+    double axe2 = (double).5f * r2 / sigmac, axn2 = (double).5f * r2 / sigmau;
+    double q4 = 3 * pow(zx, 4) + 6 * zx * zx * zy * zy + 3 * pow(zy, 4);
+    double axe4 = q4 / (8 * sigmac * sigmac), axn4 = q4 / (8 * sigmau * sigmau);
+    double axe2xn2 = (pow(zx, 4) + 10 * zx * zx * zy * zy + pow(zy, 4)) / (8 * sigmau * sigmac);
+    double coef = 1.;
+    coef = coef + c40 / 24. * (axe4 - 6 * axe2 + 3);
+    coef = coef + c04 / 24. * (axn4 - 6 * axn2 + 3);
+    coef = coef + c22 / 4. * (axe2xn2 - axn2 - axe2 + 1);
+    coef = coef / (2. * pi * sqrt(sigmau) * sqrt(sigmac));
+    double proba = coef * exp(-(axe2 + axn2) / 2.);
+    double cos2chi = cv * cs + sv * ss * cos(pi - phi);
+    if (cos2chi > 1.0) cos2chi = 0.99999999999;
+    if (cos2chi < -1.0) cos2chi = -0.99999999999;
+    double coschi = sqrt(0.5 * (1 + cos2chi)), sinchi = sqrt(0.5 * (1 - cos2chi));
+    double r1 = bd_fresnel(nr, ni, coschi, sinchi);
+    return pi * r1 * proba / (4. * cs * cv * pow(cos(tilt), 4));
+}
+
+/* bdref(wvnmlo, wvnmhi, mur, mui, phir), spectra.f:249 */
+static double bdref(double mur, double mui, double phir)
+{
+    const double pi = kPiParams;
+    const double *p = g_sfc.p;
+    if (g_sfc.ibdrf == 1) {                 /* seabdrf(wl, mus = mui, muv = mur, phir), spectra.f:421 */
+        double wndspd = p[1];
+        double wndwt = (double)2.951e-6f * pow(wndspd, (double)3.52f);
+        double rfoam = wndwt * (double)0.22f;
+        double rgl = bd_sunglint(wndspd, g_sfc.nr, g_sfc.ni, mui, mur, phir);
+        return rfoam + (1. - wndwt) * rgl + (1. - rfoam) * g_sfc.rsw;
+    }
+    if (g_sfc.ibdrf == 2) {                 /* hapkbdrf(ui = mui, ur = mur), spectra.f:298 */
+        double hssa = p[0], hasym = p[1], hotspt = p[2], hotwdth = p[3];
+        double ui = mui, ur = mur;
+        double coss = ui * ur + sqrt(1. - ur * ur) * sqrt(1. - ui * ui) * cos(pi - phir);
+        double s = acos(coss);
+        double pfun = (1. - hasym * hasym) / pow(1 + hasym * hasym + 2 * hasym * coss, 1.5);
+        double pfun0 = (1. - hasym * hasym) / pow(1 + hasym, 3.);
+        double b0 = hotspt / (hssa * pfun0);
+        double bfun = b0 / (1. + tan(s / 2) / hotwdth);
+        double hfunr = (1. + 2 * ur) / (1. + 2. * ur * sqrt(1. - hssa));
+        double hfuni = (1. + 2 * ui) / (1. + 2. * ui * sqrt(1. - hssa));
+        double bd = (1. + bfun) * pfun + hfunr * hfuni - 1.;
+        return (double).25f * hssa * bd / (ur + ui);
+    }
+    /* rtlsbdrf(mui, mur, phir), spectra.f:350 */
+    double rliso = p[0], rlvol = p[1], rlgeo = p[2], rlhot = p[3], rlwdth = p[4];
+    double ui = mui > (double).01f ? mui : (double).01f;
+    double ur = mur > (double).01f ? mur : (double).01f;
+    double cosra = cos(pi - phir);
+    double coss = ui * ur + sqrt(1. - ur * ur) * sqrt(1. - ui * ui) * cosra;
+    coss = coss < -1. ? -1. : (coss > 1. ? 1. : coss);
+    double s = acos(coss), sins = sin(s);
+    double f1 = (pi / 2 - s) * coss + sins;
+    f1 = f1 / (ui + ur) - pi / 4.;
+    double vza = acos(ur), sza = acos(ui);
+    double tanvzap = rlwdth * tan(vza), tanszap = rlwdth * tan(sza);
+    double vzap, szap;
+    if (rlwdth == 1.) { vzap = vza; szap = sza; }
+    else { vzap = atan(tanvzap); szap = atan(tanszap); }
+    double cossp = cos(szap) * cos(vzap) + sin(szap) * sin(vzap) * cosra;
+    cossp = cossp < -1. ? -1. : (cossp > 1. ? 1. : cossp);
+    double dd = tanszap * tanszap + tanvzap * tanvzap - 2 * tanszap * tanvzap * cosra;
+    double secsum = 1. / cos(szap) + 1. / cos(vzap);
+    double cost = rlhot * sqrt(dd + pow(tanszap * tanvzap * sin(pi - phir), 2.));
+    cost = cost / secsum;
+    cost = cost < -1. ? -1. : (cost > 1. ? 1. : cost);
+    double t = acos(cost);
+    double f2 = (t - sin(t) * cost) * secsum / pi;
+    f2 = f2 - 1. / cos(vzap) + (double).5f * (1. + cossp) / (cos(szap) * cos(vzap));
+    return rliso + rlvol * f1 + rlgeo * f2;
+}
+
+/* test hook: the model set with sbdo_set_bdref evaluated at one geometry */
+double sbdo_bdref_eval(double mur, double mui, double phir) { return bdref(mur, mui, phir); }
+
+#define SBDO_NMUG 50
+/* SURFAC, non-Lambertian branch (disort.f:3765-3907): Fourier coefficients of the
+ * bidirectional reflectivity at the computational and user angles by a 50-point quadrature
+ * in azimuth, directional emissivities from a 25 x 50 quadrature. */
+static void surfac_brdf(int n, int NU, int mazim, double delm0, double fbeam, double umu0,
+                        double pi, const double *cmu, const double *umu, int user,
+                        double *bdr, double *bem, double *rmu, double *emu)
+{
+    double gmu[SBDO_NMUG], gwt[SBDO_NMUG];
+    sbdo_qgausn(SBDO_NMUG / 2, gmu, gwt);
+    for (int k = 0; k < SBDO_NMUG / 2; k++) { gmu[k + SBDO_NMUG / 2] = -gmu[k]; gwt[k + SBDO_NMUG / 2] = gwt[k]; }
+    for (int iq = 0; iq < n; iq++) {
+        for (int jq = 1; jq <= n; jq++) {
+            double sum = 0.0;
+            for (int k = 0; k < SBDO_NMUG; k++)
+                sum += gwt[k] * bdref(cmu[iq], cmu[jq - 1], pi * gmu[k]) * cos(mazim * pi * gmu[k]);
+            bdr[iq * (n + 1) + jq] = 0.5 * (2. - delm0) * sum;
+        }
+        if (fbeam > 0.0) {
+            double sum = 0.0;
+            for (int k = 0; k < SBDO_NMUG; k++)
+                sum += gwt[k] * bdref(cmu[iq], umu0, pi * gmu[k]) * cos(mazim * pi * gmu[k]);
+            bdr[iq * (n + 1)] = 0.5 * (2. - delm0) * sum;
+        }
+    }
+    if (mazim == 0)
+        for (int iq = 0; iq < n; iq++) {
+            double dref = 0.0;
+            for (int jg = 0; jg < SBDO_NMUG; jg++) {
+                double sum = 0.0;
+                for (int k = 0; k < SBDO_NMUG / 2; k++)
+                    sum += gwt[k] * gmu[k] * bdref(cmu[iq], gmu[k], pi * gmu[jg]);
+                dref += gwt[jg] * sum;
+            }
+            bem[iq] = 1.0 - dref;
+        }
+    if (!user) return;
+    for (int iu = 0; iu < NU; iu++) {
+        if (!(umu[iu] > 0.0)) continue;
+        for (int iq = 1; iq <= n; iq++) {
+            double sum = 0.0;
+            for (int k = 0; k < SBDO_NMUG; k++)
+                sum += gwt[k] * bdref(umu[iu], cmu[iq - 1], pi * gmu[k]) * cos(mazim * pi * gmu[k]);
+            rmu[iu * (n + 1) + iq] = 0.5 * (2. - delm0) * sum;
+        }
+        if (fbeam > 0.0) {
+            double sum = 0.0;
+            for (int k = 0; k < SBDO_NMUG; k++)
+                sum += gwt[k] * bdref(umu[iu], umu0, pi * gmu[k]) * cos(mazim * pi * gmu[k]);
+            rmu[iu * (n + 1)] = 0.5 * (2. - delm0) * sum;
+        }
+        if (mazim == 0) {
+            double dref = 0.0;
+            for (int jg = 0; jg < SBDO_NMUG; jg++) {
+                double sum = 0.0;
+                for (int k = 0; k < SBDO_NMUG / 2; k++)
+                    sum += gwt[k] * gmu[k] * bdref(umu[iu], gmu[k], pi * gmu[jg]);
+                dref += gwt[jg] * sum;
+            }
+            emu[iu] = 1.0 - dref;
+        }
+    }
+}
+
 int sbdo_disort(const sbdo_input *in, const double *dtauc_in,
                 const double *ssalb_in, const double *pmom,
                 const double *temper, const double *utau_in,
@@ -1446,10 +1640,11 @@ int sbdo_disort(const sbdo_input *in, const double *dtauc_in,
     const int plank = in->plank, onlyfl = in->onlyfl;
 
     /* CHEKIN essentials (disort.f:4920-5155) */
-    if (N < 4 || N % 2 != 0 || L < 1 || !in->lamber) return SBDO_BAD_INPUT;
+    if (N < 4 || N % 2 != 0 || L < 1) return SBDO_BAD_INPUT;
+    if (!in->lamber && (g_sfc.ibdrf < 1 || g_sfc.ibdrf > 3)) return SBDO_BAD_INPUT;
     if (in->nmom < N) return SBDO_BAD_INPUT;
     if (fbeam < 0.0 || (fbeam > 0.0 && (umu0 <= 0.0 || umu0 > 1.0))) return SBDO_BAD_INPUT;
-    if (in->albedo < 0.0 || in->albedo > 1.0 || in->fisot < 0.0) return SBDO_BAD_INPUT;
+    if ((in->lamber && (in->albedo < 0.0 || in->albedo > 1.0)) || in->fisot < 0.0) return SBDO_BAD_INPUT;
     if (plank && (in->wvnmlo < 0.0 || in->wvnmhi <= in->wvnmlo ||
                   in->temis < 0.0 || in->temis > 1.0 || in->btemp < 0.0 ||
                   in->ttemp < 0.0)) return SBDO_BAD_INPUT;
@@ -1573,6 +1768,7 @@ int sbdo_disort(const sbdo_input *in, const double *dtauc_in,
             if (fbeam > 0.0) w->expbea[lc + 1] = exp(-w->taucpr[lc + 1] / umu0);
         }
         w->lyrcut = 0;
+        w->lamber = in->lamber;
         if (abstau >= abscut && !plank && L > 1) w->lyrcut = 1;
         if (!w->lyrcut) ncut = L;
         w->ncut = ncut;
@@ -1632,23 +1828,29 @@ int sbdo_disort(const sbdo_input *in, const double *dtauc_in,
                 for (int iq = n; iq < N; iq++) YLMC(l, iq) = sgn * YLMC(l, iq - n);
             }
         }
-        /* SURFAC, Lambertian (disort.f:3746-3763, :3834-3849) */
+        /* SURFAC (disort.f:3639): Lambertian :3746-3763, :3834-3849; BRDF :3765-3907 */
         if (!w->lyrcut) {
             memset(w->bdr, 0, sizeof(double) * (size_t)n * (n + 1));
             memset(w->bem, 0, sizeof(double) * n);
-            if (mazim == 0)
-                for (int iq = 0; iq < n; iq++) {
-                    w->bem[iq] = 1.0 - in->albedo;
-                    for (int jq = 0; jq <= n; jq++) w->bdr[iq * (n + 1) + jq] = in->albedo;
-                }
             if (!onlyfl && usrang_eff) {
                 memset(w->emu, 0, sizeof(double) * NU);
                 memset(w->rmu, 0, sizeof(double) * (size_t)NU * (n + 1));
-                for (int iu = 0; iu < NU; iu++)
-                    if (umu[iu] > 0.0 && mazim == 0) {
-                        for (int iq = 0; iq <= n; iq++) w->rmu[iu * (n + 1) + iq] = in->albedo;
-                        w->emu[iu] = 1.0 - in->albedo;
+            }
+            if (!in->lamber) {
+                surfac_brdf(n, NU, mazim, delm0, fbeam, umu0, pi, w->cmu, umu, !onlyfl && usrang_eff,
+                            w->bdr, w->bem, w->rmu, w->emu);
+            } else {
+                if (mazim == 0)
+                    for (int iq = 0; iq < n; iq++) {
+                        w->bem[iq] = 1.0 - in->albedo;
+                        for (int jq = 0; jq <= n; jq++) w->bdr[iq * (n + 1) + jq] = in->albedo;
                     }
+                if (!onlyfl && usrang_eff)
+                    for (int iu = 0; iu < NU; iu++)
+                        if (umu[iu] > 0.0 && mazim == 0) {
+                            for (int iq = 0; iq <= n; iq++) w->rmu[iu * (n + 1) + iq] = in->albedo;
+                            w->emu[iu] = 1.0 - in->albedo;
+                        }
             }
         }
         for (int lc = 0; lc < w->ncut; lc++) {

@@ -30,7 +30,7 @@ typedef struct sbdo_input {
     int plank;     /* PLANK                                                  */
     int onlyfl;    /* ONLYFL                                                 */
     int corint;    /* CORINT                                                 */
-    int lamber;    /* LAMBER -- must be 1 (BRDF surfaces out of scope)       */
+    int lamber;    /* LAMBER; 0 => BDREF surface set with sbdo_set_bdref()    */
     double fbeam, umu0, phi0, fisot, albedo;
     double btemp, ttemp, temis, wvnmlo, wvnmhi, accur;
 } sbdo_input;
@@ -77,6 +77,13 @@ int sbdo_disort_flux_batch(int nbins, int nlyr, int nstr, int nmom,
                            const int *col, double *rfldir, double *rfldn,
                            double *flup, double *dfdt, double *uavg,
                            int *status, int nthreads);
+
+/* Surface model of the following LAMBER = 0 calls (the reference's module albblk,
+ * spectra.f:20-26, set by suralb spectra.f:139-162): ibdrf 1 ocean / 2 Hapke / 3 Ross-Li,
+ * sc[5] as suralb stores them; nr, ni, rsw: the ocean model's table look-ups (INDWAT,
+ * MORCASIWAT) for the wavelength of the call.  Not thread-safe (file-scope state). */
+void sbdo_set_bdref(int ibdrf, const double *sc, double nr, double ni, double rsw);
+double sbdo_bdref_eval(double mur, double mui, double phir);
 
 /* pieces exported for unit tests */
 void sbdo_qgausn(int m, double *gmu, double *gwt);

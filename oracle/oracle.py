@@ -54,6 +54,10 @@ def lib():
         _LIB.sbdo_plkavg.argtypes = [C.c_double, C.c_double, C.c_double, ip]
         _LIB.sbdo_asymtx.restype = C.c_int
         _LIB.sbdo_asymtx.argtypes = [dp, dp, dp, C.c_int, C.c_int, C.c_int, dp]
+        _LIB.sbdo_set_bdref.restype = None
+        _LIB.sbdo_set_bdref.argtypes = [C.c_int, dp, C.c_double, C.c_double, C.c_double]
+        _LIB.sbdo_bdref_eval.restype = C.c_double
+        _LIB.sbdo_bdref_eval.argtypes = [C.c_double] * 3
         _LIB.sbdo_disort_flux_batch.restype = C.c_int
         _LIB.sbdo_disort_flux_batch.argtypes = (
             [C.c_int] * 4 + [dp] * 6 + [ip] + [dp] * 7 + [ip] + [dp] * 5 + [ip, C.c_int])
@@ -75,7 +79,7 @@ def _f64(a):
 def disort(dtauc, ssalb, pmom, *, nstr, temper=None, utau=None, umu=None,
            phi=None, fbeam=0.0, umu0=1.0, phi0=0.0, fisot=0.0, albedo=0.0,
            btemp=0.0, ttemp=0.0, temis=0.0, wvnmlo=0.0, wvnmhi=0.0,
-           plank=False, onlyfl=True, corint=False, accur=0.0):
+           plank=False, onlyfl=True, corint=False, accur=0.0, lamber=True):
     """One DISORT call through the oracle.
 
     pmom is [nlyr][nmom+1].  Returns a dict with rfldir, rfldn, flup, dfdt,
@@ -97,7 +101,7 @@ def disort(dtauc, ssalb, pmom, *, nstr, temper=None, utau=None, umu=None,
     inp.usrang = int(umu is not None)
     inp.numu = 0 if umu is None else umu.shape[0]
     inp.nphi = 0 if phi is None else phi.shape[0]
-    inp.plank, inp.onlyfl, inp.corint, inp.lamber = int(plank), int(onlyfl), int(corint), 1
+    inp.plank, inp.onlyfl, inp.corint, inp.lamber = int(plank), int(onlyfl), int(corint), int(lamber)
     inp.fbeam, inp.umu0, inp.phi0, inp.fisot, inp.albedo = fbeam, umu0, phi0, fisot, albedo
     inp.btemp, inp.ttemp, inp.temis = btemp, ttemp, temis
     inp.wvnmlo, inp.wvnmhi, inp.accur = wvnmlo, wvnmhi, accur
@@ -113,6 +117,17 @@ def disort(dtauc, ssalb, pmom, *, nstr, temper=None, utau=None, umu=None,
                            _dp(out["uavg"]), _dp(uu), _dp(u0u), C.byref(warn))
     out.update(uu=uu, u0u=u0u, status=st, warn=warn.value)
     return out
+
+
+def set_bdref(ibdrf, sc, nr=0.0, ni=0.0, rsw=0.0):
+    """Surface model of the following lamber=False calls (suralb, spectra.f:139-162)."""
+    p = np.zeros(5)
+    p[:len(sc)] = sc
+    lib().sbdo_set_bdref(int(ibdrf), _dp(p), float(nr), float(ni), float(rsw))
+
+
+def bdref(mur, mui, phir):
+    return lib().sbdo_bdref_eval(float(mur), float(mui), float(phir))
 
 
 def disort_flux_batch(dtauc, ssalb, pmom, *, nstr, fbeam, umu0, albedo,

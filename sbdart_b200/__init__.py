@@ -34,6 +34,7 @@ EXPORTS = (
     "sbd_measure_fp64_peak", "sbd_optics_upload_tables", "sbd_spectrum_run",
     "sbd_set_radiance_levels", "sbd_spectrum_set_aerosols", "sbd_set_corint", "sbd_build_id", "sbd_set_radiance_layout", "sbd_set_flux_levels",
     "sbd_spectrum_run_columns", "sbd_last_transfer_bytes", "sbd_spectrum_device_fluxes",
+    "sbd_set_surfaces", "sbd_set_bdref_callback",
 )
 
 
@@ -119,6 +120,10 @@ def lib():
     L.sbd_set_radiance_layout.argtypes = [C.c_void_p, C.c_int32]
     L.sbd_measure_fp64_peak.restype = C.c_int
     L.sbd_measure_fp64_peak.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
+    L.sbd_set_surfaces.restype = C.c_int
+    L.sbd_set_surfaces.argtypes = [C.c_void_p] + [C.c_int32] * 4 + [C.c_void_p] * 4
+    L.sbd_set_bdref_callback.restype = None
+    L.sbd_set_bdref_callback.argtypes = [C.c_void_p]
     L.sbd_disort_last_status.restype = C.c_int
     L.disort_.restype = None
     _LIB = L
@@ -137,6 +142,11 @@ def quadrature(m: int):
 
 def _f64(a):
     return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def surface_albedo(s):
+    """The `albedo` value that selects BRDF surface s (SBD_SURFACE, include/sbdart_b200.h)."""
+    return -(np.asarray(s, dtype=np.float64) + 1.0)
 
 
 def make_bins(nbins, *, fbeam=0.0, umu0=1.0, phi0=0.0, fisot=0.0, albedo=0.0, btemp=0.0,
@@ -192,6 +202,25 @@ class Solver:
         rc = lib().sbd_synchronize(self._h)
         if rc:
             raise SbdError(rc, "sbd_synchronize")
+
+    def set_surfaces(self, nstr=0, bdr=None, bem=None, rmu=None, emu=None):
+        """BRDF surfaces of the following calls (LAMBER = .FALSE.): SURFAC's tables
+        bdr [ns][modes][n][n+1], bem [ns][n], and for radiance runs rmu [ns][modes][numu][n+1],
+        emu [ns][numu] (sbdart_b200.frontend.brdf.surface_tables builds them).  A bin selects
+        surface s with albedo = surface_albedo(s).  No arguments: back to Lambertian surfaces."""
+        if bdr is None:
+            rc = lib().sbd_set_surfaces(self._h, 0, 0, 0, 0, None, None, None, None)
+        else:
+            bdr, bem = _f64(bdr), _f64(bem)
+            ns, modes = bdr.shape[0], bdr.shape[1]
+            numu = 0 if rmu is None else np.shape(rmu)[2]
+            rmu = None if rmu is None else _f64(rmu)
+            emu = None if emu is None else _f64(emu)
+            rc = lib().sbd_set_surfaces(self._h, ns, nstr, modes, numu, bdr.ctypes.data, bem.ctypes.data,
+                                        None if rmu is None else rmu.ctypes.data,
+                                        None if emu is None else emu.ctypes.data)
+        if rc:
+            raise SbdError(rc, "sbd_set_surfaces")
 
     # -- host-buffer call: the reference-facing path (H2D + kernel + D2H) ----
     def set_radiance_levels(self, levels=None):

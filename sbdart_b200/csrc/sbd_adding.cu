@@ -4,7 +4,7 @@
 //
 // Same discrete-ordinate equations, same delta-M scaling, truncation, sources and boundary
 // conditions as the reference (tests/adding_model.py states the
-// algorithm in numpy and tests/test_adding_math_cpu.py checks it against the CPU oracle).
+// algorithm in numpy and tests/test_adding_math_cpu.py checks it against the CPU restatement of the reference).
 //
 // In the flux-weighted variables u^ = sqrt(w mu) u the sums s^ = u^+ + u^- and differences
 // d^ = u^+ - u^- obey d s^/d tau = Po d^, d d^/d tau = Pe s^ with the symmetric operators of
@@ -563,6 +563,7 @@ disort_adding_kernel(const LaunchArgs a)
         double *o_uavg = (a.uavg && have) ? a.uavg + (size_t)bin * NT : nullptr;
 
         int status = have ? 0 : -1;
+        int surf = -1;
         {   // CHEKIN subset (disort.f:4920-5155)
             int badl = 0;
             for (int lc = lane; lc < L; lc += 32) {
@@ -575,7 +576,12 @@ disort_adding_kernel(const LaunchArgs a)
                 }
             }
             if (fbeam < 0.0 || (fbeam > 0.0 && !(umu0 > 0.0 && umu0 <= 1.0))) badl = 1;
-            if (!(albedo >= 0.0 && albedo <= 1.0) || bp.fisot < 0.0) badl = 1;
+            // albedo = SBD_SURFACE(s): BRDF surface s (LAMBER = .FALSE.)
+            if (albedo < 0.0) {
+                surf = (int)(-albedo) - 1;
+                if (!a.sf_bdr || surf >= a.sf_count || (double)(surf + 1) != -albedo) badl = 1;
+            } else if (!(albedo <= 1.0)) badl = 1;
+            if (bp.fisot < 0.0) badl = 1;
             if (plank && (bp.wvnmlo < 0.0 || bp.wvnmhi <= bp.wvnmlo || bp.temis < 0.0 ||
                           bp.temis > 1.0 || bp.btemp < 0.0 || bp.ttemp < 0.0)) badl = 1;
             if (plank && (!a.temper || bp.col < 0 || bp.col >= a.d.ncol)) badl = 1;
@@ -695,17 +701,39 @@ disort_adding_kernel(const LaunchArgs a)
 #pragma unroll
         for (int c = 0; c < n; c++) fnB[c] = 0.0;
         if (!status) {
-            // bottom boundary (disort.f:2919-2990, :3552-3578): Lambertian, or no upwelling
-            // radiation at the truncation level
-            const double refl = lyrcut ? 0.0 : 2.0 * albedo;
-            const double emis = lyrcut ? 0.0 : albedo * umu0 * fbeam / kPiRef * ebeam[ncut] + (1.0 - albedo) * bplank;
-            for (int e = lane; e < n * n; e += 32) sRb[e] = refl * cd[e / n] * cd[e % n];
-            if (lane < n) ssb[lane] = cd[lane] * emis;
-            if (lane == n || lane == n + 1) {
-                const double s = (lane == n) ? Wq : SWq;     // D^T D, c^T D
+            // bottom boundary (disort.f:2919-2990, :3552-3578): Lambertian or BRDF surface (m = 0
+            // tables of SURFAC), or no upwelling radiation at the truncation level.  In the scaled
+            // variables: Rb = 2 D BDR D, sb = D (BDR(:,0) mu0 F / pi E + BEM B(Ts))
+            if (surf >= 0 && !lyrcut) {
+                const double *bdr = a.sf_bdr + (size_t)surf * a.sf_modes * n * (n + 1);
+                const double *bem = a.sf_bem + (size_t)surf * n;
+                const double beamfac = umu0 * fbeam / kPiRef * ebeam[ncut];
+                for (int e = lane; e < n * n; e += 32)
+                    sRb[e] = 2.0 * cd[e / n] * bdr[(e / n) * (n + 1) + 1 + e % n] * cd[e % n];
+                if (lane < n) ssb[lane] = cd[lane] * (bdr[lane * (n + 1)] * beamfac + bem[lane] * bplank);
+                __syncwarp();
+                if (lane == n || lane == n + 1) {
+                    const double *wv = (lane == n) ? cd : csq;
+                    fnB0 = 0.0;
 #pragma unroll
-                for (int c = 0; c < n; c++) fnB[c] = refl * s * cd[c];
-                fnB0 = s * emis;
+                    for (int c = 0; c < n; c++) {
+                        double acc = 0.0;
+                        for (int k = 0; k < n; k++) acc = fma(wv[k], sRb[k * n + c], acc);
+                        fnB[c] = acc;
+                        fnB0 = fma(wv[c], ssb[c], fnB0);
+                    }
+                }
+            } else {
+                const double refl = lyrcut ? 0.0 : 2.0 * albedo;
+                const double emis = lyrcut ? 0.0 : albedo * umu0 * fbeam / kPiRef * ebeam[ncut] + (1.0 - albedo) * bplank;
+                for (int e = lane; e < n * n; e += 32) sRb[e] = refl * cd[e / n] * cd[e % n];
+                if (lane < n) ssb[lane] = cd[lane] * emis;
+                if (lane == n || lane == n + 1) {
+                    const double s = (lane == n) ? Wq : SWq;     // D^T D, c^T D
+#pragma unroll
+                    for (int c = 0; c < n; c++) fnB[c] = refl * s * cd[c];
+                    fnB0 = s * emis;
+                }
             }
             warp_copy_async(rbuf, recs + (size_t)(ncut - 1) * AL::rec, AL::rec, lane);
             cp_async_commit();

@@ -159,7 +159,7 @@ extern "C" void sbd_destroy(sbd_handle *h)
     cudaStreamSynchronize(h->stream);
     for (auto &kv : h->tables) { cudaFree(kv.second.quad); cudaFree(kv.second.ylmc); }
     cudaStreamSynchronize(h->stream2);
-    SbdDevBuf *bufs[] = { &h->redo, &h->redo2, &h->redo_scratch, &h->redo_scratch2, &h->scratch, &h->counter, &h->scratch2, &h->counter2, &h->ylmu, &h->angles, &h->d_dtauc, &h->d_ssalb,
+    SbdDevBuf *bufs[] = { &h->surfaces, &h->redo, &h->redo2, &h->redo_scratch, &h->redo_scratch2, &h->scratch, &h->counter, &h->scratch2, &h->counter2, &h->ylmu, &h->angles, &h->d_dtauc, &h->d_ssalb,
                        &h->d_pmom, &h->d_bins, &h->d_temper, &h->d_utau, &h->d_out, &h->d_uu,
                        &h->d_status, &h->opt_tables, &h->opt_atm, &h->opt_misc, &h->opt_map, &h->opt_aero,
                        &h->d_uupack, &h->d_sel, &h->d_fluxpack };
@@ -207,6 +207,31 @@ static std::vector<int32_t> selected_levels(const sbd_handle *h, int NT)
     for (int lu = 0; lu < NT; lu++)
         if (lu >= 128 || ((h->uu_mask[lu >> 6] >> (lu & 63)) & 1ull)) sel.push_back(lu);
     return sel;
+}
+
+extern "C" int sbd_set_surfaces(sbd_handle *h, int32_t nsurf, int32_t nstr, int32_t nmodes, int32_t numu,
+                                const double *bdr, const double *bem, const double *rmu, const double *emu)
+{
+    if (!h) return SBD_ERR_ARG;
+    if (nsurf <= 0) { h->sf_count = 0; return SBD_SUCCESS; }
+    if (nstr < 4 || nstr % 2 || nstr > SBD_MAX_NSTR || (nmodes != 1 && nmodes != nstr) || numu < 0 || !bdr || !bem ||
+        (numu > 0 && (!rmu || !emu))) return SBD_ERR_ARG;
+    const size_t n = nstr / 2;
+    const size_t n_bdr = (size_t)nsurf * nmodes * n * (n + 1), n_bem = (size_t)nsurf * n;
+    const size_t n_rmu = (size_t)nsurf * nmodes * numu * (n + 1), n_emu = (size_t)nsurf * numu;
+    if (cudaSetDevice(h->device) != cudaSuccess) return SBD_ERR_CUDA;
+    if (h->surfaces.reserve((n_bdr + n_bem + n_rmu + n_emu) * 8) != cudaSuccess) return SBD_ERR_CUDA;
+    double *d = (double *)h->surfaces.p;
+    // (the stream may still read the previous tables)
+    if (cudaStreamSynchronize(h->stream) != cudaSuccess) return SBD_ERR_CUDA;
+    if (cudaMemcpy(d, bdr, n_bdr * 8, cudaMemcpyHostToDevice) != cudaSuccess) return SBD_ERR_CUDA;
+    if (cudaMemcpy(d + n_bdr, bem, n_bem * 8, cudaMemcpyHostToDevice) != cudaSuccess) return SBD_ERR_CUDA;
+    if (numu > 0) {
+        if (cudaMemcpy(d + n_bdr + n_bem, rmu, n_rmu * 8, cudaMemcpyHostToDevice) != cudaSuccess) return SBD_ERR_CUDA;
+        if (cudaMemcpy(d + n_bdr + n_bem + n_rmu, emu, n_emu * 8, cudaMemcpyHostToDevice) != cudaSuccess) return SBD_ERR_CUDA;
+    }
+    h->sf_count = nsurf; h->sf_nstr = nstr; h->sf_modes = nmodes; h->sf_numu = numu;
+    return SBD_SUCCESS;
 }
 
 extern "C" int sbd_set_corint(sbd_handle *h, int32_t on)
@@ -274,12 +299,18 @@ extern "C" int sbd_disort_batch_device(sbd_handle *h, const sbd_dims *dims, cons
 
     size_t smem_limit = h->smem_optin ? h->smem_optin : 48 * 1024;
     // register kernel: NSTR 4/8/16; radiances at the layer boundaries (the mode SBDART uses)
-    const bool fast = fast_supported(N) && (NU == 0 || dims->ntau == 0) && !getenv("SBD_FORCE_GENERIC");
+    // BRDF surfaces: the adding kernel (fluxes at the layer boundaries, NSTR 4/8/16) and the
+    // general kernel implement them
+    const bool brdf = h->sf_count > 0;
+    if (brdf && (h->sf_nstr != N || (NU > 0 && (h->sf_modes != N || h->sf_numu != NU)))) return SBD_ERR_ARG;
+    const bool adding_ok = adding_supported(N) && NU == 0 && dims->ntau == 0;
+    const bool fast = fast_supported(N) && (NU == 0 || dims->ntau == 0) && !getenv("SBD_FORCE_GENERIC") &&
+                      (!brdf || adding_ok);
     // adding kernel: NSTR 4/8/16, fluxes at the layer boundaries (SBD_FORCE_ELIM: the elimination
     // kernel instead -- a tuning / comparison knob, not API)
-    const bool adding = fast && adding_supported(N) && NU == 0 && dims->ntau == 0 && !getenv("SBD_FORCE_ELIM");
+    const bool adding = fast && adding_ok && (brdf || !getenv("SBD_FORCE_ELIM"));
     // CTA-per-bin register kernel: NSTR 20/24/32, fluxes
-    const bool wide = !fast && wide_supported(N) && NU == 0 && !getenv("SBD_FORCE_GENERIC") &&
+    const bool wide = !fast && !brdf && wide_supported(N) && NU == 0 && !getenv("SBD_FORCE_GENERIC") &&
                       wide_smem_bytes(N, L, NT) <= smem_limit;
     int warps, grid;
     size_t slot;
@@ -348,6 +379,15 @@ extern "C" int sbd_disort_batch_device(sbd_handle *h, const sbd_dims *dims, cons
     h->pending_binmap = nullptr;
     h->pending_nbins_dev = nullptr;
     a.quad = tb.quad; a.ylmc = tb.ylmc;
+    if (brdf) {
+        const size_t n = N / 2;
+        const double *d = (const double *)h->surfaces.p;
+        a.sf_count = h->sf_count; a.sf_modes = h->sf_modes;
+        a.sf_bdr = d;
+        a.sf_bem = a.sf_bdr + (size_t)h->sf_count * h->sf_modes * n * (n + 1);
+        a.sf_rmu = a.sf_bem + (size_t)h->sf_count * n;
+        a.sf_emu = a.sf_rmu + (size_t)h->sf_count * h->sf_modes * h->sf_numu * (n + 1);
+    }
     a.nslots = grid * warps;
     a.slot_stride = slot;
     a.nmodes = 1;
@@ -579,6 +619,66 @@ extern "C" int sbd_disort_batch(sbd_handle *h, const sbd_dims *dims, const doubl
 // gfortran-compatible single-call entry (reference call site drt.f:541-546)
 // ---------------------------------------------------------------------------
 static thread_local int g_last_status = 0;
+
+// BDREF of the host program (spectra.f:249; REAL(KR) FUNCTION with kr = 8, everything by
+// reference): resolved from the executable when it exports the symbol (weak), or handed over
+// with sbd_set_bdref_callback.
+typedef double (*sbd_bdref_fn)(const double *wvnmlo, const double *wvnmhi, const double *mur,
+                               const double *mui, const double *phir);
+extern "C" double bdref_(const double *, const double *, const double *, const double *, const double *)
+    __attribute__((weak));
+static sbd_bdref_fn g_bdref = nullptr;
+extern "C" void sbd_set_bdref_callback(sbd_bdref_fn fn) { g_bdref = fn; }
+
+// SURFAC for LAMBER = .FALSE. (disort.f:3765-3907) on the host: Fourier coefficients of the
+// bidirectional reflectivity by a 50-point azimuth quadrature, directional emissivities by a
+// 25 x 50 quadrature.  Output layout: sbd_set_surfaces, one surface.
+static void surfac_host(sbd_bdref_fn f, int N, int nmodes, int NU, const double *umu, double fbeam,
+                        double umu0, double wlo, double whi, std::vector<double> &bdr,
+                        std::vector<double> &bem, std::vector<double> &rmu, std::vector<double> &emu)
+{
+    constexpr int NMUG = 50;
+    const int n = N / 2;
+    const double pi = kPiRef;
+    double gmu[NMUG], gwt[NMUG];
+    gauss01(NMUG / 2, gmu, gwt);
+    for (int k = 0; k < NMUG / 2; k++) { gmu[k + NMUG / 2] = -gmu[k]; gwt[k + NMUG / 2] = gwt[k]; }
+    std::vector<double> cmu(n), cwt(n);
+    gauss01(n, cmu.data(), cwt.data());
+    bdr.assign((size_t)nmodes * n * (n + 1), 0.0); bem.assign(n, 0.0);
+    rmu.assign((size_t)nmodes * NU * (n + 1), 0.0); emu.assign(NU, 0.0);
+    auto bd = [&](double mur, double mui, double phir) { return f(&wlo, &whi, &mur, &mui, &phir); };
+    // all modes of one (reflection, incidence) pair share the 50 BDREF values
+    auto fourier = [&](double mur, double mui, double *out, size_t stride) {
+        double v[NMUG];
+        for (int k = 0; k < NMUG; k++) v[k] = bd(mur, mui, pi * gmu[k]);
+        for (int m = 0; m < nmodes; m++) {
+            double sum = 0.0;
+            for (int k = 0; k < NMUG; k++) sum += gwt[k] * v[k] * cos(m * pi * gmu[k]);
+            out[m * stride] = 0.5 * (2. - (m == 0 ? 1. : 0.)) * sum;
+        }
+    };
+    auto emiss = [&](double mur) {
+        double dref = 0.0;
+        for (int jg = 0; jg < NMUG; jg++) {
+            double sum = 0.0;
+            for (int k = 0; k < NMUG / 2; k++) sum += gwt[k] * gmu[k] * bd(mur, gmu[k], pi * gmu[jg]);
+            dref += gwt[jg] * sum;
+        }
+        return 1.0 - dref;
+    };
+    for (int iq = 0; iq < n; iq++) {
+        for (int jq = 1; jq <= n; jq++) fourier(cmu[iq], cmu[jq - 1], &bdr[(size_t)iq * (n + 1) + jq], (size_t)n * (n + 1));
+        if (fbeam > 0.0) fourier(cmu[iq], umu0, &bdr[(size_t)iq * (n + 1)], (size_t)n * (n + 1));
+        bem[iq] = emiss(cmu[iq]);
+    }
+    for (int iu = 0; iu < NU; iu++) {
+        if (!(umu[iu] > 0.0)) continue;
+        for (int iq = 1; iq <= n; iq++) fourier(umu[iu], cmu[iq - 1], &rmu[(size_t)iu * (n + 1) + iq], (size_t)NU * (n + 1));
+        if (fbeam > 0.0) fourier(umu[iu], umu0, &rmu[(size_t)iu * (n + 1)], (size_t)NU * (n + 1));
+        emu[iu] = emiss(umu[iu]);
+    }
+}
 static sbd_handle *g_handle = nullptr;
 static std::mutex g_mutex;
 
@@ -606,7 +706,8 @@ extern "C" void disort_(int *nlyr, double *dtauc, double *ssalb, int *corint, in
     const bool rad = !*onlyfl;
     // outside the hot path: IBCND=1, BRDF surfaces, intensities at the quadrature
     // angles (USRANG=F, never used by SBDART), CORINT with user levels
-    if (*ibcnd != 0 || !*lamber || (rad && !*usrang) || (rad && *corint && *usrtau)) {
+    const sbd_bdref_fn bdfn = g_bdref ? g_bdref : (sbd_bdref_fn)bdref_;
+    if (*ibcnd != 0 || (rad && !*usrang) || (rad && *corint && *usrtau) || (!*lamber && (!bdfn || *corint || *usrtau))) {
         g_last_status = SBD_ERR_UNSUPPORTED;
         return;
     }
@@ -634,11 +735,21 @@ extern "C" void disort_(int *nlyr, double *dtauc, double *ssalb, int *corint, in
     if (NT > *maxulv) { g_last_status = SBD_ERR_ARG; return; }
     int32_t st = 0;
     std::vector<double> uuc(rad ? (size_t)d.nphi * NT * d.numu : 0);
+    if (!*lamber) {           // SURFAC with the host's BDREF (disort.f:3765-3907)
+        std::vector<double> bdr, bem, rmu, emu;
+        const int nmodes = rad ? N : 1;
+        surfac_host(bdfn, N, nmodes, rad ? d.numu : 0, umu, *fbeam, *umu0, *wvnmlo, *wvnmhi, bdr, bem, rmu, emu);
+        int rcs = sbd_set_surfaces(g_handle, 1, N, nmodes, rad ? d.numu : 0, bdr.data(), bem.data(),
+                                   rad ? rmu.data() : nullptr, rad ? emu.data() : nullptr);
+        if (rcs) { g_last_status = rcs; return; }
+        b.albedo = SBD_SURFACE(0);
+    }
     g_handle->corint = rad && *corint;
     int rc = sbd_disort_batch(g_handle, &d, dtauc, ssalb, pm.data(), &b, temper,
                               *usrtau ? utau : nullptr, rad ? umu : nullptr, rad ? phi : nullptr,
                               rfldir, rfldn, flup, dfdt, uavg, rad ? uuc.data() : nullptr, &st);
     g_handle->corint = false;
+    if (!*lamber) sbd_set_surfaces(g_handle, 0, 0, 0, 0, nullptr, nullptr, nullptr, nullptr);
     g_last_status = rc ? rc : st;
     if (rc) return;
     if (rad)      // UU(IU,LU,J), leading dimensions MAXUMU, MAXULV (disort.f:377)

@@ -176,6 +176,8 @@ struct BinCtx {
     double fbeam, umu0, albedo, fisot, tplank, bplank, delm0;
     const double *dtauc, *ssalb, *pmom;
     int ldp;
+    // BRDF surface (LAMBER = .FALSE.): SURFAC's tables of the current azimuth mode, or null
+    const double *bdr, *bem, *rmu, *emu;
 };
 
 // ---------------------------------------------------------------------------
@@ -780,7 +782,16 @@ __device__ double usrint_one(const BinCtx &c, const WarpShared &w, const LayerLa
     // boundary contributions (disort.f:4735-4781)
     double bndint = 0.0;
     if (negumu && m == 0) bndint = (fisot + c.tplank) * exp(utpr / umu);
-    else if (!negumu && !(c.lyrcut || m > 0))
+    else if (!negumu && c.rmu && !c.lyrcut) {
+        // BRDF surface (disort.f:4744-4778): RMU-weighted downward intensities + direct beam + emission
+        const double *rm = c.rmu + (size_t)iu * (n + 1);
+        double bnd = 0.0;
+        for (int k = 0; k < n; k++) bnd += rm[1 + k] * w.cs[k];
+        bnd *= 1.0 + c.delm0;
+        if (c.fbeam > 0.0) bnd += c.umu0 * c.fbeam / kPiRef * rm[0] * exp(-w.taucpr[L] / c.umu0);
+        if (m == 0) bnd += c.emu[iu] * c.bplank;
+        bndint = bnd * exp((utpr - w.taucpr[L]) / umu);
+    } else if (!negumu && !(c.lyrcut || m > 0))
         bndint = bnd_up * exp((utpr - w.taucpr[L]) / umu);
     return palint + plkint + bndint;
 }
@@ -854,6 +865,8 @@ disort_generic_kernel(const LaunchArgs a)
         double *o_uavg = (a.uavg && have) ? a.uavg + (size_t)bin * NT : nullptr;
 
         int status = have ? 0 : -1;
+        int surf = -1;
+        c.bdr = c.bem = c.rmu = c.emu = nullptr;
         // ---- input checks (subset of CHEKIN, disort.f:4920-5155) ----------
         {
             int badl = 0;
@@ -867,7 +880,13 @@ disort_generic_kernel(const LaunchArgs a)
                 }
             }
             if (c.fbeam < 0.0 || (c.fbeam > 0.0 && !(c.umu0 > 0.0 && c.umu0 <= 1.0))) badl = 1;
-            if (!(c.albedo >= 0.0 && c.albedo <= 1.0) || c.fisot < 0.0) badl = 1;
+            // albedo = SBD_SURFACE(s): BRDF surface s
+            if (c.albedo < 0.0) {
+                surf = (int)(-c.albedo) - 1;
+                if (!a.sf_bdr || surf >= a.sf_count || (double)(surf + 1) != -c.albedo ||
+                    (NU > 0 && a.sf_modes != N)) badl = 1;
+            } else if (!(c.albedo <= 1.0)) badl = 1;
+            if (c.fisot < 0.0) badl = 1;
             if (c.plank && (bp.wvnmlo < 0.0 || bp.wvnmhi <= bp.wvnmlo || bp.temis < 0.0 ||
                             bp.temis > 1.0 || bp.btemp < 0.0 || bp.ttemp < 0.0)) badl = 1;
             // device-pointer callers: a Planck bin needs a valid row of temper[ncol][L+1]
@@ -962,6 +981,14 @@ disort_generic_kernel(const LaunchArgs a)
         if (!(SYNC ? __syncthreads_or(mact) : (int)mact)) break;
         c.mazim = mazim;
         c.delm0 = (mazim == 0) ? 1.0 : 0.0;
+        if (surf >= 0 && !status) {       // SURFAC's tables of this mode (disort.f:3765-3907)
+            c.bdr = a.sf_bdr + ((size_t)surf * a.sf_modes + mazim) * n * (n + 1);
+            c.bem = a.sf_bem + (size_t)surf * n;
+            if (NU > 0) {
+                c.rmu = a.sf_rmu + ((size_t)surf * a.sf_modes + mazim) * NU * (n + 1);
+                c.emu = a.sf_emu + (size_t)surf * NU;
+            }
+        }
         cs.ylm = (mazim == 0) ? ylm_smem : a.ylmc + (size_t)mazim * N * n;
         const double *ylmu_m = (NU > 0) ? a.ylmu + (size_t)mazim * N * NU : nullptr;
         // Y_l^m(-mu0) (LEPOLY, disort.f:599-605)
@@ -1044,12 +1071,14 @@ disort_generic_kernel(const LaunchArgs a)
             const int lc = ncut - 1;
             const double tb = w.taucpr[ncut];
             const double eb = (c.fbeam > 0.0) ? exp(-tb / c.umu0) : 0.0;
-            // Lambertian surface reflects the m = 0 mode only (disort.f:2929-2947)
-            const int refl = !c.lyrcut && mazim == 0;
-            // sum_k w_k mu_k GC(-mu_k, j): one value per column, and for the rhs
+            // Lambertian surface reflects the m = 0 mode only (disort.f:2929-2947); a BRDF
+            // surface every mode
+            const int refl = !c.lyrcut && (mazim == 0 || c.bdr);
+            const double fref = 1.0 + c.delm0;
+            // sum_k w_k mu_k GC(-mu_k, j): one value per column, and for the rhs (Lambertian)
             for (int j = lane; j <= N; j += 32) {
                 double sacc = 0.0;
-                if (refl) {
+                if (refl && !c.bdr) {
                     for (int k = 0; k < n; k++) {
                         double g = (j < N) ? gc_elem(w.Gp[cur], w.Gm[cur], n, n - 1 - k, j)
                                            : (w.zz[cur][n - 1 - k] * eb + w.zp0[cur][n - 1 - k] + xr1c * tb);
@@ -1065,13 +1094,28 @@ disort_generic_kernel(const LaunchArgs a)
                 double v;
                 if (j < N) {
                     double g = gc_elem(w.Gp[cur], w.Gm[cur], n, r, j);
-                    if (refl) g -= 2.0 * c.albedo * w.v1[j];
+                    if (refl && c.bdr) {
+                        double sacc = 0.0;
+                        for (int k = 0; k < n; k++)
+                            sacc += cs.wt[k] * cs.mu[k] * c.bdr[i * (n + 1) + 1 + k] *
+                                    gc_elem(w.Gp[cur], w.Gm[cur], n, n - 1 - k, j);
+                        g -= fref * sacc;
+                    } else if (refl) g -= 2.0 * c.albedo * w.v1[j];
                     v = (j < n) ? g : g * w.ek[cur][j - n];
                 } else if (j < 2 * N) {
                     v = 0.0;
                 } else {
-                    v = -w.zz[cur][r] * eb - w.zp0[cur][r] - xr1c * tb;
-                    if (refl)
+                    v = -w.zz[cur][r] * eb - (mazim == 0 ? w.zp0[cur][r] + xr1c * tb : 0.0);
+                    if (refl && c.bdr) {
+                        // SOLVE0 (disort.f:3452-3466 for m > 0, :3552-3578 for m = 0)
+                        double sacc = 0.0;
+                        for (int k = 0; k < n; k++)
+                            sacc += cs.wt[k] * cs.mu[k] * c.bdr[i * (n + 1) + 1 + k] *
+                                    (w.zz[cur][n - 1 - k] * eb +
+                                     (mazim == 0 ? w.zp0[cur][n - 1 - k] + xr1c * tb : 0.0));
+                        v += fref * sacc + c.bdr[i * (n + 1)] * c.umu0 * c.fbeam / kPiRef * eb +
+                             c.delm0 * c.bem[i] * c.bplank;
+                    } else if (refl)
                         v += 2.0 * c.albedo * w.v2[0] + c.albedo * c.umu0 * c.fbeam / kPiRef * eb +
                              (1.0 - c.albedo) * c.bplank;
                 }
@@ -1111,8 +1155,10 @@ disort_generic_kernel(const LaunchArgs a)
 
                 if (NU > 0) {
                     // surface-reflected term of USRINT (disort.f:4747-4778): downward
-                    // intensities at the bottom boundary, Lambertian, m = 0 only
-                    if (lc == ncut - 1 && mazim == 0 && !c.lyrcut) {
+                    // intensities at the bottom boundary; Lambertian: m = 0 only, one value
+                    // for all angles; BRDF: every mode, the weighted intensities are kept
+                    // (in the Jacobi work vector, idle during the upward sweep) for RMU
+                    if (lc == ncut - 1 && (mazim == 0 || c.bdr) && !c.lyrcut) {
                         const double tb = w.taucpr[ncut];
                         const double eb = (c.fbeam > 0.0) ? exp(-tb / c.umu0) : 0.0;
                         double dn = 0.0;
@@ -1123,10 +1169,12 @@ disort_generic_kernel(const LaunchArgs a)
                                       w.Gp[cur][i * n + j] * w.xc[n - 1 - j];
                             ud += w.zz[cur][n - 1 - i] * eb + w.zp0[cur][n - 1 - i] + xr1c * tb;
                             dn += cs.wt[i] * cs.mu[i] * ud;
+                            if (c.bdr) w.cs[i] = cs.wt[i] * cs.mu[i] * ud;
                         }
                         dn = warp_sum(dn);
                         bnd_up = 2.0 * c.albedo * dn + c.umu0 * c.fbeam / kPiRef * c.albedo * eb +
                                  (1.0 - c.albedo) * c.bplank;
+                        __syncwarp();
                     }
                     user_terms(c, cs, w, ll, scr + (size_t)lc * ll.stride, ylmu_m, NU, lc, cur,
                                xr0c, xr1c, lane);

@@ -46,6 +46,8 @@ struct sbd_handle {
     SbdDevBuf scratch2, counter2;
     // adding kernel: list of bins handed to the elimination kernel, and that kernel's scratch
     SbdDevBuf redo, redo2, redo_scratch, redo_scratch2;
+    SbdDevBuf surfaces;                        // sbd_set_surfaces
+    int sf_count = 0, sf_nstr = 0, sf_modes = 0, sf_numu = 0;
     cudaStream_t stream2 = nullptr;
     cudaEvent_t ev_misc = nullptr;
     int scratch_set = 0;

@@ -36,6 +36,10 @@ struct LaunchArgs {
     int *redo_count;
     int *redo_list;
     bool redo_consume;        // this launch takes its bins from the list
+    // BRDF surfaces (sbd_set_surfaces): bdr [ns][modes][n][n+1], bem [ns][n],
+    // rmu [ns][modes][numu][n+1], emu [ns][numu]
+    const double *sf_bdr, *sf_bem, *sf_rmu, *sf_emu;
+    int sf_count, sf_modes;
     unsigned long long uu_mask[2]; // bit lu: intensities wanted at output level lu
     // layout of uu: [bin][nphi][uu_nt][numu]; output level lu lives in slot uu_slot[lu]
     // (-1: not wanted).  Full layout: uu_nt = NT, slot = level; packed: the wanted levels only.
