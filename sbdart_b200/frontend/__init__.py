@@ -18,7 +18,7 @@ is NOT here: `run()` takes a `solve(batch)` callable -- the CUDA batch solver
 Aerosols, zgrid, in-cloud humidity, zensun and the sensor filters live in extras.py.
 User files read from the working directory like the reference: atms.dat, albedo.dat,
 filter.dat, solar.dat.  Not covered: aerosol.dat, usrcld.dat, CKTAU (kdist=-1), BRDF
-surfaces (isalb 7-9), spowder.
+spowder.
 """
 from __future__ import annotations
 
@@ -1245,7 +1245,14 @@ class Sbdart:
             if self.nphi == 0:
                 self.nphi = 1
                 self.phi = np.array([0.0])
-        self.albedo = Albedo(p["isalb"], p["albcon"], self.sc)
+        self.surface = None
+        if p["isalb"] in (7, 8, 9):
+            # BRDF surface: LAMBER = .FALSE., rsfc unused (drt.f:469-477)
+            from . import brdf
+            self.surface = brdf.SurfaceModel(p["isalb"], list(np.atleast_1d(p.get("sc") if p.get("sc") is not None else [0.] * 5)))
+            self.albedo = lambda wl, warn=None: 0.0
+        else:
+            self.albedo = Albedo(p["isalb"], p["albcon"], self.sc)
         self.amu0 = math.cos(sza * dtor)
         self.sun = Sun(p["nf"])
         self.aerosols = extras.Aerosols(p, z, self.rhaer)
@@ -1337,8 +1344,8 @@ class Sbdart:
             raise NotImplementedError("SBDART option not supported by this front end: " + "; ".join(todo))
 
     def _unsupported_surface(self):
-        if self.p["isalb"] in (7, 8, 9):
-            return [f"isalb={self.p['isalb']} (BRDF surface, spectra.f:249-1357)"]
+        if self.p["isalb"] in (7, 8, 9) and self.radcalc and self.p["corint"]:
+            return ["corint with a BRDF surface"]
         return []
 
     @staticmethod
@@ -1426,6 +1433,7 @@ class Sbdart:
                                            gwk, dtauk, dtaugc)
                 rows.append(dict(il=il, kd=kd, nk=nk, wl=wl, dwl=dwl, wt=wt, ff=ff, dtau=dtau,
                                  ssalb=wreal, pmom=pmom, flxin=flxin, amu0=amu0, rsfc=rsfc,
+                                 surf=(il if (self.surface is not None and self.surface.spectral) else 0),
                                  plank=plank, wvnmlo=wvnmlo, wvnmhi=wvnmhi))
         return rows
 
@@ -1442,6 +1450,18 @@ class Sbdart:
                  pmom=np.stack([r["pmom"] for r in rows]), bins=bins, temper=self.temper[None, :],
                  nstr=self.p["nstr"], group=g("il"))
         self._chekin_warnings(d)
+        if self.surface is not None:
+            # LAMBER = .FALSE. (drt.f:469-470): SURFAC's tables per surface; one surface per
+            # wavelength for the ocean model (wl = 20000 / (wvnmlo + wvnmhi), spectra.f:283)
+            from . import brdf
+            ids = sorted(set(int(r["surf"]) for r in rows))
+            first = {int(r["surf"]): r for r in reversed(rows)}
+            states = [brdf.ocean_state(tables(), self.surface, 20000. / (first[i]["wvnmhi"] + first[i]["wvnmlo"]))
+                      if self.surface.spectral else None for i in ids]
+            remap = {i: k for k, i in enumerate(ids)}
+            d["surf"] = np.array([remap[int(r["surf"])] for r in rows], dtype=np.int32)
+            d["surface"] = brdf.SurfaceSpec(self.surface, states, rows[0]["amu0"], bool((g("flxin") > 0).any()),
+                                            umu=self.umu if self.radcalc else None)
         if self.radcalc:
             d["umu"], d["phi"] = self.umu, self.phi
             d["corint"] = bool(self.p["corint"])
@@ -1553,12 +1573,24 @@ class Sbdart:
         """Whole-spectrum GPU path: the optical properties of every bin are produced
         by the K2 kernel and never leave the device (frontend/device.py)."""
         from .device import device_aerosols_supported, run_spectrum
-        host_solve = lambda b: solver.disort_batch(  # noqa: E731
-            b["dtauc"], b["ssalb"], b["pmom"], b["bins"], nstr=b["nstr"], temper=b["temper"],
-            umu=b.get("umu"), phi=b.get("phi"), uu_levels=b.get("uu_levels"), corint=b.get("corint", False),
-            uu_packed=True)
+        def host_solve(b):
+            bins = b["bins"]
+            if "surface" in b:          # BRDF surfaces: tables to the device, bins select them
+                from .. import quadrature, surface_albedo
+                tab = b["surface"].tables(b["nstr"], quadrature)
+                solver.set_surfaces(b["nstr"], tab["bdr"], tab["bem"], tab.get("rmu"), tab.get("emu"))
+                bins = bins.copy()
+                bins["albedo"] = surface_albedo(b["surf"])
+            try:
+                return solver.disort_batch(
+                    b["dtauc"], b["ssalb"], b["pmom"], bins, nstr=b["nstr"], temper=b["temper"],
+                    umu=b.get("umu"), phi=b.get("phi"), uu_levels=b.get("uu_levels"),
+                    corint=b.get("corint", False), uu_packed=True)
+            finally:
+                if "surface" in b:
+                    solver.set_surfaces()
         if (not device_aerosols_supported(self.aerosols) or self.p["imomc"] not in (2, 3) or
-                (self.radcalc and self.p["corint"])):
+                (self.radcalc and self.p["corint"]) or self.surface is not None):
             # table phase functions (getmom 4/5, pmaer) and the 299-moment CORINT runs:
             # optical properties on the host, solve on the GPU
             return self.run(host_solve)
@@ -1710,7 +1742,7 @@ class Sbdart:
             if nstr < 4 or nstr > NSTRMS:
                 continue
             sub = dict(b)
-            for k in ("dtauc", "ssalb", "pmom", "bins", "group"):
+            for k in ("dtauc", "ssalb", "pmom", "bins", "group") + (("surf",) if "surf" in b else ()):
                 sub[k] = b[k][idx]
             sub["nstr"] = nstr
             r2 = solve(sub)

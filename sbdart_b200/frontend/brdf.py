@@ -258,3 +258,26 @@ def surface_tables(model: SurfaceModel, state, cmu, umu0, fbeam_on, nmodes, umu=
             emu[up] = emissivity(umu[up])
         out.update(rmu=rmu, emu=emu)
     return out
+
+
+class SurfaceSpec:
+    """The BRDF surfaces of one run: one per wavelength for the ocean model, one in all
+    otherwise.  `tables(nstr)` returns SURFAC's arrays stacked over the surfaces, in the layout
+    of sbd_set_surfaces (include/sbdart_b200.h)."""
+
+    def __init__(self, model: SurfaceModel, states, umu0, fbeam_on, umu=None):
+        self.model, self.states = model, list(states)
+        self.umu0, self.fbeam_on, self.umu = float(umu0), bool(fbeam_on), umu
+        self._cache = {}
+
+    def __len__(self):
+        return len(self.states)
+
+    def tables(self, nstr, quadrature=None):
+        if nstr not in self._cache:
+            cmu = (quadrature or _gauss01)(nstr // 2)[0]
+            nmodes = nstr if self.umu is not None else 1
+            tabs = [surface_tables(self.model, st, cmu, self.umu0, self.fbeam_on, nmodes, umu=self.umu)
+                    for st in self.states]
+            self._cache[nstr] = {k: np.stack([t[k] for t in tabs]) for k in tabs[0]}
+        return self._cache[nstr]

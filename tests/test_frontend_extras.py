@@ -321,3 +321,26 @@ def test_print_and_stop_modes():
     with pytest.raises(SbdartStop) as e:
         Sbdart("&INPUT iday=-172, time=18, alat=34.4, alon=-119.8 /")
     assert e.value.text.splitlines()[1].split()[:4] == ["172", "18.000", "34.400", "-119.800"]
+
+
+def test_brdf_surface_runs_and_lambertian_limit():
+    """isalb = 7, 8, 9 (drt.f:469-477, LAMBER = .FALSE.).  A Ross-Li surface with only the
+    isotropic kernel is a Lambertian surface of that albedo: the records must be identical to the
+    isalb = 0 run (SURFAC's quadrature of a constant, disort.f:3765-3829)."""
+    from solvers import solve_oracle
+    base = "&INPUT\n idatm=4, isat=0, wlinf=.5, wlsup=.6, wlinc=.05, iout=10, sza=40, {}\n /"
+    lam = Sbdart(base.format("isalb=0, albcon=0.2")).run(solve_oracle)
+    iso = Sbdart(base.format("isalb=9, sc=0.2,0,0,1,1")).run(solve_oracle)
+    assert lam == iso
+    hap = Sbdart(base.format("isalb=8, sc=0.6,0.3,0.4,0.1")).run(solve_oracle)
+    sea = Sbdart(base.format("isalb=7, sc=0.5,6.0,34.3")).run(solve_oracle)
+    f = lambda rec: np.array(rec.split()[3:], float)      # noqa: E731
+    # same incident flux, different upward fluxes; the ocean is the darkest of the three
+    assert f(hap)[0] == f(lam)[0] == f(sea)[0]
+    assert f(sea)[1] < f(lam)[1] and f(hap)[1] != f(lam)[1]
+    # radiances: one surface per wavelength for the ocean model, every azimuth mode
+    rad = Sbdart("&INPUT\n idatm=4, isat=0, wlinf=.5, wlsup=.6, wlinc=.05, iout=20, isalb=7, sc=0.5,6.0,34.3,"
+                 " sza=40, nstr=8, uzen=0,30,60, phi=0,90,180\n /").run(solve_oracle)
+    rows = [np.array(l.split(), float) for l in rad.splitlines()[4:7]]
+    assert rows[0][0] == rows[0][1] == rows[0][2]          # nadir view: no azimuth dependence
+    assert rows[1][0] != rows[1][2]                        # sun glint side vs. the far side

@@ -114,3 +114,24 @@ def test_fortran_entry_calls_the_hosts_bdref():
     assert np.abs(out["flup"] - ref["flup"]).max() <= 1e-8 * np.abs(ref["flup"]).max()
     uu = np.transpose(out["uu"], (2, 1, 0))[:, :, :3]      # UU(iu, lu, j) -> [j][lu][iu]
     assert np.abs(uu - ref["uu"]).max() <= 1e-7 * np.abs(ref["uu"]).max()
+
+
+@pytest.mark.parametrize("nml", [
+    "&INPUT\n idatm=4, isat=0, wlinf=.4, wlsup=.7, wlinc=.02, iout=1, isalb=7, sc=0.5,6.0,34.3, sza=40, nstr=8\n /",
+    "&INPUT\n idatm=4, isat=0, wlinf=.5, wlsup=.6, wlinc=.05, iout=20, isalb=7, sc=0.5,6.0,34.3, sza=40, nstr=8,"
+    " uzen=0,30,60, phi=0,90,180\n /",
+    "&INPUT\n idatm=4, isat=0, wlinf=.5, wlsup=.6, wlinc=.05, iout=21, isalb=8, sc=0.6,0.3,0.4,0.1, sza=55,"
+    " uzen=100,130,160,180, phi=0,60,120,180\n /"])
+def test_whole_runs_with_brdf_surfaces(nml):
+    """isalb = 7 / 8 whole runs (ocean: one surface table per wavelength; iout = 21: SBDART's
+    default NSTR = 20 on the general kernel) through Sbdart.run_device: records identical to the
+    CPU checker's up to the last printed digit."""
+    from sbchk_cases import compare_records
+    from sbdart_b200.frontend import Sbdart
+    from solvers import solve_oracle
+    ref = Sbdart(nml).run(solve_oracle)
+    s = sb.Solver(0)
+    got = Sbdart(nml).run_device(s)
+    s.close()
+    nval, nexact, worst = compare_records(got, ref, rel=1.01e-4)      # one unit of the last digit
+    assert nexact >= 0.98 * nval, (nval, nexact, worst)
