@@ -17,7 +17,7 @@ is NOT here: `run()` takes a `solve(batch)` callable -- the CUDA batch solver
 
 Aerosols, zgrid, in-cloud humidity, zensun and the sensor filters live in extras.py.
 User files read from the working directory like the reference: atms.dat, albedo.dat,
-filter.dat, solar.dat.  Not covered: aerosol.dat, usrcld.dat, CKTAU (kdist=-1), BRDF
+filter.dat, solar.dat, aerosol.dat, usrcld.dat, CKATM / CKTAU (kdist=-1).  Not covered:
 spowder.
 """
 from __future__ import annotations
@@ -723,7 +723,9 @@ def depthscl(kdist, kd, nk, wl, dtaur, dtaua, waer, dtauc, wcld, gwk, dtauk, dta
     nz = len(dtaur)
     wt = gwk[kd]
     dtaug = np.zeros(nz)
-    if kdist == 0 or nk == 1:
+    if kdist == -1:                       # optical depths from CKTAU
+        dtaug = dtauk[:, kd].copy()
+    elif kdist == 0 or nk == 1:
         wt = 1.
         tsc = tglv = tgls = 0.
         for i in range(nz):
@@ -1186,6 +1188,9 @@ class Sbdart:
             p["isat"], p["wlinf"], p["wlsup"], p["wlinc"], want_filter=True)
         kdist = 0 if iout == 2 else p["kdist"]
         self.kdist = kdist
+        if kdist == -1:
+            self._setup_ck()
+            return
         if p["idatm"] == 0:                                 # atms.f:443
             z, pr, t, wh, wo = extras.useratm()
         else:
@@ -1209,6 +1214,43 @@ class Sbdart:
         if rhaer < 0.:                                      # drt.f:319
             rhaer = extras.relhum(t[0], wh[0])
         self.rhaer = rhaer
+        self._setup_levels(z, pr, t, wh, wo)
+
+    def _setup_ck(self):
+        """kdist = -1 (drt.f:321-323, gasinit taugas.f:7297-7389): the atmosphere comes from the
+        file CKATM, the gas optical depths of every spectral interval from CKTAU."""
+        from . import extras
+        p = self.p
+        z, pr, t, h2oden = extras.ckatm()
+        rhaer = p["rhaer"]
+        if rhaer < 0.:
+            rhaer = extras.relhum(t[0], h2oden)
+        self.rhaer = rhaer
+        self.cktau = extras.cktau_records(len(z))
+        if self.wl1 == self.wl2:
+            self.vnulo, self.vnuhi = 0., float(np.finfo(np.float32).max)
+        else:
+            self.vnuhi, self.vnulo = 10000. / self.wl1, 10000. / self.wl2
+        nvnu, ended = 0, False
+        for r in self.cktau:
+            if r["vnu0"] > self.vnuhi:
+                continue
+            if r["vnu0"] < self.vnulo:
+                ended = True
+                break
+            if r["ib"] == 1:
+                nvnu += 1
+        if ended and nvnu == 0:
+            raise ValueError(f"Error --- gasinit\n no frequency samples within {self.wl1} {self.wl2}")
+        self.nwl = nvnu
+        self.trace = None
+        self._setup_levels(z, pr, t, np.zeros(len(z)), np.zeros(len(z)))
+
+    def _setup_levels(self, z, pr, t, wh, wo):
+        p = self.p
+        from . import extras
+        dtor = PI_KR / 180.
+        sza = self.sza
         self.z, self.pr, self.t, self.wh, self.wo = z, pr, t, wh, wo
         nz = len(z)
         self.nz = nz
@@ -1217,7 +1259,7 @@ class Sbdart:
         self.ttemp = self.temper[0] if p["ttemp"] < 0. else p["ttemp"]
         self.nstrsv = p["nstr"]
         self.clouds = Clouds(z, p["zcloud"], p["tcloud"], p["lwp"], p["nre"], p["imomc"])
-        if p["rhcld"] >= 0:                                 # drt.f:358-364
+        if p["rhcld"] >= 0 and self.kdist >= 0:             # drt.f:357-364
             if int(p["krhclr"]) == 1:
                 extras.satcloud(self.clouds.lcld, t, p["rhcld"], wh)
             else:
@@ -1225,7 +1267,7 @@ class Sbdart:
         if p["ngrid"] < 0 or p["idatm"] < 0:                # prnatm (drt.f:803-809)
             raise SbdartStop(f"{nz:12d}\n" + "".join(
                 _f(z[i], 11, 3) + "".join(_es(v[i], 11, 3) for v in (pr, t, wh, wo)) + "\n" for i in range(nz)))
-        self.uu = absint(z, pr, t, wh, wo, self.trace)
+        self.uu = absint(z, pr, t, wh, wo, self.trace) if self.kdist >= 0 else None
         zout = np.abs(p["zout"]) if p["zout"].min() < 0 else p["zout"]
         nbot = self._nearest(z, zout[0])
         ntop = self._nearest(z, zout[1])
@@ -1327,14 +1369,10 @@ class Sbdart:
         # options of the reference this front end does not implement: fail loudly instead of
         # running something else (module docstring, "not covered")
         todo = []
-        if p["kdist"] < 0:
-            todo.append("kdist=-1 (CKATM/CKTAU k-distribution files, taugas.f:7297-7389)")
+        if p["kdist"] < -1:
+            todo.append(f"kdist={p['kdist']}")
         if p.get("spowder"):
             todo.append("spowder (sub-surface layer, drt.f:340-352)")
-        if p["nre"][0] == 0.:
-            todo.append("nre(1)=0 (usrcld.dat, taucloud.f:142-274)")
-        if p["iaer"] == -1:
-            todo.append("iaer=-1 (aerosol.dat, tauaero.f:1526-1662)")
         if p["isalb"] in (-7, -8, -9):
             todo.append(f"isalb={p['isalb']} (dref, not in the reference source either)")
         if int(p.get("ibcnd", 0)) != 0:
@@ -1342,6 +1380,38 @@ class Sbdart:
         todo += self._unsupported_surface()
         if todo:
             raise NotImplementedError("SBDART option not supported by this front end: " + "; ".join(todo))
+
+    def _usrcloud(self, wl, nmom):
+        """usrcloud (taucloud.f:142-274): cloud layers from usrcld.dat (nre(1) = 0, no tcloud / lwp).
+        Liquid water only: with a frozen water path the reference divides by its INTEGER
+        parameter rhoice = .917 -> 0 (taucloud.f:193, :244) and the optical depth is infinite."""
+        from . import extras
+        if self.p["imomc"] < 0:
+            raise ValueError("imomc < 0 not allowed with usrcld.dat option")
+        if getattr(self, "_usrcld", None) is None:
+            self._usrcld = extras.usrcloud_table(self.nz)
+        tab = self._usrcld
+        if (tab[:, 2] != 0.).any():
+            raise NotImplementedError("usrcld.dat with a frozen water path: the reference's integer rhoice = 0 "
+                                      "makes the ice optical depth infinite (taucloud.f:193, :244)")
+        nz = self.nz
+        taucld, wcld = np.zeros(nz), np.zeros(nz)
+        pmom = np.zeros((nz, nmom + 1))
+        for i in range(nz):
+            lwp, reff, cldfrac = tab[i, 0], tab[i, 1], tab[i, 4]
+            if lwp > 0.:
+                qw, ww, gw = cloudpar(wl, reff)
+                tauw = f32(.75) * qw * lwp / reff
+            else:
+                qw = ww = gw = tauw = 0.
+            taucld[i] = tauw
+            if taucld[i] != 0.:
+                wcld[i] = (tauw * ww) / taucld[i]
+                gcld = (tauw * gw) / taucld[i]
+                pmom[i] = getmom(self.p["imomc"], gcld, nmom)
+            taucld[i] = taucld[i] * cldfrac ** 1.5
+            pmom[i, 1:] = taucld[i] * wcld[i] * pmom[i, 1:]
+        return taucld, wcld, pmom
 
     def _unsupported_surface(self):
         if self.p["isalb"] in (7, 8, 9) and self.radcalc and self.p["corint"]:
@@ -1396,12 +1466,33 @@ class Sbdart:
         if self.radcalc and p["corint"]:
             nmom = MAXMOM                 # the full phase function for INTCOR (drt.f:490-491)
         rows = []
-        for il in range(self.nwl):
-            wl, wvnmhi, wvnmlo = wllimits(il, self.nwl, self.wlinc, self.wl1, self.wl2)
+        if self.kdist == -1:
+            # readk (taugas.f:7695-7760): the spectral intervals of CKTAU inside the range
+            spectrum = []
+            for r in self.cktau:
+                if r["vnu0"] < self.vnulo:
+                    break
+                if r["vnu0"] <= self.vnuhi:
+                    if min(r["vnu1"], r["vnu2"]) <= 0.:
+                        raise ValueError(f"readk --- wvnmlo,wvnmhi:  {r['vnu1']} {r['vnu2']}")
+                    if r["dtk"].min() < 0.:
+                        raise ValueError("readk --- negative dtauk")
+                    spectrum.append(r)
+        else:
+            spectrum = range(self.nwl)
+        for il, rec in enumerate(spectrum):
             amu0 = self.amu0
-            nk, gwk, dtauk, dtaugc = gasset(self.kdist, wl, self.uu, amu0, self.z, p["xo4"])
+            ib = nb = 1
+            ewcoef = 1.
+            if self.kdist == -1:
+                wl, wvnmlo, wvnmhi = 10000. / rec["vnu0"], rec["vnu1"], rec["vnu2"]
+                ib, nb, nk, ewcoef = rec["ib"], rec["nb"], rec["nk"], rec["ewc"]
+                gwk, dtauk, dtaugc = rec["gw"], rec["dtk"], None
+            else:
+                wl, wvnmhi, wvnmlo = wllimits(il, self.nwl, self.wlinc, self.wl1, self.wl2)
+                nk, gwk, dtauk, dtaugc = gasset(self.kdist, wl, self.uu, amu0, self.z, p["xo4"])
             dwl = 10000. / wvnmlo - 10000. / wvnmhi
-            etirr = self.sun(wl) * dwl
+            etirr = rec["etf"] if (self.kdist == -1 and p["nf"] == -2) else self.sun(wl) * dwl
             flxin = etirr * p["solfac"]
             if p["nf"] == 0:
                 flxin = dwl
@@ -1409,13 +1500,15 @@ class Sbdart:
                 flxin = 0.
                 amu0 = 1.
                 self.amu0 = 1.          # the reference overwrites amu0 for good (drt.f:456-459)
-            ff = self.filter(wl)
+            ff = self.filter(wl) * ewcoef
             plank = (wl > 2.) if p["nothrm"] < 0 else (p["nothrm"] == 0)
             rsfc = max(0.0, min(self.albedo(wl, self._warn), 1.0))
             pmom = np.zeros((nz, nmom + 1))
             dtauc, wcld = np.zeros(nz), np.zeros(nz)
             if self.clouds.mcldz > 0:
                 dtauc, wcld, pmom = self.clouds(wl, nmom)
+            elif p["nre"][0] == 0.:
+                dtauc, wcld, pmom = self._usrcloud(wl, nmom)
             dtaua, waer = np.zeros(nz), np.zeros(nz)
             if self.aerosols.active:
                 dtaua, waer = self.aerosols(wl, nmom, pmom)
@@ -1431,7 +1524,7 @@ class Sbdart:
             for kd in range(nk):
                 dtau, wreal, wt = depthscl(self.kdist, kd, nk, wl, dtaur, dtaua, waer, dtauc, wcld,
                                            gwk, dtauk, dtaugc)
-                rows.append(dict(il=il, kd=kd, nk=nk, wl=wl, dwl=dwl, wt=wt, ff=ff, dtau=dtau,
+                rows.append(dict(il=il, kd=kd, nk=nk, ib=ib, nb=nb, wl=wl, dwl=dwl, wt=wt, ff=ff, dtau=dtau,
                                  ssalb=wreal, pmom=pmom, flxin=flxin, amu0=amu0, rsfc=rsfc,
                                  surf=(il if (self.surface is not None and self.surface.spectral) else 0),
                                  plank=plank, wvnmlo=wvnmlo, wvnmhi=wvnmhi))
@@ -1590,7 +1683,8 @@ class Sbdart:
                 if "surface" in b:
                     solver.set_surfaces()
         if (not device_aerosols_supported(self.aerosols) or self.p["imomc"] not in (2, 3) or
-                (self.radcalc and self.p["corint"]) or self.surface is not None):
+                (self.radcalc and self.p["corint"]) or self.surface is not None or self.kdist < 0 or
+                (self.clouds.mcldz == 0 and self.p["nre"][0] == 0.)):
             # table phase functions (getmom 4/5, pmaer) and the 299-moment CORINT runs:
             # optical properties on the host, solve on the GPU
             return self.run(host_solve)
@@ -1634,8 +1728,12 @@ class Sbdart:
             rfldir, rfldn, flup = res["rfldir"][ib], res["rfldn"][ib], res["flup"][ib]
             dwt = r["wt"] * r["ff"]
             kd, nk = r["kd"] + 1, r["nk"]
+            # sub-bands of the CKTAU files: a wavelength starts with (kd = 1, ib = nb) and is
+            # finished with (kd = nk, ib = 1) (drt.f:967, :989); ib = nb = 1 otherwise
+            first = kd == 1 and r.get("ib", 1) == r.get("nb", 1)
+            last = kd == nk and r.get("ib", 1) == 1
             if iout in (1, 5, 6):
-                if kd == 1:
+                if first:
                     topdn = topup = topdir = botdn = botup = botdir = 0.0
                     weq = wfull = 0.0
                 topdn += (rfldn[ntop] + rfldir[ntop]) * dwt
@@ -1647,16 +1745,17 @@ class Sbdart:
                 if kd == nk:
                     weq += r["dwl"] * r["ff"]
                     wfull += r["dwl"]
+                if last:
                     if weq == 0.:
                         weq = f32(1.e-30)
                     out.append(_f(r["wl"], 12, 8) + _f(weq / wfull, 9, 5) + "".join(
                         _es(_r4(x / weq), 12, 4) for x in (topdn, topup, topdir, botdn, botup, botdir)))
                 if iout in (5, 6):
                     j = ntop if iout == 5 else nbot
-                    if kd == 1:
+                    if first:
                         uurs[:] = 0.
                     uurs += res["uu"][ib][:, uslot(j), :].T * dwt
-                    if kd == nk:
+                    if last:
                         out.append(f"{self.nphi:4d}{self.nzen:4d}")
                         out += self._rows([_r4(x) for x in self.phi], 10)
                         out += self._rows([_r4(x) for x in self.uzen], 10)
@@ -1665,12 +1764,12 @@ class Sbdart:
             if iout in (10, 11, 20, 21, 22, 23) and kd == nk:
                 phidw += r["dwl"] * r["ff"]
             if iout in (7, 11, 22):
-                if iout == 7 and kd == 1:
+                if iout == 7 and first:
                     fxdn[:] = fxup[:] = fxdir[:] = 0.
                 fxdn += (rfldn[1:nz + 1] + rfldir[1:nz + 1]) * dwt
                 fxup += flup[1:nz + 1] * dwt
                 fxdir += rfldir[1:nz + 1] * dwt
-            if iout == 7 and kd == nk:
+            if iout == 7 and last:
                 out += ["", "", _f(r["wl"], 12, 8)]
                 for arr in (self.z[::-1], [_r4(x) for x in fxdir], [_r4(x) for x in fxdn - fxdir],
                             [_r4(x) for x in fxdn], [_r4(x) for x in fxup]):

@@ -42,6 +42,8 @@ STRAT_DTYPE = np.dtype([("layer", "<f8"), ("taerst", "<f8"), ("ext", "<f8", 47),
 def device_aerosols_supported(aer):
     """The producer kernel evaluates getmom(2|3) only; table phase functions (imoma 4, 5)
     and user moments (pmaer) stay on the host path."""
+    if aer.iaer == -1:          # aerosol.dat is read on the host
+        return False
     return (not aer.active) or aer.iaer <= 0 or aer.imoma in (2, 3)
 
 

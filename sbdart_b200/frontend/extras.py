@@ -78,6 +78,192 @@ def rdspec(path, nmax=5000):
     return np.ascontiguousarray(a[:, 0]), np.ascontiguousarray(a[:, 1])
 
 
+class ListReader:
+    """List-directed sequential READs of a formatted file (`read(u,*) a, b, ...`): every READ
+    starts on a new line and takes as many lines as its item list needs; what is left of
+    the last line is skipped.  read() returns None at end of file (the END= branch)."""
+
+    def __init__(self, path):
+        with open(path) as f:
+            self.lines = [[t for t in ln.replace(",", " ").split() if t] for ln in f]
+        self.pos = 0
+
+    def rewind(self):
+        self.pos = 0
+
+    def read(self, nitems):
+        vals = []
+        while len(vals) < nitems:
+            if self.pos >= len(self.lines):
+                return None
+            tok = self.lines[self.pos]
+            self.pos += 1
+            if "/" in tok:                       # a slash ends the record: the rest keeps its value
+                vals += tok[:tok.index("/")]
+                vals += [None] * (nitems - len(vals))
+                break
+            vals += tok
+        return [None if v is None else float(v.lower().replace("d", "e")) for v in vals[:nitems]]
+
+
+class AerosolFile:
+    """aeread (tauaero.f:1526-1714): boundary-layer aerosols from aerosol.dat (iaer = -1).
+
+    File: `nn nmom`, then per wavelength `wl` and nn records `taer waer pm(1..nmom)` for the
+    levels ns = nz-nn+1 .. nz (top-down layer index, nz = surface).  The reference keeps two
+    wavelength slots (ind, 3-ind) and reads forward as the requested wavelength grows; that
+    state machine is reproduced as it stands, including its treatment of a first wavelength
+    at or below the file's first one (the record is then taken as spectrally uniform between
+    wl/2 and 2 wl, and later records are still read)."""
+
+    def __init__(self, nz, imoma, path="aerosol.dat"):
+        self.nz, self.imoma = nz, imoma
+        self.f = ListReader(path)
+        self.wlbaer = [0.0, 0.0]
+        self.wl0 = 0.0
+        self.ind, self.more = 1, 1
+        self.taer = np.zeros((nz + 1, 3))
+        self.waer = np.zeros((nz + 1, 3))
+        self.gaer = None
+
+    def _layer_block(self, slot, zero_first):
+        for i in range(self.ns, self.nz + 1):
+            if zero_first:
+                self.taer[i, slot] = 0.; self.waer[i, slot] = 0.; self.gaer[:, i, slot] = 0.
+            rec = self.f.read(2 + self.nmom)
+            if rec is None:
+                raise ValueError(f"not enough aerosol records\n need {self.nz - self.ns + 1} records")
+            self.taer[i, slot], self.waer[i, slot] = rec[0], rec[1]
+            self.gaer[:, i, slot] = rec[2:]
+
+    def __call__(self, wl, nmom_out, pmom):
+        """Adds the aerosol moments x scattering depth to pmom[nz][nmom_out+1]; returns dtau, wbaer."""
+        nz = self.nz
+        if self.wlbaer[0] == 0.:
+            hdr = self.f.read(2)
+            nn, self.nmom = int(hdr[0]), int(hdr[1])
+            self.ns = nz - nn + 1
+            if self.ns <= 0:
+                raise ValueError(f"nz  nn {nz} {nn}\n too many layers specified in aerosol.dat")
+            self.gaer = np.zeros((self.nmom, nz + 1, 3))
+            first = self.f.read(1)
+            if first is None:
+                raise ValueError("no data found in aerosol.dat")
+            self.wlbaer[0] = first[0]
+            self.wl0 = self.wlbaer[0]
+            self._layer_block(1, False)
+            self.ind = 1
+        elif wl < min(self.wlbaer) and wl > self.wl0:
+            self.f.rewind()
+            self.f.read(2)
+            self.wlbaer[0] = self.f.read(1)[0]
+            self._layer_block(1, True)
+            self.wlbaer[1] = 0.
+            self.ind, self.more = 1, 1
+        if self.more == 1:
+            hit_eof = False
+            while wl > max(self.wlbaer):
+                self.more = 0
+                rec = self.f.read(1)
+                if rec is None:
+                    hit_eof = True
+                    break
+                self.ind = 3 - self.ind
+                self._layer_block(self.ind, True)
+                self.wlbaer[self.ind - 1] = rec[0]
+            if not hit_eof:
+                self.more = 1
+        ns, ind, oth = self.ns, self.ind, 3 - self.ind
+        if self.wlbaer[1] == 0.:
+            self.wlbaer = [.5 * wl, 2 * wl]
+            self.taer[ns:, 2] = self.taer[ns:, 1]
+            self.waer[ns:, 2] = self.waer[ns:, 1]
+            self.gaer[:, ns:, 2] = self.gaer[:, ns:, 1]
+            self.wl0 = 0.
+        wt = math.log(wl / self.wlbaer[ind - 1]) / math.log(self.wlbaer[oth - 1] / self.wlbaer[ind - 1])
+        wt = max(0.0, min(wt, 1.0))
+        dtau, wbaer = np.zeros(nz), np.zeros(nz)
+        from . import getmom, MAXMOM
+        for i in range(ns, nz + 1):
+            ta, tb = self.taer[i, ind], self.taer[i, oth]
+            if min(ta, tb) > 0.:
+                dtau[i - 1] = ta * (tb / ta) ** wt
+            else:
+                dtau[i - 1] = ta * (1. - wt) + tb * wt
+            wbaer[i - 1] = self.waer[i, ind] * (1. - wt) + self.waer[i, oth] * wt
+            if self.nmom == 1:
+                gg = self.gaer[0, i, ind] * (1. - wt) + self.gaer[0, i, oth] * wt
+                pm = getmom(self.imoma, gg, MAXMOM)[1:]
+            else:
+                pm = self.gaer[:, i, ind] * (1. - wt) + self.gaer[:, i, oth] * wt
+            m = min(len(pm), nmom_out)
+            pmom[i - 1, 1:m + 1] += pm[:m] * dtau[i - 1] * wbaer[i - 1]
+        return dtau, wbaer
+
+
+def usrcloud_table(nz, path="usrcld.dat"):
+    """The file part of usrcloud (taucloud.f:203-211): records lwp, reff, fwp, reice, cldfrac from
+    the lowest layer upwards; missing records and items behind a slash keep the defaults
+    0, 8, 0, -1, 1.  Returned arrays are indexed like the reference's (1 = top layer)."""
+    tab = np.tile(np.array([0., 8., 0., -1., 1.]), (nz, 1))
+    f = ListReader(path)
+    for i in range(nz, 0, -1):
+        rec = f.read(5)
+        if rec is None:
+            break
+        for k, v in enumerate(rec):
+            if v is not None:
+                tab[i - 1, k] = v
+    return tab
+
+
+# ------------------------------------------------------------------ k-distribution files
+def ckatm(path="CKATM"):
+    """gasinit, first part (taugas.f:7309-7330): `nz h2oden`, then z(1:nz), p(1:nz), t(1:nz)
+    (list-directed).  Returns bottom-up z, p, t and the surface water-vapour density."""
+    f = ListReader(path)
+    hdr = f.read(2)
+    nz, h2oden = int(hdr[0]), hdr[1]
+    if nz > MXLY:
+        raise ValueError(f"gasinit --- nz gt mxly {nz} {MXLY}")
+    z, p, t = (np.array(f.read(nz)) for _ in range(3))
+    if z[0] > z[-1]:
+        z, p, t = z[::-1].copy(), p[::-1].copy(), t[::-1].copy()
+    return z, p, t, h2oden
+
+
+def cktau_records(nz, path="CKTAU"):
+    """The records of the unformatted sequential file CKTAU (readk, taugas.f:7723-7725):
+    iv, ib, nb, nk (integers), vnu0, vnu1, vnu2, etf, ewc, gw(1:nk), dtk(1:nz,1:nk) (REAL*4),
+    each between two 4-byte record lengths."""
+    recs = []
+    with open(path, "rb") as f:
+        raw = f.read()
+    pos = 0
+    while pos + 4 <= len(raw):
+        n = int(np.frombuffer(raw, "<i4", 1, pos)[0])
+        body = raw[pos + 4: pos + 4 + n]
+        pos += 8 + n
+        iv, ib, nb, nk = (int(v) for v in np.frombuffer(body, "<i4", 4, 0))
+        fl = np.frombuffer(body, "<f4", 5 + nk + nz * nk, 16).astype(float)
+        recs.append(dict(iv=iv, ib=ib, nb=nb, nk=nk, vnu0=fl[0], vnu1=fl[1], vnu2=fl[2], etf=fl[3], ewc=fl[4],
+                         gw=fl[5:5 + nk].copy(), dtk=fl[5 + nk:].reshape(nk, nz).T.copy()))
+    return recs
+
+
+def write_cktau(path, recs):
+    """Writes records in the layout cktau_records reads (test fixtures, converters)."""
+    with open(path, "wb") as f:
+        for r in recs:
+            nk = len(r["gw"])
+            body = np.array([r["iv"], r["ib"], r["nb"], nk], "<i4").tobytes()
+            body += np.array([r["vnu0"], r["vnu1"], r["vnu2"], r["etf"], r["ewc"]], "<f4").tobytes()
+            body += np.asarray(r["gw"], "<f4").tobytes()
+            body += np.asarray(r["dtk"], "<f4").T.copy().tobytes()       # dtk(1:nz, 1:nk), column-major
+            n = np.array([len(body)], "<i4").tobytes()
+            f.write(n + body + n)
+
+
 # ------------------------------------------------------------------ vertical grid
 def zgrid(z, p, t, wh, wo, zgrid1, zgrid2, ngrid):
     """Regrid the model atmosphere to |ngrid| levels (atms.f:505-617).  Arrays are
@@ -306,8 +492,7 @@ class Aerosols:
         self.nz = len(z)
         self.npmaer = 0
         self.nwlbaer = NAERW
-        if self.iaer == -1:
-            raise NotImplementedError("iaer=-1 (aerosol.dat)")
+        self.afile = AerosolFile(self.nz, self.imoma) if self.iaer == -1 else None
         if self.iaer < -1 or self.iaer > 5:
             raise ValueError("iaer out of range [-1,5]")
         if self.jaer.min() < 0 or self.jaer.max() > 4:
@@ -555,6 +740,8 @@ class Aerosols:
             waer[:] = wa
             m = min(namom, nmom)
             pmom[:, 1:m + 1] += (pm[None, 1:m + 1] * dtauab[:, None]) * waer[:, None]
+        elif self.iaer == -1:                 # aerosol.dat (tauaero.f:1250-1254)
+            dtauab, waer = self.afile(wl, nmom, pmom)
         dtaua = dtauab.copy()
         for i in range(NAERZ):
             if self.jaer[i] != 0 and self.taerst[i] > 0.:
