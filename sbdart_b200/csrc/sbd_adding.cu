@@ -68,11 +68,14 @@ struct AddLayout {
     // functionals of the layer's top interface: fu = D^T Rb, cu = c^T Rb, D^T sb, c^T sb
     static constexpr int o_Y = 0, o_y = n * n, o_fu = n * n + n, o_cu = n * n + 2 * n, o_f0 = n * n + 3 * n;
     static_assert(n * n + 3 * n + 2 <= rec, "phase-2 record must fit into the phase-1 record");
-    // 2-D tiling of phase 2: n rows x CG column groups, CW columns per lane
-    static constexpr int CG = n >= 4 ? 4 : n;
+    // 2-D tiling of phase 2: n rows x CG column groups, CW columns per lane (n CG <= 32 lanes)
+    static constexpr int CG = n >= 10 ? 2 : (n >= 4 ? 4 : n);
     static constexpr int CW = n / CG;
+    // phase 1: a layer is owned by a group of GW lanes (the n first ones hold a row / column /
+    // mode each; for n = 10, 12 the rest shadow lane n-1)
+    static constexpr int GW = n <= 2 ? 2 : (n <= 4 ? 4 : (n <= 8 ? 8 : 16));
     // phase-1 shared memory per layer group: gl[N], K, L, P, X [n][n], 4 vectors
-    static constexpr int tasks = 32 / n;
+    static constexpr int tasks = 32 / GW;
     static constexpr int task0 = N + 4 * n * n + 4 * n;
     // padded to 4 (mod 16) doubles: the groups' areas start 8 banks apart, so the four
     // addresses of a group-wide broadcast load never share a bank
@@ -100,9 +103,10 @@ __device__ __forceinline__ double add_group_sum(double v)
 }
 
 template <int n>
-__device__ __forceinline__ unsigned add_jacobi_partners(int g)
+__device__ __forceinline__ unsigned long long add_jacobi_partners(int g)
 {
-    unsigned pk = 0;
+    constexpr int PB = n > 8 ? 4 : 3;          // bits per round
+    unsigned long long pk = 0;
 #pragma unroll
     for (int r = 0; r < n - 1; r++) {
         int partner;
@@ -113,13 +117,14 @@ __device__ __forceinline__ unsigned add_jacobi_partners(int g)
             if (partner >= n - 1) partner -= n - 1;
             if (partner >= n - 1) partner -= n - 1;
         }
-        pk |= (unsigned)partner << (3 * r);
+        pk |= (unsigned long long)partner << (PB * r);
     }
     return pk;
 }
 
 // ---------------------------------------------------------------------------
-// phase 1: one layer per group of n lanes; lane g holds row g / column g / mode g
+// phase 1: one layer per group of GW lanes; lane g < n holds row g / column g / mode g
+// (gact = false: a shadow of lane n-1 that computes along and stores nothing)
 // ---------------------------------------------------------------------------
 template <int n>
 __device__ __forceinline__ int phase1_adding(
@@ -128,10 +133,10 @@ __device__ __forceinline__ int phase1_adding(
     double fbeam, double umu0, bool plank,
     const double *cmu, const double *csq, const double *cd, const double *cylm,
     const double *y0, const double *ebeam, const double *pk,
-    double *tsm, double *rec, int g, unsigned jpart)
+    double *tsm, double *rec, int g, bool gact, unsigned long long jpart)
 {
     using AL = AddLayout<n>;
-    constexpr int N = 2 * n;
+    constexpr int N = 2 * n, GW = AL::GW, PB = n > 8 ? 4 : 3;
     double *sgl = tsm, *sK = sgl + N, *sL = sK + n * n, *sP = sL + n * n, *sX = sP + n * n, *sv = sX + n * n;
 
     double ss = ssalb[lc];
@@ -146,7 +151,7 @@ __device__ __forceinline__ int phase1_adding(
     for (int h = 0; h < 2; h++) {
         int l = g + h * n;
         double pm = (l == 0) ? 1.0 : pmom[(size_t)lc * ldp + l];
-        sgl[l] = (2 * l + 1) * oprim * (pm - f) * rf;
+        if (gact) sgl[l] = (2 * l + 1) * oprim * (pm - f) * rf;
     }
     __syncwarp();
 
@@ -184,10 +189,10 @@ __device__ __forceinline__ int phase1_adding(
         double nume = pe[j], numo = po[j];
 #pragma unroll
         for (int k = 0; k < j; k++) {
-            nume = fma(-pe[k], shfl_d(pe[k], j, n), nume);
-            numo = fma(-po[k], shfl_d(po[k], j, n), numo);
+            nume = fma(-pe[k], shfl_d(pe[k], j, GW), nume);
+            numo = fma(-po[k], shfl_d(po[k], j, GW), numo);
         }
-        double pive = shfl_d(nume, j, n), pivo = shfl_d(numo, j, n);
+        double pive = shfl_d(nume, j, GW), pivo = shfl_d(numo, j, GW);
         if (!(pivo > 0.0)) { bad = 1; pivo = 1.0; }
         // Pe is only semidefinite when w' -> 1: keep the factor real (a NaN pivot is a failure)
         const double floor_e = 1.0e-30;
@@ -198,8 +203,10 @@ __device__ __forceinline__ int phase1_adding(
         pe[j] = (g == j) ? pive * rie : ((g > j) ? nume * rie : 0.0);
         po[j] = (g == j) ? pivo * rio : ((g > j) ? numo * rio : 0.0);
     }
+    if (gact) {
 #pragma unroll
-    for (int j = 0; j < n; j++) { sK[g * n + j] = pe[j]; sL[g * n + j] = po[j]; }
+        for (int j = 0; j < n; j++) { sK[g * n + j] = pe[j]; sL[g * n + j] = po[j]; }
+    }
     __syncwarp();
 
     // column g of A = K^T L
@@ -226,13 +233,13 @@ __device__ __forceinline__ int phase1_adding(
             int big = 0;
 #pragma unroll 1
             for (int r = 0; r < n - 1; r++) {
-                const int partner = (jpart >> (3 * r)) & 7;
+                const int partner = (int)((jpart >> (PB * r)) & ((1u << PB) - 1u));
                 double pa[n];
                 double g0 = 0.0, g1 = 0.0;
-                const double oth2 = shfl_d(own2, partner, n);
+                const double oth2 = shfl_d(own2, partner, GW);
 #pragma unroll
                 for (int i = 0; i < n; i++) {
-                    pa[i] = shfl_d(a[i], partner, n);
+                    pa[i] = shfl_d(a[i], partner, GW);
                     if (i & 1) g1 = fma(a[i], pa[i], g1); else g0 = fma(a[i], pa[i], g0);
                 }
                 const double gam = g0 + g1;
@@ -277,8 +284,10 @@ __device__ __forceinline__ int phase1_adding(
         for (int k = i + 1; k < n; k++) acc = fma(-sK[k * n + i], P[k], acc);
         P[i] = acc * rK[i];
     }
+    if (gact) {
 #pragma unroll
-    for (int i = 0; i < n; i++) sP[g * n + i] = P[i];         // [mode][direction]
+        for (int i = 0; i < n; i++) sP[g * n + i] = P[i];     // [mode][direction]
+    }
 
     // ---- particular solutions in the scaled variables (u^ = D u) ------------------------
     // beam (UPBEAM, disort.f:4130, spectral form): with c_j = (P^T r)_j / (1/mu0^2 - k_j^2),
@@ -298,31 +307,31 @@ __device__ __forceinline__ int phase1_adding(
         }
         const double bs = 2.0 * fac * sqg * be;
         bdg = 2.0 * fac * sqg * bo;
-        sv[g] = bdg;
+        if (gact) sv[g] = bdg;
         __syncwarp();
         double t1 = 0.0;                                    // (K^T b_d)_g
 #pragma unroll
         for (int k = 0; k < n; k++) t1 = fma(sK[k * n + g], sv[k], t1);
-        sv[n + g] = t1;
+        if (gact) sv[n + g] = t1;
         __syncwarp();
         double t2 = 0.0;                                    // (K K^T b_d)_g
 #pragma unroll
         for (int k = 0; k < n; k++) t2 = fma(sK[g * n + k], sv[n + k], t2);
-        sv[2 * n + g] = bs * rmu0 - t2;                     // r_g
+        if (gact) sv[2 * n + g] = bs * rmu0 - t2;           // r_g
         __syncwarp();
         double cj = 0.0;
 #pragma unroll
         for (int i = 0; i < n; i++) cj = fma(P[i], sv[2 * n + i], cj);
         cj = cj * fast_rcp(rmu0 * rmu0 - s2);
-        sv[3 * n + g] = cj;
+        if (gact) sv[3 * n + g] = cj;
         __syncwarp();
 #pragma unroll
         for (int j = 0; j < n; j++) tg = fma(sP[j * n + g], sv[3 * n + j], tg);     // (P c)_g
-        sv[g] = tg;
+        if (gact) sv[g] = tg;
     } else {
         __syncwarp();
     }
-    sv[n + g] = cmu[g] * csq[g];                            // D_g
+    if (gact) sv[n + g] = cmu[g] * csq[g];                  // D_g
     __syncwarp();
     // Po^-1 [P c | D 1]: every lane runs both triangular solves (L y = b, L^T z = y)
     double zq[n];                                            // q^ (all entries, uniform in the group)
@@ -382,7 +391,7 @@ __device__ __forceinline__ int phase1_adding(
     for (int j = 0; j < n; j++) {
         double pr[n], qr[n];
 #pragma unroll
-        for (int c = 0; c < n; c++) { pr[c] = shfl_d(bp[c], j, n); qr[c] = shfl_d(bm[c], j, n); }
+        for (int c = 0; c < n; c++) { pr[c] = shfl_d(bp[c], j, GW); qr[c] = shfl_d(bm[c], j, GW); }
         const double rp = fast_rcp(pr[j]), rq = fast_rcp(qr[j]);
         if (!(pr[j] > 0.0) || !(qr[j] > 0.0)) bad = 1;
         const double mp = bp[j] * rp, mq = bm[j] * rq;
@@ -415,10 +424,12 @@ __device__ __forceinline__ int phase1_adding(
             }
         }
         __syncwarp();           // everyone is done reading K
+        if (gact) {
 #pragma unroll
-        for (int b = 0; b < n; b++) { sK[g * n + b] = up[b]; sX[g * n + b] = um[b]; }
+            for (int b = 0; b < n; b++) { sK[g * n + b] = up[b]; sX[g * n + b] = um[b]; }
+        }
     }
-    sv[g] = zup; sv[n + g] = zdn;
+    if (gact) { sv[g] = zup; sv[n + g] = zdn; }
     __syncwarp();
     // M+- = P U+- (row a = g): R = -I + M+ + M-, T = M+ - M-
     double R[n], T[n], mm[n];
@@ -477,7 +488,7 @@ __device__ __forceinline__ int phase1_adding(
         s_up += (Dg - RD) * pk[lc] - TD * pk[lc + 1] + e;
         s_dn += (Dg - RD) * pk[lc + 1] - TD * pk[lc] - e;
     }
-    if (active) {
+    if (active && gact) {
 #pragma unroll
         for (int b = 0; b < n; b += 2) {
             reinterpret_cast<double2 *>(rec + AL::r_R + g * n)[b / 2] = make_double2(R[b], R[b + 1]);
@@ -492,12 +503,14 @@ __device__ __forceinline__ int phase1_adding(
 
 // WARPS warps per CTA, 16 warps per SM; the warps of a CTA move through the phases together
 // (one instruction stream in the I-cache at a time, see sbd_fast.cu).
+// (n > 8: 4-warp CTAs, two per SM, up to 255 registers)
 template <int n, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, 16 / WARPS)
+__global__ void __launch_bounds__(WARPS * 32, n > 8 ? 2 : 16 / WARPS)
 disort_adding_kernel(const LaunchArgs a)
 {
     using AL = AddLayout<n>;
-    constexpr int N = 2 * n, TASKS = 32 / n, CG = AL::CG, CW = AL::CW;
+    constexpr int N = 2 * n, TASKS = AL::tasks, GW = AL::GW, CG = AL::CG, CW = AL::CW;
+    constexpr int KB = n > 8 ? 4 : 3, KM = (1 << KB) - 1;       // pivot key: row index bits
     const int L = a.d.nlyr;
     const int NT = L + 1;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
@@ -529,10 +542,11 @@ disort_adding_kernel(const LaunchArgs a)
 
     const int slot = blockIdx.x * warps + warp;
     double *recs = a.scratch + (size_t)slot * a.slot_stride;      // [L][rec]
-    const int g = lane % n, task = lane / n;
+    const bool gact = (lane % GW) < n;
+    const int g = gact ? lane % GW : n - 1, task = lane / GW;
     const int nbins_all = a.nbins_dev ? *a.nbins_dev : a.d.nbins;
     double *tsm = work + (size_t)task * AL::task;
-    const unsigned jpart = add_jacobi_partners<n>(g);
+    const unsigned long long jpart = add_jacobi_partners<n>(g);
     // phase-2 tiling: row i2, column group p2 (lanes beyond n*CG shadow the last row)
     const bool act2 = lane < n * CG;
     const int i2 = act2 ? lane / CG : n - 1, p2 = lane % CG, c0 = p2 * CW;
@@ -686,7 +700,7 @@ disort_adding_kernel(const LaunchArgs a)
                 if (!active) lc = ncut - 1;
                 int st = phase1_adding<n>(dtauc, ssalb, pmom, ldp, lc, active, fbeam, umu0, plank,
                                           cmu, csq, cd, cylm, y0, ebeam, pk, tsm,
-                                          recs + (size_t)lc * AL::rec, g, jpart);
+                                          recs + (size_t)lc * AL::rec, g, gact, jpart);
                 if (__any_sync(FULLMASK, st != 0)) { status = SBD_BIN_EIG_FAIL; break; }
             }
         }
@@ -780,10 +794,10 @@ disort_adding_kernel(const LaunchArgs a)
                     (void)used;
 #else
                     const int key = (act2 && !((used >> i2) & 1u))
-                                        ? ((__double2hiint(colv) & 0x7ffffff8) | (7 - i2)) : -1;
+                                        ? ((__double2hiint(colv) & ~KM & 0x7fffffff) | (KM - i2)) : -1;
                     const int mx = __reduce_max_sync(FULLMASK, key);
-                    if ((mx >> 3) <= 0) sing = 1;
-                    const int ip = 7 - (mx & 7);
+                    if ((mx >> KB) <= 0) sing = 1;
+                    const int ip = KM - (mx & KM);
                     used |= 1u << ip;
 #endif
                     const int srcl = ip * CG + p2;
@@ -856,19 +870,21 @@ disort_adding_kernel(const LaunchArgs a)
                 }
                 __syncwarp();
                 // ---- flux functionals of interface lc: D^T Rb, c^T Rb, D^T sb, c^T sb ----
-                if (lane < 2 * n) {
-                    const double *wv = (lane < n) ? cd : csq;
-                    const int c = lane % n;
-                    double acc = 0.0;
+                for (int e = lane; e < 2 * n + 2; e += 32) {
+                    if (e < 2 * n) {
+                        const double *wv = (e < n) ? cd : csq;
+                        const int c = e % n;
+                        double acc = 0.0;
 #pragma unroll
-                    for (int k = 0; k < n; k++) acc = fma(wv[k], sRb[k * n + c], acc);
-                    orec[(lane < n ? AL::o_fu : AL::o_cu) + c] = acc;
-                } else if (lane < 2 * n + 2) {
-                    const double *wv = (lane == 2 * n) ? cd : csq;
-                    double acc = 0.0;
+                        for (int k = 0; k < n; k++) acc = fma(wv[k], sRb[k * n + c], acc);
+                        orec[(e < n ? AL::o_fu : AL::o_cu) + c] = acc;
+                    } else {
+                        const double *wv = (e == 2 * n) ? cd : csq;
+                        double acc = 0.0;
 #pragma unroll
-                    for (int k = 0; k < n; k++) acc = fma(wv[k], ssb[k], acc);
-                    orec[AL::o_f0 + (lane - 2 * n)] = acc;
+                        for (int k = 0; k < n; k++) acc = fma(wv[k], ssb[k], acc);
+                        orec[AL::o_f0 + (e - 2 * n)] = acc;
+                    }
                 }
             }
         }
@@ -967,7 +983,10 @@ extern "C" void sbd_debug_add_ticks(unsigned long long *out, int reset)
 #endif
 
 // ---- host-side launch helpers ---------------------------------------------
-bool adding_supported(int N) { return N == 4 || N == 8 || N == 16; }
+bool adding_supported(int N) { return N == 4 || N == 8 || N == 16 || N == 20 || N == 24 || N == 32; }
+
+// resident warps per SM the register budget allows (launch bounds): 16 up to NSTR = 16, 8 above
+int adding_warps_per_sm(int N) { return N > 16 ? 8 : 16; }
 
 size_t adding_slot_doubles(int N, int L)
 {
@@ -975,6 +994,9 @@ size_t adding_slot_doubles(int N, int L)
     case 4: return AddLayout<2>::slot_doubles(L);
     case 8: return AddLayout<4>::slot_doubles(L);
     case 16: return AddLayout<8>::slot_doubles(L);
+    case 20: return AddLayout<10>::slot_doubles(L);
+    case 24: return AddLayout<12>::slot_doubles(L);
+    case 32: return AddLayout<16>::slot_doubles(L);
     }
     return 0;
 }
@@ -985,6 +1007,9 @@ size_t adding_smem_bytes(int N, int L, int warps)
     case 4: return 8 * (AddLayout<2>::cta + (size_t)warps * AddLayout<2>::warp_doubles(L));
     case 8: return 8 * (AddLayout<4>::cta + (size_t)warps * AddLayout<4>::warp_doubles(L));
     case 16: return 8 * (AddLayout<8>::cta + (size_t)warps * AddLayout<8>::warp_doubles(L));
+    case 20: return 8 * (AddLayout<10>::cta + (size_t)warps * AddLayout<10>::warp_doubles(L));
+    case 24: return 8 * (AddLayout<12>::cta + (size_t)warps * AddLayout<12>::warp_doubles(L));
+    case 32: return 8 * (AddLayout<16>::cta + (size_t)warps * AddLayout<16>::warp_doubles(L));
     }
     return 0;
 }
@@ -1003,9 +1028,10 @@ template <int n>
 static cudaError_t launch_adding_t(const LaunchArgs &a, int warps, int grid, cudaStream_t st)
 {
     const size_t smem = 8 * (AddLayout<n>::cta + (size_t)warps * AddLayout<n>::warp_doubles(a.d.nlyr));
+    if (n > 8) return warps == 4 ? launch_adding_k<n, 4>(a, grid, smem, st) : cudaErrorInvalidValue;
     switch (warps) {
     case 4: return launch_adding_k<n, 4>(a, grid, smem, st);
-    case 8: return launch_adding_k<n, 8>(a, grid, smem, st);
+    case 8: return launch_adding_k<(n > 8 ? 8 : n), 8>(a, grid, smem, st);
     }
     return cudaErrorInvalidValue;
 }
@@ -1016,6 +1042,9 @@ cudaError_t launch_adding(const LaunchArgs &a, int warps, int grid, cudaStream_t
     case 4: return launch_adding_t<2>(a, warps, grid, st);
     case 8: return launch_adding_t<4>(a, warps, grid, st);
     case 16: return launch_adding_t<8>(a, warps, grid, st);
+    case 20: return launch_adding_t<10>(a, warps, grid, st);
+    case 24: return launch_adding_t<12>(a, warps, grid, st);
+    case 32: return launch_adding_t<16>(a, warps, grid, st);
     }
     return cudaErrorInvalidValue;
 }

@@ -303,14 +303,15 @@ extern "C" int sbd_disort_batch_device(sbd_handle *h, const sbd_dims *dims, cons
     // general kernel implement them
     const bool brdf = h->sf_count > 0;
     if (brdf && (h->sf_nstr != N || (NU > 0 && (h->sf_modes != N || h->sf_numu != NU)))) return SBD_ERR_ARG;
-    const bool adding_ok = adding_supported(N) && NU == 0 && dims->ntau == 0;
-    const bool fast = fast_supported(N) && (NU == 0 || dims->ntau == 0) && !getenv("SBD_FORCE_GENERIC") &&
-                      (!brdf || adding_ok);
-    // adding kernel: NSTR 4/8/16, fluxes at the layer boundaries (SBD_FORCE_ELIM: the elimination
-    // kernel instead -- a tuning / comparison knob, not API)
-    const bool adding = fast && adding_ok && (brdf || !getenv("SBD_FORCE_ELIM"));
+    // adding kernel: fluxes at the layer boundaries, NSTR 4/8/16/20/24/32.  Tuning / comparison
+    // knobs (not API): SBD_FORCE_ELIM = the elimination kernels instead, SBD_FORCE_GENERIC = the
+    // general kernel for everything
+    const bool adding_ok = adding_supported(N) && NU == 0 && dims->ntau == 0 && !getenv("SBD_FORCE_GENERIC");
+    const bool adding = adding_ok && (brdf || !getenv("SBD_FORCE_ELIM"));
+    // elimination register kernel: NSTR 4/8/16; radiances at the layer boundaries (the mode SBDART uses)
+    const bool fast = !adding && !brdf && fast_supported(N) && (NU == 0 || dims->ntau == 0) && !getenv("SBD_FORCE_GENERIC");
     // CTA-per-bin register kernel: NSTR 20/24/32, fluxes
-    const bool wide = !fast && !brdf && wide_supported(N) && NU == 0 && !getenv("SBD_FORCE_GENERIC") &&
+    const bool wide = !adding && !fast && !brdf && wide_supported(N) && NU == 0 && !getenv("SBD_FORCE_GENERIC") &&
                       wide_smem_bytes(N, L, NT) <= smem_limit;
     int warps, grid;
     size_t slot;
@@ -322,16 +323,18 @@ extern "C" int sbd_disort_batch_device(sbd_handle *h, const sbd_dims *dims, cons
         grid = h->sm_count * cta_per_sm;
         warps = 1;                                   // scratch slots and work items per CTA
         slot = wide_slot_doubles(N, L);
-    } else if (fast) {
+    } else if (fast || adding) {
         // CTA shape: the preferred one (8 warps) unless 4-warp CTAs keep more warps
-        // resident per SM under the shared-memory limit (deep atmospheres)
-        warps = fast_warps();
+        // resident per SM under the shared-memory limit (deep atmospheres); the adding kernel
+        // above NSTR = 16 runs 4-warp CTAs (register budget)
+        warps = (adding && N > 16) ? 4 : fast_warps();
+        const int wmax = adding ? adding_warps_per_sm(N) : 16;
         int cta_per_sm = 0;
         for (int wtry = warps; wtry >= 4; wtry /= 2) {
             const size_t smem = adding ? adding_smem_bytes(N, L, wtry) : fast_smem_bytes(N, L, NT, wtry, NU, dims->nphi);
             if (smem > smem_limit) continue;
             int c = (int)((smem_limit + 1024) / (smem + 1024));
-            if (c > 16 / wtry) c = 16 / wtry;
+            if (c > wmax / wtry) c = wmax / wtry;
             if (c * wtry > cta_per_sm * warps || cta_per_sm == 0) { cta_per_sm = c; warps = wtry; }
         }
         if (cta_per_sm == 0) return SBD_ERR_UNSUPPORTED;
@@ -419,18 +422,29 @@ extern "C" int sbd_disort_batch_device(sbd_handle *h, const sbd_dims *dims, cons
         if (le != cudaSuccess) return SBD_ERR_CUDA;
         h->launches += 1;
         LaunchArgs a2 = a;
-        int w2 = fast_warps();
-        if (fast_smem_bytes(N, L, NT, w2, 0, 0) > smem_limit) w2 = 4;
-        if (fast_smem_bytes(N, L, NT, w2, 0, 0) > smem_limit) return SBD_ERR_UNSUPPORTED;
-        int g2 = 16;
-        if (g2 > (dims->nbins + w2 - 1) / w2) g2 = (dims->nbins + w2 - 1) / w2;
         a2.redo_consume = true;
         a2.work_counter = a.work_counter + 2;
-        a2.slot_stride = fast_slot_doubles(N, L, 0);
-        a2.nslots = g2 * w2;
-        if (rs.reserve(a2.slot_stride * (size_t)a2.nslots * 8) != cudaSuccess) return SBD_ERR_CUDA;
-        a2.scratch = (double *)rs.p;
-        le = launch_fast(a2, w2, g2, st);
+        if (fast_supported(N)) {
+            int w2 = fast_warps();
+            if (fast_smem_bytes(N, L, NT, w2, 0, 0) > smem_limit) w2 = 4;
+            if (fast_smem_bytes(N, L, NT, w2, 0, 0) > smem_limit) return SBD_ERR_UNSUPPORTED;
+            int g2 = 16;
+            if (g2 > (dims->nbins + w2 - 1) / w2) g2 = (dims->nbins + w2 - 1) / w2;
+            a2.slot_stride = fast_slot_doubles(N, L, 0);
+            a2.nslots = g2 * w2;
+            if (rs.reserve(a2.slot_stride * (size_t)a2.nslots * 8) != cudaSuccess) return SBD_ERR_CUDA;
+            a2.scratch = (double *)rs.p;
+            le = launch_fast(a2, w2, g2, st);
+        } else {
+            if (wide_smem_bytes(N, L, NT) > smem_limit) return SBD_ERR_UNSUPPORTED;
+            int g2 = 16;
+            if (g2 > dims->nbins) g2 = dims->nbins;
+            a2.slot_stride = wide_slot_doubles(N, L);
+            a2.nslots = g2;
+            if (rs.reserve(a2.slot_stride * (size_t)a2.nslots * 8) != cudaSuccess) return SBD_ERR_CUDA;
+            a2.scratch = (double *)rs.p;
+            le = launch_wide(a2, g2, st);
+        }
     } else {
         le = wide ? launch_wide(a, grid, st)
                   : (fast ? launch_fast(a, warps, grid, st) : launch_generic(a, warps, grid, st));

@@ -91,6 +91,7 @@ cudaError_t launch_fast(const LaunchArgs &a, int warps, int grid, cudaStream_t s
 
 // adding kernel: NSTR in {4, 8, 16}, fluxes at the layer boundaries (sbd_adding.cu)
 bool adding_supported(int N);
+int adding_warps_per_sm(int N);
 size_t adding_slot_doubles(int N, int L);
 size_t adding_smem_bytes(int N, int L, int warps);
 cudaError_t launch_adding(const LaunchArgs &a, int warps, int grid, cudaStream_t st);

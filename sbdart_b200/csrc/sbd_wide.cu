@@ -483,8 +483,9 @@ disort_wide_kernel(const LaunchArgs a)
         __syncthreads();
         if (tid == 0) misc[0] = atomicAdd(a.work_counter, 1);
         __syncthreads();
-        const int bin = misc[0];
-        if (bin >= (a.nbins_dev ? *a.nbins_dev : a.d.nbins)) break;
+        int bin = misc[0];
+        if (bin >= (a.redo_consume ? *a.redo_count : (a.nbins_dev ? *a.nbins_dev : a.d.nbins))) break;
+        if (a.redo_consume) bin = a.redo_list[bin];       // bins handed over by the adding kernel
         const int src = a.binmap ? a.binmap[bin] : bin;
         const sbd_bin bp = a.bins[src];
         const double *dtauc = a.dtauc + (size_t)src * L;
