@@ -1,4 +1,6 @@
-"""Tiny mixed run (flux NSTR 4/8/16 incl. thermal and truncated bins, USRTAU, radiances) for compute-sanitizer."""
+"""Tiny mixed run for compute-sanitizer: flux NSTR 4..32 (adding kernel; SBD_FORCE_ELIM=1: the
+elimination kernels) incl. thermal and truncated bins, a bin with a negative optical depth (handed
+to the elimination kernel), USRTAU, radiances, BRDF surfaces (adding and general kernel)."""
 import sys; sys.path.insert(0, '.')
 import numpy as np
 import sbdart_b200 as sb
@@ -34,4 +36,25 @@ print("generic radiance bad", int((o["status"] != 0).sum()))
 w = workloads.retrieval_batch(6, nstr=8, nlyr=6, ncols=2, seed=3)
 o = s.disort_batch(w["dtauc"], w["ssalb"], w["pmom"], w["bins"], nstr=8, umu=np.array([-0.5, 0.5]), phi=np.array([0.0, 90.0]))
 print("radiance bad", int((o["status"] != 0).sum()))
+# a negative optical depth: TAUC is not monotone, the adding kernel hands the bin over
+for nstr in (16, 32):
+    w = workloads.retrieval_batch(8, nstr=nstr, nlyr=12, ncols=2, seed=11)
+    w["dtauc"][3, 5] = -0.01
+    o = s.disort_batch(w["dtauc"], w["ssalb"], w["pmom"], w["bins"], nstr=nstr)
+    print(nstr, "handed-over bin bad", int((o["status"] != 0).sum()))
+# BRDF surfaces: fluxes (adding kernel) and radiances (general kernel)
+from sbdart_b200.frontend import brdf
+model = brdf.SurfaceModel(9, [0.2, 0.1, 0.05, 1.5, 2.0])
+umu = np.array([-0.5, 0.3, 0.8])
+for nstr, rad in ((8, False), (20, False), (8, True)):
+    mu, _ = sb.quadrature(nstr // 2)
+    w = workloads.retrieval_batch(4, nstr=nstr, nlyr=6, ncols=1, seed=7)
+    umu0 = float(w["bins"]["umu0"][0])
+    tab = brdf.surface_tables(model, None, mu, umu0, True, nstr if rad else 1, umu=umu if rad else None)
+    s.set_surfaces(nstr, tab["bdr"][None], tab["bem"][None], tab["rmu"][None] if rad else None, tab["emu"][None] if rad else None)
+    b = w["bins"].copy(); b["albedo"] = sb.surface_albedo(0)
+    o = s.disort_batch(w["dtauc"], w["ssalb"], w["pmom"], b, nstr=nstr, umu=umu if rad else None,
+                       phi=np.array([0.0, 90.0]) if rad else None)
+    print(nstr, "brdf", "radiance" if rad else "flux", "bad", int((o["status"] != 0).sum()))
+    s.set_surfaces()
 s.close()
