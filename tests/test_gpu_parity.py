@@ -252,3 +252,24 @@ def test_radiance_level_selection(solver):
         assert np.array_equal(sel[k], full[k]), k
     again = solver.disort_batch(w["dtauc"], w["ssalb"], w["pmom"], w["bins"], nstr=8, umu=umu, phi=phi)
     assert np.array_equal(again["uu"], full["uu"])          # the selection does not stick
+
+
+@pytest.mark.parametrize("nstr", [8, 16, 24, 32])
+def test_negative_optical_depths_follow_the_reference(nstr):
+    """DTAUC < 0 (legal upstream, taugas.f:7485): disort.f:487 accumulates TAUC before CHEKIN
+    clips the layer (disort.f:4944), so output levels may fall INSIDE an earlier layer.  The
+    adding kernel hands such bins to the elimination kernel on the device; the rest of the
+    batch stays on the adding path.  Both must agree with the checker."""
+    w = workloads.retrieval_batch(24, nstr=nstr, nlyr=14, ncols=3, seed=40 + nstr)
+    w["dtauc"][5, 6] = -0.02
+    w["dtauc"][17, 2] = -0.3 * w["dtauc"][17, 1]
+    s = sb.Solver(0)
+    got = s.disort_batch(w["dtauc"], w["ssalb"], w["pmom"], w["bins"], nstr=nstr)
+    s.close()
+    b = w["bins"]
+    ref = oracle.disort_flux_batch(w["dtauc"], w["ssalb"], w["pmom"], nstr=nstr, fbeam=b["fbeam"], umu0=b["umu0"],
+                                   albedo=b["albedo"], nthreads=2)
+    assert (got["status"] == ref["status"]).all() and (got["status"] == 0).all()
+    scale = np.max([np.abs(ref[k]).max(axis=1) for k in ("rfldir", "rfldn", "flup")], axis=0)[:, None]
+    for k in ("rfldir", "rfldn", "flup", "uavg", "dfdt"):
+        assert (np.abs(got[k] - ref[k]) <= 1e-7 * np.abs(ref[k]) + 1e-9 * scale).all(), k
