@@ -394,19 +394,14 @@ __device__ __forceinline__ int phase1_adding(
         for (int c = 0; c < n; c++) { pr[c] = shfl_d(bp[c], j, GW); qr[c] = shfl_d(bm[c], j, GW); }
         const double rp = fast_rcp(pr[j]), rq = fast_rcp(qr[j]);
         if (!(pr[j] > 0.0) || !(qr[j] > 0.0)) bad = 1;
-        const double mp = bp[j] * rp, mq = bm[j] * rq;
-        if (g == j) {
+        // row j (the pivot row, own row of lane j) becomes row / pivot = row - (1 - 1/pivot) row:
+        // one update for every lane, with the multiplier 1 - 1/pivot on lane j
+        const double mp = (g == j) ? 1.0 - rp : bp[j] * rp, mq = (g == j) ? 1.0 - rq : bm[j] * rq;
+        const double dp = (g == j) ? rp : -mp, dq = (g == j) ? rq : -mq;
 #pragma unroll
-            for (int c = 0; c < n; c++) {
-                bp[c] = (c == j) ? rp : pr[c] * rp;
-                bm[c] = (c == j) ? rq : qr[c] * rq;
-            }
-        } else {
-#pragma unroll
-            for (int c = 0; c < n; c++) {
-                bp[c] = (c == j) ? -mp : fma(-mp, pr[c], bp[c]);
-                bm[c] = (c == j) ? -mq : fma(-mq, qr[c], bm[c]);
-            }
+        for (int c = 0; c < n; c++) {
+            bp[c] = (c == j) ? dp : fma(-mp, pr[c], bp[c]);
+            bm[c] = (c == j) ? dq : fma(-mq, qr[c], bm[c]);
         }
     }
     // U+- = B+-^-1 P^T (row g), stored over K and X
@@ -785,6 +780,7 @@ disort_adding_kernel(const LaunchArgs a)
                 // ---- Gauss-Jordan with partial pivoting on [B | T | v], rows in registers ----
                 unsigned used = 0;
                 int myj = 0, sing = 0;
+                double myrp = 0.0;
 #pragma unroll
                 for (int j = 0; j < n; j++) {
                     const int pj = j / CW, sj = j % CW;
@@ -801,25 +797,21 @@ disort_adding_kernel(const LaunchArgs a)
                     used |= 1u << ip;
 #endif
                     const int srcl = ip * CG + p2;
+                    // rows keep their scale: multiplier = column entry / pivot (0 on the pivot row
+                    // itself); the pivot row is divided by its pivot once, after the last step
                     const double rp = fast_rcp(__shfl_sync(FULLMASK, colv, ip * CG));
-                    double pb[CW], pt[CW];
+                    const double m = (i2 == ip) ? 0.0 : colv * rp;
+                    if (i2 == ip) { myj = j; myrp = rp; }
 #pragma unroll
                     for (int s = 0; s < CW; s++) {
-                        pb[s] = __shfl_sync(FULLMASK, b[s], srcl) * rp;
-                        pt[s] = __shfl_sync(FULLMASK, t[s], srcl) * rp;
+                        b[s] = fma(-m, __shfl_sync(FULLMASK, b[s], srcl), b[s]);
+                        t[s] = fma(-m, __shfl_sync(FULLMASK, t[s], srcl), t[s]);
                     }
-                    const double pv = __shfl_sync(FULLMASK, v, srcl) * rp;
-                    if (i2 == ip) {
-#pragma unroll
-                        for (int s = 0; s < CW; s++) { b[s] = pb[s]; t[s] = pt[s]; }
-                        v = pv;
-                        myj = j;
-                    } else {
-#pragma unroll
-                        for (int s = 0; s < CW; s++) { b[s] = fma(-colv, pb[s], b[s]); t[s] = fma(-colv, pt[s], t[s]); }
-                        v = fma(-colv, pv, v);
-                    }
+                    v = fma(-m, __shfl_sync(FULLMASK, v, srcl), v);
                 }
+#pragma unroll
+                for (int s = 0; s < CW; s++) t[s] *= myrp;
+                v *= myrp;
                 if (sing) { status = SBD_BIN_SINGULAR; break; }
                 // row i2 now holds row myj of Y = (I - R Rb)^-1 T and of y
                 double *orec = recs + (size_t)lc * AL::rec;      // (the phase-1 record is in shared memory)
