@@ -98,6 +98,26 @@ __device__ void abcdta_dev(const OpticsTables &T, int iv, BandState &s)
 
 __device__ double raysig_dev(double v) { return v * v * v * v / (F32(9.38076e+18) + F32(-1.08426e+09) * v * v); }
 
+// taucor with the three k-terms on lanes 0..2 of the calling warp (every lane calls; gk, tk:
+// the lane's own term, 0 beyond lane 2).  Same Newton iteration and the same summation order
+// (ff = e0 + e1 + e2) as the scalar form below.
+__device__ __forceinline__ bool taucor_warp(double gk, double tk, double amu, double utau, double &cf)
+{
+    cf = 1.;
+    if (utau > 12.0) return true;
+    for (int it = 0; it < 20; it++) {
+        const double e = gk * exp(-cf * tk / amu), es = e * tk;
+        const double e0 = __shfl_sync(0xffffffffu, e, 0), e1 = __shfl_sync(0xffffffffu, e, 1), e2 = __shfl_sync(0xffffffffu, e, 2);
+        const double s0 = __shfl_sync(0xffffffffu, es, 0), s1 = __shfl_sync(0xffffffffu, es, 1), s2 = __shfl_sync(0xffffffffu, es, 2);
+        const double ff = (e0 + e1) + e2, fs = (s0 + s1) + s2;
+        const double f = log(ff) + utau;
+        if (fabs(f) < F32(0.000001)) return true;
+        const double fp = -fs / (ff * amu);
+        cf += -f / fp;
+    }
+    return false;
+}
+
 // taucor (taugas.f:7650-7692); returns false when the Newton iteration fails
 __device__ bool taucor_dev(const double *gwk, const double *tau, double amu, double utau, double &cf)
 {
@@ -358,7 +378,10 @@ __device__ void taugas_warp(const OpticsArgs &a, const GasCoef &c, const double 
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(kOptWarps * 32)
+#ifndef SBD_OPT_MINB
+#define SBD_OPT_MINB 4       // 16 warps per SM (128 registers): +5 % on the e2e arm against 8 warps at 255
+#endif
+__global__ void __launch_bounds__(kOptWarps * 32, SBD_OPT_MINB)
 optics_kernel(const OpticsArgs a)
 {
     extern __shared__ double sm_opt[];
@@ -465,15 +488,20 @@ optics_kernel(const OpticsArgs a)
         for (int j = lane; j < nz; j += 32)
             for (int k = 0; k < 3; k++) dk2[k * kMaxZ + j] = dtk[k * kMaxZ + j];
         __syncwarp();
-        if (P.kdist >= 2 && amu0 > 0. && lane == 0) {
-            // slant-path correction: a Newton solve per layer on running sums (sequential)
-            double tauls = 0., tglc[3] = { 0, 0, 0 };
+        if (P.kdist >= 2 && amu0 > 0.) {
+            // slant-path correction: a Newton solve per layer on running sums (sequential over
+            // the layers); the three k-terms sit on lanes 0..2
+            double tauls = 0., tgl = 0.;
+            const int kk = lane < 3 ? lane : 0;
+            const double gk = lane < 3 ? gwk[kk] : 0.0;
             for (int j = 0; j < nz; j++) {
                 tauls += dtls[j];
-                for (int k = 0; k < 3; k++) tglc[k] += dtk[k * kMaxZ + j];
+                const double dj = dtk[kk * kMaxZ + j];
+                tgl += dj;
                 double cf;
-                taucor_dev(gwk, tglc, amu0, tauls, cf);
-                for (int k = 0; k < 3; k++) { dk2[k * kMaxZ + j] = tglc[k] * (cf - 1.0) + dtk[k * kMaxZ + j]; tglc[k] *= cf; }
+                taucor_warp(gk, lane < 3 ? tgl : 0.0, amu0, tauls, cf);
+                if (lane < 3) dk2[kk * kMaxZ + j] = tgl * (cf - 1.0) + dj;
+                tgl *= cf;
             }
         }
     }

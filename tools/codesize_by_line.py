@@ -19,7 +19,7 @@ for cub in glob.glob(d + '/*.cubin'):
     print('total', sum(cnt.values()))
     b = collections.Counter()
     for (fn, ln), v in cnt.items():
-        if fn == 'sbd_fast.cu': b[(ln // 20) * 20] += v
+        if fn in ('sbd_fast.cu', 'sbd_adding.cu', 'sbd_wide.cu'): b[(ln // 20) * 20] += v
         else: b[fn] += v
     for k, v in sorted(b.items(), key=lambda kv: -kv[1])[:28]: print(v, k)
     break
