@@ -35,6 +35,9 @@
 #ifndef SBD_ADD_ROLL
 #define SBD_ADD_ROLL 1       // rolled Legendre / M loops: smaller code, +1.2 % on the C2 bench
 #endif
+#ifndef SBD_ADD_MEET
+#define SBD_ADD_MEET 1       // phases 2 / 3: two adding sweeps that meet in the middle (NSTR <= 16)
+#endif
 #ifndef SBD_ADD_SYNC
 #define SBD_ADD_SYNC 1       // CTA barriers between the phases
 #endif
@@ -80,8 +83,10 @@ struct AddLayout {
     // padded to 4 (mod 16) doubles: the groups' areas start 8 banks apart, so the four
     // addresses of a group-wide broadcast load never share a bank
     static constexpr int task = ((task0 + 11) / 16) * 16 + 4;
-    // phase-2 shared memory: Rb, sb, Y, y, W, w, two records
-    static constexpr int p2 = 3 * n * n + 3 * n + 2 * rec;
+    // phase 2 as two sweeps that meet in the middle (n <= 8: the work area holds two chains)
+    static constexpr bool MEET = (SBD_ADD_MEET != 0) && n <= 8;
+    // phase-2 shared memory per chain: Rb, sb, Y, y, W, w, two records
+    static constexpr int p2 = (MEET ? 2 : 1) * (3 * n * n + 3 * n + 2 * rec);
     static constexpr int work = tasks * task > p2 ? tasks * task : p2;
     __host__ __device__ static size_t warp_doubles(int L)
     {
@@ -744,6 +749,225 @@ disort_adding_kernel(const LaunchArgs a)
                     fnB0 = s * emis;
                 }
             }
+            if constexpr (AL::MEET) {
+            // Two adding sweeps that meet in the middle: chain 0 runs bottom-up over the layers
+            // ncut-1 .. mid (Rb, sb: reflection / emission of everything below the layer's top
+            // interface), chain 1 top-down over the layers 0 .. mid-1 (the mirror image: Ra, sa of
+            // everything above the layer's bottom interface; the same step with s_up and s_dn
+            // exchanged).  The chains are independent: every lane carries both, which doubles the
+            // instruction-level parallelism of the sequential part and halves its length.
+            constexpr int CH = 3 * n * n + 3 * n;
+            double *const chs[2] = { work, work + CH };
+            double *const rb2[2] = { work + 2 * CH, work + 2 * CH + 2 * AL::rec };
+            const int mid = ncut / 2, niter = ncut - mid;
+            {   // nothing above the top boundary reflects; it emits D (fisot + tplank)
+                double *R1 = chs[1], *s1 = R1 + n * n;
+                for (int e = lane; e < n * n; e += 32) R1[e] = 0.0;
+                if (lane < n) s1[lane] = cd[lane] * (bp.fisot + tplank);
+            }
+            warp_copy_async(rb2[0], recs + (size_t)(ncut - 1) * AL::rec, AL::rec, lane);
+            if (mid > 0) warp_copy_async(rb2[1], recs, AL::rec, lane);
+            cp_async_commit();
+            __syncwarp();
+            for (int k = 0; k < niter; k++) {
+                const int buf = k & 1;
+                const int lq[2] = { ncut - 1 - k, k };
+                const bool actq[2] = { true, k < mid };
+                if (k + 1 < niter) {
+                    warp_copy_async(rb2[0] + (buf ^ 1) * AL::rec, recs + (size_t)(lq[0] - 1) * AL::rec, AL::rec, lane);
+                    if (k + 1 < mid)
+                        warp_copy_async(rb2[1] + (buf ^ 1) * AL::rec, recs + (size_t)(lq[1] + 1) * AL::rec, AL::rec, lane);
+                    cp_async_commit();
+                    cp_async_wait_one();
+                } else {
+                    cp_async_wait_all();
+                }
+                __syncwarp();
+                // ---- B = I - R Rx (my CW columns of row i2), t = T, v = (R sx + s)_i2 ----
+                double b[2][CW], t[2][CW], v[2];
+#pragma unroll
+                for (int q = 0; q < 2; q++) {
+                    const double *rc = rb2[q] + buf * AL::rec;
+                    const double *Rr = rc + AL::r_R + i2 * n, *Tr = rc + AL::r_T + i2 * n;
+                    const double *Rx = chs[q], *sx = Rx + n * n;
+                    double r[n];
+#pragma unroll
+                    for (int kk = 0; kk < n; kk++) r[kk] = Rr[kk];
+#pragma unroll
+                    for (int s = 0; s < CW; s++) b[q][s] = (c0 + s == i2) ? 1.0 : 0.0;
+                    v[q] = rc[(q == 0 ? AL::r_sd : AL::r_su) + i2];
+#pragma unroll
+                    for (int kk = 0; kk < n; kk++) {
+#pragma unroll
+                        for (int s = 0; s < CW; s++) b[q][s] = fma(-r[kk], Rx[kk * n + c0 + s], b[q][s]);
+                        v[q] = fma(r[kk], sx[kk], v[q]);
+                    }
+#pragma unroll
+                    for (int s = 0; s < CW; s++) t[q][s] = Tr[c0 + s];
+                }
+                // ---- Gauss-Jordan with partial pivoting on [B | T | v] of both chains ----
+                unsigned used[2] = { 0u, 0u };
+                int myj[2] = { 0, 0 }, sing = 0;
+                double myrp[2] = { 0.0, 0.0 };
+#pragma unroll
+                for (int j = 0; j < n; j++) {
+                    const int pj = j / CW, sj = j % CW;
+#pragma unroll
+                    for (int q = 0; q < 2; q++) {
+                        const double colv = __shfl_sync(FULLMASK, b[q][sj], (lane & ~(CG - 1)) | pj);
+                        const int key = (act2 && !((used[q] >> i2) & 1u))
+                                            ? ((__double2hiint(colv) & ~KM & 0x7fffffff) | (KM - i2)) : -1;
+                        const int mx = __reduce_max_sync(FULLMASK, key);
+                        if (actq[q] && (mx >> KB) <= 0) sing = 1;
+                        const int ip = KM - (mx & KM);
+                        used[q] |= 1u << ip;
+                        const int srcl = ip * CG + p2;
+                        const double rp = fast_rcp(__shfl_sync(FULLMASK, colv, ip * CG));
+                        const double m = (i2 == ip) ? 0.0 : colv * rp;
+                        if (i2 == ip) { myj[q] = j; myrp[q] = rp; }
+#pragma unroll
+                        for (int s = 0; s < CW; s++) {
+                            b[q][s] = fma(-m, __shfl_sync(FULLMASK, b[q][s], srcl), b[q][s]);
+                            t[q][s] = fma(-m, __shfl_sync(FULLMASK, t[q][s], srcl), t[q][s]);
+                        }
+                        v[q] = fma(-m, __shfl_sync(FULLMASK, v[q], srcl), v[q]);
+                    }
+                }
+                if (sing) { status = SBD_BIN_SINGULAR; break; }
+                // row i2 now holds row myj of Y = (I - R Rx)^-1 T and of y
+#pragma unroll
+                for (int q = 0; q < 2; q++) {
+                    double *sY = chs[q] + n * n + n, *sy = sY + n * n;
+                    double *orec = recs + (size_t)lq[q] * AL::rec;       // (the phase-1 record is in shared memory)
+                    if (act2 && actq[q]) {
+#pragma unroll
+                        for (int s = 0; s < CW; s++) {
+                            const double y = t[q][s] * myrp[q];
+                            sY[myj[q] * n + c0 + s] = y; orec[AL::o_Y + myj[q] * n + c0 + s] = y;
+                        }
+                        if (p2 == 0) { const double y = v[q] * myrp[q]; sy[myj[q]] = y; orec[AL::o_y + myj[q]] = y; }
+                    }
+                }
+                __syncwarp();
+                // ---- W = Rx [Y | y] + [0 | sx] ----
+#pragma unroll
+                for (int q = 0; q < 2; q++) {
+                    const double *Rx = chs[q], *sx = Rx + n * n, *sY = sx + n, *sy = sY + n * n;
+                    double *sW = chs[q] + 2 * n * n + 2 * n, *sw = sW + n * n;
+                    double rb[n], w[CW], wv = sx[i2];
+#pragma unroll
+                    for (int kk = 0; kk < n; kk++) rb[kk] = Rx[i2 * n + kk];
+#pragma unroll
+                    for (int s = 0; s < CW; s++) w[s] = 0.0;
+#pragma unroll
+                    for (int kk = 0; kk < n; kk++) {
+#pragma unroll
+                        for (int s = 0; s < CW; s++) w[s] = fma(rb[kk], sY[kk * n + c0 + s], w[s]);
+                        wv = fma(rb[kk], sy[kk], wv);
+                    }
+                    if (act2 && actq[q]) {
+#pragma unroll
+                        for (int s = 0; s < CW; s++) sW[i2 * n + c0 + s] = w[s];
+                        if (p2 == 0) sw[i2] = wv;
+                    }
+                }
+                __syncwarp();
+                // ---- [Rx | sx] <- [R | s'] + T W ----
+#pragma unroll
+                for (int q = 0; q < 2; q++) {
+                    const double *rc = rb2[q] + buf * AL::rec;
+                    const double *Rr = rc + AL::r_R + i2 * n, *Tr = rc + AL::r_T + i2 * n;
+                    double *Rx = chs[q], *sx = Rx + n * n;
+                    const double *sW = chs[q] + 2 * n * n + 2 * n, *sw = sW + n * n;
+                    double tr[n], nr[CW], ns = rc[(q == 0 ? AL::r_su : AL::r_sd) + i2];
+#pragma unroll
+                    for (int kk = 0; kk < n; kk++) tr[kk] = Tr[kk];
+#pragma unroll
+                    for (int s = 0; s < CW; s++) nr[s] = Rr[c0 + s];
+#pragma unroll
+                    for (int kk = 0; kk < n; kk++) {
+#pragma unroll
+                        for (int s = 0; s < CW; s++) nr[s] = fma(tr[kk], sW[kk * n + c0 + s], nr[s]);
+                        ns = fma(tr[kk], sw[kk], ns);
+                    }
+                    if (act2 && actq[q]) {
+#pragma unroll
+                        for (int s = 0; s < CW; s++) Rx[i2 * n + c0 + s] = nr[s];
+                        if (p2 == 0) sx[i2] = ns;
+                    }
+                }
+                __syncwarp();
+                // ---- flux functionals of the chains' new interfaces: D^T Rx, c^T Rx, D^T sx, c^T sx ----
+                for (int e = lane; e < 2 * (2 * n + 2); e += 32) {
+                    const int q = e >= 2 * n + 2 ? 1 : 0, f = e - q * (2 * n + 2);
+                    if (q == 1 && k >= mid) continue;
+                    const double *Rx = work + q * CH, *sx = Rx + n * n;
+                    double *orec = recs + (size_t)(q ? k : ncut - 1 - k) * AL::rec;
+                    double acc = 0.0;
+                    if (f < 2 * n) {
+                        const double *wv = (f < n) ? cd : csq;
+                        const int c = f % n;
+#pragma unroll
+                        for (int kk = 0; kk < n; kk++) acc = fma(wv[kk], Rx[kk * n + c], acc);
+                        orec[(f < n ? AL::o_fu : AL::o_cu) + c] = acc;
+                    } else {
+                        const double *wv = (f == 2 * n) ? cd : csq;
+#pragma unroll
+                        for (int kk = 0; kk < n; kk++) acc = fma(wv[kk], sx[kk], acc);
+                        orec[AL::o_f0 + (f - 2 * n)] = acc;
+                    }
+                }
+            }
+            // ---- the chains meet at interface `mid`: (I - Ra Rb) d = Ra sb + sa, u = Rb d + sb ----
+            if (!status) {
+                __syncwarp();
+                const double *Rb = chs[0], *sb = Rb + n * n, *Ra = chs[1], *sa = Ra + n * n;
+                double *dm = chs[0] + n * n + n;                 // Y area of chain 0: d_mid, then u_mid
+                double b[CW], v, ra[n];
+#pragma unroll
+                for (int kk = 0; kk < n; kk++) ra[kk] = Ra[i2 * n + kk];
+#pragma unroll
+                for (int s = 0; s < CW; s++) b[s] = (c0 + s == i2) ? 1.0 : 0.0;
+                v = sa[i2];
+#pragma unroll
+                for (int kk = 0; kk < n; kk++) {
+#pragma unroll
+                    for (int s = 0; s < CW; s++) b[s] = fma(-ra[kk], Rb[kk * n + c0 + s], b[s]);
+                    v = fma(ra[kk], sb[kk], v);
+                }
+                unsigned used = 0u;
+                int myj = 0, sing = 0;
+                double myrp = 0.0;
+#pragma unroll
+                for (int j = 0; j < n; j++) {
+                    const int pj = j / CW, sj = j % CW;
+                    const double colv = __shfl_sync(FULLMASK, b[sj], (lane & ~(CG - 1)) | pj);
+                    const int key = (act2 && !((used >> i2) & 1u))
+                                        ? ((__double2hiint(colv) & ~KM & 0x7fffffff) | (KM - i2)) : -1;
+                    const int mx = __reduce_max_sync(FULLMASK, key);
+                    if ((mx >> KB) <= 0) sing = 1;
+                    const int ip = KM - (mx & KM);
+                    used |= 1u << ip;
+                    const int srcl = ip * CG + p2;
+                    const double rp = fast_rcp(__shfl_sync(FULLMASK, colv, ip * CG));
+                    const double m = (i2 == ip) ? 0.0 : colv * rp;
+                    if (i2 == ip) { myj = j; myrp = rp; }
+#pragma unroll
+                    for (int s = 0; s < CW; s++) b[s] = fma(-m, __shfl_sync(FULLMASK, b[s], srcl), b[s]);
+                    v = fma(-m, __shfl_sync(FULLMASK, v, srcl), v);
+                }
+                if (sing) status = SBD_BIN_SINGULAR;
+                if (act2 && p2 == 0) dm[myj] = v * myrp;
+                __syncwarp();
+                if (lane < n) {
+                    double u = sb[lane];
+#pragma unroll
+                    for (int kk = 0; kk < n; kk++) u = fma(Rb[lane * n + kk], dm[kk], u);
+                    dm[n + lane] = u;
+                }
+                __syncwarp();
+            }
+            } else {
             warp_copy_async(rbuf, recs + (size_t)(ncut - 1) * AL::rec, AL::rec, lane);
             cp_async_commit();
             __syncwarp();
@@ -879,6 +1103,7 @@ disort_adding_kernel(const LaunchArgs a)
                     }
                 }
             }
+                    }
         }
         cp_async_wait_all();
         __syncwarp();
@@ -886,8 +1111,97 @@ disort_adding_kernel(const LaunchArgs a)
         if (SBD_ADD_SYNC) __syncthreads();
         ADD_TICK(2);
 
-        // ===================== phase 3: top-down intensities + fluxes ======
-        // lane r < n: row r of Y (new downward intensity r); lanes n .. n+3: the four flux
+        // ===================== phase 3: intensities at the interfaces + fluxes ======
+        if constexpr (AL::MEET) {
+        // From interface `mid` the downward intensities are carried down (lanes 0..15: d <- Y d + y
+        // with the records of chain 0) and the upward intensities up (lanes 16..31: u <- Y' u + y'
+        // with the records of chain 1) at the same time.  In each half, lane r < n holds row r of the
+        // propagator, lanes n .. n+3 the four flux functionals of the level; every lane forms s0 + vv . x.
+        if (!status) {
+            const int half = lane >> 4, hl = lane & 15, hb = lane & 16;
+            const int role = hl - n;
+            const int mid = ncut / 2, niter = ncut - mid;
+            const double *dm = work + n * n + n;
+            const double top0 = bp.fisot + tplank;
+            double x[n], vv[n], s0 = 0.0;
+#pragma unroll
+            for (int c = 0; c < n; c++) x[c] = dm[half * n + c];
+            // record of iteration t: chain 0: layer mid + t (the surface at level ncut), chain 1: layer
+            // mid - t - 1 (the top boundary at level 0: nothing reflects, D (fisot + tplank) comes down)
+            auto load_rec = [&](int t) {
+                const int lyr = half == 0 ? mid + t : mid - t - 1;
+                const bool inrange = half == 0 ? lyr < ncut : lyr >= 0;
+                if (inrange) {
+                    const double *orec = recs + (size_t)lyr * AL::rec;
+                    if (hl < n) {
+#pragma unroll
+                        for (int c = 0; c < n; c += 2) {
+                            const double2 q = reinterpret_cast<const double2 *>(orec + AL::o_Y + hl * n)[c / 2];
+                            vv[c] = q.x; vv[c + 1] = q.y;
+                        }
+                        s0 = orec[AL::o_y + hl];
+                    } else if (role == 0 || role == 1) {
+#pragma unroll
+                        for (int c = 0; c < n; c += 2) {
+                            const double2 q = reinterpret_cast<const double2 *>(orec + (role == 0 ? AL::o_fu : AL::o_cu))[c / 2];
+                            vv[c] = q.x; vv[c + 1] = q.y;
+                        }
+                        s0 = orec[AL::o_f0 + role];
+                    }
+                } else if (role == 0 || role == 1) {
+                    if (half == 0) {
+#pragma unroll
+                        for (int c = 0; c < n; c++) vv[c] = fnB[c];
+                        s0 = fnB0;
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < n; c++) vv[c] = 0.0;
+                        s0 = (role == 0 ? Wq : SWq) * top0;
+                    }
+                }
+            };
+#pragma unroll
+            for (int c = 0; c < n; c++) vv[c] = (role == 2) ? cd[c] : ((role == 3) ? csq[c] : 0.0);
+            load_rec(0);
+            for (int t = 0; t <= niter; t++) {
+                const int lev = half == 0 ? mid + t : mid - t;
+                double xs = s0;
+#pragma unroll
+                for (int c = 0; c < n; c++) xs = fma(vv[c], x[c], xs);
+                if (t < niter) load_rec(t + 1);               // next record while this level finishes
+                // x_R: the reflected side (u+ below mid, u- above), x_V: the carried side
+                const double xcr = __shfl_sync(FULLMASK, xs, hb | (n + 1));
+                const double xdv = __shfl_sync(FULLMASK, xs, hb | (n + 2));
+                const double xcv = __shfl_sync(FULLMASK, xs, hb | (n + 3));
+                if (hl == n && (half == 0 || (t > 0 && lev >= 0))) {
+                    const double pi = kPiRef;
+                    const double fact = ebeam[lev];
+                    const double dirint = fbeam * fact;
+                    const double fldir = umu0 * (fbeam * fact);
+                    const double rfldir = umu0 * fbeam * edir[lev];
+                    const double flup = 2. * pi * (half == 0 ? xs : xdv), fldn = 2. * pi * (half == 0 ? xdv : xs);
+                    const double fdntot = fldn + fldir;
+                    constexpr double inv4pi = 1.0 / (4. * kPiRef);
+                    const double uavg = (2. * pi * (xcr + xcv) + dirint) * inv4pi;
+                    // the layer the level belongs to (its single-scattering albedo and Planck value)
+                    const int lyr = layru[lev] - 1;
+                    double ssl = ssalb[lyr];
+                    if (ssl == 1.0) ssl = 1.0 - kDither;
+                    double plsorc = 0.0;
+                    if (plank) plsorc = (lev == 0) ? pk[0] : ((taucpr[lyr + 1] - taucpr[lyr] > 0.0) ? pk[lyr + 1] : pk[lyr]);
+                    if (o_rfldir) o_rfldir[lev] = rfldir;
+                    if (o_rfldn) o_rfldn[lev] = fdntot - rfldir;
+                    if (o_flup) o_flup[lev] = flup;
+                    if (o_uavg) o_uavg[lev] = uavg;
+                    if (o_dfdt) o_dfdt[lev] = (1.0 - ssl) * 4. * pi * (uavg - plsorc);
+                }
+                // the new intensities to everyone in the half
+#pragma unroll
+                for (int c = 0; c < n; c++) x[c] = __shfl_sync(FULLMASK, xs, hb | c);
+            }
+        }
+        } else {
+        // top-down: lane r < n: row r of Y (new downward intensity r); lanes n .. n+3: the four flux
         // functionals (D^T u+, c^T u+, D^T u-, c^T u-); every lane forms  s0 + vv . d
         if (!status) {
             double d[n], vv[n], s0 = 0.0;
@@ -956,6 +1270,7 @@ disort_adding_kernel(const LaunchArgs a)
 #pragma unroll
                 for (int c = 0; c < n; c++) d[c] = __shfl_sync(FULLMASK, x, c);
             }
+        }
         }
         if (lane == 0 && have && status != -100) a.status[bin] = status;
         __syncwarp();
