@@ -61,6 +61,25 @@ module sbd_b200
        integer(c_int32_t), value :: n
      end function sbd_set_radiance_levels
 
+     ! BRDF surfaces (LAMBER = .FALSE., isalb 7-9): SURFAC's tables (disort.f:3765-3907) of nsurf
+     ! surfaces, bdr(0:n, n, nmodes, nsurf), bem(n, nsurf), rmu(0:n, numu, nmodes, nsurf),
+     ! emu(numu, nsurf) in Fortran order; bins(b)%albedo = -(s+1) selects surface s (0-based)
+     integer(c_int) function sbd_set_surfaces(h, nsurf, nstr, nmodes, numu, bdr, bem, rmu, emu) &
+          bind(c, name='sbd_set_surfaces')
+       import :: c_ptr, c_int, c_int32_t, c_double
+       type(c_ptr), value :: h
+       integer(c_int32_t), value :: nsurf, nstr, nmodes, numu
+       real(c_double), intent(in) :: bdr(*), bem(*)
+       type(c_ptr), value :: rmu, emu                    ! c_null_ptr for flux runs
+     end function sbd_set_surfaces
+
+     ! the BDREF the single-call entry disort_ uses for LAMBER = .FALSE. (spectra.f:249);
+     ! not needed when the executable exports its own bdref_ (link with -rdynamic)
+     subroutine sbd_set_bdref_callback(f) bind(c, name='sbd_set_bdref_callback')
+       import :: c_funptr
+       type(c_funptr), value :: f
+     end subroutine sbd_set_bdref_callback
+
      integer(c_int) function sbd_synchronize(h) bind(c, name='sbd_synchronize')
        import
        type(c_ptr), value :: h
