@@ -17,8 +17,7 @@ is NOT here: `run()` takes a `solve(batch)` callable -- the CUDA batch solver
 
 Aerosols, zgrid, in-cloud humidity, zensun and the sensor filters live in extras.py.
 User files read from the working directory like the reference: atms.dat, albedo.dat,
-filter.dat, solar.dat, aerosol.dat, usrcld.dat, CKATM / CKTAU (kdist=-1).  Not covered:
-spowder.
+filter.dat, solar.dat, aerosol.dat, usrcld.dat, CKATM / CKTAU (kdist=-1).
 """
 from __future__ import annotations
 
@@ -718,7 +717,7 @@ def _rolloff(wl, tsc):
     return ramp * math.exp(1. - max(tsc, 1.0))
 
 
-def depthscl(kdist, kd, nk, wl, dtaur, dtaua, waer, dtauc, wcld, gwk, dtauk, dtaugc):
+def depthscl(kdist, kd, nk, wl, dtaur, dtaua, waer, dtauc, wcld, gwk, dtauk, dtaugc, spowder=False):
     """taugas.f:7512-7621 (kd 0-based).  Returns dtau, wreal, wt."""
     nz = len(dtaur)
     wt = gwk[kd]
@@ -748,6 +747,9 @@ def depthscl(kdist, kd, nk, wl, dtaur, dtaua, waer, dtauc, wcld, gwk, dtauk, dta
             tsc += dtaur[i] + dtauc[i] + dtaua[i]
             ramp = _rolloff(wl, tsc)
             dtaug[i] = dtaugc[i] + dtauk[i, kd] * (1. - ramp) + dtauk[i, kd + 3] * ramp
+    if spowder:                           # no gas, no Rayleigh scattering in the sub-surface layer
+        dtaur[nz - 1] = 0.                # (in place, like the reference: later k-terms see it too)
+        dtaug[nz - 1] = 0.
     dtau = dtaug + dtauc + dtaua + dtaur
     tiny = np.finfo(float).tiny
     sca = dtauc * wcld + dtaua * waer + dtaur
@@ -1257,6 +1259,20 @@ class Sbdart:
         self.temper = np.concatenate([[t[nz - 1]], t[::-1]])          # drt.f:330-333
         self.btemp = self.temper[nz] if p["btemp"] < 0. else p["btemp"]
         self.ttemp = self.temper[0] if p["ttemp"] < 0. else p["ttemp"]
+        self.spowder = bool(p.get("spowder"))
+        if self.spowder:
+            # a sub-surface layer between -1 and 0 km (drt.f:337-349).  The reference extends z, p, t,
+            # wh, wo AFTER it has filled temper(0:nz): DISORT then reads temper(nz+1), an element of
+            # the static array that was never set (0 K), while t(1) = btemp only enters the gas and
+            # Rayleigh amounts.  Kept as built.
+            if nz >= MXLY:
+                raise ValueError("Error --- nz < mxly is required with spowder option")
+            z = np.concatenate([[-1.0], z]); pr = np.concatenate([[f32(1.1) * pr[0]], pr])
+            t = np.concatenate([[self.btemp], t]); wh = np.concatenate([[0.0], wh]); wo = np.concatenate([[0.0], wo])
+            self.z, self.pr, self.t, self.wh, self.wo = z, pr, t, wh, wo
+            nz += 1
+            self.nz = nz
+            self.temper = np.concatenate([self.temper, [0.0]])
         self.nstrsv = p["nstr"]
         self.clouds = Clouds(z, p["zcloud"], p["tcloud"], p["lwp"], p["nre"], p["imomc"])
         if p["rhcld"] >= 0 and self.kdist >= 0:             # drt.f:357-364
@@ -1371,8 +1387,6 @@ class Sbdart:
         todo = []
         if p["kdist"] < -1:
             todo.append(f"kdist={p['kdist']}")
-        if p.get("spowder"):
-            todo.append("spowder (sub-surface layer, drt.f:340-352)")
         if p["isalb"] in (-7, -8, -9):
             todo.append(f"isalb={p['isalb']} (dref, not in the reference source either)")
         if int(p.get("ibcnd", 0)) != 0:
@@ -1523,7 +1537,7 @@ class Sbdart:
             pmom[:, 0] = 1.
             for kd in range(nk):
                 dtau, wreal, wt = depthscl(self.kdist, kd, nk, wl, dtaur, dtaua, waer, dtauc, wcld,
-                                           gwk, dtauk, dtaugc)
+                                           gwk, dtauk, dtaugc, self.spowder)
                 rows.append(dict(il=il, kd=kd, nk=nk, ib=ib, nb=nb, wl=wl, dwl=dwl, wt=wt, ff=ff, dtau=dtau,
                                  ssalb=wreal, pmom=pmom, flxin=flxin, amu0=amu0, rsfc=rsfc,
                                  surf=(il if (self.surface is not None and self.surface.spectral) else 0),
@@ -1683,7 +1697,7 @@ class Sbdart:
                 if "surface" in b:
                     solver.set_surfaces()
         if (not device_aerosols_supported(self.aerosols) or self.p["imomc"] not in (2, 3) or
-                (self.radcalc and self.p["corint"]) or self.surface is not None or self.kdist < 0 or
+                (self.radcalc and self.p["corint"]) or self.surface is not None or self.kdist < 0 or self.spowder or
                 (self.clouds.mcldz == 0 and self.p["nre"][0] == 0.)):
             # table phase functions (getmom 4/5, pmaer) and the 299-moment CORINT runs:
             # optical properties on the host, solve on the GPU

@@ -344,3 +344,21 @@ def test_brdf_surface_runs_and_lambertian_limit():
     rows = [np.array(l.split(), float) for l in rad.splitlines()[4:7]]
     assert rows[0][0] == rows[0][1] == rows[0][2]          # nadir view: no azimuth dependence
     assert rows[1][0] != rows[1][2]                        # sun glint side vs. the far side
+
+
+def test_spowder_granular_surface_layer():
+    """spowder (drt.f:337-349, taugas.f:7592-7595): a sub-surface layer between -1 and 0 km, no gas
+    and no Rayleigh scattering in it, temper(nz+1) left unset as in the reference.  The manual's
+    example (rtdoc.txt:1418-1424: a semi-infinite layer of 100 um ice grains under a thin water
+    cloud) must behave like the reference's own snow albedo table (isalb = 1) to a few percent."""
+    from solvers import solve_oracle
+    base = "&INPUT\n sza=30, idatm=4, wlinf=.4, wlsup=.8, wlinc=.1, iout=1,\n {}\n /"
+    pw = Sbdart(base.format("spowder=t, tcloud=10000,10, zcloud=-1,2, nre=-100,10"))
+    assert pw.nz == 34 and pw.z[0] == -1.0 and pw.temper[-1] == 0.0 and pw.clouds.lcld[0] == 34
+    rows = pw.bins()
+    assert all(r["dtau"][-1] >= 9999.0 for r in rows)            # only the grains in the bottom layer
+    got = np.array([l.split() for l in pw.run(solve_oracle).splitlines()[3:]], float)
+    snow = Sbdart(base.format("tcloud=0,10, zcloud=0,2, nre=8,10, isalb=1")).run(solve_oracle)
+    ref = np.array([l.split() for l in snow.splitlines()[3:]], float)
+    assert np.allclose(got[:, 2], ref[:, 2])                     # same solar input
+    assert np.allclose(got[:, 6] / got[:, 5], ref[:, 6] / ref[:, 5], rtol=0.03)      # surface albedo

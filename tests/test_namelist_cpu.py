@@ -51,7 +51,7 @@ def test_non_finite_values_are_printed_as_gfortran_prints_them():
     assert "NaN" in Sbdart("&INPUT iout=10 /").run(solve_nan)
 
 
-@pytest.mark.parametrize("nl,what", [("kdist=-2", "kdist"), ("spowder=t", "spowder"), ("isalb=-7", "dref")])
+@pytest.mark.parametrize("nl,what", [("kdist=-2", "kdist"), ("isalb=-7", "dref")])
 def test_options_outside_the_front_end_raise(nl, what):
     with pytest.raises(NotImplementedError, match=what):
         Sbdart(f"&INPUT {nl} /")
