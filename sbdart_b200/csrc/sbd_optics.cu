@@ -202,7 +202,10 @@ __device__ void aer_interp_dev(const double *wlb, const double *ext, const doubl
 // ---------------------------------------------------------------------------
 // K2: one WARP per (column, wavelength); lanes over the layers.
 // ---------------------------------------------------------------------------
-constexpr int kOptWarps = 4;                 // warps per CTA
+#ifndef SBD_OPT_WARPS
+#define SBD_OPT_WARPS 4
+#endif
+constexpr int kOptWarps = SBD_OPT_WARPS;     // warps per CTA
 constexpr int kLayerArrays = 15;             // per-warp shared arrays of kMaxZ doubles
 
 // Everything of taugas (taugas.f:2236-2534) that depends on the wavelength only: continuum
@@ -381,7 +384,7 @@ __device__ void taugas_warp(const OpticsArgs &a, const GasCoef &c, const double 
 #ifndef SBD_OPT_MINB
 #define SBD_OPT_MINB 4       // 16 warps per SM (128 registers): +5 % on the e2e arm against 8 warps at 255
 #endif
-__global__ void __launch_bounds__(kOptWarps * 32, SBD_OPT_MINB)
+__global__ void __launch_bounds__(kOptWarps * 32, SBD_OPT_MINB * 4 / kOptWarps)
 optics_kernel(const OpticsArgs a)
 {
     extern __shared__ double sm_opt[];
@@ -488,22 +491,36 @@ optics_kernel(const OpticsArgs a)
         for (int j = lane; j < nz; j += 32)
             for (int k = 0; k < 3; k++) dk2[k * kMaxZ + j] = dtk[k * kMaxZ + j];
         __syncwarp();
-        if (P.kdist >= 2 && amu0 > 0.) {
-            // slant-path correction: a Newton solve per layer on running sums (sequential over
-            // the layers); the three k-terms sit on lanes 0..2
-            double tauls = 0., tgl = 0.;
-            const int kk = lane < 3 ? lane : 0;
-            const double gk = lane < 3 ? gwk[kk] : 0.0;
-            for (int j = 0; j < nz; j++) {
-                tauls += dtls[j];
-                const double dj = dtk[kk * kMaxZ + j];
-                tgl += dj;
-                double cf;
-                taucor_warp(gk, lane < 3 ? tgl : 0.0, amu0, tauls, cf);
-                if (lane < 3) dk2[kk * kMaxZ + j] = tgl * (cf - 1.0) + dj;
-                tgl *= cf;
+    }
+    // slant-path correction (taucor, taugas.f:7650-7692): a Newton solve per layer on running sums,
+    // sequential over the layers.  One LANE per wavelength: the CTA's warps hand their k-terms to
+    // warp 0, whose lanes 0 .. kOptWarps-1 run the recurrences side by side (a warp that did it for
+    // its own wavelength would issue the same instructions for one wavelength only).
+    {
+        double *xch = sm_opt + (size_t)kOptWarps * kLayerArrays * kMaxZ + warp * 8;
+        if (lane == 0) {
+            xch[0] = gwk[0]; xch[1] = gwk[1]; xch[2] = gwk[2]; xch[3] = amu0;
+            xch[4] = (usek && P.kdist >= 2 && amu0 > 0.) ? 1.0 : 0.0;
+        }
+        __syncthreads();
+        if (warp == 0 && lane < kOptWarps && blockIdx.x * kOptWarps + lane < ncol * P.nwl) {
+            const double *x = sm_opt + (size_t)kOptWarps * kLayerArrays * kMaxZ + lane * 8;
+            if (x[4] != 0.0) {
+                const double *wsw = sm_opt + (size_t)lane * kLayerArrays * kMaxZ;
+                const double *w_dtls = wsw + 2 * kMaxZ, *w_dtk = wsw + 3 * kMaxZ;
+                double *w_dk2 = sm_opt + (size_t)lane * kLayerArrays * kMaxZ + 6 * kMaxZ;
+                const double g3[3] = { x[0], x[1], x[2] };
+                double tauls = 0., tglc[3] = { 0, 0, 0 };
+                for (int j = 0; j < nz; j++) {
+                    tauls += w_dtls[j];
+                    for (int k = 0; k < 3; k++) tglc[k] += w_dtk[k * kMaxZ + j];
+                    double cf;
+                    taucor_dev(g3, tglc, x[3], tauls, cf);
+                    for (int k = 0; k < 3; k++) { w_dk2[k * kMaxZ + j] = tglc[k] * (cf - 1.0) + w_dtk[k * kMaxZ + j]; tglc[k] *= cf; }
+                }
             }
         }
+        __syncthreads();
     }
     __syncwarp();
     if (amu0 <= 0.)      // taugas.f:7491 -- applies to the first slant column whatever nk is
@@ -714,7 +731,7 @@ cudaError_t launch_optics(const OpticsArgs &a, cudaStream_t st)
 {
     const int ncol = a.ncol > 0 ? a.ncol : 1;
     const int items = ncol * a.p.nwl, blocks = (items + kOptWarps - 1) / kOptWarps;
-    const size_t smem = (size_t)kOptWarps * kLayerArrays * kMaxZ * 8;
+    const size_t smem = ((size_t)kOptWarps * kLayerArrays * kMaxZ + kOptWarps * 8) * 8;
     optics_kernel<<<blocks, kOptWarps * 32, smem, st>>>(a);
     return cudaGetLastError();
 }
