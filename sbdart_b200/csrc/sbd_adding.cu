@@ -77,9 +77,11 @@ struct AddLayout {
     // phase 1: a layer is owned by a group of GW lanes (the n first ones hold a row / column /
     // mode each; for n = 10, 12 the rest shadow lane n-1)
     static constexpr int GW = n <= 2 ? 2 : (n <= 4 ? 4 : (n <= 8 ? 8 : 16));
-    // phase-1 shared memory per layer group: gl[N], K, L, P, X [n][n], 4 vectors
+    // phase-1 shared memory per layer group: gl[N], K, L, P, X [n][LD], 4 vectors.  Rows are n + 2
+    // doubles apart: row-wise accesses of the group's lanes (stride 16 B x odd) hit different banks
+    static constexpr int LD = n + 2;
     static constexpr int tasks = 32 / GW;
-    static constexpr int task0 = N + 4 * n * n + 4 * n;
+    static constexpr int task0 = N + 4 * n * LD + 4 * n;
     // padded to 4 (mod 16) doubles: the groups' areas start 8 banks apart, so the four
     // addresses of a group-wide broadcast load never share a bank
     static constexpr int task = ((task0 + 11) / 16) * 16 + 4;
@@ -92,7 +94,10 @@ struct AddLayout {
     {
         // y0, work area, taucpr / tauc / beam transmissions (2), pk (+2 boundary temperatures),
         // three prologue work values per layer, level map
-        size_t d = (size_t)N + work + 4 * (L + 1) + (L + 3) + 3 * L + (L + 2) / 2 + 2;
+        // (the prologue's three work values per layer live in the work area, or behind it when the
+        // atmosphere has more layers than the area can hold)
+        const size_t lwx = (size_t)(3 * L > work ? 3 * L - work : 0);
+        size_t d = (size_t)N + work + lwx + 4 * (L + 1) + (L + 3) + (L + 2) / 2 + 2;
         return (d + 1) & ~(size_t)1;
     }
     static constexpr int cta = 4 * n + N * n + 2;     // cmu cwt csq cd, ylm, sum(w mu), sum(w)
@@ -141,8 +146,8 @@ __device__ __forceinline__ int phase1_adding(
     double *tsm, double *rec, int g, bool gact, unsigned long long jpart)
 {
     using AL = AddLayout<n>;
-    constexpr int N = 2 * n, GW = AL::GW, PB = n > 8 ? 4 : 3;
-    double *sgl = tsm, *sK = sgl + N, *sL = sK + n * n, *sP = sL + n * n, *sX = sP + n * n, *sv = sX + n * n;
+    constexpr int N = 2 * n, GW = AL::GW, PB = n > 8 ? 4 : 3, LD = AL::LD;
+    double *sgl = tsm, *sK = sgl + N, *sL = sK + n * LD, *sP = sL + n * LD, *sX = sP + n * LD, *sv = sX + n * LD;
 
     double ss = ssalb[lc];
     if (ss == 1.0) ss = 1.0 - kDither;
@@ -210,7 +215,7 @@ __device__ __forceinline__ int phase1_adding(
     }
     if (gact) {
 #pragma unroll
-        for (int j = 0; j < n; j++) { sK[g * n + j] = pe[j]; sL[g * n + j] = po[j]; }
+        for (int j = 0; j < n; j++) { sK[g * LD + j] = pe[j]; sL[g * LD + j] = po[j]; }
     }
     __syncwarp();
 
@@ -219,12 +224,12 @@ __device__ __forceinline__ int phase1_adding(
     {
         double lcol[n];
 #pragma unroll
-        for (int k = 0; k < n; k++) lcol[k] = sL[k * n + g];
+        for (int k = 0; k < n; k++) lcol[k] = sL[k * LD + g];
 #pragma unroll
         for (int i = 0; i < n; i++) {
             double acc = 0.0;
 #pragma unroll
-            for (int k = i; k < n; k++) acc = fma(sK[k * n + i], lcol[k], acc);
+            for (int k = i; k < n; k++) acc = fma(sK[k * LD + i], lcol[k], acc);
             a[i] = acc;
         }
     }
@@ -286,12 +291,12 @@ __device__ __forceinline__ int phase1_adding(
     for (int i = n - 1; i >= 0; i--) {
         double acc = a[i];
 #pragma unroll
-        for (int k = i + 1; k < n; k++) acc = fma(-sK[k * n + i], P[k], acc);
+        for (int k = i + 1; k < n; k++) acc = fma(-sK[k * LD + i], P[k], acc);
         P[i] = acc * rK[i];
     }
     if (gact) {
 #pragma unroll
-        for (int i = 0; i < n; i++) sP[g * n + i] = P[i];     // [mode][direction]
+        for (int i = 0; i < n; i++) sP[g * LD + i] = P[i];     // [mode][direction]
     }
 
     // ---- particular solutions in the scaled variables (u^ = D u) ------------------------
@@ -316,12 +321,12 @@ __device__ __forceinline__ int phase1_adding(
         __syncwarp();
         double t1 = 0.0;                                    // (K^T b_d)_g
 #pragma unroll
-        for (int k = 0; k < n; k++) t1 = fma(sK[k * n + g], sv[k], t1);
+        for (int k = 0; k < n; k++) t1 = fma(sK[k * LD + g], sv[k], t1);
         if (gact) sv[n + g] = t1;
         __syncwarp();
         double t2 = 0.0;                                    // (K K^T b_d)_g
 #pragma unroll
-        for (int k = 0; k < n; k++) t2 = fma(sK[g * n + k], sv[n + k], t2);
+        for (int k = 0; k < n; k++) t2 = fma(sK[g * LD + k], sv[n + k], t2);
         if (gact) sv[2 * n + g] = bs * rmu0 - t2;           // r_g
         __syncwarp();
         double cj = 0.0;
@@ -331,7 +336,7 @@ __device__ __forceinline__ int phase1_adding(
         if (gact) sv[3 * n + g] = cj;
         __syncwarp();
 #pragma unroll
-        for (int j = 0; j < n; j++) tg = fma(sP[j * n + g], sv[3 * n + j], tg);     // (P c)_g
+        for (int j = 0; j < n; j++) tg = fma(sP[j * LD + g], sv[3 * n + j], tg);     // (P c)_g
         if (gact) sv[g] = tg;
     } else {
         __syncwarp();
@@ -347,7 +352,7 @@ __device__ __forceinline__ int phase1_adding(
             double a1 = sv[i], a2 = sv[n + i];
 #pragma unroll
             for (int k = 0; k < i; k++) {
-                const double lik = sL[i * n + k];
+                const double lik = sL[i * LD + k];
                 a1 = fma(-lik, y1[k], a1);
                 a2 = fma(-lik, y2[k], a2);
             }
@@ -359,7 +364,7 @@ __device__ __forceinline__ int phase1_adding(
             double a1 = y1[i], a2 = y2[i];
 #pragma unroll
             for (int k = i + 1; k < n; k++) {
-                const double lki = sL[k * n + i];
+                const double lki = sL[k * LD + i];
                 a1 = fma(-lki, z1[k], a1);
                 a2 = fma(-lki, zq[k], a2);
             }
@@ -379,7 +384,7 @@ __device__ __forceinline__ int phase1_adding(
     for (int j = 0; j < n; j++) {
         double acc = 0.0;
 #pragma unroll
-        for (int i = 0; i < n; i++) acc = fma(P[i], sP[j * n + i], acc);
+        for (int i = 0; i < n; i++) acc = fma(P[i], sP[j * LD + i], acc);
         bp[j] = acc; bm[j] = acc;
     }
     {
@@ -418,7 +423,7 @@ __device__ __forceinline__ int phase1_adding(
         for (int j = 0; j < n; j++) {
 #pragma unroll
             for (int b = 0; b < n; b++) {
-                const double pj = sP[j * n + b];
+                const double pj = sP[j * LD + b];
                 up[b] = fma(bp[j], pj, up[b]);
                 um[b] = fma(bm[j], pj, um[b]);
             }
@@ -426,7 +431,7 @@ __device__ __forceinline__ int phase1_adding(
         __syncwarp();           // everyone is done reading K
         if (gact) {
 #pragma unroll
-            for (int b = 0; b < n; b++) { sK[g * n + b] = up[b]; sX[g * n + b] = um[b]; }
+            for (int b = 0; b < n; b++) { sK[g * LD + b] = up[b]; sX[g * LD + b] = um[b]; }
         }
     }
     if (gact) { sv[g] = zup; sv[n + g] = zdn; }
@@ -443,11 +448,11 @@ __device__ __forceinline__ int phase1_adding(
 #pragma unroll
 #endif
         for (int j = 0; j < n; j++) {
-            const double pa = sP[j * n + g];
+            const double pa = sP[j * LD + g];
 #pragma unroll
             for (int b = 0; b < n; b++) {
-                mp[b] = fma(pa, sK[j * n + b], mp[b]);
-                mm[b] = fma(pa, sX[j * n + b], mm[b]);
+                mp[b] = fma(pa, sK[j * LD + b], mp[b]);
+                mm[b] = fma(pa, sX[j * LD + b], mm[b]);
             }
         }
 #pragma unroll
@@ -521,11 +526,11 @@ disort_adding_kernel(const LaunchArgs a)
     double *wsm = smem_add + AL::cta + (size_t)warp * AL::warp_doubles(L);
     double *y0 = wsm;
     double *work = y0 + N;
-    double *taucpr = work + AL::work, *tauc = taucpr + (L + 1);
+    double *lw = work;                  // prologue only: 3 x L work values
+    double *taucpr = work + (3 * L > AL::work ? 3 * L : AL::work), *tauc = taucpr + (L + 1);
     double *ebeam = tauc + (L + 1), *edir = ebeam + (L + 1);
     double *pk = edir + (L + 1);
-    double *lw = pk + (L + 3);
-    int *layru = (int *)(lw + 3 * L);
+    int *layru = (int *)(pk + (L + 3));
 
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         double mu = a.quad[i], wt = a.quad[n + i];
