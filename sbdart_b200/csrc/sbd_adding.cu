@@ -396,12 +396,28 @@ __device__ __forceinline__ int phase1_adding(
         for (int j = 0; j < n; j++)
             if (j == g) { bp[j] += lam_p; bm[j] += lam_m; }
     }
-    // in-place Gauss-Jordan inversion of both SPD matrices (no pivoting), row per lane
+    // in-place Gauss-Jordan inversion of both SPD matrices (no pivoting), row per lane.  The pivot
+    // rows travel through shared memory (the owner stores 2n doubles, everyone loads them with
+    // broadcast reads: half the shared-memory-pipe instructions of 2n double shuffles); two
+    // buffers in the vector area, one warp barrier per step.
+    __syncwarp();               // (the triangular solves above read the vector area)
 #pragma unroll
     for (int j = 0; j < n; j++) {
+        double *pb = sv + (j & 1) * 2 * n;
+        if (gact && g == j) {
+#pragma unroll
+            for (int c = 0; c < n; c += 2) {
+                reinterpret_cast<double2 *>(pb)[c / 2] = make_double2(bp[c], bp[c + 1]);
+                reinterpret_cast<double2 *>(pb + n)[c / 2] = make_double2(bm[c], bm[c + 1]);
+            }
+        }
+        __syncwarp();
         double pr[n], qr[n];
 #pragma unroll
-        for (int c = 0; c < n; c++) { pr[c] = shfl_d(bp[c], j, GW); qr[c] = shfl_d(bm[c], j, GW); }
+        for (int c = 0; c < n; c += 2) {
+            const double2 u = reinterpret_cast<const double2 *>(pb)[c / 2], w = reinterpret_cast<const double2 *>(pb + n)[c / 2];
+            pr[c] = u.x; pr[c + 1] = u.y; qr[c] = w.x; qr[c + 1] = w.y;
+        }
         const double rp = fast_rcp(pr[j]), rq = fast_rcp(qr[j]);
         if (!(pr[j] > 0.0) || !(qr[j] > 0.0)) bad = 1;
         // row j (the pivot row, own row of lane j) becomes row / pivot = row - (1 - 1/pivot) row:
@@ -414,6 +430,7 @@ __device__ __forceinline__ int phase1_adding(
             bm[c] = (c == j) ? dq : fma(-mq, qr[c], bm[c]);
         }
     }
+    __syncwarp();
     // U+- = B+-^-1 P^T (row g), stored over K and X
     {
         double up[n], um[n];
