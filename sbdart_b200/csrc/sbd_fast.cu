@@ -97,7 +97,10 @@ struct FastLayout {
     // ---- shared memory (doubles) ----
     static constexpr int cta = 4 * n + N * n + 2;   // cmu cwt csq cdinv, ylm, sum(w mu), sum(w)
     static constexpr int tasks = 32 / n;
-    static constexpr int task = N + 4 * n * n + 4 * n;     // gl, K, L, G1, G2, vectors
+    // gl, K, L, G1, G2 [n][LD], vectors.  Rows n + 2 doubles apart (row-wise accesses of a layer group's
+    // lanes hit different banks), areas padded to 4 (mod 16) doubles (the groups' broadcast loads too)
+    static constexpr int LD = n + 2;
+    static constexpr int task = ((N + 4 * n * LD + 4 * n + 11) / 16) * 16 + 4;
     // work area shared by the phases: per-task areas (phase 1), 3 records + assembled rows (phase 2),
     // 2 x (pivot rows + flux record) (phase 3)
     static constexpr int cmax(int a, int b) { return a > b ? a : b; }
@@ -170,9 +173,9 @@ __device__ __forceinline__ int phase1_layers(
     unsigned jpart /* Jacobi partners of this lane, see jacobi_partners */)
 {
     using FL = FastLayout<n>;
-    constexpr int N = 2 * n;
-    double *sgl = tsm, *sK = sgl + N, *sL = sK + n * n, *sG1 = sL + n * n, *sG2 = sG1 + n * n,
-           *sv = sG2 + n * n;   // sv: 4 vectors of n
+    constexpr int N = 2 * n, LD = FL::LD;
+    double *sgl = tsm, *sK = sgl + N, *sL = sK + n * LD, *sG1 = sL + n * LD, *sG2 = sG1 + n * LD,
+           *sv = sG2 + n * LD;   // sv: 4 vectors of n
 
     double ss = ssalb[lc];
     if (ss == 1.0) ss = 1.0 - kDither;
@@ -239,7 +242,7 @@ __device__ __forceinline__ int phase1_layers(
         po[j] = (g == j) ? pivo * rio : ((g > j) ? numo * rio : 0.0);
     }
 #pragma unroll
-    for (int j = 0; j < n; j++) { sK[g * n + j] = pe[j]; sL[g * n + j] = po[j]; }
+    for (int j = 0; j < n; j++) { sK[g * LD + j] = pe[j]; sL[g * LD + j] = po[j]; }
     __syncwarp();
 
     // column g of A = K^T L
@@ -247,12 +250,12 @@ __device__ __forceinline__ int phase1_layers(
     {
         double lcol[n];
 #pragma unroll
-        for (int k = 0; k < n; k++) lcol[k] = sL[k * n + g];
+        for (int k = 0; k < n; k++) lcol[k] = sL[k * LD + g];
 #pragma unroll
         for (int i = 0; i < n; i++) {
             double acc = 0.0;
 #pragma unroll
-            for (int k = i; k < n; k++) acc = fma(sK[k * n + i], lcol[k], acc);
+            for (int k = i; k < n; k++) acc = fma(sK[k * LD + i], lcol[k], acc);
             a[i] = acc;
         }
     }
@@ -327,7 +330,7 @@ __device__ __forceinline__ int phase1_layers(
     for (int i = n - 1; i >= 0; i--) {
         double acc = a[i];
 #pragma unroll
-        for (int k = i + 1; k < n; k++) acc = fma(-sK[k * n + i], P[k], acc);
+        for (int k = i + 1; k < n; k++) acc = fma(-sK[k * LD + i], P[k], acc);
         P[i] = acc * rK[i];
     }
     {
@@ -336,14 +339,14 @@ __device__ __forceinline__ int phase1_layers(
         for (int i = 0; i < n; i++) {
             double acc = P[i];
 #pragma unroll
-            for (int k = 0; k < i; k++) acc = fma(-sL[i * n + k], y[k], acc);
+            for (int k = 0; k < i; k++) acc = fma(-sL[i * LD + k], y[k], acc);
             y[i] = acc * rL[i];
         }
 #pragma unroll
         for (int i = n - 1; i >= 0; i--) {
             double acc = y[i];
 #pragma unroll
-            for (int k = i + 1; k < n; k++) acc = fma(-sL[k * n + i], Q[k], acc);
+            for (int k = i + 1; k < n; k++) acc = fma(-sL[k * LD + i], Q[k], acc);
             Q[i] = acc * rL[i];
         }
     }
@@ -357,8 +360,8 @@ __device__ __forceinline__ int phase1_layers(
     for (int i = 0; i < n; i++) {
         gd[i] = cdinv[i] * Q[i];
         gs[i] = -cdinv[i] * P[i] * rk;
-        sG1[g * n + i] = gs[i];      // [mode j][direction i]
-        sG2[g * n + i] = gd[i];
+        sG1[g * LD + i] = gs[i];      // [mode j][direction i]
+        sG2[g * LD + i] = gd[i];
         const double gpi = 0.5 * (gs[i] + gd[i]), gmi = 0.5 * (gs[i] - gd[i]);
         const double wm = cwt[i] * cmu[i];
         fA = fma(wm, gpi, fA);
@@ -398,12 +401,12 @@ __device__ __forceinline__ int phase1_layers(
         __syncwarp();
         double t1 = 0.0;                                    // (K^T b^_d)_g
 #pragma unroll
-        for (int k = 0; k < n; k++) t1 = fma(sK[k * n + g], sv[k], t1);
+        for (int k = 0; k < n; k++) t1 = fma(sK[k * LD + g], sv[k], t1);
         sv[n + g] = t1;
         __syncwarp();
         double t2 = 0.0;                                    // (K K^T b^_d)_g
 #pragma unroll
-        for (int k = 0; k < n; k++) t2 = fma(sK[g * n + k], sv[n + k], t2);
+        for (int k = 0; k < n; k++) t2 = fma(sK[g * LD + k], sv[n + k], t2);
         sv[2 * n + g] = bs * rmu0 - t2;                     // r_g
         __syncwarp();
         double cj = 0.0;                                    // (P^T r)_g / (1/mu0^2 - k^2)
@@ -417,8 +420,8 @@ __device__ __forceinline__ int phase1_layers(
         double dv = 0.0, sv2 = 0.0;
 #pragma unroll
         for (int j = 0; j < n; j++) {
-            dv = fma(sG2[j * n + g], sv[3 * n + j], dv);
-            sv2 = fma(sG1[j * n + g], sv[j], sv2);
+            dv = fma(sG2[j * LD + g], sv[3 * n + j], dv);
+            sv2 = fma(sG1[j * LD + g], sv[j], sv2);
         }
         sv2 = umu0 * (cdinv[g] * bd + sv2);
         zup = 0.5 * (sv2 + dv);
@@ -436,14 +439,14 @@ __device__ __forceinline__ int phase1_layers(
         for (int i = 0; i < n; i++) {
             double acc = cmu[i] * csq[i];      // D_i = sqrt(w mu) = mu sqrt(w/mu)
 #pragma unroll
-            for (int k = 0; k < i; k++) acc = fma(-sL[i * n + k], y[k], acc);
+            for (int k = 0; k < i; k++) acc = fma(-sL[i * LD + k], y[k], acc);
             y[i] = acc * rL[i];
         }
 #pragma unroll
         for (int i = n - 1; i >= 0; i--) {
             double acc = y[i];
 #pragma unroll
-            for (int k = i + 1; k < n; k++) acc = fma(-sL[k * n + i], z[k], acc);
+            for (int k = i + 1; k < n; k++) acc = fma(-sL[k * LD + i], z[k], acc);
             z[i] = acc * rL[i];
             if (i == g) q = cdinv[i] * z[i];
         }
