@@ -722,35 +722,36 @@ __device__ __forceinline__ void user_terms_fast(
 // the layer top; else the layer bottom.
 template <int n>
 __device__ __forceinline__ double layer_source(const double *gu /* GU row of this angle */, const double *kk,
-                                               const double *ek, double umu, double t0, double t1,
+                                               const double *ek, double umu, double rmu /* 1 / umu */,
+                                               double rdenom /* 1 / (1 + umu/umu0), 0: L'Hospital */,
+                                               double t0, double t1,
                                                double eb0, double eb1 /* beam transmission at t0, t1 */,
                                                bool beam, double umu0, bool therm, double &T)
 {
     constexpr int N = 2 * n;
     const double dtau = t1 - t0;
     const bool up = umu > 0.0;
-    const double rmu = 1.0 / umu;
     T = exp(-dtau * fabs(rmu));
     double s = 0.0;
     if (beam) {
-        const double denom = 1. + umu / umu0;
         double expn;
-        if (fabs(denom) < 0.0001) expn = (dtau / umu0) * (up ? eb0 : eb1);
-        else expn = up ? (eb0 - T * eb1) / denom : (eb1 - T * eb0) / denom;
+        if (rdenom == 0.0) expn = (dtau / umu0) * (up ? eb0 : eb1);
+        else expn = up ? (eb0 - T * eb1) * rdenom : (eb1 - T * eb0) * rdenom;
         s = gu[N] * expn;
     }
 #pragma unroll 1
     for (int j = 0; j < n; j++) {
         const double k = kk[j], wk = ek[j];
-        // column n-1-j belongs to -k_j, column n+j to +k_j (disort.f:3264-3312)
+        // column n-1-j belongs to -k_j, column n+j to +k_j (disort.f:3264-3312); the divisions by
+        // 1 -+ umu k are reciprocal multiplications (the IEEE division costs ~40 instructions each)
         const double dm = 1.0 - umu * k, dp = 1.0 + umu * k;
         double em, ep;
         if (up) {
-            em = (fabs(dm) < 0.0001) ? dtau * rmu * T : (wk - T) / dm;
-            ep = (1.0 - T * wk) / dp;
+            em = (fabs(dm) < 0.0001) ? dtau * rmu * T : (wk - T) * fast_rcp(dm);
+            ep = (1.0 - T * wk) * fast_rcp(dp);
         } else {
-            em = (1.0 - T * wk) / dm;
-            ep = (fabs(dp) < 0.0001) ? -dtau * rmu * T : (wk - T) / dp;
+            em = (1.0 - T * wk) * fast_rcp(dm);
+            ep = (fabs(dp) < 0.0001) ? -dtau * rmu * T : (wk - T) * fast_rcp(dp);
         }
         s = fma(gu[n - 1 - j], em, s);
         s = fma(gu[n + j], ep, s);
@@ -1399,9 +1400,11 @@ disort_fast_kernel(const LaunchArgs a)
                                        (2. - delm0) * fbeam / (4.0 * kPiRef), therm, oprim, uE, uGU, lane);
                     for (int iu = lane; iu < NU; iu += 32) {
                         const double umu = a.umu[iu];
+                        const double rmu = fast_rcp(umu), denom = 1. + umu / umu0;
                         double T;
                         const double S = layer_source<n>(uGU + iu * FL::ecols, urec + FL::off_kk, urec + FL::off_ek,
-                                                         umu, taucpr[lc], taucpr[lc + 1], ebeam[lc], ebeam[lc + 1],
+                                                         umu, rmu, fabs(denom) < 0.0001 ? 0.0 : fast_rcp(denom),
+                                                         taucpr[lc], taucpr[lc + 1], ebeam[lc], ebeam[lc + 1],
                                                          fbeam > 0.0, umu0, therm, T);
                         if (umu > 0.0) {
                             const double below = T * uI[iu];
