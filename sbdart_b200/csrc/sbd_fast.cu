@@ -96,6 +96,8 @@ struct FastLayout {
     __host__ __device__ static size_t slot_doubles(int L) { return (size_t)L * (rec + frec + ublk); }
     // ---- shared memory (doubles) ----
     static constexpr int cta = 4 * n + N * n + 2;   // cmu cwt csq cdinv, ylm, sum(w mu), sum(w)
+    // radiance runs: Y_l^m at the user cosines of the current azimuth mode, CTA-shared
+    __host__ __device__ static size_t cta_doubles(int NU) { return (size_t)cta + (((size_t)N * NU + 1) & ~(size_t)1); }
     static constexpr int tasks = 32 / n;
     // gl, K, L, G1, G2 [n][LD], vectors.  Rows n + 2 doubles apart (row-wise accesses of a layer group's
     // lanes hit different banks), areas padded to 4 (mod 16) doubles (the groups' broadcast loads too)
@@ -652,7 +654,7 @@ __device__ __forceinline__ void lepoly_mode(int m, int N, double x, double *y)
 template <int n>
 __device__ __forceinline__ void user_terms_fast(
     const double *rec, const double (&xs)[2 * n], const double *gl, const double *cwt,
-    const double *cylm, const double *y0, const double *__restrict__ ylmu_m, int NU, int mazim,
+    const double *cylm, const double *y0, const double *ylmu_m, int NU, int mazim,
     bool beam, double fact, bool therm, double oprim, double *E, double *GU, int lane)
 {
     using FL = FastLayout<n>;
@@ -706,7 +708,7 @@ __device__ __forceinline__ void user_terms_fast(
     for (int e = lane; e < NU * EC; e += 32) {
         const int iu = e / EC, c = e - iu * EC;
         double acc = 0.0;
-        for (int l = mazim; l < N; l++) acc = fma(E[l * EC + c], __ldg(ylmu_m + l * NU + iu), acc);
+        for (int l = mazim; l < N; l++) acc = fma(E[l * EC + c], ylmu_m[l * NU + iu], acc);
         if (therm && c == N + 1) acc += (1. - oprim) * xr0;
         if (therm && c == N + 2) acc += (1. - oprim) * xr1;
         GU[e] = acc;
@@ -787,7 +789,8 @@ disort_fast_kernel(const LaunchArgs a)
     extern __shared__ double smem_fast[];
     double *cmu = smem_fast, *cwt = cmu + n, *csq = cwt + n, *cdinv = csq + n;
     double *cylm = cdinv + n + 2;       // cylm[-2] = sum(w mu), cylm[-1] = sum(w)
-    double *wsm = smem_fast + FL::cta + (size_t)warp * FL::warp_doubles(L, NT, NU, NPHI);
+    double *cylmu = smem_fast + FL::cta;
+    double *wsm = smem_fast + FL::cta_doubles(NU) + (size_t)warp * FL::warp_doubles(L, NT, NU, NPHI);
     double *y0 = wsm;
     // 16-byte aligned work area: per-task areas in phase 1, cp.async staging afterwards
     double *tsm_base = y0 + N;
@@ -996,13 +999,14 @@ disort_fast_kernel(const LaunchArgs a)
             const bool mact = !status && mazim <= naz;
             if (!__syncthreads_or(mact)) break;
             for (int e = threadIdx.x; e < N * n; e += blockDim.x) cylm[e] = a.ylmc[(size_t)mazim * N * n + e];
+            for (int e = threadIdx.x; e < N * NU; e += blockDim.x) cylmu[e] = a.ylmu[(size_t)mazim * N * NU + e];
             if (lane == 0 && fbeam > 0.0 && mazim > 0) lepoly_mode(mazim, N, -umu0, y0);
             __syncthreads();
         } else if (mazim > 0) break;
         const bool mrun = !RAD || mazim <= naz;      // false: parked, only attends the barriers
         const bool m0 = !RAD || mazim == 0;
         const double delm0 = m0 ? 1.0 : 0.0;
-        const double *ylmu_m = RAD ? a.ylmu + (size_t)mazim * N * NU : nullptr;
+        const double *ylmu_m = RAD ? cylmu : nullptr;       // this mode's table (shared memory)
         // ===================== phase 1 =====================================
         if (mrun && !status) {
             for (int lc0 = 0; lc0 < ncut; lc0 += TASKS) {
@@ -1224,6 +1228,14 @@ disort_fast_kernel(const LaunchArgs a)
             fetch_layer(ncut - 1, 0);
             for (int lc = ncut - 1; lc >= 0; lc--) {
                 const int buf = (ncut - 1 - lc) & 1;
+                // radiance runs: the layer's single-scattering albedo and moments for g_l, loaded
+                // here so that the back substitution hides their latency
+                double rad_ss = 0.0, rad_f = 0.0, rad_pm = 1.0;
+                if (RAD) {
+                    rad_ss = ssalb[lc];
+                    rad_f = pmom[(size_t)lc * ldp + N];
+                    if (lane > 0 && lane < N) rad_pm = pmom[(size_t)lc * ldp + lane];
+                }
 #ifdef SBD_PHASE_TIMING
                 long long tsub = clock64();
 #endif
@@ -1378,15 +1390,13 @@ disort_fast_kernel(const LaunchArgs a)
                     // ---- intensities at the user angles (TERPEV, TERPSO, USRINT) ----
                     const double *urec = fr + FL::frec;
                     const double *sc = fr + FL::f_sc;
-                    double ss = ssalb[lc];
+                    double ss = rad_ss;
                     if (ss == 1.0) ss = 1.0 - kDither;
-                    const double f = pmom[(size_t)lc * ldp + N];
+                    const double f = rad_f;
                     const double oprim = ss * (1. - f) / (1. - f * ss);
                     (void)sc;
-                    if (lane < N) {                      // g_l of this layer (delta-M, disort.f:2583)
-                        const double pm = (lane == 0) ? 1.0 : pmom[(size_t)lc * ldp + lane];
-                        ugl[lane] = (2 * lane + 1) * oprim * (pm - f) / (1. - f);
-                    }
+                    if (lane < N)                        // g_l of this layer (delta-M, disort.f:2583)
+                        ugl[lane] = (2 * lane + 1) * oprim * (rad_pm - f) / (1. - f);
                     __syncwarp();
                     const bool therm = plank && m0;
                     if (lc == ncut - 1)                   // intensity entering the bottom layer from below
@@ -1499,7 +1509,7 @@ template <int n>
 static cudaError_t launch_fast_t(const LaunchArgs &a, int warps, int grid, cudaStream_t st)
 {
     const int L = a.d.nlyr, NT = a.d.ntau > 0 ? a.d.ntau : L + 1;
-    size_t smem = 8 * (FastLayout<n>::cta + (size_t)warps * FastLayout<n>::warp_doubles(L, NT, a.d.numu, a.d.nphi));
+    size_t smem = 8 * (FastLayout<n>::cta_doubles(a.d.numu) + (size_t)warps * FastLayout<n>::warp_doubles(L, NT, a.d.numu, a.d.nphi));
     if (a.d.numu > 0) {      // radiance runs: CTA-synchronous always
         switch (warps) {
         case 4: return launch_fast_k<n, 4, true, true>(a, grid, smem, st);
@@ -1530,9 +1540,9 @@ size_t fast_slot_doubles(int N, int L, int NU)
 size_t fast_smem_bytes(int N, int L, int NT, int warps, int NU, int NPHI)
 {
     switch (N) {
-    case 4: return 8 * (FastLayout<2>::cta + (size_t)warps * FastLayout<2>::warp_doubles(L, NT, NU, NPHI));
-    case 8: return 8 * (FastLayout<4>::cta + (size_t)warps * FastLayout<4>::warp_doubles(L, NT, NU, NPHI));
-    case 16: return 8 * (FastLayout<8>::cta + (size_t)warps * FastLayout<8>::warp_doubles(L, NT, NU, NPHI));
+    case 4: return 8 * (FastLayout<2>::cta_doubles(NU) + (size_t)warps * FastLayout<2>::warp_doubles(L, NT, NU, NPHI));
+    case 8: return 8 * (FastLayout<4>::cta_doubles(NU) + (size_t)warps * FastLayout<4>::warp_doubles(L, NT, NU, NPHI));
+    case 16: return 8 * (FastLayout<8>::cta_doubles(NU) + (size_t)warps * FastLayout<8>::warp_doubles(L, NT, NU, NPHI));
     }
     return 0;
 }
