@@ -380,12 +380,27 @@ __device__ __forceinline__ int phase1_adding(
 
     // ---- B+- = P^T P + diag(k tanh(kh) | k coth(kh)), row g (mode g) ---------------------
     double bp[n], bm[n];
+    if constexpr (n > 8) {
+        // large n: rolled loops (the code of this phase would not stay in the instruction cache);
+        // the row goes through the X area because bp[j] cannot be indexed at run time
+#pragma unroll 1
+        for (int j = 0; j < n; j++) {
+            double acc = 0.0;
 #pragma unroll
-    for (int j = 0; j < n; j++) {
-        double acc = 0.0;
+            for (int i = 0; i < n; i++) acc = fma(P[i], sP[j * LD + i], acc);
+            if (gact) sX[g * LD + j] = acc;
+        }
+        __syncwarp();
 #pragma unroll
-        for (int i = 0; i < n; i++) acc = fma(P[i], sP[j * LD + i], acc);
-        bp[j] = acc; bm[j] = acc;
+        for (int j = 0; j < n; j++) { bp[j] = sX[g * LD + j]; bm[j] = bp[j]; }
+    } else {
+#pragma unroll
+        for (int j = 0; j < n; j++) {
+            double acc = 0.0;
+#pragma unroll
+            for (int i = 0; i < n; i++) acc = fma(P[i], sP[j * LD + i], acc);
+            bp[j] = acc; bm[j] = acc;
+        }
     }
     {
         const double x = expm1(-kk * dtaucp);               // e^{-2kh} - 1
@@ -436,13 +451,33 @@ __device__ __forceinline__ int phase1_adding(
         double up[n], um[n];
 #pragma unroll
         for (int b = 0; b < n; b++) { up[b] = 0.0; um[b] = 0.0; }
+        if constexpr (n > 8) {
+            // rolled over j: the rows of the inverses wait in the K and X areas
+            __syncwarp();       // everyone is done reading K (and X)
+            if (gact) {
 #pragma unroll
-        for (int j = 0; j < n; j++) {
+                for (int j = 0; j < n; j++) { sK[g * LD + j] = bp[j]; sX[g * LD + j] = bm[j]; }
+            }
+            __syncwarp();
+#pragma unroll 1
+            for (int j = 0; j < n; j++) {
+                const double bpj = sK[g * LD + j], bmj = sX[g * LD + j];
 #pragma unroll
-            for (int b = 0; b < n; b++) {
-                const double pj = sP[j * LD + b];
-                up[b] = fma(bp[j], pj, up[b]);
-                um[b] = fma(bm[j], pj, um[b]);
+                for (int b = 0; b < n; b++) {
+                    const double pj = sP[j * LD + b];
+                    up[b] = fma(bpj, pj, up[b]);
+                    um[b] = fma(bmj, pj, um[b]);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < n; j++) {
+#pragma unroll
+                for (int b = 0; b < n; b++) {
+                    const double pj = sP[j * LD + b];
+                    up[b] = fma(bp[j], pj, up[b]);
+                    um[b] = fma(bm[j], pj, um[b]);
+                }
             }
         }
         __syncwarp();           // everyone is done reading K
