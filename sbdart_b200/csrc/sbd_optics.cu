@@ -13,6 +13,7 @@
 
 #include "sbd_internal.h"
 #include "sbd_optics.cuh"
+#include "sbd_devutil.cuh"
 
 namespace sbd {
 
@@ -98,41 +99,22 @@ __device__ void abcdta_dev(const OpticsTables &T, int iv, BandState &s)
 
 __device__ double raysig_dev(double v) { return v * v * v * v / (F32(9.38076e+18) + F32(-1.08426e+09) * v * v); }
 
-// taucor with the three k-terms on lanes 0..2 of the calling warp (every lane calls; gk, tk:
-// the lane's own term, 0 beyond lane 2).  Same Newton iteration and the same summation order
-// (ff = e0 + e1 + e2) as the scalar form below.
-__device__ __forceinline__ bool taucor_warp(double gk, double tk, double amu, double utau, double &cf)
-{
-    cf = 1.;
-    if (utau > 12.0) return true;
-    for (int it = 0; it < 20; it++) {
-        const double e = gk * exp(-cf * tk / amu), es = e * tk;
-        const double e0 = __shfl_sync(0xffffffffu, e, 0), e1 = __shfl_sync(0xffffffffu, e, 1), e2 = __shfl_sync(0xffffffffu, e, 2);
-        const double s0 = __shfl_sync(0xffffffffu, es, 0), s1 = __shfl_sync(0xffffffffu, es, 1), s2 = __shfl_sync(0xffffffffu, es, 2);
-        const double ff = (e0 + e1) + e2, fs = (s0 + s1) + s2;
-        const double f = log(ff) + utau;
-        if (fabs(f) < F32(0.000001)) return true;
-        const double fp = -fs / (ff * amu);
-        cf += -f / fp;
-    }
-    return false;
-}
-
-// taucor (taugas.f:7650-7692); returns false when the Newton iteration fails
+// taucor (taugas.f:7650-7692); returns false when the Newton iteration fails.  The recurrence is the
+// longest dependency chain of the kernel: its divisions are reciprocal multiplications
+// (tau / amu once per call, cf -= f / f' as f ff amu / fs with one reciprocal).
 __device__ bool taucor_dev(const double *gwk, const double *tau, double amu, double utau, double &cf)
 {
     cf = 1.;
     if (utau > 12.0) return true;
+    const double ramu = fast_rcp(amu);
+    const double t0 = tau[0] * ramu, t1 = tau[1] * ramu, t2 = tau[2] * ramu;
     for (int it = 0; it < 20; it++) {
-        double ff = 0.0, fs = 0.0;
-        for (int k = 0; k < 3; k++) {
-            const double e = gwk[k] * exp(-cf * tau[k] / amu);
-            ff += e; fs += e * tau[k];
-        }
+        const double e0 = gwk[0] * exp(-cf * t0), e1 = gwk[1] * exp(-cf * t1), e2 = gwk[2] * exp(-cf * t2);
+        const double ff = (e0 + e1) + e2;
+        const double fs = fma(e2, tau[2], fma(e1, tau[1], e0 * tau[0]));
         const double f = log(ff) + utau;
         if (fabs(f) < F32(0.000001)) return true;
-        const double fp = -fs / (ff * amu);
-        cf += -f / fp;
+        cf = fma(f * (ff * amu), fast_rcp(fs), cf);        // cf += -f / fp, fp = -fs / (ff amu)
     }
     return false;
 }
