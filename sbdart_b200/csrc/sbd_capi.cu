@@ -222,8 +222,9 @@ extern "C" int sbd_set_surfaces(sbd_handle *h, int32_t nsurf, int32_t nstr, int3
     if (cudaSetDevice(h->device) != cudaSuccess) return SBD_ERR_CUDA;
     if (h->surfaces.reserve((n_bdr + n_bem + n_rmu + n_emu) * 8) != cudaSuccess) return SBD_ERR_CUDA;
     double *d = (double *)h->surfaces.p;
-    // (the stream may still read the previous tables)
+    // (launches in flight may still read the previous tables)
     if (cudaStreamSynchronize(h->stream) != cudaSuccess) return SBD_ERR_CUDA;
+    if (h->stream2 && cudaStreamSynchronize(h->stream2) != cudaSuccess) return SBD_ERR_CUDA;
     if (cudaMemcpy(d, bdr, n_bdr * 8, cudaMemcpyHostToDevice) != cudaSuccess) return SBD_ERR_CUDA;
     if (cudaMemcpy(d + n_bdr, bem, n_bem * 8, cudaMemcpyHostToDevice) != cudaSuccess) return SBD_ERR_CUDA;
     if (numu > 0) {
