@@ -35,6 +35,7 @@
 #include "sbd_internal.h"
 #include "sbd_planck.cuh"
 #include "sbd_devutil.cuh"
+#include "sbd_addops.cuh"
 
 // Staging of scratch data between the phases (global -> shared): bulk asynchronous copies
 // (cp.async.bulk: the TMA engine, one instruction by one lane, completion on an mbarrier) or
@@ -163,7 +164,7 @@ __device__ __forceinline__ unsigned jacobi_partners(int g)
 // ---------------------------------------------------------------------------
 // phase 1: one layer per group of n lanes
 // ---------------------------------------------------------------------------
-template <int n>
+template <int n, bool ADDREC>
 __device__ __forceinline__ int phase1_layers(
     const double *__restrict__ dtauc, const double *__restrict__ ssalb,
     const double *__restrict__ pmom, int ldp, int lc, bool active, int mazim,
@@ -172,7 +173,8 @@ __device__ __forceinline__ int phase1_layers(
     const double *y0, const double *taucpr, const double *pk,
     double *tsm /* per-task shared */, double *rec /* scratch record of this layer */,
     double *frec /* flux record of this layer */, int g /* lane in group */,
-    unsigned jpart /* Jacobi partners of this lane, see jacobi_partners */)
+    unsigned jpart /* Jacobi partners of this lane, see jacobi_partners */,
+    double *arec = nullptr /* ADDREC: the layer's R, T, s_up, s_dn */, const double *ebeam = nullptr)
 {
     using FL = FastLayout<n>;
     constexpr int N = 2 * n, LD = FL::LD;
@@ -475,6 +477,16 @@ __device__ __forceinline__ int phase1_layers(
         rec[FL::off_zp0 + n - 1 - g] = xr0 - xr1 * q;
         if (g == 0) { rec[FL::off_xr] = xr0; rec[FL::off_xr + 1] = xr1; }
     }
+    if (ADDREC) {
+        // the layer's reflection / transmission operators and sources for the adding sweeps
+        // (scaled variables u^ = D u, D = sqrt(w mu) = 1 / cdinv)
+        const double Dg = cmu[g] * csq[g];
+        const bool therm = plank && mazim == 0;
+        bad |= layer_operators<n, LD>(P, kk, dtaucp, zup * Dg, zdn * Dg, q * Dg, xr1,
+                                      therm ? pk[lc] : 0.0, therm ? pk[lc + 1] : 0.0,
+                                      fbeam > 0.0 ? ebeam[lc] : 0.0, fbeam > 0.0 ? ebeam[lc + 1] : 0.0,
+                                      fbeam > 0.0, therm, cmu, csq, sG1, sK, sG2, sv, arec, active, g);
+    }
     __syncwarp();
     return (bad && active) ? SBD_BIN_EIG_FAIL : 0;
 }
@@ -774,11 +786,17 @@ __device__ __forceinline__ double layer_source(const double *gu /* GU row of thi
 // RAD: intensities at user angles (a.d.numu > 0): the phases are repeated for every azimuth
 // mode, phase 3 also re-expands the layer solutions at the user cosines and integrates the
 // source function (levels = layer boundaries, a.d.ntau == 0; always CTA-synchronous).
-template <int n, int WARPS, bool SYNC, bool RAD>
+// ADD (radiance runs): the boundary-value problem in the adding form (sbd_addops.cuh) instead of
+// the elimination: two sweeps leave the intensities at every interface, and the layer solutions
+// the source-function integration needs follow from them by the eigenvectors' orthogonality.
+template <int n, int WARPS, bool SYNC, bool RAD, bool ADD = false>
 __global__ void __launch_bounds__(WARPS * 32, 16 / WARPS)
 disort_fast_kernel(const LaunchArgs a)
 {
     using FL = FastLayout<n>;
+    using AO = AddOps<n>;
+    static_assert(!ADD || RAD, "the adding form of this kernel serves the radiance runs");
+    static_assert(!ADD || (size_t)AO::arec * 64 + 2 * n * 65 <= (size_t)FL::ublk * 64, "sweep records live in the pivot-row area");
     constexpr int N = 2 * n, TASKS = 32 / n, KS = FL::KS, LC = FL::LC, US = FL::US;
     static_assert(!RAD || SYNC, "radiance runs reload the CTA's Legendre table per azimuth mode");
     const int L = a.d.nlyr;
@@ -826,6 +844,8 @@ disort_fast_kernel(const LaunchArgs a)
     double *frecs = scr + (size_t)L * FL::rec;            // [L][frec]
     double *ublk = frecs + (size_t)L * FL::frec;          // [L][N][US]
     double *dscr = ublk + (size_t)L * FL::ublk;           // RAD: [L][2][NU] downward source, transmission
+    double *arecs = ublk;                                 // ADD: [L][arec] sweep records, then [L+1][2n] interface intensities
+    double *levs = ublk + (size_t)L * AO::arec;
     const int g = lane % n, task = lane / n;
     // the spectrum path keeps the bin count on the device (a.d.nbins is then an upper bound)
     const int nbins_all = a.redo_consume ? *a.redo_count : (a.nbins_dev ? *a.nbins_dev : a.d.nbins);
@@ -1013,9 +1033,10 @@ disort_fast_kernel(const LaunchArgs a)
                 int lc = lc0 + task;
                 const bool active = lc < ncut;
                 if (!active) lc = ncut - 1;
-                int st = phase1_layers<n>(dtauc, ssalb, pmom, ldp, lc, active, RAD ? mazim : 0, fbeam, umu0,
-                                          plank && m0, delm0, cmu, cwt, csq, cdinv, cylm, y0, taucpr, pk, tsm,
-                                          recs + (size_t)lc * FL::rec, frecs + (size_t)lc * FL::frec, g, jpart);
+                int st = phase1_layers<n, ADD>(dtauc, ssalb, pmom, ldp, lc, active, RAD ? mazim : 0, fbeam, umu0,
+                                               plank && m0, delm0, cmu, cwt, csq, cdinv, cylm, y0, taucpr, pk, tsm,
+                                               recs + (size_t)lc * FL::rec, frecs + (size_t)lc * FL::frec, g, jpart,
+                                               arecs + (size_t)lc * AO::arec, ebeam);
                 if (__any_sync(FULLMASK, st != 0)) { status = SBD_BIN_EIG_FAIL; break; }
             }
         }
@@ -1031,7 +1052,21 @@ disort_fast_kernel(const LaunchArgs a)
         // stage lc uses records lc and lc+1 while record lc+2 is in flight.
         double *rslot = tsm_base;   // phase-1 task areas are idle now
         double *stg = tsm_base + 3 * FL::rec;     // assembled rows of the current layer
-        if (mrun && !status) {
+        if (ADD && mrun && !status) {
+            // adding sweeps: bottom boundary (Lambertian: reflects the m = 0 mode only; nothing comes
+            // up at a truncation level), bottom-up operators, top-down intensities
+            const bool refl = !lyrcut && m0;
+            const double rbB = refl ? 2.0 * albedo : 0.0;
+            const double sbB = refl ? albedo * umu0 * fbeam / kPiRef * ebeam[ncut] + (1.0 - albedo) * bplank : 0.0;
+            double *sRb = tsm_base, *ssb = sRb + n * n;
+            for (int e = lane; e < n * n; e += 32) sRb[e] = rbB * (cmu[e / n] * csq[e / n]) * (cmu[e % n] * csq[e % n]);
+            if (lane < n) ssb[lane] = cmu[lane] * csq[lane] * sbB;
+            __syncwarp();
+            if (!adding_sweep_up<n>(arecs, ncut, tsm_base, lane)) status = SBD_BIN_SINGULAR;
+            if (!status)
+                adding_sweep_down<n>(arecs, ncut, levs, m0 ? bp.fisot + tplank : 0.0, rbB, sbB, cmu, csq, lane);
+        }
+        if (!ADD && mrun && !status) {
             double w[KS][LC], rhs[KS];
 #if SBD_TMA_P2
             __syncwarp();
@@ -1184,13 +1219,13 @@ disort_fast_kernel(const LaunchArgs a)
                 double *dstp = tsm_base + buf * kSlot;
 #if SBD_TMA_P3
                 if (lane == 0) {
-                    SBD_BULK_BEGIN(mbar + buf, 8u * kSlot);
-                    bulk_g2s(dstp, ublk + (size_t)lyr * FL::ublk, 8u * FL::ublk, mbar + buf);
+                    SBD_BULK_BEGIN(mbar + buf, 8u * (kSlot - (ADD ? FL::ublk : 0)));
+                    if (!ADD) bulk_g2s(dstp, ublk + (size_t)lyr * FL::ublk, 8u * FL::ublk, mbar + buf);
                     bulk_g2s(dstp + FL::ublk, frecs + (size_t)lyr * FL::frec, 8u * FL::frec, mbar + buf);
                     if (RAD) bulk_g2s(dstp + FL::ublk + FL::frec, recs + (size_t)lyr * FL::rec, 8u * FL::rec, mbar + buf);
                 }
 #else
-                warp_copy_async(dstp, ublk + (size_t)lyr * FL::ublk, FL::ublk, lane);
+                if (!ADD) warp_copy_async(dstp, ublk + (size_t)lyr * FL::ublk, FL::ublk, lane);
                 warp_copy_async(dstp + FL::ublk, frecs + (size_t)lyr * FL::frec, FL::frec, lane);
                 if (RAD) warp_copy_async(dstp + FL::ublk + FL::frec, recs + (size_t)lyr * FL::rec, FL::rec, lane);
                 cp_async_commit();
@@ -1253,6 +1288,42 @@ disort_fast_kernel(const LaunchArgs a)
 #endif
                 const double *ubuf = tsm_base + buf * kSlot;
                 const double *fr = ubuf + FL::ublk;
+                if (ADD) {
+                    // Layer solution from the interface intensities (scaled, u^ = D u): with the
+                    // homogeneous parts du = u^ - D p at the layer top and bottom,
+                    //   x(+k_j) = -k_j sum_i D_i [G+_ij du+_i - G-_ij du-_i]   at the top,
+                    //   x(-k_j) =  k_j sum_i D_i [G+_ij du-_i - G-_ij du+_i]   at the bottom
+                    // (orthogonality of the eigenvectors; each family is taken at the boundary where
+                    // it is not attenuated).
+                    const double *urc = fr + FL::frec;
+                    const double *lt = levs + (size_t)lc * 2 * n, *lb = lt + 2 * n;
+                    double xp = 0.0, xm = 0.0;
+                    if (lane < n) {
+                        const double et = ebeam[lc], ebt = ebeam[lc + 1], tt = taucpr[lc], tb = taucpr[lc + 1];
+                        const double xr1 = urc[FL::off_xr + 1];
+                        double ap = 0.0, am = 0.0;
+#pragma unroll
+                        for (int i = 0; i < n; i++) {
+                            const double Di = cmu[i] * csq[i];
+                            const double zu = urc[FL::off_zz + n + i], zd = urc[FL::off_zz + n - 1 - i];
+                            const double pu = urc[FL::off_zp0 + n + i], pd = urc[FL::off_zp0 + n - 1 - i];
+                            const double gp = urc[FL::off_gp + i * n + lane], gm = urc[FL::off_gm + i * n + lane];
+                            const double dut = lt[n + i] - Di * (zu * et + pu + xr1 * tt);
+                            const double ddt = lt[i] - Di * (zd * et + pd + xr1 * tt);
+                            const double dub = lb[n + i] - Di * (zu * ebt + pu + xr1 * tb);
+                            const double ddb = lb[i] - Di * (zd * ebt + pd + xr1 * tb);
+                            ap = fma(Di, gp * dut - gm * ddt, ap);
+                            am = fma(Di, gp * ddb - gm * dub, am);
+                        }
+                        const double k = urc[FL::off_kk + lane];
+                        xp = -k * ap; xm = k * am;
+                    }
+#pragma unroll
+                    for (int j = 0; j < n; j++) {
+                        xs[n + j] = __shfl_sync(FULLMASK, xp, j);
+                        xs[n - 1 - j] = __shfl_sync(FULLMASK, xm, j);
+                    }
+                } else {
                 double acc, dinv;
                 double ur[N];      // row `lane` of the upper triangle, pre-divided by the diagonal
                                    // (entries left of the diagonal unused)
@@ -1277,6 +1348,7 @@ disort_fast_kernel(const LaunchArgs a)
                     const double xc = __shfl_sync(FULLMASK, acc, c);
                     xs[c] = xc;
                     if (lane < c) acc = fma(-ur[c], xc, acc);
+                }
                 }
 #ifdef SBD_PHASE_TIMING
                 if (threadIdx.x == 0) { const long long t = clock64(); atomicAdd(&g_phase_ticks[5], (unsigned long long)(t - tsub)); tsub = t; }
@@ -1495,13 +1567,13 @@ static bool fast_sync(int warps)
     return e ? atoi(e) != 0 : warps > 4;
 }
 
-template <int n, int WARPS, bool SYNC, bool RAD>
+template <int n, int WARPS, bool SYNC, bool RAD, bool ADD = false>
 static cudaError_t launch_fast_k(const LaunchArgs &a, int grid, size_t smem, cudaStream_t st)
 {
-    cudaError_t e = cudaFuncSetAttribute(disort_fast_kernel<n, WARPS, SYNC, RAD>,
+    cudaError_t e = cudaFuncSetAttribute(disort_fast_kernel<n, WARPS, SYNC, RAD, ADD>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    disort_fast_kernel<n, WARPS, SYNC, RAD><<<grid, WARPS * 32, smem, st>>>(a);
+    disort_fast_kernel<n, WARPS, SYNC, RAD, ADD><<<grid, WARPS * 32, smem, st>>>(a);
     return cudaGetLastError();
 }
 
@@ -1511,9 +1583,11 @@ static cudaError_t launch_fast_t(const LaunchArgs &a, int warps, int grid, cudaS
     const int L = a.d.nlyr, NT = a.d.ntau > 0 ? a.d.ntau : L + 1;
     size_t smem = 8 * (FastLayout<n>::cta_doubles(a.d.numu) + (size_t)warps * FastLayout<n>::warp_doubles(L, NT, a.d.numu, a.d.nphi));
     if (a.d.numu > 0) {      // radiance runs: CTA-synchronous always
+        // adding sweeps + solution recovery; SBD_RAD_ELIM = 1: the elimination (comparison knob)
+        const bool add = !getenv("SBD_RAD_ELIM");
         switch (warps) {
-        case 4: return launch_fast_k<n, 4, true, true>(a, grid, smem, st);
-        case 8: return launch_fast_k<n, 8, true, true>(a, grid, smem, st);
+        case 4: return add ? launch_fast_k<n, 4, true, true, true>(a, grid, smem, st) : launch_fast_k<n, 4, true, true>(a, grid, smem, st);
+        case 8: return add ? launch_fast_k<n, 8, true, true, true>(a, grid, smem, st) : launch_fast_k<n, 8, true, true>(a, grid, smem, st);
         }
         return cudaErrorInvalidValue;
     }
