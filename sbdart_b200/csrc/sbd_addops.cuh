@@ -15,7 +15,7 @@ struct AddOps {
     static constexpr int arec = 2 * n * n + 2 * n;      // R, T, s_up, s_dn  ->  Y, y, Rb, sb
     static constexpr int r_R = 0, r_T = n * n, r_su = 2 * n * n, r_sd = 2 * n * n + n;
     static constexpr int o_Y = 0, o_y = n * n, o_Rb = n * n + n, o_sb = 2 * n * n + n;
-    static constexpr int CG = n >= 4 ? 4 : n, CW = n / CG;
+    static constexpr int CG = n >= 10 ? 2 : (n >= 4 ? 4 : n), CW = n / CG;
     static constexpr int p2 = 3 * n * n + 3 * n + 2 * arec;     // shared memory of the sweeps
 };
 
@@ -30,14 +30,14 @@ __device__ __forceinline__ int layer_operators(const double (&P)[n], double kk, 
                                                double pk_top, double pk_bot, double et, double eb,
                                                bool beam, bool therm, const double *cmu, const double *csq,
                                                double *mP, double *mA, double *mB, double *sv,
-                                               double *rec, bool active, int g)
+                                               double *rec, bool active, int g, bool gact = true)
 {
     using AO = AddOps<n>;
     int bad = 0;
     __syncwarp();
 #pragma unroll
-    for (int i = 0; i < n; i++) mP[g * LD + i] = P[i];        // [mode][direction]
-    sv[g] = zus; sv[n + g] = zds; sv[2 * n + g] = qs;
+    for (int i = 0; i < n; i++) if (gact) mP[g * LD + i] = P[i];        // [mode][direction]
+    if (gact) { sv[g] = zus; sv[n + g] = zds; sv[2 * n + g] = qs; }
     __syncwarp();
     double bp[n], bm[n];
 #pragma unroll
@@ -60,7 +60,7 @@ __device__ __forceinline__ int layer_operators(const double (&P)[n], double kk, 
 #pragma unroll
     for (int j = 0; j < n; j++) {
         double *pb = mB + (j & 1) * 2 * n;
-        if (g == j) {
+        if (g == j && gact) {
 #pragma unroll
             for (int c = 0; c < n; c++) { pb[c] = bp[c]; pb[n + c] = bm[c]; }
         }
@@ -93,7 +93,7 @@ __device__ __forceinline__ int layer_operators(const double (&P)[n], double kk, 
             }
         }
 #pragma unroll
-        for (int b = 0; b < n; b++) { mA[g * LD + b] = up[b]; mB[g * LD + b] = um[b]; }
+        for (int b = 0; b < n; b++) if (gact) { mA[g * LD + b] = up[b]; mB[g * LD + b] = um[b]; }
     }
     __syncwarp();
     double R[n], T[n], mm[n];
@@ -159,7 +159,7 @@ template <int n>
 __device__ __forceinline__ bool adding_sweep_up(double *recs, int ncut, double *sm, int lane)
 {
     using AO = AddOps<n>;
-    constexpr int CG = AO::CG, CW = AO::CW, REC = AO::arec;
+    constexpr int CG = AO::CG, CW = AO::CW, REC = AO::arec, KB = n > 8 ? 4 : 3, KM = (1 << KB) - 1;
     const bool act2 = lane < n * CG;
     const int i2 = act2 ? lane / CG : n - 1, p2 = lane % CG, c0 = p2 * CW;
     double *sRb = sm, *ssb = sRb + n * n, *sY = ssb + n, *sy = sY + n * n, *sW = sy + n, *sw = sW + n * n;
@@ -204,10 +204,10 @@ __device__ __forceinline__ bool adding_sweep_up(double *recs, int ncut, double *
         for (int j = 0; j < n; j++) {
             const int pj = j / CW, sj = j % CW;
             const double colv = __shfl_sync(FULLMASK, b[sj], (lane & ~(CG - 1)) | pj);
-            const int key = (act2 && !((used >> i2) & 1u)) ? ((__double2hiint(colv) & 0x7ffffff8) | (7 - i2)) : -1;
+            const int key = (act2 && !((used >> i2) & 1u)) ? ((__double2hiint(colv) & (0x7fffffff & ~KM)) | (KM - i2)) : -1;
             const int mx = __reduce_max_sync(FULLMASK, key);
-            if ((mx >> 3) <= 0) sing = 1;
-            const int ip = 7 - (mx & 7);
+            if ((mx >> KB) <= 0) sing = 1;
+            const int ip = KM - (mx & KM);
             used |= 1u << ip;
             const int srcl = ip * CG + p2;
             const double rp = fast_rcp(__shfl_sync(FULLMASK, colv, ip * CG));
@@ -289,6 +289,7 @@ __device__ __forceinline__ void adding_sweep_down(const double *recs, int ncut, 
 #pragma unroll
     for (int c = 0; c < n; c++) { cd[c] = cmu[c] * csq[c]; d[c] = cd[c] * d0; }
     const int row = lane < n ? lane : (lane < 2 * n ? lane - n : 0);
+    double dme = cmu[row] * csq[row] * d0;          // lanes < n: d[lane]
     for (int lev = 0; lev <= ncut; lev++) {
         double x;
         if (lev < ncut) {
@@ -304,8 +305,9 @@ __device__ __forceinline__ void adding_sweep_down(const double *recs, int ncut, 
             for (int c = 0; c < n; c++) dd = fma(cd[c], d[c], dd);
             x = cmu[row] * csq[row] * (rbB * dd + sbB);
         }
-        if (lane < n) levs[(size_t)lev * 2 * n + lane] = d[lane];
+        if (lane < n) levs[(size_t)lev * 2 * n + lane] = dme;
         else if (lane < 2 * n) levs[(size_t)lev * 2 * n + lane] = x;        // u_lev
+        dme = x;
 #pragma unroll
         for (int c = 0; c < n; c++) d[c] = __shfl_sync(FULLMASK, x, c);
     }

@@ -310,7 +310,8 @@ extern "C" int sbd_disort_batch_device(sbd_handle *h, const sbd_dims *dims, cons
     const bool adding_ok = adding_supported(N) && NU == 0 && dims->ntau == 0 && !getenv("SBD_FORCE_GENERIC");
     const bool adding = adding_ok && (brdf || !getenv("SBD_FORCE_ELIM"));
     // elimination register kernel: NSTR 4/8/16; radiances at the layer boundaries (the mode SBDART uses)
-    const bool fast = !adding && !brdf && fast_supported(N) && (NU == 0 || dims->ntau == 0) && !getenv("SBD_FORCE_GENERIC");
+    const bool fast = !adding && !brdf && (NU > 0 ? fast_rad_supported(N) && dims->ntau == 0 : fast_supported(N)) &&
+                      !getenv("SBD_FORCE_GENERIC");
     // CTA-per-bin register kernel: NSTR 20/24/32, fluxes
     const bool wide = !adding && !fast && !brdf && wide_supported(N) && NU == 0 && !getenv("SBD_FORCE_GENERIC") &&
                       wide_smem_bytes(N, L, NT) <= smem_limit;
@@ -328,8 +329,8 @@ extern "C" int sbd_disort_batch_device(sbd_handle *h, const sbd_dims *dims, cons
         // CTA shape: the preferred one (8 warps) unless 4-warp CTAs keep more warps
         // resident per SM under the shared-memory limit (deep atmospheres); the adding kernel
         // above NSTR = 16 runs 4-warp CTAs (register budget)
-        warps = (adding && N > 16) ? 4 : fast_warps();
-        const int wmax = adding ? adding_warps_per_sm(N) : 16;
+        warps = N > 16 ? 4 : fast_warps();
+        const int wmax = adding ? adding_warps_per_sm(N) : (N > 16 ? 4 : 16);
         int cta_per_sm = 0;
         for (int wtry = warps; wtry >= 4; wtry /= 2) {
             const size_t smem = adding ? adding_smem_bytes(N, L, wtry) : fast_smem_bytes(N, L, NT, wtry, NU, dims->nphi);

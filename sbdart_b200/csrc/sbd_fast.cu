@@ -99,7 +99,10 @@ struct FastLayout {
     static constexpr int cta = 4 * n + N * n + 2;   // cmu cwt csq cdinv, ylm, sum(w mu), sum(w)
     // radiance runs: Y_l^m at the user cosines of the current azimuth mode, CTA-shared
     __host__ __device__ static size_t cta_doubles(int NU) { return (size_t)cta + (((size_t)N * NU + 1) & ~(size_t)1); }
-    static constexpr int tasks = 32 / n;
+    // phase 1: a layer is owned by a group of GW lanes (the n first ones hold a row / column /
+    // mode each; for n = 10, 12 the rest shadow lane n-1, compute along and store nothing)
+    static constexpr int GW = n <= 2 ? 2 : (n <= 4 ? 4 : (n <= 8 ? 8 : 16));
+    static constexpr int tasks = 32 / GW;
     // gl, K, L, G1, G2 [n][LD], vectors.  Rows n + 2 doubles apart (row-wise accesses of a layer group's
     // lanes hit different banks), areas padded to 4 (mod 16) doubles (the groups' broadcast loads too)
     static constexpr int LD = n + 2;
@@ -109,7 +112,10 @@ struct FastLayout {
     static constexpr int cmax(int a, int b) { return a > b ? a : b; }
     static constexpr int work = cmax(cmax(tasks * task, 3 * rec + ublk), 2 * (ublk + frec));
     // radiance runs also stage the layer record in phase 3 (eigenvectors at the user angles)
-    static constexpr int work_rad = cmax(work, 2 * (ublk + frec + rec));
+    // (NSTR > 16 runs the adding form only: no pivot rows in the phase-3 buffers)
+    static constexpr int stage_rows3 = n > 8 ? 0 : ublk;
+    static constexpr int work_rad = n > 8 ? cmax(cmax(tasks * task, AddOps<n>::p2), 2 * (frec + rec))
+                                          : cmax(work, 2 * (ublk + frec + rec));
     static constexpr int ecols = N + 3;            // eigen-terms + beam, Planck Z0, Z1 sources
     // user-angle work values: E[N][ecols], GU[NU][ecols], running intensity [NU], cos(m dphi) [NPHI], g_l [N]
     __host__ __device__ static size_t rad_doubles(int NU, int NPHI)
@@ -131,21 +137,22 @@ struct FastLayout {
     __host__ __device__ static size_t slot_doubles_rad(int L, int NU) { return slot_doubles(L) + (size_t)2 * L * NU; }
 };
 
-// sum over the n lanes of a layer group
-template <int n>
+// sum over the GW lanes of a layer group (shadow lanes pass zero)
+template <int GW>
 __device__ __forceinline__ double group_sum(double v)
 {
 #pragma unroll
-    for (int o = n / 2; o > 0; o >>= 1) v += __shfl_xor_sync(FULLMASK, v, o, n);
+    for (int o = GW / 2; o > 0; o >>= 1) v += __shfl_xor_sync(FULLMASK, v, o, GW);
     return v;
 }
 
 // Round-robin (tournament) pairing of the one-sided Jacobi sweeps: the partner of
-// lane g in round r, 3 bits per round (n <= 8).
+// lane g in round r, 3 bits per round (4 above n = 8).
 template <int n>
-__device__ __forceinline__ unsigned jacobi_partners(int g)
+__device__ __forceinline__ unsigned long long jacobi_partners(int g)
 {
-    unsigned pk = 0;
+    constexpr int PB = n > 8 ? 4 : 3;
+    unsigned long long pk = 0;
 #pragma unroll
     for (int r = 0; r < n - 1; r++) {
         int partner;
@@ -156,7 +163,7 @@ __device__ __forceinline__ unsigned jacobi_partners(int g)
             if (partner >= n - 1) partner -= n - 1;
             if (partner >= n - 1) partner -= n - 1;
         }
-        pk |= (unsigned)partner << (3 * r);
+        pk |= (unsigned long long)partner << (PB * r);
     }
     return pk;
 }
@@ -172,12 +179,13 @@ __device__ __forceinline__ int phase1_layers(
     const double *cmu, const double *cwt, const double *csq, const double *cdinv, const double *cylm,
     const double *y0, const double *taucpr, const double *pk,
     double *tsm /* per-task shared */, double *rec /* scratch record of this layer */,
-    double *frec /* flux record of this layer */, int g /* lane in group */,
-    unsigned jpart /* Jacobi partners of this lane, see jacobi_partners */,
+    double *frec /* flux record of this layer */, int g /* lane in group (shadow lanes: n-1) */,
+    bool gact /* false: shadow lane */,
+    unsigned long long jpart /* Jacobi partners of this lane, see jacobi_partners */,
     double *arec = nullptr /* ADDREC: the layer's R, T, s_up, s_dn */, const double *ebeam = nullptr)
 {
     using FL = FastLayout<n>;
-    constexpr int N = 2 * n, LD = FL::LD;
+    constexpr int N = 2 * n, LD = FL::LD, GW = FL::GW, PB = n > 8 ? 4 : 3;
     double *sgl = tsm, *sK = sgl + N, *sL = sK + n * LD, *sG1 = sL + n * LD, *sG2 = sG1 + n * LD,
            *sv = sG2 + n * LD;   // sv: 4 vectors of n
 
@@ -193,7 +201,7 @@ __device__ __forceinline__ int phase1_layers(
     for (int h = 0; h < 2; h++) {
         int l = g + h * n;
         double pm = (l == 0) ? 1.0 : pmom[(size_t)lc * ldp + l];
-        sgl[l] = (2 * l + 1) * oprim * (pm - f) * rf;
+        if (gact) sgl[l] = (2 * l + 1) * oprim * (pm - f) * rf;
     }
     __syncwarp();
 
@@ -231,10 +239,10 @@ __device__ __forceinline__ int phase1_layers(
         double nume = pe[j], numo = po[j];
 #pragma unroll
         for (int k = 0; k < j; k++) {
-            nume = fma(-pe[k], shfl_d(pe[k], j, n), nume);
-            numo = fma(-po[k], shfl_d(po[k], j, n), numo);
+            nume = fma(-pe[k], shfl_d(pe[k], j, GW), nume);
+            numo = fma(-po[k], shfl_d(po[k], j, GW), numo);
         }
-        double pive = shfl_d(nume, j, n), pivo = shfl_d(numo, j, n);
+        double pive = shfl_d(nume, j, GW), pivo = shfl_d(numo, j, GW);
         if (!(pivo > 0.0)) { bad = 1; pivo = 1.0; }
         // Pe~ is only semidefinite when w' -> 1: keep the factor real (a NaN pivot is a failure)
         const double floor_e = 1.0e-30;
@@ -246,7 +254,7 @@ __device__ __forceinline__ int phase1_layers(
         po[j] = (g == j) ? pivo * rio : ((g > j) ? numo * rio : 0.0);
     }
 #pragma unroll
-    for (int j = 0; j < n; j++) { sK[g * LD + j] = pe[j]; sL[g * LD + j] = po[j]; }
+    for (int j = 0; j < n; j++) if (gact) { sK[g * LD + j] = pe[j]; sL[g * LD + j] = po[j]; }
     __syncwarp();
 
     // column g of A = K^T L
@@ -282,13 +290,13 @@ __device__ __forceinline__ int phase1_layers(
             int big = 0;
 #pragma unroll 1
             for (int r = 0; r < n - 1; r++) {     // not unrolled: keeps the code in the I-cache
-                const int partner = (jpart >> (3 * r)) & 7;
+                const int partner = (int)(jpart >> (PB * r)) & ((1 << PB) - 1);
                 double pa[n];
                 double g0 = 0.0, g1 = 0.0;
-                const double oth2 = shfl_d(own2, partner, n);
+                const double oth2 = shfl_d(own2, partner, GW);
 #pragma unroll
                 for (int i = 0; i < n; i++) {
-                    pa[i] = shfl_d(a[i], partner, n);
+                    pa[i] = shfl_d(a[i], partner, GW);
                     if (i & 1) g1 = fma(a[i], pa[i], g1); else g0 = fma(a[i], pa[i], g0);
                 }
                 const double gam = g0 + g1;
@@ -364,19 +372,21 @@ __device__ __forceinline__ int phase1_layers(
     for (int i = 0; i < n; i++) {
         gd[i] = cdinv[i] * Q[i];
         gs[i] = -cdinv[i] * P[i] * rk;
-        sG1[g * LD + i] = gs[i];      // [mode j][direction i]
-        sG2[g * LD + i] = gd[i];
+        if (gact) {
+            sG1[g * LD + i] = gs[i];      // [mode j][direction i]
+            sG2[g * LD + i] = gd[i];
+        }
         const double gpi = 0.5 * (gs[i] + gd[i]), gmi = 0.5 * (gs[i] - gd[i]);
         const double wm = cwt[i] * cmu[i];
         fA = fma(wm, gpi, fA);
         fB = fma(wm, gmi, fB);
         fC = fma(cwt[i], gs[i], fC);
-        if (active) {
+        if (active && gact) {
             rec[FL::off_gp + i * n + g] = gpi;
             rec[FL::off_gm + i * n + g] = gmi;
         }
     }
-    if (active) {
+    if (active && gact) {
         rec[FL::off_kk + g] = kk;
         rec[FL::off_ek + g] = ek;
         // solution column n+g belongs to +k_g, column n-1-g to -k_g (disort.f:3264-3312)
@@ -401,24 +411,23 @@ __device__ __forceinline__ int phase1_layers(
             }
         }
         const double bs = 2.0 * fac * sqg * be, bd = 2.0 * fac * sqg * bo;
-        sv[g] = bd;
+        if (gact) sv[g] = bd;
         __syncwarp();
         double t1 = 0.0;                                    // (K^T b^_d)_g
 #pragma unroll
         for (int k = 0; k < n; k++) t1 = fma(sK[k * LD + g], sv[k], t1);
-        sv[n + g] = t1;
+        if (gact) sv[n + g] = t1;
         __syncwarp();
         double t2 = 0.0;                                    // (K K^T b^_d)_g
 #pragma unroll
         for (int k = 0; k < n; k++) t2 = fma(sK[g * LD + k], sv[n + k], t2);
-        sv[2 * n + g] = bs * rmu0 - t2;                     // r_g
+        if (gact) sv[2 * n + g] = bs * rmu0 - t2;           // r_g
         __syncwarp();
         double cj = 0.0;                                    // (P^T r)_g / (1/mu0^2 - k^2)
 #pragma unroll
         for (int i = 0; i < n; i++) cj = fma(P[i], sv[2 * n + i], cj);
         cj = cj * fast_rcp(rmu0 * rmu0 - s2);
-        sv[3 * n + g] = cj;
-        sv[g] = cj * kk;
+        if (gact) { sv[3 * n + g] = cj; sv[g] = cj * kk; }
         __syncwarp();
         // d = sum_j Gd(:,j) c_j ; s = mu0 (D^-1 b^_d + sum_j Gs(:,j) k_j c_j), direction i = g
         double dv = 0.0, sv2 = 0.0;
@@ -457,11 +466,11 @@ __device__ __forceinline__ int phase1_layers(
     }
     // quadrature sums of the particular solutions (same functionals as above)
     {
-        const double wmg = cwt[g] * cmu[g];
-        const double Zu = group_sum<n>(wmg * zup);
-        const double Zd = group_sum<n>(wmg * zdn);
-        const double Za = group_sum<n>(cwt[g] * (zup + zdn));
-        const double Q1 = (plank && mazim == 0) ? group_sum<n>(wmg * q) : 0.0;
+        const double wmg = gact ? cwt[g] * cmu[g] : 0.0, wg = gact ? cwt[g] : 0.0;
+        const double Zu = group_sum<GW>(wmg * zup);
+        const double Zd = group_sum<GW>(wmg * zdn);
+        const double Za = group_sum<GW>(wg * (zup + zdn));
+        const double Q1 = (plank && mazim == 0) ? group_sum<GW>(wmg * q) : 0.0;
         if (active && g == 0) {
             const double W = cylm[-2], SW = cylm[-1];      // sum(w mu), sum(w): see the kernel
             double *sc = frec + FL::f_sc;
@@ -470,7 +479,7 @@ __device__ __forceinline__ int phase1_layers(
             sc[6] = xr0; sc[7] = xr1; sc[8] = 1.0 - ss; sc[9] = 1.0 - ss * f;
         }
     }
-    if (active) {
+    if (active && gact) {
         rec[FL::off_zz + n + g] = zup;
         rec[FL::off_zz + n - 1 - g] = zdn;
         rec[FL::off_zp0 + n + g] = xr0 + xr1 * q;
@@ -485,7 +494,7 @@ __device__ __forceinline__ int phase1_layers(
         bad |= layer_operators<n, LD>(P, kk, dtaucp, zup * Dg, zdn * Dg, q * Dg, xr1,
                                       therm ? pk[lc] : 0.0, therm ? pk[lc + 1] : 0.0,
                                       fbeam > 0.0 ? ebeam[lc] : 0.0, fbeam > 0.0 ? ebeam[lc + 1] : 0.0,
-                                      fbeam > 0.0, therm, cmu, csq, sG1, sK, sG2, sv, arec, active, g);
+                                      fbeam > 0.0, therm, cmu, csq, sG1, sK, sG2, sv, arec, active && gact, g, gact);
     }
     __syncwarp();
     return (bad && active) ? SBD_BIN_EIG_FAIL : 0;
@@ -790,14 +799,15 @@ __device__ __forceinline__ double layer_source(const double *gu /* GU row of thi
 // the elimination: two sweeps leave the intensities at every interface, and the layer solutions
 // the source-function integration needs follow from them by the eigenvectors' orthogonality.
 template <int n, int WARPS, bool SYNC, bool RAD, bool ADD = false>
-__global__ void __launch_bounds__(WARPS * 32, 16 / WARPS)
+__global__ void __launch_bounds__(WARPS * 32, n > 8 ? 1 : 16 / WARPS)
 disort_fast_kernel(const LaunchArgs a)
 {
     using FL = FastLayout<n>;
     using AO = AddOps<n>;
     static_assert(!ADD || RAD, "the adding form of this kernel serves the radiance runs");
     static_assert(!ADD || (size_t)AO::arec * 64 + 2 * n * 65 <= (size_t)FL::ublk * 64, "sweep records live in the pivot-row area");
-    constexpr int N = 2 * n, TASKS = 32 / n, KS = FL::KS, LC = FL::LC, US = FL::US;
+    constexpr int N = 2 * n, TASKS = FL::tasks, GW = FL::GW, KS = FL::KS, LC = FL::LC, US = FL::US;
+    static_assert(n <= 8 || ADD, "NSTR > 16: adding form only");
     static_assert(!RAD || SYNC, "radiance runs reload the CTA's Legendre table per azimuth mode");
     const int L = a.d.nlyr;
     const int NT = a.d.ntau > 0 ? a.d.ntau : L + 1;
@@ -846,12 +856,14 @@ disort_fast_kernel(const LaunchArgs a)
     double *dscr = ublk + (size_t)L * FL::ublk;           // RAD: [L][2][NU] downward source, transmission
     double *arecs = ublk;                                 // ADD: [L][arec] sweep records, then [L+1][2n] interface intensities
     double *levs = ublk + (size_t)L * AO::arec;
-    const int g = lane % n, task = lane / n;
+    const int task = lane / GW;
+    const bool gact = lane % GW < n;
+    const int g = gact ? lane % GW : n - 1;
     // the spectrum path keeps the bin count on the device (a.d.nbins is then an upper bound)
     const int nbins_all = a.redo_consume ? *a.redo_count : (a.nbins_dev ? *a.nbins_dev : a.d.nbins);
     double *tsm = tsm_base + (size_t)task * FL::task;
     const int rg = lane >> 2, cg = lane & 3;              // 2-D tiling of phase 2
-    const unsigned jpart = jacobi_partners<n>(g);
+    const unsigned long long jpart = jacobi_partners<n>(g);
 #if SBD_USE_TMA
     if (lane == 0) { mbar_init(mbar, 1); mbar_init(mbar + 1, 1); mbar_init(mbar + 2, 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -1035,7 +1047,7 @@ disort_fast_kernel(const LaunchArgs a)
                 if (!active) lc = ncut - 1;
                 int st = phase1_layers<n, ADD>(dtauc, ssalb, pmom, ldp, lc, active, RAD ? mazim : 0, fbeam, umu0,
                                                plank && m0, delm0, cmu, cwt, csq, cdinv, cylm, y0, taucpr, pk, tsm,
-                                               recs + (size_t)lc * FL::rec, frecs + (size_t)lc * FL::frec, g, jpart,
+                                               recs + (size_t)lc * FL::rec, frecs + (size_t)lc * FL::frec, g, gact, jpart,
                                                arecs + (size_t)lc * AO::arec, ebeam);
                 if (__any_sync(FULLMASK, st != 0)) { status = SBD_BIN_EIG_FAIL; break; }
             }
@@ -1066,7 +1078,7 @@ disort_fast_kernel(const LaunchArgs a)
             if (!status)
                 adding_sweep_down<n>(arecs, ncut, levs, m0 ? bp.fisot + tplank : 0.0, rbB, sbB, cmu, csq, lane);
         }
-        if (!ADD && mrun && !status) {
+        if constexpr (!ADD) if (mrun && !status) {
             double w[KS][LC], rhs[KS];
 #if SBD_TMA_P2
             __syncwarp();
@@ -1214,20 +1226,21 @@ disort_fast_kernel(const LaunchArgs a)
             int lu_next = NT - 1;  // levels are visited bottom-up when the map is monotone
             // pivot rows + flux record of layer lc-1 stream into the other half of a
             // double buffer (cp.async) while layer lc is being solved
-            constexpr int kSlot = FL::ublk + FL::frec + (RAD ? FL::rec : 0);
+            constexpr int UB = RAD ? FL::stage_rows3 : FL::ublk;      // pivot-row part of a buffer
+            constexpr int kSlot = UB + FL::frec + (RAD ? FL::rec : 0);
             auto fetch_layer = [&](int lyr, int buf) {
                 double *dstp = tsm_base + buf * kSlot;
 #if SBD_TMA_P3
                 if (lane == 0) {
-                    SBD_BULK_BEGIN(mbar + buf, 8u * (kSlot - (ADD ? FL::ublk : 0)));
+                    SBD_BULK_BEGIN(mbar + buf, 8u * (kSlot - (ADD ? UB : 0)));
                     if (!ADD) bulk_g2s(dstp, ublk + (size_t)lyr * FL::ublk, 8u * FL::ublk, mbar + buf);
-                    bulk_g2s(dstp + FL::ublk, frecs + (size_t)lyr * FL::frec, 8u * FL::frec, mbar + buf);
-                    if (RAD) bulk_g2s(dstp + FL::ublk + FL::frec, recs + (size_t)lyr * FL::rec, 8u * FL::rec, mbar + buf);
+                    bulk_g2s(dstp + UB, frecs + (size_t)lyr * FL::frec, 8u * FL::frec, mbar + buf);
+                    if (RAD) bulk_g2s(dstp + UB + FL::frec, recs + (size_t)lyr * FL::rec, 8u * FL::rec, mbar + buf);
                 }
 #else
                 if (!ADD) warp_copy_async(dstp, ublk + (size_t)lyr * FL::ublk, FL::ublk, lane);
-                warp_copy_async(dstp + FL::ublk, frecs + (size_t)lyr * FL::frec, FL::frec, lane);
-                if (RAD) warp_copy_async(dstp + FL::ublk + FL::frec, recs + (size_t)lyr * FL::rec, FL::rec, lane);
+                warp_copy_async(dstp + UB, frecs + (size_t)lyr * FL::frec, FL::frec, lane);
+                if (RAD) warp_copy_async(dstp + UB + FL::frec, recs + (size_t)lyr * FL::rec, FL::rec, lane);
                 cp_async_commit();
 #endif
             };
@@ -1287,8 +1300,8 @@ disort_fast_kernel(const LaunchArgs a)
                 if (threadIdx.x == 0) { const long long t = clock64(); atomicAdd(&g_phase_ticks[4], (unsigned long long)(t - tsub)); tsub = t; }
 #endif
                 const double *ubuf = tsm_base + buf * kSlot;
-                const double *fr = ubuf + FL::ublk;
-                if (ADD) {
+                const double *fr = ubuf + UB;
+                if constexpr (ADD) {
                     // Layer solution from the interface intensities (scaled, u^ = D u): with the
                     // homogeneous parts du = u^ - D p at the layer top and bottom,
                     //   x(+k_j) = -k_j sum_i D_i [G+_ij du+_i - G-_ij du-_i]   at the top,
@@ -1582,6 +1595,10 @@ static cudaError_t launch_fast_t(const LaunchArgs &a, int warps, int grid, cudaS
 {
     const int L = a.d.nlyr, NT = a.d.ntau > 0 ? a.d.ntau : L + 1;
     size_t smem = 8 * (FastLayout<n>::cta_doubles(a.d.numu) + (size_t)warps * FastLayout<n>::warp_doubles(L, NT, a.d.numu, a.d.nphi));
+    if constexpr (n > 8) {   // NSTR 20/24/32: radiance runs in the adding form, 4-warp CTAs (register budget)
+        if (a.d.numu == 0 || warps != 4) return cudaErrorInvalidValue;
+        return launch_fast_k<n, 4, true, true, true>(a, grid, smem, st);
+    } else {
     if (a.d.numu > 0) {      // radiance runs: CTA-synchronous always
         // adding sweeps + solution recovery; SBD_RAD_ELIM = 1: the elimination (comparison knob)
         const bool add = !getenv("SBD_RAD_ELIM");
@@ -1597,9 +1614,12 @@ static cudaError_t launch_fast_t(const LaunchArgs &a, int warps, int grid, cudaS
     case 8: return launch_fast_k<n, 8, true, false>(a, grid, smem, st);
     }
     return cudaErrorInvalidValue;
+    }
 }
 
 bool fast_supported(int N) { return N == 4 || N == 8 || N == 16; }
+// radiance runs (adding form) reach further
+bool fast_rad_supported(int N) { return fast_supported(N) || ((N == 20 || N == 24 || N == 32) && !getenv("SBD_RAD_ELIM")); }
 
 size_t fast_slot_doubles(int N, int L, int NU)
 {
@@ -1607,6 +1627,9 @@ size_t fast_slot_doubles(int N, int L, int NU)
     case 4: return FastLayout<2>::slot_doubles_rad(L, NU);
     case 8: return FastLayout<4>::slot_doubles_rad(L, NU);
     case 16: return FastLayout<8>::slot_doubles_rad(L, NU);
+    case 20: return FastLayout<10>::slot_doubles_rad(L, NU);
+    case 24: return FastLayout<12>::slot_doubles_rad(L, NU);
+    case 32: return FastLayout<16>::slot_doubles_rad(L, NU);
     }
     return 0;
 }
@@ -1617,6 +1640,9 @@ size_t fast_smem_bytes(int N, int L, int NT, int warps, int NU, int NPHI)
     case 4: return 8 * (FastLayout<2>::cta_doubles(NU) + (size_t)warps * FastLayout<2>::warp_doubles(L, NT, NU, NPHI));
     case 8: return 8 * (FastLayout<4>::cta_doubles(NU) + (size_t)warps * FastLayout<4>::warp_doubles(L, NT, NU, NPHI));
     case 16: return 8 * (FastLayout<8>::cta_doubles(NU) + (size_t)warps * FastLayout<8>::warp_doubles(L, NT, NU, NPHI));
+    case 20: return 8 * (FastLayout<10>::cta_doubles(NU) + (size_t)warps * FastLayout<10>::warp_doubles(L, NT, NU, NPHI));
+    case 24: return 8 * (FastLayout<12>::cta_doubles(NU) + (size_t)warps * FastLayout<12>::warp_doubles(L, NT, NU, NPHI));
+    case 32: return 8 * (FastLayout<16>::cta_doubles(NU) + (size_t)warps * FastLayout<16>::warp_doubles(L, NT, NU, NPHI));
     }
     return 0;
 }
@@ -1627,6 +1653,9 @@ cudaError_t launch_fast(const LaunchArgs &a, int warps, int grid, cudaStream_t s
     case 4: return launch_fast_t<2>(a, warps, grid, st);
     case 8: return launch_fast_t<4>(a, warps, grid, st);
     case 16: return launch_fast_t<8>(a, warps, grid, st);
+    case 20: return launch_fast_t<10>(a, warps, grid, st);
+    case 24: return launch_fast_t<12>(a, warps, grid, st);
+    case 32: return launch_fast_t<16>(a, warps, grid, st);
     }
     return cudaErrorInvalidValue;
 }

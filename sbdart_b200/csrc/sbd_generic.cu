@@ -973,7 +973,7 @@ disort_generic_kernel(const LaunchArgs a)
         }
         const int R = n + N, C = 2 * N + 1;
         const unsigned rC = div_magic(C);
-        const double *ylm_smem = cs.ylm;
+        const double *ylm_smem = ylm_s;        // (cs.ylm points at the last mode of the previous bin)
         int kconv = 0;
 
       for (int mazim = 0; ; mazim++) {

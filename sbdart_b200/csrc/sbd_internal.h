@@ -84,6 +84,7 @@ cudaError_t launch_intcor(const LaunchArgs &a, cudaStream_t st);
 
 // register-resident kernel for NSTR in {4, 8, 16} (sbd_fast.cu)
 bool fast_supported(int N);
+bool fast_rad_supported(int N);
 int fast_warps();
 size_t fast_slot_doubles(int N, int L, int NU);
 size_t fast_smem_bytes(int N, int L, int NT, int warps, int NU, int NPHI);

@@ -102,3 +102,44 @@ def test_headline_spectrum_is_placement_independent(solver):
         assert np.array_equal(o[k], base[k][src]), k
     w1 = dict(w, nstr=16)
     _oracle_sample(w1, base, np.arange(0, B, 97))
+
+
+@pytest.mark.parametrize("nstr", [8, 20])
+def test_radiance_batches_beyond_one_wave_of_warps(monkeypatch, nstr):
+    """Radiance bins beyond the first wave (more bins than resident warps): every warp solves
+    several bins in a row, so anything a bin leaves behind (tables of its last azimuth mode,
+    convergence counters) would show in the next one.  The register kernel and the general kernel
+    (SBD_FORCE_GENERIC, the comparison knob) must agree on every bin; a strided sample is
+    compared with the oracle."""
+    B = 6144 if nstr == 8 else 3072
+    w = workloads.retrieval_batch(B, nstr=nstr, nlyr=12, ncols=8, seed=7 + nstr)
+    w["bins"]["phi0"] = 30.0
+    umu = np.array([-1.0, -0.5, -0.1, 0.2, 0.7, 1.0])
+    phi = np.array([0.0, 90.0])
+    res = {}
+    for mode in ("register", "general"):
+        if mode == "general":
+            monkeypatch.setenv("SBD_FORCE_GENERIC", "1")
+        s = sb.Solver(0)
+        res[mode] = s.disort_batch(w["dtauc"], w["ssalb"], w["pmom"], w["bins"], nstr=nstr, umu=umu, phi=phi)
+        s.close()
+    monkeypatch.delenv("SBD_FORCE_GENERIC")
+    a, g = res["register"], res["general"]
+    assert (a["status"] == g["status"]).all()
+    ok = a["status"] == 0
+    sc = np.abs(g["uu"][ok]).reshape(ok.sum(), -1).max(1)
+    d = np.abs(a["uu"][ok] - g["uu"][ok]).reshape(ok.sum(), -1).max(1)
+    assert (d <= 1e-7 * sc).all(), (int((d > 1e-7 * sc).sum()), float((d / sc).max()))
+    b = w["bins"]
+    for i in range(5, B, B // 6):
+        r = oracle.disort(w["dtauc"][i], w["ssalb"][i], w["pmom"][i], nstr=nstr,
+                          temper=w["temper"][b["col"][i]] if w.get("temper") is not None else None,
+                          umu=umu, phi=phi, fbeam=b["fbeam"][i], umu0=b["umu0"][i], phi0=b["phi0"][i],
+                          fisot=b["fisot"][i], albedo=b["albedo"][i], btemp=b["btemp"][i], ttemp=b["ttemp"][i],
+                          temis=b["temis"][i], wvnmlo=b["wvnmlo"][i], wvnmhi=b["wvnmhi"][i],
+                          plank=bool(b["plank"][i]), onlyfl=False)
+        assert a["status"][i] == r["status"]
+        if r["status"] == 0:
+            so = np.abs(r["uu"]).max()
+            assert np.abs(a["uu"][i] - r["uu"]).max() <= 1e-7 * so, i
+            assert np.abs(g["uu"][i] - r["uu"]).max() <= 1e-7 * so, i

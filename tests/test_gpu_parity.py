@@ -127,7 +127,7 @@ def assert_radiance_close(got, refs, rtol=1e-7, atol_scale=1e-9):
             np.testing.assert_allclose(got[k][i], r[k], rtol=1e-7, atol=1e-9 * max(np.abs(r[k]).max(), 1e-300))
 
 
-@pytest.mark.parametrize("nstr,nlyr", [(8, 6), (16, 12), (20, 33)])
+@pytest.mark.parametrize("nstr,nlyr", [(8, 6), (16, 12), (20, 33), (24, 12), (32, 20)])
 def test_radiances_match_oracle(solver, nstr, nlyr):
     """User-angle intensities (TERPEV/TERPSO/USRINT + azimuth sum)."""
     w = workloads.retrieval_batch(12, nstr=nstr, nlyr=nlyr, ncols=4, seed=100 + nstr)
