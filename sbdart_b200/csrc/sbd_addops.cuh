@@ -277,33 +277,28 @@ __device__ __forceinline__ bool adding_sweep_up(double *recs, int ncut, double *
 
 // Top-down sweep: the scaled intensities at every interface, levs[lev][0..n) = d (downward),
 // levs[lev][n..2n) = u (upward), lev = 0 .. ncut.  d0: the downward intensity at the top boundary
-// (scaled), rbB / sbB: reflection factor and emission of the bottom boundary in the form
-// u = rbB D (D . d) + D sbB (Lambertian; zeros: nothing comes up).
+// (scaled), bot: Rb [n][n] and sb [n] of the bottom boundary, u = Rb d + sb (zeros: nothing comes up).
 template <int n>
 __device__ __forceinline__ void adding_sweep_down(const double *recs, int ncut, double *levs, double d0,
-                                                  double rbB, double sbB, const double *cmu, const double *csq, int lane)
+                                                  const double *bot, const double *cmu, const double *csq, int lane)
 {
     using AO = AddOps<n>;
     constexpr int REC = AO::arec;
-    double d[n], cd[n];
+    double d[n];
 #pragma unroll
-    for (int c = 0; c < n; c++) { cd[c] = cmu[c] * csq[c]; d[c] = cd[c] * d0; }
+    for (int c = 0; c < n; c++) d[c] = cmu[c] * csq[c] * d0;
     const int row = lane < n ? lane : (lane < 2 * n ? lane - n : 0);
     double dme = cmu[row] * csq[row] * d0;          // lanes < n: d[lane]
     for (int lev = 0; lev <= ncut; lev++) {
         double x;
-        if (lev < ncut) {
-            // lanes 0..n-1: row of Y (next d); lanes n..2n-1: row of Rb (u at this level)
+        {
+            // lanes 0..n-1: row of Y (next d); lanes n..2n-1: row of Rb (u at this level; the
+            // bottom boundary's own at the last one)
             const double *orec = recs + (size_t)lev * REC;
-            const double *mrow = orec + (lane < n ? AO::o_Y : AO::o_Rb) + row * n;
-            x = orec[(lane < n ? AO::o_y : AO::o_sb) + row];
+            const double *mrow = lev < ncut ? orec + (lane < n ? AO::o_Y : AO::o_Rb) + row * n : bot + row * n;
+            x = lev < ncut ? orec[(lane < n ? AO::o_y : AO::o_sb) + row] : bot[n * n + row];
 #pragma unroll
             for (int c = 0; c < n; c++) x = fma(mrow[c], d[c], x);
-        } else {
-            double dd = 0.0;
-#pragma unroll
-            for (int c = 0; c < n; c++) dd = fma(cd[c], d[c], dd);
-            x = cmu[row] * csq[row] * (rbB * dd + sbB);
         }
         if (lane < n) levs[(size_t)lev * 2 * n + lane] = dme;
         else if (lane < 2 * n) levs[(size_t)lev * 2 * n + lane] = x;        // u_lev

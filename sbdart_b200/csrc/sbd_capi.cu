@@ -310,8 +310,9 @@ extern "C" int sbd_disort_batch_device(sbd_handle *h, const sbd_dims *dims, cons
     const bool adding_ok = adding_supported(N) && NU == 0 && dims->ntau == 0 && !getenv("SBD_FORCE_GENERIC");
     const bool adding = adding_ok && (brdf || !getenv("SBD_FORCE_ELIM"));
     // elimination register kernel: NSTR 4/8/16; radiances at the layer boundaries (the mode SBDART uses)
-    const bool fast = !adding && !brdf && (NU > 0 ? fast_rad_supported(N) && dims->ntau == 0 : fast_supported(N)) &&
-                      !getenv("SBD_FORCE_GENERIC");
+    // (radiance runs in the adding form: NSTR up to 32, BRDF surfaces too)
+    const bool fast_rad = NU > 0 && dims->ntau == 0 && fast_rad_supported(N) && (!brdf || !getenv("SBD_RAD_ELIM"));
+    const bool fast = !adding && (NU > 0 ? fast_rad : (!brdf && fast_supported(N))) && !getenv("SBD_FORCE_GENERIC");
     // CTA-per-bin register kernel: NSTR 20/24/32, fluxes
     const bool wide = !adding && !fast && !brdf && wide_supported(N) && NU == 0 && !getenv("SBD_FORCE_GENERIC") &&
                       wide_smem_bytes(N, L, NT) <= smem_limit;

@@ -805,7 +805,9 @@ disort_fast_kernel(const LaunchArgs a)
     using FL = FastLayout<n>;
     using AO = AddOps<n>;
     static_assert(!ADD || RAD, "the adding form of this kernel serves the radiance runs");
-    static_assert(!ADD || (size_t)AO::arec * 64 + 2 * n * 65 <= (size_t)FL::ublk * 64, "sweep records live in the pivot-row area");
+    static_assert(!ADD || ((size_t)AO::arec * 64 + 2 * n * 65 + n * n + n <= (size_t)FL::ublk * 64 &&
+                           (size_t)AO::arec + 2 * n * 2 + n * n + n <= (size_t)FL::ublk),
+                  "sweep records live in the pivot-row area");
     constexpr int N = 2 * n, TASKS = FL::tasks, GW = FL::GW, KS = FL::KS, LC = FL::LC, US = FL::US;
     static_assert(n <= 8 || ADD, "NSTR > 16: adding form only");
     static_assert(!RAD || SYNC, "radiance runs reload the CTA's Legendre table per azimuth mode");
@@ -856,6 +858,7 @@ disort_fast_kernel(const LaunchArgs a)
     double *dscr = ublk + (size_t)L * FL::ublk;           // RAD: [L][2][NU] downward source, transmission
     double *arecs = ublk;                                 // ADD: [L][arec] sweep records, then [L+1][2n] interface intensities
     double *levs = ublk + (size_t)L * AO::arec;
+    double *botb = levs + (size_t)(L + 1) * 2 * n;       // ADD: Rb, sb of the bottom boundary
     const int task = lane / GW;
     const bool gact = lane % GW < n;
     const int g = gact ? lane % GW : n - 1;
@@ -902,6 +905,7 @@ disort_fast_kernel(const LaunchArgs a)
         double *o_uavg = (a.uavg && have) ? a.uavg + (size_t)bin * NT : nullptr;
 
         int status = have ? 0 : -1;
+        int surf = -1;
         {   // CHEKIN subset (disort.f:4920-5155)
             int badl = 0;
             for (int lc = lane; lc < L; lc += 32) {
@@ -914,7 +918,12 @@ disort_fast_kernel(const LaunchArgs a)
                 }
             }
             if (fbeam < 0.0 || (fbeam > 0.0 && !(umu0 > 0.0 && umu0 <= 1.0))) badl = 1;
-            if (!(albedo >= 0.0 && albedo <= 1.0) || bp.fisot < 0.0) badl = 1;
+            // albedo = SBD_SURFACE(s): BRDF surface s (LAMBER = .FALSE.; the adding form carries it)
+            if (ADD && albedo < 0.0) {
+                surf = (int)(-albedo) - 1;
+                if (!a.sf_bdr || surf >= a.sf_count || (double)(surf + 1) != -albedo || a.sf_modes != N) badl = 1;
+            } else if (!(albedo >= 0.0 && albedo <= 1.0)) badl = 1;
+            if (bp.fisot < 0.0) badl = 1;
             if (plank && (bp.wvnmlo < 0.0 || bp.wvnmhi <= bp.wvnmlo || bp.temis < 0.0 ||
                           bp.temis > 1.0 || bp.btemp < 0.0 || bp.ttemp < 0.0)) badl = 1;
             // device-pointer callers: a Planck bin needs a valid row of temper[ncol][L+1]
@@ -1065,18 +1074,33 @@ disort_fast_kernel(const LaunchArgs a)
         double *rslot = tsm_base;   // phase-1 task areas are idle now
         double *stg = tsm_base + 3 * FL::rec;     // assembled rows of the current layer
         if (ADD && mrun && !status) {
-            // adding sweeps: bottom boundary (Lambertian: reflects the m = 0 mode only; nothing comes
-            // up at a truncation level), bottom-up operators, top-down intensities
-            const bool refl = !lyrcut && m0;
-            const double rbB = refl ? 2.0 * albedo : 0.0;
-            const double sbB = refl ? albedo * umu0 * fbeam / kPiRef * ebeam[ncut] + (1.0 - albedo) * bplank : 0.0;
+            // adding sweeps: bottom boundary (Lambertian: reflects the m = 0 mode only; a BRDF surface
+            // every mode, SURFAC's tables disort.f:3765-3907; nothing comes up at a truncation level),
+            // bottom-up operators, top-down intensities.  Scaled: Rb = (1 + delta_0m) D BDR D
             double *sRb = tsm_base, *ssb = sRb + n * n;
-            for (int e = lane; e < n * n; e += 32) sRb[e] = rbB * (cmu[e / n] * csq[e / n]) * (cmu[e % n] * csq[e % n]);
-            if (lane < n) ssb[lane] = cmu[lane] * csq[lane] * sbB;
+            if (surf >= 0 && !lyrcut) {
+                const double *bdr = a.sf_bdr + ((size_t)surf * a.sf_modes + mazim) * n * (n + 1);
+                const double *bem = a.sf_bem + (size_t)surf * n;
+                const double beamfac = umu0 * fbeam / kPiRef * ebeam[ncut];
+                for (int e = lane; e < n * n; e += 32) {
+                    const int i = e / n, k = e - i * n;
+                    sRb[e] = (1.0 + delm0) * (cmu[i] * csq[i]) * bdr[i * (n + 1) + 1 + k] * (cmu[k] * csq[k]);
+                }
+                if (lane < n)
+                    ssb[lane] = cmu[lane] * csq[lane] * (bdr[lane * (n + 1)] * beamfac + delm0 * bem[lane] * bplank);
+            } else {
+                const bool refl = !lyrcut && m0;
+                const double rbB = refl ? 2.0 * albedo : 0.0;
+                const double sbB = refl ? albedo * umu0 * fbeam / kPiRef * ebeam[ncut] + (1.0 - albedo) * bplank : 0.0;
+                for (int e = lane; e < n * n; e += 32) sRb[e] = rbB * (cmu[e / n] * csq[e / n]) * (cmu[e % n] * csq[e % n]);
+                if (lane < n) ssb[lane] = cmu[lane] * csq[lane] * sbB;
+            }
+            __syncwarp();
+            for (int e = lane; e < n * n + n; e += 32) botb[e] = sRb[e];      // kept for the top-down sweep
             __syncwarp();
             if (!adding_sweep_up<n>(arecs, ncut, tsm_base, lane)) status = SBD_BIN_SINGULAR;
             if (!status)
-                adding_sweep_down<n>(arecs, ncut, levs, m0 ? bp.fisot + tplank : 0.0, rbB, sbB, cmu, csq, lane);
+                adding_sweep_down<n>(arecs, ncut, levs, m0 ? bp.fisot + tplank : 0.0, botb, cmu, csq, lane);
         }
         if constexpr (!ADD) if (mrun && !status) {
             double w[KS][LC], rhs[KS];
@@ -1450,7 +1474,7 @@ disort_fast_kernel(const LaunchArgs a)
                     }
                     const double sdn = __shfl_sync(FULLMASK, dot, 1);
                     const double sav = __shfl_sync(FULLMASK, dot, 2);
-                    if (RAD && lu == L && !lyrcut)      // Lambertian surface, m = 0 (disort.f:4747-4778)
+                    if (RAD && lu == L && !lyrcut && surf < 0)      // Lambertian surface, m = 0 (disort.f:4747-4778)
                         bnd_up = 2.0 * albedo * sdn + umu0 * fbeam / kPiRef * albedo * fact + (1.0 - albedo) * bplank;
                     if (lane == 0) {
                         const double pi = kPiRef;
@@ -1484,8 +1508,24 @@ disort_fast_kernel(const LaunchArgs a)
                         ugl[lane] = (2 * lane + 1) * oprim * (rad_pm - f) / (1. - f);
                     __syncwarp();
                     const bool therm = plank && m0;
-                    if (lc == ncut - 1)                   // intensity entering the bottom layer from below
-                        for (int iu = lane; iu < NU; iu += 32) uI[iu] = (a.umu[iu] > 0.0 && m0 && !lyrcut) ? bnd_up : 0.0;
+                    if (lc == ncut - 1) {                 // intensity entering the bottom layer from below
+                        for (int iu = lane; iu < NU; iu += 32) {
+                            double v = 0.0;
+                            if (a.umu[iu] > 0.0 && !lyrcut) {
+                                if (ADD && surf >= 0) {
+                                    // BRDF surface (disort.f:4744-4778): RMU-weighted downward intensities
+                                    // at the bottom (w mu u = D u^), direct beam, emission
+                                    const double *rm = a.sf_rmu + (((size_t)surf * a.sf_modes + mazim) * NU + iu) * (n + 1);
+                                    const double *db = levs + (size_t)ncut * 2 * n;
+                                    for (int k = 0; k < n; k++) v = fma(rm[1 + k], cmu[k] * csq[k] * db[k], v);
+                                    v *= 1.0 + delm0;
+                                    if (fbeam > 0.0) v += umu0 * fbeam / kPiRef * rm[0] * ebeam[ncut];
+                                    if (m0) v += a.sf_emu[(size_t)surf * NU + iu] * bplank;
+                                } else if (m0) v = bnd_up;
+                            }
+                            uI[iu] = v;
+                        }
+                    }
                     // level at the bottom of the bottom layer
                     if (lc == ncut - 1)
                         for (int iu = lane; iu < NU; iu += 32)
