@@ -1,6 +1,6 @@
 """Tiny mixed run for compute-sanitizer: flux NSTR 4..32 (adding kernel; SBD_FORCE_ELIM=1: the
 elimination kernels) incl. thermal and truncated bins, a bin with a negative optical depth (handed
-to the elimination kernel), USRTAU, radiances, BRDF surfaces (adding and general kernel)."""
+to the elimination kernel), USRTAU, radiances (register kernel NSTR 8/20/32 and the general kernel), BRDF surfaces (fluxes and radiances)."""
 import sys; sys.path.insert(0, '.')
 import numpy as np
 import sbdart_b200 as sb
@@ -25,14 +25,22 @@ for nstr in (20, 24, 32):
 w = workloads.mls_shortwave(nstr=32, nlyr=65, wlinf=1.8, wlsup=2.2, wlinc=0.1, cloud_tau=10.0)
 o = s.disort_batch(w["dtauc"], w["ssalb"], w["pmom"], w["bins"], nstr=32, temper=w["temper"])
 print("wide thermal bad", int((o["status"] != 0).sum()))
-# radiances: register kernel (NSTR 8, azimuth modes, packed levels) and generic kernel (NSTR 20)
+# radiances: register kernel (NSTR 8, 20, 32; azimuth modes, packed levels) and general kernel
 w = workloads.retrieval_batch(6, nstr=8, nlyr=6, ncols=2, seed=3)
 o = s.disort_batch(w["dtauc"], w["ssalb"], w["pmom"], w["bins"], nstr=8, umu=np.array([-0.5, 0.5]), phi=np.array([0.0, 90.0]),
                    uu_levels=[0, 6], uu_packed=True)
 print("packed radiance bad", int((o["status"] != 0).sum()))
 w = workloads.retrieval_batch(4, nstr=20, nlyr=6, ncols=2, seed=5)
 o = s.disort_batch(w["dtauc"], w["ssalb"], w["pmom"], w["bins"], nstr=20, umu=np.array([-0.5, 0.5]), phi=np.array([0.0, 90.0]))
+print("20 radiance bad", int((o["status"] != 0).sum()))
+import os
+os.environ["SBD_FORCE_GENERIC"] = "1"
+o = s.disort_batch(w["dtauc"], w["ssalb"], w["pmom"], w["bins"], nstr=20, umu=np.array([-0.5, 0.5]), phi=np.array([0.0, 90.0]))
+del os.environ["SBD_FORCE_GENERIC"]
 print("generic radiance bad", int((o["status"] != 0).sum()))
+w = workloads.retrieval_batch(3, nstr=32, nlyr=5, ncols=2, seed=6)
+o = s.disort_batch(w["dtauc"], w["ssalb"], w["pmom"], w["bins"], nstr=32, umu=np.array([-0.5, 0.5]), phi=np.array([0.0]))
+print("32 radiance bad", int((o["status"] != 0).sum()))
 w = workloads.retrieval_batch(6, nstr=8, nlyr=6, ncols=2, seed=3)
 o = s.disort_batch(w["dtauc"], w["ssalb"], w["pmom"], w["bins"], nstr=8, umu=np.array([-0.5, 0.5]), phi=np.array([0.0, 90.0]))
 print("radiance bad", int((o["status"] != 0).sum()))
@@ -42,11 +50,11 @@ for nstr in (16, 32):
     w["dtauc"][3, 5] = -0.01
     o = s.disort_batch(w["dtauc"], w["ssalb"], w["pmom"], w["bins"], nstr=nstr)
     print(nstr, "handed-over bin bad", int((o["status"] != 0).sum()))
-# BRDF surfaces: fluxes (adding kernel) and radiances (general kernel)
+# BRDF surfaces: fluxes (adding kernel) and radiances (register kernel)
 from sbdart_b200.frontend import brdf
 model = brdf.SurfaceModel(9, [0.2, 0.1, 0.05, 1.5, 2.0])
 umu = np.array([-0.5, 0.3, 0.8])
-for nstr, rad in ((8, False), (20, False), (8, True)):
+for nstr, rad in ((8, False), (20, False), (8, True), (20, True)):
     mu, _ = sb.quadrature(nstr // 2)
     w = workloads.retrieval_batch(4, nstr=nstr, nlyr=6, ncols=1, seed=7)
     umu0 = float(w["bins"]["umu0"][0])
