@@ -331,7 +331,7 @@ extern "C" int sbd_disort_batch_device(sbd_handle *h, const sbd_dims *dims, cons
         // resident per SM under the shared-memory limit (deep atmospheres); the adding kernel
         // above NSTR = 16 runs 4-warp CTAs (register budget)
         warps = N > 16 ? 4 : fast_warps();
-        const int wmax = adding ? adding_warps_per_sm(N) : (N > 16 ? 4 : 16);
+        const int wmax = adding ? adding_warps_per_sm(N) : (N > 16 ? 8 : 16);
         int cta_per_sm = 0;
         for (int wtry = warps; wtry >= 4; wtry /= 2) {
             const size_t smem = adding ? adding_smem_bytes(N, L, wtry) : fast_smem_bytes(N, L, NT, wtry, NU, dims->nphi);

@@ -110,12 +110,10 @@ struct FastLayout {
     // work area shared by the phases: per-task areas (phase 1), 3 records + assembled rows (phase 2),
     // 2 x (pivot rows + flux record) (phase 3)
     static constexpr int cmax(int a, int b) { return a > b ? a : b; }
-    static constexpr int work = cmax(cmax(tasks * task, 3 * rec + ublk), 2 * (ublk + frec));
-    // radiance runs also stage the layer record in phase 3 (eigenvectors at the user angles)
-    // (NSTR > 16 runs the adding form only: no pivot rows in the phase-3 buffers)
-    static constexpr int stage_rows3 = n > 8 ? 0 : ublk;
-    static constexpr int work_rad = n > 8 ? cmax(cmax(tasks * task, AddOps<n>::p2), 2 * (frec + rec))
-                                          : cmax(work, 2 * (ublk + frec + rec));
+    static constexpr int work = cmax(cmax(cmax(tasks * task, 3 * rec + ublk), 2 * (ublk + frec)), 3 * SBD_MAX_NLYR);
+    // radiance runs also stage the layer record in phase 3 (eigenvectors at the user angles); the
+    // adding form has no pivot rows in its phase-3 buffers
+    __host__ __device__ static constexpr int stage3(bool add) { return 2 * ((add ? 0 : ublk) + frec + rec); }
     static constexpr int ecols = N + 3;            // eigen-terms + beam, Planck Z0, Z1 sources
     // user-angle work values: E[N][ecols], GU[NU][ecols], running intensity [NU], cos(m dphi) [NPHI], g_l [N]
     __host__ __device__ static size_t rad_doubles(int NU, int NPHI)
@@ -123,14 +121,21 @@ struct FastLayout {
         size_t d = (size_t)N * ecols + (size_t)NU * ecols + NU + NPHI + N;
         return (d + 1) & ~(size_t)1;
     }
-    __host__ __device__ static size_t warp_doubles(int L, int NT, int NU = 0, int NPHI = 0)
+    // work area of a radiance run: the phase-1 task areas (or the sweeps' matrices), later the
+    // phase-3 buffers with the user-angle work values behind them
+    __host__ __device__ static size_t work_rad(int NU, int NPHI, bool add)
     {
-        // y0, work area, taucpr/tauc, beam transmissions (2), pk(+2 boundary temps),
-        // prologue work values, level map; kept even for 16-byte alignment
+        const size_t base = n > 8 ? (size_t)cmax(tasks * task, AddOps<n>::p2) : (size_t)work;
+        const size_t p3 = (size_t)stage3(add) + rad_doubles(NU, NPHI);
+        return ((base > p3 ? base : p3) + 1) & ~(size_t)1;
+    }
+    __host__ __device__ static size_t warp_doubles(int L, int NT, int NU = 0, int NPHI = 0, bool add = false)
+    {
+        // y0, work area (also the 3 L prologue work values), taucpr/tauc, beam transmissions (2),
+        // pk(+2 boundary temps), level map; kept even for 16-byte alignment
         // (+ three mbarriers of the bulk-copy staging and a spare)
-        size_t d = (size_t)N + (NU > 0 ? work_rad : work) + 4 * (L + 1) + (L + 3) + 3 * L + (NT + 1) / 2 + 4;
-        d = (d + 1) & ~(size_t)1;
-        return d + (NU > 0 ? rad_doubles(NU, NPHI) : 0);
+        size_t d = (size_t)N + (NU > 0 ? work_rad(NU, NPHI, add) : (size_t)work) + 4 * (L + 1) + (L + 3) + (NT + 1) / 2 + 4;
+        return (d + 1) & ~(size_t)1;
     }
     // global scratch per warp: records, flux records, pivot rows (+ the downward-intensity
     // source and transmission of every layer for the top-down pass of radiance runs)
@@ -820,21 +825,21 @@ disort_fast_kernel(const LaunchArgs a)
     double *cmu = smem_fast, *cwt = cmu + n, *csq = cwt + n, *cdinv = csq + n;
     double *cylm = cdinv + n + 2;       // cylm[-2] = sum(w mu), cylm[-1] = sum(w)
     double *cylmu = smem_fast + FL::cta;
-    double *wsm = smem_fast + FL::cta_doubles(NU) + (size_t)warp * FL::warp_doubles(L, NT, NU, NPHI);
+    double *wsm = smem_fast + FL::cta_doubles(NU) + (size_t)warp * FL::warp_doubles(L, NT, NU, NPHI, ADD);
     double *y0 = wsm;
     // 16-byte aligned work area: per-task areas in phase 1, cp.async staging afterwards
     double *tsm_base = y0 + N;
-    double *taucpr = tsm_base + (RAD ? FL::work_rad : FL::work), *tauc = taucpr + (L + 1);
+    double *taucpr = tsm_base + (RAD ? FL::work_rad(NU, NPHI, ADD) : (size_t)FL::work), *tauc = taucpr + (L + 1);
     double *ebeam = tauc + (L + 1), *edir = ebeam + (L + 1);   // exp(-tau'/mu0), exp(-tau/mu0)
     double *pk = edir + (L + 1);
-    double *lw = pk + (L + 3);                                   // 3 x L prologue work values
-    int *layru = (int *)(lw + 3 * L);
+    double *lw = tsm_base;                                       // 3 x L prologue work values (the work area is idle then)
+    int *layru = (int *)(pk + (L + 3));
 #if SBD_USE_TMA
     // mbarriers of the bulk-copy staging: [0], [1] phase-3 double buffer, [2] phase-2 record prefetch
-    unsigned long long *mbar = reinterpret_cast<unsigned long long *>(lw + 3 * L + (NT + 1) / 2);
+    unsigned long long *mbar = reinterpret_cast<unsigned long long *>(pk + (L + 3) + (NT + 1) / 2);
 #endif
-    // radiance work values, behind the level map
-    double *uE = wsm + (FL::warp_doubles(L, NT, NU, NPHI) - FL::rad_doubles(NU, NPHI));
+    // radiance work values (phase 3 only): behind the phase-3 buffers in the work area
+    double *uE = tsm_base + FL::stage3(ADD);
     double *uGU = uE + N * FL::ecols, *uI = uGU + NU * FL::ecols, *cosm = uI + NU, *ugl = cosm + NPHI;
 
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -1250,7 +1255,7 @@ disort_fast_kernel(const LaunchArgs a)
             int lu_next = NT - 1;  // levels are visited bottom-up when the map is monotone
             // pivot rows + flux record of layer lc-1 stream into the other half of a
             // double buffer (cp.async) while layer lc is being solved
-            constexpr int UB = RAD ? FL::stage_rows3 : FL::ublk;      // pivot-row part of a buffer
+            constexpr int UB = ADD ? 0 : FL::ublk;      // pivot-row part of a buffer
             constexpr int kSlot = UB + FL::frec + (RAD ? FL::rec : 0);
             auto fetch_layer = [&](int lyr, int buf) {
                 double *dstp = tsm_base + buf * kSlot;
@@ -1630,18 +1635,22 @@ static cudaError_t launch_fast_k(const LaunchArgs &a, int grid, size_t smem, cud
     return cudaGetLastError();
 }
 
+// radiance runs: the adding form unless SBD_RAD_ELIM = 1 asks for the elimination (comparison knob, NSTR <= 16)
+static bool rad_adding(int N) { return N > 16 || !getenv("SBD_RAD_ELIM"); }
+
 template <int n>
 static cudaError_t launch_fast_t(const LaunchArgs &a, int warps, int grid, cudaStream_t st)
 {
     const int L = a.d.nlyr, NT = a.d.ntau > 0 ? a.d.ntau : L + 1;
-    size_t smem = 8 * (FastLayout<n>::cta_doubles(a.d.numu) + (size_t)warps * FastLayout<n>::warp_doubles(L, NT, a.d.numu, a.d.nphi));
+    const bool radd = rad_adding(a.d.nstr);
+    size_t smem = 8 * (FastLayout<n>::cta_doubles(a.d.numu) + (size_t)warps * FastLayout<n>::warp_doubles(L, NT, a.d.numu, a.d.nphi, radd));
     if constexpr (n > 8) {   // NSTR 20/24/32: radiance runs in the adding form, 4-warp CTAs (register budget)
         if (a.d.numu == 0 || warps != 4) return cudaErrorInvalidValue;
         return launch_fast_k<n, 4, true, true, true>(a, grid, smem, st);
     } else {
     if (a.d.numu > 0) {      // radiance runs: CTA-synchronous always
         // adding sweeps + solution recovery; SBD_RAD_ELIM = 1: the elimination (comparison knob)
-        const bool add = !getenv("SBD_RAD_ELIM");
+        const bool add = radd;
         switch (warps) {
         case 4: return add ? launch_fast_k<n, 4, true, true, true>(a, grid, smem, st) : launch_fast_k<n, 4, true, true>(a, grid, smem, st);
         case 8: return add ? launch_fast_k<n, 8, true, true, true>(a, grid, smem, st) : launch_fast_k<n, 8, true, true>(a, grid, smem, st);
@@ -1677,12 +1686,12 @@ size_t fast_slot_doubles(int N, int L, int NU)
 size_t fast_smem_bytes(int N, int L, int NT, int warps, int NU, int NPHI)
 {
     switch (N) {
-    case 4: return 8 * (FastLayout<2>::cta_doubles(NU) + (size_t)warps * FastLayout<2>::warp_doubles(L, NT, NU, NPHI));
-    case 8: return 8 * (FastLayout<4>::cta_doubles(NU) + (size_t)warps * FastLayout<4>::warp_doubles(L, NT, NU, NPHI));
-    case 16: return 8 * (FastLayout<8>::cta_doubles(NU) + (size_t)warps * FastLayout<8>::warp_doubles(L, NT, NU, NPHI));
-    case 20: return 8 * (FastLayout<10>::cta_doubles(NU) + (size_t)warps * FastLayout<10>::warp_doubles(L, NT, NU, NPHI));
-    case 24: return 8 * (FastLayout<12>::cta_doubles(NU) + (size_t)warps * FastLayout<12>::warp_doubles(L, NT, NU, NPHI));
-    case 32: return 8 * (FastLayout<16>::cta_doubles(NU) + (size_t)warps * FastLayout<16>::warp_doubles(L, NT, NU, NPHI));
+    case 4: return 8 * (FastLayout<2>::cta_doubles(NU) + (size_t)warps * FastLayout<2>::warp_doubles(L, NT, NU, NPHI, rad_adding(N)));
+    case 8: return 8 * (FastLayout<4>::cta_doubles(NU) + (size_t)warps * FastLayout<4>::warp_doubles(L, NT, NU, NPHI, rad_adding(N)));
+    case 16: return 8 * (FastLayout<8>::cta_doubles(NU) + (size_t)warps * FastLayout<8>::warp_doubles(L, NT, NU, NPHI, rad_adding(N)));
+    case 20: return 8 * (FastLayout<10>::cta_doubles(NU) + (size_t)warps * FastLayout<10>::warp_doubles(L, NT, NU, NPHI, rad_adding(N)));
+    case 24: return 8 * (FastLayout<12>::cta_doubles(NU) + (size_t)warps * FastLayout<12>::warp_doubles(L, NT, NU, NPHI, rad_adding(N)));
+    case 32: return 8 * (FastLayout<16>::cta_doubles(NU) + (size_t)warps * FastLayout<16>::warp_doubles(L, NT, NU, NPHI, rad_adding(N)));
     }
     return 0;
 }
