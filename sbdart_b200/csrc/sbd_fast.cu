@@ -115,10 +115,11 @@ struct FastLayout {
     // adding form has no pivot rows in its phase-3 buffers
     __host__ __device__ static constexpr int stage3(bool add) { return 2 * ((add ? 0 : ublk) + frec + rec); }
     static constexpr int ecols = N + 3;            // eigen-terms + beam, Planck Z0, Z1 sources
-    // user-angle work values: E[N][ecols], GU[NU][ecols], running intensity [NU], cos(m dphi) [NPHI], g_l [N]
+    // user-angle work values: E[N][ecols], GU[NU][ecols], running intensity [NU], cos(m dphi) [NPHI], g_l [N],
+    // layer solution [N]
     __host__ __device__ static size_t rad_doubles(int NU, int NPHI)
     {
-        size_t d = (size_t)N * ecols + (size_t)NU * ecols + NU + NPHI + N;
+        size_t d = (size_t)N * ecols + (size_t)NU * ecols + NU + NPHI + 2 * N;
         return (d + 1) & ~(size_t)1;
     }
     // work area of a radiance run: the phase-1 task areas (or the sweeps' matrices), later the
@@ -672,53 +673,69 @@ __device__ __forceinline__ void lepoly_mode(int m, int N, double x, double *y)
 
 // User-angle terms of one layer for azimuth mode m (TERPEV disort.f:3920, TERPSO :3980):
 // the eigenvectors times the solution coefficients, the beam and the Planck particular
-// solutions re-expanded at the user cosines through the Legendre sum.
-//   E [l][c]  = 1/2 g_l sum_i w_i Y_l^m(mu_i) V_c(mu_i)     c < N: eigenvector c times x_c;
-//               c = N beam (+ the direct term), N+1 / N+2 Planck Z0 / Z1
-//   GU[iu][c] = sum_l E[l][c] Y_l^m(umu_iu)
-// rec: the layer record (shared); xs: the layer's solution (uniform registers).
+// solutions re-expanded at the user cosines through the Legendre sum,
+//   GU[iu][c] = sum_l 1/2 g_l [sum_i w_i Y_l^m(mu_i) V_c(mu_i)] Y_l^m(umu_iu)      (V_c over all N directions)
+//               c < N: eigenvector c times x_c; c = N beam (+ the direct term), N+1 / N+2 Planck Z0 / Z1.
+// With Y_l^m(-mu) = (-1)^(l-m) Y_l^m(mu) the sum over the N directions of the eigenvector pair +-k_j
+// needs only F[l][j] = sum_i w_i Y_l^m(mu_i) (G+ + G-)(i,j) for even l-m, (G+ - G-)(i,j) for odd l-m:
+//   column n+j:   x (He + Ho),   column n-1-j:   x (Ho - He),   He / Ho = sum over even / odd l-m of
+//   1/2 g_l F[l][j] Y_l^m(umu)  -- half the products of the straightforward form, and the solution
+// enters at the end.
+// rec: the layer record (shared); sx: the layer's solution (shared); E: work area, N x ecols.
 template <int n>
 __device__ __forceinline__ void user_terms_fast(
-    const double *rec, const double (&xs)[2 * n], const double *gl, const double *cwt,
+    const double *rec, const double *sx, const double *gl, const double *cwt,
     const double *cylm, const double *y0, const double *ylmu_m, int NU, int mazim,
     bool beam, double fact, bool therm, double oprim, double *E, double *GU, int lane)
 {
     using FL = FastLayout<n>;
     constexpr int N = 2 * n, EC = FL::ecols;
+    constexpr int JW = (n % 4 == 0) ? 4 : 2, JG = n / JW;      // columns per work item
     const double *gp = rec + FL::off_gp, *gm = rec + FL::off_gm;
     const double *zz = rec + FL::off_zz, *zp0 = rec + FL::off_zp0;
     const double xr0 = rec[FL::off_xr], xr1 = rec[FL::off_xr + 1];
-    double xl[N];
+    double *Fs = E, *Eb = E + N * n;         // [N][n] scaled F, [N][3] beam / Planck columns
+    for (int it = lane; it < N * JG; it += 32) {
+        const int l = it / JG, jq = (it - l * JG) * JW;
+        double acc[JW];
 #pragma unroll
-    for (int j = 0; j < N; j++) xl[j] = xs[j];
-    for (int e = lane; e < N * EC; e += 32) {
-        const int l = e / EC, c = e - l * EC;
+        for (int q = 0; q < JW; q++) acc[q] = 0.0;
+        if (l >= mazim) {
+            const bool odd = (l - mazim) & 1;
+            const double *yl = cylm + l * n;
+#pragma unroll
+            for (int i = 0; i < n; i++) {
+                const double wy = cwt[i] * yl[i];
+                const double2 *a2 = reinterpret_cast<const double2 *>(gp + i * n + jq);
+                const double2 *b2 = reinterpret_cast<const double2 *>(gm + i * n + jq);
+#pragma unroll
+                for (int q2 = 0; q2 < JW / 2; q2++) {
+                    const double2 a = a2[q2], b = b2[q2];
+                    acc[2 * q2] = fma(wy, odd ? a.x - b.x : a.x + b.x, acc[2 * q2]);
+                    acc[2 * q2 + 1] = fma(wy, odd ? a.y - b.y : a.y + b.y, acc[2 * q2 + 1]);
+                }
+            }
+            const double h = 0.5 * gl[l];
+#pragma unroll
+            for (int q = 0; q < JW; q++) acc[q] *= h;
+        }
+#pragma unroll
+        for (int q = 0; q < JW; q++) Fs[l * n + jq + q] = acc[q];
+    }
+    for (int e = lane; e < N * 3; e += 32) {
+        const int l = e / 3, cc = e - l * 3;
         double acc = 0.0;
         if (l >= mazim) {
             const double sg = ((l - mazim) & 1) ? -1.0 : 1.0;
             const double *yl = cylm + l * n;
-            if (c < N) {
-                const bool plus = c >= n;
-                const int j = plus ? c - n : n - 1 - c;
-#pragma unroll
-                for (int i = 0; i < n; i++) {
-                    const double a = gp[i * n + j], b = gm[i * n + j];
-                    const double ev = plus ? fma(sg, b, a) : -fma(sg, a, b);
-                    acc = fma(cwt[i] * yl[i], ev, acc);
-                }
-                // x_c: the register array is indexed with a run-time c through a select chain
-                double xc = 0.0;
-#pragma unroll
-                for (int j2 = 0; j2 < N; j2++) xc = (c == j2) ? xl[j2] : xc;
-                acc *= 0.5 * gl[l] * xc;
-            } else if (c == N) {
+            if (cc == 0) {
                 if (beam) {
 #pragma unroll
                     for (int i = 0; i < n; i++) acc = fma(cwt[i] * yl[i], fma(sg, zz[n - 1 - i], zz[n + i]), acc);
                     acc = 0.5 * gl[l] * acc + fact * gl[l] * y0[l];
                 }
             } else if (therm) {
-                if (c == N + 1) {
+                if (cc == 1) {
 #pragma unroll
                     for (int i = 0; i < n; i++) acc = fma(cwt[i] * yl[i], fma(sg, zp0[n - 1 - i], zp0[n + i]), acc);
                 } else {
@@ -728,16 +745,48 @@ __device__ __forceinline__ void user_terms_fast(
                 acc *= 0.5 * gl[l];
             }
         }
-        E[e] = acc;
+        Eb[e] = acc;
     }
     __syncwarp();
-    for (int e = lane; e < NU * EC; e += 32) {
-        const int iu = e / EC, c = e - iu * EC;
+    for (int it = lane; it < NU * JG; it += 32) {
+        const int iu = it / JG, jq = (it - iu * JG) * JW;
+        double he[JW], ho[JW];
+#pragma unroll
+        for (int q = 0; q < JW; q++) { he[q] = 0.0; ho[q] = 0.0; }
+        for (int l = mazim; l < N; l += 2) {
+            const double yu0 = ylmu_m[l * NU + iu];
+            const double2 *f0 = reinterpret_cast<const double2 *>(Fs + l * n + jq);
+#pragma unroll
+            for (int q2 = 0; q2 < JW / 2; q2++) {
+                const double2 f = f0[q2];
+                he[2 * q2] = fma(f.x, yu0, he[2 * q2]);
+                he[2 * q2 + 1] = fma(f.y, yu0, he[2 * q2 + 1]);
+            }
+            if (l + 1 < N) {
+                const double yu1 = ylmu_m[(l + 1) * NU + iu];
+                const double2 *f1 = reinterpret_cast<const double2 *>(Fs + (l + 1) * n + jq);
+#pragma unroll
+                for (int q2 = 0; q2 < JW / 2; q2++) {
+                    const double2 f = f1[q2];
+                    ho[2 * q2] = fma(f.x, yu1, ho[2 * q2]);
+                    ho[2 * q2 + 1] = fma(f.y, yu1, ho[2 * q2 + 1]);
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < JW; q++) {
+            const int j = jq + q;
+            GU[iu * EC + n + j] = sx[n + j] * (he[q] + ho[q]);
+            GU[iu * EC + n - 1 - j] = sx[n - 1 - j] * (ho[q] - he[q]);
+        }
+    }
+    for (int e = lane; e < NU * 3; e += 32) {
+        const int iu = e / 3, cc = e - iu * 3;
         double acc = 0.0;
-        for (int l = mazim; l < N; l++) acc = fma(E[l * EC + c], ylmu_m[l * NU + iu], acc);
-        if (therm && c == N + 1) acc += (1. - oprim) * xr0;
-        if (therm && c == N + 2) acc += (1. - oprim) * xr1;
-        GU[e] = acc;
+        for (int l = mazim; l < N; l++) acc = fma(Eb[l * 3 + cc], ylmu_m[l * NU + iu], acc);
+        if (therm && cc == 1) acc += (1. - oprim) * xr0;
+        if (therm && cc == 2) acc += (1. - oprim) * xr1;
+        GU[iu * EC + N + cc] = acc;
     }
     __syncwarp();
 }
@@ -840,7 +889,7 @@ disort_fast_kernel(const LaunchArgs a)
 #endif
     // radiance work values (phase 3 only): behind the phase-3 buffers in the work area
     double *uE = tsm_base + FL::stage3(ADD);
-    double *uGU = uE + N * FL::ecols, *uI = uGU + NU * FL::ecols, *cosm = uI + NU, *ugl = cosm + NPHI;
+    double *uGU = uE + N * FL::ecols, *uI = uGU + NU * FL::ecols, *cosm = uI + NU, *ugl = cosm + NPHI, *usx = ugl + N;
 
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         double mu = a.quad[i], wt = a.quad[n + i];
@@ -1291,12 +1340,12 @@ disort_fast_kernel(const LaunchArgs a)
                     const double azterm = val * cosm[j];
                     const double unew = *pu + azterm;
                     *pu = unew;
-                    const double aa = fabs(azterm), bb = fabs(unew);       // RATIO, disort.f:6159
-                    double rr;
-                    if (aa == 0.0) rr = (bb == 0.0) ? 1.0 : 0.0;
-                    else if (bb == 0.0) rr = 1.79e308;
-                    else rr = aa / bb;
-                    azerr = fmax(azerr, rr);
+                    // convergence test of the series (RATIO, disort.f:6159, and :821): is
+                    // |term| / |sum| <= ACCUR everywhere?  Kept as a flag (a comparison instead of a
+                    // division per intensity; SBDART runs ACCUR = 0, where both forms say term == 0)
+                    const double aa = fabs(azterm), bb = fabs(unew);
+                    const bool small = (aa == 0.0) ? (bb != 0.0 || 1.0 <= bp.accur) : (bb != 0.0 && aa <= bp.accur * bb);
+                    if (!small) azerr = 1.0;
                 }
             };
 #if SBD_TMA_P3
@@ -1365,6 +1414,7 @@ disort_fast_kernel(const LaunchArgs a)
                         xs[n + j] = __shfl_sync(FULLMASK, xp, j);
                         xs[n - 1 - j] = __shfl_sync(FULLMASK, xm, j);
                     }
+                    if (lane < n) { usx[n + lane] = xp; usx[n - 1 - lane] = xm; }
                 } else {
                 double acc, dinv;
                 double ur[N];      // row `lane` of the upper triangle, pre-divided by the diagonal
@@ -1390,6 +1440,12 @@ disort_fast_kernel(const LaunchArgs a)
                     const double xc = __shfl_sync(FULLMASK, acc, c);
                     xs[c] = xc;
                     if (lane < c) acc = fma(-ur[c], xc, acc);
+                }
+                if (RAD) {
+                    double v = 0.0;
+#pragma unroll
+                    for (int j2 = 0; j2 < N; j2++) v = (lane == j2) ? xs[j2] : v;
+                    if (lane < N) usx[lane] = v;
                 }
                 }
 #ifdef SBD_PHASE_TIMING
@@ -1500,6 +1556,9 @@ disort_fast_kernel(const LaunchArgs a)
                         if (o_dfdt) o_dfdt[lu] = sc[8] * 4. * pi * (uavg - plsorc);
                     }
                 }
+#ifdef SBD_PHASE_TIMING
+                if (RAD && threadIdx.x == 0) { const long long t = clock64(); atomicAdd(&g_phase_ticks[6], (unsigned long long)(t - tsub)); tsub = t; }
+#endif
                 if (RAD) {
                     // ---- intensities at the user angles (TERPEV, TERPSO, USRINT) ----
                     const double *urec = fr + FL::frec;
@@ -1536,7 +1595,7 @@ disort_fast_kernel(const LaunchArgs a)
                         for (int iu = lane; iu < NU; iu += 32)
                             if (a.umu[iu] > 0.0) emit(ncut, iu, uI[iu]);
                     __syncwarp();
-                    user_terms_fast<n>(urec, xs, ugl, cwt, cylm, y0, ylmu_m, NU, mazim, fbeam > 0.0,
+                    user_terms_fast<n>(urec, usx, ugl, cwt, cylm, y0, ylmu_m, NU, mazim, fbeam > 0.0,
                                        (2. - delm0) * fbeam / (4.0 * kPiRef), therm, oprim, uE, uGU, lane);
                     for (int iu = lane; iu < NU; iu += 32) {
                         const double umu = a.umu[iu];
@@ -1564,7 +1623,7 @@ disort_fast_kernel(const LaunchArgs a)
                 }
                 __syncwarp();     // everyone is done with this half of the double buffer
 #ifdef SBD_PHASE_TIMING
-                if (threadIdx.x == 0) { const long long t = clock64(); atomicAdd(&g_phase_ticks[6], (unsigned long long)(t - tsub)); tsub = t; }
+                if (threadIdx.x == 0) { const long long t = clock64(); atomicAdd(&g_phase_ticks[RAD ? 7 : 6], (unsigned long long)(t - tsub)); tsub = t; }
 #endif
             }
             if (RAD) {
@@ -1582,14 +1641,13 @@ disort_fast_kernel(const LaunchArgs a)
                     }
                 }
                 if (mazim > 0) {
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) azerr = fmax(azerr, __shfl_xor_sync(FULLMASK, azerr, o));
-                    if (azerr <= bp.accur) kconv++;
+                    if (!__any_sync(FULLMASK, azerr != 0.0)) kconv++;
                     if (kconv >= 2) naz = mazim;       // converged: no further modes (disort.f:821-823)
                 }
                 __syncwarp();
             }
         }
+        if (RAD) SBD_TICK(3);
       }   // azimuth modes
         cp_async_wait_all();
         if (lane == 0 && have) a.status[bin] = status;
