@@ -816,7 +816,8 @@ __device__ __forceinline__ double layer_source(const double *gu /* GU row of thi
         else expn = up ? (eb0 - T * eb1) * rdenom : (eb1 - T * eb0) * rdenom;
         s = gu[N] * expn;
     }
-#pragma unroll 1
+    double sp = 0.0;      // second accumulator: two modes in flight (the reciprocals overlap)
+#pragma unroll 2
     for (int j = 0; j < n; j++) {
         const double k = kk[j], wk = ek[j];
         // column n-1-j belongs to -k_j, column n+j to +k_j (disort.f:3264-3312); the divisions by
@@ -831,8 +832,9 @@ __device__ __forceinline__ double layer_source(const double *gu /* GU row of thi
             ep = (fabs(dp) < 0.0001) ? -dtau * rmu * T : (wk - T) * fast_rcp(dp);
         }
         s = fma(gu[n - 1 - j], em, s);
-        s = fma(gu[n + j], ep, s);
+        sp = fma(gu[n + j], ep, sp);
     }
+    s += sp;
     if (therm) {
         const double f0 = 1.0 - T;
         const double f1 = up ? (t0 + umu) - (t1 + umu) * T : (t1 + umu) - (t0 + umu) * T;
