@@ -622,7 +622,7 @@ __device__ __forceinline__ bool elim_step(double (&w)[FastLayout<n>::KS][FastLay
 #pragma unroll
         for (int l2 = 0; l2 < W / 2; l2++)
             reinterpret_cast<double2 *>(uslice)[l2] = make_double2(p[2 * l2], p[2 * l2 + 1]);
-        if (cg == 0) uslice[4 * LC] = pr;
+        if (cg == 0) *reinterpret_cast<double2 *>(uslice + 4 * LC) = make_double2(pr, 0.0);   // rhs, pad
     }
     // update; after the last column group of a slice position every row drops its
     // leading entry, so the current column is always entry 0 of the slice (dead

@@ -760,7 +760,7 @@ disort_wide_kernel(const LaunchArgs a)
 #pragma unroll
                         for (int l2 = 0; l2 < LC / 2; l2++)
                             reinterpret_cast<double2 *>(urow + cg * LC)[l2] = make_double2(p[2 * l2], p[2 * l2 + 1]);
-                        if (cg == 0) urow[CG * LC] = pr;
+                        if (cg == 0) *reinterpret_cast<double2 *>(urow + CG * LC) = make_double2(pr, 0.0);   // rhs, pad
                     }
 #pragma unroll
                     for (int k = 0; k < KS; k++) rhs[k] = fma(m[k], pr, rhs[k]);

@@ -7,6 +7,7 @@ import numpy as np
 import sbdart_b200 as sb
 from sbdart_b200 import workloads
 nstr = int(sys.argv[1]) if len(sys.argv) > 1 else 16
+top_only = len(sys.argv) > 2 and sys.argv[2] == 'top'      # what SBDART's iout=5/20 consume
 umu = np.array([-1.0, -0.8, -0.5, -0.2, -0.05, 0.05, 0.3, 0.6, 0.9, 1.0])
 phi = np.array([0.0, 60.0, 180.0])
 w = workloads.retrieval_batch(4096, nstr=nstr, nlyr=33, ncols=8, seed=nstr)
@@ -15,7 +16,8 @@ s = sb.Solver(0)
 L = sb.lib()
 t = (C.c_ulonglong * 8)()
 for rep in range(2):
-    s.disort_batch(w["dtauc"], w["ssalb"], w["pmom"], w["bins"], nstr=nstr, umu=umu, phi=phi)
+    s.disort_batch(w["dtauc"], w["ssalb"], w["pmom"], w["bins"], nstr=nstr, umu=umu, phi=phi,
+                   uu_levels=[0] if top_only else None, uu_packed=top_only)
     L.sbd_debug_phase_ticks(t, 1)
 tot = sum(t[:4])
 for name, v in zip(("prologue", "phase 1", "phase 2", "phase 3"), t):
