@@ -101,7 +101,9 @@ struct FastLayout {
     __host__ __device__ static size_t cta_doubles(int NU) { return (size_t)cta + (((size_t)N * NU + 1) & ~(size_t)1); }
     // phase 1: a layer is owned by a group of GW lanes (the n first ones hold a row / column /
     // mode each; for n = 10, 12 the rest shadow lane n-1, compute along and store nothing)
-    static constexpr int GW = n <= 2 ? 2 : (n <= 4 ? 4 : (n <= 8 ? 8 : 16));
+    // (n = 10: three groups of 10 lanes, lanes 30 and 31 shadow lane 29; shuffles then name the
+    // source lane in the warp)
+    static constexpr int GW = n <= 2 ? 2 : (n <= 4 ? 4 : (n <= 8 ? 8 : (n == 10 ? 10 : 16)));
     static constexpr int tasks = 32 / GW;
     // gl, K, L, G1, G2 [n][LD], vectors.  Rows n + 2 doubles apart (row-wise accesses of a layer group's
     // lanes hit different banks), areas padded to 4 (mod 16) doubles (the groups' broadcast loads too)
@@ -143,13 +145,30 @@ struct FastLayout {
     __host__ __device__ static size_t slot_doubles_rad(int L, int NU) { return slot_doubles(L) + (size_t)2 * L * NU; }
 };
 
-// sum over the GW lanes of a layer group (shadow lanes pass zero)
+// sum over the GW lanes of a layer group (shadow lanes pass zero); g: lane in group, gbase: first lane
 template <int GW>
-__device__ __forceinline__ double group_sum(double v)
+__device__ __forceinline__ double group_sum(double v, int g, int gbase)
 {
+    if constexpr ((GW & (GW - 1)) == 0) {
 #pragma unroll
-    for (int o = GW / 2; o > 0; o >>= 1) v += __shfl_xor_sync(FULLMASK, v, o, GW);
-    return v;
+        for (int o = GW / 2; o > 0; o >>= 1) v += __shfl_xor_sync(FULLMASK, v, o, GW);
+        return v;
+    } else {
+        static_assert(GW == 10, "group of 10 lanes");
+        const double t = __shfl_down_sync(FULLMASK, v, 8);
+        if (g < 2) v += t;
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) v += __shfl_down_sync(FULLMASK, v, o);
+        return __shfl_sync(FULLMASK, v, gbase);
+    }
+}
+
+// value of lane j of the layer group
+template <int GW>
+__device__ __forceinline__ double group_get(double v, int j, int gbase)
+{
+    if constexpr ((GW & (GW - 1)) == 0) return shfl_d(v, j, GW);
+    else return __shfl_sync(FULLMASK, v, gbase + j);
 }
 
 // Round-robin (tournament) pairing of the one-sided Jacobi sweeps: the partner of
@@ -186,7 +205,7 @@ __device__ __forceinline__ int phase1_layers(
     const double *y0, const double *taucpr, const double *pk,
     double *tsm /* per-task shared */, double *rec /* scratch record of this layer */,
     double *frec /* flux record of this layer */, int g /* lane in group (shadow lanes: n-1) */,
-    bool gact /* false: shadow lane */,
+    bool gact /* false: shadow lane */, int gbase /* first lane of the group */,
     unsigned long long jpart /* Jacobi partners of this lane, see jacobi_partners */,
     double *arec = nullptr /* ADDREC: the layer's R, T, s_up, s_dn */, const double *ebeam = nullptr)
 {
@@ -245,10 +264,10 @@ __device__ __forceinline__ int phase1_layers(
         double nume = pe[j], numo = po[j];
 #pragma unroll
         for (int k = 0; k < j; k++) {
-            nume = fma(-pe[k], shfl_d(pe[k], j, GW), nume);
-            numo = fma(-po[k], shfl_d(po[k], j, GW), numo);
+            nume = fma(-pe[k], group_get<GW>(pe[k], j, gbase), nume);
+            numo = fma(-po[k], group_get<GW>(po[k], j, gbase), numo);
         }
-        double pive = shfl_d(nume, j, GW), pivo = shfl_d(numo, j, GW);
+        double pive = group_get<GW>(nume, j, gbase), pivo = group_get<GW>(numo, j, gbase);
         if (!(pivo > 0.0)) { bad = 1; pivo = 1.0; }
         // Pe~ is only semidefinite when w' -> 1: keep the factor real (a NaN pivot is a failure)
         const double floor_e = 1.0e-30;
@@ -299,10 +318,10 @@ __device__ __forceinline__ int phase1_layers(
                 const int partner = (int)(jpart >> (PB * r)) & ((1 << PB) - 1);
                 double pa[n];
                 double g0 = 0.0, g1 = 0.0;
-                const double oth2 = shfl_d(own2, partner, GW);
+                const double oth2 = group_get<GW>(own2, partner, gbase);
 #pragma unroll
                 for (int i = 0; i < n; i++) {
-                    pa[i] = shfl_d(a[i], partner, GW);
+                    pa[i] = group_get<GW>(a[i], partner, gbase);
                     if (i & 1) g1 = fma(a[i], pa[i], g1); else g0 = fma(a[i], pa[i], g0);
                 }
                 const double gam = g0 + g1;
@@ -473,10 +492,10 @@ __device__ __forceinline__ int phase1_layers(
     // quadrature sums of the particular solutions (same functionals as above)
     {
         const double wmg = gact ? cwt[g] * cmu[g] : 0.0, wg = gact ? cwt[g] : 0.0;
-        const double Zu = group_sum<GW>(wmg * zup);
-        const double Zd = group_sum<GW>(wmg * zdn);
-        const double Za = group_sum<GW>(wg * (zup + zdn));
-        const double Q1 = (plank && mazim == 0) ? group_sum<GW>(wmg * q) : 0.0;
+        const double Zu = group_sum<GW>(wmg * zup, g, gbase);
+        const double Zd = group_sum<GW>(wmg * zdn, g, gbase);
+        const double Za = group_sum<GW>(wg * (zup + zdn), g, gbase);
+        const double Q1 = (plank && mazim == 0) ? group_sum<GW>(wmg * q, g, gbase) : 0.0;
         if (active && g == 0) {
             const double W = cylm[-2], SW = cylm[-1];      // sum(w mu), sum(w): see the kernel
             double *sc = frec + FL::f_sc;
@@ -915,9 +934,11 @@ disort_fast_kernel(const LaunchArgs a)
     double *arecs = ublk;                                 // ADD: [L][arec] sweep records, then [L+1][2n] interface intensities
     double *levs = ublk + (size_t)L * AO::arec;
     double *botb = levs + (size_t)(L + 1) * 2 * n;       // ADD: Rb, sb of the bottom boundary
-    const int task = lane / GW;
-    const bool gact = lane % GW < n;
+    // layer group of this lane; lanes beyond the last full group shadow its last lane
+    const int task = lane / GW < TASKS ? lane / GW : TASKS - 1;
+    const bool gact = lane < TASKS * GW && lane % GW < n;
     const int g = gact ? lane % GW : n - 1;
+    const int gbase = task * GW;
     // the spectrum path keeps the bin count on the device (a.d.nbins is then an upper bound)
     const int nbins_all = a.redo_consume ? *a.redo_count : (a.nbins_dev ? *a.nbins_dev : a.d.nbins);
     double *tsm = tsm_base + (size_t)task * FL::task;
@@ -1112,7 +1133,7 @@ disort_fast_kernel(const LaunchArgs a)
                 if (!active) lc = ncut - 1;
                 int st = phase1_layers<n, ADD>(dtauc, ssalb, pmom, ldp, lc, active, RAD ? mazim : 0, fbeam, umu0,
                                                plank && m0, delm0, cmu, cwt, csq, cdinv, cylm, y0, taucpr, pk, tsm,
-                                               recs + (size_t)lc * FL::rec, frecs + (size_t)lc * FL::frec, g, gact, jpart,
+                                               recs + (size_t)lc * FL::rec, frecs + (size_t)lc * FL::frec, g, gact, gbase, jpart,
                                                arecs + (size_t)lc * AO::arec, ebeam);
                 if (__any_sync(FULLMASK, st != 0)) { status = SBD_BIN_EIG_FAIL; break; }
             }
