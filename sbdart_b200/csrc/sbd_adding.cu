@@ -76,7 +76,8 @@ struct AddLayout {
     static constexpr int CW = n / CG;
     // phase 1: a layer is owned by a group of GW lanes (the n first ones hold a row / column /
     // mode each; for n = 10, 12 the rest shadow lane n-1)
-    static constexpr int GW = n <= 2 ? 2 : (n <= 4 ? 4 : (n <= 8 ? 8 : 16));
+    // (n = 10: three groups of 10 lanes, lanes 30 and 31 shadow lane 29)
+    static constexpr int GW = n <= 2 ? 2 : (n <= 4 ? 4 : (n <= 8 ? 8 : (n == 10 ? 10 : 16)));
     // phase-1 shared memory per layer group: gl[N], K, L, P, X [n][LD], 4 vectors.  Rows are n + 2
     // doubles apart: row-wise accesses of the group's lanes (stride 16 B x odd) hit different banks
     static constexpr int LD = n + 2;
@@ -104,13 +105,6 @@ struct AddLayout {
     __host__ __device__ static size_t slot_doubles(int L) { return (size_t)L * rec; }
 };
 
-template <int n>
-__device__ __forceinline__ double add_group_sum(double v)
-{
-#pragma unroll
-    for (int o = n / 2; o > 0; o >>= 1) v += __shfl_xor_sync(FULLMASK, v, o, n);
-    return v;
-}
 
 template <int n>
 __device__ __forceinline__ unsigned long long add_jacobi_partners(int g)
@@ -143,7 +137,7 @@ __device__ __forceinline__ int phase1_adding(
     double fbeam, double umu0, bool plank,
     const double *cmu, const double *csq, const double *cd, const double *cylm,
     const double *y0, const double *ebeam, const double *pk,
-    double *tsm, double *rec, int g, bool gact, unsigned long long jpart)
+    double *tsm, double *rec, int g, bool gact, int gbase, unsigned long long jpart)
 {
     using AL = AddLayout<n>;
     constexpr int N = 2 * n, GW = AL::GW, PB = n > 8 ? 4 : 3, LD = AL::LD;
@@ -199,10 +193,10 @@ __device__ __forceinline__ int phase1_adding(
         double nume = pe[j], numo = po[j];
 #pragma unroll
         for (int k = 0; k < j; k++) {
-            nume = fma(-pe[k], shfl_d(pe[k], j, GW), nume);
-            numo = fma(-po[k], shfl_d(po[k], j, GW), numo);
+            nume = fma(-pe[k], group_get<GW>(pe[k], j, gbase), nume);
+            numo = fma(-po[k], group_get<GW>(po[k], j, gbase), numo);
         }
-        double pive = shfl_d(nume, j, GW), pivo = shfl_d(numo, j, GW);
+        double pive = group_get<GW>(nume, j, gbase), pivo = group_get<GW>(numo, j, gbase);
         if (!(pivo > 0.0)) { bad = 1; pivo = 1.0; }
         // Pe is only semidefinite when w' -> 1: keep the factor real (a NaN pivot is a failure)
         const double floor_e = 1.0e-30;
@@ -246,10 +240,10 @@ __device__ __forceinline__ int phase1_adding(
                 const int partner = (int)((jpart >> (PB * r)) & ((1u << PB) - 1u));
                 double pa[n];
                 double g0 = 0.0, g1 = 0.0;
-                const double oth2 = shfl_d(own2, partner, GW);
+                const double oth2 = group_get<GW>(own2, partner, gbase);
 #pragma unroll
                 for (int i = 0; i < n; i++) {
-                    pa[i] = shfl_d(a[i], partner, GW);
+                    pa[i] = group_get<GW>(a[i], partner, gbase);
                     if (i & 1) g1 = fma(a[i], pa[i], g1); else g0 = fma(a[i], pa[i], g0);
                 }
                 const double gam = g0 + g1;
@@ -599,8 +593,10 @@ disort_adding_kernel(const LaunchArgs a)
 
     const int slot = blockIdx.x * warps + warp;
     double *recs = a.scratch + (size_t)slot * a.slot_stride;      // [L][rec]
-    const bool gact = (lane % GW) < n;
-    const int g = gact ? lane % GW : n - 1, task = lane / GW;
+    // layer group of this lane; lanes beyond the last full group shadow its last lane
+    const int task = lane / GW < TASKS ? lane / GW : TASKS - 1;
+    const bool gact = lane < TASKS * GW && (lane % GW) < n;
+    const int g = gact ? lane % GW : n - 1, gbase = task * GW;
     const int nbins_all = a.nbins_dev ? *a.nbins_dev : a.d.nbins;
     double *tsm = work + (size_t)task * AL::task;
     const unsigned long long jpart = add_jacobi_partners<n>(g);
@@ -757,7 +753,7 @@ disort_adding_kernel(const LaunchArgs a)
                 if (!active) lc = ncut - 1;
                 int st = phase1_adding<n>(dtauc, ssalb, pmom, ldp, lc, active, fbeam, umu0, plank,
                                           cmu, csq, cd, cylm, y0, ebeam, pk, tsm,
-                                          recs + (size_t)lc * AL::rec, g, gact, jpart);
+                                          recs + (size_t)lc * AL::rec, g, gact, gbase, jpart);
                 if (__any_sync(FULLMASK, st != 0)) { status = SBD_BIN_EIG_FAIL; break; }
             }
         }

@@ -13,6 +13,15 @@ __device__ __forceinline__ double shfl_d(double v, int src, int width)
     return __shfl_sync(FULLMASK, v, src, width);
 }
 
+// value of lane j of a layer group of GW lanes (phase 1 of the register kernels); a group of 10
+// lanes (NSTR = 20: three groups per warp) names the source lane in the warp, gbase = first lane
+template <int GW>
+__device__ __forceinline__ double group_get(double v, int j, int gbase)
+{
+    if constexpr ((GW & (GW - 1)) == 0) return shfl_d(v, j, GW);
+    else return __shfl_sync(FULLMASK, v, gbase + j);
+}
+
 // ---- asynchronous global -> shared staging (LDGSTS) ------------------------
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
 {

@@ -163,13 +163,7 @@ __device__ __forceinline__ double group_sum(double v, int g, int gbase)
     }
 }
 
-// value of lane j of the layer group
-template <int GW>
-__device__ __forceinline__ double group_get(double v, int j, int gbase)
-{
-    if constexpr ((GW & (GW - 1)) == 0) return shfl_d(v, j, GW);
-    else return __shfl_sync(FULLMASK, v, gbase + j);
-}
+
 
 // Round-robin (tournament) pairing of the one-sided Jacobi sweeps: the partner of
 // lane g in round r, 3 bits per round (4 above n = 8).
