@@ -138,15 +138,17 @@ def test_radiances_match_oracle(solver, nstr, nlyr):
     assert_radiance_close(got, oracle_radiance(w, umu, phi))
 
 
-def test_thermal_radiances_match_oracle(solver):
-    """Thermal IR shape of config C3: NSTR=8, Planck source, no beam (one azimuth mode)."""
-    w = workloads.mls_shortwave(nstr=8, wlinf=4.0, wlsup=12.0, wlinc=0.5)
+@pytest.mark.parametrize("nstr", [8, 20, 32])
+def test_thermal_radiances_match_oracle(solver, nstr):
+    """Thermal IR shape of config C3: Planck source, no beam (one azimuth mode); NSTR=8 as in C3, 20 = SBDART's
+    default for radiance output (three 10-lane layer groups per warp), 32."""
+    w = workloads.mls_shortwave(nstr=nstr, wlinf=4.0, wlsup=12.0, wlinc=0.5 if nstr == 8 else 1.0)
     w["bins"]["fbeam"] = 0.0
     w["bins"]["temis"] = 0.3
     umu = np.cos(np.deg2rad(np.array([180, 160, 140, 120, 100, 80, 60, 40, 20, 0.0])))
     umu = np.sort(umu)
     phi = np.array([0.0])
-    got = solver.disort_batch(w["dtauc"], w["ssalb"], w["pmom"], w["bins"], nstr=8,
+    got = solver.disort_batch(w["dtauc"], w["ssalb"], w["pmom"], w["bins"], nstr=nstr,
                               temper=w["temper"], umu=umu, phi=phi)
     assert_radiance_close(got, oracle_radiance(w, umu, phi))
 
