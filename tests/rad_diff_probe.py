@@ -1,6 +1,6 @@
 """Where do the register and the general kernel disagree on radiances?  Worst bins against the CPU checker."""
 import os, sys
-sys.path.insert(0, "."); sys.path.insert(0, "tests")
+sys.path.insert(0, ".")
 import numpy as np
 import sbdart_b200 as sb
 from sbdart_b200 import workloads
