@@ -448,6 +448,30 @@ extern "C" int sbd_disort_batch_device(sbd_handle *h, const sbd_dims *dims, cons
             a2.scratch = (double *)rs.p;
             le = launch_wide(a2, g2, st);
         }
+    } else if (fast && NU > 0) {
+        // radiance register kernel; bins whose TAUC is not monotone go to the general kernel
+        // launched behind (normally the list stays empty and that launch ends at once)
+        SbdDevBuf &rl = h->scratch_set ? h->redo2 : h->redo;
+        SbdDevBuf &rs = h->scratch_set ? h->redo_scratch2 : h->redo_scratch;
+        if (rl.reserve((size_t)dims->nbins * sizeof(int)) != cudaSuccess) return SBD_ERR_CUDA;
+        a.redo_count = a.work_counter + 1;
+        a.redo_list = (int *)rl.p;
+        le = launch_fast(a, warps, grid, st);
+        if (le != cudaSuccess) return SBD_ERR_CUDA;
+        h->launches += 1;
+        LaunchArgs a2 = a;
+        a2.redo_consume = true;
+        a2.work_counter = a.work_counter + 2;
+        int w2 = generic_pick_warps(N, L, NT, smem_limit);
+        if (w2 == 0) return SBD_ERR_UNSUPPORTED;
+        if (w2 >= 8) w2 = 4;
+        int g2 = 16;
+        if (g2 > (dims->nbins + w2 - 1) / w2) g2 = (dims->nbins + w2 - 1) / w2;
+        a2.slot_stride = generic_slot_doubles(N, L, NU);
+        a2.nslots = g2 * w2;
+        if (rs.reserve(a2.slot_stride * (size_t)a2.nslots * 8) != cudaSuccess) return SBD_ERR_CUDA;
+        a2.scratch = (double *)rs.p;
+        le = launch_generic(a2, w2, g2, st);
     } else {
         le = wide ? launch_wide(a, grid, st)
                   : (fast ? launch_fast(a, warps, grid, st) : launch_generic(a, warps, grid, st));

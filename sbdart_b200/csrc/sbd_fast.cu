@@ -1035,6 +1035,17 @@ disort_fast_kernel(const LaunchArgs a)
         monotone = __shfl_sync(FULLMASK, monotone, 0);
         const bool fastmap = (a.d.ntau == 0) && monotone;
         __syncwarp();
+        // Radiance runs: negative optical depths (legal upstream, taugas.f:7485) make TAUC
+        // non-monotone (disort.f:487 accumulates before CHEKIN clips) and the reference then
+        // integrates the source function to levels INSIDE earlier layers; this kernel's recurrence
+        // has its levels at the layer boundaries, so such bins go to the general kernel
+        if (RAD && !monotone && !status && have && a.redo_list && !a.redo_consume) {
+            if (lane == 0) {
+                const int k = atomicAdd(a.redo_count, 1);
+                a.redo_list[k] = bin;
+            }
+            status = -100;          // parked: no phases, no status write
+        }
         // beam transmission to every layer boundary: scaled depth (EXPBEA, disort.f:2592)
         // and true depth (the direct flux that is reported, disort.f:1998)
         for (int lev = lane; lev <= L; lev += 32) {
@@ -1667,7 +1678,7 @@ disort_fast_kernel(const LaunchArgs a)
         if (RAD) SBD_TICK(3);
       }   // azimuth modes
         cp_async_wait_all();
-        if (lane == 0 && have) a.status[bin] = status;
+        if (lane == 0 && have && status != -100) a.status[bin] = status;
         __syncwarp();
 #ifdef SBD_PHASE_TIMING
         if (SYNC) __syncthreads();

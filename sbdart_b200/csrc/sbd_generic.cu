@@ -845,8 +845,9 @@ disort_generic_kernel(const LaunchArgs a)
         // (CTA barriers with per-warp "active" flags): they then execute the same code
         // at the same time and share its instruction-cache lines -- free-running warps
         // of this 150 KB kernel spend 40 % of their time waiting for instructions.
-        const bool have = bin < (a.nbins_dev ? *a.nbins_dev : a.d.nbins);
+        const bool have = bin < (a.redo_consume ? *a.redo_count : (a.nbins_dev ? *a.nbins_dev : a.d.nbins));
         if (!(SYNC ? __syncthreads_or(have) : (int)have)) break;
+        if (a.redo_consume && have) bin = a.redo_list[bin];      // bins handed over by the radiance register kernel
 
         const int src = !have ? 0 : (a.binmap ? a.binmap[bin] : bin);     // input slot of this bin
         const sbd_bin bp = a.bins[src];

@@ -275,3 +275,19 @@ def test_negative_optical_depths_follow_the_reference(nstr):
     scale = np.max([np.abs(ref[k]).max(axis=1) for k in ("rfldir", "rfldn", "flup")], axis=0)[:, None]
     for k in ("rfldir", "rfldn", "flup", "uavg", "dfdt"):
         assert (np.abs(got[k] - ref[k]) <= 1e-7 * np.abs(ref[k]) + 1e-9 * scale).all(), k
+
+
+@pytest.mark.parametrize("nstr", [8, 20])
+def test_negative_optical_depths_in_radiance_runs(solver, nstr):
+    """The same inputs with user angles: the reference integrates the source function to levels
+    inside earlier layers for such bins; the radiance register kernel (levels at the layer
+    boundaries) hands them to the general kernel on the device.  Every bin must agree with the checker."""
+    w = workloads.retrieval_batch(24, nstr=nstr, nlyr=14, ncols=3, seed=40 + nstr)
+    w["bins"]["phi0"] = 20.0
+    w["dtauc"][5, 6] = -0.02
+    w["dtauc"][17, 2] = -0.3 * w["dtauc"][17, 1]
+    umu = np.array([-1.0, -0.6, -0.1, 0.2, 0.7, 1.0])
+    phi = np.array([0.0, 120.0])
+    got = solver.disort_batch(w["dtauc"], w["ssalb"], w["pmom"], w["bins"], nstr=nstr, umu=umu, phi=phi)
+    ref = oracle_radiance(w, umu, phi)
+    assert_radiance_close(got, ref)

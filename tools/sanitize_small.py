@@ -44,6 +44,9 @@ print("32 radiance bad", int((o["status"] != 0).sum()))
 w = workloads.retrieval_batch(6, nstr=8, nlyr=6, ncols=2, seed=3)
 o = s.disort_batch(w["dtauc"], w["ssalb"], w["pmom"], w["bins"], nstr=8, umu=np.array([-0.5, 0.5]), phi=np.array([0.0, 90.0]))
 print("radiance bad", int((o["status"] != 0).sum()))
+w["dtauc"][2, 3] = -0.01       # radiance bin handed to the general kernel
+o = s.disort_batch(w["dtauc"], w["ssalb"], w["pmom"], w["bins"], nstr=8, umu=np.array([-0.5, 0.5]), phi=np.array([0.0, 90.0]))
+print("radiance with a handed-over bin bad", int((o["status"] != 0).sum()))
 # a negative optical depth: TAUC is not monotone, the adding kernel hands the bin over
 for nstr in (16, 32):
     w = workloads.retrieval_batch(8, nstr=nstr, nlyr=12, ncols=2, seed=11)
