@@ -135,7 +135,9 @@ int sbd_synchronize(sbd_handle *h);
  * the source function for every level.  The device-pointer call writes zeros at
  * the unselected levels of uu; the host-buffer call copies back the selected
  * levels only and leaves the rest of the caller's uu untouched (the copy of all
- * L+1 levels would dominate the call).  Fluxes are not affected. */
+ * L+1 levels would dominate the call).  Fluxes are not affected.  With ACCUR > 0
+ * the convergence test of the azimuth series (disort.f:802-823) sees the selected
+ * levels only (SBDART runs ACCUR = 0: every mode is summed). */
 int sbd_set_radiance_levels(sbd_handle *h, const int32_t *levels, int32_t n);
 
 /* Layout of uu in the following batched calls while a level selection is active:

@@ -291,3 +291,27 @@ def test_negative_optical_depths_in_radiance_runs(solver, nstr):
     got = solver.disort_batch(w["dtauc"], w["ssalb"], w["pmom"], w["bins"], nstr=nstr, umu=umu, phi=phi)
     ref = oracle_radiance(w, umu, phi)
     assert_radiance_close(got, ref)
+
+
+@pytest.mark.parametrize("kernel", ["register", "general"])
+def test_azimuth_series_stops_at_accur(monkeypatch, kernel):
+    """ACCUR > 0 (disort.f:821-823): the azimuth series ends after two consecutive modes whose largest
+    term-to-sum ratio is below ACCUR.  (SBDART itself runs ACCUR = 0; other DISORT hosts do not.)"""
+    if kernel == "general":
+        monkeypatch.setenv("SBD_FORCE_GENERIC", "1")
+    w = workloads.retrieval_batch(12, nstr=16, nlyr=10, ncols=3, seed=77)
+    w["bins"]["phi0"] = 10.0
+    w["bins"]["accur"] = 1.0e-2
+    # some isotropic illumination: without it the downward intensities at the top are 0 in every
+    # mode, RATIO(0, 0) = 1 (disort.f:6219) and the series never stops early
+    w["bins"]["fisot"] = 0.05
+    umu = np.array([-0.9, -0.4, -0.1, 0.15, 0.5, 0.95])
+    phi = np.array([0.0, 70.0, 180.0])
+    s = sb.Solver(0)
+    got = s.disort_batch(w["dtauc"], w["ssalb"], w["pmom"], w["bins"], nstr=16, umu=umu, phi=phi)
+    s.close()
+    full = oracle_radiance(w, umu, phi, accur=0.0)
+    cut = oracle_radiance(w, umu, phi, accur=1.0e-2)
+    # the test is only meaningful if the early exit changes something
+    assert any(np.abs(a["uu"] - b["uu"]).max() > 1e-6 * np.abs(a["uu"]).max() for a, b in zip(full, cut))
+    assert_radiance_close(got, cut)
