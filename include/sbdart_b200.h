@@ -334,9 +334,8 @@ void disort_(int *nlyr, double *dtauc, double *ssalb, int *corint, int *nmom,
  * n = nstr/2, nmodes = 1 (fluxes) or nstr (all azimuth modes).  HOST arrays, copied to the
  * device; they stay set until the next call (nsurf = 0 clears them).  A bin selects surface s
  * with bins[b].albedo = SBD_SURFACE(s).  Flux runs at the layer boundaries with NSTR
- * 4/8/16/20/24/32 and all radiance runs support it.  A flux bin that combines a BRDF surface
- * with a negative optical depth reports SBD_BIN_BAD_INPUT.  Launches given
- * their own stream must have finished before the call.
+ * 4/8/16/20/24/32 and all radiance runs support it.  Launches given their own stream must
+ * have finished before the call.
  */
 #define SBD_SURFACE(s) (-(double)((s) + 1))
 int sbd_set_surfaces(sbd_handle *h, int32_t nsurf, int32_t nstr, int32_t nmodes, int32_t numu,

@@ -427,7 +427,19 @@ extern "C" int sbd_disort_batch_device(sbd_handle *h, const sbd_dims *dims, cons
         LaunchArgs a2 = a;
         a2.redo_consume = true;
         a2.work_counter = a.work_counter + 2;
-        if (fast_supported(N)) {
+        if (brdf) {
+            // (the elimination kernels are Lambertian: BRDF bins go to the general kernel)
+            int w2 = generic_pick_warps(N, L, NT, smem_limit);
+            if (w2 == 0) return SBD_ERR_UNSUPPORTED;
+            if (w2 >= 8) w2 = 4;
+            int g2 = 16;
+            if (g2 > (dims->nbins + w2 - 1) / w2) g2 = (dims->nbins + w2 - 1) / w2;
+            a2.slot_stride = generic_slot_doubles(N, L, NU);
+            a2.nslots = g2 * w2;
+            if (rs.reserve(a2.slot_stride * (size_t)a2.nslots * 8) != cudaSuccess) return SBD_ERR_CUDA;
+            a2.scratch = (double *)rs.p;
+            le = launch_generic(a2, w2, g2, st);
+        } else if (fast_supported(N)) {
             int w2 = fast_warps();
             if (fast_smem_bytes(N, L, NT, w2, 0, 0) > smem_limit) w2 = 4;
             if (fast_smem_bytes(N, L, NT, w2, 0, 0) > smem_limit) return SBD_ERR_UNSUPPORTED;

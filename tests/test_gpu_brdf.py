@@ -135,3 +135,32 @@ def test_whole_runs_with_brdf_surfaces(nml):
     s.close()
     nval, nexact, worst = compare_records(got, ref, rel=1.01e-4)      # one unit of the last digit
     assert nexact >= 0.98 * nval, (nval, nexact, worst)
+
+
+@pytest.mark.parametrize("nstr", [8, 20])
+def test_brdf_flux_bin_with_a_negative_optical_depth(nstr):
+    """A BRDF flux bin whose TAUC is not monotone: the adding kernel hands it over, and because the
+    elimination kernels are Lambertian it is the general kernel that solves it."""
+    isalb, sc = MODELS[0]
+    rng = np.random.default_rng(1000 + nstr)
+    L = 9
+    model = brdf.SurfaceModel(isalb, sc)
+    state = brdf.ocean_state(tables(), model, 0.55) if model.spectral else None
+    _set_oracle(model, state)
+    mu, _ = sb.quadrature(nstr // 2)
+    dt, ss, pm = _atm(nstr, L, rng)
+    dt[4] = -0.2 * dt[3]
+    kw = dict(fbeam=1.0, umu0=0.6, fisot=0.0)
+    ref = oracle.disort(dt, ss, pm, nstr=nstr, lamber=False, **kw)
+    assert ref["status"] == 0
+    tab = brdf.surface_tables(model, state, mu, 0.6, True, 1)
+    s = sb.Solver(0)
+    s.set_surfaces(nstr, tab["bdr"][None], tab["bem"][None])
+    bins = sb.make_bins(1, albedo=sb.surface_albedo(0), **kw)
+    got = s.disort_batch(dt[None], ss[None], pm[None], bins, nstr=nstr)
+    s.set_surfaces()
+    s.close()
+    assert got["status"][0] == 0
+    sc_ = max(np.abs(ref[k]).max() for k in ("rfldir", "rfldn", "flup"))
+    for k in ("rfldir", "rfldn", "flup", "uavg"):
+        assert np.abs(got[k][0] - ref[k]).max() <= 1e-8 * sc_, k
