@@ -1613,6 +1613,14 @@ disort_fast_kernel(const LaunchArgs a)
                                     v *= 1.0 + delm0;
                                     if (fbeam > 0.0) v += umu0 * fbeam / kPiRef * rm[0] * ebeam[ncut];
                                     if (m0) v += a.sf_emu[(size_t)surf * NU + iu] * bplank;
+                                } else if (ADD && m0) {
+                                    // Lambertian surface (disort.f:4747-4778), from the downward
+                                    // intensities at the bottom interface (not from the flux of level
+                                    // L: with empty layers that level is evaluated in an earlier layer)
+                                    const double *db = levs + (size_t)ncut * 2 * n;
+                                    double dn = 0.0;
+                                    for (int k = 0; k < n; k++) dn = fma(cmu[k] * csq[k], db[k], dn);
+                                    v = 2.0 * albedo * dn + umu0 * fbeam / kPiRef * albedo * ebeam[ncut] + (1.0 - albedo) * bplank;
                                 } else if (m0) v = bnd_up;
                             }
                             uI[iu] = v;

@@ -77,3 +77,37 @@ def test_hard_cases_match_the_checker(nstr):
             assert err <= tol, (name, k, err)
     s.close()
     print("worst", worst)
+
+
+@pytest.mark.parametrize("nstr", [8, 16, 20])
+def test_hard_cases_radiances(nstr):
+    """The same atmospheres with user angles (radiance register kernel: adding sweeps, layer solutions
+    recovered from the interface intensities -- the recovery multiplies by k, which is ~1e-7 for the
+    dithered conservative layers)."""
+    umu = np.array([-1.0, -0.5, -0.1, 0.1, 0.6, 1.0])
+    phi = np.array([0.0, 90.0])
+    s = sb.Solver(0)
+    worst = 0.0
+    for name, dt, ss, pm, kw in _cases(nstr):
+        if "mixed thin" in name:
+            continue          # the checker itself is only good to 1e-3 there (see above)
+        L = len(dt)
+        kw = dict(kw)
+        plank = kw.pop("plank", False)
+        temper = np.linspace(210.0, 300.0, L + 1)
+        okw = dict(kw)
+        if plank:
+            okw.update(plank=True, temper=temper, wvnmlo=600.0, wvnmhi=700.0, btemp=310.0, ttemp=100.0, temis=1.0)
+        ref = oracle.disort(dt, ss, pm, nstr=nstr, umu=umu, phi=phi, phi0=30.0, onlyfl=False, **okw)
+        bins = sb.make_bins(1, plank=int(plank), phi0=30.0, **{k: v for k, v in okw.items() if k not in ("plank", "temper")})
+        got = s.disort_batch(dt[None], ss[None], pm[None], bins, nstr=nstr, temper=temper[None], umu=umu, phi=phi)
+        assert got["status"][0] == ref["status"], (name, got["status"][0], ref["status"])
+        if ref["status"] != 0:
+            continue
+        scale = max(np.abs(ref["uu"]).max(), np.abs(ref["flup"]).max() / np.pi, np.abs(ref["rfldn"]).max() / np.pi)
+        err = np.abs(got["uu"][0] - ref["uu"]).max() / scale
+        worst = max(worst, err)
+        tol = 1e-5 if "albedo 1" in name else 1e-6
+        assert err <= tol, (name, err)
+    s.close()
+    print("worst", worst)
