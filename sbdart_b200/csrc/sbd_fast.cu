@@ -809,25 +809,27 @@ __device__ __forceinline__ void user_terms_fast(
 //   I(near boundary) = T I(far boundary) + S,   T = exp(-dtau' / |umu|),
 // with S the analytic integral of the layer's source terms; same L'Hospital limits as the
 // reference (|1 +- umu k| < 1e-4, |1 + umu/umu0| < 1e-4).  up: umu > 0, the near boundary is
-// the layer top; else the layer bottom.
+// the layer top; else the layer bottom.  The reference's L'Hospital form of the beam term
+// (disort.f:4560-4566: ZBEAM dtau/umu0 exp(-utau'/umu0), the exponential taken at the USER LEVEL
+// for every layer of the path) is not a recurrence term: rdenom == 0 leaves it out of S and
+// returns its coefficient ZBEAM dtau/umu0 in `bl` -- the caller keeps the running sum.
 template <int n>
 __device__ __forceinline__ double layer_source(const double *gu /* GU row of this angle */, const double *kk,
                                                const double *ek, double umu, double rmu /* 1 / umu */,
                                                double rdenom /* 1 / (1 + umu/umu0), 0: L'Hospital */,
                                                double t0, double t1,
                                                double eb0, double eb1 /* beam transmission at t0, t1 */,
-                                               bool beam, double umu0, bool therm, double &T)
+                                               bool beam, double umu0, bool therm, double &T, double &bl)
 {
     constexpr int N = 2 * n;
     const double dtau = t1 - t0;
     const bool up = umu > 0.0;
     T = exp(-dtau * fabs(rmu));
     double s = 0.0;
+    bl = 0.0;
     if (beam) {
-        double expn;
-        if (rdenom == 0.0) expn = (dtau / umu0) * (up ? eb0 : eb1);
-        else expn = up ? (eb0 - T * eb1) * rdenom : (eb1 - T * eb0) * rdenom;
-        s = gu[N] * expn;
+        if (rdenom == 0.0) bl = gu[N] * (dtau / umu0);
+        else s = gu[N] * (up ? (eb0 - T * eb1) * rdenom : (eb1 - T * eb0) * rdenom);
     }
     double sp = 0.0;      // second accumulator: two modes in flight (the reciprocals overlap)
 #pragma unroll 2
@@ -1636,11 +1638,11 @@ disort_fast_kernel(const LaunchArgs a)
                     for (int iu = lane; iu < NU; iu += 32) {
                         const double umu = a.umu[iu];
                         const double rmu = fast_rcp(umu), denom = 1. + umu / umu0;
-                        double T;
+                        double T, bl;
                         const double S = layer_source<n>(uGU + iu * FL::ecols, urec + FL::off_kk, urec + FL::off_ek,
                                                          umu, rmu, fabs(denom) < 0.0001 ? 0.0 : fast_rcp(denom),
                                                          taucpr[lc], taucpr[lc + 1], ebeam[lc], ebeam[lc + 1],
-                                                         fbeam > 0.0, umu0, therm, T);
+                                                         fbeam > 0.0, umu0, therm, T, bl);
                         if (umu > 0.0) {
                             const double below = T * uI[iu];
                             const double v = below + S;
@@ -1652,8 +1654,10 @@ disort_fast_kernel(const LaunchArgs a)
                             // top layer seen from level 0 -- kept so that thin cap layers agree
                             emit(lc, iu, (lc == 0 && taucpr[1] - taucpr[0] < 1.e-6) ? below : v);
                         } else {                          // kept for the top-down pass
+                            // (viewing against the beam, |1 + umu/umu0| < 1e-4: the beam coefficient
+                            // instead of the transmission, which the pass then recomputes)
                             dscr[((size_t)lc * 2) * NU + iu] = S;
-                            dscr[((size_t)lc * 2 + 1) * NU + iu] = T;
+                            dscr[((size_t)lc * 2 + 1) * NU + iu] = (fbeam > 0.0 && fabs(denom) < 0.0001) ? bl : T;
                         }
                     }
                 }
@@ -1669,11 +1673,24 @@ disort_fast_kernel(const LaunchArgs a)
                     if (a.umu[iu] > 0.0) continue;
                     double v = m0 ? bp.fisot + tplank : 0.0;
                     emit(0, iu, v);
+                    // viewing against the beam: the reference's L'Hospital beam term of the layers above
+                    // a level is exp(-tau'_level / umu0) x the sum of their coefficients (disort.f:4560-4566)
+                    const bool lh = fbeam > 0.0 && fabs(1. + a.umu[iu] / umu0) < 0.0001;
+                    const double armu = fabs(1.0 / a.umu[iu]);
+                    double accb = 0.0;
                     for (int lc = 0; lc < ncut; lc++) {
-                        const double above = dscr[((size_t)lc * 2 + 1) * NU + iu] * v;
+                        const double w1 = dscr[((size_t)lc * 2 + 1) * NU + iu];
+                        const double T = lh ? exp(-(taucpr[lc + 1] - taucpr[lc]) * armu) : w1;
+                        const double above = T * v;
                         v = above + dscr[((size_t)lc * 2) * NU + iu];
                         // (same rule: a layer thinner than 1e-6 directly above the level, disort.f:4635-4641)
-                        emit(lc + 1, iu, (taucpr[lc + 1] - taucpr[lc] < 1.e-6) ? above : v);
+                        const bool thin = taucpr[lc + 1] - taucpr[lc] < 1.e-6;
+                        double out = thin ? above : v;
+                        if (lh) {
+                            out += ebeam[lc + 1] * (thin ? accb : accb + w1);
+                            accb += w1;
+                        }
+                        emit(lc + 1, iu, out);
                     }
                 }
                 if (mazim > 0) {

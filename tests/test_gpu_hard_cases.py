@@ -111,3 +111,54 @@ def test_hard_cases_radiances(nstr):
         assert err <= tol, (name, err)
     s.close()
     print("worst", worst)
+
+
+@pytest.mark.parametrize("umu", [[1.0], [-1.0], [-1.0, 1.0], [0.3], [-0.99999, 0.5]])
+def test_special_user_angle_sets(umu):
+    """DISORT sums the m = 0 mode only when every user direction is vertical or the sun is overhead
+    (disort.f:577-586); one and two user angles are the special cases of that rule."""
+    from sbdart_b200 import workloads
+    umu = np.array(umu)
+    phi = np.array([25.0])
+    w = workloads.retrieval_batch(6, nstr=8, nlyr=7, ncols=2, seed=5)
+    w["bins"]["phi0"] = 0.0
+    w["bins"]["umu0"][3] = 1.0 - 1e-6          # sun overhead: one mode
+    s = sb.Solver(0)
+    got = s.disort_batch(w["dtauc"], w["ssalb"], w["pmom"], w["bins"], nstr=8, umu=umu, phi=phi)
+    s.close()
+    b = w["bins"]
+    for i in range(len(b)):
+        r = oracle.disort(w["dtauc"][i], w["ssalb"][i], w["pmom"][i], nstr=8, umu=umu, phi=phi, fbeam=b["fbeam"][i],
+                          umu0=b["umu0"][i], phi0=0.0, fisot=b["fisot"][i], albedo=b["albedo"][i], onlyfl=False)
+        assert got["status"][i] == r["status"]
+        if r["status"] == 0:
+            scale = max(np.abs(r["uu"]).max(), np.abs(r["flup"]).max() / np.pi)
+            assert np.abs(got["uu"][i] - r["uu"]).max() <= 1e-7 * scale, (i, umu)
+
+
+@pytest.mark.parametrize("kernel", ["register", "general"])
+def test_viewing_against_the_beam(monkeypatch, kernel):
+    """|1 + umu/umu0| < 1e-4 but not zero: the reference's L'Hospital form of the beam term takes its
+    exponential at the user level for every layer of the path (disort.f:4560-4566), which is not what an
+    exact integration gives at that distance from the limit (relative difference ~ dtau x 1e-4 / umu) --
+    parity means the reference's form."""
+    from sbdart_b200 import workloads
+    if kernel == "general":
+        monkeypatch.setenv("SBD_FORCE_GENERIC", "1")
+    w = workloads.retrieval_batch(6, nstr=8, nlyr=9, ncols=2, seed=9)
+    w["bins"]["umu0"] = 0.6
+    w["bins"]["phi0"] = 0.0
+    w["dtauc"] *= 3.0
+    umu = np.array([-0.6 * (1.0 + 8.0e-5), -0.6 * (1.0 - 5.0e-5), 0.4])        # increasing, as CHEKIN demands
+    phi = np.array([180.0, 0.0])
+    s = sb.Solver(0)
+    got = s.disort_batch(w["dtauc"], w["ssalb"], w["pmom"], w["bins"], nstr=8, umu=umu, phi=phi)
+    s.close()
+    b = w["bins"]
+    for i in range(len(b)):
+        r = oracle.disort(w["dtauc"][i], w["ssalb"][i], w["pmom"][i], nstr=8, umu=umu, phi=phi, fbeam=b["fbeam"][i],
+                          umu0=0.6, phi0=0.0, fisot=b["fisot"][i], albedo=b["albedo"][i], onlyfl=False)
+        assert got["status"][i] == r["status"]
+        if r["status"] == 0:
+            scale = max(np.abs(r["uu"]).max(), np.abs(r["flup"]).max() / np.pi)
+            assert np.abs(got["uu"][i] - r["uu"]).max() <= 1e-7 * scale, i
