@@ -162,3 +162,32 @@ def test_viewing_against_the_beam(monkeypatch, kernel):
         if r["status"] == 0:
             scale = max(np.abs(r["uu"]).max(), np.abs(r["flup"]).max() / np.pi)
             assert np.abs(got["uu"][i] - r["uu"]).max() <= 1e-7 * scale, i
+
+
+def test_radiances_with_negligible_layers_and_many_angles():
+    """Layers thinner than 1e-6 in scaled depth (the reference drops their source integral for the level
+    they touch, disort.f:4635-4641) between ordinary ones; 36 user angles x 5 azimuths (more angles
+    than lanes)."""
+    nstr = 8
+    dt = np.array([1e-8, 0.5, 1e-7, 0.3, 1e-9, 0.7, 2e-7])
+    ss = np.array([0.9, 0.95, 0.5, 0.8, 1.0, 0.6, 0.99])
+    pm = _hg([0.1, 0.8, 0.3, 0.7, 0.2, 0.6, 0.4], nstr + 2)
+    umu = np.concatenate([-np.linspace(1.0, 0.02, 18), np.linspace(0.02, 1.0, 18)])
+    phi = np.array([0.0, 45.0, 90.0, 135.0, 180.0])
+    kw = dict(fbeam=1.0, umu0=0.55, albedo=0.35, fisot=0.02)
+    ref = oracle.disort(dt, ss, pm, nstr=nstr, umu=umu, phi=phi, phi0=15.0, onlyfl=False, **kw)
+    assert ref["status"] == 0
+    for env in (None, "SBD_FORCE_GENERIC"):
+        import os
+        if env:
+            os.environ[env] = "1"
+        try:
+            s = sb.Solver(0)
+            got = s.disort_batch(dt[None], ss[None], pm[None], sb.make_bins(1, phi0=15.0, **kw), nstr=nstr, umu=umu, phi=phi)
+            s.close()
+        finally:
+            if env:
+                del os.environ[env]
+        assert got["status"][0] == 0
+        scale = np.abs(ref["uu"]).max()
+        assert np.abs(got["uu"][0] - ref["uu"]).max() <= 1e-7 * scale, env
