@@ -312,7 +312,10 @@ extern "C" int sbd_disort_batch_device(sbd_handle *h, const sbd_dims *dims, cons
     // elimination register kernel: NSTR 4/8/16; radiances at the layer boundaries (the mode SBDART uses)
     // (radiance runs in the adding form: NSTR up to 32, BRDF surfaces too)
     const bool fast_rad = NU > 0 && dims->ntau == 0 && fast_rad_supported(N) && (!brdf || !getenv("SBD_RAD_ELIM"));
-    const bool fast = !adding && (NU > 0 ? fast_rad : (!brdf && fast_supported(N))) && !getenv("SBD_FORCE_GENERIC");
+    // (a radiance run with very many user angles may not fit the register kernel's shared memory:
+    // the general kernel takes it)
+    const bool fast_fits = fast_smem_bytes(N, L, NT, 4, NU, dims->nphi) <= smem_limit;
+    const bool fast = !adding && (NU > 0 ? fast_rad && fast_fits : (!brdf && fast_supported(N))) && !getenv("SBD_FORCE_GENERIC");
     // CTA-per-bin register kernel: NSTR 20/24/32, fluxes
     const bool wide = !adding && !fast && !brdf && wide_supported(N) && NU == 0 && !getenv("SBD_FORCE_GENERIC") &&
                       wide_smem_bytes(N, L, NT) <= smem_limit;

@@ -191,3 +191,22 @@ def test_radiances_with_negligible_layers_and_many_angles():
         assert got["status"][0] == 0
         scale = np.abs(ref["uu"]).max()
         assert np.abs(got["uu"][0] - ref["uu"]).max() <= 1e-7 * scale, env
+
+
+def test_more_user_angles_than_the_register_kernel_holds():
+    """200 user angles x 3 azimuths at NSTR 32: the register kernel's work area does not fit the SM's
+    shared memory, the general kernel takes the run (no error)."""
+    nstr = 32
+    rng = np.random.default_rng(2)
+    L = 4
+    dt = rng.uniform(0.05, 1.0, L); ss = rng.uniform(0.5, 1.0, L)
+    pm = _hg(rng.uniform(0.0, 0.8, L), nstr + 2)
+    umu = np.concatenate([-np.linspace(1.0, 0.01, 100), np.linspace(0.01, 1.0, 100)])
+    phi = np.array([0.0, 90.0, 180.0])
+    kw = dict(fbeam=1.0, umu0=0.5, albedo=0.2)
+    ref = oracle.disort(dt, ss, pm, nstr=nstr, umu=umu, phi=phi, phi0=0.0, onlyfl=False, **kw)
+    s = sb.Solver(0)
+    got = s.disort_batch(dt[None], ss[None], pm[None], sb.make_bins(1, **kw), nstr=nstr, umu=umu, phi=phi)
+    s.close()
+    assert got["status"][0] == 0 and ref["status"] == 0
+    assert np.abs(got["uu"][0] - ref["uu"]).max() <= 1e-7 * np.abs(ref["uu"]).max()
