@@ -210,3 +210,28 @@ def test_more_user_angles_than_the_register_kernel_holds():
     s.close()
     assert got["status"][0] == 0 and ref["status"] == 0
     assert np.abs(got["uu"][0] - ref["uu"]).max() <= 1e-7 * np.abs(ref["uu"]).max()
+
+
+@pytest.mark.parametrize("nstr,rad", [(16, False), (32, False), (8, True), (20, True)])
+def test_maximum_layer_count(nstr, rad):
+    """SBD_MAX_NLYR = 128 layers: the CTA shapes shrink to what the shared memory holds."""
+    from sbdart_b200 import workloads
+    w = workloads.retrieval_batch(6, nstr=nstr, nlyr=128, ncols=2, seed=3)
+    w["dtauc"] *= 0.3
+    umu = np.array([-0.7, -0.2, 0.3, 0.9]) if rad else None
+    phi = np.array([0.0, 120.0]) if rad else None
+    s = sb.Solver(0)
+    got = s.disort_batch(w["dtauc"], w["ssalb"], w["pmom"], w["bins"], nstr=nstr, umu=umu, phi=phi)
+    s.close()
+    b = w["bins"]
+    for i in range(len(b)):
+        r = oracle.disort(w["dtauc"][i], w["ssalb"][i], w["pmom"][i], nstr=nstr, umu=umu, phi=phi, fbeam=b["fbeam"][i],
+                          umu0=b["umu0"][i], phi0=b["phi0"][i], fisot=b["fisot"][i], albedo=b["albedo"][i], onlyfl=not rad)
+        assert got["status"][i] == r["status"]
+        if r["status"] != 0:
+            continue
+        scale = max(np.abs(r[k]).max() for k in ("rfldir", "rfldn", "flup"))
+        for k in ("rfldir", "rfldn", "flup"):
+            assert np.abs(got[k][i] - r[k]).max() <= 1e-7 * scale, (i, k)
+        if rad:
+            assert np.abs(got["uu"][i] - r["uu"]).max() <= 1e-7 * max(np.abs(r["uu"]).max(), scale / np.pi), i
