@@ -235,3 +235,50 @@ def test_maximum_layer_count(nstr, rad):
             assert np.abs(got[k][i] - r[k]).max() <= 1e-7 * scale, (i, k)
         if rad:
             assert np.abs(got["uu"][i] - r["uu"]).max() <= 1e-7 * max(np.abs(r["uu"]).max(), scale / np.pi), i
+
+
+@pytest.mark.parametrize("nstr,rad", [(16, False), (12, False), (32, False), (8, True), (20, True)])
+def test_rejected_inputs_are_reported_per_bin(nstr, rad):
+    """CHEKIN's input checks (disort.f:4920-5155) end the reference program; here the offending bin
+    reports a status and the other bins of the batch are solved as usual."""
+    from sbdart_b200 import workloads
+    w = workloads.retrieval_batch(12, nstr=nstr, nlyr=6, ncols=2, seed=13)
+    good = {k: w[k].copy() for k in ("dtauc", "ssalb", "pmom")}
+    good_bins = w["bins"].copy()
+    b = w["bins"]
+    w["ssalb"][1, 2] = 1.0 + 1e-9
+    w["ssalb"][2, 0] = -0.1
+    w["dtauc"][3, 4] = np.nan
+    w["pmom"][4, 1, 3] = 1.5
+    b["fbeam"][5] = -1.0
+    b["umu0"][6] = 1.5
+    b["albedo"][7] = 1.2
+    b["fisot"][8] = -0.5
+    b["umu0"][9] = 0.0
+    umu = np.array([-0.5, 0.4]) if rad else None
+    phi = np.array([0.0]) if rad else None
+    s = sb.Solver(0)
+    got = s.disort_batch(w["dtauc"], w["ssalb"], w["pmom"], b, nstr=nstr, umu=umu, phi=phi)
+    ref = s.disort_batch(good["dtauc"], good["ssalb"], good["pmom"], good_bins, nstr=nstr, umu=umu, phi=phi)
+    s.close()
+    bad = np.arange(1, 10)
+    assert (got["status"][bad] == sb.BIN_BAD_INPUT).all(), got["status"]
+    ok = np.array([0, 10, 11])
+    assert (got["status"][ok] == 0).all()
+    for k in ("rfldir", "rfldn", "flup") + (("uu",) if rad else ()):
+        assert np.array_equal(got[k][ok], ref[k][ok]), k      # placement independent, bit for bit
+
+
+def test_argument_errors():
+    from sbdart_b200 import workloads
+    w = workloads.retrieval_batch(2, nstr=8, nlyr=4, ncols=1, seed=1)
+    s = sb.Solver(0)
+    with pytest.raises(sb.SbdError):
+        s.disort_batch(w["dtauc"], w["ssalb"], w["pmom"], w["bins"], nstr=7)           # odd
+    with pytest.raises(sb.SbdError):
+        s.disort_batch(w["dtauc"], w["ssalb"], w["pmom"], w["bins"], nstr=42)          # > SBD_MAX_NSTR
+    with pytest.raises(sb.SbdError):
+        s.disort_batch(w["dtauc"], w["ssalb"], w["pmom"], w["bins"], nstr=8, umu=np.array([0.5, -0.5]), phi=np.array([0.0]))   # not increasing
+    with pytest.raises(sb.SbdError):
+        s.disort_batch(w["dtauc"], w["ssalb"], w["pmom"], w["bins"], nstr=8, umu=np.array([0.0, 0.5]), phi=np.array([0.0]))    # horizontal
+    s.close()
