@@ -60,8 +60,10 @@ def test_flux_with_brdf_surface(isalb, sc, nstr):
 
 
 @pytest.mark.parametrize("isalb,sc", MODELS)
-@pytest.mark.parametrize("nstr", [8, 20])
-def test_radiances_with_brdf_surface(isalb, sc, nstr):
+@pytest.mark.parametrize("nstr,variant", [(8, "beam"), (20, "beam"), (8, "thermal"), (16, "thick")])
+def test_radiances_with_brdf_surface(isalb, sc, nstr, variant):
+    """beam: sunlit; thermal: surface emission EMU B(Ts) and an emitting top boundary besides the beam;
+    thick: an absorbing layer deep enough for the layer truncation (the surface is then not seen)."""
     rng = np.random.default_rng(isalb * 10 + nstr)
     L = 6
     model = brdf.SurfaceModel(isalb, sc)
@@ -73,13 +75,21 @@ def test_radiances_with_brdf_surface(isalb, sc, nstr):
     dt, ss, pm = _atm(nstr, L, rng)
     umu0 = 0.6
     kw = dict(fbeam=1.0, umu0=umu0, phi0=20.0)
-    ref = oracle.disort(dt, ss, pm, nstr=nstr, lamber=False, onlyfl=False, umu=umu, phi=phi, **kw)
+    okw = dict(kw)
+    temper = np.linspace(230.0, 290.0, L + 1)
+    if variant == "thermal":
+        kw.update(wvnmlo=2400.0, wvnmhi=2600.0, btemp=305.0, ttemp=250.0, temis=0.4, fisot=0.01)
+        okw = dict(kw, plank=True, temper=temper)
+    if variant == "thick":
+        dt[3] = 40.0; ss[3] = 0.3
+    ref = oracle.disort(dt, ss, pm, nstr=nstr, lamber=False, onlyfl=False, umu=umu, phi=phi, **okw)
     assert ref["status"] == 0
     tab = brdf.surface_tables(model, state, mu, umu0, True, nstr, umu=umu)
     s = sb.Solver(0)
     s.set_surfaces(nstr, tab["bdr"][None], tab["bem"][None], tab["rmu"][None], tab["emu"][None])
-    bins = sb.make_bins(1, albedo=sb.surface_albedo(0), **kw)
-    got = s.disort_batch(dt[None], ss[None], pm[None], bins, nstr=nstr, umu=umu, phi=phi)
+    bins = sb.make_bins(1, albedo=sb.surface_albedo(0), plank=int(variant == "thermal"), **kw)
+    got = s.disort_batch(dt[None], ss[None], pm[None], bins, nstr=nstr, umu=umu, phi=phi,
+                         temper=temper[None] if variant == "thermal" else None)
     s.set_surfaces()
     s.close()
     assert got["status"][0] == 0

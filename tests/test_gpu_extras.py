@@ -120,6 +120,9 @@ CORINT_RUNS = [
     # deep cloud (layer truncation below the cloud in the visible), ice cloud on top
     "&INPUT idatm=1, nstr=8, tcloud=60,3, zcloud=1,9, nre=8,-30, wlinf=1.5, wlsup=1.7, wlinc=.1, sza=20, iout=23,"
     " uzen=10,150,165, phi=0,90, corint=t /",
+    # SBDART's default stream count for radiance output (NSTR=20: register kernel, 10-lane layer groups)
+    "&INPUT idatm=2, nstr=20, tcloud=1, zcloud=3, wlinf=.55, wlsup=.65, wlinc=.1, sza=40, iout=20,"
+    " uzen=0,45,95,150, phi=0,60,180, corint=t /",
 ]
 
 
