@@ -315,3 +315,30 @@ def test_azimuth_series_stops_at_accur(monkeypatch, kernel):
     # the test is only meaningful if the early exit changes something
     assert any(np.abs(a["uu"] - b["uu"]).max() > 1e-6 * np.abs(a["uu"]).max() for a, b in zip(full, cut))
     assert_radiance_close(got, cut)
+
+
+@pytest.mark.parametrize("nstr", [8, 20])
+def test_radiances_at_user_optical_depths(solver, nstr):
+    """USRTAU together with USRANG (general kernel): intensities at levels inside layers, on a layer
+    boundary, at the top and at the bottom."""
+    w = workloads.retrieval_batch(8, nstr=nstr, nlyr=7, ncols=2, seed=31 + nstr)
+    w["bins"]["phi0"] = 40.0
+    B, L = w["dtauc"].shape
+    tot = w["dtauc"].sum(axis=1)
+    frac = np.array([0.0, 0.13, 0.5, 0.77, 1.0])
+    utau = frac[None, :] * tot[:, None]
+    utau[:, 2] = np.cumsum(w["dtauc"], axis=1)[:, 3]
+    utau = np.sort(utau, axis=1)
+    umu = np.array([-1.0, -0.3, 0.2, 0.8])
+    phi = np.array([0.0, 100.0])
+    got = solver.disort_batch(w["dtauc"], w["ssalb"], w["pmom"], w["bins"], nstr=nstr, utau=utau, umu=umu, phi=phi)
+    b = w["bins"]
+    for i in range(B):
+        r = oracle.disort(w["dtauc"][i], w["ssalb"][i], w["pmom"][i], nstr=nstr, utau=utau[i], umu=umu, phi=phi,
+                          fbeam=b["fbeam"][i], umu0=b["umu0"][i], phi0=40.0, fisot=b["fisot"][i], albedo=b["albedo"][i],
+                          onlyfl=False)
+        assert got["status"][i] == r["status"] == 0
+        scale = max(np.abs(r["uu"]).max(), np.abs(r["flup"]).max() / np.pi)
+        assert np.abs(got["uu"][i] - r["uu"]).max() <= 1e-7 * scale, i
+        for k in ("rfldir", "rfldn", "flup"):
+            assert np.abs(got[k][i] - r[k]).max() <= 1e-7 * np.pi * scale, (i, k)
