@@ -174,3 +174,22 @@ def test_corint_through_the_fortran_entry():
     uu = np.transpose(got["uu"][:2, :3, :2], (2, 1, 0))          # UU(iu, lu, j) -> [j][lu][iu]
     np.testing.assert_allclose(uu, want["uu"], rtol=1e-6, atol=1e-9 * np.abs(want["uu"]).max())
     np.testing.assert_allclose(got["flup"][:3], want["flup"], rtol=1e-8)
+
+
+@pytest.mark.parametrize("nl", [
+    # nstr left to its default: 20 streams for radiance output (drt.f:241-247)
+    "&INPUT idatm=2, tcloud=3, zcloud=2, wlinf=.5, wlsup=.8, wlinc=.05, sza=35, iout=5, uzen=0,30,60,85,100,150, phi=0,90,180 /",
+    "&INPUT idatm=4, wlinf=9, wlsup=12, wlinc=.5, sza=95, iout=6, uzen=5,50,95,140,175, phi=0 /",
+    "&INPUT idatm=2, nstr=24, iaer=1, vis=15, wlinf=.45, wlsup=.55, wlinc=.05, sza=60, iout=21, uzen=20,70,110,160, phi=0,45 /",
+])
+def test_whole_radiance_runs_at_the_default_stream_count(nl):
+    """iout = 5 / 6 / 21 radiance records through the device path (K2 + radiance register kernel at
+    NSTR 20 / 24) against the front end driven by the CPU checker."""
+    s = sb.Solver(0)
+    run = Sbdart(nl)
+    assert run.p["nstr"] in (20, 24)
+    want = Sbdart(nl).run(solve_oracle)
+    got = Sbdart(nl).run_device(s)
+    nval, nexact, worst = compare_records(got, want, rel=1.2e-4)
+    assert nval > 20 and worst <= 1.2e-4
+    s.close()
